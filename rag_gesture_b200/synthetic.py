@@ -1,0 +1,178 @@
+"""Deterministic synthetic weights and inputs (there is no dataset or checkpoint on the boxes).
+
+Everything here is a pure function of integer seeds drawn from torch CPU generators, so the
+golden-fixture script (run next to the reference), the CPU oracle tests and the GPU parity tests
+all see bit-identical tensors without shipping 564 MB of weights.
+
+Weight scales (see DESIGN.md "synthetic weights"): the reference zero-initialises `out`,
+`ffn.linear2` and every `StylizationBlock.out_layers.2` (diffusion_transformer.py:79,415;
+stylization_block.py:26), which makes a fresh model the zero function, so those are drawn
+non-zero.  Cross-attention `value` projections are drawn small so that |y| < 1/32 on the
+query-masked rows {10,20,30}: there the reference adds -1e6 in fp32 (efficient_attention.py:98),
+i.e. rounds y to a 1/16 grid, and its output is a discontinuous function of y unless the row
+collapses to exactly -1e6 (SURVEY 7 "-1e6 additive masks").  `normal_scale=True` lifts that
+restriction for the single-step row-group test.
+"""
+import math
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import config as C
+
+
+def denoiser_param_shapes():
+    """state-dict keys and shapes of ReGestureTransformer minus the VAEs, in the
+    reference's own registration order."""
+    D, E, F, TD = C.LATENT_DIM, C.TIME_EMBED_DIM, C.FF_SIZE, C.TEXT_DIM
+    s = OrderedDict()
+    s["sequence_embedding.pe"] = (C.N_CHUNKS, 1, D)
+    s["global_positional_embedding.pe"] = (C.N_TOKENS, 1, D)
+    s["text_pre_proj.weight"] = (D, TD)
+    s["text_pre_proj.bias"] = (D,)
+    s["audio_pre_proj.weight"] = (D, TD)
+    s["audio_pre_proj.bias"] = (D,)
+    s["speaker_embedding.weight"] = (C.NUM_SPEAKERS, D)
+    s["joint_embed.weight"] = (D, D)
+    s["joint_embed.bias"] = (D,)
+    s["time_embed.0.weight"] = (E, D)
+    s["time_embed.0.bias"] = (E,)
+    s["time_embed.2.weight"] = (E, E)
+    s["time_embed.2.bias"] = (E,)
+
+    def styl(p):
+        s[p + ".emb_layers.1.weight"] = (2 * D, E)
+        s[p + ".emb_layers.1.bias"] = (2 * D,)
+        s[p + ".norm.weight"] = (D,)
+        s[p + ".norm.bias"] = (D,)
+        s[p + ".out_layers.2.weight"] = (D, D)
+        s[p + ".out_layers.2.bias"] = (D,)
+
+    for l in range(C.NUM_LAYERS):
+        p = f"temporal_decoder_blocks.{l}"
+        s[p + ".sa_block.norm.weight"] = (D,)
+        s[p + ".sa_block.norm.bias"] = (D,)
+        for n in ("query", "key", "value"):
+            s[f"{p}.sa_block.{n}.weight"] = (D, D)
+            s[f"{p}.sa_block.{n}.bias"] = (D,)
+        styl(p + ".sa_block.proj_out")
+        for c in C.CONDS:
+            q = f"{p}.ca_blocks.{c}"
+            for n in ("norm", "text_norm"):
+                s[f"{q}.{n}.weight"] = (D,)
+                s[f"{q}.{n}.bias"] = (D,)
+            for n in ("query", "key", "value"):
+                s[f"{q}.{n}.weight"] = (D, D)
+                s[f"{q}.{n}.bias"] = (D,)
+            styl(q + ".proj_out")
+        s[p + ".ca_mix.weight"] = (D, 3 * D)
+        s[p + ".ca_mix.bias"] = (D,)
+        s[p + ".ffn.linear1.weight"] = (F, D)
+        s[p + ".ffn.linear1.bias"] = (F,)
+        s[p + ".ffn.linear2.weight"] = (D, F)
+        s[p + ".ffn.linear2.bias"] = (D,)
+        styl(p + ".ffn.proj_out")
+    s["out.weight"] = (D, D)
+    s["out.bias"] = (D,)
+    return s
+
+
+def sine_position_table(max_len, d_model):
+    """PositionEmbeddingSine1D buffer (detr_utils.py:33-39), shape [max_len, 1, d_model]."""
+    pe = torch.zeros(max_len, d_model)
+    position = torch.arange(0, max_len, dtype=torch.float).unsqueeze(1)
+    div_term = torch.exp(torch.arange(0, d_model, 2).float() * (-np.log(10000.0) / d_model))
+    pe[:, 0::2] = torch.sin(position * div_term)
+    pe[:, 1::2] = torch.cos(position * div_term)
+    return pe.unsqueeze(0).transpose(0, 1).contiguous()
+
+
+def synthetic_state_dict(seed=0, normal_scale=False):
+    """Key-ordered deterministic weights for the denoiser (fp32, CPU)."""
+    g = torch.Generator().manual_seed(int(seed))
+    sd = OrderedDict()
+    for k, shp in denoiser_param_shapes().items():
+        if k == "sequence_embedding.pe":
+            sd[k] = sine_position_table(shp[0], shp[2])
+            continue
+        r = torch.randn(shp, generator=g, dtype=torch.float32)
+        if k == "global_positional_embedding.pe":
+            v = 0.05 * r
+        elif k == "speaker_embedding.weight":
+            v = r / C.LATENT_DIM                      # diffusion_transformer.py:540-541
+        elif k.endswith("norm.weight"):
+            v = 1.0 + 0.1 * r
+        elif k.endswith("norm.bias"):
+            v = 0.1 * r
+        elif k.endswith(".bias"):
+            v = 0.02 * r
+            if ".ca_blocks." in k and k.endswith("value.bias") and not normal_scale:
+                v = (0.0005 if ".xf_spk." in k else 0.002) * r
+        else:                                         # Linear weight [out, in]
+            gain = 1.0
+            if k.endswith("emb_layers.1.weight") or k.endswith("out_layers.2.weight"):
+                gain = 0.5
+            if ".ca_blocks." in k and k.endswith("value.weight") and not normal_scale:
+                # xf_spk repeats one embedding row 150 times, so y == that value row (no
+                # averaging over tokens): it needs the smaller gain to stay below 1/32
+                gain = 0.003 if ".xf_spk." in k else 0.02
+            v = r * (gain / math.sqrt(shp[-1]))
+        sd[k] = v.contiguous()
+    return sd
+
+
+def synthetic_conditions(n_clips, seed=1234, first_clip=0):
+    """Per-clip condition features of the len150@15fps shape: BERT-like
+    `word` [B,150,768], wav2vec-like `audio` [B,499,768], `speaker_ids` [B,150] int64.
+    Clip i depends only on (seed, first_clip+i), so shards of a batch agree with the whole."""
+    word = torch.empty(n_clips, C.N_TEXT, C.TEXT_DIM)
+    audio = torch.empty(n_clips, C.N_AUDIO, C.TEXT_DIM)
+    spk = torch.empty(n_clips, C.N_SPK, dtype=torch.int64)
+    for i in range(n_clips):
+        g = torch.Generator().manual_seed(int(seed) * 1_000_003 + first_clip + i)
+        word[i] = torch.randn(C.N_TEXT, C.TEXT_DIM, generator=g)
+        audio[i] = torch.randn(C.N_AUDIO, C.TEXT_DIM, generator=g)
+        spk[i] = int(torch.randint(0, C.NUM_SPEAKERS, (1,), generator=g))
+    return dict(word=word, audio=audio, speaker_ids=spk)
+
+
+def synthetic_latents(n_clips, seed=99, first_clip=0, scale=1.0):
+    """[B,43,512] latents with exact zeros on the separator rows {10,21,32} (what
+    GestureRepEncoder.encode emits, diffusion_transformer.py:241-250)."""
+    x = torch.empty(n_clips, C.N_TOKENS, C.LATENT_DIM)
+    for i in range(n_clips):
+        g = torch.Generator().manual_seed(int(seed) * 1_000_003 + first_clip + i)
+        x[i] = scale * torch.randn(C.N_TOKENS, C.LATENT_DIM, generator=g)
+    x[:, C.SEPARATOR_ROWS] = 0
+    return x
+
+
+def motion_mask(n_clips):
+    """src/motion mask after encode: 1 everywhere, 0 on separators {10,21,32}."""
+    m = torch.ones(n_clips, C.N_TOKENS)
+    m[:, C.SEPARATOR_ROWS] = 0
+    return m
+
+
+def query_masks(n_clips):
+    """cross-attention query masks: 0 on rows {10,20,30} (diffusion_architecture.py:152-166)."""
+    m = torch.ones(n_clips, C.N_TOKENS)
+    m[:, C.QUERY_MASK_ZERO_ROWS] = 0
+    return {c: m.clone() for c in C.CONDS}
+
+
+class NoiseTape:
+    """Pre-drawn Gaussian draws handed out in call order.
+
+    The reference draws from the global torch generator in a fixed order.  CPU and
+    CUDA generators produce different streams, so parity tests draw the tape once on the CPU and
+    replay it on both sides."""
+
+    def __init__(self, seed):
+        self.g = torch.Generator().manual_seed(int(seed))
+        self.n = 0
+
+    def randn(self, shape, device="cpu"):
+        self.n += 1
+        return torch.randn(tuple(shape), generator=self.g, dtype=torch.float32).to(device)
