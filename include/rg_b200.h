@@ -1,0 +1,179 @@
+/* rg_b200.h -- C ABI of the B200-native guided-DDIM + exemplar-retrieval hot path of RAG-Gesture.
+ *
+ * The reference (m-hamza-mughal/RAG-Gesture) is pure Python and has no FFI: its seam is the mmcv
+ * registry plus Python call signatures.  This library sits UNDER re-registered
+ * Python classes of the same names (rag_gesture_b200/mogen_api.py); every entry point below
+ * names the reference function(s) it replaces.  Conventions:
+ *   - plain C: raw pointers + sizes; all tensors are dense row-major fp32 unless stated otherwise;
+ *   - every `dev` pointer is device memory on the CURRENT cuda device, borrowed for the call;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); calls enqueue
+ *     work and return without synchronising unless stated otherwise;
+ *   - return value 0 = ok, otherwise rg_last_error() describes the failure (thread-local);
+ *   - a handle is re-entrant from one thread at a time; distinct handles are independent.
+ * There is no CPU fallback anywhere: without a CUDA device every compute entry point fails.
+ */
+#ifndef RG_B200_H
+#define RG_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
+#endif
+
+#define RG_ABI_VERSION 1
+
+typedef struct rg_model* rg_handle;
+
+/* Hyper-parameters: configs/raggesture_beatx/basegesture_len150_beat.py:32-42.
+ * latent_dim must be 512 and num_heads 16 (head dim 32 == warp width is baked into the kernels). */
+typedef struct rg_config {
+    int32_t latent_dim;      /* 512  */
+    int32_t num_heads;       /* 16   */
+    int32_t ffn_dim;         /* 1024 */
+    int32_t time_embed_dim;  /* 2048 */
+    int32_t num_layers;      /* 8    */
+    int32_t n_tokens;        /* 43 = 4 * n_chunks + 3 */
+    int32_t n_chunks;        /* 10   */
+    int32_t text_dim;        /* 768  (text_pre_proj / audio_pre_proj input width) */
+    int32_t num_speakers;    /* 25   */
+    int32_t precision;       /* RG_PREC_*: arithmetic of the dense contractions */
+} rg_config;
+
+enum { RG_PREC_FP32 = 0,      /* fp32 FMA GEMMs: the exact tier (rel-L2 <= 1e-3 vs reference)      */
+       RG_PREC_BF16 = 1,      /* tcgen05 bf16 x bf16 -> fp32 TMEM accumulate (rel-L2 <= 2e-2)       */
+       RG_PREC_BF16X3 = 2 };  /* tcgen05, operands split hi+lo bf16, 3 products: fp32-class accuracy */
+
+const char* rg_last_error(void);
+int rg_abi_version(void);
+/* number of CUDA kernels launched by this library in the calling process so far */
+int64_t rg_launch_count(void);
+
+/* Build a denoiser from the reference state dict of ReGestureTransformer (minus the VAEs):
+ * names[i] is the state-dict key without the leading "model." (SURVEY.md 8b lists them),
+ * ptrs[i] points to numels[i] fp32 values on the HOST.  The library keeps its own packed device
+ * copies (fused QKV, LayerNorm affine folded into the consuming Linear, ...).
+ * Replaces: DiffusionTransformer.__init__ + load_checkpoint (diffusion_transformer.py:335-425). */
+int rg_create(const rg_config* cfg, int n_tensors, const char* const* names,
+              const float* const* ptrs, const int64_t* numels, rg_handle* out);
+int rg_destroy(rg_handle h);
+
+/* Install the respaced sampling schedule and build the timestep table (K7):
+ * timestep_map[s] = original timestep of step s (SpacedDiffusion.timestep_map,
+ * gaussian_diffusion.py:1723-1738); coef[s*8 + i], fp32 values the reference uses at step s:
+ *   0 sqrt_recip_alphas_cumprod  1 sqrt_recipm1_alphas_cumprod     (:437-438, cast at :1623)
+ *   2 sqrt(alphas_cumprod_prev)  3 sqrt(1 - alphas_cumprod_prev)   (:994-995)
+ *   4 sqrt(alphas_cumprod_next)  5 sqrt(1 - alphas_cumprod_next)   (:1035-1036)
+ *   6 sqrt_alphas_cumprod        7 sqrt_one_minus_alphas_cumprod   (:473-476)
+ * The table holds, for every step, every layer and each of its 5 StylizationBlocks, the
+ * (scale | shift) vector emb_layers(SiLU(time_embed(timestep_embedding(t)))) -- computed once
+ * instead of per step per clip (diffusion_transformer.py:27-46,404-408,643; stylization_block.py:35-37).
+ * Synchronises the stream. */
+int rg_set_schedule(rg_handle h, int n_steps, const int32_t* timestep_map, const float* coef,
+                    void* stream);
+
+/* xf_text = text_pre_proj(word), xf_audio = audio_pre_proj(audio), xf_spk = speaker_embedding[ids]
+ * Replaces: encode_text / encode_audio / encode_spks (diffusion_transformer.py:544-606) as called
+ * from ReGestureTransformer.get_precompute_condition (raggesture.py:978-987).
+ * word [B,n_text,text_dim], audio [B,n_audio,text_dim], spk_ids int64 [B,n_spk] (all dev);
+ * outputs [B,n_*,512] (dev). */
+int rg_encode_conditions(rg_handle h, const float* word, const float* audio,
+                         const int64_t* spk_ids, int B, int n_text, int n_audio, int n_spk,
+                         float* xf_text, float* xf_audio, float* xf_spk, void* stream);
+
+/* Cross-attention key/value state of B clips for all layers and the 3 conditions (K6):
+ * state[b][layer][cond][head][32][32] = softmax_tokens(key(text_norm(xf)))^T value(text_norm(xf)).
+ * The reference recomputes this on every denoiser call (efficient_attention.py:74,78-89); it
+ * depends on neither x nor t.  rg_state_floats_per_clip() gives the per-clip size. */
+int64_t rg_state_floats_per_clip(rg_handle h);
+int rg_precompute_clip_state(rg_handle h, const float* xf_text, const float* xf_audio,
+                             const float* xf_spk, int n_text, int n_audio, int n_spk, int B,
+                             float* state, void* stream);
+
+/* One denoiser evaluation for B clips that share one timestep:  x0 = model(x, t).
+ * Replaces: DiffusionTransformer.forward + ReGestureTransformer.forward_test, single conditional
+ * branch (diffusion_transformer.py:620-668, raggesture.py:1041-1086) incl. all 8 DecoderLayers.
+ * step_idx >= 0 selects a row of the schedule's timestep table; step_idx < 0 evaluates at the
+ * original-scale timestep `tau` (table row computed on the fly).
+ * x,x0_out [B,T,512]; src_mask [B,T] (motion_mask); query_mask [3,B,T] or NULL; state from
+ * rg_precompute_clip_state.  x0_out may alias x. */
+int rg_denoise(rg_handle h, const float* x, int B, int step_idx, int tau, const float* src_mask,
+               const float* query_mask, const float* state, float* x0_out, void* stream);
+
+/* DDIM update (eta = 0), bit-exact fp32 op order of the reference:
+ *   eps = (c0*x - x0)/c1 ; out = x0*ca + cb*eps ; direction -1: (ca,cb) = coef 2,3 (ddim_sample,
+ *   gaussian_diffusion.py:983-1001); direction +1: coef 4,5 (ddim_reverse_sample :1032-1038).
+ * n = number of floats (multiple of 4).  out may alias x or x0. */
+int rg_ddim_update(rg_handle h, const float* x, const float* x0, int step_idx, int direction,
+                   float* out, int64_t n, void* stream);
+
+/* in_seq outpainting blend of ddim_sample (gaussian_diffusion.py:934-947): rows of in_seq with any
+ * non-zero entry replace the same rows of x by q_sample(in_seq, t, noise).  rows = B*T rows of 512.
+ * out may alias x. */
+int rg_blend_in_seq(rg_handle h, const float* x, const float* in_seq, const float* noise,
+                    int step_idx, float* out, int64_t rows, void* stream);
+
+/* `iters` closed-form gradient steps of the insertion guidance (gaussian_diffusion.py:1351-1378):
+ * x <- x - lr * grad_x mse(x * m, in_seq), m = any(in_seq != 0, -1); numel = B*T*512 of the batch the
+ * reference would have run (mse_loss 'mean').  In place. */
+int rg_guidance_steps(rg_handle h, float* x, const float* in_seq, int64_t rows, int iters,
+                      float lr, int64_t numel, void* stream);
+
+/* ---- op-level entry points (used by the per-module Python mirrors and the unit parity tests) -- */
+
+/* y = epilogue(x W^T + b).  x [M,K] (row stride ldx), W [N,K], b [N] or NULL, residual [M,N] or
+ * NULL (epilogue RG_OP_RESIDUAL), out [M,N].  Replaces nn.Linear on the path. */
+enum { RG_OP_NONE = 0, RG_OP_RESIDUAL = 1, RG_OP_GELU = 2, RG_OP_SILU = 4 };
+int rg_op_linear(const float* x, int ldx, const float* W, const float* b, const float* residual,
+                 float* out, int M, int N, int K, int epilogue, void* stream);
+/* LayerNorm over 512-wide rows, eps 1e-5; gamma/beta may be NULL (no affine). */
+int rg_op_layernorm(const float* x, const float* gamma, const float* beta, float* out, int M,
+                    void* stream);
+int rg_op_silu(const float* x, float* out, int64_t n, void* stream);
+/* StylizationBlock row part (stylization_block.py:38-39 up to the SiLU):
+ * out = silu(LN(y)*(1+scale)+shift); ss [n_clips or 1, 1024] = emb_layers output. */
+int rg_op_stylization_rows(const float* y, const float* gamma, const float* beta, const float* ss,
+                           int ss_per_clip, int rows_per_clip, float* out, int M, void* stream);
+/* EfficientSelfAttention core (efficient_attention.py:30-39) from fused qkv [B*T,1536]:
+ * with_styl=1: out = silu(LN(Y)*(1+scale)+shift) (input of proj_out.out_layers);
+ * with_styl=0: out = x_res + Y (time_embed_dim=None variant, :41-42). */
+int rg_op_self_attention(const float* qkv, const float* src_mask, const float* gamma,
+                         const float* beta, const float* ss, int ss_per_clip, const float* x_res,
+                         float* out, int B, int T, int with_styl, void* stream);
+/* EfficientCrossAttention core for ONE condition (efficient_attention.py:72-101 minus the
+ * projections): q [B*T,512] pre-softmax queries, state [B,16,32,32], query_mask [B,T] or NULL. */
+int rg_op_cross_attention(const float* q, const float* state, const float* query_mask,
+                          const float* gamma, const float* beta, const float* ss, int ss_per_clip,
+                          float* out, int B, int T, void* stream);
+/* K/V -> state for ONE condition/layer: kv [B*N,1024] = [key | value] projections. */
+int rg_op_kv_state(const float* kv, int n_tokens, int B, float* state, void* stream);
+
+/* ---- exemplar retrieval (K10/K11) -------------------------------------------------------- */
+
+/* Token-aligned text-similarity scores of one query against a padded exemplar database:
+ *   score[i] = (1/m) * sum_{t<m} <query[t,:], db[i,t,:]>,  m = min(tq, db_len[i])
+ * == mean(diag(Q D_i^T)) of sort_sidx_by_textsimilarity (rag/utils.py:86-132), un-normalised.
+ * db [n, max_len, dim] zero-padded, db_len int32 [n]; subset int32 [n_sub] (indices to score) or
+ * NULL for all; scores fp32 [n_sub or n]. */
+int rg_text_similarity(const float* db, const int32_t* db_len, int64_t n, int max_len, int dim,
+                       const float* query, int tq, const int32_t* subset, int64_t n_sub,
+                       float* scores, void* stream);
+
+/* Exact fp32 top-k by dot product of q queries against a database shard (flat embeddings):
+ * out_idx int64 [q,k] (global index = local + idx_base), out_score fp32 [q,k], ordered by
+ * (score desc, index asc) -- the order of Python's stable sorted(..., reverse=True). */
+int rg_knn_topk(const float* db, int64_t n, int dim, const float* queries, int q, int k,
+                int64_t idx_base, int64_t* out_idx, float* out_score, void* stream);
+/* Merge `parts` per-shard candidate lists [parts,q,k] (as all-gathered) into the global top-k. */
+int rg_knn_merge(const int64_t* idx_parts, const float* score_parts, int parts, int q, int k,
+                 int64_t* out_idx, float* out_score, void* stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* RG_B200_H */

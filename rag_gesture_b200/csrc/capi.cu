@@ -1,0 +1,570 @@
+// C ABI of the hot path (include/rg_b200.h): handle management, weight packing, the timestep
+// table (K7), the per-clip cross-attention state (K6) and the per-step denoiser orchestration.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/rg_b200.h"
+#include "rg_common.cuh"
+#include "rg_internal.h"
+
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static long long g_launches = 0;
+
+int rg_fail(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return 1;
+}
+void rg_count_launch(int n) { g_launches += n; }
+
+#define CU(expr)                                                                              \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess)                                                                \
+            return rg_fail("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+    } while (0)
+#define LAUNCH(expr)      \
+    do {                  \
+        CU(expr);         \
+        ++g_launches;     \
+    } while (0)
+
+struct Layer {
+    float *Wqkv, *bqkv;                   // [1536,512] sa q|k|v with sa_block.norm folded in
+    float *sa_g, *sa_b, *sa_Wo, *sa_bo;   // sa_block.proj_out.{norm, out_layers.2}
+    float *Wcaq, *bcaq;                   // [1536,512] 3 x ca query with ca norm folded in
+    float *ca_g, *ca_b;                   // [3,512] ca proj_out.norm
+    float *ca_Wo, *ca_bo;                 // [3,512,512], [3,512] ca proj_out.out_layers.2
+    float *Wmix, *bmix;                   // [512,1536]
+    float *W1, *b1, *W2, *b2;             // ffn
+    float *ffn_g, *ffn_b, *ffn_Wo, *ffn_bo;
+};
+
+struct rg_model {
+    rg_config cfg;
+    int device;
+    std::vector<void*> allocs;
+    std::vector<Layer> layers;
+    float *W_joint, *b_joint, *W_out, *b_out, *pos;
+    float *W_text, *b_text, *W_audio, *b_audio, *spk_table;
+    float *W_t0, *b_t0, *W_t2, *b_t2;     // time_embed
+    float *We_all, *be_all;               // [L*5*1024, E] all emb_layers.1, block order sa,text,audio,spk,ffn
+    float* Wkv_all[3];                    // [L*1024, 512] per cond: key|value with text_norm folded in
+    float* bkv_all[3];
+    // schedule
+    int n_steps;
+    std::vector<int> timestep_map;
+    std::vector<float> coef;
+    float* table;                         // [n_steps, L, 5, 1024]
+    float* tau_row;                       // [L*5*1024] scratch for an off-table timestep
+    int tau_cached;
+    // workspace
+    long long ws_rows;
+    float *h, *a, *big, *o3, *g, *y;
+    long long kv_rows;
+    float *kv_ln, *kv_buf;
+    long long tt_rows;
+    float *tt_emb, *tt_t1, *tt_e;
+};
+
+static int dalloc(rg_model* m, void** p, size_t bytes) {
+    CU(cudaMalloc(p, bytes ? bytes : 4));
+    m->allocs.push_back(*p);
+    return 0;
+}
+static void dfree_one(rg_model* m, void* p) {
+    if (!p) return;
+    for (size_t i = 0; i < m->allocs.size(); ++i)
+        if (m->allocs[i] == p) { m->allocs.erase(m->allocs.begin() + i); break; }
+    cudaFree(p);
+}
+
+struct TensorMap {
+    std::map<std::string, std::pair<const float*, long long>> t;
+    const float* get(const std::string& k, long long numel) const {
+        auto it = t.find(k);
+        if (it == t.end()) { rg_fail("missing tensor '%s'", k.c_str()); return nullptr; }
+        if (it->second.second != numel) {
+            rg_fail("tensor '%s': expected %lld elements, got %lld", k.c_str(), numel, it->second.second);
+            return nullptr;
+        }
+        return it->second.first;
+    }
+};
+
+// upload `numel` host floats of tensor `key` to dst (device)
+static int up_to(const TensorMap& tm, const std::string& key, long long numel, float* dst) {
+    const float* src = tm.get(key, numel);
+    if (!src) return 1;
+    CU(cudaMemcpy(dst, src, (size_t)numel * sizeof(float), cudaMemcpyHostToDevice));
+    return 0;
+}
+static int up_new(rg_model* m, const TensorMap& tm, const std::string& key, long long numel, float** dst) {
+    if (dalloc(m, (void**)dst, (size_t)numel * sizeof(float))) return 1;
+    return up_to(tm, key, numel, *dst);
+}
+
+static RgGemm mk_gemm(const float* A, int lda, const float* W, const float* bias, float* C, int ldc,
+                      int M, int N, int K, int epi) {
+    RgGemm g;
+    memset(&g, 0, sizeof(g));
+    g.A = A; g.W = W; g.bias = bias; g.C = C;
+    g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldw = K; g.ldc = ldc; g.groups = 1; g.epi = epi;
+    return g;
+}
+
+extern "C" const char* rg_last_error(void) { return g_err; }
+extern "C" int rg_abi_version(void) { return RG_ABI_VERSION; }
+extern "C" int64_t rg_launch_count(void) { return g_launches; }
+
+extern "C" int rg_destroy(rg_handle h) {
+    if (!h) return 0;
+    for (void* p : h->allocs) cudaFree(p);
+    delete h;
+    return 0;
+}
+
+extern "C" int rg_create(const rg_config* cfg, int n_tensors, const char* const* names,
+                         const float* const* ptrs, const int64_t* numels, rg_handle* out) {
+    if (!cfg || !out) return rg_fail("rg_create: null argument");
+    if (cfg->latent_dim != RG_D || cfg->num_heads != RG_H)
+        return rg_fail("rg_create: kernels are built for latent_dim=%d, num_heads=%d (got %d, %d)",
+                       RG_D, RG_H, cfg->latent_dim, cfg->num_heads);
+    if (cfg->n_tokens > RG_MAX_T || cfg->n_tokens != 4 * cfg->n_chunks + 3)
+        return rg_fail("rg_create: n_tokens=%d must be 4*n_chunks+3 and <= %d", cfg->n_tokens, RG_MAX_T);
+    if (cfg->ffn_dim % 128 || cfg->time_embed_dim % 128 || cfg->text_dim % 16)
+        return rg_fail("rg_create: ffn_dim/time_embed_dim must be multiples of 128, text_dim of 16");
+    if (cfg->precision != RG_PREC_FP32)
+        return rg_fail("rg_create: precision %d not available in this build", cfg->precision);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return rg_fail("rg_create: no CUDA device (this library has no CPU path)");
+    TensorMap tm;
+    for (int i = 0; i < n_tensors; ++i) tm.t[names[i]] = {ptrs[i], (long long)numels[i]};
+
+    rg_model* m = new rg_model();
+    memset(&m->cfg, 0, sizeof(m->cfg));
+    m->cfg = *cfg;
+    cudaGetDevice(&m->device);
+    m->n_steps = 0; m->table = nullptr; m->tau_row = nullptr; m->tau_cached = -1;
+    m->ws_rows = 0; m->h = m->a = m->big = m->o3 = m->g = m->y = nullptr;
+    m->kv_rows = 0; m->kv_ln = m->kv_buf = nullptr;
+    m->tt_rows = 0; m->tt_emb = m->tt_t1 = m->tt_e = nullptr;
+    const int D = RG_D, E = cfg->time_embed_dim, F = cfg->ffn_dim, L = cfg->num_layers, T = cfg->n_tokens;
+    const long long DD = (long long)D * D;
+    cudaStream_t st = 0;
+    int rc = 1;
+    float *tmpW = nullptr, *tmpb = nullptr, *tmpg = nullptr, *tmpbe = nullptr, *seq = nullptr, *glob = nullptr;
+#define TRY(x) do { if (x) goto fail; } while (0)
+#define TRYCU(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { rg_fail("%s -> %s", #x, cudaGetErrorString(_e)); goto fail; } } while (0)
+    TRY(up_new(m, tm, "joint_embed.weight", DD, &m->W_joint));
+    TRY(up_new(m, tm, "joint_embed.bias", D, &m->b_joint));
+    TRY(up_new(m, tm, "out.weight", DD, &m->W_out));
+    TRY(up_new(m, tm, "out.bias", D, &m->b_out));
+    TRY(up_new(m, tm, "text_pre_proj.weight", (long long)D * cfg->text_dim, &m->W_text));
+    TRY(up_new(m, tm, "text_pre_proj.bias", D, &m->b_text));
+    TRY(up_new(m, tm, "audio_pre_proj.weight", (long long)D * cfg->text_dim, &m->W_audio));
+    TRY(up_new(m, tm, "audio_pre_proj.bias", D, &m->b_audio));
+    TRY(up_new(m, tm, "speaker_embedding.weight", (long long)cfg->num_speakers * D, &m->spk_table));
+    TRY(up_new(m, tm, "time_embed.0.weight", (long long)E * D, &m->W_t0));
+    TRY(up_new(m, tm, "time_embed.0.bias", E, &m->b_t0));
+    TRY(up_new(m, tm, "time_embed.2.weight", (long long)E * E, &m->W_t2));
+    TRY(up_new(m, tm, "time_embed.2.bias", E, &m->b_t2));
+    // positional table: per-part sine + learned global
+    TRY(up_new(m, tm, "sequence_embedding.pe", (long long)cfg->n_chunks * D, &seq));
+    TRY(up_new(m, tm, "global_positional_embedding.pe", (long long)T * D, &glob));
+    TRY(dalloc(m, (void**)&m->pos, (size_t)T * D * sizeof(float)));
+    TRYCU(rg_launch_pos_table(seq, glob, m->pos, T, cfg->n_chunks, st));
+    ++g_launches;
+
+    TRY(dalloc(m, (void**)&m->We_all, (size_t)L * 5 * 2 * D * E * sizeof(float)));
+    TRY(dalloc(m, (void**)&m->be_all, (size_t)L * 5 * 2 * D * sizeof(float)));
+    for (int c = 0; c < 3; ++c) {
+        TRY(dalloc(m, (void**)&m->Wkv_all[c], (size_t)L * 2 * DD * sizeof(float)));
+        TRY(dalloc(m, (void**)&m->bkv_all[c], (size_t)L * 2 * D * sizeof(float)));
+    }
+    // scratch for folding
+    TRY(dalloc(m, (void**)&tmpW, (size_t)3 * DD * sizeof(float)));
+    TRY(dalloc(m, (void**)&tmpb, (size_t)3 * D * sizeof(float)));
+    TRY(dalloc(m, (void**)&tmpg, (size_t)D * sizeof(float)));
+    TRY(dalloc(m, (void**)&tmpbe, (size_t)D * sizeof(float)));
+
+    m->layers.resize(L);
+    for (int l = 0; l < L; ++l) {
+        Layer& ly = m->layers[l];
+        const std::string p = "temporal_decoder_blocks." + std::to_string(l);
+        const char* conds[3] = {"xf_text", "xf_audio", "xf_spk"};
+        // self-attention q|k|v, LayerNorm folded
+        const char* qkv[3] = {"query", "key", "value"};
+        for (int i = 0; i < 3; ++i) {
+            TRY(up_to(tm, p + ".sa_block." + qkv[i] + ".weight", DD, tmpW + i * DD));
+            TRY(up_to(tm, p + ".sa_block." + qkv[i] + ".bias", D, tmpb + i * D));
+        }
+        TRY(up_to(tm, p + ".sa_block.norm.weight", D, tmpg));
+        TRY(up_to(tm, p + ".sa_block.norm.bias", D, tmpbe));
+        TRY(dalloc(m, (void**)&ly.Wqkv, (size_t)3 * DD * sizeof(float)));
+        TRY(dalloc(m, (void**)&ly.bqkv, (size_t)3 * D * sizeof(float)));
+        TRYCU(rg_launch_fold_ln(tmpW, tmpb, tmpg, tmpbe, ly.Wqkv, ly.bqkv, 3 * D, D, st));
+        ++g_launches;
+        auto styl = [&](const std::string& q, int blk, float** gmm, float** bta, float* Wo, float* bo) -> int {
+            if (up_to(tm, q + ".emb_layers.1.weight", (long long)2 * D * E, m->We_all + ((long long)l * 5 + blk) * 2 * D * E)) return 1;
+            if (up_to(tm, q + ".emb_layers.1.bias", 2 * D, m->be_all + ((long long)l * 5 + blk) * 2 * D)) return 1;
+            if (up_to(tm, q + ".norm.weight", D, *gmm)) return 1;
+            if (up_to(tm, q + ".norm.bias", D, *bta)) return 1;
+            if (up_to(tm, q + ".out_layers.2.weight", DD, Wo)) return 1;
+            if (up_to(tm, q + ".out_layers.2.bias", D, bo)) return 1;
+            return 0;
+        };
+        TRY(dalloc(m, (void**)&ly.sa_g, D * sizeof(float)));
+        TRY(dalloc(m, (void**)&ly.sa_b, D * sizeof(float)));
+        TRY(dalloc(m, (void**)&ly.sa_Wo, DD * sizeof(float)));
+        TRY(dalloc(m, (void**)&ly.sa_bo, D * sizeof(float)));
+        TRY(styl(p + ".sa_block.proj_out", 0, &ly.sa_g, &ly.sa_b, ly.sa_Wo, ly.sa_bo));
+        // cross-attention
+        TRY(dalloc(m, (void**)&ly.Wcaq, (size_t)3 * DD * sizeof(float)));
+        TRY(dalloc(m, (void**)&ly.bcaq, (size_t)3 * D * sizeof(float)));
+        TRY(dalloc(m, (void**)&ly.ca_g, (size_t)3 * D * sizeof(float)));
+        TRY(dalloc(m, (void**)&ly.ca_b, (size_t)3 * D * sizeof(float)));
+        TRY(dalloc(m, (void**)&ly.ca_Wo, (size_t)3 * DD * sizeof(float)));
+        TRY(dalloc(m, (void**)&ly.ca_bo, (size_t)3 * D * sizeof(float)));
+        for (int c = 0; c < 3; ++c) {
+            const std::string q = p + ".ca_blocks." + conds[c];
+            TRY(up_to(tm, q + ".query.weight", DD, tmpW));
+            TRY(up_to(tm, q + ".query.bias", D, tmpb));
+            TRY(up_to(tm, q + ".norm.weight", D, tmpg));
+            TRY(up_to(tm, q + ".norm.bias", D, tmpbe));
+            TRYCU(rg_launch_fold_ln(tmpW, tmpb, tmpg, tmpbe, ly.Wcaq + c * DD, ly.bcaq + c * D, D, D, st));
+            ++g_launches;
+            TRYCU(cudaStreamSynchronize(st));
+            TRY(up_to(tm, q + ".key.weight", DD, tmpW));
+            TRY(up_to(tm, q + ".key.bias", D, tmpb));
+            TRY(up_to(tm, q + ".value.weight", DD, tmpW + DD));
+            TRY(up_to(tm, q + ".value.bias", D, tmpb + D));
+            TRY(up_to(tm, q + ".text_norm.weight", D, tmpg));
+            TRY(up_to(tm, q + ".text_norm.bias", D, tmpbe));
+            TRYCU(rg_launch_fold_ln(tmpW, tmpb, tmpg, tmpbe, m->Wkv_all[c] + (long long)l * 2 * DD,
+                                    m->bkv_all[c] + (long long)l * 2 * D, 2 * D, D, st));
+            ++g_launches;
+            TRYCU(cudaStreamSynchronize(st));
+            float* gq = ly.ca_g + c * D; float* bq = ly.ca_b + c * D;
+            TRY(styl(q + ".proj_out", 1 + c, &gq, &bq, ly.ca_Wo + c * DD, ly.ca_bo + c * D));
+        }
+        TRY(up_new(m, tm, p + ".ca_mix.weight", 3 * DD, &ly.Wmix));
+        TRY(up_new(m, tm, p + ".ca_mix.bias", D, &ly.bmix));
+        TRY(up_new(m, tm, p + ".ffn.linear1.weight", (long long)F * D, &ly.W1));
+        TRY(up_new(m, tm, p + ".ffn.linear1.bias", F, &ly.b1));
+        TRY(up_new(m, tm, p + ".ffn.linear2.weight", (long long)D * F, &ly.W2));
+        TRY(up_new(m, tm, p + ".ffn.linear2.bias", D, &ly.b2));
+        TRY(dalloc(m, (void**)&ly.ffn_g, D * sizeof(float)));
+        TRY(dalloc(m, (void**)&ly.ffn_b, D * sizeof(float)));
+        TRY(dalloc(m, (void**)&ly.ffn_Wo, DD * sizeof(float)));
+        TRY(dalloc(m, (void**)&ly.ffn_bo, D * sizeof(float)));
+        TRY(styl(p + ".ffn.proj_out", 4, &ly.ffn_g, &ly.ffn_b, ly.ffn_Wo, ly.ffn_bo));
+        TRYCU(cudaStreamSynchronize(st));   // tmp buffers are reused by the next layer
+    }
+    TRYCU(cudaDeviceSynchronize());
+    dfree_one(m, tmpW); dfree_one(m, tmpb); dfree_one(m, tmpg); dfree_one(m, tmpbe);
+    dfree_one(m, seq); dfree_one(m, glob);
+    TRY(dalloc(m, (void**)&m->tau_row, (size_t)L * 5 * 2 * D * sizeof(float)));
+    *out = m;
+    rc = 0;
+fail:
+    if (rc) { std::string keep = g_err; rg_destroy(m); snprintf(g_err, sizeof(g_err), "%s", keep.c_str()); }
+    return rc;
+#undef TRY
+#undef TRYCU
+}
+
+// ---- K7: (scale|shift) rows for arbitrary timesteps ------------------------------------------
+// taus: n original-scale timesteps (host).  out [n, L*5*1024] (device).
+static int time_rows(rg_model* m, const int* taus, int n, float* out, cudaStream_t st) {
+    const int D = RG_D, E = m->cfg.time_embed_dim, L = m->cfg.num_layers;
+    if (n > m->tt_rows) {
+        dfree_one(m, m->tt_emb); dfree_one(m, m->tt_t1); dfree_one(m, m->tt_e);
+        m->tt_emb = m->tt_t1 = m->tt_e = nullptr; m->tt_rows = 0;
+        if (dalloc(m, (void**)&m->tt_emb, (size_t)n * D * sizeof(float))) return 1;
+        if (dalloc(m, (void**)&m->tt_t1, (size_t)n * E * sizeof(float))) return 1;
+        if (dalloc(m, (void**)&m->tt_e, (size_t)n * E * sizeof(float))) return 1;
+        m->tt_rows = n;
+    }
+    // timestep_embedding (diffusion_transformer.py:36-43) in the reference's fp32 op order
+    std::vector<float> temb((size_t)n * D);
+    const int half = D / 2;
+    const float neg_log = (float)(-log(10000.0));
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < half; ++j) {
+            const float freq = expf((neg_log * (float)j) / (float)half);
+            const float arg = (float)taus[i] * freq;
+            temb[(size_t)i * D + j] = cosf(arg);
+            temb[(size_t)i * D + half + j] = sinf(arg);
+        }
+    CU(cudaMemcpyAsync(m->tt_emb, temb.data(), temb.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));   // temb is a stack-owned host buffer
+    LAUNCH(rg_launch_gemm_f32(mk_gemm(m->tt_emb, D, m->W_t0, m->b_t0, m->tt_t1, E, n, E, D, RG_EPI_BIAS_SILU), st));
+    // emb = time_embed.2(.)  then SiLU (the first op of every emb_layers)
+    LAUNCH(rg_launch_gemm_f32(mk_gemm(m->tt_t1, E, m->W_t2, m->b_t2, m->tt_e, E, n, E, E, RG_EPI_BIAS_SILU), st));
+    const int NT = L * 5 * 2 * D;
+    LAUNCH(rg_launch_gemm_f32(mk_gemm(m->tt_e, E, m->We_all, m->be_all, out, NT, n, NT, E, RG_EPI_BIAS), st));
+    return 0;
+}
+
+extern "C" int rg_set_schedule(rg_handle m, int n_steps, const int32_t* timestep_map,
+                               const float* coef, void* stream) {
+    if (!m || n_steps <= 0 || !timestep_map || !coef) return rg_fail("rg_set_schedule: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long NT = (long long)m->cfg.num_layers * 5 * 2 * RG_D;
+    if (m->table) { dfree_one(m, m->table); m->table = nullptr; }
+    if (dalloc(m, (void**)&m->table, (size_t)n_steps * NT * sizeof(float))) return 1;
+    m->n_steps = n_steps;
+    m->timestep_map.assign(timestep_map, timestep_map + n_steps);
+    m->coef.assign(coef, coef + (size_t)n_steps * 8);
+    std::vector<int> taus(timestep_map, timestep_map + n_steps);
+    if (time_rows(m, taus.data(), n_steps, m->table, st)) return 1;
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ---- workspaces ------------------------------------------------------------------------------
+static int ensure_ws(rg_model* m, long long rows) {
+    if (rows <= m->ws_rows) return 0;
+    float** bufs[6] = {&m->h, &m->a, &m->big, &m->o3, &m->g, &m->y};
+    for (auto b : bufs) { dfree_one(m, *b); *b = nullptr; }
+    m->ws_rows = 0;
+    const int D = RG_D, F = m->cfg.ffn_dim;
+    if (dalloc(m, (void**)&m->h, (size_t)rows * D * sizeof(float))) return 1;
+    if (dalloc(m, (void**)&m->a, (size_t)rows * 3 * D * sizeof(float))) return 1;
+    if (dalloc(m, (void**)&m->big, (size_t)rows * 3 * D * sizeof(float))) return 1;
+    if (dalloc(m, (void**)&m->o3, (size_t)rows * 3 * D * sizeof(float))) return 1;
+    if (dalloc(m, (void**)&m->g, (size_t)rows * F * sizeof(float))) return 1;
+    if (dalloc(m, (void**)&m->y, (size_t)rows * D * sizeof(float))) return 1;
+    m->ws_rows = rows;
+    return 0;
+}
+
+extern "C" int64_t rg_state_floats_per_clip(rg_handle m) {
+    return m ? (int64_t)m->cfg.num_layers * 3 * RG_H * RG_HD * RG_HD : 0;
+}
+
+extern "C" int rg_encode_conditions(rg_handle m, const float* word, const float* audio,
+                                    const int64_t* spk_ids, int B, int n_text, int n_audio,
+                                    int n_spk, float* xf_text, float* xf_audio, float* xf_spk,
+                                    void* stream) {
+    if (!m) return rg_fail("rg_encode_conditions: null handle");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int D = RG_D, TD = m->cfg.text_dim;
+    if (word && xf_text)
+        LAUNCH(rg_launch_gemm_f32(mk_gemm(word, TD, m->W_text, m->b_text, xf_text, D, B * n_text, D, TD, RG_EPI_BIAS), st));
+    if (audio && xf_audio)
+        LAUNCH(rg_launch_gemm_f32(mk_gemm(audio, TD, m->W_audio, m->b_audio, xf_audio, D, B * n_audio, D, TD, RG_EPI_BIAS), st));
+    if (spk_ids && xf_spk)
+        LAUNCH(rg_launch_gather_rows(m->spk_table, (const long long*)spk_ids, xf_spk, (long long)B * n_spk,
+                                     m->cfg.num_speakers, st));
+    return 0;
+}
+
+extern "C" int rg_precompute_clip_state(rg_handle m, const float* xf_text, const float* xf_audio,
+                                        const float* xf_spk, int n_text, int n_audio, int n_spk,
+                                        int B, float* state, void* stream) {
+    if (!m || !state) return rg_fail("rg_precompute_clip_state: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int D = RG_D, L = m->cfg.num_layers;
+    const long long clip_stride = rg_state_floats_per_clip(m);
+    const float* xf[3] = {xf_text, xf_audio, xf_spk};
+    const int nt[3] = {n_text, n_audio, n_spk};
+    const long long MAX_ROWS = 8192;
+    for (int c = 0; c < 3; ++c) {
+        if (!xf[c] || nt[c] <= 0) return rg_fail("rg_precompute_clip_state: condition %d missing", c);
+        const int N = nt[c];
+        int per = (int)(MAX_ROWS / N); if (per < 1) per = 1;
+        const long long need = (long long)per * N;
+        if (need > m->kv_rows) {
+            dfree_one(m, m->kv_ln); dfree_one(m, m->kv_buf); m->kv_ln = m->kv_buf = nullptr; m->kv_rows = 0;
+            if (dalloc(m, (void**)&m->kv_ln, (size_t)need * D * sizeof(float))) return 1;
+            if (dalloc(m, (void**)&m->kv_buf, (size_t)need * L * 2 * D * sizeof(float))) return 1;
+            m->kv_rows = need;
+        }
+        for (int b0 = 0; b0 < B; b0 += per) {
+            const int nb = (B - b0 < per) ? B - b0 : per;
+            const int rows = nb * N;
+            LAUNCH(rg_launch_ln_rows(xf[c] + (long long)b0 * N * D, D, nullptr, nullptr, m->kv_ln, D, rows, st));
+            LAUNCH(rg_launch_gemm_f32(mk_gemm(m->kv_ln, D, m->Wkv_all[c], m->bkv_all[c], m->kv_buf, L * 2 * D,
+                                              rows, L * 2 * D, D, RG_EPI_BIAS), st));
+            LAUNCH(rg_launch_kv_state(m->kv_buf, L * 2 * D, 0, D, N,
+                                      state + (long long)b0 * clip_stride + (long long)c * RG_H * RG_HD * RG_HD,
+                                      clip_stride, nb, L, 2 * D, (long long)3 * RG_H * RG_HD * RG_HD, st));
+        }
+    }
+    return 0;
+}
+
+extern "C" int rg_denoise(rg_handle m, const float* x, int B, int step_idx, int tau,
+                          const float* src_mask, const float* query_mask, const float* state,
+                          float* x0_out, void* stream) {
+    if (!m || !x || !src_mask || !state || !x0_out) return rg_fail("rg_denoise: null argument");
+    if (B <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int D = RG_D, F = m->cfg.ffn_dim, L = m->cfg.num_layers, T = m->cfg.n_tokens;
+    const int M = B * T;
+    const long long NT = (long long)L * 5 * 2 * D;
+    const float* ssrow;
+    if (step_idx >= 0) {
+        if (step_idx >= m->n_steps) return rg_fail("rg_denoise: step_idx %d outside the schedule (%d steps)", step_idx, m->n_steps);
+        ssrow = m->table + (long long)step_idx * NT;
+    } else {
+        if (m->tau_cached != tau) {
+            if (time_rows(m, &tau, 1, m->tau_row, st)) return 1;
+            m->tau_cached = tau;
+        }
+        ssrow = m->tau_row;
+    }
+    if (ensure_ws(m, M)) return 1;
+    const long long clip_stride = rg_state_floats_per_clip(m);
+    const long long HS = (long long)RG_H * RG_HD * RG_HD;
+
+    // h = joint_embed(x) + positional tables
+    {
+        RgGemm g = mk_gemm(x, D, m->W_joint, m->b_joint, m->h, D, M, D, D, RG_EPI_BIAS_POS);
+        g.pos = m->pos; g.pos_T = T;
+        LAUNCH(rg_launch_gemm_f32(g, st));
+    }
+    for (int l = 0; l < L; ++l) {
+        const Layer& ly = m->layers[l];
+        const float* ss = ssrow + (long long)l * 5 * 2 * D;
+        // --- self-attention
+        LAUNCH(rg_launch_ln_rows(m->h, D, nullptr, nullptr, m->a, D, M, st));
+        LAUNCH(rg_launch_gemm_f32(mk_gemm(m->a, D, ly.Wqkv, ly.bqkv, m->big, 3 * D, M, 3 * D, D, RG_EPI_BIAS), st));
+        RgStylParams sp = {ly.sa_g, ly.sa_b, ss, 0};
+        LAUNCH(rg_launch_sa_attention(m->big, src_mask, sp, nullptr, m->a, B, T, 1, st));
+        {
+            RgGemm g = mk_gemm(m->a, D, ly.sa_Wo, ly.sa_bo, m->h, D, M, D, D, RG_EPI_BIAS_RESIDUAL);
+            g.R = m->h; g.ldr = D;
+            LAUNCH(rg_launch_gemm_f32(g, st));
+        }
+        // --- three cross-attentions on the same h
+        LAUNCH(rg_launch_ln_rows(m->h, D, nullptr, nullptr, m->a, D, M, st));
+        LAUNCH(rg_launch_gemm_f32(mk_gemm(m->a, D, ly.Wcaq, ly.bcaq, m->big, 3 * D, M, 3 * D, D, RG_EPI_BIAS), st));
+        RgStylParams sp3[3];
+        for (int c = 0; c < 3; ++c) sp3[c] = {ly.ca_g + c * D, ly.ca_b + c * D, ss + (1 + c) * 2 * D, 0};
+        LAUNCH(rg_launch_ca_attention(m->big, 3 * D, state + (long long)l * 3 * HS, clip_stride, HS, query_mask,
+                                      (long long)B * T, sp3, m->a, 3 * D, B, T, 3, st));
+        {
+            RgGemm g = mk_gemm(m->a, 3 * D, ly.ca_Wo, ly.ca_bo, m->o3, 3 * D, M, D, D, RG_EPI_BIAS_RESIDUAL);
+            g.groups = 3; g.a_g = D; g.w_g = (long long)D * D; g.b_g = D; g.c_g = D; g.R = m->h; g.ldr = D; g.r_g = 0;
+            LAUNCH(rg_launch_gemm_f32(g, st));
+        }
+        LAUNCH(rg_launch_gemm_f32(mk_gemm(m->o3, 3 * D, ly.Wmix, ly.bmix, m->h, D, M, D, 3 * D, RG_EPI_BIAS), st));
+        // --- FFN
+        LAUNCH(rg_launch_gemm_f32(mk_gemm(m->h, D, ly.W1, ly.b1, m->g, F, M, F, D, RG_EPI_BIAS_GELU), st));
+        LAUNCH(rg_launch_gemm_f32(mk_gemm(m->g, F, ly.W2, ly.b2, m->y, D, M, D, F, RG_EPI_BIAS), st));
+        RgStylParams spf = {ly.ffn_g, ly.ffn_b, ss + 4 * 2 * D, 0};
+        LAUNCH(rg_launch_styl_rows(m->y, D, spf, T, m->a, D, M, st));
+        {
+            RgGemm g = mk_gemm(m->a, D, ly.ffn_Wo, ly.ffn_bo, m->h, D, M, D, D, RG_EPI_BIAS_RESIDUAL);
+            g.R = m->h; g.ldr = D;
+            LAUNCH(rg_launch_gemm_f32(g, st));
+        }
+    }
+    LAUNCH(rg_launch_gemm_f32(mk_gemm(m->h, D, m->W_out, m->b_out, x0_out, D, M, D, D, RG_EPI_BIAS), st));
+    return 0;
+}
+
+static int step_coef(rg_model* m, int step_idx, const float** c) {
+    if (!m) return rg_fail("null handle");
+    if (step_idx < 0 || step_idx >= m->n_steps) return rg_fail("step_idx %d outside the schedule (%d steps)", step_idx, m->n_steps);
+    *c = m->coef.data() + (size_t)step_idx * 8;
+    return 0;
+}
+
+extern "C" int rg_ddim_update(rg_handle m, const float* x, const float* x0, int step_idx,
+                              int direction, float* out, int64_t n, void* stream) {
+    const float* c;
+    if (step_coef(m, step_idx, &c)) return 1;
+    const float ca = direction < 0 ? c[2] : c[4], cb = direction < 0 ? c[3] : c[5];
+    LAUNCH(rg_launch_ddim_update(x, x0, out, n, c[0], c[1], ca, cb, (cudaStream_t)stream));
+    return 0;
+}
+
+extern "C" int rg_blend_in_seq(rg_handle m, const float* x, const float* in_seq, const float* noise,
+                               int step_idx, float* out, int64_t rows, void* stream) {
+    const float* c;
+    if (step_coef(m, step_idx, &c)) return 1;
+    LAUNCH(rg_launch_blend(x, in_seq, noise, out, rows, c[6], c[7], (cudaStream_t)stream));
+    return 0;
+}
+
+extern "C" int rg_guidance_steps(rg_handle, float* x, const float* in_seq, int64_t rows, int iters,
+                                 float lr, int64_t numel, void* stream) {
+    if (iters <= 0) return 0;
+    LAUNCH(rg_launch_guidance(x, in_seq, rows, iters, (float)(2.0 * (double)lr / (double)numel), (cudaStream_t)stream));
+    return 0;
+}
+
+// ---- op-level entry points -------------------------------------------------------------------
+extern "C" int rg_op_linear(const float* x, int ldx, const float* W, const float* b,
+                            const float* residual, float* out, int M, int N, int K, int epilogue,
+                            void* stream) {
+    int epi;
+    switch (epilogue) {
+        case RG_OP_NONE: epi = RG_EPI_BIAS; break;
+        case RG_OP_RESIDUAL: epi = RG_EPI_BIAS_RESIDUAL; break;
+        case RG_OP_GELU: epi = RG_EPI_BIAS_GELU; break;
+        case RG_OP_SILU: epi = RG_EPI_BIAS_SILU; break;
+        default: return rg_fail("rg_op_linear: unknown epilogue %d", epilogue);
+    }
+    if (epi == RG_EPI_BIAS_RESIDUAL && !residual) return rg_fail("rg_op_linear: residual epilogue without residual");
+    RgGemm g = mk_gemm(x, ldx, W, b, out, N, M, N, K, epi);
+    g.R = residual; g.ldr = N;
+    LAUNCH(rg_launch_gemm_f32(g, (cudaStream_t)stream));
+    return 0;
+}
+extern "C" int rg_op_layernorm(const float* x, const float* gamma, const float* beta, float* out,
+                               int M, void* stream) {
+    LAUNCH(rg_launch_ln_rows(x, RG_D, gamma, beta, out, RG_D, M, (cudaStream_t)stream));
+    return 0;
+}
+extern "C" int rg_op_silu(const float* x, float* out, int64_t n, void* stream) {
+    LAUNCH(rg_launch_silu(x, out, n, (cudaStream_t)stream));
+    return 0;
+}
+extern "C" int rg_op_stylization_rows(const float* y, const float* gamma, const float* beta,
+                                      const float* ss, int ss_per_clip, int rows_per_clip,
+                                      float* out, int M, void* stream) {
+    RgStylParams sp = {gamma, beta, ss, ss_per_clip ? 2 * RG_D : 0};
+    LAUNCH(rg_launch_styl_rows(y, RG_D, sp, rows_per_clip, out, RG_D, M, (cudaStream_t)stream));
+    return 0;
+}
+extern "C" int rg_op_self_attention(const float* qkv, const float* src_mask, const float* gamma,
+                                    const float* beta, const float* ss, int ss_per_clip,
+                                    const float* x_res, float* out, int B, int T, int with_styl,
+                                    void* stream) {
+    if (T > RG_MAX_T) return rg_fail("rg_op_self_attention: T=%d > %d", T, RG_MAX_T);
+    if (!with_styl && !x_res) return rg_fail("rg_op_self_attention: x_res required when with_styl=0");
+    RgStylParams sp = {gamma, beta, ss, ss_per_clip ? 2 * RG_D : 0};
+    LAUNCH(rg_launch_sa_attention(qkv, src_mask, sp, x_res, out, B, T, with_styl, (cudaStream_t)stream));
+    return 0;
+}
+extern "C" int rg_op_cross_attention(const float* q, const float* state, const float* query_mask,
+                                     const float* gamma, const float* beta, const float* ss,
+                                     int ss_per_clip, float* out, int B, int T, void* stream) {
+    if (T > RG_MAX_T) return rg_fail("rg_op_cross_attention: T=%d > %d", T, RG_MAX_T);
+    RgStylParams sp[3];
+    sp[0] = {gamma, beta, ss, ss_per_clip ? 2 * RG_D : 0};
+    sp[1] = sp[0]; sp[2] = sp[0];
+    LAUNCH(rg_launch_ca_attention(q, RG_D, state, (long long)RG_H * RG_HD * RG_HD, 0, query_mask, 0, sp, out,
+                                  RG_D, B, T, 1, (cudaStream_t)stream));
+    return 0;
+}
+extern "C" int rg_op_kv_state(const float* kv, int n_tokens, int B, float* state, void* stream) {
+    LAUNCH(rg_launch_kv_state(kv, 2 * RG_D, 0, RG_D, n_tokens, state, (long long)RG_H * RG_HD * RG_HD, B, 1, 0, 0,
+                              (cudaStream_t)stream));
+    return 0;
+}

@@ -1,0 +1,94 @@
+"""Op-level wrappers over the C ABI (the `rg_op_*` entry points of include/rg_b200.h).
+
+Used by the per-module mirrors in mogen_api.py (API-faithful path: one call per reference module)
+and by the unit parity tests.  Inputs must be CUDA fp32 tensors; nothing here computes in PyTorch.
+"""
+import torch
+
+from . import _lib
+
+D = 512
+
+
+def _prep(*ts):
+    _lib.require_cuda(*ts)
+    return [None if t is None else t.float().contiguous() for t in ts]
+
+
+def linear(x, weight, bias=None, residual=None, epilogue=_lib.OP_NONE):
+    """epilogue(x @ weight.T + bias [+ residual]); x [..., K] -> [..., N]."""
+    x, weight, bias, residual = _prep(x, weight, bias, residual)
+    N, K = weight.shape
+    M = x.numel() // K
+    out = torch.empty(*x.shape[:-1], N, device=x.device)
+    if residual is not None:
+        epilogue = _lib.OP_RESIDUAL
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().rg_op_linear(_lib.ptr(x), K, _lib.ptr(weight), _lib.ptr(bias),
+                                            _lib.ptr(residual), _lib.ptr(out), M, N, K, epilogue,
+                                            _lib.stream_ptr()))
+    return out
+
+
+def layernorm(x, gamma=None, beta=None):
+    x, gamma, beta = _prep(x, gamma, beta)
+    assert x.shape[-1] == D, "rg_b200 LayerNorm kernels are built for 512-wide rows"
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().rg_op_layernorm(_lib.ptr(x), _lib.ptr(gamma), _lib.ptr(beta),
+                                               _lib.ptr(out), x.numel() // D, _lib.stream_ptr()))
+    return out
+
+
+def silu(x):
+    (x,) = _prep(x)
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().rg_op_silu(_lib.ptr(x), _lib.ptr(out), x.numel(), _lib.stream_ptr()))
+    return out
+
+
+def stylization_rows(y, gamma, beta, ss, rows_per_clip):
+    """silu(LN(y) * (1 + scale) + shift); ss [B,1024] (per clip) or [1024] (shared)."""
+    y, gamma, beta, ss = _prep(y, gamma, beta, ss)
+    out = torch.empty_like(y)
+    with torch.cuda.device(y.device):
+        _lib.check(_lib.load().rg_op_stylization_rows(
+            _lib.ptr(y), _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(ss), int(ss.dim() > 1),
+            rows_per_clip, _lib.ptr(out), y.numel() // D, _lib.stream_ptr()))
+    return out
+
+
+def self_attention(qkv, src_mask, gamma=None, beta=None, ss=None, x_res=None):
+    """qkv [B,T,1536], src_mask [B,T] -> [B,T,512]; stylised rows if ss is given else x_res + Y."""
+    qkv, src_mask, gamma, beta, ss, x_res = _prep(qkv, src_mask, gamma, beta, ss, x_res)
+    B, T = qkv.shape[0], qkv.shape[1]
+    out = torch.empty(B, T, D, device=qkv.device)
+    with torch.cuda.device(qkv.device):
+        _lib.check(_lib.load().rg_op_self_attention(
+            _lib.ptr(qkv), _lib.ptr(src_mask), _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(ss),
+            int(ss is not None and ss.dim() > 1), _lib.ptr(x_res), _lib.ptr(out), B, T,
+            int(ss is not None), _lib.stream_ptr()))
+    return out
+
+
+def cross_attention(q, state, query_mask, gamma, beta, ss):
+    """q [B,T,512] pre-softmax, state [B,16,32,32], query_mask [B,T] or None -> stylised rows."""
+    q, state, query_mask, gamma, beta, ss = _prep(q, state, query_mask, gamma, beta, ss)
+    B, T = q.shape[0], q.shape[1]
+    out = torch.empty(B, T, D, device=q.device)
+    with torch.cuda.device(q.device):
+        _lib.check(_lib.load().rg_op_cross_attention(
+            _lib.ptr(q), _lib.ptr(state), _lib.ptr(query_mask), _lib.ptr(gamma), _lib.ptr(beta),
+            _lib.ptr(ss), int(ss.dim() > 1), _lib.ptr(out), B, T, _lib.stream_ptr()))
+    return out
+
+
+def kv_state(kv, B, n_tokens):
+    """kv [B*N,1024] = [key | value] projections -> state [B,16,32,32]."""
+    (kv,) = _prep(kv)
+    state = torch.empty(B, 16, 32, 32, device=kv.device)
+    with torch.cuda.device(kv.device):
+        _lib.check(_lib.load().rg_op_kv_state(_lib.ptr(kv), n_tokens, B, _lib.ptr(state),
+                                              _lib.stream_ptr()))
+    return state

@@ -176,3 +176,104 @@ class NoiseTape:
     def randn(self, shape, device="cpu"):
         self.n += 1
         return torch.randn(tuple(shape), generator=self.g, dtype=torch.float32).to(device)
+
+
+# ---- synthetic annotated dataset (schema of beatx_dataset.py:1262-1295) -------------
+CONNECTIVES = ["and", "but", "so", "because", "then", "when", "if", "also", "while", "although",
+               "however", "since", "though", "or", "as well", "so that"]
+SENSES = ["Expansion.Conjunction", "Comparison.Contrast", "Contingency.Cause", "Temporal.Asynchronous",
+          "Temporal.Synchronous", "Contingency.Condition", "Comparison.Concession", "Expansion.Alternative"]
+FILLERS = ["the", "gesture", "people", "really", "think", "time", "maybe", "little"]
+
+
+class SyntheticGestureDataset:
+    """In-memory stand-in for BEATXDataset: `ds[i]` / `ds[sample_name]` -> per-sample dict with the
+    keys the hot path reads (raggesture.py:556-570, 244-276).  Every sample is a pure function of
+    (seed, index); tensors are generated on access, annotations are cheap and cached."""
+
+    def __init__(self, n, seed=7, frames=150, per_file=30):
+        self.n, self.seed, self.frames, self.per_file = n, seed, frames, per_file
+        self._ann = {}
+        self.names = [self._name(i) for i in range(n)]
+        self._by_name = {nm: i for i, nm in enumerate(self.names)}
+
+    def _name(self, i):
+        f, j = divmod(i, self.per_file)
+        spk = (f * 7 + 3) % C.NUM_SPEAKERS
+        return f"{spk}_synth_0_{f}_{f}/{j * 15 if j % 2 == 0 else j * 15 + 4}"
+
+    def __len__(self):
+        return self.n
+
+    def __iter__(self):
+        return (self[i] for i in range(self.n))
+
+    def annotations(self, i):
+        """(speaker, discourse, prominence, gesture_labels, n_text_tokens) of sample i."""
+        if i in self._ann:
+            return self._ann[i]
+        import random
+        r = random.Random(self.seed * 1_000_003 + i)
+        f = i // self.per_file
+        spk = (f * 7 + 3) % C.NUM_SPEAKERS
+        discourse, prominence = [], []
+        for _ in range(r.choice([0, 1, 1, 2, 2, 3])):
+            conn = r.choice(CONNECTIVES)
+            sense = r.choice(SENSES[:4]) if r.random() < 0.7 else r.choice(SENSES)
+            ts = sorted(round(r.uniform(0, 10), 3) for _ in range(4))
+            cs = round(r.uniform(ts[0], ts[3]), 3)
+            ce = round(min(10.0, cs + r.uniform(0.15, 0.8)), 3)
+            discourse.append((conn, sense, "arg1", "arg2", ts[0], ts[3], cs, ce))
+        discourse.sort(key=lambda d: d[6])
+        for w in r.sample(FILLERS, 3):
+            s = round(r.uniform(0, 9.5), 3)
+            prominence.append((w, s, round(s + 0.3, 3), round(r.uniform(0, 3), 4)))
+        for d in discourse:
+            if r.random() < 0.65:                      # the rest map to None (integer-score tiers)
+                for w in d[0].split():
+                    prominence.append((w, d[6], d[7], round(r.uniform(0, 3), 4)))
+        prominence.sort(key=lambda p: p[1])
+        gestures = [{"name": r.choice(["beat", "deictic", "iconic", "metaphoric"]), "start": d[6],
+                     "end": d[7], "word": d[0]} for d in discourse[:1]]
+        self._ann[i] = (spk, discourse, prominence, gestures, r.randint(8, 32))
+        return self._ann[i]
+
+    def text_feature(self, i):
+        n_tok = self.annotations(i)[4]
+        g = torch.Generator().manual_seed(self.seed * 7_000_003 + i)
+        return torch.randn(n_tok, C.TEXT_DIM, generator=g)
+
+    def __getitem__(self, key):
+        i = self._by_name[key] if isinstance(key, str) else int(key)
+        spk, discourse, prominence, gestures, _ = self.annotations(i)
+        g = torch.Generator().manual_seed(self.seed * 9_000_011 + i)
+        F = self.frames
+        rn = lambda *s: 0.1 * torch.randn(*s, generator=g)
+        upper, lower, face, hands = rn(F, 39), rn(F, 27), rn(F, 3), rn(F, 90)
+        trans, facial, contact = rn(F, 3), rn(F, 100), rn(F, 4)
+        return dict(
+            motion=torch.cat([upper, lower, face, hands, rn(F, 6)], -1), motion_upper=upper,
+            motion_lower=lower, motion_face=face, motion_hands=hands, trans=trans, facial=facial,
+            contact=contact, motion_mask=torch.ones(F), motion_length=F,
+            word=torch.randn(C.N_TEXT, C.TEXT_DIM, generator=g),
+            audio=torch.randn(C.N_AUDIO, C.TEXT_DIM, generator=g),
+            speaker_id=torch.full((F,), spk, dtype=torch.int64), text_feature=self.text_feature(i),
+            raw_word="", raw_audio=None, text_segments=[], discourse=list(discourse),
+            prominence=list(prominence), gesture_labels=list(gestures), sample_name=self.names[i],
+            sample_idx=i)
+
+
+def collate(samples):
+    """beatx_collate_fn (mogen/datasets/builder.py:59-91): tensors stacked, list fields kept as lists,
+    speaker_id -> speaker_ids, text_feature -> text_features."""
+    out = {}
+    for k in samples[0]:
+        vals = [s[k] for s in samples]
+        if isinstance(vals[0], torch.Tensor) and k != "text_feature":
+            out[k] = torch.stack(vals, 0)
+        else:
+            out[k] = vals
+    out["speaker_ids"] = out.pop("speaker_id")
+    out["text_features"] = out.pop("text_feature")
+    out["motion_length"] = torch.tensor(out["motion_length"])
+    return out

@@ -1,0 +1,214 @@
+"""End-to-end parity of the CUDA path (fused engine + samplers, through the reference-shaped API)
+against the golden vectors of the unmodified reference and against the oracle.  Needs a GPU.
+
+Tolerances (fp32 tier of BASELINE.json north_star: rel-L2 <= 1e-3 on denoised latents)."""
+import pytest
+import torch
+
+from conftest import rel_l2
+from rag_gesture_b200 import config as C
+from rag_gesture_b200 import synthetic as S
+
+pytestmark = pytest.mark.gpu
+TOL_STEP = 1e-4      # one denoiser evaluation
+TOL_LOOP = 1e-3      # 50-step trajectories (north_star fp32 tier)
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def model(dev, sd0):
+    from rag_gesture_b200 import mogen_api as M
+    cfg = C.denoiser_cfg()
+    m = M.build_submodule(cfg, database=None, use_retrieval_for_test=False)
+    missing, unexpected = m.load_state_dict(sd0, strict=False)
+    assert not unexpected and all(k.startswith("gesture_rep_encoder.") for k in missing), (missing, unexpected)
+    return m.to(dev).eval()
+
+
+@pytest.fixture(scope="module")
+def diffusion():
+    from rag_gesture_b200.diffusion import build_diffusion
+    return build_diffusion(C.diffusion_test_cfg())
+
+
+def _kw(model, cond, B, dev):
+    pc = model.get_precompute_condition(device=dev, text=cond["word"], audio=cond["audio"],
+                                        speaker_ids=cond["speaker_ids"], re_dict=1)
+    return dict(xf_out=pc["xf_out"], re_dict=None, sample_idx=None,
+                query_mask={k: v.to(dev) for k, v in S.query_masks(B).items()},
+                motion_mask=S.motion_mask(B).to(dev))
+
+
+def test_state_dict_keys_match_reference(model):
+    keys = [k for k in model.state_dict().keys() if not k.startswith("gesture_rep_encoder.")]
+    assert keys and set(keys) == set(S.denoiser_param_shapes().keys())
+    for k, shp in S.denoiser_param_shapes().items():
+        assert tuple(model.state_dict()[k].shape) == tuple(shp), k
+
+
+def test_condition_encoding(model, golden, dev):
+    g = golden("denoiser_step")
+    cond = S.synthetic_conditions(2, seed=11)
+    kw = _kw(model, cond, 2, dev)
+    assert rel_l2(kw["xf_out"]["xf_text"][:, :4].cpu(), torch.from_numpy(g["xf_text"])) < 1e-5
+
+
+def test_denoiser_step_fused_vs_golden(model, golden, dev):
+    g = golden("denoiser_step")
+    B = 2
+    kw = _kw(model, S.synthetic_conditions(B, seed=11), B, dev)
+    x = S.synthetic_latents(B, seed=12).to(dev)
+    with torch.no_grad():
+        for tau in (14, 514, 999):
+            out = model(x, torch.full((B,), tau, device=dev), **kw).cpu()
+            assert rel_l2(out, torch.from_numpy(g[f"x0_t{tau}"])) < TOL_STEP, tau
+        # off-schedule timestep through the on-the-fly table row, against the oracle
+        from oracle import denoiser as OD
+    sd = {k: v.cpu() for k, v in model.state_dict().items()}
+    cond = S.synthetic_conditions(B, seed=11)
+    xf = OD.encode_conditions(sd, cond["word"], cond["audio"], cond["speaker_ids"])
+    ref = OD.denoiser_forward(sd, x.cpu(), torch.full((B,), 777), S.motion_mask(B), xf, S.query_masks(B))
+    with torch.no_grad():
+        out = model(x, torch.full((B,), 777, device=dev), **kw).cpu()
+    assert rel_l2(out, ref) < TOL_STEP
+
+
+def test_denoiser_module_path_matches_fused(model, dev):
+    """forward_test over the per-module kernels (K/V recomputed per call, arbitrary emb) == fused."""
+    from oracle import denoiser as OD
+    B = 2
+    cond = S.synthetic_conditions(B, seed=31)
+    kw = _kw(model, cond, B, dev)
+    x = S.synthetic_latents(B, seed=32).to(dev)
+    sd = {k: v.cpu() for k, v in model.state_dict().items()}
+    ts = torch.full((B,), 428)
+    emb = OD._lin(sd, "time_embed.2", torch.nn.functional.silu(OD._lin(sd, "time_embed.0", OD.timestep_embedding(ts, 512))))
+    h = OD.embed_latents(sd, x.cpu())
+    with torch.no_grad():
+        out_m = model.forward_test(h=h.to(dev), src_mask=S.motion_mask(B).unsqueeze(-1).to(dev), emb=emb.to(dev),
+                                   xf_out=kw["xf_out"], query_mask=kw["query_mask"], timesteps=ts.to(dev)).cpu()
+        out_f = model(x, ts.to(dev), **kw).cpu()
+    assert rel_l2(out_m, out_f) < 2e-5
+
+
+def test_normal_scale_row_groups(golden, dev):
+    """Cross-attention values at ordinary scale: rows 20/30 get y - 1e6 rounded to a 1/16 grid
+    (efficient_attention.py:98), a discontinuous function; every other row group must still agree."""
+    from rag_gesture_b200 import mogen_api as M
+    g = golden("denoiser_step_normal_scale")
+    sd = S.synthetic_state_dict(1, normal_scale=True)
+    m = M.build_submodule(C.denoiser_cfg(), database=None, use_retrieval_for_test=False)
+    m.load_state_dict(sd, strict=False)
+    m = m.to(dev).eval()
+    B = 2
+    kw = _kw(m, S.synthetic_conditions(B, seed=11), B, dev)
+    x = S.synthetic_latents(B, seed=12).to(dev)
+    with torch.no_grad():
+        out = m(x, torch.full((B,), 514, device=dev), **kw).cpu()
+    ref = torch.from_numpy(g["x0_t514"])
+    rows = [r for r in range(C.N_TOKENS) if r not in (20, 30)]
+    print("normal-scale rel-L2: other rows %.3g, rows 20/30 %.3g" % (
+        rel_l2(out[:, rows], ref[:, rows]), rel_l2(out[:, [20, 30]], ref[:, [20, 30]])))
+    # measured on B200: 1.0e-2 / 4.8e-2 -- a handful of 1/16-grid roundings flip between any two
+    # fp32 implementations (also CPU vs GPU runs of the reference itself); see DESIGN.md
+    assert rel_l2(out[:, rows], ref[:, rows]) < 5e-2
+    assert rel_l2(out, ref) < 2e-1
+
+
+def test_plain_ddim_loop_config1(model, diffusion, golden, dev):
+    """BASELINE.json configs[0]: B=1, 50-step plain DDIM, same noise as the reference run."""
+    g = golden("ddim_plain_b1")
+    kw = _kw(model, S.synthetic_conditions(1, seed=21), 1, dev)
+    tape = S.NoiseTape(1234)
+    diffusion.noise_fn = tape.randn
+    traj = [o["sample"].cpu() for o in diffusion.ddim_sample_loop_progressive(
+        model, (1, C.N_TOKENS, C.LATENT_DIM), clip_denoised=False, model_kwargs=kw, eta=0)]
+    diffusion.noise_fn = None
+    assert tape.n == 51
+    assert rel_l2(traj[0], torch.from_numpy(g["step49"])) < TOL_STEP
+    assert rel_l2(traj[24], torch.from_numpy(g["step25"])) < TOL_LOOP
+    assert rel_l2(traj[49], torch.from_numpy(g["final"])) < TOL_LOOP
+
+
+def _inverted(model, diffusion, dev):
+    kw = _kw(model, S.synthetic_conditions(1, seed=21), 1, dev)
+    xs = S.synthetic_latents(1, seed=22, scale=0.5).to(dev)
+    inv = diffusion.ddim_reverse_sample_loop(model, start_img=xs, clip_denoised=False, model_kwargs=kw,
+                                             eta=0, return_all_timesteps=True)
+    return torch.cat(inv, 0), kw
+
+
+def test_reverse_loop(model, diffusion, golden, dev):
+    g = golden("ddim_reverse_b1")
+    inv, _ = _inverted(model, diffusion, dev)
+    inv = inv.cpu()
+    assert rel_l2(inv[0], torch.from_numpy(g["inv0"])) < TOL_STEP
+    assert rel_l2(inv[24], torch.from_numpy(g["inv24"])) < TOL_LOOP
+    assert rel_l2(inv[49], torch.from_numpy(g["inv49"])) < TOL_LOOP
+
+
+def test_reverse_loop_batched_equals_single(model, diffusion, dev):
+    """Batching the B=1 inversions of the reference changes nothing: no op couples clips."""
+    cond = S.synthetic_conditions(3, seed=41)
+    kw3 = _kw(model, cond, 3, dev)
+    xs = S.synthetic_latents(3, seed=42, scale=0.5).to(dev)
+    all3 = diffusion.ddim_reverse_sample_loop(model, start_img=xs, clip_denoised=False, model_kwargs=kw3, eta=0)
+    one = {k: (v[1:2] if torch.is_tensor(v) else v) for k, v in S.synthetic_conditions(3, seed=41).items()}
+    kw1 = _kw(model, one, 1, dev)
+    single = diffusion.ddim_reverse_sample_loop(model, start_img=xs[1:2].contiguous(), clip_denoised=False,
+                                                model_kwargs=kw1, eta=0)
+    assert torch.equal(all3[1:2], single)
+
+
+def test_guided_loop_and_dead_guidance(model, diffusion, golden, dev):
+    gg = golden("ddim_guided_b2")
+    inv, kw1 = _inverted(model, diffusion, dev)
+    B, T, D, n = 2, C.N_TOKENS, C.LATENT_DIM, C.N_CHUNKS
+    kw2 = _kw(model, S.synthetic_conditions(B, seed=23), B, dev)
+    inv_list = torch.zeros(50, B, T, D, device=dev)
+    for b, (q0, q1, r0, r1) in enumerate([(2, 5, 4, 7), (6, 10, 0, 4)]):
+        inv_list[:, b, q0:q1] = inv[:, r0:r1]
+        inv_list[:, b, n + 1 + q0:n + 1 + q1] = inv[:, n + 1 + r0:n + 1 + r1]
+    finals = []
+    for skip in (True, False):
+        tape = S.NoiseTape(4321)
+        start = tape.randn((B, T, D), dev)
+        nz = inv_list[49] != 0
+        start[nz] = inv_list[49][nz]
+        diffusion.noise_fn, diffusion.skip_dead_guidance = tape.randn, skip
+        finals.append(diffusion.ddim_guided_sample_loop(
+            model, (B, T, D), noise=start, clip_denoised=False, model_kwargs=kw2, eta=0, in_seq=None,
+            guidance_iters=[0] * 25 + list(range(25)), inverted_latent_list=inv_list, guidance_lr=0.1).cpu())
+    diffusion.noise_fn, diffusion.skip_dead_guidance = None, True
+    assert torch.equal(finals[0], finals[1])            # executing the gradient steps changes nothing
+    assert rel_l2(finals[0], torch.from_numpy(gg["final"])) < 2e-3
+
+    # long-form mode: prev_latent blended on every step of the plain loop
+    prev = torch.zeros(1, T, D)
+    prev[:, [0, n + 1, 2 * n + 2, 3 * n + 3]] = S.synthetic_latents(1, seed=24)[:, [9, 20, 31, 42]]
+    tape = S.NoiseTape(999)
+    diffusion.noise_fn = tape.randn
+    fp = diffusion.ddim_sample_loop(model, (1, T, D), clip_denoised=False, model_kwargs=kw1, eta=0,
+                                    in_seq=prev.to(dev)).cpu()
+    diffusion.noise_fn = None
+    assert rel_l2(fp, torch.from_numpy(gg["final_prev_latent_b1"])) < TOL_LOOP
+
+
+def test_batch_sizes_and_ragged(model, diffusion, dev):
+    """B = 1, 3, 64 give per-clip identical answers (no cross-clip coupling, tile edges)."""
+    B = 64
+    cond = S.synthetic_conditions(B, seed=51)
+    kw = _kw(model, cond, B, dev)
+    x = S.synthetic_latents(B, seed=52).to(dev)
+    with torch.no_grad():
+        full = model(x, torch.full((B,), 600, device=dev), **kw)
+        for sl in (slice(0, 1), slice(5, 8), slice(63, 64)):
+            sub = {k: v[sl] for k, v in cond.items()}
+            n = sl.stop - sl.start
+            out = model(x[sl].contiguous(), torch.full((n,), 600, device=dev), **_kw(model, sub, n, dev))
+            assert torch.equal(out, full[sl])
