@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""Benchmark of the guided-DDIM + exemplar-retrieval hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...      (N > 1)
+
+Metric: guided DDIM clip-steps/s.  One "step" of this script = ONE guided batch of B=64 clips per GPU
+(BASELINE.json configs[1]; per-GPU work fixed -> weak scaling, 8 GPUs = the 512 clips of configs[2]):
+discourse retrieval against a 4096-entry synthetic annotated DB, batched 50-step DDIM inversion of the
+E retrieved exemplars, 50 insertion-guided sampling steps  =  50 * (B + E) clip-steps.
+  value : the device-resident loops (K6 state + inversion + guided sampling), CUDA-event timed;
+  e2e   : MotionDiffusion.forward(**host_batch) -- pinned-host inputs, H2D, retrieval, codec, loops,
+          decode, D2H of the latents -- the call tools/visualize.py:200 makes.
+Also reported: the exact fp32 kNN sweep of configs[3] (queries/s, HBM roofline) under "knn".
+--impl reference times the reference's algorithm (oracle/ port: as-written op sequence, exemplars
+inverted one by one at B=1) on the host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC, UNIT = "guided_ddim_clip_steps_per_sec", "clip-steps/s"
+B_PER_GPU, N_DB, STEPS = 64, 4096, 50
+GFLOP_PER_CLIP_STEP = 3.348          # algorithmic, invariants hoisted
+GEMM_GFLOP_PER_CLIP_STEP = 3.291     # dense-GEMM share of the above
+GUIDANCE = [0] * 25 + list(range(25))   # decreasing_till_25 (tools/visualize.py:90-91)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["hbm_gbs"], d["bf16_tflops"], d.get("bf16_tflops_sustained", d["bf16_tflops"]), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.p = [], None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-i", str(index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.p.terminate()
+        rows = [r for r in self.rows if len(r) >= 6 and r[0].isdigit()]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(int(r[0]) for r in rows), "sm_max_mhz": int(rows[0][1]),
+                "reasons": reasons, "samples": len(rows)}
+
+
+def dist_env():
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    return rank, world, int(os.environ.get("LOCAL_RANK", 0))
+
+
+# ------------------------------------------------------------------------------------------------
+def make_batch(first_clip, n_clips):
+    """Synthetic query clips (pinned host memory) with discourse annotations, collated like
+    beatx_collate_fn; clip i depends only on its global index, so shards agree with the whole."""
+    from rag_gesture_b200 import synthetic as S
+    qs = S.SyntheticGestureDataset(first_clip + n_clips, seed=8)
+    batch = S.collate([qs[first_clip + i] for i in range(n_clips)])
+    for k, v in batch.items():
+        if torch.is_tensor(v):
+            batch[k] = v.pin_memory()
+        elif isinstance(v, list) and v and torch.is_tensor(v[0]):
+            batch[k] = [t.pin_memory() for t in v]
+    batch["retrieval_method"] = "discourse"
+    return batch
+
+
+def infer_kwargs():
+    return dict(use_inversion=True, outpaint=False, inversion_start_time=-1, insertion_guidance=True,
+                guidance_iters=list(GUIDANCE), guidance_lr=0.1)
+
+
+def h2d_bytes(batch):
+    n = 0
+    for v in batch.values():
+        if torch.is_tensor(v):
+            n += v.numel() * v.element_size()
+        elif isinstance(v, list) and v and torch.is_tensor(v[0]):
+            n += sum(t.numel() * t.element_size() for t in v)
+    return n
+
+
+def run_b200(args):
+    import torch.distributed as dist
+    import rag_gesture_b200 as R
+    from rag_gesture_b200 import config as C
+    from rag_gesture_b200 import synthetic as S
+    from rag_gesture_b200.engine import launch_count
+    rank, world, local = dist_env()
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch N>1 with torchrun)"
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device; there is no CPU fallback"
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    hbm_peak, tc_burst, tc_sus, peak_src = peaks()
+
+    cfg = C.model_cfg()
+    cfg["use_retrieval_for_test"] = True
+    arch = R.build_architecture(cfg, database=S.SyntheticGestureDataset(N_DB, seed=7))
+    arch.model.load_state_dict(S.synthetic_state_dict(0), strict=False)
+    arch = arch.to(dev).eval()
+    B = B_PER_GPU
+    batch = make_batch(rank * B, B)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        evs = []
+        for _ in range(steps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            evs.append((a, b))
+        barrier()
+        t = torch.tensor([sum(a.elapsed_time(b) for a, b in evs) / 1e3], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    # ---- value: device-resident loops -------------------------------------------------------------
+    gb = arch.prepare(**dict(batch, inference_kwargs=infer_kwargs()))
+    E = len(gb.jobs)
+    clip_steps = gb.clip_steps(STEPS)
+    sampler = ClockSampler(local)
+    out_holder = {}
+
+    def hot():
+        out_holder["x"] = arch.run_prepared(gb)
+    n0 = launch_count()
+    t_hot = timed(hot, args.steps, args.warmup)
+    launches = (launch_count() - n0) // (args.steps + args.warmup)
+    total_steps = torch.tensor([clip_steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(total_steps)
+    value = float(total_steps) * args.steps / t_hot
+
+    # ---- e2e: the public call with host buffers ---------------------------------------------------------
+    host_out = torch.empty(B, C.N_TOKENS, C.LATENT_DIM).pin_memory()
+
+    def e2e():
+        db = arch.model.database          # no retrieval-cache hits: every step ranks from scratch
+        for d in (db.test_indexes, db.test_dbounds, db.test_qbounds):
+            d.clear()
+        res = arch(**dict(batch, inference_kwargs=infer_kwargs()))
+        host_out.copy_(res["prev_latentout"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    t_e2e = timed(e2e, args.steps, max(1, args.warmup // 2))
+    clocks = sampler.stop()
+    e2e_value = float(total_steps) * args.steps / t_e2e
+
+    # ---- roofline of the dominant kernel family: the dense GEMMs of one denoiser evaluation --------------
+    roof = gemm_roofline(arch, B + E, dev, flush, tc_sus, peak_src)
+    knn = knn_bench(args, dev, rank, world, hbm_peak, peak_src, flush)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(1e3 * t_hot / args.steps, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[1]: 64 clips/GPU guided DDIM (discourse retrieval, inversion + "
+                                   "insertion guidance decreasing_till_25, len150@15fps)",
+                       "clips_per_gpu": B, "exemplars_rank0": E, "clip_steps_per_step_rank0": clip_steps,
+                       "db_entries": N_DB, "ddim_steps": STEPS, "precision": "fp32 (exact tier)",
+                       "l2": "256 MiB flush between timed iterations; fp32 weights (564 MB) exceed L2",
+                       "parallelism": f"clips sharded over {world} GPU(s), no collective in the loop"},
+            "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes(batch),
+                    "d2h_bytes_per_step": host_out.numel() * 4, "ms_per_step": round(1e3 * t_e2e / args.steps, 3)},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
+            "cpu_baseline": cpu_baseline(sample_seconds=args.cpu_seconds), "knn": knn,
+            "gflop_per_clip_step": GFLOP_PER_CLIP_STEP,
+            "achieved_tflops_loop": round(value * GFLOP_PER_CLIP_STEP / 1e3 / world, 2),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def gemm_roofline(arch, n_clips, dev, flush, tc_peak, peak_src):
+    """Every dense contraction of one denoiser evaluation, timed per shape through rg_op_linear
+    (same kernel, same shapes as inside rg_denoise) with CUDA events on the launching stream."""
+    from rag_gesture_b200 import ops
+    M = n_clips * 43
+    shapes = [("qkv", 1536, 512, 8), ("sa_proj", 512, 512, 8), ("ca_q", 1536, 512, 8), ("ca_proj", 512, 512, 24),
+              ("ca_mix", 512, 1536, 8), ("ffn1", 1024, 512, 8), ("ffn2", 512, 1024, 8), ("ffn_proj", 512, 512, 8),
+              ("embed/out", 512, 512, 2)]
+    tot_t, tot_f, per = 0.0, 0.0, {}
+    for name, N, K, count in shapes:
+        x, w, b = torch.randn(M, K, device=dev), torch.randn(N, K, device=dev), torch.randn(N, device=dev)
+        for _ in range(3):
+            ops.linear(x, w, b)
+        ts = []
+        for _ in range(5):
+            flush.zero_()
+            a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            ops.linear(x, w, b)
+            e.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(e) / 1e3)
+        t = statistics.median(ts)
+        per[name] = round(2.0 * M * N * K / t / 1e12, 2)
+        tot_t += t * count
+        tot_f += 2.0 * M * N * K * count
+    ach = tot_f / tot_t / 1e12
+    return {"bound": "tensor", "kernel": "gemm_tn_f32_kernel (fp32 FMA pipe; all GEMMs of one denoiser "
+            "evaluation, time-weighted)", "achieved": round(ach, 2), "peak": tc_peak, "unit": "TFLOP/s",
+            "frac": round(ach / tc_peak, 4), "traffic": None, "peak_source": f"{peak_src} bf16 sustained",
+            "rows": M, "per_shape_tflops": per,
+            "note": "exact fp32 tier runs on CUDA cores; the tcgen05 bf16 path is the next kernel"}
+
+
+def knn_bench(args, dev, rank, world, hbm_peak, peak_src, flush):
+    """configs[3] sweep point: 1M x 768 fp32 embeddings row-sharded over the ranks, top-8, Q=8
+    (one pass over the shard: the HBM-bound regime) through sharded_knn (all-gather + merge)."""
+    import torch.distributed as dist
+    from rag_gesture_b200.parallel import shard_range, sharded_knn
+    n_total, dim, k, Q = args.knn_n, 768, 8, 8
+    lo, hi = shard_range(n_total, rank, world)
+    g = torch.Generator(device=dev).manual_seed(42 + rank)
+    db = torch.nn.functional.normalize(torch.randn(hi - lo, dim, device=dev, generator=g), dim=1)
+    q = torch.nn.functional.normalize(torch.randn(Q, dim, device=dev, generator=torch.Generator(device=dev).manual_seed(43)), dim=1)
+    for _ in range(2):
+        sharded_knn(db, q, k, n_total)
+    ts = []
+    for _ in range(5):
+        flush.zero_()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        sharded_knn(db, q, k, n_total)
+        e.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(e) / 1e3], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ts.append(float(t))
+    t = statistics.median(ts)
+    gbs = (hi - lo) * dim * 4 / t / 1e9
+    return {"queries_per_sec": round(Q / t, 1), "n": n_total, "dim": dim, "k": k, "q": Q, "ms": round(t * 1e3, 3),
+            "roofline": {"bound": "hbm", "achieved": round(gbs, 1), "peak": hbm_peak, "unit": "GB/s",
+                         "frac": round(gbs / hbm_peak, 4), "peak_source": peak_src,
+                         "bytes_per_launch": (hi - lo) * dim * 4}}
+
+
+# ---- the reference's algorithm on the host cores ------------------------------------------------------
+def cpu_reference_sample(n_clips, n_exemplars, n_steps, threads):
+    """Bounded sample of the guided batch, executed like the reference: exemplars inverted one by one
+    at B=1 (diffusion_architecture.py:323-354), then guided sampling of the clips, `n_steps` levels
+    each.  Returns (clip_steps, seconds)."""
+    from oracle import denoiser as OD
+    from oracle import diffusion as ODF
+    from rag_gesture_b200 import config as C
+    from rag_gesture_b200 import synthetic as S
+    torch.set_num_threads(threads)
+    sd = cpu_reference_sample.sd = getattr(cpu_reference_sample, "sd", None) or S.synthetic_state_dict(0)
+    model, diff = OD.OracleDenoiser(sd), ODF.OracleDiffusion()
+    T, D = C.N_TOKENS, C.LATENT_DIM
+    cond = S.synthetic_conditions(n_clips + n_exemplars, seed=5)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        inv_rows = []
+        for e in range(n_exemplars):
+            c1 = {k: v[n_clips + e:n_clips + e + 1] for k, v in cond.items()}
+            kw = dict(xf_out=OD.encode_conditions(sd, c1["word"], c1["audio"], c1["speaker_ids"]),
+                      query_mask=S.query_masks(1), motion_mask=S.motion_mask(1))
+            img = S.synthetic_latents(1, seed=6 + e, scale=0.5)
+            for i in range(n_steps):
+                img = diff.ddim_reverse_sample(model, img, torch.tensor([i]), kw)
+            inv_rows.append(img)
+        cb = {k: v[:n_clips] for k, v in cond.items()}
+        kw = dict(xf_out=OD.encode_conditions(sd, cb["word"], cb["audio"], cb["speaker_ids"]),
+                  query_mask=S.query_masks(n_clips), motion_mask=S.motion_mask(n_clips))
+        in_seq = torch.zeros(n_clips, T, D)
+        for e in range(min(n_exemplars, n_clips)):
+            in_seq[e, 2:5] = inv_rows[e][0, 2:5]
+        img = torch.randn(n_clips, T, D)
+        for i in reversed(range(STEPS - n_steps, STEPS)):
+            img, _ = diff.ddim_sample(model, img, torch.tensor([i] * n_clips), kw, in_seq)
+    return (n_clips + n_exemplars) * n_steps, time.perf_counter() - t0
+
+
+def cpu_baseline(sample_seconds=15.0):
+    threads = os.cpu_count() or 1
+    cpu_reference_sample(2, 1, 1, threads)                      # warm-up (allocations, weights)
+    cs, dt = cpu_reference_sample(8, 4, 1, threads)             # calibrate: 12 clip-steps
+    n_steps = max(1, min(STEPS, int(sample_seconds / max(dt, 1e-3))))
+    cs, dt = cpu_reference_sample(8, 4, n_steps, threads)
+    return {"value": round(cs / dt, 2), "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"oracle port of the reference algorithm: 4 exemplars inverted at B=1 + 8 clips guided, "
+                      f"{n_steps} of 50 DDIM levels each = {cs} clip-steps in {dt:.1f} s"}
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    for _ in range(args.warmup):
+        cpu_reference_sample(2, 1, 1, threads)
+    cs_tot, t_tot = 0, 0.0
+    cs1, dt1 = cpu_reference_sample(8, 4, 1, threads)
+    n_steps = max(1, min(STEPS, int(args.cpu_seconds / max(dt1, 1e-3) / max(1, args.steps))))
+    for _ in range(args.steps):
+        cs, dt = cpu_reference_sample(8, 4, n_steps, threads)
+        cs_tot, t_tot = cs_tot + cs, t_tot + dt
+    v = cs_tot / t_tot
+    sample = (f"per step: 4 exemplars inverted at B=1 + 8 clips guided, {n_steps} of 50 DDIM levels "
+              f"(oracle port of the reference algorithm, torch CPU fp32, {threads} threads)")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": round(v, 2), "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * t_tot / args.steps, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1] guided DDIM (bounded sample of the same workload on host cores)"},
+        "cpu_baseline": {"value": round(v, 2), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": round(v, 2), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}), flush=True)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--knn-n", type=int, default=1_000_000)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -1,0 +1,221 @@
+"""MotionDiffusion: the orchestration of one guided batch, same constructor / forward(**batch) /
+result keys as mogen/models/architectures/diffusion_architecture.py:64-582 (inference branch).
+
+What changes is HOW the batch is executed on a B200:
+  * all exemplars of all clips are DDIM-inverted in ONE batched reverse loop (the reference runs one
+    50-step loop per exemplar at B=1 inside a double Python loop, :323-354); no denoiser op couples
+    clips, so the latents are the same (tests/test_gpu_denoiser.py::test_reverse_loop_batched_equals_single);
+  * cross-attention K/V state and the timestep table are computed once (engine K6/K7);
+  * the guided loop skips the provably dead gradient steps.
+The global-RNG draw order of the reference is preserved: GT encode, exemplar encodes
+(clip-major), start_noise, then per step randn_like(in_seq), randn_like(x).
+Training branch, DDPM sampling and the `visualize_inversion` debug outputs are out of scope.
+"""
+import copy
+
+import torch
+import torch.nn as nn
+
+from . import config as CFG
+from .diffusion import build_diffusion
+from .mogen_api import ARCHITECTURES, LOSSES, build_loss, build_submodule
+
+
+@LOSSES.register_module()
+class MSELoss(nn.Module):
+    """Constructor-compatible placeholder (mogen/models/losses/mse_loss.py:33-70): MotionDiffusion
+    builds `loss_recon` even for inference (diffusion_architecture.py:86); training is out of scope."""
+
+    def __init__(self, reduction="mean", loss_weight=1.0):
+        super().__init__()
+        assert reduction in (None, "none", "mean", "sum")
+        self.reduction, self.loss_weight = reduction or "none", loss_weight
+
+    def forward(self, *a, **k):
+        raise NotImplementedError("training losses are out of scope of rg_b200")
+
+
+@ARCHITECTURES.register_module()
+class MotionDiffusion(nn.Module):
+    def __init__(self, model=None, loss_recon=None, loss_gen=None, loss_contact=None, loss_laplace=None,
+                 diffusion_train=None, diffusion_test=None, init_cfg=None, inference_type="ddpm",
+                 genloss_acceleration_weight=True, genloss_hands_weight=2, genloss_smooth=True,
+                 body_part_lossweights=None, **kwargs):
+        super().__init__()
+        self.loss_recon = build_loss(loss_recon)
+        if loss_contact is not None or loss_gen is not None or loss_laplace is not None:
+            raise NotImplementedError("auxiliary training losses are out of scope of rg_b200")
+        self.model = build_submodule(copy.deepcopy(model), **kwargs)
+        self.diffusion_train = build_diffusion(diffusion_train) if diffusion_train is not None else None
+        self.diffusion_test = build_diffusion(diffusion_test)
+        self.inference_type = inference_type
+        self.body_part_lossweights = body_part_lossweights
+
+    @staticmethod
+    def _row_sets(T):
+        n = (T - 3) // 4
+        return (list(range(0, n)), list(range(n + 1, 2 * n + 1)), list(range(2 * n + 2, 3 * n + 2)),
+                list(range(3 * n + 3, T)))
+
+    def _scatter(self, kwargs):
+        """Host -> device move of the batch (what MMDataParallel.scatter does for the reference,
+        tools/visualize.py:146): tensors and lists of tensors, asynchronously from pinned memory."""
+        dev = self.model.out.weight.device
+
+        def mv(v):
+            if torch.is_tensor(v):
+                return v.to(dev, non_blocking=True)
+            if isinstance(v, list) and v and torch.is_tensor(v[0]):
+                return [t.to(dev, non_blocking=True) for t in v]
+            return v
+        return {k: mv(v) for k, v in kwargs.items()}
+
+    def forward(self, **kwargs):
+        """batch dict (beatx_collate_fn schema, host or device tensors) -> the same dict plus
+        retrieval_dict, prev_latentout [B,43,512] and the decoded pred_* poses (:479,572-577)."""
+        gb = self.prepare(**kwargs)
+        output = self.run_prepared(gb)
+        return self.finish(gb, output)
+
+    # ---- stage 1: host logic + codec + retrieval (everything that is not the denoising loops) ----
+    def prepare(self, **kwargs):
+        if self.training:
+            raise NotImplementedError("rg_b200 is inference-only; call model.eval()")
+        kwargs = self._scatter(kwargs)
+        motion_mask = kwargs["motion_mask"].float()
+        codec = self.model.gesture_rep_encoder
+        with torch.no_grad():
+            motion, motion_mask = codec.encode(kwargs["motion_upper"], kwargs["motion_lower"],
+                                               kwargs["motion_face"], kwargs["motion_hands"], kwargs["trans"],
+                                               kwargs["facial"], kwargs["contact"], motion_mask)
+        B, T = motion.shape[:2]
+        device = motion.device
+        # cross-attention is skipped on rows {(T-3)//4 * k}: NOT the separator rows
+        qmask = torch.ones_like(motion_mask)
+        qmask[:, [(T - 3) // 4, 2 * (T - 3) // 4, 3 * (T - 3) // 4]] = 0
+        query_masks = {c: qmask for c in CFG.CONDS}
+
+        ik = kwargs.get("inference_kwargs", {})
+        gb = GuidedBatch()
+        gb.use_outpaint = ik.pop("outpaint", False)
+        gb.use_inversion = ik.pop("use_inversion", False)
+        gb.inversion_start_time = ik.pop("inversion_start_time", -1)
+        if ik.pop("visualize_inversion", False):
+            raise NotImplementedError("visualize_inversion debug outputs are out of scope of rg_b200")
+        gb.use_guidance = ik.pop("insertion_guidance", False)
+        gb.guidance_iters = ik.pop("guidance_iters", [10] * 50)
+        gb.guidance_lr = ik.pop("guidance_lr", 0.1)
+        gb.use_prev = ik.pop("use_prev_latent", False)
+        gb.prev_latent = ik.pop("prev_latent", None)
+        gb.extra = ik
+        if gb.use_prev:
+            assert not gb.use_outpaint
+        if gb.use_outpaint:
+            assert not gb.use_inversion and not gb.use_guidance
+        if gb.use_guidance:
+            assert not gb.use_outpaint and gb.use_inversion
+        if self.inference_type != "ddim":
+            raise NotImplementedError("rg_b200 implements inference_type='ddim' only")
+
+        kwargs.update({"motion_mask": motion_mask, "text": kwargs["word"], "raw_text": kwargs["raw_word"],
+                       "text_times": kwargs["text_segments"]})
+        with torch.no_grad():
+            model_kwargs = self.model.get_precompute_condition(device=device, **kwargs)
+        model_kwargs["query_mask"] = query_masks
+        model_kwargs["motion_mask"] = motion_mask
+        model_kwargs["sample_idx"] = kwargs.get("sample_idx", None)
+        retrieval_dict = model_kwargs["re_dict"]
+        kwargs["retrieval_dict"] = copy.deepcopy(retrieval_dict)
+        gb.results, gb.model_kwargs, gb.shape, gb.device = kwargs, model_kwargs, (B, T, codec.vae_latent_dim), device
+
+        if gb.use_outpaint:
+            seq = retrieval_dict["raw_motion_latents"]
+            assert seq.shape[1] == 1
+            gb.outpaint_seq = seq.squeeze(1)
+        if gb.use_prev and gb.prev_latent is not None:
+            upper, hands, face, lower = self._row_sets(T)
+            prev = gb.prev_latent.to(device)
+            masked = torch.zeros_like(prev)
+            for rows in (upper, hands, face, lower):       # last token of each part -> its first token
+                masked[:, rows[0]] = prev[:, rows[-1]]
+            gb.prev_latent = masked
+
+        # all exemplars of all clips, in the reference's visiting order (clip-major, dict order)
+        if gb.use_inversion:
+            lat = retrieval_dict["retr_uncropped_latents"]
+            gb.jobs = [(b, q) for b, lats in enumerate(lat) for q in lats.keys()]
+            if gb.jobs:
+                cat = lambda key: torch.cat([lat[b][q][key] for b, q in gb.jobs], 0).to(device)
+                gb.ex = {k: cat(k) for k in ("retr_text", "retr_audio", "retr_spkid", "retr_motion_mask",
+                                             "retr_motion_latent")}
+                clip_of = torch.tensor([b for b, _ in gb.jobs], device=device)
+                gb.ex_query_mask = {c: m[clip_of] for c, m in query_masks.items()}
+                gb.windows = [(retrieval_dict["retr_startends"][b][q], retrieval_dict["query_startends"][b][q])
+                              for b, q in gb.jobs]
+        return gb
+
+    # ---- stage 2: the hot path proper, device-resident inputs -> output latents ---------------------
+    def run_prepared(self, gb):
+        """K6 state for the B clips and E exemplars, ONE batched 50-step inversion of the exemplars,
+        window insertion, 50 guided (or plain) sampling steps: 50 * (B + E) clip-steps."""
+        diff, (B, T, D), device = self.diffusion_test, gb.shape, gb.device
+        n = (T - 3) // 4
+        self.model._state_cache = (None, None)
+        start_noise, inv_per_t = None, None
+        if gb.use_inversion:
+            start_noise = diff._randn((B, T, D), device)
+            if gb.use_guidance:
+                inv_per_t = torch.zeros(diff.num_timesteps, B, T, D, device=device)
+            if gb.jobs:
+                with torch.no_grad():
+                    ex_kwargs = self.model.get_precompute_condition(
+                        device=device, text=gb.ex["retr_text"], audio=gb.ex["retr_audio"],
+                        speaker_ids=gb.ex["retr_spkid"], re_dict=1)
+                ex_kwargs["query_mask"] = gb.ex_query_mask
+                ex_kwargs["motion_mask"] = gb.ex["retr_motion_mask"]
+                inv = diff.ddim_reverse_sample_loop(self.model, start_img=gb.ex["retr_motion_latent"],
+                                                    clip_denoised=False, progress=False,
+                                                    model_kwargs=ex_kwargs, eta=0,
+                                                    return_all_timesteps=True, **gb.extra)
+                inv = torch.stack(inv, 0)                   # [steps, E, T, D], clean -> noisy
+                for e, ((b, _), ((r0, r1), (q0, q1))) in enumerate(zip(gb.jobs, gb.windows)):
+                    assert r1 - r0 == q1 - q0
+                    for o in (0, n + 1):                    # upper body and hands only (:394-407)
+                        start_noise[b, o + q0:o + q1] = inv[gb.inversion_start_time, e, o + r0:o + r1]
+                        if gb.use_guidance:
+                            inv_per_t[:, b, o + q0:o + q1] = inv[:, e, o + r0:o + r1]
+            if gb.use_guidance and gb.use_prev and gb.prev_latent is not None:
+                inv_per_t[:, :, [0, n + 1, 2 * n + 2, 3 * n + 3], :] = 0
+        self.model._state_cache = (None, None)
+        if gb.use_guidance:
+            output = diff.ddim_guided_sample_loop(
+                self.model, (B, T, D), noise=start_noise if gb.use_inversion else None, clip_denoised=False,
+                progress=False, model_kwargs=gb.model_kwargs, eta=0,
+                in_seq=gb.prev_latent if gb.use_prev else None, guidance_iters=gb.guidance_iters,
+                inverted_latent_list=inv_per_t, guidance_lr=gb.guidance_lr, **gb.extra)
+        else:
+            in_seq = gb.prev_latent if gb.use_prev else (gb.outpaint_seq if gb.use_outpaint else None)
+            output = diff.ddim_sample_loop(
+                self.model, (B, T, D), noise=start_noise if gb.use_inversion else None, clip_denoised=False,
+                progress=False, model_kwargs=gb.model_kwargs, eta=0, in_seq=in_seq, **gb.extra)
+        if getattr(self.model, "post_process") is not None:
+            output = self.model.post_process(output)
+        return output
+
+    # ---- stage 3: decode ---------------------------------------------------------------------------------
+    def finish(self, gb, output):
+        results = gb.results
+        results["prev_latentout"] = output
+        with torch.no_grad():
+            up, lo, fa, ha, tr, ex, _ = self.model.gesture_rep_encoder.decode(output)
+        results.update(pred_upper=up, pred_lower=lo, pred_facepose=fa, pred_hands=ha, pred_transl=tr, pred_exps=ex)
+        return results
+
+
+class GuidedBatch:
+    """Device-resident inputs of one guided batch between MotionDiffusion.prepare and run_prepared."""
+    jobs, ex, ex_query_mask, windows, outpaint_seq, prev_latent = (), None, None, (), None, None
+
+    def clip_steps(self, num_timesteps):
+        """Work of the batch in the metric's unit: 50 * (B + E)."""
+        return num_timesteps * (self.shape[0] + len(self.jobs))

@@ -1,0 +1,432 @@
+"""Exemplar retrieval: RetrievalDatabase with the reference's hooks (SURVEY 8b "Retrieval hooks").
+
+Mirrors mogen/models/transformers/raggesture.py:157-884 (RetrievalDatabase: in-RAM annotation dicts,
+`retrieve`, `forward` = window placement + exemplar encode) and rag/discourse_retrieval.py +
+rag/utils.py (rule scores, score tiers, text-similarity ranking inside a tier).
+
+B200-first differences in HOW, not WHAT:
+  * the text features of all DB entries live on the GPU as one padded [N, Lmax, 768] block; ranking a
+    tier is one rg_text_similarity launch over the tier's row indices + one top-k launch, instead of
+    a Python loop of torch.mm over every candidate (rag/utils.py:107-129);
+  * rule scoring walks an inverted index sense -> DB rows instead of every DB sample per connective
+    (rag/discourse_retrieval.py:86), producing the same float64 scores in the same operation order,
+    hence the same score tiers;
+  * the on-disk LMDB+pyarrow cache (raggesture.py:90-154) is out of scope: dicts are built from the
+    dataset in memory, keyed and ordered like LMDB returns them (ASCII-sorted sample names).
+`retrieval_method` keeps the reference's keys; "gesture_type" and "llm" raise.
+"""
+import copy
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+def _clean(s):
+    return "".join(ch for ch in str(s) if ch.isalnum() or ch.isspace())
+
+
+def map_conns_to_prominence(conn_list, prominence_list):
+    """For each connective: (cleaned connective, prominence) of the matching word(s) of the
+    prosodic-prominence list, averaged for multi-word connectives, or None (rag/utils.py:171-228)."""
+    hits = {}
+    open_ = [True] * len(conn_list)
+    cleaned = [_clean(c) for c in conn_list]
+    for dp in prominence_list:
+        w = _clean(dp[0])
+        for i, sc in enumerate(cleaned):
+            hits.setdefault(i, [])          # a connective is "seen" once any word scans past it
+            if not open_[i]:
+                continue
+            parts = sc.split()
+            if w == sc or w in parts:
+                hits[i].append((sc, dp[3]))
+                if w == sc or w == parts[-1]:
+                    open_[i] = False
+                break
+    out = {}
+    for i, h in hits.items():
+        if len(h) > 1:
+            assert h[0][0] == cleaned[i]
+            out[i] = (conn_list[i], sum(x[1] for x in h) / len(h))
+        else:
+            out[i] = h[0] if h else None
+    # the reference stops in breakpoint() here (rag/utils.py:225-227)
+    assert len(out) == len(conn_list), "a connective was never scanned against the prominence list"
+    return out
+
+
+class TextSimilarityIndex:
+    """Device-resident padded text features of the DB + the two kernels that rank against them."""
+
+    def __init__(self, names, feats, device):
+        self.names = list(names)
+        self.row = {n: i for i, n in enumerate(self.names)}
+        self.device = torch.device(device)
+        self.dim = feats[0].shape[1] if feats else 768
+        self.max_len = max((f.shape[0] for f in feats), default=1)
+        db = torch.zeros(len(feats), self.max_len, self.dim)
+        for i, f in enumerate(feats):
+            db[i, :f.shape[0]] = f
+        self.db = db.to(self.device)
+        self.len = torch.tensor([f.shape[0] for f in feats], dtype=torch.int32, device=self.device)
+
+    def scores(self, query, rows=None):
+        """score[j] = mean(diag(Q D_j^T)) over min(Tq, Td) aligned tokens (rag/utils.py:107-118)."""
+        lib = _lib.load()
+        q = query.to(device=self.device, dtype=torch.float32).contiguous()
+        sub = None if rows is None else torch.as_tensor(rows, dtype=torch.int32, device=self.device)
+        n_out = len(self.names) if sub is None else sub.numel()
+        out = torch.empty(n_out, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(lib.rg_text_similarity(_lib.ptr(self.db), _lib.ptr(self.len), len(self.names),
+                                              self.max_len, self.dim, _lib.ptr(q), q.shape[0],
+                                              _lib.ptr(sub), n_out, _lib.ptr(out), _lib.stream_ptr()))
+        return out
+
+    def rank(self, query, rows, k):
+        """First k of `rows` ordered by similarity, descending, ties in given order (the stable
+        `sorted(..., reverse=True)` of rag/utils.py:127-129).  rows: list of DB row indices."""
+        if not rows:
+            return []
+        k = min(k, len(rows))
+        sc = self.scores(query, rows).view(1, 1, -1)
+        order = []
+        lib = _lib.load()
+        # top-k of one candidate list == merge of ceil(n/32) "parts" of 32 candidates
+        n = sc.shape[-1]
+        pad = (-n) % 32
+        idx = torch.arange(n + pad, dtype=torch.int64, device=self.device)
+        if pad:
+            sc = torch.cat([sc.view(-1), torch.full((pad,), float("-inf"), device=self.device)])
+            idx[n:] = -1
+        parts = (n + pad) // 32
+        out_i = torch.empty(32, dtype=torch.int64, device=self.device)
+        out_s = torch.empty(32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(lib.rg_knn_merge(_lib.ptr(idx.contiguous()), _lib.ptr(sc.contiguous().view(-1)),
+                                        parts, 1, 32, _lib.ptr(out_i), _lib.ptr(out_s), _lib.stream_ptr()))
+        for j in out_i[:k].tolist():
+            order.append(rows[j])
+        return order
+
+
+def discourse_retrieval(text, discourse, prominence, speaker_id, db_idx_2_sense, db_idx_2_discbounds,
+                        db_idx_2_prominence, encoded_text, text_feat_cache, index=None, sense_index=None):
+    """Rule-based discourse retrieval, same arguments and return triple as
+    rag/discourse_retrieval.py:8-316:  ({q: [sample names]}, {q: {name: (conn, sense, start, end)}},
+    {q: (conn_lower, sense, conn_start, conn_end)}).  `index` (TextSimilarityIndex) and `sense_index`
+    are supplied by RetrievalDatabase; without them they are built on the fly from the dicts."""
+    sample_indexes, d_bounds = {}, {}
+    if len(discourse) == 0:
+        return sample_indexes, d_bounds, {}
+    if index is None:
+        names = list(text_feat_cache.keys())
+        index = TextSimilarityIndex(names, [text_feat_cache[n][0] for n in names], encoded_text.device
+                                    if encoded_text.is_cuda else "cuda")
+    if sense_index is None:
+        sense_index = build_sense_index(db_idx_2_sense)
+    senses = [d[1] for d in discourse]
+    conns = [d[0] for d in discourse]
+    query_bounds = {i: (d[0].lower(), d[1], d[6], d[7]) for i, d in enumerate(discourse)}
+    q_prom = map_conns_to_prominence(conns, prominence)
+    for i, cv in q_prom.items():
+        if cv is not None:
+            assert cv[0] == _clean(conns[i]), f"{cv[0]} != {_clean(conns[i])}"
+            q_prom[i] = (senses[i], cv[1])
+
+    for qi, (sense, conn) in enumerate(zip(senses, conns)):
+        scored, bounds_of = [], {}
+        for name in sense_index.get(sense, ()):            # DB order; only samples holding the sense
+            entry = db_idx_2_sense[name]
+            spk, disco = entry[0], entry[1:]
+            s_senses = [d[0] for d in disco]
+            s_conns = [d[1] for d in disco]
+            s_prom = db_idx_2_prominence[name]
+            assert len(s_prom) == len(s_senses), f"{len(s_prom)} != {len(s_senses)}"
+            rel = [j for j, s in enumerate(s_senses) if s == sense]
+            score = 2
+            top, chosen = rel[0], False
+            rel_conns = [s_conns[j] for j in rel]
+            if conn in rel_conns:
+                score += 4
+                top, chosen = rel[rel_conns.index(conn)], True
+            if spk == speaker_id:
+                score += 3
+            acc, cnt, diffs = 0, 0, {}
+            for j in rel:
+                if s_prom[j] is None or q_prom[qi] is None:
+                    continue
+                d = abs(s_prom[j][1] - q_prom[qi][1])
+                diffs[j] = d
+                acc += 4 / (1 + 2 * d)
+                cnt += 1
+            if cnt > 0:
+                score += acc / cnt
+                best = sorted(diffs, key=diffs.get)[0]
+                if top != best and not chosen:
+                    top = best
+            scored.append((name, score))
+            bounds_of[name] = db_idx_2_discbounds[name][top]
+        # equal-score tiers, best first; a tier with several members is ordered by text similarity
+        tiers = {}
+        for name, score in sorted(scored, key=lambda t: t[1], reverse=True):
+            tiers.setdefault(score, []).append(name)
+        ranked = []
+        for score in sorted(tiers, reverse=True):
+            tier = tiers[score]
+            if len(tier) > 1:
+                tier = [index.names[r] for r in index.rank(encoded_text, [index.row[n] for n in tier], len(tier))] \
+                    if len(tier) <= 32 else _rank_long_tier(index, encoded_text, tier)
+            ranked += tier
+            if len(ranked) >= 10:
+                break
+        sample_indexes[qi] = ranked[:10]
+        d_bounds[qi] = {}
+        for name in ranked[:10]:
+            b = bounds_of[name]
+            d_bounds[qi][name] = (b[1], b[0], round(b[4], 3), round(b[5], 3))
+    assert len(d_bounds) == len(sample_indexes) == len(query_bounds)
+    return sample_indexes, d_bounds, query_bounds
+
+
+def _rank_long_tier(index, query, tier):
+    """Tiers longer than the kernel's k<=32: only the first 32 by similarity can reach the top 10,
+    the rest keep tier order behind them (they are cut off by [:10] in the caller anyway)."""
+    rows = [index.row[n] for n in tier]
+    head = index.rank(query, rows, 32)
+    head_set = set(head)
+    return [index.names[r] for r in head] + [n for n in tier if index.row[n] not in head_set]
+
+
+def build_sense_index(db_idx_2_sense):
+    out = {}
+    for name, entry in db_idx_2_sense.items():
+        for s in dict.fromkeys(d[0] for d in entry[1:]):
+            out.setdefault(s, []).append(name)
+    return out
+
+
+def _not_supported(name):
+    def f(**kwargs):
+        raise NotImplementedError(f"retrieval_method '{name}' is out of scope of rg_b200 (SURVEY 2 row 10)")
+    return f
+
+
+class RetrievalDatabase(nn.Module):
+    def __init__(self, dataset, num_retrieval=None, topk=None, latent_dim=512, text_latent_dim=768,
+                 max_seq_len=150, motion_fps=15, motion_framechunksize=15,
+                 stratified_db_creation=False, stratification_interval=15, device=None, **unused):
+        super().__init__()
+        self.num_retrieval, self.topk = num_retrieval, topk
+        self.latent_dim, self.text_latent_dim = latent_dim, text_latent_dim
+        self.max_seq_len, self.motion_fps, self.motion_framechunksize = max_seq_len, motion_fps, motion_framechunksize
+        self.dataset = dataset
+        self.retrieval_method = {"discourse": self._discourse, "gesture_type": _not_supported("gesture_type"),
+                                 "llm": _not_supported("llm")}
+        self.train_indexes, self.test_indexes = {}, {}
+        self.train_dbounds, self.test_dbounds = {}, {}
+        self.train_qbounds, self.test_qbounds = {}, {}
+        rows = {}
+        fast = hasattr(dataset, "annotations") and hasattr(dataset, "text_feature")
+        for i in range(len(dataset)):
+            name = dataset.names[i] if fast else None
+            smp = None
+            if not fast:
+                smp = dataset[i]
+                name = smp["sample_name"]
+            if stratified_db_creation and int(name.split("/")[1]) % stratification_interval != 0:
+                continue
+            if fast:
+                spk, disc, prom, gest, _ = dataset.annotations(i)
+                feat = dataset.text_feature(i)
+            else:
+                spk, disc, prom, gest = int(smp["speaker_id"][0].item()), smp["discourse"], smp["prominence"], smp["gesture_labels"]
+                feat = smp["text_feature"]
+            rows[name] = (feat, spk, disc, prom, gest)
+        self.idx_2_text, self.idx_2_sense, self.idx_2_discbounds = {}, {}, {}
+        self.idx_2_gesture_labels, self.idx_2_prominence, self.idx_2_gestprom = {}, {}, {}
+        for name in sorted(rows, key=lambda s: s.encode("ascii")):      # LMDB cursor order
+            feat, spk, disc, prom, gest = rows[name]
+            self.idx_2_text[name] = (feat, spk)
+            self.idx_2_sense[name] = [spk] + [(d[1], d[0]) for d in disc]
+            self.idx_2_discbounds[name] = [(d[1], d[0], d[4], d[5], d[6], d[7]) for d in disc]
+            self.idx_2_gesture_labels[name] = [spk] + list(gest)
+            self.idx_2_prominence[name] = map_conns_to_prominence([d[0] for d in disc], prom)
+            self.idx_2_gestprom[name] = map_conns_to_prominence([g["word"] for g in gest], prom)
+        self.sample_names = {i: s for i, s in enumerate(self.idx_2_text.keys())}
+        self._sense_index = build_sense_index(self.idx_2_sense)
+        self._index, self._index_device = None, device
+
+    def text_index(self, device):
+        if self._index is None or torch.device(self._index.device).type != torch.device(device).type:
+            names = list(self.idx_2_text.keys())
+            self._index = TextSimilarityIndex(names, [self.idx_2_text[n][0] for n in names], device)
+        return self._index
+
+    def _discourse(self, **kw):
+        dev = kw["encoded_text"].device if kw["encoded_text"].is_cuda else (self._index_device or "cuda")
+        return discourse_retrieval(index=self.text_index(dev), sense_index=self._sense_index, **kw)
+
+    # raggesture.py:313-477, inference branches only
+    def retrieve(self, retr_method, text, text_features, audio, discourse, gesture_labels, text_times,
+                 prominence, speaker_id, idx=None):
+        assert retr_method in ["gesture_type", "discourse", "llm"]
+        if self.training:
+            raise NotImplementedError("Not released for training for retrieval")
+        if idx in self.test_indexes and idx is not None:
+            hit = self.test_indexes[idx]
+            if retr_method not in hit:
+                print(f"WARNUNG: Retrieval method {retr_method} not found for idx {idx}")
+                return {}, {}, {}
+            sample_indexes = hit[retr_method]
+            # the reference reads the bounds from the wrong dict here (raggesture.py:365, SURVEY
+            # quirk 7); the cache is keyed identically, so serve the right one
+            sample_bounds, query_bounds = self.test_dbounds[idx][retr_method], self.test_qbounds[idx][retr_method]
+        else:
+            args = {"text": text, "speaker_id": speaker_id, "encoded_text": text_features,
+                    "text_feat_cache": self.idx_2_text}
+            if retr_method == "discourse":
+                args.update(discourse=discourse, prominence=prominence, db_idx_2_sense=self.idx_2_sense,
+                            db_idx_2_discbounds=self.idx_2_discbounds, db_idx_2_prominence=self.idx_2_prominence)
+            elif retr_method == "gesture_type":
+                args.update(gesture_labels=gesture_labels, db_idx_2_gesture_labels=self.idx_2_gesture_labels)
+            else:
+                args.update(text_times=text_times, db_idx_2_gesture_labels=self.idx_2_gesture_labels,
+                            prominence=prominence, db_idx_2_prominence=self.idx_2_gestprom)
+            sample_indexes, sample_bounds, query_bounds = self.retrieval_method[retr_method](**args)
+            for d in (self.train_indexes, self.train_dbounds, self.train_qbounds):
+                d[idx] = {}
+            self.test_indexes[idx] = {retr_method: sample_indexes}
+            self.test_dbounds[idx] = {retr_method: sample_bounds}
+            self.test_qbounds[idx] = {retr_method: query_bounds}
+        data = {q: [s for s in names if s != idx][: self.num_retrieval] for q, names in sample_indexes.items()}
+        return data, sample_bounds, query_bounds
+
+    def place_window(self, query_bound, retr_bound, retrieval_method, prev_end):
+        """Exemplar seconds -> (exemplar chunk window, query chunk window) or None (SURVEY App. D;
+        raggesture.py:595-733).  Pure integer/float host logic."""
+        fps, cs, L = self.motion_fps, self.motion_framechunksize, self.max_seq_len
+        n = L // cs
+        _, _, q_start, q_end = query_bound
+        q_start = int(max(0, q_start) * fps)
+        q_end = int(min(L / fps, q_end) * fps)
+        assert q_start // cs < q_end // cs + 1
+        r_start, r_end = retr_bound[2], retr_bound[3]
+        if retrieval_method in ("gesture_type", "llm") and (r_end - r_start) > 0.9:
+            r_start, r_end = max(0, r_start - 0.2), min(L / fps, r_end + 0.1)
+        else:
+            r_start, r_end = max(0, r_start - 0.666), min(L / fps, r_end + 0.333)
+        r_start, r_end = int(r_start * fps), int(r_end * fps)
+        if r_start == r_end:
+            return None
+        if r_end == L:
+            r_end, r_start = L - 1, max(0, r_start - 1)
+        r0, r1 = r_start // cs, r_end // cs + 1
+        assert r0 < r1
+        mid = ((q_start + q_end) // 2) // cs
+        ln = r1 - r0
+        half = ln // 2
+        if ln == 1:
+            s, e = mid, mid + 1
+        elif ln == 2:
+            s, e = mid, mid + half + 1
+        elif ln % 2 == 1:
+            s, e = mid - half - 1, mid + half
+        else:
+            s, e = mid - half, mid + half
+        if s < 0:
+            s, e = 0, ln
+        if e > n:
+            s, e = s - (e - n), n
+        if s < prev_end:
+            s = prev_end
+            e = s + ln
+            if e > n:
+                e = n
+                ln = e - s
+                if ln <= 0:
+                    return None
+                r1 = r0 + ln
+        return (r0, r1), (s, e)
+
+    # raggesture.py:479-884
+    def forward(self, conditions, lengths, device, idx=None, retrieval_method="gesture_type",
+                gesture_rep_encoder=None):
+        B = len(conditions["text"])
+        T = self.max_seq_len // self.motion_framechunksize * 4 + 3
+        n, cs = (T - 3) // 4, self.motion_framechunksize
+        ref = self.dataset[0]
+        motions, raw_m, raw_t, raw_f = [], [], [], []
+        all_idx, all_t2w, all_rse, all_qse, all_lat = [], [], [], [], []
+        for b in range(B):
+            retr_indexes, retr_bounds, query_bounds = self.retrieve(
+                retrieval_method, text=conditions["text"][b], text_features=conditions["text_features"][b],
+                audio=conditions["audio"][b], discourse=conditions["discourse"][b],
+                gesture_labels=conditions["gesture_labels"][b], text_times=conditions["text_times"][b],
+                prominence=conditions["prominence"][b], speaker_id=conditions["speaker_ids"][b, 0].item(),
+                idx=idx[b] if idx is not None else None)
+            all_idx.append(retr_indexes)
+            zero_motion = torch.zeros(T, self.latent_dim, device=device)
+            z_raw = torch.zeros_like(ref["motion"]).to(device)
+            z_trans = torch.zeros_like(ref["trans"]).to(device)
+            z_facial = torch.zeros_like(ref["facial"]).to(device)
+            t2w, rse, qse, lat = {}, {}, {}, {}
+            prev_end = -1
+            for q, names in retr_indexes.items():
+                if len(names) == 0 or q not in query_bounds:
+                    continue
+                qb = query_bounds[q]
+                if qb[2] > qb[3]:
+                    continue
+                assert len(names) == self.num_retrieval == 1
+                name = names[0]
+                smp = self.dataset[name]
+                assert gesture_rep_encoder is not None
+                u = lambda k: smp[k].unsqueeze(0).to(device)
+                latent, lat_mask = gesture_rep_encoder.encode(
+                    u("motion_upper"), u("motion_lower"), u("motion_face"), u("motion_hands"), u("trans"),
+                    u("facial"), u("contact"), u("motion_mask"))
+                latent = latent.squeeze(0)
+                rb = retr_bounds[q][name]
+                t2w[q] = (qb[0], qb[1], rb[0], rb[1])
+                win = self.place_window(qb, rb, retrieval_method, prev_end)
+                if win is None:
+                    continue
+                (r0, r1), (s, e) = win
+                prev_end = e
+                lat[q] = {"retr_motion_latent": latent.unsqueeze(0), "retr_text": u("word"), "retr_audio": u("audio"),
+                          "retr_spkid": u("speaker_id"), "retr_motion_mask": lat_mask}
+                rse[q], qse[q] = (r0, r1), (s, e)
+                for part in range(4):
+                    o = part * (n + 1)
+                    zero_motion[o + s:o + e] = latent[o + r0:o + r1]
+                z_raw[s * cs:e * cs] = smp["motion"].to(device)[r0 * cs:r1 * cs]
+                z_trans[s * cs:e * cs] = smp["trans"].to(device)[r0 * cs:r1 * cs]
+                z_facial[s * cs:e * cs] = smp["facial"].to(device)[r0 * cs:r1 * cs]
+            motions.append(zero_motion); raw_m.append(z_raw); raw_t.append(z_trans); raw_f.append(z_facial)
+            all_t2w.append(t2w); all_rse.append(rse); all_qse.append(qse); all_lat.append(lat)
+        all_motions = torch.stack(motions, 0)
+        names_out = []
+        for b in range(B):
+            names_out.append({})
+            for q, nm in all_idx[b].items():
+                if q in all_t2w[b]:
+                    names_out[-1][all_t2w[b][q][0]] = self.dataset[nm[0]]["sample_name"]
+        src_mask = (all_motions != 0).any(dim=-1).to(torch.int)
+        raw_latent_mask = src_mask.clone()
+        raw_latents = all_motions.clone()
+        dead = list(range(2 * n + 2, 3 * n + 2)) + list(range(3 * n + 3, T))     # face + lower/transl rows
+        src_mask[:, dead] = 0
+        raw_latents[:, dead, :] = 0
+        R = self.num_retrieval
+        return dict(
+            re_text=None, re_motion=None, re_mask=src_mask,
+            raw_motion_latents=raw_latents.view(B, R, T, -1).contiguous(),
+            raw_motion=torch.stack(raw_m, 0).view(B, R, self.max_seq_len, -1).contiguous(),
+            raw_trans=torch.stack(raw_t, 0).view(B, R, self.max_seq_len, -1).contiguous(),
+            raw_facial=torch.stack(raw_f, 0).view(B, R, self.max_seq_len, 100).contiguous(),
+            raw_sample_names=names_out, raw_type2words=all_t2w, raw_latent_mask=raw_latent_mask,
+            retr_startends=all_rse, query_startends=all_qse, retr_uncropped_latents=all_lat)

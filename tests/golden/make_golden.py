@@ -180,7 +180,141 @@ def gen_loops(ns):
          final_prev_latent_b1=final_prev)
 
 
-GROUPS = {"schedule": gen_schedule, "denoiser": gen_denoiser, "loops": gen_loops}
+def make_ref_db_class(ns):
+    """The reference RetrievalDatabase with only __init__ replaced: the in-RAM dicts it normally
+    loads from its LMDB cache (raggesture.py:244-303) are filled from the synthetic dataset, in LMDB
+    cursor order; retrieve() / forward() are the reference's own code."""
+    class RefDB(ns.rg.RetrievalDatabase):
+        def __init__(self, dataset=None, num_retrieval=1, topk=2, latent_dim=512, text_latent_dim=768,
+                     max_seq_len=150, motion_fps=15, motion_framechunksize=15, **kw):
+            torch.nn.Module.__init__(self)
+            self.num_retrieval, self.topk, self.latent_dim = num_retrieval, topk, latent_dim
+            self.text_latent_dim, self.max_seq_len = text_latent_dim, max_seq_len
+            self.motion_fps, self.motion_framechunksize = motion_fps, motion_framechunksize
+            self.retrieval_method = {"discourse": ns.discourse.discourse_retrieval}
+            self.train_indexes, self.test_indexes = {}, {}
+            self.train_dbounds, self.test_dbounds = {}, {}
+            self.train_qbounds, self.test_qbounds = {}, {}
+            self.dataset = dataset
+            d = {k: {} for k in ("text", "sense", "discbounds", "gesture_labels", "prominence", "gestprom")}
+            for i in sorted(range(len(dataset)), key=lambda i: dataset.names[i].encode("ascii")):
+                spk, disc, prom, gest, _ = dataset.annotations(i)
+                name = dataset.names[i]
+                d["text"][name] = [dataset.text_feature(i), spk]
+                d["sense"][name] = [spk] + [(x[1], x[0]) for x in disc]
+                d["discbounds"][name] = [(x[1], x[0], x[4], x[5], x[6], x[7]) for x in disc]
+                d["gesture_labels"][name] = [spk] + list(gest)
+                d["prominence"][name] = ns.rag_utils.map_conns_to_prominence([x[0] for x in disc], prom)
+                d["gestprom"][name] = ns.rag_utils.map_conns_to_prominence([g["word"] for g in gest], prom)
+            for k, v in d.items():
+                setattr(self, "idx_2_" + k, v)
+    return RefDB
+
+
+def _jsonable(o):
+    if isinstance(o, dict):
+        return {str(k): _jsonable(v) for k, v in o.items()}
+    if isinstance(o, (list, tuple)):
+        return [_jsonable(v) for v in o]
+    if isinstance(o, (np.floating, np.integer)):
+        return o.item()
+    return o
+
+
+N_DB, N_QUERY = 1200, 48
+
+
+def gen_retrieval(ns):
+    """discourse_retrieval + sort_sidx_by_textsimilarity + RetrievalDatabase.forward window placement
+    of the reference on the synthetic annotated dataset (queries = samples from a second dataset)."""
+    import json
+    from rag_gesture_b200.codec import SyntheticGestureCodec
+    ds = S.SyntheticGestureDataset(N_DB, seed=7)
+    qs = S.SyntheticGestureDataset(N_QUERY, seed=8)
+    db = make_ref_db_class(ns)(dataset=ds, **C.retrieval_cfg()).eval()
+    out = {"queries": []}
+    for i in range(N_QUERY):
+        spk, disc, prom, gest, _ = qs.annotations(i)
+        idx, bounds, qb = ns.discourse.discourse_retrieval(
+            text="", discourse=disc, prominence=prom, speaker_id=spk, db_idx_2_sense=db.idx_2_sense,
+            db_idx_2_discbounds=db.idx_2_discbounds, db_idx_2_prominence=db.idx_2_prominence,
+            encoded_text=qs.text_feature(i), text_feat_cache=db.idx_2_text)
+        out["queries"].append(_jsonable({"idx": idx, "bounds": bounds, "qbounds": qb}))
+    names = list(db.idx_2_text.keys())[:200]
+    out["sim_order"] = ns.rag_utils.sort_sidx_by_textsimilarity(names, "", qs.text_feature(0), db.idx_2_text)
+    # window placement through the reference forward (codec: synthetic; RNG seeded)
+    codec = SyntheticGestureCodec(C.denoiser_cfg()["vae_cfg"])
+    batch = S.collate([qs[i] for i in range(N_QUERY)])
+    cond = dict(text=batch["raw_word"], audio=batch["raw_audio"], text_enc=batch["word"],
+                text_features=batch["text_features"], audio_enc=batch["audio"], discourse=batch["discourse"],
+                prominence=batch["prominence"], speaker_ids=batch["speaker_ids"],
+                gesture_labels=batch["gesture_labels"], text_times=batch["text_segments"])
+    torch.manual_seed(5)
+    with torch.no_grad():
+        re = db(cond, batch["motion_length"], "cpu", idx=batch["sample_name"], retrieval_method="discourse",
+                gesture_rep_encoder=codec)
+    out["retr_startends"] = _jsonable(re["retr_startends"])
+    out["query_startends"] = _jsonable(re["query_startends"])
+    out["raw_sample_names"] = _jsonable(re["raw_sample_names"])
+    out["re_mask_sum"] = re["re_mask"].sum(1).tolist()
+    with open(os.path.join(HERE, "retrieval.json"), "w") as f:
+        json.dump(out, f)
+    save("retrieval_latents", raw_motion_latents=re["raw_motion_latents"][:4])
+    print("wrote retrieval.json; exemplars placed:", sum(len(x) for x in re["retr_startends"]))
+
+
+def build_reference_architecture(ns, ds, sd):
+    from rag_gesture_b200.codec import SyntheticGestureCodec
+    ns.dt.GestureRepEncoder = SyntheticGestureCodec
+    ns.rg.RetrievalDatabase = make_ref_db_class(ns)
+    cfg = C.model_cfg()
+    cfg["use_retrieval_for_test"] = True
+    arch = ns.builder.build_architecture(cfg, database=ds)
+    missing, unexpected = arch.model.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.startswith("gesture_rep_encoder.") for k in missing)
+    return arch.eval()
+
+
+def gen_pipeline(ns):
+    """MotionDiffusion.forward of the reference, B=3: discourse retrieval -> per-exemplar inversion ->
+    insertion-guided sampling (decreasing_till_25) -> decode; then a 2-window prev_latent chain."""
+    ds = S.SyntheticGestureDataset(N_DB, seed=7)
+    qs = S.SyntheticGestureDataset(N_QUERY, seed=8)
+    arch = build_reference_architecture(ns, ds, S.synthetic_state_dict(0))
+    pick = [1, 2, 4]
+    batch = S.collate([qs[i] for i in pick])
+    batch["retrieval_method"] = "discourse"
+    batch["inference_kwargs"] = dict(use_inversion=True, outpaint=False, inversion_start_time=-1,
+                                     insertion_guidance=True, guidance_iters=[0] * 25 + list(range(25)),
+                                     guidance_lr=0.1)
+    torch.manual_seed(2024)
+    with torch.no_grad():
+        res = arch(**batch)
+    n_ex = sum(len(x) for x in res["retrieval_dict"]["retr_startends"])
+    print("pipeline exemplars:", n_ex, res["retrieval_dict"]["raw_sample_names"])
+    # long-form chaining: window 2 starts from window 1's last tokens
+    # (a different clip per window: a repeated sample_name would hit the reference's broken
+    #  retrieval-cache branch, raggesture.py:365, SURVEY quirk 7)
+    outs = []
+    prev = None
+    torch.manual_seed(77)
+    for w in range(2):
+        bw = S.collate([qs[5 + w]])
+        bw["retrieval_method"] = "discourse"
+        bw["inference_kwargs"] = dict(use_inversion=True, insertion_guidance=True,
+                                      guidance_iters=[0] * 25 + list(range(25)), guidance_lr=0.1,
+                                      use_prev_latent=True, prev_latent=prev)
+        with torch.no_grad():
+            r = arch(**bw)
+        prev = r["prev_latentout"]
+        outs.append(prev)
+    save("pipeline_b3", prev_latentout=res["prev_latentout"], pred_upper=res["pred_upper"][:, ::10],
+         pred_hands=res["pred_hands"][:, ::10], n_exemplars=np.array(n_ex),
+         chain_w0=outs[0], chain_w1=outs[1])
+
+
+GROUPS = {"schedule": gen_schedule, "denoiser": gen_denoiser, "loops": gen_loops,
+          "retrieval": gen_retrieval, "pipeline": gen_pipeline}
 
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())

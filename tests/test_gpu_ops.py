@@ -59,7 +59,7 @@ def test_layernorm_and_stylization_rows(dev):
     out = ops.stylization_rows(y.view(B * T, D).to(dev), gam.to(dev), bet.to(dev), ss.to(dev), T).cpu().view(B, T, D)
     assert rel_l2(out, ref) < 2e-6
     # -1e6 rows (efficient_attention.py:98): the row collapses to a constant -> LN returns beta
-    y2 = 0.01 * torch.randn(2, D, generator=g) + -1000000.0
+    y2 = 0.004 * torch.randn(2, D, generator=g) + -1000000.0      # |y| < 1/32: every entry rounds to -1e6
     out2 = ops.layernorm(y2.to(dev), gam.to(dev), bet.to(dev)).cpu()
     assert torch.equal(out2[0], bet) and torch.equal(out2[1], bet)
     assert torch.allclose(out2, F.layer_norm(y2, (D,), gam, bet, 1e-5), atol=1e-6, rtol=0)

@@ -1,0 +1,154 @@
+"""GPU parity of the retrieval kernels (K10/K11) and of the whole guided batch
+(MotionDiffusion.forward) against the reference's golden outputs.  Needs a GPU."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, rel_l2
+from oracle import retrieval as ORT
+from rag_gesture_b200 import config as C
+from rag_gesture_b200 import synthetic as S
+
+pytestmark = pytest.mark.gpu
+N_DB, N_QUERY = 1200, 48
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def db(dev):
+    from rag_gesture_b200.retrieval import RetrievalDatabase
+    return RetrievalDatabase(dataset=S.SyntheticGestureDataset(N_DB, seed=7), device=dev, **C.retrieval_cfg()).eval()
+
+
+def test_text_similarity_kernel(db, dev):
+    """rg_text_similarity == mean(diag(Q D^T)) over min(Tq,Td) tokens (rag/utils.py:107-118)."""
+    index = db.text_index(dev)
+    qs = S.SyntheticGestureDataset(N_QUERY, seed=8)
+    for qi in (0, 3):
+        q = qs.text_feature(qi)
+        got = index.scores(q.to(dev)).cpu()
+        ref = torch.stack([torch.diagonal(torch.mm(q.double(), db.idx_2_text[n][0].double().T)).mean()
+                           for n in index.names]).float()
+        assert torch.allclose(got, ref, rtol=2e-5, atol=2e-5)
+        rows = [5, 900, 17, 17, 1199]
+        assert torch.equal(index.scores(q.to(dev), rows).cpu(), got[rows])
+    names = index.names[:200]
+    with open(os.path.join(GOLDEN, "retrieval.json")) as f:
+        gold = json.load(f)
+    order = [index.names[r] for r in index.rank(qs.text_feature(0).to(dev), [index.row[n] for n in names], 32)]
+    assert order == gold["sim_order"][:32]
+
+
+def test_discourse_retrieval_vs_reference(db, dev):
+    with open(os.path.join(GOLDEN, "retrieval.json")) as f:
+        gold = json.load(f)
+    qs = S.SyntheticGestureDataset(N_QUERY, seed=8)
+    for i in range(N_QUERY):
+        spk, disc, prom, _, _ = qs.annotations(i)
+        idx, bounds, qb = db.retrieval_method["discourse"](
+            text="", discourse=disc, prominence=prom, speaker_id=spk, db_idx_2_sense=db.idx_2_sense,
+            db_idx_2_discbounds=db.idx_2_discbounds, db_idx_2_prominence=db.idx_2_prominence,
+            encoded_text=qs.text_feature(i).to(dev), text_feat_cache=db.idx_2_text)
+        g = gold["queries"][i]
+        assert json.loads(json.dumps({str(k): v for k, v in idx.items()})) == g["idx"], i
+        assert json.loads(json.dumps({str(k): v for k, v in bounds.items()})) == g["bounds"], i
+
+
+@pytest.mark.parametrize("N,Q,k", [(20000, 1, 8), (20000, 5, 8), (4099, 64, 8), (777, 9, 32), (40, 3, 8), (5, 2, 8)])
+def test_knn_topk_exact(dev, N, Q, k):
+    """Retrieved indices bit-exact against the float64 oracle unless the oracle itself reports an
+    fp32-level near-tie at the cut (north_star: exact indices, deterministic tie-break)."""
+    from rag_gesture_b200.parallel import knn_topk
+    g = torch.Generator().manual_seed(N + Q)
+    db = torch.nn.functional.normalize(torch.randn(N, 768, generator=g), dim=1)
+    qs = torch.nn.functional.normalize(torch.randn(Q, 768, generator=g), dim=1)
+    if N == 777:                       # exact duplicates: ties must resolve to the lower index
+        db[500:520] = db[100:120]
+    idx, sc = knn_topk(db.to(dev), qs.to(dev), k, idx_base=1000)
+    idx, sc = idx.cpu(), sc.cpu()
+    kk = min(k, N)
+    ref_idx, ref_sc, gaps = ORT.knn_topk_f64(db, qs, kk)
+    for q in range(Q):
+        if gaps[q] > 1e-6:
+            assert torch.equal(idx[q, :kk] - 1000, ref_idx[q]), q
+        assert torch.allclose(sc[q, :kk].double(), ref_sc[q], atol=2e-6)
+    if k > N:
+        assert bool((idx[:, N:] == -1).all())
+
+
+def test_knn_merge_matches_single_shard(dev):
+    from rag_gesture_b200.parallel import _cuda_merge, knn_topk, shard_range
+    g = torch.Generator().manual_seed(3)
+    db = torch.randn(10007, 768, generator=g).to(dev)
+    qs = torch.randn(16, 768, generator=g).to(dev)
+    full_i, full_s = knn_topk(db, qs, 8)
+    parts_i, parts_s = [], []
+    for r in range(8):
+        lo, hi = shard_range(db.shape[0], r, 8)
+        i, s = knn_topk(db[lo:hi].contiguous(), qs, 8, idx_base=lo)
+        parts_i.append(i)
+        parts_s.append(s)
+    mi, ms = _cuda_merge(torch.stack(parts_i), torch.stack(parts_s), 8)
+    assert torch.equal(mi, full_i) and torch.equal(ms, full_s)
+
+
+@pytest.fixture(scope="module")
+def arch(dev):
+    import rag_gesture_b200 as R
+    cfg = C.model_cfg()
+    cfg["use_retrieval_for_test"] = True
+    m = R.build_architecture(cfg, database=S.SyntheticGestureDataset(N_DB, seed=7))
+    missing, unexpected = m.model.load_state_dict(S.synthetic_state_dict(0), strict=False)
+    assert not unexpected
+    return m.to(dev).eval()
+
+
+def _cpu_noise(shape, device):
+    return torch.randn(*shape).to(device)     # global CPU generator, like the reference run
+
+
+def test_full_guided_batch_vs_reference(arch, dev):
+    """configs[1] in miniature: B=3, discourse retrieval, batched inversion, insertion guidance."""
+    g = np.load(os.path.join(GOLDEN, "pipeline_b3.npz"))
+    qs = S.SyntheticGestureDataset(N_QUERY, seed=8)
+    batch = S.collate([qs[i] for i in [1, 2, 4]])
+    batch["retrieval_method"] = "discourse"
+    batch["inference_kwargs"] = dict(use_inversion=True, outpaint=False, inversion_start_time=-1,
+                                     insertion_guidance=True, guidance_iters=[0] * 25 + list(range(25)),
+                                     guidance_lr=0.1)
+    arch.diffusion_test.noise_fn = _cpu_noise
+    torch.manual_seed(2024)
+    res = arch(**batch)
+    n_ex = sum(len(x) for x in res["retrieval_dict"]["retr_startends"])
+    assert n_ex == int(g["n_exemplars"]) and n_ex > 0
+    assert rel_l2(res["prev_latentout"].cpu(), torch.from_numpy(g["prev_latentout"])) < 2e-3
+    assert rel_l2(res["pred_upper"][:, ::10].cpu(), torch.from_numpy(g["pred_upper"])) < 2e-3
+    assert rel_l2(res["pred_hands"][:, ::10].cpu(), torch.from_numpy(g["pred_hands"])) < 2e-3
+    assert tuple(res["pred_lower"].shape) == (3, 150, 27) and tuple(res["pred_exps"].shape) == (3, 150, 100)
+
+
+def test_longform_prev_latent_chain(arch, dev):
+    g = np.load(os.path.join(GOLDEN, "pipeline_b3.npz"))
+    qs = S.SyntheticGestureDataset(N_QUERY, seed=8)
+    arch.diffusion_test.noise_fn = _cpu_noise
+    prev = None
+    torch.manual_seed(77)
+    outs = []
+    for w in range(2):
+        bw = S.collate([qs[5 + w]])
+        bw["retrieval_method"] = "discourse"
+        bw["inference_kwargs"] = dict(use_inversion=True, insertion_guidance=True,
+                                      guidance_iters=[0] * 25 + list(range(25)), guidance_lr=0.1,
+                                      use_prev_latent=True, prev_latent=prev)
+        prev = arch(**bw)["prev_latentout"]
+        outs.append(prev.cpu())
+    assert rel_l2(outs[0], torch.from_numpy(g["chain_w0"])) < 2e-3
+    assert rel_l2(outs[1], torch.from_numpy(g["chain_w1"])) < 2e-3
