@@ -128,6 +128,13 @@ int rg_guidance_steps(rg_handle h, float* x, const float* in_seq, int64_t rows, 
 enum { RG_OP_NONE = 0, RG_OP_RESIDUAL = 1, RG_OP_GELU = 2, RG_OP_SILU = 4 };
 int rg_op_linear(const float* x, int ldx, const float* W, const float* b, const float* residual,
                  float* out, int M, int N, int K, int epilogue, void* stream);
+/* The same contraction on the 5th-gen tensor cores (tcgen05.mma, TMEM accumulator, TMA-fed):
+ * operands are converted to bf16 on the fly; split=0: bf16 x bf16 -> fp32 (RG_PREC_BF16);
+ * split=1: hi+lo operand split, 3 products (RG_PREC_BF16X3, fp32-class accuracy).
+ * N % 128 == 0, K % 64 == 0.  out (fp32 [M,N]) and/or out_bf16 (bf16 [M,N], or [M,2N] = hi|lo planes
+ * when split) may be NULL.  Used by the unit parity tests and bench.py's roofline probe. */
+int rg_op_linear_tc(const float* x, const float* W, const float* b, const float* residual, float* out,
+                    void* out_bf16, int M, int N, int K, int epilogue, int split, void* stream);
 /* LayerNorm over 512-wide rows, eps 1e-5; gamma/beta may be NULL (no affine). */
 int rg_op_layernorm(const float* x, const float* gamma, const float* beta, float* out, int M,
                     void* stream);

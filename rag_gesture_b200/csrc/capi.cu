@@ -12,6 +12,7 @@
 #include "../../include/rg_b200.h"
 #include "rg_common.cuh"
 #include "rg_internal.h"
+#include "rg_gemm_tc.h"
 
 // ---------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
@@ -524,6 +525,39 @@ extern "C" int rg_op_linear(const float* x, int ldx, const float* W, const float
     RgGemm g = mk_gemm(x, ldx, W, b, out, N, M, N, K, epi);
     g.R = residual; g.ldr = N;
     LAUNCH(rg_launch_gemm_f32(g, (cudaStream_t)stream));
+    return 0;
+}
+extern "C" int rg_op_linear_tc(const float* x, const float* W, const float* b, const float* residual,
+                               float* out, void* out_bf16, int M, int N, int K, int epilogue, int split,
+                               void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int epi;
+    switch (epilogue) {
+        case RG_OP_NONE: epi = RG_EPI_BIAS; break;
+        case RG_OP_RESIDUAL: epi = RG_EPI_BIAS_RESIDUAL; break;
+        case RG_OP_GELU: epi = RG_EPI_BIAS_GELU; break;
+        case RG_OP_SILU: epi = RG_EPI_BIAS_SILU; break;
+        default: return rg_fail("rg_op_linear_tc: unknown epilogue %d", epilogue);
+    }
+    if (N % 128 || K % 64) return rg_fail("rg_op_linear_tc: need N %% 128 == 0 and K %% 64 == 0 (got N=%d K=%d)", N, K);
+    if (epi == RG_EPI_BIAS_RESIDUAL && !residual) return rg_fail("rg_op_linear_tc: residual epilogue without residual");
+    const int planes = split ? 2 : 1;
+    void *a16 = nullptr, *w16 = nullptr;
+    CU(cudaMallocAsync(&a16, (size_t)M * K * planes * 2, st));
+    CU(cudaMallocAsync(&w16, (size_t)N * K * planes * 2, st));
+    LAUNCH(rg_launch_split_bf16(x, K, a16, K * planes, split ? K : 0, M, K, st));
+    LAUNCH(rg_launch_split_bf16(W, K, w16, K * planes, split ? K : 0, N, K, st));
+    CUtensorMap tmA, tmW;
+    CU(rg_make_tensor_map(&tmA, a16, M, (long long)K * planes, (long long)K * planes, 128));
+    CU(rg_make_tensor_map(&tmW, w16, N, (long long)K * planes, (long long)K * planes, 128));
+    RgGemmTc p;
+    memset(&p, 0, sizeof(p));
+    p.M = M; p.N = N; p.K = K; p.split = split ? 1 : 0; p.a_lo_off = K; p.w_lo_off = K; p.groups = 1;
+    p.bias = b; p.R = residual; p.ldr = N; p.C32 = out; p.ldc32 = N;
+    p.C16_ = out_bf16; p.ldc16 = N * planes; p.c16_lo_off = split ? N : 0; p.epi = epi;
+    LAUNCH(rg_launch_gemm_tc(tmA, tmW, p, st));
+    CU(cudaFreeAsync(a16, st));
+    CU(cudaFreeAsync(w16, st));
     return 0;
 }
 extern "C" int rg_op_layernorm(const float* x, const float* gamma, const float* beta, float* out,

@@ -1,0 +1,323 @@
+// tcgen05 GEMM  C[M,N] = A[M,K] * W[N,K]^T  for sm_100a: bf16 operands staged by TMA
+// (cp.async.bulk.tensor, SWIZZLE_128B) into a 3-stage shared-memory ring, one elected thread issuing
+// tcgen05.mma.cta_group::1.kind::f16 (UMMA 128xBNx16) into a TMEM accumulator (fp32, 128 lanes x BN
+// columns), epilogue warps reading it back with tcgen05.ld and fusing bias / residual / GELU / SiLU /
+// positional add, writing fp32 and/or bf16 (optionally hi+lo split) outputs.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = epilogue (TMEM lane group = warp % 4).  Two CTAs are resident per SM
+// (96 KB smem, 128 TMEM columns each) so one tile's epilogue overlaps another tile's main loop.
+//
+// "split" mode (RG_PREC_BF16X3): operands are stored as [hi | lo] bf16 planes (x = hi + lo + O(2^-17 x));
+// the K loop runs three passes  A_hi*W_hi + A_lo*W_hi + A_hi*W_lo  into the same fp32 accumulator:
+// fp32-class accuracy (~2^-16 per product) on the bf16 tensor pipe, without a second kernel.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#include "rg_common.cuh"
+#include "rg_gemm_tc.h"
+
+namespace {
+
+constexpr int BM = 128, BK = 64, STAGES = 3;
+constexpr int UMMA_K = 16;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(pred));
+    return pred != 0;
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm100 version 1):
+// rows 128 B apart, 8-row groups SBO = 1024 B apart; LBO is 1 (unused for swizzled K-major).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);        // start address  [0,14)
+    d |= static_cast<uint64_t>(1) << 16;                       // leading byte offset >> 4  [16,30)
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;               // stride byte offset >> 4   [32,46)
+    d |= static_cast<uint64_t>(1) << 46;                       // descriptor version (Blackwell)
+    d |= static_cast<uint64_t>(2) << 61;                       // layout type: SWIZZLE_128B
+    return d;
+}
+// cute::UMMA::InstrDescriptor for kind::f16: D=f32, A=B=bf16, both K-major, M x N
+__device__ __forceinline__ uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
+           (static_cast<uint32_t>(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t v[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+
+template <int BN>
+__global__ void __launch_bounds__(192, 2)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, RgGemmTc p) {
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B tiles need 1024-byte alignment
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+    __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar;
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.z;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int nkb = p.K / BK;
+    const int total_kb = p.split ? 3 * nkb : nkb;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+            mbar_init(smem_u32(&tmem_full_bar), 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(BN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (elect_one()) {
+            const int a_k0 = g * p.a_goff, w_n0 = g * p.w_goff + n0;
+            for (int j = 0; j < total_kb; ++j) {
+                const int s = j % STAGES, ph = (j / STAGES) & 1;
+                mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
+                const int pass = j / nkb, kb = j - pass * nkb;          // pass 0: hi*hi, 1: lo*hi, 2: hi*lo
+                const int ka = a_k0 + (pass == 1 ? p.a_lo_off : 0) + kb * BK;
+                const int kw = (pass == 2 ? p.w_lo_off : 0) + kb * BK;
+                const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
+                mbar_expect_tx(smem_u32(&full_bar[s]), STAGE_BYTES);
+                tma_load_2d(sa, &tmA, smem_u32(&full_bar[s]), ka, m0);
+                tma_load_2d(sb, &tmW, smem_u32(&full_bar[s]), kw, w_n0);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        const uint32_t idesc = make_idesc(BM, BN);
+        for (int j = 0; j < total_kb; ++j) {
+            const int s = j % STAGES, ph = (j / STAGES) & 1;
+            mbar_wait(smem_u32(&full_bar[s]), ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (elect_one()) {
+                const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
+                const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sb);
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k)      // +32 B per UMMA_K inside the 128 B swizzle row
+                    umma_bf16(tmem_base, da + (k * UMMA_K * 2 >> 4), db + (k * UMMA_K * 2 >> 4), idesc, (j | k) != 0);
+                umma_commit(smem_u32(&empty_bar[s]));                   // frees the smem slot when the MMAs retire
+                if (j == total_kb - 1) umma_commit(smem_u32(&tmem_full_bar));
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> global =====
+        mbar_wait(smem_u32(&tmem_full_bar), 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int lg = warp & 3;                                        // TMEM lane group of this warp
+        const int row = m0 + lg * 32 + lane;
+        const bool row_ok = row < p.M;
+        const float* bias = p.bias ? p.bias + g * p.b_goff : nullptr;
+        const int cbase = g * p.c_goff + n0;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + c * 32, v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (!row_ok) continue;
+            const int col = cbase + c * 32;                             // column in C / R
+            float f[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+            if (bias) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n0 + c * 32 + i));
+                    f[i] += b.x; f[i + 1] += b.y; f[i + 2] += b.z; f[i + 3] += b.w;
+                }
+            }
+            if (p.epi == RG_EPI_BIAS_RESIDUAL) {
+                const float* r = p.R + (long long)row * p.ldr + (p.r_grouped ? col : n0 + c * 32);
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    const float4 b = *reinterpret_cast<const float4*>(r + i);
+                    f[i] += b.x; f[i + 1] += b.y; f[i + 2] += b.z; f[i + 3] += b.w;
+                }
+            } else if (p.epi == RG_EPI_BIAS_GELU) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) f[i] = rg_gelu_erf(f[i]);
+            } else if (p.epi == RG_EPI_BIAS_SILU) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) f[i] = rg_silu(f[i]);
+            } else if (p.epi == RG_EPI_BIAS_POS) {
+                const float* r = p.pos + (long long)(row % p.pos_T) * p.N + n0 + c * 32;
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(r + i));
+                    f[i] += b.x; f[i + 1] += b.y; f[i + 2] += b.z; f[i + 3] += b.w;
+                }
+            }
+            if (p.C32) {
+                float* o = p.C32 + (long long)row * p.ldc32 + col;
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+            }
+            if (p.C16_) {
+                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.C16_) + (long long)row * p.ldc16 + col;
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    const __nv_bfloat16 h0 = __float2bfloat16_rn(f[i]), h1 = __float2bfloat16_rn(f[i + 1]);
+                    hi[i >> 1] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                    const __nv_bfloat16 l0 = __float2bfloat16_rn(f[i] - __bfloat162float(h0));
+                    const __nv_bfloat16 l1 = __float2bfloat16_rn(f[i + 1] - __bfloat162float(h1));
+                    lo[i >> 1] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                }
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) *reinterpret_cast<uint4*>(o + i * 2) = make_uint4(hi[i], hi[i + 1], hi[i + 2], hi[i + 3]);
+                if (p.c16_lo_off) {
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4)
+                        *reinterpret_cast<uint4*>(o + p.c16_lo_off + i * 2) = make_uint4(lo[i], lo[i + 1], lo[i + 2], lo[i + 3]);
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN));
+    }
+}
+
+// fp32 -> bf16 hi (and lo = bf16(x - hi)) planes; row-major, lo plane at column offset lo_off (0 = none)
+__global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ x, int ldx,
+                                                        __nv_bfloat16* __restrict__ out, int ldo, int lo_off,
+                                                        long long rows, int cols) {
+    const long long n4 = rows * (cols / 4);
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n4; i += stride) {
+        const long long r = i / (cols / 4);
+        const int c = (int)(i - r * (cols / 4)) * 4;
+        const float4 v = *reinterpret_cast<const float4*>(x + r * ldx + c);
+        const float f[4] = {v.x, v.y, v.z, v.w};
+        __nv_bfloat16 h[4], l[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { h[k] = __float2bfloat16_rn(f[k]); l[k] = __float2bfloat16_rn(f[k] - __bfloat162float(h[k])); }
+        *reinterpret_cast<uint2*>(out + r * ldo + c) = *reinterpret_cast<uint2*>(h);
+        if (lo_off) *reinterpret_cast<uint2*>(out + r * ldo + lo_off + c) = *reinterpret_cast<uint2*>(l);
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+
+}  // namespace
+
+// row-major bf16 [rows, cols] with pitch ld (elements): box = 64 (K) x box_rows, 128-byte swizzle
+cudaError_t rg_make_tensor_map(CUtensorMap* tm, const void* ptr, long long rows, long long cols, long long ld,
+                               int box_rows) {
+    if (!g_encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+        if (e != cudaSuccess) return e;
+        if (q != cudaDriverEntryPointSuccess || !fn) return cudaErrorNotSupported;
+        g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+cudaError_t rg_launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmW, const RgGemmTc& p, cudaStream_t st) {
+    if (p.M <= 0 || p.N <= 0) return cudaSuccess;
+    constexpr int BN = 128;
+    if (p.K % BK || p.N % BN || (p.C32 && p.ldc32 % 4) || (p.C16_ && p.ldc16 % 8) || (p.R && p.ldr % 4))
+        return cudaErrorInvalidValue;
+    const size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 1024;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    dim3 grid(p.N / BN, (p.M + BM - 1) / BM, p.groups > 0 ? p.groups : 1);
+    gemm_tc_kernel<BN><<<grid, 192, smem, st>>>(tmA, tmW, p);
+    return cudaGetLastError();
+}
+
+cudaError_t rg_launch_split_bf16(const float* x, int ldx, void* out, int ldo, int lo_off, long long rows, int cols,
+                                 cudaStream_t st) {
+    if (rows <= 0) return cudaSuccess;
+    if (cols % 4 || ldx % 4 || ldo % 4 || lo_off % 4) return cudaErrorInvalidValue;
+    const long long n4 = rows * (cols / 4);
+    const int blocks = (int)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
+    split_bf16_kernel<<<blocks, 256, 0, st>>>(x, ldx, reinterpret_cast<__nv_bfloat16*>(out), ldo, lo_off, rows, cols);
+    return cudaGetLastError();
+}

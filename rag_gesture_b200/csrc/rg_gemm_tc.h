@@ -1,0 +1,25 @@
+// tcgen05 GEMM launcher interface (gemm_tc.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+struct RgGemmTc {
+    int M, N, K;              // K: reduction length of ONE operand plane
+    int split;                // 0: bf16 x bf16;  1: three passes hi*hi + lo*hi + hi*lo (bf16x3)
+    int a_lo_off, w_lo_off;   // column (K) offset of the lo plane inside A / W rows (split mode)
+    int groups;               // blockIdx.z: A K-offset += a_goff, W row += w_goff, bias += b_goff, C col += c_goff
+    int a_goff, w_goff, b_goff, c_goff, r_grouped;
+    const float* bias;
+    const float* R; int ldr;  // fp32 residual (RG_EPI_BIAS_RESIDUAL)
+    const float* pos; int pos_T;
+    float* C32; int ldc32;    // optional fp32 output
+    void* C16_; int ldc16;    // optional bf16 output (+ lo plane at column c16_lo_off when non-zero)
+    int c16_lo_off;
+    int epi;                  // RgEpilogue
+};
+
+cudaError_t rg_make_tensor_map(CUtensorMap* tm, const void* ptr, long long rows, long long cols, long long ld,
+                               int box_rows);
+cudaError_t rg_launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmW, const RgGemmTc& p, cudaStream_t st);
+cudaError_t rg_launch_split_bf16(const float* x, int ldx, void* out, int ldo, int lo_off, long long rows, int cols,
+                                 cudaStream_t st);

@@ -30,6 +30,23 @@ def linear(x, weight, bias=None, residual=None, epilogue=_lib.OP_NONE):
     return out
 
 
+def linear_tc(x, weight, bias=None, residual=None, epilogue=_lib.OP_NONE, split=False, want_bf16=False):
+    """Tensor-core (tcgen05) version of `linear`: bf16 operands (split=False) or bf16x3 (split=True).
+    Returns fp32 [.., N] and, if want_bf16, also the bf16 output planes as a bf16 tensor."""
+    x, weight, bias, residual = _prep(x, weight, bias, residual)
+    N, K = weight.shape
+    M = x.numel() // K
+    out = torch.empty(*x.shape[:-1], N, device=x.device)
+    o16 = torch.empty(M, N * (2 if split else 1), device=x.device, dtype=torch.bfloat16) if want_bf16 else None
+    if residual is not None:
+        epilogue = _lib.OP_RESIDUAL
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().rg_op_linear_tc(_lib.ptr(x), _lib.ptr(weight), _lib.ptr(bias), _lib.ptr(residual),
+                                               _lib.ptr(out), _lib.ptr(o16), M, N, K, epilogue, int(split),
+                                               _lib.stream_ptr()))
+    return (out, o16) if want_bf16 else out
+
+
 def layernorm(x, gamma=None, beta=None):
     x, gamma, beta = _prep(x, gamma, beta)
     assert x.shape[-1] == D, "rg_b200 LayerNorm kernels are built for 512-wide rows"
