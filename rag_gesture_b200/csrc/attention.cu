@@ -16,8 +16,8 @@ struct RgStyl3 { RgStylParams p[3]; };
 
 // rows of Ysm -> LN/modulate/SiLU (or + residual) -> out; 16 warps stride over the T rows
 __device__ __forceinline__ void finish_rows(const float* Ysm, int T, int clip, const RgStylParams& sp,
-                                            int with_styl, const float* x_res, int ldr, float* out,
-                                            int ldo, int warp, int lane) {
+                                            int with_styl, const float* x_res, int ldr, const RgRowOut& out,
+                                            int col0, int warp, int lane) {
     for (int n = warp; n < T; n += RG_H) {
         float4 v[4];
         load_row(Ysm + n * RG_D, lane, v);
@@ -30,7 +30,7 @@ __device__ __forceinline__ void finish_rows(const float* Ysm, int T, int clip, c
 #pragma unroll
             for (int j = 0; j < 4; ++j) { v[j].x += r[j].x; v[j].y += r[j].y; v[j].z += r[j].z; v[j].w += r[j].w; }
         }
-        store_row(out + row * ldo, lane, v);
+        rg_store_row_out(out, row, col0, lane, v);
     }
 }
 
@@ -48,7 +48,7 @@ __device__ __forceinline__ float q_dot_A(float q, const float A[RG_HD]) {
 __global__ void __launch_bounds__(512) sa_attn_kernel(const float* __restrict__ qkv,
                                                      const float* __restrict__ src_mask,
                                                      RgStylParams sp, const float* __restrict__ x_res,
-                                                     float* __restrict__ out, int T, int with_styl) {
+                                                     RgRowOut out, int T, int with_styl) {
     extern __shared__ __align__(16) float Ysm[];   // [T][512]
     const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float* base = qkv + (long long)b * T * (3 * RG_D) + warp * RG_HD + lane;
@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(512) sa_attn_kernel(const float* __restrict__ 
     for (int n = 0; n < T; ++n)
         Ysm[n * RG_D + warp * RG_HD + lane] = q_dot_A(base[(long long)n * (3 * RG_D)], A);
     __syncthreads();
-    finish_rows(Ysm, T, b, sp, with_styl, x_res, RG_D, out, RG_D, warp, lane);
+    finish_rows(Ysm, T, b, sp, with_styl, x_res, RG_D, out, 0, warp, lane);
 }
 
 __global__ void __launch_bounds__(512) ca_attn_kernel(const float* __restrict__ q3, int ldq,
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(512) ca_attn_kernel(const float* __restrict__ 
                                                      long long state_cond_stride,
                                                      const float* __restrict__ qmask,
                                                      long long qmask_cond_stride, RgStyl3 sp3,
-                                                     float* __restrict__ out, int ldo, int T) {
+                                                     RgRowOut out, int T) {
     extern __shared__ __align__(16) float Ysm[];
     const int b = blockIdx.x, c = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float* Ap = state + (long long)b * state_clip_stride + (long long)c * state_cond_stride +
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(512) ca_attn_kernel(const float* __restrict__ 
         Ysm[n * RG_D + warp * RG_HD + lane] = y;
     }
     __syncthreads();
-    finish_rows(Ysm, T, b, sp3.p[c], 1, nullptr, 0, out + c * RG_D, ldo, warp, lane);
+    finish_rows(Ysm, T, b, sp3.p[c], 1, nullptr, 0, out, c * RG_D, warp, lane);
 }
 
 // state[b][set][h][d][l] = sum_n softmax_n(K[b,n,h,d]) * V[b,n,h,l]; warp = d, lane = l
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(1024) kv_state_kernel(const float* __restrict_
 }  // namespace
 
 cudaError_t rg_launch_sa_attention(const float* qkv, const float* src_mask, RgStylParams sp,
-                                   const float* x_res, float* out, int B, int T, int with_styl,
+                                   const float* x_res, RgRowOut out, int B, int T, int with_styl,
                                    cudaStream_t st) {
     if (B <= 0) return cudaSuccess;
     if (T > RG_MAX_T) return cudaErrorInvalidValue;
@@ -147,7 +147,7 @@ cudaError_t rg_launch_sa_attention(const float* qkv, const float* src_mask, RgSt
 cudaError_t rg_launch_ca_attention(const float* q3, int ldq, const float* state,
                                    long long state_clip_stride, long long state_cond_stride,
                                    const float* qmask, long long qmask_cond_stride,
-                                   const RgStylParams* sp3, float* out, int ldo, int B, int T,
+                                   const RgStylParams* sp3, RgRowOut out, int B, int T,
                                    int n_cond, cudaStream_t st) {
     if (B <= 0) return cudaSuccess;
     if (T > RG_MAX_T || n_cond < 1 || n_cond > 3) return cudaErrorInvalidValue;
@@ -159,7 +159,7 @@ cudaError_t rg_launch_ca_attention(const float* q3, int ldq, const float* state,
     if (e != cudaSuccess) return e;
     ca_attn_kernel<<<dim3(B, n_cond), 512, smem, st>>>(q3, ldq, state, state_clip_stride,
                                                        state_cond_stride, qmask, qmask_cond_stride,
-                                                       s3, out, ldo, T);
+                                                       s3, out, T);
     return cudaGetLastError();
 }
 

@@ -50,8 +50,21 @@ struct Layer {
     float *ffn_g, *ffn_b, *ffn_Wo, *ffn_bo;
 };
 
+struct W16 {                 // bf16 operand planes [N, planes*K] (hi | lo) + its TMA descriptor
+    void* ptr;
+    CUtensorMap tm;
+    int N, K;
+};
+struct LayerTc { W16 qkv, sa_o, caq, ca_o, mix, w1, w2, ffn_o; };
+
 struct rg_model {
     rg_config cfg;
+    // tensor-core path (cfg.precision != RG_PREC_FP32)
+    int planes;              // 1: bf16 operands, 2: hi|lo planes (bf16x3)
+    std::vector<LayerTc> tc;
+    W16 tc_joint, tc_out;
+    void *x16, *a16, *a16w, *o16, *h16, *g16;
+    CUtensorMap tm_x16, tm_a16, tm_a16w, tm_o16, tm_h16, tm_g16;
     int device;
     std::vector<void*> allocs;
     std::vector<Layer> layers;
@@ -123,6 +136,17 @@ static RgGemm mk_gemm(const float* A, int lda, const float* W, const float* bias
     return g;
 }
 
+// fp32 [N,K] weight -> bf16 planes [N, planes*K] + TMA descriptor (box 64 x 128, 128B swizzle)
+static int make_w16(rg_model* m, const float* W, int N, int K, W16* out) {
+    const int P = m->planes;
+    if (dalloc(m, &out->ptr, (size_t)N * K * P * 2)) return 1;
+    CU(rg_launch_split_bf16(W, K, out->ptr, K * P, P == 2 ? K : 0, N, K, 0));
+    ++g_launches;
+    CU(rg_make_tensor_map(&out->tm, out->ptr, N, (long long)K * P, (long long)K * P, 128));
+    out->N = N; out->K = K;
+    return 0;
+}
+
 extern "C" const char* rg_last_error(void) { return g_err; }
 extern "C" int rg_abi_version(void) { return RG_ABI_VERSION; }
 extern "C" int64_t rg_launch_count(void) { return g_launches; }
@@ -144,8 +168,8 @@ extern "C" int rg_create(const rg_config* cfg, int n_tensors, const char* const*
         return rg_fail("rg_create: n_tokens=%d must be 4*n_chunks+3 and <= %d", cfg->n_tokens, RG_MAX_T);
     if (cfg->ffn_dim % 128 || cfg->time_embed_dim % 128 || cfg->text_dim % 16)
         return rg_fail("rg_create: ffn_dim/time_embed_dim must be multiples of 128, text_dim of 16");
-    if (cfg->precision != RG_PREC_FP32)
-        return rg_fail("rg_create: precision %d not available in this build", cfg->precision);
+    if (cfg->precision != RG_PREC_FP32 && cfg->precision != RG_PREC_BF16 && cfg->precision != RG_PREC_BF16X3)
+        return rg_fail("rg_create: unknown precision %d", cfg->precision);
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return rg_fail("rg_create: no CUDA device (this library has no CPU path)");
@@ -160,6 +184,8 @@ extern "C" int rg_create(const rg_config* cfg, int n_tensors, const char* const*
     m->ws_rows = 0; m->h = m->a = m->big = m->o3 = m->g = m->y = nullptr;
     m->kv_rows = 0; m->kv_ln = m->kv_buf = nullptr;
     m->tt_rows = 0; m->tt_emb = m->tt_t1 = m->tt_e = nullptr;
+    m->planes = cfg->precision == RG_PREC_BF16X3 ? 2 : 1;
+    m->x16 = m->a16 = m->a16w = m->o16 = m->h16 = m->g16 = nullptr;
     const int D = RG_D, E = cfg->time_embed_dim, F = cfg->ffn_dim, L = cfg->num_layers, T = cfg->n_tokens;
     const long long DD = (long long)D * D;
     cudaStream_t st = 0;
@@ -276,6 +302,24 @@ extern "C" int rg_create(const rg_config* cfg, int n_tensors, const char* const*
     dfree_one(m, tmpW); dfree_one(m, tmpb); dfree_one(m, tmpg); dfree_one(m, tmpbe);
     dfree_one(m, seq); dfree_one(m, glob);
     TRY(dalloc(m, (void**)&m->tau_row, (size_t)L * 5 * 2 * D * sizeof(float)));
+    if (cfg->precision != RG_PREC_FP32) {
+        m->tc.resize(L);
+        TRY(make_w16(m, m->W_joint, D, D, &m->tc_joint));
+        TRY(make_w16(m, m->W_out, D, D, &m->tc_out));
+        for (int l = 0; l < L; ++l) {
+            const Layer& ly = m->layers[l];
+            LayerTc& t = m->tc[l];
+            TRY(make_w16(m, ly.Wqkv, 3 * D, D, &t.qkv));
+            TRY(make_w16(m, ly.sa_Wo, D, D, &t.sa_o));
+            TRY(make_w16(m, ly.Wcaq, 3 * D, D, &t.caq));
+            TRY(make_w16(m, ly.ca_Wo, 3 * D, D, &t.ca_o));      // 3 stacked [512,512] blocks
+            TRY(make_w16(m, ly.Wmix, D, 3 * D, &t.mix));
+            TRY(make_w16(m, ly.W1, F, D, &t.w1));
+            TRY(make_w16(m, ly.W2, D, F, &t.w2));
+            TRY(make_w16(m, ly.ffn_Wo, D, D, &t.ffn_o));
+        }
+        TRYCU(cudaDeviceSynchronize());
+    }
     *out = m;
     rc = 0;
 fail:
@@ -347,6 +391,18 @@ static int ensure_ws(rg_model* m, long long rows) {
     if (dalloc(m, (void**)&m->o3, (size_t)rows * 3 * D * sizeof(float))) return 1;
     if (dalloc(m, (void**)&m->g, (size_t)rows * F * sizeof(float))) return 1;
     if (dalloc(m, (void**)&m->y, (size_t)rows * D * sizeof(float))) return 1;
+    if (m->cfg.precision != RG_PREC_FP32) {
+        const int P = m->planes;
+        void** b16[6] = {&m->x16, &m->a16, &m->a16w, &m->o16, &m->h16, &m->g16};
+        const int width[6] = {D, D, 3 * D, 3 * D, D, F};
+        CUtensorMap* tms[6] = {&m->tm_x16, &m->tm_a16, &m->tm_a16w, &m->tm_o16, &m->tm_h16, &m->tm_g16};
+        for (int i = 0; i < 6; ++i) {
+            dfree_one(m, *b16[i]); *b16[i] = nullptr;
+            if (dalloc(m, b16[i], (size_t)rows * width[i] * P * 2)) return 1;
+            CU(cudaMemset(*b16[i], 0, (size_t)rows * width[i] * P * 2));
+            CU(rg_make_tensor_map(tms[i], *b16[i], rows, (long long)width[i] * P, (long long)width[i] * P, 128));
+        }
+    }
     m->ws_rows = rows;
     return 0;
 }
@@ -396,7 +452,7 @@ extern "C" int rg_precompute_clip_state(rg_handle m, const float* xf_text, const
         for (int b0 = 0; b0 < B; b0 += per) {
             const int nb = (B - b0 < per) ? B - b0 : per;
             const int rows = nb * N;
-            LAUNCH(rg_launch_ln_rows(xf[c] + (long long)b0 * N * D, D, nullptr, nullptr, m->kv_ln, D, rows, st));
+            LAUNCH(rg_launch_ln_rows(xf[c] + (long long)b0 * N * D, D, nullptr, nullptr, rg_out_f32(m->kv_ln, D), rows, st));
             LAUNCH(rg_launch_gemm_f32(mk_gemm(m->kv_ln, D, m->Wkv_all[c], m->bkv_all[c], m->kv_buf, L * 2 * D,
                                               rows, L * 2 * D, D, RG_EPI_BIAS), st));
             LAUNCH(rg_launch_kv_state(m->kv_buf, L * 2 * D, 0, D, N,
@@ -405,6 +461,62 @@ extern "C" int rg_precompute_clip_state(rg_handle m, const float* xf_text, const
         }
     }
     return 0;
+}
+
+// one tcgen05 GEMM: A (bf16 planes, tensor map tmA, plane width a_w) x W16 -> fp32 and/or bf16 planes
+static int tc_gemm(rg_model* m, const CUtensorMap& tmA, int a_w, const W16& w, const float* bias, int M, int N,
+                   int K, int epi, const float* R, float* C32, int ldc32, void* C16, int c16_w, cudaStream_t st,
+                   int groups = 1, int a_goff = 0, int w_goff = 0, int bc_goff = 0) {
+    RgGemmTc p;
+    memset(&p, 0, sizeof(p));
+    p.M = M; p.N = N; p.K = K; p.split = m->planes == 2; p.a_lo_off = a_w; p.w_lo_off = w.K;
+    p.groups = groups; p.a_goff = a_goff; p.w_goff = w_goff; p.b_goff = bc_goff; p.c_goff = bc_goff;
+    p.bias = bias; p.R = R; p.ldr = RG_D; p.pos = m->pos; p.pos_T = m->cfg.n_tokens;
+    p.C32 = C32; p.ldc32 = ldc32; p.C16_ = C16; p.ldc16 = c16_w * m->planes;
+    p.c16_lo_off = m->planes == 2 ? c16_w : 0; p.epi = epi;
+    LAUNCH(rg_launch_gemm_tc(tmA, w.tm, p, st));
+    return 0;
+}
+
+// rg_denoise on the tensor cores: bf16 (or hi|lo bf16) operands, fp32 accumulation in TMEM, fp32
+// residual stream / softmaxes / LayerNorm statistics / -1e6 masks exactly as on the fp32 path.
+static int denoise_tc(rg_model* m, const float* x, int B, const float* ssrow, const float* src_mask,
+                      const float* query_mask, const float* state, float* x0_out, cudaStream_t st) {
+    const int D = RG_D, F = m->cfg.ffn_dim, L = m->cfg.num_layers, T = m->cfg.n_tokens, P = m->planes;
+    const int M = B * T;
+    const long long clip_stride = rg_state_floats_per_clip(m);
+    const long long HS = (long long)RG_H * RG_HD * RG_HD;
+    const int lo = P == 2;
+    LAUNCH(rg_launch_split_bf16(x, D, m->x16, D * P, lo ? D : 0, M, D, st));
+    if (tc_gemm(m, m->tm_x16, D, m->tc_joint, m->b_joint, M, D, D, RG_EPI_BIAS_POS, nullptr, m->h, D, nullptr, 0, st)) return 1;
+    for (int l = 0; l < L; ++l) {
+        const Layer& ly = m->layers[l];
+        const LayerTc& t = m->tc[l];
+        const float* ss = ssrow + (long long)l * 5 * 2 * D;
+        // --- self-attention
+        LAUNCH(rg_launch_ln_rows(m->h, D, nullptr, nullptr, rg_out_b16(m->a16, D * P, lo ? D : 0), M, st));
+        if (tc_gemm(m, m->tm_a16, D, t.qkv, ly.bqkv, M, 3 * D, D, RG_EPI_BIAS, nullptr, m->big, 3 * D, nullptr, 0, st)) return 1;
+        RgStylParams sp = {ly.sa_g, ly.sa_b, ss, 0};
+        LAUNCH(rg_launch_sa_attention(m->big, src_mask, sp, nullptr, rg_out_b16(m->a16, D * P, lo ? D : 0), B, T, 1, st));
+        if (tc_gemm(m, m->tm_a16, D, t.sa_o, ly.sa_bo, M, D, D, RG_EPI_BIAS_RESIDUAL, m->h, m->h, D, nullptr, 0, st)) return 1;
+        // --- three cross-attentions on the same h
+        LAUNCH(rg_launch_ln_rows(m->h, D, nullptr, nullptr, rg_out_b16(m->a16, D * P, lo ? D : 0), M, st));
+        if (tc_gemm(m, m->tm_a16, D, t.caq, ly.bcaq, M, 3 * D, D, RG_EPI_BIAS, nullptr, m->big, 3 * D, nullptr, 0, st)) return 1;
+        RgStylParams sp3[3];
+        for (int c = 0; c < 3; ++c) sp3[c] = {ly.ca_g + c * D, ly.ca_b + c * D, ss + (1 + c) * 2 * D, 0};
+        LAUNCH(rg_launch_ca_attention(m->big, 3 * D, state + (long long)l * 3 * HS, clip_stride, HS, query_mask,
+                                      (long long)B * T, sp3, rg_out_b16(m->a16w, 3 * D * P, lo ? 3 * D : 0), B, T, 3, st));
+        if (tc_gemm(m, m->tm_a16w, 3 * D, t.ca_o, ly.ca_bo, M, D, D, RG_EPI_BIAS_RESIDUAL, m->h, nullptr, 0, m->o16,
+                    3 * D, st, 3, D, D, D)) return 1;
+        if (tc_gemm(m, m->tm_o16, 3 * D, t.mix, ly.bmix, M, D, 3 * D, RG_EPI_BIAS, nullptr, m->h, D, m->h16, D, st)) return 1;
+        // --- FFN
+        if (tc_gemm(m, m->tm_h16, D, t.w1, ly.b1, M, F, D, RG_EPI_BIAS_GELU, nullptr, nullptr, 0, m->g16, F, st)) return 1;
+        if (tc_gemm(m, m->tm_g16, F, t.w2, ly.b2, M, D, F, RG_EPI_BIAS, nullptr, m->y, D, nullptr, 0, st)) return 1;
+        RgStylParams spf = {ly.ffn_g, ly.ffn_b, ss + 4 * 2 * D, 0};
+        LAUNCH(rg_launch_styl_rows(m->y, D, spf, T, rg_out_b16(m->a16, D * P, lo ? D : 0), M, st));
+        if (tc_gemm(m, m->tm_a16, D, t.ffn_o, ly.ffn_bo, M, D, D, RG_EPI_BIAS_RESIDUAL, m->h, m->h, D, m->h16, D, st)) return 1;
+    }
+    return tc_gemm(m, m->tm_h16, D, m->tc_out, m->b_out, M, D, D, RG_EPI_BIAS, nullptr, x0_out, D, nullptr, 0, st);
 }
 
 extern "C" int rg_denoise(rg_handle m, const float* x, int B, int step_idx, int tau,
@@ -428,6 +540,8 @@ extern "C" int rg_denoise(rg_handle m, const float* x, int B, int step_idx, int 
         ssrow = m->tau_row;
     }
     if (ensure_ws(m, M)) return 1;
+    if (m->cfg.precision != RG_PREC_FP32)
+        return denoise_tc(m, x, B, ssrow, src_mask, query_mask, state, x0_out, st);
     const long long clip_stride = rg_state_floats_per_clip(m);
     const long long HS = (long long)RG_H * RG_HD * RG_HD;
 
@@ -441,22 +555,22 @@ extern "C" int rg_denoise(rg_handle m, const float* x, int B, int step_idx, int 
         const Layer& ly = m->layers[l];
         const float* ss = ssrow + (long long)l * 5 * 2 * D;
         // --- self-attention
-        LAUNCH(rg_launch_ln_rows(m->h, D, nullptr, nullptr, m->a, D, M, st));
+        LAUNCH(rg_launch_ln_rows(m->h, D, nullptr, nullptr, rg_out_f32(m->a, D), M, st));
         LAUNCH(rg_launch_gemm_f32(mk_gemm(m->a, D, ly.Wqkv, ly.bqkv, m->big, 3 * D, M, 3 * D, D, RG_EPI_BIAS), st));
         RgStylParams sp = {ly.sa_g, ly.sa_b, ss, 0};
-        LAUNCH(rg_launch_sa_attention(m->big, src_mask, sp, nullptr, m->a, B, T, 1, st));
+        LAUNCH(rg_launch_sa_attention(m->big, src_mask, sp, nullptr, rg_out_f32(m->a, D), B, T, 1, st));
         {
             RgGemm g = mk_gemm(m->a, D, ly.sa_Wo, ly.sa_bo, m->h, D, M, D, D, RG_EPI_BIAS_RESIDUAL);
             g.R = m->h; g.ldr = D;
             LAUNCH(rg_launch_gemm_f32(g, st));
         }
         // --- three cross-attentions on the same h
-        LAUNCH(rg_launch_ln_rows(m->h, D, nullptr, nullptr, m->a, D, M, st));
+        LAUNCH(rg_launch_ln_rows(m->h, D, nullptr, nullptr, rg_out_f32(m->a, D), M, st));
         LAUNCH(rg_launch_gemm_f32(mk_gemm(m->a, D, ly.Wcaq, ly.bcaq, m->big, 3 * D, M, 3 * D, D, RG_EPI_BIAS), st));
         RgStylParams sp3[3];
         for (int c = 0; c < 3; ++c) sp3[c] = {ly.ca_g + c * D, ly.ca_b + c * D, ss + (1 + c) * 2 * D, 0};
         LAUNCH(rg_launch_ca_attention(m->big, 3 * D, state + (long long)l * 3 * HS, clip_stride, HS, query_mask,
-                                      (long long)B * T, sp3, m->a, 3 * D, B, T, 3, st));
+                                      (long long)B * T, sp3, rg_out_f32(m->a, 3 * D), B, T, 3, st));
         {
             RgGemm g = mk_gemm(m->a, 3 * D, ly.ca_Wo, ly.ca_bo, m->o3, 3 * D, M, D, D, RG_EPI_BIAS_RESIDUAL);
             g.groups = 3; g.a_g = D; g.w_g = (long long)D * D; g.b_g = D; g.c_g = D; g.R = m->h; g.ldr = D; g.r_g = 0;
@@ -467,7 +581,7 @@ extern "C" int rg_denoise(rg_handle m, const float* x, int B, int step_idx, int 
         LAUNCH(rg_launch_gemm_f32(mk_gemm(m->h, D, ly.W1, ly.b1, m->g, F, M, F, D, RG_EPI_BIAS_GELU), st));
         LAUNCH(rg_launch_gemm_f32(mk_gemm(m->g, F, ly.W2, ly.b2, m->y, D, M, D, F, RG_EPI_BIAS), st));
         RgStylParams spf = {ly.ffn_g, ly.ffn_b, ss + 4 * 2 * D, 0};
-        LAUNCH(rg_launch_styl_rows(m->y, D, spf, T, m->a, D, M, st));
+        LAUNCH(rg_launch_styl_rows(m->y, D, spf, T, rg_out_f32(m->a, D), M, st));
         {
             RgGemm g = mk_gemm(m->a, D, ly.ffn_Wo, ly.ffn_bo, m->h, D, M, D, D, RG_EPI_BIAS_RESIDUAL);
             g.R = m->h; g.ldr = D;
@@ -562,7 +676,7 @@ extern "C" int rg_op_linear_tc(const float* x, const float* W, const float* b, c
 }
 extern "C" int rg_op_layernorm(const float* x, const float* gamma, const float* beta, float* out,
                                int M, void* stream) {
-    LAUNCH(rg_launch_ln_rows(x, RG_D, gamma, beta, out, RG_D, M, (cudaStream_t)stream));
+    LAUNCH(rg_launch_ln_rows(x, RG_D, gamma, beta, rg_out_f32(out, RG_D), M, (cudaStream_t)stream));
     return 0;
 }
 extern "C" int rg_op_silu(const float* x, float* out, int64_t n, void* stream) {
@@ -573,7 +687,7 @@ extern "C" int rg_op_stylization_rows(const float* y, const float* gamma, const 
                                       const float* ss, int ss_per_clip, int rows_per_clip,
                                       float* out, int M, void* stream) {
     RgStylParams sp = {gamma, beta, ss, ss_per_clip ? 2 * RG_D : 0};
-    LAUNCH(rg_launch_styl_rows(y, RG_D, sp, rows_per_clip, out, RG_D, M, (cudaStream_t)stream));
+    LAUNCH(rg_launch_styl_rows(y, RG_D, sp, rows_per_clip, rg_out_f32(out, RG_D), M, (cudaStream_t)stream));
     return 0;
 }
 extern "C" int rg_op_self_attention(const float* qkv, const float* src_mask, const float* gamma,
@@ -583,7 +697,7 @@ extern "C" int rg_op_self_attention(const float* qkv, const float* src_mask, con
     if (T > RG_MAX_T) return rg_fail("rg_op_self_attention: T=%d > %d", T, RG_MAX_T);
     if (!with_styl && !x_res) return rg_fail("rg_op_self_attention: x_res required when with_styl=0");
     RgStylParams sp = {gamma, beta, ss, ss_per_clip ? 2 * RG_D : 0};
-    LAUNCH(rg_launch_sa_attention(qkv, src_mask, sp, x_res, out, B, T, with_styl, (cudaStream_t)stream));
+    LAUNCH(rg_launch_sa_attention(qkv, src_mask, sp, x_res, rg_out_f32(out, RG_D), B, T, with_styl, (cudaStream_t)stream));
     return 0;
 }
 extern "C" int rg_op_cross_attention(const float* q, const float* state, const float* query_mask,
@@ -593,8 +707,8 @@ extern "C" int rg_op_cross_attention(const float* q, const float* state, const f
     RgStylParams sp[3];
     sp[0] = {gamma, beta, ss, ss_per_clip ? 2 * RG_D : 0};
     sp[1] = sp[0]; sp[2] = sp[0];
-    LAUNCH(rg_launch_ca_attention(q, RG_D, state, (long long)RG_H * RG_HD * RG_HD, 0, query_mask, 0, sp, out,
-                                  RG_D, B, T, 1, (cudaStream_t)stream));
+    LAUNCH(rg_launch_ca_attention(q, RG_D, state, (long long)RG_H * RG_HD * RG_HD, 0, query_mask, 0, sp,
+                                  rg_out_f32(out, RG_D), B, T, 1, (cudaStream_t)stream));
     return 0;
 }
 extern "C" int rg_op_kv_state(const float* kv, int n_tokens, int B, float* state, void* stream) {

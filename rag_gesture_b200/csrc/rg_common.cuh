@@ -40,13 +40,27 @@ struct RgStylParams {           // one StylizationBlock's row-wise part
     long long ss_clip_stride;   // 0: the same row for every clip (one timestep for the batch)
 };
 
+// Destination of a row-wise kernel: fp32 rows, or bf16 rows (hi plane, plus the lo = bf16(x - hi)
+// plane lo_off columns further when lo_off != 0) for the tensor-core GEMM that consumes them.
+struct RgRowOut {
+    float* f32;
+    __nv_bfloat16* b16;
+    int ld;
+    int lo_off;
+};
+static inline RgRowOut rg_out_f32(float* p, int ld) { RgRowOut o = {p, nullptr, ld, 0}; return o; }
+static inline RgRowOut rg_out_b16(void* p, int ld, int lo_off) {
+    RgRowOut o = {nullptr, reinterpret_cast<__nv_bfloat16*>(p), ld, lo_off};
+    return o;
+}
+
 cudaError_t rg_launch_gemm_f32(const RgGemm& g, cudaStream_t st);
 
 // rowops.cu
 cudaError_t rg_launch_ln_rows(const float* x, int ldx, const float* gamma, const float* beta,
-                              float* out, int ldo, int M, cudaStream_t st);
+                              RgRowOut out, int M, cudaStream_t st);
 cudaError_t rg_launch_styl_rows(const float* y, int ldy, RgStylParams sp, int rows_per_clip,
-                                float* out, int ldo, int M, cudaStream_t st);
+                                RgRowOut out, int M, cudaStream_t st);
 cudaError_t rg_launch_silu(const float* x, float* out, long long n, cudaStream_t st);
 cudaError_t rg_launch_gather_rows(const float* table, const long long* idx, float* out,
                                   long long n_rows, int n_table, cudaStream_t st);
@@ -65,12 +79,12 @@ cudaError_t rg_launch_pos_table(const float* seq_pe, const float* glob_pe, float
 
 // attention.cu
 cudaError_t rg_launch_sa_attention(const float* qkv, const float* src_mask, RgStylParams sp,
-                                   const float* x_res, float* out, int B, int T, int with_styl,
+                                   const float* x_res, RgRowOut out, int B, int T, int with_styl,
                                    cudaStream_t st);
 cudaError_t rg_launch_ca_attention(const float* q3, int ldq, const float* state,
                                    long long state_clip_stride, long long state_cond_stride,
                                    const float* qmask, long long qmask_cond_stride,
-                                   const RgStylParams* sp3, float* out, int ldo, int B, int T,
+                                   const RgStylParams* sp3, RgRowOut out, int B, int T,
                                    int n_cond, cudaStream_t st);
 cudaError_t rg_launch_kv_state(const float* kv, int ldkv, int k_off, int v_off, int n_tokens,
                                float* state, long long state_clip_stride, int B, int n_sets,

@@ -11,6 +11,28 @@ __device__ __forceinline__ void store_row(float* p, int lane, const float4 v[4])
     for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(p + (lane + 32 * j) * 4) = v[j];
 }
 
+// one 512-wide row (starting at column col0 of row `row`) to an RgRowOut destination
+__device__ __forceinline__ void rg_store_row_out(const RgRowOut& o, long long row, int col0, int lane,
+                                                 const float4 v[4]) {
+    if (o.f32) {
+        store_row(o.f32 + row * o.ld + col0, lane, v);
+        return;
+    }
+    __nv_bfloat16* base = o.b16 + row * o.ld + col0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float f[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+        __nv_bfloat16 h[4], l[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            h[k] = __float2bfloat16_rn(f[k]);
+            l[k] = __float2bfloat16_rn(f[k] - __bfloat162float(h[k]));
+        }
+        *reinterpret_cast<uint2*>(base + (lane + 32 * j) * 4) = *reinterpret_cast<uint2*>(h);
+        if (o.lo_off) *reinterpret_cast<uint2*>(base + o.lo_off + (lane + 32 * j) * 4) = *reinterpret_cast<uint2*>(l);
+    }
+}
+
 // two-pass LayerNorm statistics over a 512-wide row spread across the warp (eps = 1e-5)
 __device__ __forceinline__ void rg_ln_normalize(float4 v[4]) {
     float s = 0.f;

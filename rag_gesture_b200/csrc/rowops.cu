@@ -15,7 +15,7 @@ constexpr int ROWS_PER_BLOCK = 8;   // 8 warps
 __global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ x, int ldx,
                                                      const float* __restrict__ gamma,
                                                      const float* __restrict__ beta,
-                                                     float* __restrict__ out, int ldo, int M) {
+                                                     RgRowOut out, int M) {
     const int row = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= M) return;
@@ -30,19 +30,19 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ 
             v[j] = affine4(v[j], g, b);
         }
     }
-    store_row(out + (long long)row * ldo, lane, v);
+    rg_store_row_out(out, row, 0, lane, v);
 }
 
 __global__ void __launch_bounds__(256) styl_rows_kernel(const float* __restrict__ y, int ldy,
                                                        RgStylParams sp, int rows_per_clip,
-                                                       float* __restrict__ out, int ldo, int M) {
+                                                       RgRowOut out, int M) {
     const int row = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= M) return;
     float4 v[4];
     load_row(y + (long long)row * ldy, lane, v);
     rg_styl_row(v, sp, row / rows_per_clip, lane);
-    store_row(out + (long long)row * ldo, lane, v);
+    rg_store_row_out(out, row, 0, lane, v);
 }
 
 __global__ void silu_kernel(const float* __restrict__ x, float* __restrict__ out, long long n) {
@@ -178,15 +178,15 @@ inline int row_blocks(long long rows) { return (int)((rows + ROWS_PER_BLOCK - 1)
 }  // namespace
 
 cudaError_t rg_launch_ln_rows(const float* x, int ldx, const float* gamma, const float* beta,
-                              float* out, int ldo, int M, cudaStream_t st) {
+                              RgRowOut out, int M, cudaStream_t st) {
     if (M <= 0) return cudaSuccess;
-    ln_rows_kernel<<<row_blocks(M), 256, 0, st>>>(x, ldx, gamma, beta, out, ldo, M);
+    ln_rows_kernel<<<row_blocks(M), 256, 0, st>>>(x, ldx, gamma, beta, out, M);
     return cudaGetLastError();
 }
 cudaError_t rg_launch_styl_rows(const float* y, int ldy, RgStylParams sp, int rows_per_clip,
-                                float* out, int ldo, int M, cudaStream_t st) {
+                                RgRowOut out, int M, cudaStream_t st) {
     if (M <= 0) return cudaSuccess;
-    styl_rows_kernel<<<row_blocks(M), 256, 0, st>>>(y, ldy, sp, rows_per_clip, out, ldo, M);
+    styl_rows_kernel<<<row_blocks(M), 256, 0, st>>>(y, ldy, sp, rows_per_clip, out, M);
     return cudaGetLastError();
 }
 cudaError_t rg_launch_silu(const float* x, float* out, long long n, cudaStream_t st) {

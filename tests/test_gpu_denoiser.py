@@ -212,3 +212,64 @@ def test_batch_sizes_and_ragged(model, diffusion, dev):
             n = sl.stop - sl.start
             out = model(x[sl].contiguous(), torch.full((n,), 600, device=dev), **_kw(model, sub, n, dev))
             assert torch.equal(out, full[sl])
+
+
+# ---- tensor-core precisions (tcgen05): bf16x3 = fp32 tier (<= 1e-3), bf16 = reduced tier (<= 2e-2) ----------
+from rag_gesture_b200 import _lib as _L  # noqa: E402
+
+TC_TIERS = [(_L.PREC_BF16X3, 1e-4, 1e-3), (_L.PREC_BF16, 1e-2, 2e-2)]
+
+
+@pytest.fixture(scope="module", params=TC_TIERS, ids=["bf16x3", "bf16"])
+def tc_model(request, dev, sd0):
+    from rag_gesture_b200 import mogen_api as M
+    prec, tol_step, tol_loop = request.param
+    m = M.build_submodule(dict(C.denoiser_cfg(), precision=prec), database=None, use_retrieval_for_test=False)
+    m.load_state_dict(sd0, strict=False)
+    return m.to(dev).eval(), tol_step, tol_loop
+
+
+def test_tc_denoiser_step_vs_golden(tc_model, golden, dev):
+    model, tol_step, _ = tc_model
+    g = golden("denoiser_step")
+    B = 2
+    kw = _kw(model, S.synthetic_conditions(B, seed=11), B, dev)
+    x = S.synthetic_latents(B, seed=12).to(dev)
+    with torch.no_grad():
+        for tau in (14, 514, 999):
+            out = model(x, torch.full((B,), tau, device=dev), **kw).cpu()
+            err = rel_l2(out, torch.from_numpy(g[f"x0_t{tau}"]))
+            print(f"precision {model.precision} tau {tau}: rel-L2 {err:.3g}")
+            assert err < tol_step, tau
+
+
+def test_tc_loops_vs_golden(tc_model, diffusion, golden, dev):
+    model, _, tol_loop = tc_model
+    g = golden("ddim_plain_b1")
+    kw = _kw(model, S.synthetic_conditions(1, seed=21), 1, dev)
+    tape = S.NoiseTape(1234)
+    diffusion.noise_fn = tape.randn
+    final = diffusion.ddim_sample_loop(model, (1, C.N_TOKENS, C.LATENT_DIM), clip_denoised=False,
+                                       model_kwargs=kw, eta=0).cpu()
+    diffusion.noise_fn = None
+    err = rel_l2(final, torch.from_numpy(g["final"]))
+    gr = golden("ddim_reverse_b1")
+    xs = S.synthetic_latents(1, seed=22, scale=0.5).to(dev)
+    inv = diffusion.ddim_reverse_sample_loop(model, start_img=xs, clip_denoised=False, model_kwargs=kw, eta=0)
+    err_r = rel_l2(inv.cpu(), torch.from_numpy(gr["inv49"]))
+    print(f"precision {model.precision}: plain loop rel-L2 {err:.3g}, reverse loop {err_r:.3g}")
+    assert err < tol_loop and err_r < tol_loop
+
+
+def test_tc_batch_independence(tc_model, dev):
+    """Ragged M (TMA zero-fill, row guards): a clip's answer does not depend on its batch."""
+    model, _, _ = tc_model
+    B = 7
+    cond = S.synthetic_conditions(B, seed=61)
+    kw = _kw(model, cond, B, dev)
+    x = S.synthetic_latents(B, seed=62).to(dev)
+    with torch.no_grad():
+        full = model(x, torch.full((B,), 300, device=dev), **kw)
+        sub = {k: v[3:4] for k, v in cond.items()}
+        one = model(x[3:4].contiguous(), torch.full((1,), 300, device=dev), **_kw(model, sub, 1, dev))
+    assert torch.equal(one, full[3:4])
