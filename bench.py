@@ -127,8 +127,11 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     hbm_peak, tc_burst, tc_sus, peak_src = peaks()
 
+    from rag_gesture_b200 import _lib
+    prec = {"bf16": _lib.PREC_BF16, "bf16x3": _lib.PREC_BF16X3, "fp32": _lib.PREC_FP32}[args.precision]
     cfg = C.model_cfg()
     cfg["use_retrieval_for_test"] = True
+    cfg["model"]["precision"] = prec
     arch = R.build_architecture(cfg, database=S.SyntheticGestureDataset(N_DB, seed=7))
     arch.model.load_state_dict(S.synthetic_state_dict(0), strict=False)
     arch = arch.to(dev).eval()
@@ -192,18 +195,22 @@ def run_b200(args):
     e2e_value = float(total_steps) * args.steps / t_e2e
 
     # ---- roofline of the dominant kernel family: the dense GEMMs of one denoiser evaluation --------------
-    roof = gemm_roofline(arch, B + E, dev, flush, tc_sus, peak_src)
+    roof = gemm_roofline(arch, B + E, dev, flush, tc_sus, peak_src, args.precision)
     knn = knn_bench(args, dev, rank, world, hbm_peak, peak_src, flush)
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(1e3 * t_hot / args.steps, 3), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": {"bf16": "bf16", "bf16x3": "bf16x3", "fp32": "f32"}[args.precision],
+            "data": "synthetic",
             "config": {"workload": "configs[1]: 64 clips/GPU guided DDIM (discourse retrieval, inversion + "
                                    "insertion guidance decreasing_till_25, len150@15fps)",
                        "clips_per_gpu": B, "exemplars_rank0": E, "clip_steps_per_step_rank0": clip_steps,
-                       "db_entries": N_DB, "ddim_steps": STEPS, "precision": "fp32 (exact tier)",
+                       "db_entries": N_DB, "ddim_steps": STEPS,
+                       "precision": {"bf16": "tcgen05 bf16 operands, fp32 TMEM accumulate (parity tier rel-L2 <= 2e-2)",
+                                     "bf16x3": "tcgen05 hi+lo bf16 split, 3 products (parity tier rel-L2 <= 1e-3)",
+                                     "fp32": "fp32 FMA GEMMs (exact tier)"}[args.precision],
                        "l2": "256 MiB flush between timed iterations; fp32 weights (564 MB) exceed L2",
                        "parallelism": f"clips sharded over {world} GPU(s), no collective in the loop"},
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes(batch),
@@ -219,10 +226,12 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-def gemm_roofline(arch, n_clips, dev, flush, tc_peak, peak_src):
-    """Every dense contraction of one denoiser evaluation, timed per shape through rg_op_linear
-    (same kernel, same shapes as inside rg_denoise) with CUDA events on the launching stream."""
-    from rag_gesture_b200 import ops
+def gemm_roofline(arch, n_clips, dev, flush, tc_peak, peak_src, precision):
+    """Every dense contraction of one denoiser evaluation, timed per shape (same kernel, same shapes
+    as inside rg_denoise) with CUDA events on the launching stream, L2 flushed between launches."""
+    from rag_gesture_b200 import _lib, ops
+    if precision != "fp32":
+        return gemm_roofline_tc(n_clips, dev, flush, tc_peak, peak_src, precision == "bf16x3")
     M = n_clips * 43
     shapes = [("qkv", 1536, 512, 8), ("sa_proj", 512, 512, 8), ("ca_q", 1536, 512, 8), ("ca_proj", 512, 512, 24),
               ("ca_mix", 512, 1536, 8), ("ffn1", 1024, 512, 8), ("ffn2", 512, 1024, 8), ("ffn_proj", 512, 512, 8),
@@ -251,6 +260,35 @@ def gemm_roofline(arch, n_clips, dev, flush, tc_peak, peak_src):
             "frac": round(ach / tc_peak, 4), "traffic": None, "peak_source": f"{peak_src} bf16 sustained",
             "rows": M, "per_shape_tflops": per,
             "note": "exact fp32 tier runs on CUDA cores; the tcgen05 bf16 path is the next kernel"}
+
+
+def gemm_roofline_tc(n_clips, dev, flush, tc_peak, peak_src, split):
+    """tcgen05 GEMM launches alone (operands pre-converted to bf16 planes, as inside rg_denoise):
+    ALGORITHMIC flops 2*M*N*K per launch (bf16x3 executes 3x that on the pipe) / event time."""
+    import ctypes
+    from rag_gesture_b200 import _lib
+    lib = _lib.load()
+    M = n_clips * 43
+    shapes = [("qkv", 1536, 512, 8), ("sa_proj", 512, 512, 8), ("ca_q", 1536, 512, 8), ("ca_proj", 512, 512, 24),
+              ("ca_mix", 512, 1536, 8), ("ffn1", 1024, 512, 8), ("ffn2", 512, 1024, 8), ("ffn_proj", 512, 512, 8),
+              ("embed/out", 512, 512, 2)]
+    tot_t, tot_f, per = 0.0, 0.0, {}
+    for name, N, K, count in shapes:
+        x, w, b = torch.randn(M, K, device=dev), torch.randn(N, K, device=dev), torch.randn(N, device=dev)
+        out = torch.empty(M, N, device=dev)
+        ts = ctypes.c_float()
+        _lib.check(lib.rg_probe_gemm_tc(_lib.ptr(x), _lib.ptr(w), _lib.ptr(b), _lib.ptr(out), M, N, K, int(split),
+                                        5, _lib.ptr(flush), flush.numel(), ctypes.byref(ts), _lib.stream_ptr()))
+        t = ts.value / 1e3
+        per[name] = round(2.0 * M * N * K / t / 1e12, 1)
+        tot_t += t * count
+        tot_f += 2.0 * M * N * K * count
+    ach = tot_f / tot_t / 1e12
+    return {"bound": "tensor", "kernel": "gemm_tc_kernel<128> (tcgen05.mma kind::f16, TMA-fed, TMEM accumulator; all "
+            "GEMM shapes of one denoiser evaluation, time-weighted)", "achieved": round(ach, 1), "peak": tc_peak,
+            "unit": "TFLOP/s", "frac": round(ach / tc_peak, 4), "traffic": None,
+            "peak_source": f"{peak_src} bf16 sustained", "rows": M, "per_shape_tflops": per,
+            "executed_flop_multiplier": 3 if split else 1}
 
 
 def knn_bench(args, dev, rank, world, hbm_peak, peak_src, flush):
@@ -368,6 +406,7 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3", "fp32"])
     ap.add_argument("--knn-n", type=int, default=1_000_000)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     a = ap.parse_args()

@@ -135,6 +135,11 @@ int rg_op_linear(const float* x, int ldx, const float* W, const float* b, const 
  * when split) may be NULL.  Used by the unit parity tests and bench.py's roofline probe. */
 int rg_op_linear_tc(const float* x, const float* W, const float* b, const float* residual, float* out,
                     void* out_bf16, int M, int N, int K, int epilogue, int split, void* stream);
+/* Measurement probe for bench.py's roofline: converts operands once, then times `reps` launches of the
+ * tcgen05 GEMM alone with CUDA events on `stream` (flush_buf, if given, is overwritten before every
+ * launch to evict L2); *median_ms receives the median launch time.  Synchronises. */
+int rg_probe_gemm_tc(const float* x, const float* W, const float* b, float* out, int M, int N, int K,
+                     int split, int reps, void* flush_buf, int64_t flush_bytes, float* median_ms, void* stream);
 /* LayerNorm over 512-wide rows, eps 1e-5; gamma/beta may be NULL (no affine). */
 int rg_op_layernorm(const float* x, const float* gamma, const float* beta, float* out, int M,
                     void* stream);

@@ -36,6 +36,7 @@ SIGNATURES = {
     "rg_guidance_steps": (_I, [_P, _P, _P, _L, _I, _F, _L, _P]),
     "rg_op_linear": (_I, [_P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "rg_op_linear_tc": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "rg_probe_gemm_tc": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _L, C.POINTER(C.c_float), _P]),
     "rg_op_layernorm": (_I, [_P, _P, _P, _P, _I, _P]),
     "rg_op_silu": (_I, [_P, _P, _L, _P]),
     "rg_op_stylization_rows": (_I, [_P, _P, _P, _P, _I, _I, _P, _I, _P]),

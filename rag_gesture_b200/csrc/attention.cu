@@ -34,59 +34,130 @@ __device__ __forceinline__ void finish_rows(const float* Ysm, int T, int clip, c
     }
 }
 
-// Y[n, lane] = sum_d softmax_d(q[n, :])[d] * A[d]   for one head
-__device__ __forceinline__ float q_dot_A(float q, const float A[RG_HD]) {
-    const float qmax = rg_warp_max(q);
-    const float e = expf(q - qmax);
-    const float qs = e / rg_warp_sum(e);
-    float y = 0.f;
+// Per head (= per warp) the kernels keep A[32][32] as 32 registers per lane (lane = output feature l)
+// and use this warp's [T][32] slice of the shared Y buffer three times over: first for exp(K - max),
+// then for softmax(Q), finally for Y itself.  Rows are read back as broadcast 128-bit LDS (all lanes
+// read the same 4 values), so the 32x32 contractions run on the FMA pipe instead of 32 shuffles per
+// token (shuffle issue rate, not arithmetic, bounded the first version: 56 us -> see profiles/).
+__device__ __forceinline__ void row_times_A(const float* row, const float A[RG_HD], float& y) {
+    y = 0.f;
 #pragma unroll
-    for (int d = 0; d < RG_HD; ++d) y = fmaf(__shfl_sync(0xffffffffu, qs, d), A[d], y);
-    return y;
+    for (int d4 = 0; d4 < RG_HD / 4; ++d4) {
+        const float4 q = *reinterpret_cast<const float4*>(row + d4 * 4);
+        y = fmaf(q.x, A[d4 * 4 + 0], y); y = fmaf(q.y, A[d4 * 4 + 1], y);
+        y = fmaf(q.z, A[d4 * 4 + 2], y); y = fmaf(q.w, A[d4 * 4 + 3], y);
+    }
 }
 
-__global__ void __launch_bounds__(512) sa_attn_kernel(const float* __restrict__ qkv,
-                                                     const float* __restrict__ src_mask,
-                                                     RgStylParams sp, const float* __restrict__ x_res,
-                                                     RgRowOut out, int T, int with_styl) {
+// softmax over the 32 head features of Q for tokens [0,T) -> slice[n][lane]; loads batched CH-wide
+__device__ __forceinline__ void q_softmax_to_smem(const float* qcol, long long stride, int T, float* slice, int lane) {
+    constexpr int CH = 8;
+    for (int n0 = 0; n0 < T; n0 += CH) {
+        float qq[CH];
+#pragma unroll
+        for (int i = 0; i < CH; ++i) qq[i] = (n0 + i < T) ? qcol[(n0 + i) * stride] : 0.f;
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+            if (n0 + i < T) {
+                const float e = expf(qq[i] - rg_warp_max(qq[i]));
+                slice[(n0 + i) * RG_D + lane] = e / rg_warp_sum(e);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(512, 2) sa_attn_kernel(const float* __restrict__ qkv,
+                                                        const float* __restrict__ src_mask,
+                                                        RgStylParams sp, const float* __restrict__ x_res,
+                                                        RgRowOut out, int T, int with_styl) {
     extern __shared__ __align__(16) float Ysm[];   // [T][512]
     const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float* base = qkv + (long long)b * T * (3 * RG_D) + warp * RG_HD + lane;
     const float* mrow = src_mask + (long long)b * T;
-
-    // token softmax of K (column `lane` of this head): max, then normaliser
+    float* slice = Ysm + warp * RG_HD;              // this head's [T][32] window, row pitch 512
+    constexpr int CH = 8;
+    const long long RS = 3 * RG_D;
+    // sweep 1: column max of K (+ -1e6 on masked tokens, efficient_attention.py:32); lane = feature d
     float kmax = -INFINITY;
-    for (int n = 0; n < T; ++n)
-        kmax = fmaxf(kmax, base[(long long)n * (3 * RG_D) + RG_D] + (1.0f - mrow[n]) * RG_NEG_MASK);
+    for (int n0 = 0; n0 < T; n0 += CH) {
+        float kk[CH];
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+            const int n = n0 + i;
+            kk[i] = n < T ? base[n * RS + RG_D] + (1.0f - mrow[n]) * RG_NEG_MASK : -INFINITY;
+        }
+#pragma unroll
+        for (int i = 0; i < CH; ++i) kmax = fmaxf(kmax, kk[i]);
+    }
+    // sweep 2a: E[n][d] = exp(K - max) -> smem, column sums in registers
     float ksum = 0.f;
-    for (int n = 0; n < T; ++n)
-        ksum += expf(base[(long long)n * (3 * RG_D) + RG_D] + (1.0f - mrow[n]) * RG_NEG_MASK - kmax);
-
-    // A[d][lane] = sum_n softmaxK[n][d] * (V[n][lane] * mask[n])
+    for (int n0 = 0; n0 < T; n0 += CH) {
+        float kk[CH];
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+            const int n = n0 + i;
+            kk[i] = n < T ? base[n * RS + RG_D] + (1.0f - mrow[n]) * RG_NEG_MASK : -INFINITY;
+        }
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+            if (n0 + i < T) {
+                const float e = expf(kk[i] - kmax);
+                ksum += e;
+                slice[(n0 + i) * RG_D + lane] = e;
+            }
+        }
+    }
+    __syncwarp();
+    // sweep 2b: A[d][lane] = sum_n E[n][d] * (V[n][lane] * mask[n]); lane = feature l
     float A[RG_HD];
 #pragma unroll
     for (int d = 0; d < RG_HD; ++d) A[d] = 0.f;
-    for (int n = 0; n < T; ++n) {
-        const float m = mrow[n];
-        const float kk = base[(long long)n * (3 * RG_D) + RG_D] + (1.0f - m) * RG_NEG_MASK;
-        const float ks = expf(kk - kmax) / ksum;
-        const float vv = base[(long long)n * (3 * RG_D) + 2 * RG_D] * m;
+    for (int n0 = 0; n0 < T; n0 += CH) {
+        float vv[CH];
 #pragma unroll
-        for (int d = 0; d < RG_HD; ++d) A[d] = fmaf(__shfl_sync(0xffffffffu, ks, d), vv, A[d]);
+        for (int i = 0; i < CH; ++i) vv[i] = (n0 + i < T) ? base[(n0 + i) * RS + 2 * RG_D] * mrow[n0 + i] : 0.f;
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+            if (n0 + i < T) {
+                const float* row = slice + (n0 + i) * RG_D;
+#pragma unroll
+                for (int d4 = 0; d4 < RG_HD / 4; ++d4) {
+                    const float4 e = *reinterpret_cast<const float4*>(row + d4 * 4);
+                    A[d4 * 4 + 0] = fmaf(e.x, vv[i], A[d4 * 4 + 0]); A[d4 * 4 + 1] = fmaf(e.y, vv[i], A[d4 * 4 + 1]);
+                    A[d4 * 4 + 2] = fmaf(e.z, vv[i], A[d4 * 4 + 2]); A[d4 * 4 + 3] = fmaf(e.w, vv[i], A[d4 * 4 + 3]);
+                }
+            }
+        }
     }
-    for (int n = 0; n < T; ++n)
-        Ysm[n * RG_D + warp * RG_HD + lane] = q_dot_A(base[(long long)n * (3 * RG_D)], A);
+    __syncwarp();
+    slice[lane] = ksum;                              // row 0 is free again: publish the normalisers
+    __syncwarp();
+#pragma unroll
+    for (int d4 = 0; d4 < RG_HD / 4; ++d4) {
+        const float4 s4 = *reinterpret_cast<const float4*>(slice + d4 * 4);
+        A[d4 * 4 + 0] /= s4.x; A[d4 * 4 + 1] /= s4.y; A[d4 * 4 + 2] /= s4.z; A[d4 * 4 + 3] /= s4.w;
+    }
+    __syncwarp();
+    // sweep 3: softmax_features(Q) -> smem, then Y = Q A written in place
+    q_softmax_to_smem(base, RS, T, slice, lane);
+    __syncwarp();
+    for (int n = 0; n < T; ++n) {
+        float y;
+        row_times_A(slice + n * RG_D, A, y);
+        __syncwarp();
+        slice[n * RG_D + lane] = y;
+    }
     __syncthreads();
     finish_rows(Ysm, T, b, sp, with_styl, x_res, RG_D, out, 0, warp, lane);
 }
 
-__global__ void __launch_bounds__(512) ca_attn_kernel(const float* __restrict__ q3, int ldq,
-                                                     const float* __restrict__ state,
-                                                     long long state_clip_stride,
-                                                     long long state_cond_stride,
-                                                     const float* __restrict__ qmask,
-                                                     long long qmask_cond_stride, RgStyl3 sp3,
-                                                     RgRowOut out, int T) {
+__global__ void __launch_bounds__(512, 2) ca_attn_kernel(const float* __restrict__ q3, int ldq,
+                                                        const float* __restrict__ state,
+                                                        long long state_clip_stride,
+                                                        long long state_cond_stride,
+                                                        const float* __restrict__ qmask,
+                                                        long long qmask_cond_stride, RgStyl3 sp3,
+                                                        RgRowOut out, int T) {
     extern __shared__ __align__(16) float Ysm[];
     const int b = blockIdx.x, c = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float* Ap = state + (long long)b * state_clip_stride + (long long)c * state_cond_stride +
@@ -96,37 +167,97 @@ __global__ void __launch_bounds__(512) ca_attn_kernel(const float* __restrict__ 
     for (int d = 0; d < RG_HD; ++d) A[d] = __ldg(Ap + d * RG_HD);
     const float* qb = q3 + (long long)b * T * ldq + c * RG_D + warp * RG_HD + lane;
     const float* qm = qmask ? qmask + (long long)c * qmask_cond_stride + (long long)b * T : nullptr;
+    float* slice = Ysm + warp * RG_HD;
+    q_softmax_to_smem(qb, ldq, T, slice, lane);
+    __syncwarp();
     for (int n = 0; n < T; ++n) {
-        float y = q_dot_A(qb[(long long)n * ldq], A);
-        if (qm) y = y + (1.0f - qm[n]) * RG_NEG_MASK;     // fp32 add: y - 1e6 rounds to a 1/16 grid
-        Ysm[n * RG_D + warp * RG_HD + lane] = y;
+        float y;
+        row_times_A(slice + n * RG_D, A, y);
+        if (qm) y = y + (1.0f - qm[n]) * RG_NEG_MASK;       // fp32 add: y - 1e6 rounds to a 1/16 grid
+        __syncwarp();
+        slice[n * RG_D + lane] = y;
     }
     __syncthreads();
     finish_rows(Ysm, T, b, sp3.p[c], 1, nullptr, 0, out, c * RG_D, warp, lane);
 }
 
-// state[b][set][h][d][l] = sum_n softmax_n(K[b,n,h,d]) * V[b,n,h,l]; warp = d, lane = l
-__global__ void __launch_bounds__(1024) kv_state_kernel(const float* __restrict__ kv, int ldkv,
-                                                       int k_off, int v_off, int N,
-                                                       float* __restrict__ state,
-                                                       long long state_clip_stride,
-                                                       int kv_set_stride, long long state_set_stride) {
+// state[b][set][h][d][l] = sum_n softmax_n(K[b,n,h,d]) * V[b,n,h,l]   (K6; efficient_attention.py:78-89)
+// One CTA (256 threads) per (clip, head, set).  Pass 1: column max of K over the N tokens.  Pass 2:
+// tiles of 64 tokens staged in shared memory with coalesced 128-bit loads; exp(K - max) is evaluated
+// once per element, then E^T V (32x32 outputs, 4 per thread) accumulates from shared memory.
+constexpr int KV_TILE = 64;
+__global__ void __launch_bounds__(256) kv_state_kernel(const float* __restrict__ kv, int ldkv,
+                                                      int k_off, int v_off, int N,
+                                                      float* __restrict__ state,
+                                                      long long state_clip_stride,
+                                                      int kv_set_stride, long long state_set_stride) {
+    __shared__ __align__(16) float Es[KV_TILE][RG_HD + 1];   // +1: column reads in the product are conflict-free
+    __shared__ __align__(16) float Vs[KV_TILE][RG_HD];
+    __shared__ float red[8][RG_HD];
+    __shared__ float kmax_s[RG_HD], ksum_s[RG_HD];
     const int b = blockIdx.x, h = blockIdx.y, set = blockIdx.z;
-    const int d = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tid = threadIdx.x, lane = tid & 31, wg = tid >> 5;
     const float* rows = kv + (long long)b * N * ldkv + (long long)set * kv_set_stride;
-    const float* kcol = rows + k_off + h * RG_HD + d;
-    const float* vcol = rows + v_off + h * RG_HD + lane;
+    const float* kbase = rows + k_off + h * RG_HD;
+    const float* vbase = rows + v_off + h * RG_HD;
+    // pass 1: column max (lane = column, 8 warps stride over tokens, 4 loads in flight per thread)
     float m = -INFINITY;
-    for (int n = lane; n < N; n += 32) m = fmaxf(m, kcol[(long long)n * ldkv]);
-    m = rg_warp_max(m);
-    float s = 0.f;
-    for (int n = lane; n < N; n += 32) s += expf(kcol[(long long)n * ldkv] - m);
-    s = rg_warp_sum(s);
-    float acc = 0.f;
-    for (int n = 0; n < N; ++n)
-        acc = fmaf(expf(kcol[(long long)n * ldkv] - m), vcol[(long long)n * ldkv], acc);
-    state[(long long)b * state_clip_stride + (long long)set * state_set_stride +
-          ((long long)h * RG_HD + d) * RG_HD + lane] = acc / s;
+    for (int n0 = wg; n0 < N; n0 += 32) {
+        float t[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) t[i] = (n0 + 8 * i < N) ? kbase[(long long)(n0 + 8 * i) * ldkv + lane] : -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) m = fmaxf(m, t[i]);
+    }
+    red[wg][lane] = m;
+    __syncthreads();
+    if (wg == 0) {
+#pragma unroll
+        for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i][lane]);
+        kmax_s[lane] = m;
+        ksum_s[lane] = 0.f;
+    }
+    __syncthreads();
+    // pass 2
+    const int d = tid >> 3, l4 = (tid & 7) * 4;          // this thread's outputs: A[d][l4..l4+3]
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float colsum = 0.f;                                    // partial sum of exp for column (tid & 31) ...
+    const int ld_row = tid >> 3, ld_c4 = (tid & 7) * 4;    // tile loader: 32 rows x 8 float4 per pass
+    for (int n0 = 0; n0 < N; n0 += KV_TILE) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int r = ld_row + half * 32, n = n0 + r;
+            float4 kq = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY), vq = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n < N) {
+                kq = *reinterpret_cast<const float4*>(kbase + (long long)n * ldkv + ld_c4);
+                vq = *reinterpret_cast<const float4*>(vbase + (long long)n * ldkv + ld_c4);
+            }
+            Es[r][ld_c4 + 0] = expf(kq.x - kmax_s[ld_c4 + 0]);
+            Es[r][ld_c4 + 1] = expf(kq.y - kmax_s[ld_c4 + 1]);
+            Es[r][ld_c4 + 2] = expf(kq.z - kmax_s[ld_c4 + 2]);
+            Es[r][ld_c4 + 3] = expf(kq.w - kmax_s[ld_c4 + 3]);
+            *reinterpret_cast<float4*>(&Vs[r][ld_c4]) = vq;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int r = 0; r < KV_TILE; ++r) {
+            const float e = Es[r][d];
+            const float4 v = *reinterpret_cast<const float4*>(&Vs[r][l4]);
+            acc.x = fmaf(e, v.x, acc.x); acc.y = fmaf(e, v.y, acc.y);
+            acc.z = fmaf(e, v.z, acc.z); acc.w = fmaf(e, v.w, acc.w);
+        }
+        if (tid < RG_HD) {
+#pragma unroll 8
+            for (int r = 0; r < KV_TILE; ++r) colsum += Es[r][tid];
+        }
+        __syncthreads();
+    }
+    if (tid < RG_HD) ksum_s[tid] = colsum;
+    __syncthreads();
+    const float s = ksum_s[d];
+    float* o = state + (long long)b * state_clip_stride + (long long)set * state_set_stride +
+               ((long long)h * RG_HD + d) * RG_HD + l4;
+    *reinterpret_cast<float4*>(o) = make_float4(acc.x / s, acc.y / s, acc.z / s, acc.w / s);
 }
 
 }  // namespace
@@ -167,7 +298,7 @@ cudaError_t rg_launch_kv_state(const float* kv, int ldkv, int k_off, int v_off, 
                                float* state, long long state_clip_stride, int B, int n_sets,
                                int kv_set_stride, long long state_set_stride, cudaStream_t st) {
     if (B <= 0 || n_tokens <= 0) return cudaSuccess;
-    kv_state_kernel<<<dim3(B, RG_H, n_sets), 1024, 0, st>>>(kv, ldkv, k_off, v_off, n_tokens, state,
+    kv_state_kernel<<<dim3(B, RG_H, n_sets), 256, 0, st>>>(kv, ldkv, k_off, v_off, n_tokens, state,
                                                             state_clip_stride, kv_set_stride,
                                                             state_set_stride);
     return cudaGetLastError();

@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <map>
 #include <string>
 #include <vector>
@@ -62,7 +63,8 @@ struct rg_model {
     // tensor-core path (cfg.precision != RG_PREC_FP32)
     int planes;              // 1: bf16 operands, 2: hi|lo planes (bf16x3)
     std::vector<LayerTc> tc;
-    W16 tc_joint, tc_out;
+    W16 tc_joint, tc_out, tc_kv[3];
+    void* kv_a16;
     void *x16, *a16, *a16w, *o16, *h16, *g16;
     CUtensorMap tm_x16, tm_a16, tm_a16w, tm_o16, tm_h16, tm_g16;
     int device;
@@ -185,7 +187,7 @@ extern "C" int rg_create(const rg_config* cfg, int n_tensors, const char* const*
     m->kv_rows = 0; m->kv_ln = m->kv_buf = nullptr;
     m->tt_rows = 0; m->tt_emb = m->tt_t1 = m->tt_e = nullptr;
     m->planes = cfg->precision == RG_PREC_BF16X3 ? 2 : 1;
-    m->x16 = m->a16 = m->a16w = m->o16 = m->h16 = m->g16 = nullptr;
+    m->x16 = m->a16 = m->a16w = m->o16 = m->h16 = m->g16 = nullptr; m->kv_a16 = nullptr;
     const int D = RG_D, E = cfg->time_embed_dim, F = cfg->ffn_dim, L = cfg->num_layers, T = cfg->n_tokens;
     const long long DD = (long long)D * D;
     cudaStream_t st = 0;
@@ -306,6 +308,7 @@ extern "C" int rg_create(const rg_config* cfg, int n_tensors, const char* const*
         m->tc.resize(L);
         TRY(make_w16(m, m->W_joint, D, D, &m->tc_joint));
         TRY(make_w16(m, m->W_out, D, D, &m->tc_out));
+        for (int c = 0; c < 3; ++c) TRY(make_w16(m, m->Wkv_all[c], L * 2 * D, D, &m->tc_kv[c]));
         for (int l = 0; l < L; ++l) {
             const Layer& ly = m->layers[l];
             LayerTc& t = m->tc[l];
@@ -407,6 +410,10 @@ static int ensure_ws(rg_model* m, long long rows) {
     return 0;
 }
 
+static int tc_gemm(rg_model* m, const CUtensorMap& tmA, int a_w, const W16& w, const float* bias, int M, int N,
+                   int K, int epi, const float* R, float* C32, int ldc32, void* C16, int c16_w, cudaStream_t st,
+                   int groups = 1, int a_goff = 0, int w_goff = 0, int bc_goff = 0);
+
 extern "C" int64_t rg_state_floats_per_clip(rg_handle m) {
     return m ? (int64_t)m->cfg.num_layers * 3 * RG_H * RG_HD * RG_HD : 0;
 }
@@ -437,24 +444,38 @@ extern "C" int rg_precompute_clip_state(rg_handle m, const float* xf_text, const
     const long long clip_stride = rg_state_floats_per_clip(m);
     const float* xf[3] = {xf_text, xf_audio, xf_spk};
     const int nt[3] = {n_text, n_audio, n_spk};
-    const long long MAX_ROWS = 8192;
+    const long long MAX_ROWS = 32768;
     for (int c = 0; c < 3; ++c) {
         if (!xf[c] || nt[c] <= 0) return rg_fail("rg_precompute_clip_state: condition %d missing", c);
         const int N = nt[c];
         int per = (int)(MAX_ROWS / N); if (per < 1) per = 1;
         const long long need = (long long)per * N;
+        const bool tc = m->cfg.precision != RG_PREC_FP32;
+        const int P = m->planes;
         if (need > m->kv_rows) {
-            dfree_one(m, m->kv_ln); dfree_one(m, m->kv_buf); m->kv_ln = m->kv_buf = nullptr; m->kv_rows = 0;
-            if (dalloc(m, (void**)&m->kv_ln, (size_t)need * D * sizeof(float))) return 1;
+            dfree_one(m, m->kv_ln); dfree_one(m, m->kv_buf); dfree_one(m, m->kv_a16);
+            m->kv_ln = m->kv_buf = nullptr; m->kv_a16 = nullptr; m->kv_rows = 0;
+            if (!tc && dalloc(m, (void**)&m->kv_ln, (size_t)need * D * sizeof(float))) return 1;
+            if (tc && dalloc(m, &m->kv_a16, (size_t)need * D * P * 2)) return 1;
             if (dalloc(m, (void**)&m->kv_buf, (size_t)need * L * 2 * D * sizeof(float))) return 1;
             m->kv_rows = need;
         }
         for (int b0 = 0; b0 < B; b0 += per) {
             const int nb = (B - b0 < per) ? B - b0 : per;
             const int rows = nb * N;
-            LAUNCH(rg_launch_ln_rows(xf[c] + (long long)b0 * N * D, D, nullptr, nullptr, rg_out_f32(m->kv_ln, D), rows, st));
-            LAUNCH(rg_launch_gemm_f32(mk_gemm(m->kv_ln, D, m->Wkv_all[c], m->bkv_all[c], m->kv_buf, L * 2 * D,
-                                              rows, L * 2 * D, D, RG_EPI_BIAS), st));
+            if (tc) {
+                // normalised condition rows as bf16 planes, then all 8 layers' key|value in one tcgen05 GEMM
+                LAUNCH(rg_launch_ln_rows(xf[c] + (long long)b0 * N * D, D, nullptr, nullptr,
+                                         rg_out_b16(m->kv_a16, D * P, P == 2 ? D : 0), rows, st));
+                CUtensorMap tmA;
+                CU(rg_make_tensor_map(&tmA, m->kv_a16, rows, (long long)D * P, (long long)D * P, 128));
+                if (tc_gemm(m, tmA, D, m->tc_kv[c], m->bkv_all[c], rows, L * 2 * D, D, RG_EPI_BIAS, nullptr, m->kv_buf,
+                            L * 2 * D, nullptr, 0, st)) return 1;
+            } else {
+                LAUNCH(rg_launch_ln_rows(xf[c] + (long long)b0 * N * D, D, nullptr, nullptr, rg_out_f32(m->kv_ln, D), rows, st));
+                LAUNCH(rg_launch_gemm_f32(mk_gemm(m->kv_ln, D, m->Wkv_all[c], m->bkv_all[c], m->kv_buf, L * 2 * D,
+                                                  rows, L * 2 * D, D, RG_EPI_BIAS), st));
+            }
             LAUNCH(rg_launch_kv_state(m->kv_buf, L * 2 * D, 0, D, N,
                                       state + (long long)b0 * clip_stride + (long long)c * RG_H * RG_HD * RG_HD,
                                       clip_stride, nb, L, 2 * D, (long long)3 * RG_H * RG_HD * RG_HD, st));
@@ -466,7 +487,7 @@ extern "C" int rg_precompute_clip_state(rg_handle m, const float* xf_text, const
 // one tcgen05 GEMM: A (bf16 planes, tensor map tmA, plane width a_w) x W16 -> fp32 and/or bf16 planes
 static int tc_gemm(rg_model* m, const CUtensorMap& tmA, int a_w, const W16& w, const float* bias, int M, int N,
                    int K, int epi, const float* R, float* C32, int ldc32, void* C16, int c16_w, cudaStream_t st,
-                   int groups = 1, int a_goff = 0, int w_goff = 0, int bc_goff = 0) {
+                   int groups, int a_goff, int w_goff, int bc_goff) {
     RgGemmTc p;
     memset(&p, 0, sizeof(p));
     p.M = M; p.N = N; p.K = K; p.split = m->planes == 2; p.a_lo_off = a_w; p.w_lo_off = w.K;
@@ -672,6 +693,44 @@ extern "C" int rg_op_linear_tc(const float* x, const float* W, const float* b, c
     LAUNCH(rg_launch_gemm_tc(tmA, tmW, p, st));
     CU(cudaFreeAsync(a16, st));
     CU(cudaFreeAsync(w16, st));
+    return 0;
+}
+extern "C" int rg_probe_gemm_tc(const float* x, const float* W, const float* b, float* out, int M, int N, int K,
+                                int split, int reps, void* flush_buf, int64_t flush_bytes, float* median_ms,
+                                void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N % 128 || K % 64 || reps < 1 || reps > 64) return rg_fail("rg_probe_gemm_tc: bad shape or reps");
+    const int planes = split ? 2 : 1;
+    void *a16 = nullptr, *w16 = nullptr;
+    CU(cudaMalloc(&a16, (size_t)M * K * planes * 2));
+    CU(cudaMalloc(&w16, (size_t)N * K * planes * 2));
+    LAUNCH(rg_launch_split_bf16(x, K, a16, K * planes, split ? K : 0, M, K, st));
+    LAUNCH(rg_launch_split_bf16(W, K, w16, K * planes, split ? K : 0, N, K, st));
+    CUtensorMap tmA, tmW;
+    CU(rg_make_tensor_map(&tmA, a16, M, (long long)K * planes, (long long)K * planes, 128));
+    CU(rg_make_tensor_map(&tmW, w16, N, (long long)K * planes, (long long)K * planes, 128));
+    RgGemmTc p;
+    memset(&p, 0, sizeof(p));
+    p.M = M; p.N = N; p.K = K; p.split = split ? 1 : 0; p.a_lo_off = K; p.w_lo_off = K; p.groups = 1;
+    p.bias = b; p.C32 = out; p.ldc32 = N; p.epi = RG_EPI_BIAS;
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    std::vector<float> ts;
+    for (int i = 0; i < reps + 2; ++i) {
+        if (flush_buf) CU(cudaMemsetAsync(flush_buf, i, (size_t)flush_bytes, st));
+        CU(cudaEventRecord(e0, st));
+        LAUNCH(rg_launch_gemm_tc(tmA, tmW, p, st));
+        CU(cudaEventRecord(e1, st));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        if (i >= 2) ts.push_back(ms);
+    }
+    std::sort(ts.begin(), ts.end());
+    *median_ms = ts[ts.size() / 2];
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(a16); cudaFree(w16);
     return 0;
 }
 extern "C" int rg_op_layernorm(const float* x, const float* gamma, const float* beta, float* out,

@@ -167,74 +167,70 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             __syncwarp();
         }
     } else {
-        // ===== epilogue: TMEM -> registers -> global =====
+        // ===== epilogue: TMEM -> registers -> smem (transpose) -> coalesced global =====
+        // tcgen05.ld gives thread `lane` one accumulator ROW (32 columns per load); storing that
+        // straight to global would touch 32 different cache lines per instruction.  The operand
+        // ring is idle once tmem_full fires, so each warp parks its 32 x BN quadrant there
+        // (row pitch BN+4 floats: conflict-free 128-bit accesses both ways) and then walks it row by
+        // row with lanes along N: bias / residual / pos loads and all stores are 512 B contiguous.
         mbar_wait(smem_u32(&tmem_full_bar), 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int lg = warp & 3;                                        // TMEM lane group of this warp
-        const int row = m0 + lg * 32 + lane;
-        const bool row_ok = row < p.M;
-        const float* bias = p.bias ? p.bias + g * p.b_goff : nullptr;
-        const int cbase = g * p.c_goff + n0;
+        constexpr int PITCH = BN + 4;
+        float* stage = reinterpret_cast<float*>(smem) + lg * 32 * PITCH;
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
             uint32_t v[32];
             tmem_ld32(tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + c * 32, v);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (!row_ok) continue;
-            const int col = cbase + c * 32;                             // column in C / R
-            float f[32];
+            float* dst = stage + lane * PITCH + c * 32;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-            if (bias) {
+            for (int i = 0; i < 32; i += 4)
+                *reinterpret_cast<float4*>(dst + i) = make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]),
+                                                                  __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+        }
+        __syncwarp();
+        const float* bias = p.bias ? p.bias + g * p.b_goff + n0 : nullptr;
+        const int cbase = g * p.c_goff + n0;                            // first column of this tile in C
+        const int rbase = p.r_grouped ? cbase : n0;
+        constexpr int NV = BN / 128;                                    // float4 per lane per row
+        float4 bv[NV];
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n0 + c * 32 + i));
-                    f[i] += b.x; f[i + 1] += b.y; f[i + 2] += b.z; f[i + 3] += b.w;
+        for (int q = 0; q < NV; ++q)
+            bv[q] = bias ? __ldg(reinterpret_cast<const float4*>(bias + q * 128 + lane * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const int row0 = m0 + lg * 32;
+#pragma unroll 2
+        for (int r = 0; r < 32; ++r) {
+            const int row = row0 + r;
+            if (row >= p.M) break;
+#pragma unroll
+            for (int q = 0; q < NV; ++q) {
+                const int cc = q * 128 + lane * 4;
+                float4 f = *reinterpret_cast<const float4*>(stage + r * PITCH + cc);
+                f.x += bv[q].x; f.y += bv[q].y; f.z += bv[q].z; f.w += bv[q].w;
+                if (p.epi == RG_EPI_BIAS_RESIDUAL) {
+                    const float4 b = *reinterpret_cast<const float4*>(p.R + (long long)row * p.ldr + rbase + cc);
+                    f.x += b.x; f.y += b.y; f.z += b.z; f.w += b.w;
+                } else if (p.epi == RG_EPI_BIAS_GELU) {
+                    f.x = rg_gelu_erf(f.x); f.y = rg_gelu_erf(f.y); f.z = rg_gelu_erf(f.z); f.w = rg_gelu_erf(f.w);
+                } else if (p.epi == RG_EPI_BIAS_SILU) {
+                    f.x = rg_silu(f.x); f.y = rg_silu(f.y); f.z = rg_silu(f.z); f.w = rg_silu(f.w);
+                } else if (p.epi == RG_EPI_BIAS_POS) {
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(p.pos + (long long)(row % p.pos_T) * p.N + n0 + cc));
+                    f.x += b.x; f.y += b.y; f.z += b.z; f.w += b.w;
                 }
-            }
-            if (p.epi == RG_EPI_BIAS_RESIDUAL) {
-                const float* r = p.R + (long long)row * p.ldr + (p.r_grouped ? col : n0 + c * 32);
+                if (p.C32) *reinterpret_cast<float4*>(p.C32 + (long long)row * p.ldc32 + cbase + cc) = f;
+                if (p.C16_) {
+                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.C16_) + (long long)row * p.ldc16 + cbase + cc;
+                    const float ff[4] = {f.x, f.y, f.z, f.w};
+                    __nv_bfloat16 h[4], l[4];
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    const float4 b = *reinterpret_cast<const float4*>(r + i);
-                    f[i] += b.x; f[i + 1] += b.y; f[i + 2] += b.z; f[i + 3] += b.w;
-                }
-            } else if (p.epi == RG_EPI_BIAS_GELU) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) f[i] = rg_gelu_erf(f[i]);
-            } else if (p.epi == RG_EPI_BIAS_SILU) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) f[i] = rg_silu(f[i]);
-            } else if (p.epi == RG_EPI_BIAS_POS) {
-                const float* r = p.pos + (long long)(row % p.pos_T) * p.N + n0 + c * 32;
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(r + i));
-                    f[i] += b.x; f[i + 1] += b.y; f[i + 2] += b.z; f[i + 3] += b.w;
-                }
-            }
-            if (p.C32) {
-                float* o = p.C32 + (long long)row * p.ldc32 + col;
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
-            }
-            if (p.C16_) {
-                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.C16_) + (long long)row * p.ldc16 + col;
-                uint32_t hi[16], lo[16];
-#pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    const __nv_bfloat16 h0 = __float2bfloat16_rn(f[i]), h1 = __float2bfloat16_rn(f[i + 1]);
-                    hi[i >> 1] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                    const __nv_bfloat16 l0 = __float2bfloat16_rn(f[i] - __bfloat162float(h0));
-                    const __nv_bfloat16 l1 = __float2bfloat16_rn(f[i + 1] - __bfloat162float(h1));
-                    lo[i >> 1] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-                }
-#pragma unroll
-                for (int i = 0; i < 16; i += 4) *reinterpret_cast<uint4*>(o + i * 2) = make_uint4(hi[i], hi[i + 1], hi[i + 2], hi[i + 3]);
-                if (p.c16_lo_off) {
-#pragma unroll
-                    for (int i = 0; i < 16; i += 4)
-                        *reinterpret_cast<uint4*>(o + p.c16_lo_off + i * 2) = make_uint4(lo[i], lo[i + 1], lo[i + 2], lo[i + 3]);
+                    for (int k = 0; k < 4; ++k) {
+                        h[k] = __float2bfloat16_rn(ff[k]);
+                        l[k] = __float2bfloat16_rn(ff[k] - __bfloat162float(h[k]));
+                    }
+                    *reinterpret_cast<uint2*>(o) = *reinterpret_cast<uint2*>(h);
+                    if (p.c16_lo_off) *reinterpret_cast<uint2*>(o + p.c16_lo_off) = *reinterpret_cast<uint2*>(l);
                 }
             }
         }
