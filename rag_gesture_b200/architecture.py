@@ -125,7 +125,7 @@ class MotionDiffusion(nn.Module):
         model_kwargs["motion_mask"] = motion_mask
         model_kwargs["sample_idx"] = kwargs.get("sample_idx", None)
         retrieval_dict = model_kwargs["re_dict"]
-        kwargs["retrieval_dict"] = copy.deepcopy(retrieval_dict)
+        kwargs["retrieval_dict"] = retrieval_dict     # the reference deep-copies (:275); nothing mutates it here
         gb.results, gb.model_kwargs, gb.shape, gb.device = kwargs, model_kwargs, (B, T, codec.vae_latent_dim), device
 
         if gb.use_outpaint:

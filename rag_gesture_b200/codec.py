@@ -48,6 +48,25 @@ class SyntheticGestureCodec(nn.Module):
         ms = torch.zeros_like(m[:, :1])
         return motion, torch.cat([m, ms, m, ms, m, ms, m], dim=1)
 
+    def encode_many(self, motion_upper, motion_lower, motion_face, motion_hands, motion_transl,
+                    motion_facial, motion_contact, motion_mask):
+        """E exemplars in one pass; the Gaussian draws are made exemplar by exemplar, part by part, i.e.
+        exactly the sequence E separate encode() calls at B=1 would consume."""
+        E, F, D, c = motion_upper.shape[0], motion_upper.shape[1], self.vae_latent_dim, self.frame_chunk_size
+        eps = torch.stack([torch.stack([torch.randn(F // c, 1, D) for _ in PARTS], 0) for _ in range(E)], 0)
+        eps = eps.to(motion_upper.device)                       # [E, 4, n, 1, D]
+        feats = (motion_upper, motion_hands, torch.cat([motion_face, motion_facial], dim=-1),
+                 torch.cat([motion_lower, motion_transl, motion_contact], dim=-1))
+        zs = []
+        for p, ((name, w), f) in enumerate(zip(PARTS, feats)):
+            mu = f.reshape(E, F // c, c * w) @ getattr(self, f"{name}_enc")
+            zs.append(mu + 0.05 * eps[:, p, :, 0, :])
+        sep = torch.zeros_like(zs[0][:, :1, :])
+        motion = torch.cat([zs[0], sep, zs[1], sep, zs[2], sep, zs[3]], dim=1)
+        m = motion_mask[:, ::c]
+        ms = torch.zeros_like(m[:, :1])
+        return motion, torch.cat([m, ms, m, ms, m, ms, m], dim=1)
+
     def _dec(self, name, z, w):
         B, n, _ = z.shape
         return (z @ getattr(self, f"{name}_dec")).reshape(B, n * self.frame_chunk_size, w)

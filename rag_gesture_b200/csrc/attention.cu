@@ -40,17 +40,19 @@ __device__ __forceinline__ void finish_rows(const float* Ysm, int T, int clip, c
 // read the same 4 values), so the 32x32 contractions run on the FMA pipe instead of 32 shuffles per
 // token (shuffle issue rate, not arithmetic, bounded the first version: 56 us -> see profiles/).
 __device__ __forceinline__ void row_times_A(const float* row, const float A[RG_HD], float& y) {
-    y = 0.f;
+    float y0 = 0.f, y1 = 0.f, y2 = 0.f, y3 = 0.f;       // four chains: the 32 FMAs are not serialised
 #pragma unroll
     for (int d4 = 0; d4 < RG_HD / 4; ++d4) {
         const float4 q = *reinterpret_cast<const float4*>(row + d4 * 4);
-        y = fmaf(q.x, A[d4 * 4 + 0], y); y = fmaf(q.y, A[d4 * 4 + 1], y);
-        y = fmaf(q.z, A[d4 * 4 + 2], y); y = fmaf(q.w, A[d4 * 4 + 3], y);
+        y0 = fmaf(q.x, A[d4 * 4 + 0], y0); y1 = fmaf(q.y, A[d4 * 4 + 1], y1);
+        y2 = fmaf(q.z, A[d4 * 4 + 2], y2); y3 = fmaf(q.w, A[d4 * 4 + 3], y3);
     }
+    y = (y0 + y1) + (y2 + y3);
 }
 
 // softmax over the 32 head features of Q for tokens [0,T) -> slice[n][lane]; loads batched CH-wide
-__device__ __forceinline__ void q_softmax_to_smem(const float* qcol, long long stride, int T, float* slice, int lane) {
+__device__ __forceinline__ void q_softmax_to_smem(const float* qcol, long long stride, int T, float* slice, int lane,
+                                                  int pitch = RG_D) {
     constexpr int CH = 8;
     for (int n0 = 0; n0 < T; n0 += CH) {
         float qq[CH];
@@ -59,22 +61,15 @@ __device__ __forceinline__ void q_softmax_to_smem(const float* qcol, long long s
 #pragma unroll
         for (int i = 0; i < CH; ++i) {
             if (n0 + i < T) {
-                const float e = expf(qq[i] - rg_warp_max(qq[i]));
-                slice[(n0 + i) * RG_D + lane] = e / rg_warp_sum(e);
+                const float e = rg_exp(qq[i] - rg_warp_max(qq[i]));
+                slice[(n0 + i) * pitch + lane] = __fdividef(e, rg_warp_sum(e));
             }
         }
     }
 }
 
-__global__ void __launch_bounds__(512, 2) sa_attn_kernel(const float* __restrict__ qkv,
-                                                        const float* __restrict__ src_mask,
-                                                        RgStylParams sp, const float* __restrict__ x_res,
-                                                        RgRowOut out, int T, int with_styl) {
-    extern __shared__ __align__(16) float Ysm[];   // [T][512]
-    const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const float* base = qkv + (long long)b * T * (3 * RG_D) + warp * RG_HD + lane;
-    const float* mrow = src_mask + (long long)b * T;
-    float* slice = Ysm + warp * RG_HD;              // this head's [T][32] window, row pitch 512
+// One head of EfficientSelfAttention on one warp: on return slice[n*pitch + lane] = Y[n][head*32 + lane].
+__device__ __forceinline__ void sa_head(const float* base, const float* mrow, int T, float* slice, int pitch, int lane) {
     constexpr int CH = 8;
     const long long RS = 3 * RG_D;
     // sweep 1: column max of K (+ -1e6 on masked tokens, efficient_attention.py:32); lane = feature d
@@ -101,9 +96,9 @@ __global__ void __launch_bounds__(512, 2) sa_attn_kernel(const float* __restrict
 #pragma unroll
         for (int i = 0; i < CH; ++i) {
             if (n0 + i < T) {
-                const float e = expf(kk[i] - kmax);
+                const float e = rg_exp(kk[i] - kmax);
                 ksum += e;
-                slice[(n0 + i) * RG_D + lane] = e;
+                slice[(n0 + i) * pitch + lane] = e;
             }
         }
     }
@@ -119,7 +114,7 @@ __global__ void __launch_bounds__(512, 2) sa_attn_kernel(const float* __restrict
 #pragma unroll
         for (int i = 0; i < CH; ++i) {
             if (n0 + i < T) {
-                const float* row = slice + (n0 + i) * RG_D;
+                const float* row = slice + (n0 + i) * pitch;
 #pragma unroll
                 for (int d4 = 0; d4 < RG_HD / 4; ++d4) {
                     const float4 e = *reinterpret_cast<const float4*>(row + d4 * 4);
@@ -135,20 +130,88 @@ __global__ void __launch_bounds__(512, 2) sa_attn_kernel(const float* __restrict
 #pragma unroll
     for (int d4 = 0; d4 < RG_HD / 4; ++d4) {
         const float4 s4 = *reinterpret_cast<const float4*>(slice + d4 * 4);
-        A[d4 * 4 + 0] /= s4.x; A[d4 * 4 + 1] /= s4.y; A[d4 * 4 + 2] /= s4.z; A[d4 * 4 + 3] /= s4.w;
+        A[d4 * 4 + 0] = __fdividef(A[d4 * 4 + 0], s4.x); A[d4 * 4 + 1] = __fdividef(A[d4 * 4 + 1], s4.y);
+        A[d4 * 4 + 2] = __fdividef(A[d4 * 4 + 2], s4.z); A[d4 * 4 + 3] = __fdividef(A[d4 * 4 + 3], s4.w);
     }
     __syncwarp();
     // sweep 3: softmax_features(Q) -> smem, then Y = Q A written in place
-    q_softmax_to_smem(base, RS, T, slice, lane);
+    q_softmax_to_smem(base, RS, T, slice, lane, pitch);
     __syncwarp();
     for (int n = 0; n < T; ++n) {
         float y;
-        row_times_A(slice + n * RG_D, A, y);
+        row_times_A(slice + n * pitch, A, y);
         __syncwarp();
-        slice[n * RG_D + lane] = y;
+        slice[n * pitch + lane] = y;
     }
+}
+
+__global__ void __launch_bounds__(512, 2) sa_attn_kernel(const float* __restrict__ qkv,
+                                                        const float* __restrict__ src_mask,
+                                                        RgStylParams sp, const float* __restrict__ x_res,
+                                                        RgRowOut out, int T, int with_styl) {
+    extern __shared__ __align__(16) float Ysm[];   // [T][512]
+    const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    sa_head(qkv + (long long)b * T * (3 * RG_D) + warp * RG_HD + lane, src_mask + (long long)b * T, T,
+            Ysm + warp * RG_HD, RG_D, lane);
     __syncthreads();
     finish_rows(Ysm, T, b, sp, with_styl, x_res, RG_D, out, 0, warp, lane);
+}
+
+// Finer-grained variants for the fused denoiser: HG heads per CTA, Y goes to global fp32 and the
+// Stylization prologue runs as a row kernel.  4x/12x more CTAs than one-CTA-per-clip: at 64-160 clips
+// the per-clip kernels left most SMs idle and were latency-bound (profiles/).
+constexpr int HG = 4;
+__global__ void __launch_bounds__(HG * 32) sa_core_kernel(const float* __restrict__ qkv,
+                                                         const float* __restrict__ src_mask,
+                                                         float* __restrict__ Y, int T) {
+    extern __shared__ __align__(16) float Ysm[];   // [T][HG*32]
+    const int b = blockIdx.x, hq = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int head = hq * HG + warp;
+    float* slice = Ysm + warp * RG_HD;
+    sa_head(qkv + (long long)b * T * (3 * RG_D) + head * RG_HD + lane, src_mask + (long long)b * T, T, slice,
+            HG * RG_HD, lane);
+    __syncwarp();
+    float* o = Y + (long long)b * T * RG_D + head * RG_HD + lane;
+    for (int n = 0; n < T; ++n) o[(long long)n * RG_D] = slice[n * HG * RG_HD + lane];
+}
+
+__global__ void __launch_bounds__(HG * 32) ca_core_kernel(const float* __restrict__ q3, int ldq,
+                                                         const float* __restrict__ state,
+                                                         long long state_clip_stride, long long state_cond_stride,
+                                                         const float* __restrict__ qmask,
+                                                         long long qmask_cond_stride, float* __restrict__ Y,
+                                                         int ldy, int T) {
+    extern __shared__ __align__(16) float Ysm[];
+    const int b = blockIdx.x, c = blockIdx.y, hq = blockIdx.z, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int head = hq * HG + warp;
+    const float* Ap = state + (long long)b * state_clip_stride + (long long)c * state_cond_stride +
+                      (long long)head * RG_HD * RG_HD + lane;
+    float A[RG_HD];
+#pragma unroll
+    for (int d = 0; d < RG_HD; ++d) A[d] = __ldg(Ap + d * RG_HD);
+    const float* qb = q3 + (long long)b * T * ldq + c * RG_D + head * RG_HD + lane;
+    const float* qm = qmask ? qmask + (long long)c * qmask_cond_stride + (long long)b * T : nullptr;
+    float* slice = Ysm + warp * RG_HD;
+    q_softmax_to_smem(qb, ldq, T, slice, lane, HG * RG_HD);
+    __syncwarp();
+    float* o = Y + (long long)b * T * ldy + c * RG_D + head * RG_HD + lane;
+    for (int n = 0; n < T; ++n) {
+        float y;
+        row_times_A(slice + n * HG * RG_HD, A, y);
+        if (qm) y = y + (1.0f - qm[n]) * RG_NEG_MASK;       // fp32 add: y - 1e6 rounds to a 1/16 grid
+        o[(long long)n * ldy] = y;
+    }
+}
+
+// Stylization prologue of the three cross-attention blocks over Y[M,1536]: blockIdx.y = condition
+__global__ void __launch_bounds__(256) styl_rows3_kernel(const float* __restrict__ y, int ldy, RgStyl3 sp3,
+                                                        int rows_per_clip, RgRowOut out, int M) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), c = blockIdx.y, lane = threadIdx.x & 31;
+    if (row >= M) return;
+    float4 v[4];
+    load_row(y + (long long)row * ldy + c * RG_D, lane, v);
+    rg_styl_row(v, sp3.p[c], row / rows_per_clip, lane);
+    rg_store_row_out(out, row, c * RG_D, lane, v);
 }
 
 __global__ void __launch_bounds__(512, 2) ca_attn_kernel(const float* __restrict__ q3, int ldq,
@@ -291,6 +354,32 @@ cudaError_t rg_launch_ca_attention(const float* q3, int ldq, const float* state,
     ca_attn_kernel<<<dim3(B, n_cond), 512, smem, st>>>(q3, ldq, state, state_clip_stride,
                                                        state_cond_stride, qmask, qmask_cond_stride,
                                                        s3, out, T);
+    return cudaGetLastError();
+}
+
+cudaError_t rg_launch_sa_core(const float* qkv, const float* src_mask, float* Y, int B, int T, cudaStream_t st) {
+    if (B <= 0) return cudaSuccess;
+    if (T > RG_MAX_T) return cudaErrorInvalidValue;
+    sa_core_kernel<<<dim3(B, RG_H / HG), HG * 32, (size_t)T * HG * RG_HD * sizeof(float), st>>>(qkv, src_mask, Y, T);
+    return cudaGetLastError();
+}
+
+cudaError_t rg_launch_ca_core(const float* q3, int ldq, const float* state, long long state_clip_stride,
+                              long long state_cond_stride, const float* qmask, long long qmask_cond_stride,
+                              float* Y, int ldy, int B, int T, cudaStream_t st) {
+    if (B <= 0) return cudaSuccess;
+    if (T > RG_MAX_T) return cudaErrorInvalidValue;
+    ca_core_kernel<<<dim3(B, 3, RG_H / HG), HG * 32, (size_t)T * HG * RG_HD * sizeof(float), st>>>(
+        q3, ldq, state, state_clip_stride, state_cond_stride, qmask, qmask_cond_stride, Y, ldy, T);
+    return cudaGetLastError();
+}
+
+cudaError_t rg_launch_styl_rows3(const float* y, int ldy, const RgStylParams* sp3, int rows_per_clip,
+                                 RgRowOut out, int M, cudaStream_t st) {
+    if (M <= 0) return cudaSuccess;
+    RgStyl3 s3;
+    for (int c = 0; c < 3; ++c) s3.p[c] = sp3[c];
+    styl_rows3_kernel<<<dim3((M + 7) / 8, 3), 256, 0, st>>>(y, ldy, s3, rows_per_clip, out, M);
     return cudaGetLastError();
 }
 

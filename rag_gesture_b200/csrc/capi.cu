@@ -518,15 +518,17 @@ static int denoise_tc(rg_model* m, const float* x, int B, const float* ssrow, co
         LAUNCH(rg_launch_ln_rows(m->h, D, nullptr, nullptr, rg_out_b16(m->a16, D * P, lo ? D : 0), M, st));
         if (tc_gemm(m, m->tm_a16, D, t.qkv, ly.bqkv, M, 3 * D, D, RG_EPI_BIAS, nullptr, m->big, 3 * D, nullptr, 0, st)) return 1;
         RgStylParams sp = {ly.sa_g, ly.sa_b, ss, 0};
-        LAUNCH(rg_launch_sa_attention(m->big, src_mask, sp, nullptr, rg_out_b16(m->a16, D * P, lo ? D : 0), B, T, 1, st));
+        LAUNCH(rg_launch_sa_core(m->big, src_mask, m->y, B, T, st));
+        LAUNCH(rg_launch_styl_rows(m->y, D, sp, T, rg_out_b16(m->a16, D * P, lo ? D : 0), M, st));
         if (tc_gemm(m, m->tm_a16, D, t.sa_o, ly.sa_bo, M, D, D, RG_EPI_BIAS_RESIDUAL, m->h, m->h, D, nullptr, 0, st)) return 1;
         // --- three cross-attentions on the same h
         LAUNCH(rg_launch_ln_rows(m->h, D, nullptr, nullptr, rg_out_b16(m->a16, D * P, lo ? D : 0), M, st));
         if (tc_gemm(m, m->tm_a16, D, t.caq, ly.bcaq, M, 3 * D, D, RG_EPI_BIAS, nullptr, m->big, 3 * D, nullptr, 0, st)) return 1;
         RgStylParams sp3[3];
         for (int c = 0; c < 3; ++c) sp3[c] = {ly.ca_g + c * D, ly.ca_b + c * D, ss + (1 + c) * 2 * D, 0};
-        LAUNCH(rg_launch_ca_attention(m->big, 3 * D, state + (long long)l * 3 * HS, clip_stride, HS, query_mask,
-                                      (long long)B * T, sp3, rg_out_b16(m->a16w, 3 * D * P, lo ? 3 * D : 0), B, T, 3, st));
+        LAUNCH(rg_launch_ca_core(m->big, 3 * D, state + (long long)l * 3 * HS, clip_stride, HS, query_mask,
+                                 (long long)B * T, m->o3, 3 * D, B, T, st));
+        LAUNCH(rg_launch_styl_rows3(m->o3, 3 * D, sp3, T, rg_out_b16(m->a16w, 3 * D * P, lo ? 3 * D : 0), M, st));
         if (tc_gemm(m, m->tm_a16w, 3 * D, t.ca_o, ly.ca_bo, M, D, D, RG_EPI_BIAS_RESIDUAL, m->h, nullptr, 0, m->o16,
                     3 * D, st, 3, D, D, D)) return 1;
         if (tc_gemm(m, m->tm_o16, 3 * D, t.mix, ly.bmix, M, D, 3 * D, RG_EPI_BIAS, nullptr, m->h, D, m->h16, D, st)) return 1;

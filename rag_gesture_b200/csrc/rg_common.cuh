@@ -86,6 +86,12 @@ cudaError_t rg_launch_ca_attention(const float* q3, int ldq, const float* state,
                                    const float* qmask, long long qmask_cond_stride,
                                    const RgStylParams* sp3, RgRowOut out, int B, int T,
                                    int n_cond, cudaStream_t st);
+cudaError_t rg_launch_sa_core(const float* qkv, const float* src_mask, float* Y, int B, int T, cudaStream_t st);
+cudaError_t rg_launch_ca_core(const float* q3, int ldq, const float* state, long long state_clip_stride,
+                              long long state_cond_stride, const float* qmask, long long qmask_cond_stride,
+                              float* Y, int ldy, int B, int T, cudaStream_t st);
+cudaError_t rg_launch_styl_rows3(const float* y, int ldy, const RgStylParams* sp3, int rows_per_clip,
+                                 RgRowOut out, int M, cudaStream_t st);
 cudaError_t rg_launch_kv_state(const float* kv, int ldkv, int k_off, int v_off, int n_tokens,
                                float* state, long long state_clip_stride, int B, int n_sets,
                                int kv_set_stride, long long state_set_stride, cudaStream_t st);
@@ -101,7 +107,10 @@ __device__ __forceinline__ float rg_warp_max(float v) {
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
-__device__ __forceinline__ float rg_silu(float v) { return v / (1.0f + expf(-v)); }
+// exp via ex2.approx (<= 2 ulp + |x|*6e-8 relative) and approximate division: these sit in the inner
+// loops of every row/attention kernel; their error is far below every parity tier (tests).
+__device__ __forceinline__ float rg_exp(float v) { return __expf(v); }
+__device__ __forceinline__ float rg_silu(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 __device__ __forceinline__ float rg_gelu_erf(float v) {
     return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
 }

@@ -299,11 +299,27 @@ class ReGestureTransformer(nn.Module):
         else:
             self.database = None
         self._engine, self._engine_key, self._sched_key = None, None, None
+        self._epoch = getattr(self, "_epoch", 0)
         self._state_cache = (None, None)
 
     # -- engine lifetime: rebuilt when weights move or change (load_state_dict, .to(), .cuda()) ------
     def _weights_key(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        """Cheap fingerprint of the parameter set: bumped by load_state_dict / .to() / .cuda() (hooks
+        below) plus identity+version of the first and last tensors (in-place edits of the others are
+        not detected: call `invalidate_engine()` after such edits)."""
+        a, b = self.joint_embed.weight, self.out.weight
+        return (self._epoch, a.data_ptr(), a._version, b.data_ptr(), b._version)
+
+    def invalidate_engine(self):
+        self._epoch += 1
+
+    def _apply(self, fn, *a, **k):
+        self._epoch = getattr(self, "_epoch", 0) + 1
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self._epoch = getattr(self, "_epoch", 0) + 1
+        return super().load_state_dict(*a, **k)
 
     def rg_engine(self, diffusion=None):
         dev = self.out.weight.device

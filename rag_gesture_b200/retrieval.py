@@ -114,7 +114,8 @@ class TextSimilarityIndex:
 
 
 def discourse_retrieval(text, discourse, prominence, speaker_id, db_idx_2_sense, db_idx_2_discbounds,
-                        db_idx_2_prominence, encoded_text, text_feat_cache, index=None, sense_index=None):
+                        db_idx_2_prominence, encoded_text, text_feat_cache, index=None, sense_index=None,
+                        sense_tables=None):
     """Rule-based discourse retrieval, same arguments and return triple as
     rag/discourse_retrieval.py:8-316:  ({q: [sample names]}, {q: {name: (conn, sense, start, end)}},
     {q: (conn_lower, sense, conn_start, conn_end)}).  `index` (TextSimilarityIndex) and `sense_index`
@@ -139,37 +140,19 @@ def discourse_retrieval(text, discourse, prominence, speaker_id, db_idx_2_sense,
 
     for qi, (sense, conn) in enumerate(zip(senses, conns)):
         scored, bounds_of = [], {}
-        for name in sense_index.get(sense, ()):            # DB order; only samples holding the sense
-            entry = db_idx_2_sense[name]
-            spk, disco = entry[0], entry[1:]
-            s_senses = [d[0] for d in disco]
-            s_conns = [d[1] for d in disco]
-            s_prom = db_idx_2_prominence[name]
-            assert len(s_prom) == len(s_senses), f"{len(s_prom)} != {len(s_senses)}"
-            rel = [j for j, s in enumerate(s_senses) if s == sense]
-            score = 2
-            top, chosen = rel[0], False
-            rel_conns = [s_conns[j] for j in rel]
-            if conn in rel_conns:
-                score += 4
-                top, chosen = rel[rel_conns.index(conn)], True
-            if spk == speaker_id:
-                score += 3
-            acc, cnt, diffs = 0, 0, {}
-            for j in rel:
-                if s_prom[j] is None or q_prom[qi] is None:
-                    continue
-                d = abs(s_prom[j][1] - q_prom[qi][1])
-                diffs[j] = d
-                acc += 4 / (1 + 2 * d)
-                cnt += 1
-            if cnt > 0:
-                score += acc / cnt
-                best = sorted(diffs, key=diffs.get)[0]
-                if top != best and not chosen:
-                    top = best
-            scored.append((name, score))
-            bounds_of[name] = db_idx_2_discbounds[name][top]
+        if sense_tables is not None:
+            # vectorised scoring (same float64 operations in the same order as the loop below)
+            tabs, conn_ids = sense_tables
+            if sense not in tabs:
+                tabs[sense] = SenseTable(sense, sense_index.get(sense, []), db_idx_2_sense, db_idx_2_prominence, conn_ids)
+            tab = tabs[sense]
+            if len(tab.names):
+                sc, top = tab.score(conn_ids.get(conn), speaker_id, None if q_prom[qi] is None else float(q_prom[qi][1]))
+                scored = list(zip(tab.names, sc.tolist()))
+                bounds_of = {n: db_idx_2_discbounds[n][t] for n, t in zip(tab.names, top.tolist())}
+        else:
+            scored, bounds_of = _score_loop(sense, conn, qi, q_prom, speaker_id, sense_index, db_idx_2_sense,
+                                            db_idx_2_discbounds, db_idx_2_prominence)
         # equal-score tiers, best first; a tier with several members is ordered by text similarity
         tiers = {}
         for name, score in sorted(scored, key=lambda t: t[1], reverse=True):
@@ -190,6 +173,110 @@ def discourse_retrieval(text, discourse, prominence, speaker_id, db_idx_2_sense,
             d_bounds[qi][name] = (b[1], b[0], round(b[4], 3), round(b[5], 3))
     assert len(d_bounds) == len(sample_indexes) == len(query_bounds)
     return sample_indexes, d_bounds, query_bounds
+
+
+def _score_loop(sense, conn, qi, q_prom, speaker_id, sense_index, db_idx_2_sense, db_idx_2_discbounds,
+                db_idx_2_prominence):
+    """Per-sample Python form of the rule scores (reference order of operations); the vectorised
+    SenseTable.score is held to it by tests/test_retrieval_host.py."""
+    scored, bounds_of = [], {}
+    for name in sense_index.get(sense, ()):            # DB order; only samples holding the sense
+        entry = db_idx_2_sense[name]
+        spk, disco = entry[0], entry[1:]
+        s_senses = [d[0] for d in disco]
+        s_conns = [d[1] for d in disco]
+        s_prom = db_idx_2_prominence[name]
+        assert len(s_prom) == len(s_senses), f"{len(s_prom)} != {len(s_senses)}"
+        rel = [j for j, s in enumerate(s_senses) if s == sense]
+        score = 2
+        top, chosen = rel[0], False
+        rel_conns = [s_conns[j] for j in rel]
+        if conn in rel_conns:
+            score += 4
+            top, chosen = rel[rel_conns.index(conn)], True
+        if spk == speaker_id:
+            score += 3
+        acc, cnt, diffs = 0, 0, {}
+        for j in rel:
+            if s_prom[j] is None or q_prom[qi] is None:
+                continue
+            d = abs(s_prom[j][1] - q_prom[qi][1])
+            diffs[j] = d
+            acc += 4 / (1 + 2 * d)
+            cnt += 1
+        if cnt > 0:
+            score += acc / cnt
+            best = sorted(diffs, key=diffs.get)[0]
+            if top != best and not chosen:
+                top = best
+        scored.append((name, score))
+        bounds_of[name] = db_idx_2_discbounds[name][top]
+    return scored, bounds_of
+
+
+class SenseTable:
+    """Flat numpy encoding of every DB sample that holds one discourse sense (built once per DB), so
+    that the rule scores of rag/discourse_retrieval.py:86-213 are evaluated for all those samples at
+    once.  Scores are float64 and accumulated entry by entry in the reference's order, hence equal
+    bit for bit to the Python loop's (the score TIERS depend on exact equality)."""
+
+    def __init__(self, sense, names, db_sense, db_prom, conn_ids):
+        import numpy as np
+        self.names = names
+        self.spk = np.array([db_sense[n][0] for n in names], dtype=np.int64)
+        seg_start, e_idx, e_conn, e_prom = [], [], [], []
+        for n in names:
+            disco = db_sense[n][1:]
+            prom = db_prom[n]
+            seg_start.append(len(e_idx))
+            for j, (s_, c_) in enumerate(disco):
+                if s_ == sense:
+                    e_idx.append(j)
+                    e_conn.append(conn_ids.setdefault(c_, len(conn_ids)))
+                    e_prom.append(float("nan") if prom[j] is None else float(prom[j][1]))
+        self.seg_start = np.array(seg_start, dtype=np.int64)
+        self.seg_len = np.diff(np.append(self.seg_start, len(e_idx)))
+        self.e_idx = np.array(e_idx, dtype=np.int64)
+        self.e_conn = np.array(e_conn, dtype=np.int64)
+        self.e_prom = np.array(e_prom, dtype=np.float64)
+        self.max_len = int(self.seg_len.max()) if len(names) else 0
+
+    def score(self, conn_id, speaker_id, q_prom):
+        """-> (score float64 [n], top entry index int64 [n]) for the query connective."""
+        import numpy as np
+        n = len(self.names)
+        score = np.full(n, 2.0)
+        top = self.e_idx[self.seg_start].copy()            # first entry with the sense
+        chosen = np.zeros(n, dtype=bool)
+        acc = np.zeros(n)
+        cnt = np.zeros(n, dtype=np.int64)
+        best_d = np.full(n, np.inf)
+        best_j = np.full(n, -1, dtype=np.int64)
+        for k in range(self.max_len):                      # k-th relevant entry of every sample
+            has = self.seg_len > k
+            pos = self.seg_start[has] + k
+            hit = has.copy()
+            hit[has] = (self.e_conn[pos] == conn_id) if conn_id is not None else False
+            first = hit & ~chosen                          # list.index(): the first matching entry wins
+            top[first] = self.e_idx[self.seg_start[first] + k]
+            chosen |= hit
+            if q_prom is not None:
+                pr = self.e_prom[pos]
+                ok = ~np.isnan(pr)
+                rows = np.flatnonzero(has)[ok]
+                d = np.abs(pr[ok] - q_prom)
+                acc[rows] = acc[rows] + 4 / (1 + 2 * d)
+                cnt[rows] += 1
+                better = d < best_d[rows]                  # stable sorted(...)[0]: first minimum wins
+                best_d[rows[better]] = d[better]
+                best_j[rows[better]] = self.e_idx[pos[ok]][better]
+        score[chosen] += 4
+        score[self.spk == speaker_id] += 3
+        withp = cnt > 0
+        score[withp] = score[withp] + acc[withp] / cnt[withp]
+        move = withp & ~chosen & (best_j != top)
+        top[move] = best_j[move]
+        return score, top
 
 
 def _rank_long_tier(index, query, tier):
@@ -258,6 +345,7 @@ class RetrievalDatabase(nn.Module):
             self.idx_2_gestprom[name] = map_conns_to_prominence([g["word"] for g in gest], prom)
         self.sample_names = {i: s for i, s in enumerate(self.idx_2_text.keys())}
         self._sense_index = build_sense_index(self.idx_2_sense)
+        self._sense_tables = ({}, {})      # (sense -> SenseTable, connective -> id)
         self._index, self._index_device = None, device
 
     def text_index(self, device):
@@ -268,7 +356,8 @@ class RetrievalDatabase(nn.Module):
 
     def _discourse(self, **kw):
         dev = kw["encoded_text"].device if kw["encoded_text"].is_cuda else (self._index_device or "cuda")
-        return discourse_retrieval(index=self.text_index(dev), sense_index=self._sense_index, **kw)
+        return discourse_retrieval(index=self.text_index(dev), sense_index=self._sense_index,
+                                   sense_tables=self._sense_tables, **kw)
 
     # raggesture.py:313-477, inference branches only
     def retrieve(self, retr_method, text, text_features, audio, discourse, gesture_labels, text_times,
@@ -355,12 +444,16 @@ class RetrievalDatabase(nn.Module):
     # raggesture.py:479-884
     def forward(self, conditions, lengths, device, idx=None, retrieval_method="gesture_type",
                 gesture_rep_encoder=None):
+        """Same re_dict as the reference.  Executed in two phases instead of one exemplar at a time:
+        (1) retrieval decisions for every clip (host rules + CUDA ranking), (2) ONE host->device copy
+        per field and ONE codec call for all exemplars (noise drawn per exemplar in the reference's
+        order when the codec offers `encode_many`), then window placement."""
         B = len(conditions["text"])
         T = self.max_seq_len // self.motion_framechunksize * 4 + 3
         n, cs = (T - 3) // 4, self.motion_framechunksize
         ref = self.dataset[0]
-        motions, raw_m, raw_t, raw_f = [], [], [], []
-        all_idx, all_t2w, all_rse, all_qse, all_lat = [], [], [], [], []
+        # ---- phase 1: which exemplar for which query point --------------------------------------
+        decided, jobs = [], []                      # jobs: (clip, q, name) in the reference's visiting order
         for b in range(B):
             retr_indexes, retr_bounds, query_bounds = self.retrieve(
                 retrieval_method, text=conditions["text"][b], text_features=conditions["text_features"][b],
@@ -368,56 +461,69 @@ class RetrievalDatabase(nn.Module):
                 gesture_labels=conditions["gesture_labels"][b], text_times=conditions["text_times"][b],
                 prominence=conditions["prominence"][b], speaker_id=conditions["speaker_ids"][b, 0].item(),
                 idx=idx[b] if idx is not None else None)
-            all_idx.append(retr_indexes)
-            zero_motion = torch.zeros(T, self.latent_dim, device=device)
-            z_raw = torch.zeros_like(ref["motion"]).to(device)
-            z_trans = torch.zeros_like(ref["trans"]).to(device)
-            z_facial = torch.zeros_like(ref["facial"]).to(device)
-            t2w, rse, qse, lat = {}, {}, {}, {}
-            prev_end = -1
+            decided.append((retr_indexes, retr_bounds, query_bounds))
             for q, names in retr_indexes.items():
                 if len(names) == 0 or q not in query_bounds:
                     continue
-                qb = query_bounds[q]
-                if qb[2] > qb[3]:
+                if query_bounds[q][2] > query_bounds[q][3]:
                     continue
                 assert len(names) == self.num_retrieval == 1
-                name = names[0]
-                smp = self.dataset[name]
-                assert gesture_rep_encoder is not None
-                u = lambda k: smp[k].unsqueeze(0).to(device)
-                latent, lat_mask = gesture_rep_encoder.encode(
-                    u("motion_upper"), u("motion_lower"), u("motion_face"), u("motion_hands"), u("trans"),
-                    u("facial"), u("contact"), u("motion_mask"))
-                latent = latent.squeeze(0)
-                rb = retr_bounds[q][name]
-                t2w[q] = (qb[0], qb[1], rb[0], rb[1])
-                win = self.place_window(qb, rb, retrieval_method, prev_end)
-                if win is None:
-                    continue
-                (r0, r1), (s, e) = win
-                prev_end = e
-                lat[q] = {"retr_motion_latent": latent.unsqueeze(0), "retr_text": u("word"), "retr_audio": u("audio"),
-                          "retr_spkid": u("speaker_id"), "retr_motion_mask": lat_mask}
-                rse[q], qse[q] = (r0, r1), (s, e)
-                for part in range(4):
-                    o = part * (n + 1)
-                    zero_motion[o + s:o + e] = latent[o + r0:o + r1]
-                z_raw[s * cs:e * cs] = smp["motion"].to(device)[r0 * cs:r1 * cs]
-                z_trans[s * cs:e * cs] = smp["trans"].to(device)[r0 * cs:r1 * cs]
-                z_facial[s * cs:e * cs] = smp["facial"].to(device)[r0 * cs:r1 * cs]
-            motions.append(zero_motion); raw_m.append(z_raw); raw_t.append(z_trans); raw_f.append(z_facial)
-            all_t2w.append(t2w); all_rse.append(rse); all_qse.append(qse); all_lat.append(lat)
-        all_motions = torch.stack(motions, 0)
+                jobs.append((b, q, names[0]))
+        # ---- phase 2: fetch + encode all exemplars at once -----------------------------------------
+        assert gesture_rep_encoder is not None or not jobs
+        ex = {}
+        if jobs:
+            smps = [self.dataset[name] for _, _, name in jobs]
+            keys = ("motion_upper", "motion_lower", "motion_face", "motion_hands", "trans", "facial", "contact",
+                    "motion_mask", "word", "audio", "speaker_id", "motion")
+            ex = {k: torch.stack([s_[k] for s_ in smps], 0).to(device, non_blocking=True) for k in keys}
+            args = [ex[k] for k in keys[:8]]
+            if hasattr(gesture_rep_encoder, "encode_many"):
+                lat_all, mask_all = gesture_rep_encoder.encode_many(*args)
+            else:                                   # any GestureRepEncoder: one call per exemplar, as the reference
+                outs = [gesture_rep_encoder.encode(*[a[e:e + 1].clone() for a in args]) for e in range(len(jobs))]
+                lat_all, mask_all = torch.cat([o[0] for o in outs], 0), torch.cat([o[1] for o in outs], 0)
+        # ---- phase 3: window placement ----------------------------------------------------------------
+        motions = torch.zeros(B, T, self.latent_dim, device=device)
+        raw_m = torch.zeros((B,) + tuple(ref["motion"].shape), device=device)
+        raw_t = torch.zeros((B,) + tuple(ref["trans"].shape), device=device)
+        raw_f = torch.zeros((B,) + tuple(ref["facial"].shape), device=device)
+        all_idx = [d[0] for d in decided]
+        all_t2w = [{} for _ in range(B)]
+        all_rse = [{} for _ in range(B)]
+        all_qse = [{} for _ in range(B)]
+        all_lat = [{} for _ in range(B)]
+        prev_end, cur_b = -1, -1
+        for e, (b, q, name) in enumerate(jobs):
+            if b != cur_b:
+                prev_end, cur_b = -1, b
+            _, retr_bounds, query_bounds = decided[b]
+            qb, rb = query_bounds[q], retr_bounds[q][name]
+            all_t2w[b][q] = (qb[0], qb[1], rb[0], rb[1])
+            win = self.place_window(qb, rb, retrieval_method, prev_end)
+            if win is None:
+                continue
+            (r0, r1), (s_, e_) = win
+            prev_end = e_
+            all_lat[b][q] = {"retr_motion_latent": lat_all[e:e + 1], "retr_text": ex["word"][e:e + 1],
+                             "retr_audio": ex["audio"][e:e + 1], "retr_spkid": ex["speaker_id"][e:e + 1],
+                             "retr_motion_mask": mask_all[e:e + 1]}
+            all_rse[b][q], all_qse[b][q] = (r0, r1), (s_, e_)
+            for part in range(4):
+                o = part * (n + 1)
+                motions[b, o + s_:o + e_] = lat_all[e, o + r0:o + r1]
+            raw_m[b, s_ * cs:e_ * cs] = ex["motion"][e, r0 * cs:r1 * cs]
+            raw_t[b, s_ * cs:e_ * cs] = ex["trans"][e, r0 * cs:r1 * cs]
+            raw_f[b, s_ * cs:e_ * cs] = ex["facial"][e, r0 * cs:r1 * cs]
         names_out = []
         for b in range(B):
             names_out.append({})
             for q, nm in all_idx[b].items():
                 if q in all_t2w[b]:
-                    names_out[-1][all_t2w[b][q][0]] = self.dataset[nm[0]]["sample_name"]
-        src_mask = (all_motions != 0).any(dim=-1).to(torch.int)
+                    names_out[-1][all_t2w[b][q][0]] = nm[0]     # == dataset[nm[0]]["sample_name"]
+        src_mask = (motions != 0).any(dim=-1).to(torch.int)
         raw_latent_mask = src_mask.clone()
-        raw_latents = all_motions.clone()
+        raw_latents = motions.clone()
         dead = list(range(2 * n + 2, 3 * n + 2)) + list(range(3 * n + 3, T))     # face + lower/transl rows
         src_mask[:, dead] = 0
         raw_latents[:, dead, :] = 0
@@ -425,8 +531,8 @@ class RetrievalDatabase(nn.Module):
         return dict(
             re_text=None, re_motion=None, re_mask=src_mask,
             raw_motion_latents=raw_latents.view(B, R, T, -1).contiguous(),
-            raw_motion=torch.stack(raw_m, 0).view(B, R, self.max_seq_len, -1).contiguous(),
-            raw_trans=torch.stack(raw_t, 0).view(B, R, self.max_seq_len, -1).contiguous(),
-            raw_facial=torch.stack(raw_f, 0).view(B, R, self.max_seq_len, 100).contiguous(),
+            raw_motion=raw_m.view(B, R, self.max_seq_len, -1).contiguous(),
+            raw_trans=raw_t.view(B, R, self.max_seq_len, -1).contiguous(),
+            raw_facial=raw_f.view(B, R, self.max_seq_len, 100).contiguous(),
             raw_sample_names=names_out, raw_type2words=all_t2w, raw_latent_mask=raw_latent_mask,
             retr_startends=all_rse, query_startends=all_qse, retr_uncropped_latents=all_lat)

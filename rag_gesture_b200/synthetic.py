@@ -193,7 +193,7 @@ class SyntheticGestureDataset:
 
     def __init__(self, n, seed=7, frames=150, per_file=30):
         self.n, self.seed, self.frames, self.per_file = n, seed, frames, per_file
-        self._ann = {}
+        self._ann, self._samples = {}, {}
         self.names = [self._name(i) for i in range(n)]
         self._by_name = {nm: i for i, nm in enumerate(self.names)}
 
@@ -244,7 +244,14 @@ class SyntheticGestureDataset:
         return torch.randn(n_tok, C.TEXT_DIM, generator=g)
 
     def __getitem__(self, key):
+        """Samples are materialised once and then served from memory (the stand-in for the dataset's
+        LMDB cache; generating 0.5 M Gaussians per access would dominate the host side)."""
         i = self._by_name[key] if isinstance(key, str) else int(key)
+        if i not in self._samples:
+            self._samples[i] = self._make(i)
+        return dict(self._samples[i])
+
+    def _make(self, i):
         spk, discourse, prominence, gestures, _ = self.annotations(i)
         g = torch.Generator().manual_seed(self.seed * 9_000_011 + i)
         F = self.frames

@@ -119,3 +119,34 @@ def test_unsupported_methods_raise(db):
         db.retrieval_method["llm"](text="")
     with pytest.raises(AssertionError):
         db.retrieve("prosody", None, None, None, [], [], [], [], 0)
+
+
+def test_vectorised_scores_equal_loop(db):
+    """SenseTable.score (numpy, all samples of a sense at once) == the per-sample loop, bit for bit
+    (float64 scores and chosen entry), for every query connective of the synthetic set."""
+    from rag_gesture_b200 import retrieval as RT
+    qs = S.SyntheticGestureDataset(N_QUERY, seed=8)
+    tabs, conn_ids = {}, {}
+    n_checked = 0
+    for i in range(N_QUERY):
+        spk, disc, prom, _, _ = qs.annotations(i)
+        if not disc:
+            continue
+        conns = [d[0] for d in disc]
+        q_prom = RT.map_conns_to_prominence(conns, prom)
+        for k, cv in q_prom.items():
+            if cv is not None:
+                q_prom[k] = (disc[k][1], cv[1])
+        for qi, d in enumerate(disc):
+            sense, conn = d[1], d[0]
+            ref_scored, ref_bounds = RT._score_loop(sense, conn, qi, q_prom, spk, db._sense_index, db.idx_2_sense,
+                                                    db.idx_2_discbounds, db.idx_2_prominence)
+            if sense not in tabs:
+                tabs[sense] = RT.SenseTable(sense, db._sense_index.get(sense, []), db.idx_2_sense,
+                                            db.idx_2_prominence, conn_ids)
+            sc, top = tabs[sense].score(conn_ids.get(conn), spk, None if q_prom[qi] is None else float(q_prom[qi][1]))
+            assert [n for n, _ in ref_scored] == tabs[sense].names
+            assert [s_ for _, s_ in ref_scored] == sc.tolist()
+            assert [ref_bounds[n] for n in tabs[sense].names] == [db.idx_2_discbounds[n][t] for n, t in zip(tabs[sense].names, top.tolist())]
+            n_checked += len(ref_scored)
+    assert n_checked > 5000
