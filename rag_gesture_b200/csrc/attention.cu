@@ -157,55 +157,162 @@ __global__ void __launch_bounds__(512, 2) sa_attn_kernel(const float* __restrict
     finish_rows(Ysm, T, b, sp, with_styl, x_res, RG_D, out, 0, warp, lane);
 }
 
-// Finer-grained variants for the fused denoiser: HG heads per CTA, Y goes to global fp32 and the
-// Stylization prologue runs as a row kernel.  4x/12x more CTAs than one-CTA-per-clip: at 64-160 clips
-// the per-clip kernels left most SMs idle and were latency-bound (profiles/).
-constexpr int HG = 4;
-__global__ void __launch_bounds__(HG * 32) sa_core_kernel(const float* __restrict__ qkv,
+// Finer-grained variants for the fused denoiser: ONE head per CTA, its tokens split over 4 warps
+// (warp w takes tokens n = w, w+4, ...), Y goes to global fp32 and the Stylization prologue runs as a
+// row kernel.  At 64-160 clips the one-CTA-per-clip kernels left most SMs idle and each warp walked a
+// ~6k-instruction dependent chain (33 us measured); here there are 16x/48x more CTAs, every chain is
+// 4x shorter and the per-warp partials of max / sum / A are combined through shared memory.
+constexpr int TW = 4;                                   // warps (token groups) per head
+struct HeadSmem {
+    float row[RG_MAX_T][RG_HD];                         // E, then softmax(Q), per token
+    float Apart[TW][RG_HD][RG_HD];                      // per-warp partial K^T V
+    float kmaxp[TW][RG_HD], ksump[TW][RG_HD];
+};
+
+__global__ void __launch_bounds__(TW * 32) sa_core_kernel(const float* __restrict__ qkv,
                                                          const float* __restrict__ src_mask,
                                                          float* __restrict__ Y, int T) {
-    extern __shared__ __align__(16) float Ysm[];   // [T][HG*32]
-    const int b = blockIdx.x, hq = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int head = hq * HG + warp;
-    float* slice = Ysm + warp * RG_HD;
-    sa_head(qkv + (long long)b * T * (3 * RG_D) + head * RG_HD + lane, src_mask + (long long)b * T, T, slice,
-            HG * RG_HD, lane);
+    __shared__ __align__(16) HeadSmem sm;
+    rg_pdl_launch();
+    rg_pdl_wait();
+    const int b = blockIdx.x, head = blockIdx.y, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* base = qkv + (long long)b * T * (3 * RG_D) + head * RG_HD + lane;
+    const float* mrow = src_mask + (long long)b * T;
+    const long long RS = 3 * RG_D;
+    constexpr int MAXN = (RG_MAX_T + TW - 1) / TW;       // tokens per warp, upper bound (16)
+    // own tokens' keys (+ -1e6 on masked tokens) and values in registers: all loads in flight at once
+    float kk[MAXN], vv[MAXN];
+#pragma unroll
+    for (int i = 0; i < MAXN; ++i) {
+        const int n = w + i * TW;
+        const float m = n < T ? mrow[n] : 0.f;
+        kk[i] = n < T ? base[n * RS + RG_D] + (1.0f - m) * RG_NEG_MASK : -INFINITY;
+        vv[i] = n < T ? base[n * RS + 2 * RG_D] * m : 0.f;
+    }
+    float kmax = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < MAXN; ++i) kmax = fmaxf(kmax, kk[i]);
+    sm.kmaxp[w][lane] = kmax;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < TW; ++j) kmax = fmaxf(kmax, sm.kmaxp[j][lane]);
+    float ksum = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXN; ++i) {
+        const int n = w + i * TW;
+        if (n < T) {
+            const float e = rg_exp(kk[i] - kmax);
+            ksum += e;
+            sm.row[n][lane] = e;
+        }
+    }
+    sm.ksump[w][lane] = ksum;
     __syncwarp();
+    // partial A over own tokens: A[d][lane] += E[n][d] * V[n][lane]
+    float A[RG_HD];
+#pragma unroll
+    for (int d = 0; d < RG_HD; ++d) A[d] = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXN; ++i) {
+        const int n = w + i * TW;
+        if (n < T) {
+#pragma unroll
+            for (int d4 = 0; d4 < RG_HD / 4; ++d4) {
+                const float4 e = *reinterpret_cast<const float4*>(&sm.row[n][d4 * 4]);
+                A[d4 * 4 + 0] = fmaf(e.x, vv[i], A[d4 * 4 + 0]); A[d4 * 4 + 1] = fmaf(e.y, vv[i], A[d4 * 4 + 1]);
+                A[d4 * 4 + 2] = fmaf(e.z, vv[i], A[d4 * 4 + 2]); A[d4 * 4 + 3] = fmaf(e.w, vv[i], A[d4 * 4 + 3]);
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < RG_HD; ++d) sm.Apart[w][d][lane] = A[d];
+    // queries of own tokens (loads overlap the barrier)
+    float qq[MAXN];
+#pragma unroll
+    for (int i = 0; i < MAXN; ++i) qq[i] = (w + i * TW < T) ? base[(w + i * TW) * RS] : 0.f;
+    __syncthreads();
+    // full normalised A = sum of the partials / column sums
+#pragma unroll
+    for (int d = 0; d < RG_HD; ++d) {
+        float a = 0.f, s = 0.f;
+#pragma unroll
+        for (int j = 0; j < TW; ++j) { a += sm.Apart[j][d][lane]; s += sm.ksump[j][d]; }
+        A[d] = __fdividef(a, s);
+    }
+    // softmax_features(Q) then Y = Q A for own tokens
     float* o = Y + (long long)b * T * RG_D + head * RG_HD + lane;
-    for (int n = 0; n < T; ++n) o[(long long)n * RG_D] = slice[n * HG * RG_HD + lane];
+#pragma unroll
+    for (int i = 0; i < MAXN; ++i) {
+        const int n = w + i * TW;
+        if (n < T) {
+            const float e = rg_exp(qq[i] - rg_warp_max(qq[i]));
+            sm.row[n][lane] = __fdividef(e, rg_warp_sum(e));
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < MAXN; ++i) {
+        const int n = w + i * TW;
+        if (n < T) {
+            float y;
+            row_times_A(&sm.row[n][0], A, y);
+            o[(long long)n * RG_D] = y;
+        }
+    }
 }
 
-__global__ void __launch_bounds__(HG * 32) ca_core_kernel(const float* __restrict__ q3, int ldq,
+__global__ void __launch_bounds__(TW * 32) ca_core_kernel(const float* __restrict__ q3, int ldq,
                                                          const float* __restrict__ state,
                                                          long long state_clip_stride, long long state_cond_stride,
                                                          const float* __restrict__ qmask,
                                                          long long qmask_cond_stride, float* __restrict__ Y,
                                                          int ldy, int T) {
-    extern __shared__ __align__(16) float Ysm[];
-    const int b = blockIdx.x, c = blockIdx.y, hq = blockIdx.z, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int head = hq * HG + warp;
+    __shared__ __align__(16) float rows[RG_MAX_T][RG_HD];
+    rg_pdl_launch();
+    rg_pdl_wait();
+    const int b = blockIdx.x, c = blockIdx.y, head = blockIdx.z, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int MAXN = (RG_MAX_T + TW - 1) / TW;
+    const float* qb = q3 + (long long)b * T * ldq + c * RG_D + head * RG_HD + lane;
+    const float* qm = qmask ? qmask + (long long)c * qmask_cond_stride + (long long)b * T : nullptr;
+    float qq[MAXN], mk[MAXN];
+#pragma unroll
+    for (int i = 0; i < MAXN; ++i) {
+        const int n = w + i * TW;
+        qq[i] = n < T ? qb[(long long)n * ldq] : 0.f;
+        mk[i] = (qm && n < T) ? qm[n] : 1.f;
+    }
     const float* Ap = state + (long long)b * state_clip_stride + (long long)c * state_cond_stride +
                       (long long)head * RG_HD * RG_HD + lane;
     float A[RG_HD];
 #pragma unroll
     for (int d = 0; d < RG_HD; ++d) A[d] = __ldg(Ap + d * RG_HD);
-    const float* qb = q3 + (long long)b * T * ldq + c * RG_D + head * RG_HD + lane;
-    const float* qm = qmask ? qmask + (long long)c * qmask_cond_stride + (long long)b * T : nullptr;
-    float* slice = Ysm + warp * RG_HD;
-    q_softmax_to_smem(qb, ldq, T, slice, lane, HG * RG_HD);
+#pragma unroll
+    for (int i = 0; i < MAXN; ++i) {
+        const int n = w + i * TW;
+        if (n < T) {
+            const float e = rg_exp(qq[i] - rg_warp_max(qq[i]));
+            rows[n][lane] = __fdividef(e, rg_warp_sum(e));
+        }
+    }
     __syncwarp();
     float* o = Y + (long long)b * T * ldy + c * RG_D + head * RG_HD + lane;
-    for (int n = 0; n < T; ++n) {
-        float y;
-        row_times_A(slice + n * HG * RG_HD, A, y);
-        if (qm) y = y + (1.0f - qm[n]) * RG_NEG_MASK;       // fp32 add: y - 1e6 rounds to a 1/16 grid
-        o[(long long)n * ldy] = y;
+#pragma unroll
+    for (int i = 0; i < MAXN; ++i) {
+        const int n = w + i * TW;
+        if (n < T) {
+            float y;
+            row_times_A(&rows[n][0], A, y);
+            if (qm) y = y + (1.0f - mk[i]) * RG_NEG_MASK;   // fp32 add: y - 1e6 rounds to a 1/16 grid
+            o[(long long)n * ldy] = y;
+        }
     }
 }
 
 // Stylization prologue of the three cross-attention blocks over Y[M,1536]: blockIdx.y = condition
 __global__ void __launch_bounds__(256) styl_rows3_kernel(const float* __restrict__ y, int ldy, RgStyl3 sp3,
                                                         int rows_per_clip, RgRowOut out, int M) {
+    rg_pdl_launch();
+    rg_pdl_wait();
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), c = blockIdx.y, lane = threadIdx.x & 31;
     if (row >= M) return;
     float4 v[4];
@@ -360,8 +467,7 @@ cudaError_t rg_launch_ca_attention(const float* q3, int ldq, const float* state,
 cudaError_t rg_launch_sa_core(const float* qkv, const float* src_mask, float* Y, int B, int T, cudaStream_t st) {
     if (B <= 0) return cudaSuccess;
     if (T > RG_MAX_T) return cudaErrorInvalidValue;
-    sa_core_kernel<<<dim3(B, RG_H / HG), HG * 32, (size_t)T * HG * RG_HD * sizeof(float), st>>>(qkv, src_mask, Y, T);
-    return cudaGetLastError();
+    return rg_launch_pdl(sa_core_kernel, dim3(B, RG_H), dim3(TW * 32), 0, st, qkv, src_mask, Y, T);
 }
 
 cudaError_t rg_launch_ca_core(const float* q3, int ldq, const float* state, long long state_clip_stride,
@@ -369,9 +475,8 @@ cudaError_t rg_launch_ca_core(const float* q3, int ldq, const float* state, long
                               float* Y, int ldy, int B, int T, cudaStream_t st) {
     if (B <= 0) return cudaSuccess;
     if (T > RG_MAX_T) return cudaErrorInvalidValue;
-    ca_core_kernel<<<dim3(B, 3, RG_H / HG), HG * 32, (size_t)T * HG * RG_HD * sizeof(float), st>>>(
-        q3, ldq, state, state_clip_stride, state_cond_stride, qmask, qmask_cond_stride, Y, ldy, T);
-    return cudaGetLastError();
+    return rg_launch_pdl(ca_core_kernel, dim3(B, 3, RG_H), dim3(TW * 32), 0, st, q3, ldq, state, state_clip_stride,
+                         state_cond_stride, qmask, qmask_cond_stride, Y, ldy, T);
 }
 
 cudaError_t rg_launch_styl_rows3(const float* y, int ldy, const RgStylParams* sp3, int rows_per_clip,
@@ -379,8 +484,7 @@ cudaError_t rg_launch_styl_rows3(const float* y, int ldy, const RgStylParams* sp
     if (M <= 0) return cudaSuccess;
     RgStyl3 s3;
     for (int c = 0; c < 3; ++c) s3.p[c] = sp3[c];
-    styl_rows3_kernel<<<dim3((M + 7) / 8, 3), 256, 0, st>>>(y, ldy, s3, rows_per_clip, out, M);
-    return cudaGetLastError();
+    return rg_launch_pdl(styl_rows3_kernel, dim3((M + 7) / 8, 3), dim3(256), 0, st, y, ldy, s3, rows_per_clip, out, M);
 }
 
 cudaError_t rg_launch_kv_state(const float* kv, int ldkv, int k_off, int v_off, int n_tokens,

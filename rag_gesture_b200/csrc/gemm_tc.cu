@@ -20,7 +20,7 @@
 
 namespace {
 
-constexpr int BM = 128, BK = 64, STAGES = 3;
+constexpr int BM = 128, BK = 64;
 constexpr int UMMA_K = 16;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -97,8 +97,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t v[32]) {
         : "r"(taddr));
 }
 
-template <int BN>
-__global__ void __launch_bounds__(192, 2)
+// STAGES = 3: two CTAs per SM (grids above one wave); STAGES = 6: one CTA per SM with the whole K = 512
+// reduction in flight (small grids, where a tile's latency, not throughput, is what is measured).
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, STAGES <= 3 ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, RgGemmTc p) {
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment
@@ -107,6 +109,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar;
     __shared__ uint32_t tmem_base_smem;
 
+    rg_pdl_launch();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = blockIdx.z;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
@@ -131,6 +134,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_smem;
+    rg_pdl_wait();      // barriers, TMEM and descriptors are set up; operands of the previous kernel from here on
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -199,38 +203,54 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int q = 0; q < NV; ++q)
             bv[q] = bias ? __ldg(reinterpret_cast<const float4*>(bias + q * 128 + lane * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
         const int row0 = m0 + lg * 32;
-#pragma unroll 2
-        for (int r = 0; r < 32; ++r) {
-            const int row = row0 + r;
-            if (row >= p.M) break;
+        constexpr int RB = 8;                       // rows per batch: all shared/global loads first
+#pragma unroll 1
+        for (int r0 = 0; r0 < 32; r0 += RB) {
+            float4 f[RB][NV], rr[RB][NV];
 #pragma unroll
-            for (int q = 0; q < NV; ++q) {
-                const int cc = q * 128 + lane * 4;
-                float4 f = *reinterpret_cast<const float4*>(stage + r * PITCH + cc);
-                f.x += bv[q].x; f.y += bv[q].y; f.z += bv[q].z; f.w += bv[q].w;
-                if (p.epi == RG_EPI_BIAS_RESIDUAL) {
-                    const float4 b = *reinterpret_cast<const float4*>(p.R + (long long)row * p.ldr + rbase + cc);
-                    f.x += b.x; f.y += b.y; f.z += b.z; f.w += b.w;
-                } else if (p.epi == RG_EPI_BIAS_GELU) {
-                    f.x = rg_gelu_erf(f.x); f.y = rg_gelu_erf(f.y); f.z = rg_gelu_erf(f.z); f.w = rg_gelu_erf(f.w);
-                } else if (p.epi == RG_EPI_BIAS_SILU) {
-                    f.x = rg_silu(f.x); f.y = rg_silu(f.y); f.z = rg_silu(f.z); f.w = rg_silu(f.w);
-                } else if (p.epi == RG_EPI_BIAS_POS) {
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(p.pos + (long long)(row % p.pos_T) * p.N + n0 + cc));
-                    f.x += b.x; f.y += b.y; f.z += b.z; f.w += b.w;
-                }
-                if (p.C32) *reinterpret_cast<float4*>(p.C32 + (long long)row * p.ldc32 + cbase + cc) = f;
-                if (p.C16_) {
-                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.C16_) + (long long)row * p.ldc16 + cbase + cc;
-                    const float ff[4] = {f.x, f.y, f.z, f.w};
-                    __nv_bfloat16 h[4], l[4];
+            for (int i = 0; i < RB; ++i) {
+                const int row = row0 + r0 + i;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        h[k] = __float2bfloat16_rn(ff[k]);
-                        l[k] = __float2bfloat16_rn(ff[k] - __bfloat162float(h[k]));
+                for (int q = 0; q < NV; ++q) {
+                    const int cc = q * 128 + lane * 4;
+                    f[i][q] = *reinterpret_cast<const float4*>(stage + (r0 + i) * PITCH + cc);
+                    rr[i][q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (row < p.M) {
+                        if (p.epi == RG_EPI_BIAS_RESIDUAL)
+                            rr[i][q] = *reinterpret_cast<const float4*>(p.R + (long long)row * p.ldr + rbase + cc);
+                        else if (p.epi == RG_EPI_BIAS_POS)
+                            rr[i][q] = __ldg(reinterpret_cast<const float4*>(p.pos + (long long)(row % p.pos_T) * p.N + n0 + cc));
                     }
-                    *reinterpret_cast<uint2*>(o) = *reinterpret_cast<uint2*>(h);
-                    if (p.c16_lo_off) *reinterpret_cast<uint2*>(o + p.c16_lo_off) = *reinterpret_cast<uint2*>(l);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < RB; ++i) {
+                const int row = row0 + r0 + i;
+                if (row >= p.M) break;
+#pragma unroll
+                for (int q = 0; q < NV; ++q) {
+                    const int cc = q * 128 + lane * 4;
+                    float4 v = f[i][q];
+                    v.x += bv[q].x + rr[i][q].x; v.y += bv[q].y + rr[i][q].y;
+                    v.z += bv[q].z + rr[i][q].z; v.w += bv[q].w + rr[i][q].w;
+                    if (p.epi == RG_EPI_BIAS_GELU) {
+                        v.x = rg_gelu_erf(v.x); v.y = rg_gelu_erf(v.y); v.z = rg_gelu_erf(v.z); v.w = rg_gelu_erf(v.w);
+                    } else if (p.epi == RG_EPI_BIAS_SILU) {
+                        v.x = rg_silu(v.x); v.y = rg_silu(v.y); v.z = rg_silu(v.z); v.w = rg_silu(v.w);
+                    }
+                    if (p.C32) *reinterpret_cast<float4*>(p.C32 + (long long)row * p.ldc32 + cbase + cc) = v;
+                    if (p.C16_) {
+                        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.C16_) + (long long)row * p.ldc16 + cbase + cc;
+                        const float ff[4] = {v.x, v.y, v.z, v.w};
+                        __nv_bfloat16 h[4], l[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            h[k] = __float2bfloat16_rn(ff[k]);
+                            l[k] = __float2bfloat16_rn(ff[k] - __bfloat162float(h[k]));
+                        }
+                        *reinterpret_cast<uint2*>(o) = *reinterpret_cast<uint2*>(h);
+                        if (p.c16_lo_off) *reinterpret_cast<uint2*>(o + p.c16_lo_off) = *reinterpret_cast<uint2*>(l);
+                    }
                 }
             }
         }
@@ -247,6 +267,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 __global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ x, int ldx,
                                                         __nv_bfloat16* __restrict__ out, int ldo, int lo_off,
                                                         long long rows, int cols) {
+    rg_pdl_launch();
+    rg_pdl_wait();
     const long long n4 = rows * (cols / 4);
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -296,16 +318,20 @@ cudaError_t rg_launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmW, co
     constexpr int BN = 128;
     if (p.K % BK || p.N % BN || (p.C32 && p.ldc32 % 4) || (p.C16_ && p.ldc16 % 8) || (p.R && p.ldr % 4))
         return cudaErrorInvalidValue;
-    const size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 1024;
+    constexpr size_t STAGE = BM * BK * 2 + BN * BK * 2;
+    constexpr size_t smem3 = 3 * STAGE + 1024, smem6 = 6 * STAGE + 1024;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<BN, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
     dim3 grid(p.N / BN, (p.M + BM - 1) / BM, p.groups > 0 ? p.groups : 1);
-    gemm_tc_kernel<BN><<<grid, 192, smem, st>>>(tmA, tmW, p);
-    return cudaGetLastError();
+    const long long ctas = (long long)grid.x * grid.y * grid.z;
+    if (ctas <= 148)
+        return rg_launch_pdl(gemm_tc_kernel<BN, 6>, grid, dim3(192), smem6, st, tmA, tmW, p);
+    return rg_launch_pdl(gemm_tc_kernel<BN, 3>, grid, dim3(192), smem3, st, tmA, tmW, p);
 }
 
 cudaError_t rg_launch_split_bf16(const float* x, int ldx, void* out, int ldo, int lo_off, long long rows, int cols,
@@ -314,6 +340,6 @@ cudaError_t rg_launch_split_bf16(const float* x, int ldx, void* out, int ldo, in
     if (cols % 4 || ldx % 4 || ldo % 4 || lo_off % 4) return cudaErrorInvalidValue;
     const long long n4 = rows * (cols / 4);
     const int blocks = (int)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
-    split_bf16_kernel<<<blocks, 256, 0, st>>>(x, ldx, reinterpret_cast<__nv_bfloat16*>(out), ldo, lo_off, rows, cols);
-    return cudaGetLastError();
+    return rg_launch_pdl(split_bf16_kernel, dim3(blocks), dim3(256), 0, st, x, ldx, reinterpret_cast<__nv_bfloat16*>(out),
+                         ldo, lo_off, rows, cols);
 }

@@ -96,6 +96,29 @@ cudaError_t rg_launch_kv_state(const float* kv, int ldkv, int k_off, int v_off, 
                                float* state, long long state_clip_stride, int B, int n_sets,
                                int kv_set_stride, long long state_set_stride, cudaStream_t st);
 
+// ---- programmatic dependent launch (PDL) ----------------------------------------------------
+// Every kernel of the per-step chain is launched with programmaticStreamSerialization and starts with
+// rg_pdl_launch() (lets the NEXT kernel's CTAs be scheduled early) and rg_pdl_wait() (blocks until the
+// PREVIOUS kernel has completed and its writes are visible) before touching dependent data: the launch
+// latency and prologue of kernel N+1 overlap the tail of kernel N.  Without the launch attribute both
+// instructions are no-ops.
+#ifdef __CUDACC__
+__device__ __forceinline__ void rg_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void rg_pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t rg_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                        cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
+
 // ---- device helpers ---------------------------------------------------------------------
 __device__ __forceinline__ float rg_warp_sum(float v) {
 #pragma unroll

@@ -16,6 +16,8 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ 
                                                      const float* __restrict__ gamma,
                                                      const float* __restrict__ beta,
                                                      RgRowOut out, int M) {
+    rg_pdl_launch();
+    rg_pdl_wait();
     const int row = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= M) return;
@@ -36,6 +38,8 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ 
 __global__ void __launch_bounds__(256) styl_rows_kernel(const float* __restrict__ y, int ldy,
                                                        RgStylParams sp, int rows_per_clip,
                                                        RgRowOut out, int M) {
+    rg_pdl_launch();
+    rg_pdl_wait();
     const int row = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= M) return;
@@ -91,6 +95,8 @@ __global__ void __launch_bounds__(256) ddim_update_kernel(const float4* x, const
                                                          float4* out, long long n4,
                                                          float c_recip, float c_recipm1, float c_a,
                                                          float c_b) {
+    rg_pdl_launch();
+    rg_pdl_wait();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (; i < n4; i += stride) {
@@ -113,6 +119,8 @@ __global__ void __launch_bounds__(256) blend_kernel(const float* x,
                                                    const float* __restrict__ noise,
                                                    float* out, long long rows,
                                                    float s_ab, float s_1mab) {
+    rg_pdl_launch();
+    rg_pdl_wait();
     const long long row = (long long)blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -180,14 +188,12 @@ inline int row_blocks(long long rows) { return (int)((rows + ROWS_PER_BLOCK - 1)
 cudaError_t rg_launch_ln_rows(const float* x, int ldx, const float* gamma, const float* beta,
                               RgRowOut out, int M, cudaStream_t st) {
     if (M <= 0) return cudaSuccess;
-    ln_rows_kernel<<<row_blocks(M), 256, 0, st>>>(x, ldx, gamma, beta, out, M);
-    return cudaGetLastError();
+    return rg_launch_pdl(ln_rows_kernel, dim3(row_blocks(M)), dim3(256), 0, st, x, ldx, gamma, beta, out, M);
 }
 cudaError_t rg_launch_styl_rows(const float* y, int ldy, RgStylParams sp, int rows_per_clip,
                                 RgRowOut out, int M, cudaStream_t st) {
     if (M <= 0) return cudaSuccess;
-    styl_rows_kernel<<<row_blocks(M), 256, 0, st>>>(y, ldy, sp, rows_per_clip, out, M);
-    return cudaGetLastError();
+    return rg_launch_pdl(styl_rows_kernel, dim3(row_blocks(M)), dim3(256), 0, st, y, ldy, sp, rows_per_clip, out, M);
 }
 cudaError_t rg_launch_silu(const float* x, float* out, long long n, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
@@ -213,17 +219,14 @@ cudaError_t rg_launch_ddim_update(const float* x, const float* x0, float* out, l
     if (n % 4) return cudaErrorInvalidValue;
     const long long n4 = n / 4;
     const int blocks = (int)((n4 + 255) / 256 < 148 * 8 ? (n4 + 255) / 256 : 148 * 8);
-    ddim_update_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(x),
-                                               reinterpret_cast<const float4*>(x0),
-                                               reinterpret_cast<float4*>(out), n4, c_recip,
-                                               c_recipm1, c_a, c_b);
-    return cudaGetLastError();
+    return rg_launch_pdl(ddim_update_kernel, dim3(blocks), dim3(256), 0, st, reinterpret_cast<const float4*>(x),
+                         reinterpret_cast<const float4*>(x0), reinterpret_cast<float4*>(out), n4, c_recip,
+                         c_recipm1, c_a, c_b);
 }
 cudaError_t rg_launch_blend(const float* x, const float* in_seq, const float* noise, float* out,
                             long long rows, float s_ab, float s_1mab, cudaStream_t st) {
     if (rows <= 0) return cudaSuccess;
-    blend_kernel<<<row_blocks(rows), 256, 0, st>>>(x, in_seq, noise, out, rows, s_ab, s_1mab);
-    return cudaGetLastError();
+    return rg_launch_pdl(blend_kernel, dim3(row_blocks(rows)), dim3(256), 0, st, x, in_seq, noise, out, rows, s_ab, s_1mab);
 }
 cudaError_t rg_launch_guidance(float* x, const float* in_seq, long long rows, int iters,
                                float lr_2_over_n, cudaStream_t st) {

@@ -35,7 +35,7 @@ def ev_time(fn, n):
     return a.elapsed_time(b) / n, t_launch
 
 
-for B in (64, 96, 160):
+for B in [int(b) for b in os.environ.get('DIAG_B', '64,96,160').split(',')]:
     cond = S.synthetic_conditions(B, seed=5)
     xf = eng.encode_conditions(cond["word"].to(dev), cond["audio"].to(dev), cond["speaker_ids"].to(dev))
     t_state, _ = ev_time(lambda: eng.precompute_state(xf), 3)
