@@ -27,6 +27,17 @@ int rg_fail(const char* fmt, ...) {
     return 1;
 }
 void rg_count_launch(int n) { g_launches += n; }
+void rg_keep_mempool() {
+    static int done_for = -1;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev == done_for) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    done_for = dev;
+}
 
 #define CU(expr)                                                                              \
     do {                                                                                      \
@@ -679,6 +690,7 @@ extern "C" int rg_op_linear_tc(const float* x, const float* W, const float* b, c
     if (N % 128 || K % 64) return rg_fail("rg_op_linear_tc: need N %% 128 == 0 and K %% 64 == 0 (got N=%d K=%d)", N, K);
     if (epi == RG_EPI_BIAS_RESIDUAL && !residual) return rg_fail("rg_op_linear_tc: residual epilogue without residual");
     const int planes = split ? 2 : 1;
+    rg_keep_mempool();
     void *a16 = nullptr, *w16 = nullptr;
     CU(cudaMallocAsync(&a16, (size_t)M * K * planes * 2, st));
     CU(cudaMallocAsync(&w16, (size_t)N * K * planes * 2, st));

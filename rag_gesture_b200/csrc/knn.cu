@@ -136,6 +136,144 @@ __global__ void __launch_bounds__(256) knn_scan_kernel(const float* __restrict__
     }
 }
 
+// ---- fast path: dim == 768 (the embedding width of the path) ------------------------------------------
+// Budget at HBM rate: 133 SM-cycles per 3 KB row.  Each warp takes R = 4 rows per iteration and issues all
+// 24 128-bit loads first (12 KB in flight per warp); the query chunk read from shared memory then serves 4
+// rows (LDS traffic /4), the R*QT partial sums are reduced with a transposing butterfly (31 shuffles instead
+// of 160), and the owning lane tests against the replicated k-th best before any cooperative insert.
+template <int NV>
+__device__ __forceinline__ float reduce_transpose(float (&a)[NV], int lane) {
+    int n = NV / 2;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        if (n >= 1) {
+            const bool upper = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < NV / 2; ++i) {
+                if (i < n) {
+                    const float send = upper ? a[i] : a[i + n];
+                    const float keep = upper ? a[i + n] : a[i];
+                    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
+            }
+            n >>= 1;
+        } else {
+            a[0] += __shfl_xor_sync(0xffffffffu, a[0], off);
+        }
+    }
+    return a[0];
+}
+
+template <int QT>
+__global__ void __launch_bounds__(256, 1) knn_scan768_kernel(const float* __restrict__ db, long long n,
+                                                            const float* __restrict__ queries, int q_total,
+                                                            int q0, int k, long long rows_per_block,
+                                                            long long* __restrict__ part_idx,
+                                                            float* __restrict__ part_score) {
+    constexpr int DIM = 768, NCH = DIM / 128, R = 4, NV = R * QT;
+    constexpr int SHIFT = (NV == 32) ? 0 : (NV == 16) ? 1 : (NV == 8) ? 2 : (NV == 4) ? 3 : 4;   // pair = lane >> SHIFT
+    extern __shared__ __align__(16) float smem[];
+    float* qs = smem;                                                   // [QT][768]
+    float* ms = smem + QT * DIM;                                        // [WARPS][QT][32]
+    long long* mi = reinterpret_cast<long long*>(ms + KNN_WARPS * QT * 32);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nq = (q_total - q0 < QT) ? q_total - q0 : QT;
+    for (int e = threadIdx.x; e < QT * DIM; e += blockDim.x)
+        qs[e] = (e / DIM < nq) ? queries[(long long)q0 * DIM + e] : 0.f;
+    __syncthreads();
+
+    float ls[QT], ts[QT];
+    long long li[QT], ti[QT];
+#pragma unroll
+    for (int q = 0; q < QT; ++q) { ls[q] = -INFINITY; li[q] = IDX_NONE; ts[q] = -INFINITY; ti[q] = IDX_NONE; }
+
+    const long long row0 = (long long)blockIdx.x * rows_per_block;
+    long long row1 = row0 + rows_per_block;
+    if (row1 > n) row1 = n;
+    const int pair = lane >> SHIFT, pi = pair / QT, pq = pair % QT;
+    const bool holder = (lane & ((1 << SHIFT) - 1)) == 0;
+    for (long long r = row0 + R * warp; r < row1; r += R * KNN_WARPS) {
+        float4 x[R][NCH];
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            const long long rr = (r + i < row1) ? r + i : r;            // clamp: duplicates are discarded below
+            const float4* p4 = reinterpret_cast<const float4*>(db + rr * DIM);
+#pragma unroll
+            for (int j = 0; j < NCH; ++j) x[i][j] = __ldg(p4 + lane + 32 * j);
+        }
+        float acc[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) acc[v] = 0.f;
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) {
+#pragma unroll
+            for (int q = 0; q < QT; ++q) {
+                const float4 w = *reinterpret_cast<const float4*>(qs + q * DIM + (lane + 32 * j) * 4);
+#pragma unroll
+                for (int i = 0; i < R; ++i) {
+                    float a = acc[i * QT + q];
+                    a = fmaf(x[i][j].x, w.x, a); a = fmaf(x[i][j].y, w.y, a);
+                    a = fmaf(x[i][j].z, w.z, a); a = fmaf(x[i][j].w, w.w, a);
+                    acc[i * QT + q] = a;
+                }
+            }
+        }
+        const float v = reduce_transpose<NV>(acc, lane);                // lane holds the score of (row pi, query pq)
+        const long long id = r + pi;
+        float tq = ts[0];
+        long long tiq = ti[0];
+#pragma unroll
+        for (int q = 1; q < QT; ++q) if (pq == q) { tq = ts[q]; tiq = ti[q]; }
+        unsigned cand = __ballot_sync(0xffffffffu, holder && pq < nq && id < row1 && better(v, id, tq, tiq));
+        while (cand) {
+            const int src = __ffs(cand) - 1;
+            cand &= cand - 1;
+            const float s = __shfl_sync(0xffffffffu, v, src);
+            const int sp = src >> SHIFT, sq = sp % QT;
+            const long long sid = r + sp / QT;
+#pragma unroll
+            for (int q = 0; q < QT; ++q) {
+                if (q == sq) {
+                    list_insert(ls[q], li[q], s, sid, k, lane);
+                    ts[q] = __shfl_sync(0xffffffffu, ls[q], k - 1);
+                    ti[q] = __shfl_sync(0xffffffffu, li[q], k - 1);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < QT; ++q) {
+        ms[(warp * QT + q) * 32 + lane] = ls[q];
+        mi[(warp * QT + q) * 32 + lane] = li[q];
+    }
+    __syncthreads();
+    for (int q = warp; q < nq; q += KNN_WARPS) {
+        float bs = -INFINITY;
+        long long bi = IDX_NONE;
+        for (int w = 0; w < KNN_WARPS; ++w)
+            for (int j = 0; j < k; ++j) {
+                const long long id = mi[(w * QT + q) * 32 + j];
+                if (id != IDX_NONE) list_insert(bs, bi, ms[(w * QT + q) * 32 + j], id, k, lane);
+            }
+        if (lane < k) {
+            const long long o = ((long long)blockIdx.x * q_total + (q0 + q)) * k + lane;
+            part_idx[o] = bi;
+            part_score[o] = bs;
+        }
+    }
+}
+
+template <int QT>
+static cudaError_t launch_scan768(const float* db, long long n, const float* queries, int q, int q0, int k,
+                                  int blocks, long long rows_per_block, long long* part_idx, float* part_score,
+                                  cudaStream_t st) {
+    const size_t smem = (size_t)QT * 768 * sizeof(float) + (size_t)KNN_WARPS * QT * 32 * (sizeof(float) + sizeof(long long));
+    cudaError_t e = cudaFuncSetAttribute(knn_scan768_kernel<QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    knn_scan768_kernel<QT><<<blocks, 256, smem, st>>>(db, n, queries, q, q0, k, rows_per_block, part_idx, part_score);
+    return cudaGetLastError();
+}
+
 // one warp per query: merge parts*k candidates
 __global__ void __launch_bounds__(256) knn_merge_kernel(const long long* __restrict__ idx_parts,
                                                        const float* __restrict__ score_parts,
@@ -198,9 +336,12 @@ extern "C" int rg_knn_topk(const float* db, int64_t n, int dim, const float* que
     if (dim % 4 || dim > 4096) return rg_fail("rg_knn_topk: dim must be a multiple of 4 and <= 4096");
     if (q <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
+    rg_keep_mempool();
     // grid: a multiple of the SM count; each block scans a contiguous slab of the shard
-    int blocks = 148 * 4;
-    if (n < (long long)blocks * 2 * KNN_WARPS) blocks = (int)((n + 2 * KNN_WARPS - 1) / (2 * KNN_WARPS));
+    const bool fast = (dim == 768);
+    int blocks = fast ? 148 : 148 * 4;
+    const int rows_per_iter = (fast ? 4 : 2) * KNN_WARPS;
+    if (n < (long long)blocks * rows_per_iter) blocks = (int)((n + rows_per_iter - 1) / rows_per_iter);
     if (blocks < 1) blocks = 1;
     const long long rows_per_block = (n + blocks - 1) / blocks;
     long long* part_idx = nullptr;
@@ -208,11 +349,21 @@ extern "C" int rg_knn_topk(const float* db, int64_t n, int dim, const float* que
     RG_CU(cudaMallocAsync((void**)&part_idx, (size_t)blocks * q * k * sizeof(long long), st));
     RG_CU(cudaMallocAsync((void**)&part_score, (size_t)blocks * q * k * sizeof(float), st));
     const size_t smem = (size_t)KNN_QT * dim * sizeof(float) + (size_t)KNN_WARPS * KNN_QT * 32 * (sizeof(float) + sizeof(long long));
-    RG_CU(cudaFuncSetAttribute(knn_scan_kernel<KNN_QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    for (int q0 = 0; q0 < q; q0 += KNN_QT) {
-        knn_scan_kernel<KNN_QT><<<blocks, 256, smem, st>>>(db, n, dim, queries, q, q0, k, rows_per_block,
-                                                           part_idx, part_score);
-        RG_CU(cudaGetLastError());
+    if (!fast) RG_CU(cudaFuncSetAttribute(knn_scan_kernel<KNN_QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int q0 = 0; q0 < q;) {
+        const int left = q - q0;
+        if (fast) {
+            // widest tile that is not mostly padding: 8 queries per pass, 4 / 2 / 1 for the tail
+            if (left >= 5) { RG_CU(launch_scan768<8>(db, n, queries, q, q0, k, blocks, rows_per_block, part_idx, part_score, st)); q0 += 8; }
+            else if (left >= 3) { RG_CU(launch_scan768<4>(db, n, queries, q, q0, k, blocks, rows_per_block, part_idx, part_score, st)); q0 += 4; }
+            else if (left == 2) { RG_CU(launch_scan768<2>(db, n, queries, q, q0, k, blocks, rows_per_block, part_idx, part_score, st)); q0 += 2; }
+            else { RG_CU(launch_scan768<1>(db, n, queries, q, q0, k, blocks, rows_per_block, part_idx, part_score, st)); q0 += 1; }
+        } else {
+            knn_scan_kernel<KNN_QT><<<blocks, 256, smem, st>>>(db, n, dim, queries, q, q0, k, rows_per_block,
+                                                               part_idx, part_score);
+            RG_CU(cudaGetLastError());
+            q0 += KNN_QT;
+        }
         rg_count_launch(1);
     }
     knn_merge_kernel<<<(q + KNN_WARPS - 1) / KNN_WARPS, 256, 0, st>>>(part_idx, part_score, blocks, q, k,

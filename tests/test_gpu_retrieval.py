@@ -84,6 +84,19 @@ def test_knn_topk_exact(dev, N, Q, k):
         assert bool((idx[:, N:] == -1).all())
 
 
+def test_knn_topk_generic_dim(dev):
+    """dim != 768 takes the generic scan kernel."""
+    from rag_gesture_b200.parallel import knn_topk
+    g = torch.Generator().manual_seed(5)
+    db, qs = torch.randn(3001, 256, generator=g), torch.randn(11, 256, generator=g)
+    idx, sc = knn_topk(db.to(dev), qs.to(dev), 8)
+    ref_idx, ref_sc, gaps = ORT.knn_topk_f64(db, qs, 8)
+    for q in range(11):
+        if gaps[q] > 1e-5:
+            assert torch.equal(idx[q].cpu(), ref_idx[q]), q
+    assert torch.allclose(sc.cpu().double(), ref_sc, atol=1e-4)
+
+
 def test_knn_merge_matches_single_shard(dev):
     from rag_gesture_b200.parallel import _cuda_merge, knn_topk, shard_range
     g = torch.Generator().manual_seed(3)
