@@ -195,7 +195,7 @@ def run_b200(args):
     e2e_value = float(total_steps) * args.steps / t_e2e
 
     # ---- roofline of the dominant kernel family: the dense GEMMs of one denoiser evaluation --------------
-    roof = gemm_roofline(arch, B + E, dev, flush, tc_sus, peak_src, args.precision)
+    roof = gemm_roofline(arch, [B, E], dev, flush, tc_sus, peak_src, args.precision)
     knn = knn_bench(args, dev, rank, world, hbm_peak, peak_src, flush)
 
     if rank == 0:
@@ -232,7 +232,7 @@ def gemm_roofline(arch, n_clips, dev, flush, tc_peak, peak_src, precision):
     from rag_gesture_b200 import _lib, ops
     if precision != "fp32":
         return gemm_roofline_tc(n_clips, dev, flush, tc_peak, peak_src, precision == "bf16x3")
-    M = n_clips * 43
+    M = sum(n_clips) * 43
     shapes = [("qkv", 1536, 512, 8), ("sa_proj", 512, 512, 8), ("ca_q", 1536, 512, 8), ("ca_proj", 512, 512, 24),
               ("ca_mix", 512, 1536, 8), ("ffn1", 1024, 512, 8), ("ffn2", 512, 1024, 8), ("ffn_proj", 512, 512, 8),
               ("embed/out", 512, 512, 2)]
@@ -263,32 +263,37 @@ def gemm_roofline(arch, n_clips, dev, flush, tc_peak, peak_src, precision):
 
 
 def gemm_roofline_tc(n_clips, dev, flush, tc_peak, peak_src, split):
-    """tcgen05 GEMM launches alone (operands pre-converted to bf16 planes, as inside rg_denoise):
-    ALGORITHMIC flops 2*M*N*K per launch (bf16x3 executes 3x that on the pipe) / event time."""
+    """tcgen05 GEMM launches alone, at the row counts the two loops of a bench step actually launch
+    (M = 43 * clips for the guided loop, 43 * exemplars for the inversion loop; 50 evaluations each),
+    operands pre-converted to bf16 planes as inside rg_denoise.  achieved = ALGORITHMIC flops
+    (2*M*N*K per launch; bf16x3 executes 3x that on the pipe) / CUDA-event time, time-weighted."""
     import ctypes
     from rag_gesture_b200 import _lib
     lib = _lib.load()
-    M = n_clips * 43
     shapes = [("qkv", 1536, 512, 8), ("sa_proj", 512, 512, 8), ("ca_q", 1536, 512, 8), ("ca_proj", 512, 512, 24),
               ("ca_mix", 512, 1536, 8), ("ffn1", 1024, 512, 8), ("ffn2", 512, 1024, 8), ("ffn_proj", 512, 512, 8),
               ("embed/out", 512, 512, 2)]
     tot_t, tot_f, per = 0.0, 0.0, {}
-    for name, N, K, count in shapes:
-        x, w, b = torch.randn(M, K, device=dev), torch.randn(N, K, device=dev), torch.randn(N, device=dev)
-        out = torch.empty(M, N, device=dev)
-        ts = ctypes.c_float()
-        _lib.check(lib.rg_probe_gemm_tc(_lib.ptr(x), _lib.ptr(w), _lib.ptr(b), _lib.ptr(out), M, N, K, int(split),
-                                        5, _lib.ptr(flush), flush.numel(), ctypes.byref(ts), _lib.stream_ptr()))
-        t = ts.value / 1e3
-        per[name] = round(2.0 * M * N * K / t / 1e12, 1)
-        tot_t += t * count
-        tot_f += 2.0 * M * N * K * count
+    for clips in n_clips:
+        M = clips * 43
+        if M <= 0:
+            continue
+        for name, N, K, count in shapes:
+            x, w, b = torch.randn(M, K, device=dev), torch.randn(N, K, device=dev), torch.randn(N, device=dev)
+            out = torch.empty(M, N, device=dev)
+            ts = ctypes.c_float()
+            _lib.check(lib.rg_probe_gemm_tc(_lib.ptr(x), _lib.ptr(w), _lib.ptr(b), _lib.ptr(out), M, N, K, int(split),
+                                            5, _lib.ptr(flush), flush.numel(), ctypes.byref(ts), _lib.stream_ptr()))
+            t = ts.value / 1e3
+            per[f"{name}@M{M}"] = round(2.0 * M * N * K / t / 1e12, 1)
+            tot_t += t * count
+            tot_f += 2.0 * M * N * K * count
     ach = tot_f / tot_t / 1e12
-    return {"bound": "tensor", "kernel": "gemm_tc_kernel<128> (tcgen05.mma kind::f16, TMA-fed, TMEM accumulator; all "
-            "GEMM shapes of one denoiser evaluation, time-weighted)", "achieved": round(ach, 1), "peak": tc_peak,
-            "unit": "TFLOP/s", "frac": round(ach / tc_peak, 4), "traffic": None,
-            "peak_source": f"{peak_src} bf16 sustained", "rows": M, "per_shape_tflops": per,
-            "executed_flop_multiplier": 3 if split else 1}
+    return {"bound": "tensor", "kernel": "gemm_tc_kernel<128,*> (tcgen05.mma kind::f16, TMA-fed, TMEM accumulator; all "
+            "GEMM launches of one inversion + one sampling evaluation, time-weighted, L2 flushed before each)",
+            "achieved": round(ach, 1), "peak": tc_peak, "unit": "TFLOP/s", "frac": round(ach / tc_peak, 4),
+            "traffic": None, "peak_source": f"{peak_src} bf16 sustained", "rows": [c * 43 for c in n_clips],
+            "per_shape_tflops": per, "executed_flop_multiplier": 3 if split else 1}
 
 
 def knn_bench(args, dev, rank, world, hbm_peak, peak_src, flush):

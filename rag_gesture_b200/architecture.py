@@ -133,12 +133,7 @@ class MotionDiffusion(nn.Module):
             assert seq.shape[1] == 1
             gb.outpaint_seq = seq.squeeze(1)
         if gb.use_prev and gb.prev_latent is not None:
-            upper, hands, face, lower = self._row_sets(T)
-            prev = gb.prev_latent.to(device)
-            masked = torch.zeros_like(prev)
-            for rows in (upper, hands, face, lower):       # last token of each part -> its first token
-                masked[:, rows[0]] = prev[:, rows[-1]]
-            gb.prev_latent = masked
+            gb.prev_latent = self.mask_prev_latent(gb.prev_latent.to(device))
 
         # all exemplars of all clips, in the reference's visiting order (clip-major, dict order)
         if gb.use_inversion:
@@ -154,36 +149,61 @@ class MotionDiffusion(nn.Module):
                               for b, q in gb.jobs]
         return gb
 
+    def mask_prev_latent(self, prev):
+        """Long-form chaining (:286-297): only the first token of each body part is kept, and it takes the
+        LAST token of that part of the previous window; None stays None."""
+        if prev is None:
+            return None
+        masked = torch.zeros_like(prev)
+        for rows in self._row_sets(prev.shape[1]):
+            masked[:, rows[0]] = prev[:, rows[-1]]
+        return masked
+
+    def invert_many(self, gbs):
+        """DDIM-invert the exemplars of one or several prepared batches in ONE batched 50-step reverse loop
+        (the reference: one loop per exemplar at B=1, :323-354).  Sets gb.inv = [steps, E_gb, T, D]."""
+        todo = [gb for gb in gbs if gb.use_inversion and gb.jobs and gb.inv is None]
+        if not todo:
+            return
+        diff, device = self.diffusion_test, todo[0].device
+        cat = lambda key: torch.cat([gb.ex[key] for gb in todo], 0)
+        self.model._state_cache = (None, None)
+        with torch.no_grad():
+            ex_kwargs = self.model.get_precompute_condition(device=device, text=cat("retr_text"), audio=cat("retr_audio"),
+                                                            speaker_ids=cat("retr_spkid"), re_dict=1)
+        ex_kwargs["query_mask"] = {c: torch.cat([gb.ex_query_mask[c] for gb in todo], 0) for c in CFG.CONDS}
+        ex_kwargs["motion_mask"] = cat("retr_motion_mask")
+        inv = diff.ddim_reverse_sample_loop(self.model, start_img=cat("retr_motion_latent"), clip_denoised=False,
+                                            progress=False, model_kwargs=ex_kwargs, eta=0,
+                                            return_all_timesteps=True, **todo[0].extra)
+        inv = torch.stack(inv, 0)                       # [steps, E_total, T, D], clean -> noisy
+        off = 0
+        for gb in todo:
+            gb.inv = inv[:, off:off + len(gb.jobs)]
+            off += len(gb.jobs)
+
     # ---- stage 2: the hot path proper, device-resident inputs -> output latents ---------------------
-    def run_prepared(self, gb):
+    def run_prepared(self, gb, keep_inversion=False):
         """K6 state for the B clips and E exemplars, ONE batched 50-step inversion of the exemplars,
         window insertion, 50 guided (or plain) sampling steps: 50 * (B + E) clip-steps."""
         diff, (B, T, D), device = self.diffusion_test, gb.shape, gb.device
         n = (T - 3) // 4
-        self.model._state_cache = (None, None)
         start_noise, inv_per_t = None, None
         if gb.use_inversion:
             start_noise = diff._randn((B, T, D), device)
             if gb.use_guidance:
                 inv_per_t = torch.zeros(diff.num_timesteps, B, T, D, device=device)
             if gb.jobs:
-                with torch.no_grad():
-                    ex_kwargs = self.model.get_precompute_condition(
-                        device=device, text=gb.ex["retr_text"], audio=gb.ex["retr_audio"],
-                        speaker_ids=gb.ex["retr_spkid"], re_dict=1)
-                ex_kwargs["query_mask"] = gb.ex_query_mask
-                ex_kwargs["motion_mask"] = gb.ex["retr_motion_mask"]
-                inv = diff.ddim_reverse_sample_loop(self.model, start_img=gb.ex["retr_motion_latent"],
-                                                    clip_denoised=False, progress=False,
-                                                    model_kwargs=ex_kwargs, eta=0,
-                                                    return_all_timesteps=True, **gb.extra)
-                inv = torch.stack(inv, 0)                   # [steps, E, T, D], clean -> noisy
+                self.invert_many([gb])
+                inv = gb.inv
                 for e, ((b, _), ((r0, r1), (q0, q1))) in enumerate(zip(gb.jobs, gb.windows)):
                     assert r1 - r0 == q1 - q0
                     for o in (0, n + 1):                    # upper body and hands only (:394-407)
                         start_noise[b, o + q0:o + q1] = inv[gb.inversion_start_time, e, o + r0:o + r1]
                         if gb.use_guidance:
                             inv_per_t[:, b, o + q0:o + q1] = inv[:, e, o + r0:o + r1]
+                if not keep_inversion:
+                    gb.inv = None                           # a GuidedBatch re-run (bench) inverts again
             if gb.use_guidance and gb.use_prev and gb.prev_latent is not None:
                 inv_per_t[:, :, [0, n + 1, 2 * n + 2, 3 * n + 3], :] = 0
         self.model._state_cache = (None, None)
@@ -214,7 +234,7 @@ class MotionDiffusion(nn.Module):
 
 class GuidedBatch:
     """Device-resident inputs of one guided batch between MotionDiffusion.prepare and run_prepared."""
-    jobs, ex, ex_query_mask, windows, outpaint_seq, prev_latent = (), None, None, (), None, None
+    jobs, ex, ex_query_mask, windows, outpaint_seq, prev_latent, inv = (), None, None, (), None, None, None
 
     def clip_steps(self, num_timesteps):
         """Work of the batch in the metric's unit: 50 * (B + E)."""

@@ -1,0 +1,135 @@
+"""Long-form synthesis: the window/chain logic of tools/longform_synthesis.py:258-478 (BASELINE config 5).
+
+A stream of L frames is cut into 150-frame windows with a 15-frame overlap
+(`chunk_starts = [0] + range(135, L, 135)`, last window zero-padded, :263-287); annotations are re-based
+to window time (:348-381); window c is sampled with `use_prev_latent=True, prev_latent=` the output latent
+of window c-1 (:389-404), so SAMPLING is a serial chain ("replicas only") while retrieval and the
+DDIM inversions of all windows do not depend on the chain.  `LongformSynthesizer.run` therefore
+  1. prepares every window (retrieval, exemplar fetch/encode) and inverts ALL windows' exemplars in one
+     batched 50-step loop (`batch_inversions=True`; the reference inverts per window, per exemplar, B=1),
+  2. runs the guided sampling chain window by window,
+  3. cross-fades consecutive windows linearly over the overlap: rotations in 6D space, expressions and
+     translation directly (:431-478).
+BERT / wav2vec feature extraction per window is out of scope: the caller supplies per-window features.
+"""
+import torch
+
+from . import config as CFG
+
+
+def chunk_starts(n_frames, window=CFG.MAX_SEQ_LEN, overlap=15):
+    """[0] + range(window - overlap, n_frames, window - overlap)  (longform_synthesis.py:263)."""
+    return [0] + list(range(window - overlap, n_frames, window - overlap))
+
+
+def rebase_annotations(discourse, prominence, gesture_labels, t0, t1):
+    """Keep the annotations lying inside [t0, t1] seconds and shift them to window time (:348-381)."""
+    disc = [(d[0], d[1], d[2], d[3], d[4] - t0, d[5] - t0, d[6] - t0, d[7] - t0)
+            for d in discourse if d[4] >= t0 and d[5] <= t1]
+    prom = [(p[0], p[1] - t0, p[2] - t0, p[3]) for p in prominence if p[1] >= t0 and p[2] <= t1]
+    gest = [{"start": g["start"] - t0, "end": g["end"] - t0, "name": g["name"], "word": g["word"]}
+            for g in gesture_labels if g["start"] >= t0 and g["end"] <= t1]
+    return disc, prom, gest
+
+
+# ---- rotation helpers for the 6D cross-fade (standard formulas; torch, any device) -----------------------
+def axis_angle_to_matrix(aa):
+    """Rodrigues: [..., 3] -> [..., 3, 3]."""
+    angle = aa.norm(dim=-1, keepdim=True)
+    small = angle < 1e-6
+    axis = aa / torch.where(small, torch.ones_like(angle), angle)
+    x, y, z = axis.unbind(-1)
+    zero = torch.zeros_like(x)
+    K = torch.stack([zero, -z, y, z, zero, -x, -y, x, zero], -1).reshape(aa.shape[:-1] + (3, 3))
+    s, c = torch.sin(angle)[..., None], torch.cos(angle)[..., None]
+    eye = torch.eye(3, dtype=aa.dtype, device=aa.device).expand(K.shape)
+    R = eye + s * K + (1 - c) * (K @ K)
+    return torch.where(small[..., None], eye, R)
+
+
+def matrix_to_rotation_6d(m):
+    return m[..., :2, :].clone().reshape(m.shape[:-2] + (6,))
+
+
+def rotation_6d_to_matrix(d6):
+    a1, a2 = d6[..., :3], d6[..., 3:]
+    b1 = torch.nn.functional.normalize(a1, dim=-1)
+    b2 = torch.nn.functional.normalize(a2 - (b1 * a2).sum(-1, keepdim=True) * b1, dim=-1)
+    return torch.stack((b1, b2, torch.cross(b1, b2, dim=-1)), dim=-2)
+
+
+def matrix_to_axis_angle(R):
+    """[..., 3, 3] -> [..., 3] (angle in [0, pi]); quaternion route for stability near 0 and pi."""
+    m00, m11, m22 = R[..., 0, 0], R[..., 1, 1], R[..., 2, 2]
+    qw = 0.5 * torch.sqrt(torch.clamp(1 + m00 + m11 + m22, min=0))
+    qx = 0.5 * torch.sqrt(torch.clamp(1 + m00 - m11 - m22, min=0)) * torch.sign(R[..., 2, 1] - R[..., 1, 2] + 1e-30)
+    qy = 0.5 * torch.sqrt(torch.clamp(1 - m00 + m11 - m22, min=0)) * torch.sign(R[..., 0, 2] - R[..., 2, 0] + 1e-30)
+    qz = 0.5 * torch.sqrt(torch.clamp(1 - m00 - m11 + m22, min=0)) * torch.sign(R[..., 1, 0] - R[..., 0, 1] + 1e-30)
+    v = torch.stack([qx, qy, qz], -1)
+    n = v.norm(dim=-1, keepdim=True)
+    angle = 2 * torch.atan2(n, qw[..., None])
+    return torch.where(n < 1e-8, torch.zeros_like(v), v / n.clamp_min(1e-30) * angle)
+
+
+def crossfade_rotations(prev_tail, new_head):
+    """Linear blend over the overlap in 6D space (:449-471): [B, F, J*3] axis-angle in and out."""
+    B, F, D = new_head.shape
+    w = torch.linspace(0, 1, F, device=new_head.device, dtype=new_head.dtype).view(1, F, 1)
+    to6 = lambda a: matrix_to_rotation_6d(axis_angle_to_matrix(a.reshape(B, F, D // 3, 3))).reshape(B, F, D // 3 * 6)
+    blended = to6(prev_tail) * (1 - w) + to6(new_head) * w
+    return matrix_to_axis_angle(rotation_6d_to_matrix(blended.reshape(B, F, D // 3, 6))).reshape(B, F, D)
+
+
+def crossfade_linear(prev_tail, new_head):
+    F = new_head.shape[1]
+    w = torch.linspace(0, 1, F, device=new_head.device, dtype=new_head.dtype).view(1, F, 1)
+    return prev_tail * (1 - w) + new_head * w
+
+
+class LongformSynthesizer:
+    """Drives a MotionDiffusion over one stream.  `window_fn(cidx, f0, f1)` returns the batch dict of window
+    cidx (frames [f0, f1), schema of beatx_collate_fn with B=1; per-window audio/text features included)."""
+
+    ROT_KEYS = ("pred_upper", "pred_lower", "pred_hands", "pred_facepose")
+    LIN_KEYS = ("pred_exps", "pred_transl")
+
+    def __init__(self, arch, window=CFG.MAX_SEQ_LEN, overlap=15, fps=CFG.MOTION_FPS):
+        self.arch, self.window, self.overlap, self.fps = arch, window, overlap, fps
+
+    def run(self, n_frames, window_fn, inference_kwargs, batch_inversions=True):
+        starts = chunk_starts(n_frames, self.window, self.overlap)
+        arch = self.arch
+        prepared = []
+        for cidx, f0 in enumerate(starts):
+            batch = dict(window_fn(cidx, f0, f0 + self.window))
+            ik = dict(inference_kwargs, use_prev_latent=True, prev_latent=None)
+            batch["inference_kwargs"] = ik
+            if not batch_inversions:
+                prepared.append(batch)
+                continue
+            gb = arch.prepare(**batch)
+            prepared.append(gb)
+        if batch_inversions:
+            arch.invert_many(prepared)              # one batched reverse loop for every window's exemplars
+        outs, prev, latents = None, None, []
+        for cidx, item in enumerate(prepared):
+            if batch_inversions:
+                item.use_prev, item.prev_latent = True, arch.mask_prev_latent(prev)
+                res = arch.finish(item, arch.run_prepared(item))
+            else:
+                item["inference_kwargs"]["prev_latent"] = prev
+                res = arch(**item)
+            prev = res["prev_latentout"]
+            latents.append(prev)
+            cur = {k: res[k] for k in self.ROT_KEYS + self.LIN_KEYS}
+            if outs is None:
+                outs = cur
+                continue
+            ov = self.overlap
+            for k in cur:
+                fade = crossfade_rotations if k in self.ROT_KEYS else crossfade_linear
+                head = fade(outs[k][:, -ov:], cur[k][:, :ov])
+                outs[k] = torch.cat([outs[k][:, :-ov], head, cur[k][:, ov:]], dim=1)
+        outs["latents"] = torch.cat(latents, 0)
+        outs["window_starts"] = starts
+        return outs

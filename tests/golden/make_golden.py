@@ -313,7 +313,22 @@ def gen_pipeline(ns):
          chain_w0=outs[0], chain_w1=outs[1])
 
 
-GROUPS = {"schedule": gen_schedule, "denoiser": gen_denoiser, "loops": gen_loops,
+def gen_rotation(ns):
+    """6D cross-fade of tools/longform_synthesis.py:449-471 with the reference's rotation_conversions."""
+    import importlib
+    rc = importlib.import_module("mogen.models.utils.rotation_conversions")
+    g = torch.Generator().manual_seed(3)
+    bs, F, J = 2, 15, 7
+    prev = 0.8 * torch.randn(bs, F, J * 3, generator=g)
+    new = 0.8 * torch.randn(bs, F, J * 3, generator=g)
+    to6 = lambda a: rc.matrix_to_rotation_6d(rc.axis_angle_to_matrix(a.reshape(bs, F, J, 3))).reshape(bs, F, J * 6)
+    w = torch.linspace(0, 1, F).unsqueeze(0).unsqueeze(-1)
+    blended = to6(prev) * (1 - w) + to6(new) * w
+    out = rc.matrix_to_axis_angle(rc.rotation_6d_to_matrix(blended.reshape(bs, F, J, 6))).reshape(bs, F, J * 3)
+    save("rotation_crossfade", prev=prev, new=new, out=out, six=to6(prev))
+
+
+GROUPS = {"rotation": gen_rotation, "schedule": gen_schedule, "denoiser": gen_denoiser, "loops": gen_loops,
           "retrieval": gen_retrieval, "pipeline": gen_pipeline}
 
 if __name__ == "__main__":

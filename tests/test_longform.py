@@ -1,0 +1,103 @@
+"""Long-form window/chain logic (BASELINE config 5): CPU tests of the chunking, annotation re-basing and
+the 6D cross-fade (against the reference's rotation_conversions, golden), GPU tests of the batched
+inversion and of a short 3-window stream."""
+import numpy as np
+import pytest
+import torch
+
+from rag_gesture_b200 import config as C
+from rag_gesture_b200 import longform as LF
+from rag_gesture_b200 import synthetic as S
+
+
+def test_chunk_starts_config5():
+    st = LF.chunk_starts(9000)                  # 600 s @ 15 fps
+    assert len(st) == 67 and st[:3] == [0, 135, 270] and st[-1] == 8910
+    assert LF.chunk_starts(150) == [0, 135] and LF.chunk_starts(100) == [0]
+
+
+def test_rebase_annotations():
+    disc = [("and", "s", "a", "b", 1.0, 4.0, 2.0, 2.5), ("but", "s", "a", "b", 8.0, 12.0, 9.5, 10.0),
+            ("so", "s", "a", "b", 10.0, 14.0, 11.0, 11.4)]
+    prom = [("and", 2.0, 2.5, 1.0), ("so", 11.0, 11.4, 2.0)]
+    gest = [{"start": 10.5, "end": 12.0, "name": "beat", "word": "so"}]
+    d, p, g = LF.rebase_annotations(disc, prom, gest, 9.0, 19.0)
+    assert d == [("so", "s", "a", "b", 1.0, 5.0, 2.0, pytest.approx(2.4))]
+    assert p == [("so", 2.0, pytest.approx(2.4), 2.0)] and g[0]["start"] == 1.5
+
+
+def test_crossfade_matches_reference(golden):
+    g = golden("rotation_crossfade")
+    prev, new = torch.from_numpy(g["prev"]), torch.from_numpy(g["new"])
+    six = LF.matrix_to_rotation_6d(LF.axis_angle_to_matrix(prev.reshape(2, 15, 7, 3))).reshape(2, 15, 42)
+    assert torch.allclose(six, torch.from_numpy(g["six"]), atol=1e-5)
+    out = LF.crossfade_rotations(prev, new)
+    # compare as rotations (axis-angle is 2*pi periodic): back to matrices
+    R1 = LF.axis_angle_to_matrix(out.reshape(2, 15, 7, 3))
+    R2 = LF.axis_angle_to_matrix(torch.from_numpy(g["out"]).reshape(2, 15, 7, 3))
+    assert torch.allclose(R1, R2, atol=2e-5)
+    lin = LF.crossfade_linear(prev, new)
+    assert torch.equal(lin[:, 0], prev[:, 0]) and torch.equal(lin[:, -1], new[:, -1])
+
+
+@pytest.fixture(scope="module")
+def arch():
+    import rag_gesture_b200 as R
+    assert torch.cuda.is_available()
+    cfg = C.model_cfg()
+    cfg["use_retrieval_for_test"] = True
+    m = R.build_architecture(cfg, database=S.SyntheticGestureDataset(1200, seed=7))
+    m.model.load_state_dict(S.synthetic_state_dict(0), strict=False)
+    return m.to("cuda:0").eval()
+
+
+def _window_fn(qs):
+    def fn(cidx, f0, f1):
+        b = S.collate([qs[3 + cidx]])
+        b["retrieval_method"] = "discourse"
+        return b
+    return fn
+
+
+IK = dict(use_inversion=True, insertion_guidance=True, guidance_iters=[0] * 25 + list(range(25)), guidance_lr=0.1)
+
+
+@pytest.mark.gpu
+def test_batched_inversion_equals_per_window(arch):
+    qs = S.SyntheticGestureDataset(48, seed=8)
+    fn = _window_fn(qs)
+    invs = []
+    for mode in ("together", "separate"):
+        torch.manual_seed(11)
+        for d in (arch.model.database.test_indexes, arch.model.database.test_dbounds, arch.model.database.test_qbounds):
+            d.clear()
+        gbs = [arch.prepare(**dict(fn(c, 0, 150), inference_kwargs=dict(IK, use_prev_latent=True, prev_latent=None)))
+               for c in range(3)]
+        if mode == "together":
+            arch.invert_many(gbs)
+        else:
+            for gb in gbs:
+                arch.invert_many([gb])
+        invs.append([gb.inv for gb in gbs])
+    assert sum(len(g.jobs) for g in gbs) >= 2
+    for a, b in zip(*invs):
+        assert (a is None and b is None) or torch.equal(a, b)
+
+
+@pytest.mark.gpu
+def test_three_window_stream(arch):
+    qs = S.SyntheticGestureDataset(48, seed=8)
+    torch.manual_seed(5)
+    out = LF.LongformSynthesizer(arch).run(150 + 2 * 135, _window_fn(qs), IK, batch_inversions=True)
+    assert out["window_starts"] == [0, 135, 270, 405][:len(out["window_starts"])]
+    n_win = len(out["window_starts"])
+    assert tuple(out["latents"].shape) == (n_win, 43, 512)
+    frames = 150 + (n_win - 1) * 135
+    assert tuple(out["pred_upper"].shape) == (1, frames, 39) and tuple(out["pred_exps"].shape) == (1, frames, 100)
+    assert all(bool(torch.isfinite(out[k]).all()) for k in ("pred_upper", "pred_hands", "pred_transl", "latents"))
+    # the sequential mode (reference order of operations) runs too and chains the latents
+    for d in (arch.model.database.test_indexes, arch.model.database.test_dbounds, arch.model.database.test_qbounds):
+        d.clear()
+    torch.manual_seed(5)
+    out2 = LF.LongformSynthesizer(arch).run(150 + 2 * 135, _window_fn(qs), IK, batch_inversions=False)
+    assert tuple(out2["latents"].shape) == tuple(out["latents"].shape)
