@@ -331,9 +331,19 @@ def knn_bench(args, dev, rank, world, hbm_peak, peak_src, flush):
         out[f"q{Q}"] = {"queries_per_sec": round(Q / t, 1), "ms": round(t * 1e3, 3), "hbm_gbs": round(gbs, 1),
                         "frac_hbm": round(gbs / hbm_peak, 4)}
     head = out["q8"]
+    # the scan kernel alone (what the HBM roofline is about): CUDA events around the launch only
+    import ctypes
+    from rag_gesture_b200 import _lib
+    q8 = torch.nn.functional.normalize(torch.randn(8, dim, device=dev), dim=1)
+    ms = ctypes.c_float()
+    _lib.check(_lib.load().rg_probe_knn_scan(_lib.ptr(db), hi - lo, dim, _lib.ptr(q8), 8, k, 5, _lib.ptr(flush),
+                                             flush.numel(), ctypes.byref(ms), _lib.stream_ptr()))
+    head = dict(head, hbm_gbs=round((hi - lo) * dim * 4 / (ms.value / 1e3) / 1e9, 1), scan_ms=round(ms.value, 3))
+    head["frac_hbm"] = round(head["hbm_gbs"] / hbm_peak, 4)
     return {"queries_per_sec": head["queries_per_sec"], "n": n_total, "dim": dim, "k": k, "q": 8, "ms": head["ms"],
             "sweep": out,
-            "roofline": {"bound": "hbm", "kernel": "knn_scan768_kernel<8> (exact fp32, 1 pass over the shard)",
+            "roofline": {"bound": "hbm", "kernel": "knn_scan768_kernel<8> alone (exact fp32, 8 queries, 1 pass over the shard)",
+                         "launch_ms": head["scan_ms"],
                          "achieved": head["hbm_gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": head["frac_hbm"],
                          "peak_source": peak_src, "bytes_per_launch": (hi - lo) * dim * 4}}
 

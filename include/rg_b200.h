@@ -178,6 +178,10 @@ int rg_text_similarity(const float* db, const int32_t* db_len, int64_t n, int ma
  * (score desc, index asc) -- the order of Python's stable sorted(..., reverse=True). */
 int rg_knn_topk(const float* db, int64_t n, int dim, const float* queries, int q, int k,
                 int64_t idx_base, int64_t* out_idx, float* out_score, void* stream);
+/* Measurement probe for bench.py's roofline: like rg_knn_topk for q <= 8 queries, but times ONLY the scan
+ * kernel (`reps` launches, CUDA events on `stream`, flush_buf overwritten before each) -> *median_ms. */
+int rg_probe_knn_scan(const float* db, int64_t n, int dim, const float* queries, int q, int k, int reps,
+                      void* flush_buf, int64_t flush_bytes, float* median_ms, void* stream);
 /* Merge `parts` per-shard candidate lists [parts,q,k] (as all-gathered) into the global top-k. */
 int rg_knn_merge(const int64_t* idx_parts, const float* score_parts, int parts, int q, int k,
                  int64_t* out_idx, float* out_score, void* stream);

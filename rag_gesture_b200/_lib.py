@@ -45,6 +45,7 @@ SIGNATURES = {
     "rg_op_kv_state": (_I, [_P, _I, _I, _P, _P]),
     "rg_text_similarity": (_I, [_P, _P, _L, _I, _I, _P, _I, _P, _L, _P, _P]),
     "rg_knn_topk": (_I, [_P, _L, _I, _P, _I, _I, _L, _P, _P, _P]),
+    "rg_probe_knn_scan": (_I, [_P, _L, _I, _P, _I, _I, _I, _P, _L, C.POINTER(C.c_float), _P]),
     "rg_knn_merge": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
 }
 

@@ -704,6 +704,7 @@ extern "C" int rg_op_linear_tc(const float* x, const float* W, const float* b, c
     p.M = M; p.N = N; p.K = K; p.split = split ? 1 : 0; p.a_lo_off = K; p.w_lo_off = K; p.groups = 1;
     p.bias = b; p.R = residual; p.ldr = N; p.C32 = out; p.ldc32 = N;
     p.C16_ = out_bf16; p.ldc16 = N * planes; p.c16_lo_off = split ? N : 0; p.epi = epi;
+    p.no_pdl = 1;       // W planes were written by the split kernel just above
     LAUNCH(rg_launch_gemm_tc(tmA, tmW, p, st));
     CU(cudaFreeAsync(a16, st));
     CU(cudaFreeAsync(w16, st));

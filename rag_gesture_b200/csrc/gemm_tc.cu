@@ -134,18 +134,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_smem;
-    rg_pdl_wait();      // barriers, TMEM and descriptors are set up; operands of the previous kernel from here on
 
     if (warp == 0) {
         // ===== TMA producer =====
         if (elect_one()) {
             const int a_k0 = g * p.a_goff, w_n0 = g * p.w_goff + n0;
-            for (int j = 0; j < total_kb; ++j) {
+            auto coords = [&](int j, int& ka, int& kw) {
+                const int pass = j / nkb, kb = j - pass * nkb;          // pass 0: hi*hi, 1: lo*hi, 2: hi*lo
+                ka = a_k0 + (pass == 1 ? p.a_lo_off : 0) + kb * BK;
+                kw = (pass == 2 ? p.w_lo_off : 0) + kb * BK;
+            };
+            // The weight operand does not depend on the previous kernel: its first STAGES tiles are
+            // requested BEFORE griddepcontrol.wait, so under PDL they stream in while the producer of
+            // our A operand is still finishing.  The activation tiles follow once it has completed.
+            const int pre = total_kb < STAGES ? total_kb : STAGES;
+            for (int j = 0; j < pre; ++j) {
+                int ka, kw;
+                coords(j, ka, kw);
+                mbar_expect_tx(smem_u32(&full_bar[j]), STAGE_BYTES);
+                tma_load_2d(smem_u32(smem + j * STAGE_BYTES) + A_BYTES, &tmW, smem_u32(&full_bar[j]), kw, w_n0);
+            }
+            rg_pdl_wait();
+            for (int j = 0; j < pre; ++j) {
+                int ka, kw;
+                coords(j, ka, kw);
+                tma_load_2d(smem_u32(smem + j * STAGE_BYTES), &tmA, smem_u32(&full_bar[j]), ka, m0);
+            }
+            for (int j = pre; j < total_kb; ++j) {
                 const int s = j % STAGES, ph = (j / STAGES) & 1;
                 mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
-                const int pass = j / nkb, kb = j - pass * nkb;          // pass 0: hi*hi, 1: lo*hi, 2: hi*lo
-                const int ka = a_k0 + (pass == 1 ? p.a_lo_off : 0) + kb * BK;
-                const int kw = (pass == 2 ? p.w_lo_off : 0) + kb * BK;
+                int ka, kw;
+                coords(j, ka, kw);
                 const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
                 mbar_expect_tx(smem_u32(&full_bar[s]), STAGE_BYTES);
                 tma_load_2d(sa, &tmA, smem_u32(&full_bar[s]), ka, m0);
@@ -177,6 +196,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ring is idle once tmem_full fires, so each warp parks its 32 x BN quadrant there
         // (row pitch BN+4 floats: conflict-free 128-bit accesses both ways) and then walks it row by
         // row with lanes along N: bias / residual / pos loads and all stores are 512 B contiguous.
+        rg_pdl_wait();          // residual reads and all stores below touch buffers of the previous kernel
         mbar_wait(smem_u32(&tmem_full_bar), 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int lg = warp & 3;                                        // TMEM lane group of this warp
@@ -329,6 +349,11 @@ cudaError_t rg_launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmW, co
     }
     dim3 grid(p.N / BN, (p.M + BM - 1) / BM, p.groups > 0 ? p.groups : 1);
     const long long ctas = (long long)grid.x * grid.y * grid.z;
+    if (p.no_pdl) {     // weight tiles are prefetched before griddepcontrol.wait: only valid for constant W
+        if (ctas <= 148) gemm_tc_kernel<BN, 6><<<grid, 192, smem6, st>>>(tmA, tmW, p);
+        else gemm_tc_kernel<BN, 3><<<grid, 192, smem3, st>>>(tmA, tmW, p);
+        return cudaGetLastError();
+    }
     if (ctas <= 148)
         return rg_launch_pdl(gemm_tc_kernel<BN, 6>, grid, dim3(192), smem6, st, tmA, tmW, p);
     return rg_launch_pdl(gemm_tc_kernel<BN, 3>, grid, dim3(192), smem3, st, tmA, tmW, p);

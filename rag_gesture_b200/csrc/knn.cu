@@ -8,6 +8,8 @@
 //    Python's stable sorted(..., reverse=True) / torch sort(descending, stable) tie order.
 //  * rg_knn_merge: merges per-shard candidate lists after the NCCL all-gather (K11).
 #include <math.h>
+#include <algorithm>
+#include <vector>
 #include "../../include/rg_b200.h"
 #include "rg_common.cuh"
 #include "rg_internal.h"
@@ -372,5 +374,41 @@ extern "C" int rg_knn_topk(const float* db, int64_t n, int dim, const float* que
     rg_count_launch(1);
     RG_CU(cudaFreeAsync(part_idx, st));
     RG_CU(cudaFreeAsync(part_score, st));
+    return 0;
+}
+
+extern "C" int rg_probe_knn_scan(const float* db, int64_t n, int dim, const float* queries, int q, int k, int reps,
+                                 void* flush_buf, int64_t flush_bytes, float* median_ms, void* stream) {
+    if (dim != 768 || q < 1 || q > 8 || k < 1 || k > 32 || reps < 1 || reps > 64)
+        return rg_fail("rg_probe_knn_scan: needs dim 768, 1 <= q <= 8, 1 <= k <= 32");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int blocks = 148;
+    const long long rows_per_block = (n + blocks - 1) / blocks;
+    long long* part_idx = nullptr;
+    float* part_score = nullptr;
+    RG_CU(cudaMalloc((void**)&part_idx, (size_t)blocks * q * k * sizeof(long long)));
+    RG_CU(cudaMalloc((void**)&part_score, (size_t)blocks * q * k * sizeof(float)));
+    cudaEvent_t e0, e1;
+    RG_CU(cudaEventCreate(&e0));
+    RG_CU(cudaEventCreate(&e1));
+    std::vector<float> ts;
+    for (int i = 0; i < reps + 2; ++i) {
+        if (flush_buf) RG_CU(cudaMemsetAsync(flush_buf, i, (size_t)flush_bytes, st));
+        RG_CU(cudaEventRecord(e0, st));
+        if (q >= 5) RG_CU(launch_scan768<8>(db, n, queries, q, 0, k, blocks, rows_per_block, part_idx, part_score, st));
+        else if (q >= 3) RG_CU(launch_scan768<4>(db, n, queries, q, 0, k, blocks, rows_per_block, part_idx, part_score, st));
+        else if (q == 2) RG_CU(launch_scan768<2>(db, n, queries, q, 0, k, blocks, rows_per_block, part_idx, part_score, st));
+        else RG_CU(launch_scan768<1>(db, n, queries, q, 0, k, blocks, rows_per_block, part_idx, part_score, st));
+        rg_count_launch(1);
+        RG_CU(cudaEventRecord(e1, st));
+        RG_CU(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        RG_CU(cudaEventElapsedTime(&ms, e0, e1));
+        if (i >= 2) ts.push_back(ms);
+    }
+    std::sort(ts.begin(), ts.end());
+    *median_ms = ts[ts.size() / 2];
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(part_idx); cudaFree(part_score);
     return 0;
 }

@@ -16,6 +16,7 @@ struct RgGemmTc {
     void* C16_; int ldc16;    // optional bf16 output (+ lo plane at column c16_lo_off when non-zero)
     int c16_lo_off;
     int epi;                  // RgEpilogue
+    int no_pdl;               // 1: W was produced by the preceding kernel -> plain (fully serialised) launch
 };
 
 cudaError_t rg_make_tensor_map(CUtensorMap* tm, const void* ptr, long long rows, long long cols, long long ld,
