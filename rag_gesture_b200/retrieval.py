@@ -138,39 +138,53 @@ def discourse_retrieval(text, discourse, prominence, speaker_id, db_idx_2_sense,
             assert cv[0] == _clean(conns[i]), f"{cv[0]} != {_clean(conns[i])}"
             q_prom[i] = (senses[i], cv[1])
 
+    import numpy as np
     for qi, (sense, conn) in enumerate(zip(senses, conns)):
-        scored, bounds_of = [], {}
         if sense_tables is not None:
-            # vectorised scoring (same float64 operations in the same order as the loop below)
+            # vectorised scoring (same float64 operations in the same order as _score_loop)
             tabs, conn_ids = sense_tables
             if sense not in tabs:
                 tabs[sense] = SenseTable(sense, sense_index.get(sense, []), db_idx_2_sense, db_idx_2_prominence, conn_ids)
             tab = tabs[sense]
-            if len(tab.names):
+            names = tab.names
+            if len(names):
                 sc, top = tab.score(conn_ids.get(conn), speaker_id, None if q_prom[qi] is None else float(q_prom[qi][1]))
-                scored = list(zip(tab.names, sc.tolist()))
-                bounds_of = {n: db_idx_2_discbounds[n][t] for n, t in zip(tab.names, top.tolist())}
+            else:
+                sc, top = np.zeros(0), np.zeros(0, dtype=np.int64)
+            bound_of = lambda i: db_idx_2_discbounds[names[i]][int(top[i])]
         else:
             scored, bounds_of = _score_loop(sense, conn, qi, q_prom, speaker_id, sense_index, db_idx_2_sense,
                                             db_idx_2_discbounds, db_idx_2_prominence)
-        # equal-score tiers, best first; a tier with several members is ordered by text similarity
-        tiers = {}
-        for name, score in sorted(scored, key=lambda t: t[1], reverse=True):
-            tiers.setdefault(score, []).append(name)
-        ranked = []
-        for score in sorted(tiers, reverse=True):
-            tier = tiers[score]
+            names = [n for n, _ in scored]
+            sc = np.array([v for _, v in scored], dtype=np.float64)
+            bound_of = lambda i: bounds_of[names[i]]
+        # equal-score tiers, best first (stable: DB order inside a tier); a tier with several members is
+        # ordered by text similarity; stop once 10 are collected (rag/discourse_retrieval.py:215-246)
+        order = np.argsort(-sc, kind="stable")
+        ranked, pos = [], 0
+        while pos < len(order) and len(ranked) < 10:
+            end_ = pos + 1
+            while end_ < len(order) and sc[order[end_]] == sc[order[pos]]:
+                end_ += 1
+            tier = order[pos:end_].tolist()
             if len(tier) > 1:
-                tier = [index.names[r] for r in index.rank(encoded_text, [index.row[n] for n in tier], len(tier))] \
-                    if len(tier) <= 32 else _rank_long_tier(index, encoded_text, tier)
+                rows = [index.row[names[i]] for i in tier]
+                back = {r: i for r, i in zip(rows, tier)}
+                if len(tier) <= 32:
+                    tier = [back[r] for r in index.rank(encoded_text, rows, len(tier))]
+                else:
+                    # only the first 32 by similarity can reach the top 10; the rest keep tier order
+                    head = index.rank(encoded_text, rows, 32)
+                    hs = set(head)
+                    tier = [back[r] for r in head] + [i for r, i in zip(rows, tier) if r not in hs]
             ranked += tier
-            if len(ranked) >= 10:
-                break
-        sample_indexes[qi] = ranked[:10]
+            pos = end_
+        ranked = ranked[:10]
+        sample_indexes[qi] = [names[i] for i in ranked]
         d_bounds[qi] = {}
-        for name in ranked[:10]:
-            b = bounds_of[name]
-            d_bounds[qi][name] = (b[1], b[0], round(b[4], 3), round(b[5], 3))
+        for i in ranked:
+            b = bound_of(i)
+            d_bounds[qi][names[i]] = (b[1], b[0], round(b[4], 3), round(b[5], 3))
     assert len(d_bounds) == len(sample_indexes) == len(query_bounds)
     return sample_indexes, d_bounds, query_bounds
 
@@ -277,15 +291,6 @@ class SenseTable:
         move = withp & ~chosen & (best_j != top)
         top[move] = best_j[move]
         return score, top
-
-
-def _rank_long_tier(index, query, tier):
-    """Tiers longer than the kernel's k<=32: only the first 32 by similarity can reach the top 10,
-    the rest keep tier order behind them (they are cut off by [:10] in the caller anyway)."""
-    rows = [index.row[n] for n in tier]
-    head = index.rank(query, rows, 32)
-    head_set = set(head)
-    return [index.names[r] for r in head] + [n for n in tier if index.row[n] not in head_set]
 
 
 def build_sense_index(db_idx_2_sense):

@@ -186,7 +186,9 @@ def test_guided_loop_and_dead_guidance(model, diffusion, golden, dev):
             guidance_iters=[0] * 25 + list(range(25)), inverted_latent_list=inv_list, guidance_lr=0.1).cpu())
     diffusion.noise_fn, diffusion.skip_dead_guidance = None, True
     assert torch.equal(finals[0], finals[1])            # executing the gradient steps changes nothing
-    assert rel_l2(finals[0], torch.from_numpy(gg["final"])) < 2e-3
+    err = rel_l2(finals[0], torch.from_numpy(gg["final"]))
+    print(f"guided loop (fp32 tier) rel-L2 vs reference: {err:.3g}")
+    assert err < TOL_LOOP
 
     # long-form mode: prev_latent blended on every step of the plain loop
     prev = torch.zeros(1, T, D)

@@ -142,9 +142,11 @@ def test_full_guided_batch_vs_reference(arch, dev):
     res = arch(**batch)
     n_ex = sum(len(x) for x in res["retrieval_dict"]["retr_startends"])
     assert n_ex == int(g["n_exemplars"]) and n_ex > 0
-    assert rel_l2(res["prev_latentout"].cpu(), torch.from_numpy(g["prev_latentout"])) < 2e-3
-    assert rel_l2(res["pred_upper"][:, ::10].cpu(), torch.from_numpy(g["pred_upper"])) < 2e-3
-    assert rel_l2(res["pred_hands"][:, ::10].cpu(), torch.from_numpy(g["pred_hands"])) < 2e-3
+    errs = (rel_l2(res["prev_latentout"].cpu(), torch.from_numpy(g["prev_latentout"])),
+            rel_l2(res["pred_upper"][:, ::10].cpu(), torch.from_numpy(g["pred_upper"])),
+            rel_l2(res["pred_hands"][:, ::10].cpu(), torch.from_numpy(g["pred_hands"])))
+    print("full guided batch (fp32 tier) rel-L2 vs reference: latents %.3g, upper %.3g, hands %.3g" % errs)
+    assert max(errs) < 1e-3          # north_star fp32 tier
     assert tuple(res["pred_lower"].shape) == (3, 150, 27) and tuple(res["pred_exps"].shape) == (3, 150, 100)
 
 
@@ -163,5 +165,6 @@ def test_longform_prev_latent_chain(arch, dev):
                                       use_prev_latent=True, prev_latent=prev)
         prev = arch(**bw)["prev_latentout"]
         outs.append(prev.cpu())
-    assert rel_l2(outs[0], torch.from_numpy(g["chain_w0"])) < 2e-3
-    assert rel_l2(outs[1], torch.from_numpy(g["chain_w1"])) < 2e-3
+    errs = (rel_l2(outs[0], torch.from_numpy(g["chain_w0"])), rel_l2(outs[1], torch.from_numpy(g["chain_w1"])))
+    print("prev-latent chain (fp32 tier) rel-L2 vs reference: window 0 %.3g, window 1 %.3g" % errs)
+    assert max(errs) < 1e-3
