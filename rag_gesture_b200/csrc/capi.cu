@@ -67,7 +67,7 @@ struct W16 {                 // bf16 operand planes [N, planes*K] (hi | lo) + it
     CUtensorMap tm;
     int N, K;
 };
-struct LayerTc { W16 qkv, sa_o, caq, ca_o, mix, w1, w2, ffn_o; };
+struct LayerTc { W16 qkv, sa_o, caq, fold, w1, w2, ffn_o; float* b_fold; };
 
 struct rg_model {
     rg_config cfg;
@@ -76,8 +76,8 @@ struct rg_model {
     std::vector<LayerTc> tc;
     W16 tc_joint, tc_out, tc_kv[3];
     void* kv_a16;
-    void *x16, *a16, *a16w, *o16, *h16, *g16;
-    CUtensorMap tm_x16, tm_a16, tm_a16w, tm_o16, tm_h16, tm_g16;
+    void *x16, *a16, *a16x, *h16, *g16;
+    CUtensorMap tm_x16, tm_a16, tm_a16x, tm_h16, tm_g16;
     int device;
     std::vector<void*> allocs;
     std::vector<Layer> layers;
@@ -160,6 +160,31 @@ static int make_w16(rg_model* m, const float* W, int N, int K, W16* out) {
     return 0;
 }
 
+// ca_mix(cat_c(h + proj_c(s_c))) == W_f [s_text | s_audio | s_spk | h] + b_f  with
+//   W_f[:, c] = Wmix[:, c] Wo_c,  W_f[:, 3] = sum_c Wmix[:, c],  b_f = bmix + sum_c Wmix[:, c] bo_c
+// (diffusion_transformer.py:115-122 + stylization_block.py:39): the three projections and the mix become
+// ONE K = 2048 contraction on the tensor-core tiers.  Folded once, in fp32, at model creation.
+static int make_fold(rg_model* m, const Layer& ly, LayerTc* t) {
+    const int D = RG_D;
+    float *Wf = nullptr, *WoT = nullptr;
+    if (dalloc(m, (void**)&Wf, (size_t)D * 4 * D * sizeof(float))) return 1;
+    if (dalloc(m, (void**)&WoT, (size_t)D * D * sizeof(float))) return 1;
+    if (dalloc(m, (void**)&t->b_fold, (size_t)D * sizeof(float))) return 1;
+    for (int c = 0; c < 3; ++c) {
+        CU(rg_launch_transpose_sq(ly.ca_Wo + (long long)c * D * D, WoT, D, 0));
+        RgGemm g = mk_gemm(ly.Wmix + c * D, 3 * D, WoT, nullptr, Wf + c * D, 4 * D, D, D, D, RG_EPI_BIAS);
+        CU(rg_launch_gemm_f32(g, 0));
+        g_launches += 2;
+    }
+    CU(rg_launch_sum3_blocks(ly.Wmix, 3 * D, Wf + 3 * D, 4 * D, D, D, 0));
+    CU(rg_launch_gemm_f32(mk_gemm(ly.ca_bo, 3 * D, ly.Wmix, ly.bmix, t->b_fold, D, 1, D, 3 * D, RG_EPI_BIAS), 0));
+    g_launches += 2;
+    if (make_w16(m, Wf, D, 4 * D, &t->fold)) return 1;
+    CU(cudaStreamSynchronize(0));
+    dfree_one(m, Wf); dfree_one(m, WoT);
+    return 0;
+}
+
 extern "C" const char* rg_last_error(void) { return g_err; }
 extern "C" int rg_abi_version(void) { return RG_ABI_VERSION; }
 extern "C" int64_t rg_launch_count(void) { return g_launches; }
@@ -198,7 +223,7 @@ extern "C" int rg_create(const rg_config* cfg, int n_tensors, const char* const*
     m->kv_rows = 0; m->kv_ln = m->kv_buf = nullptr;
     m->tt_rows = 0; m->tt_emb = m->tt_t1 = m->tt_e = nullptr;
     m->planes = cfg->precision == RG_PREC_BF16X3 ? 2 : 1;
-    m->x16 = m->a16 = m->a16w = m->o16 = m->h16 = m->g16 = nullptr; m->kv_a16 = nullptr;
+    m->x16 = m->a16 = m->a16x = m->h16 = m->g16 = nullptr; m->kv_a16 = nullptr;
     const int D = RG_D, E = cfg->time_embed_dim, F = cfg->ffn_dim, L = cfg->num_layers, T = cfg->n_tokens;
     const long long DD = (long long)D * D;
     cudaStream_t st = 0;
@@ -326,8 +351,7 @@ extern "C" int rg_create(const rg_config* cfg, int n_tensors, const char* const*
             TRY(make_w16(m, ly.Wqkv, 3 * D, D, &t.qkv));
             TRY(make_w16(m, ly.sa_Wo, D, D, &t.sa_o));
             TRY(make_w16(m, ly.Wcaq, 3 * D, D, &t.caq));
-            TRY(make_w16(m, ly.ca_Wo, 3 * D, D, &t.ca_o));      // 3 stacked [512,512] blocks
-            TRY(make_w16(m, ly.Wmix, D, 3 * D, &t.mix));
+            TRY(make_fold(m, ly, &t));
             TRY(make_w16(m, ly.W1, F, D, &t.w1));
             TRY(make_w16(m, ly.W2, D, F, &t.w2));
             TRY(make_w16(m, ly.ffn_Wo, D, D, &t.ffn_o));
@@ -407,10 +431,10 @@ static int ensure_ws(rg_model* m, long long rows) {
     if (dalloc(m, (void**)&m->y, (size_t)rows * D * sizeof(float))) return 1;
     if (m->cfg.precision != RG_PREC_FP32) {
         const int P = m->planes;
-        void** b16[6] = {&m->x16, &m->a16, &m->a16w, &m->o16, &m->h16, &m->g16};
-        const int width[6] = {D, D, 3 * D, 3 * D, D, F};
-        CUtensorMap* tms[6] = {&m->tm_x16, &m->tm_a16, &m->tm_a16w, &m->tm_o16, &m->tm_h16, &m->tm_g16};
-        for (int i = 0; i < 6; ++i) {
+        void** b16[5] = {&m->x16, &m->a16, &m->a16x, &m->h16, &m->g16};
+        const int width[5] = {D, D, 4 * D, D, F};
+        CUtensorMap* tms[5] = {&m->tm_x16, &m->tm_a16, &m->tm_a16x, &m->tm_h16, &m->tm_g16};
+        for (int i = 0; i < 5; ++i) {
             dfree_one(m, *b16[i]); *b16[i] = nullptr;
             if (dalloc(m, b16[i], (size_t)rows * width[i] * P * 2)) return 1;
             CU(cudaMemset(*b16[i], 0, (size_t)rows * width[i] * P * 2));
@@ -531,18 +555,25 @@ static int denoise_tc(rg_model* m, const float* x, int B, const float* ssrow, co
         RgStylParams sp = {ly.sa_g, ly.sa_b, ss, 0};
         LAUNCH(rg_launch_sa_core(m->big, src_mask, m->y, B, T, st));
         LAUNCH(rg_launch_styl_rows(m->y, D, sp, T, rg_out_b16(m->a16, D * P, lo ? D : 0), M, st));
-        if (tc_gemm(m, m->tm_a16, D, t.sa_o, ly.sa_bo, M, D, D, RG_EPI_BIAS_RESIDUAL, m->h, m->h, D, nullptr, 0, st)) return 1;
-        // --- three cross-attentions on the same h
+        // h1 = h + proj(...): fp32 residual stream + its bf16 planes as the 4th K-block of the folded ca GEMM
+        {
+            RgGemmTc p;
+            memset(&p, 0, sizeof(p));
+            p.M = M; p.N = D; p.K = D; p.split = lo; p.a_lo_off = D; p.w_lo_off = D; p.groups = 1;
+            p.bias = ly.sa_bo; p.R = m->h; p.ldr = D; p.C32 = m->h; p.ldc32 = D;
+            p.C16_ = reinterpret_cast<__nv_bfloat16*>(m->a16x) + 3 * D; p.ldc16 = 4 * D * P; p.c16_lo_off = lo ? 4 * D : 0;
+            p.epi = RG_EPI_BIAS_RESIDUAL;
+            LAUNCH(rg_launch_gemm_tc(m->tm_a16, t.sa_o.tm, p, st));
+        }
+        // --- three cross-attentions on the same h, their projections and ca_mix folded into one GEMM
         LAUNCH(rg_launch_ln_rows(m->h, D, nullptr, nullptr, rg_out_b16(m->a16, D * P, lo ? D : 0), M, st));
         if (tc_gemm(m, m->tm_a16, D, t.caq, ly.bcaq, M, 3 * D, D, RG_EPI_BIAS, nullptr, m->big, 3 * D, nullptr, 0, st)) return 1;
         RgStylParams sp3[3];
         for (int c = 0; c < 3; ++c) sp3[c] = {ly.ca_g + c * D, ly.ca_b + c * D, ss + (1 + c) * 2 * D, 0};
         LAUNCH(rg_launch_ca_core(m->big, 3 * D, state + (long long)l * 3 * HS, clip_stride, HS, query_mask,
                                  (long long)B * T, m->o3, 3 * D, B, T, st));
-        LAUNCH(rg_launch_styl_rows3(m->o3, 3 * D, sp3, T, rg_out_b16(m->a16w, 3 * D * P, lo ? 3 * D : 0), M, st));
-        if (tc_gemm(m, m->tm_a16w, 3 * D, t.ca_o, ly.ca_bo, M, D, D, RG_EPI_BIAS_RESIDUAL, m->h, nullptr, 0, m->o16,
-                    3 * D, st, 3, D, D, D)) return 1;
-        if (tc_gemm(m, m->tm_o16, 3 * D, t.mix, ly.bmix, M, D, 3 * D, RG_EPI_BIAS, nullptr, m->h, D, m->h16, D, st)) return 1;
+        LAUNCH(rg_launch_styl_rows3(m->o3, 3 * D, sp3, T, rg_out_b16(m->a16x, 4 * D * P, lo ? 4 * D : 0), M, st));
+        if (tc_gemm(m, m->tm_a16x, 4 * D, t.fold, t.b_fold, M, D, 4 * D, RG_EPI_BIAS, nullptr, m->h, D, m->h16, D, st)) return 1;
         // --- FFN
         if (tc_gemm(m, m->tm_h16, D, t.w1, ly.b1, M, F, D, RG_EPI_BIAS_GELU, nullptr, nullptr, 0, m->g16, F, st)) return 1;
         if (tc_gemm(m, m->tm_g16, F, t.w2, ly.b2, M, D, F, RG_EPI_BIAS, nullptr, m->y, D, nullptr, 0, st)) return 1;

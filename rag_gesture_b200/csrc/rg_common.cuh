@@ -74,6 +74,8 @@ cudaError_t rg_launch_blend(const float* x, const float* in_seq, const float* no
                             long long rows, float s_ab, float s_1mab, cudaStream_t st);
 cudaError_t rg_launch_guidance(float* x, const float* in_seq, long long rows, int iters,
                                float lr_2_over_n, cudaStream_t st);
+cudaError_t rg_launch_transpose_sq(const float* in, float* out, int n, cudaStream_t st);
+cudaError_t rg_launch_sum3_blocks(const float* a, int lda, float* out, int ldo, int n, int rows, cudaStream_t st);
 cudaError_t rg_launch_pos_table(const float* seq_pe, const float* glob_pe, float* pos, int T,
                                 int n_chunks, cudaStream_t st);
 

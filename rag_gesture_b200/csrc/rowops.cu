@@ -181,6 +181,22 @@ __global__ void pos_table_kernel(const float* __restrict__ seq_pe, const float* 
     }
 }
 
+// out[c][r] = in[r][c] for an n x n fp32 matrix (weight folding at model creation)
+__global__ void transpose_sq_kernel(const float* __restrict__ in, float* __restrict__ out, int n) {
+    __shared__ float t[32][33];
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) t[i][threadIdx.x] = in[(long long)(by + i) * n + bx + threadIdx.x];
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) out[(long long)(bx + i) * n + by + threadIdx.x] = t[threadIdx.x][i];
+}
+
+// out[r][c] = a[r][c] + a[r][c + n] + a[r][c + 2n]   (sum of the three column blocks of ca_mix.weight)
+__global__ void sum3_blocks_kernel(const float* __restrict__ a, int lda, float* __restrict__ out, int ldo, int n) {
+    const int r = blockIdx.x;
+    for (int c = threadIdx.x; c < n; c += blockDim.x)
+        out[(long long)r * ldo + c] = a[(long long)r * lda + c] + a[(long long)r * lda + n + c] + a[(long long)r * lda + 2 * n + c];
+}
+
 inline int row_blocks(long long rows) { return (int)((rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK); }
 
 }  // namespace
@@ -237,5 +253,15 @@ cudaError_t rg_launch_guidance(float* x, const float* in_seq, long long rows, in
 cudaError_t rg_launch_pos_table(const float* seq_pe, const float* glob_pe, float* pos, int T,
                                 int n_chunks, cudaStream_t st) {
     pos_table_kernel<<<T, 128, 0, st>>>(seq_pe, glob_pe, pos, T, n_chunks);
+    return cudaGetLastError();
+}
+
+cudaError_t rg_launch_transpose_sq(const float* in, float* out, int n, cudaStream_t st) {
+    if (n % 32) return cudaErrorInvalidValue;
+    transpose_sq_kernel<<<dim3(n / 32, n / 32), dim3(32, 8), 0, st>>>(in, out, n);
+    return cudaGetLastError();
+}
+cudaError_t rg_launch_sum3_blocks(const float* a, int lda, float* out, int ldo, int n, int rows, cudaStream_t st) {
+    sum3_blocks_kernel<<<rows, 256, 0, st>>>(a, lda, out, ldo, n);
     return cudaGetLastError();
 }
