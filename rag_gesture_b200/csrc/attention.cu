@@ -169,7 +169,8 @@ struct HeadSmem {
     float kmaxp[TW][RG_HD], ksump[TW][RG_HD];
 };
 
-__global__ void __launch_bounds__(TW * 32) sa_core_kernel(const float* __restrict__ qkv,
+template <int MAXN>
+__global__ void __launch_bounds__(TW * 32, 8) sa_core_kernel(const float* __restrict__ qkv,
                                                          const float* __restrict__ src_mask,
                                                          float* __restrict__ Y, int T) {
     __shared__ __align__(16) HeadSmem sm;
@@ -179,7 +180,6 @@ __global__ void __launch_bounds__(TW * 32) sa_core_kernel(const float* __restric
     const float* base = qkv + (long long)b * T * (3 * RG_D) + head * RG_HD + lane;
     const float* mrow = src_mask + (long long)b * T;
     const long long RS = 3 * RG_D;
-    constexpr int MAXN = (RG_MAX_T + TW - 1) / TW;       // tokens per warp, upper bound (16)
     // own tokens' keys (+ -1e6 on masked tokens) and values in registers: all loads in flight at once
     float kk[MAXN], vv[MAXN];
 #pragma unroll
@@ -261,7 +261,8 @@ __global__ void __launch_bounds__(TW * 32) sa_core_kernel(const float* __restric
     }
 }
 
-__global__ void __launch_bounds__(TW * 32) ca_core_kernel(const float* __restrict__ q3, int ldq,
+template <int MAXN>
+__global__ void __launch_bounds__(TW * 32, 8) ca_core_kernel(const float* __restrict__ q3, int ldq,
                                                          const float* __restrict__ state,
                                                          long long state_clip_stride, long long state_cond_stride,
                                                          const float* __restrict__ qmask,
@@ -271,7 +272,6 @@ __global__ void __launch_bounds__(TW * 32) ca_core_kernel(const float* __restric
     rg_pdl_launch();
     rg_pdl_wait();
     const int b = blockIdx.x, c = blockIdx.y, head = blockIdx.z, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int MAXN = (RG_MAX_T + TW - 1) / TW;
     const float* qb = q3 + (long long)b * T * ldq + c * RG_D + head * RG_HD + lane;
     const float* qm = qmask ? qmask + (long long)c * qmask_cond_stride + (long long)b * T : nullptr;
     float qq[MAXN], mk[MAXN];
@@ -467,7 +467,8 @@ cudaError_t rg_launch_ca_attention(const float* q3, int ldq, const float* state,
 cudaError_t rg_launch_sa_core(const float* qkv, const float* src_mask, float* Y, int B, int T, cudaStream_t st) {
     if (B <= 0) return cudaSuccess;
     if (T > RG_MAX_T) return cudaErrorInvalidValue;
-    return rg_launch_pdl(sa_core_kernel, dim3(B, RG_H), dim3(TW * 32), 0, st, qkv, src_mask, Y, T);
+    if (T <= 11 * TW) return rg_launch_pdl(sa_core_kernel<11>, dim3(B, RG_H), dim3(TW * 32), 0, st, qkv, src_mask, Y, T);
+    return rg_launch_pdl(sa_core_kernel<16>, dim3(B, RG_H), dim3(TW * 32), 0, st, qkv, src_mask, Y, T);
 }
 
 cudaError_t rg_launch_ca_core(const float* q3, int ldq, const float* state, long long state_clip_stride,
@@ -475,7 +476,10 @@ cudaError_t rg_launch_ca_core(const float* q3, int ldq, const float* state, long
                               float* Y, int ldy, int B, int T, cudaStream_t st) {
     if (B <= 0) return cudaSuccess;
     if (T > RG_MAX_T) return cudaErrorInvalidValue;
-    return rg_launch_pdl(ca_core_kernel, dim3(B, 3, RG_H), dim3(TW * 32), 0, st, q3, ldq, state, state_clip_stride,
+    if (T <= 11 * TW)
+        return rg_launch_pdl(ca_core_kernel<11>, dim3(B, 3, RG_H), dim3(TW * 32), 0, st, q3, ldq, state,
+                             state_clip_stride, state_cond_stride, qmask, qmask_cond_stride, Y, ldy, T);
+    return rg_launch_pdl(ca_core_kernel<16>, dim3(B, 3, RG_H), dim3(TW * 32), 0, st, q3, ldq, state, state_clip_stride,
                          state_cond_stride, qmask, qmask_cond_stride, Y, ldy, T);
 }
 
