@@ -4,8 +4,8 @@
 // columns), epilogue warps reading it back with tcgen05.ld and fusing bias / residual / GELU / SiLU /
 // positional add, writing fp32 and/or bf16 (optionally hi+lo split) outputs.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..5 = epilogue (TMEM lane group = warp % 4).  Two CTAs are resident per SM
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..9 = epilogue (TMEM lane group = warp % 4, two warps per group split the columns).  Two CTAs are resident per SM
 // (96 KB smem, 128 TMEM columns each) so one tile's epilogue overlaps another tile's main loop.
 //
 // "split" mode (RG_PREC_BF16X3): operands are stored as [hi | lo] bf16 planes (x = hi + lo + O(2^-17 x));
@@ -100,7 +100,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t v[32]) {
 // STAGES = 3: two CTAs per SM (grids above one wave); STAGES = 6: one CTA per SM with the whole K = 512
 // reduction in flight (small grids, where a tile's latency, not throughput, is what is measured).
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(192, STAGES <= 3 ? 2 : 1)
+__global__ void __launch_bounds__(320, STAGES <= 3 ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, RgGemmTc p) {
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment
@@ -190,22 +190,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             __syncwarp();
         }
     } else {
-        // ===== epilogue: TMEM -> registers -> smem (transpose) -> coalesced global =====
+        // ===== epilogue (8 warps): TMEM -> registers -> smem (transpose) -> coalesced global =====
         // tcgen05.ld gives thread `lane` one accumulator ROW (32 columns per load); storing that
         // straight to global would touch 32 different cache lines per instruction.  The operand
-        // ring is idle once tmem_full fires, so each warp parks its 32 x BN quadrant there
-        // (row pitch BN+4 floats: conflict-free 128-bit accesses both ways) and then walks it row by
-        // row with lanes along N: bias / residual / pos loads and all stores are 512 B contiguous.
+        // ring is idle once tmem_full fires, so every warp parks its 32-row x BN/2-column block there
+        // (row pitch BN/2+4 floats: conflict-free both ways) and then walks it row by row with lanes
+        // along N: bias / residual / pos loads and all stores are contiguous, 8 rows in flight.
+        // Two warps share each TMEM lane group (a warp may only read lanes 32*(warp%4)..+31) and split
+        // the columns, which halves the serial latency of this phase.
         rg_pdl_wait();          // residual reads and all stores below touch buffers of the previous kernel
         mbar_wait(smem_u32(&tmem_full_bar), 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int lg = warp & 3;                                        // TMEM lane group of this warp
-        constexpr int PITCH = BN + 4;
-        float* stage = reinterpret_cast<float*>(smem) + lg * 32 * PITCH;
+        const int half = (warp - 2) >> 2;                               // which half of the tile's columns
+        constexpr int HC = BN / 2, PITCH = HC + 4;
+        float* stage = reinterpret_cast<float*>(smem) + ((warp - 2) * 32) * PITCH;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = 0; c < HC / 32; ++c) {
             uint32_t v[32];
-            tmem_ld32(tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + c * 32, v);
+            tmem_ld32(tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + half * HC + c * 32, v);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             float* dst = stage + lane * PITCH + c * 32;
 #pragma unroll
@@ -214,32 +217,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                                                   __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
         }
         __syncwarp();
-        const float* bias = p.bias ? p.bias + g * p.b_goff + n0 : nullptr;
-        const int cbase = g * p.c_goff + n0;                            // first column of this tile in C
-        const int rbase = p.r_grouped ? cbase : n0;
-        constexpr int NV = BN / 128;                                    // float4 per lane per row
-        float4 bv[NV];
+        const int tcol = half * HC;                                     // first column of this warp inside the tile
+        const float* bias = p.bias ? p.bias + g * p.b_goff + n0 + tcol : nullptr;
+        const int cbase = g * p.c_goff + n0 + tcol;                     // ... in C
+        const int rbase = (p.r_grouped ? g * p.c_goff : 0) + n0 + tcol; // ... in R
+        constexpr int NV = HC / 64;                                     // float2 per lane per row
+        float2 bv[NV];
 #pragma unroll
         for (int q = 0; q < NV; ++q)
-            bv[q] = bias ? __ldg(reinterpret_cast<const float4*>(bias + q * 128 + lane * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            bv[q] = bias ? __ldg(reinterpret_cast<const float2*>(bias + q * 64 + lane * 2)) : make_float2(0.f, 0.f);
         const int row0 = m0 + lg * 32;
         constexpr int RB = 8;                       // rows per batch: all shared/global loads first
 #pragma unroll 1
         for (int r0 = 0; r0 < 32; r0 += RB) {
-            float4 f[RB][NV], rr[RB][NV];
+            float2 f[RB][NV], rr[RB][NV];
 #pragma unroll
             for (int i = 0; i < RB; ++i) {
                 const int row = row0 + r0 + i;
 #pragma unroll
                 for (int q = 0; q < NV; ++q) {
-                    const int cc = q * 128 + lane * 4;
-                    f[i][q] = *reinterpret_cast<const float4*>(stage + (r0 + i) * PITCH + cc);
-                    rr[i][q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const int cc = q * 64 + lane * 2;
+                    f[i][q] = *reinterpret_cast<const float2*>(stage + (r0 + i) * PITCH + cc);
+                    rr[i][q] = make_float2(0.f, 0.f);
                     if (row < p.M) {
                         if (p.epi == RG_EPI_BIAS_RESIDUAL)
-                            rr[i][q] = *reinterpret_cast<const float4*>(p.R + (long long)row * p.ldr + rbase + cc);
+                            rr[i][q] = *reinterpret_cast<const float2*>(p.R + (long long)row * p.ldr + rbase + cc);
                         else if (p.epi == RG_EPI_BIAS_POS)
-                            rr[i][q] = __ldg(reinterpret_cast<const float4*>(p.pos + (long long)(row % p.pos_T) * p.N + n0 + cc));
+                            rr[i][q] = __ldg(reinterpret_cast<const float2*>(p.pos + (long long)(row % p.pos_T) * p.N + n0 + tcol + cc));
                     }
                 }
             }
@@ -249,27 +253,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (row >= p.M) break;
 #pragma unroll
                 for (int q = 0; q < NV; ++q) {
-                    const int cc = q * 128 + lane * 4;
-                    float4 v = f[i][q];
+                    const int cc = q * 64 + lane * 2;
+                    float2 v = f[i][q];
                     v.x += bv[q].x + rr[i][q].x; v.y += bv[q].y + rr[i][q].y;
-                    v.z += bv[q].z + rr[i][q].z; v.w += bv[q].w + rr[i][q].w;
                     if (p.epi == RG_EPI_BIAS_GELU) {
-                        v.x = rg_gelu_erf(v.x); v.y = rg_gelu_erf(v.y); v.z = rg_gelu_erf(v.z); v.w = rg_gelu_erf(v.w);
+                        v.x = rg_gelu_erf(v.x); v.y = rg_gelu_erf(v.y);
                     } else if (p.epi == RG_EPI_BIAS_SILU) {
-                        v.x = rg_silu(v.x); v.y = rg_silu(v.y); v.z = rg_silu(v.z); v.w = rg_silu(v.w);
+                        v.x = rg_silu(v.x); v.y = rg_silu(v.y);
                     }
-                    if (p.C32) *reinterpret_cast<float4*>(p.C32 + (long long)row * p.ldc32 + cbase + cc) = v;
+                    if (p.C32) *reinterpret_cast<float2*>(p.C32 + (long long)row * p.ldc32 + cbase + cc) = v;
                     if (p.C16_) {
                         __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.C16_) + (long long)row * p.ldc16 + cbase + cc;
-                        const float ff[4] = {v.x, v.y, v.z, v.w};
-                        __nv_bfloat16 h[4], l[4];
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            h[k] = __float2bfloat16_rn(ff[k]);
-                            l[k] = __float2bfloat16_rn(ff[k] - __bfloat162float(h[k]));
+                        const __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y);
+                        *reinterpret_cast<uint32_t*>(o) = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                        if (p.c16_lo_off) {
+                            const __nv_bfloat16 l0 = __float2bfloat16_rn(v.x - __bfloat162float(h0));
+                            const __nv_bfloat16 l1 = __float2bfloat16_rn(v.y - __bfloat162float(h1));
+                            *reinterpret_cast<uint32_t*>(o + p.c16_lo_off) =
+                                (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
                         }
-                        *reinterpret_cast<uint2*>(o) = *reinterpret_cast<uint2*>(h);
-                        if (p.c16_lo_off) *reinterpret_cast<uint2*>(o + p.c16_lo_off) = *reinterpret_cast<uint2*>(l);
                     }
                 }
             }
@@ -350,13 +352,13 @@ cudaError_t rg_launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmW, co
     dim3 grid(p.N / BN, (p.M + BM - 1) / BM, p.groups > 0 ? p.groups : 1);
     const long long ctas = (long long)grid.x * grid.y * grid.z;
     if (p.no_pdl) {     // weight tiles are prefetched before griddepcontrol.wait: only valid for constant W
-        if (ctas <= 148) gemm_tc_kernel<BN, 6><<<grid, 192, smem6, st>>>(tmA, tmW, p);
-        else gemm_tc_kernel<BN, 3><<<grid, 192, smem3, st>>>(tmA, tmW, p);
+        if (ctas <= 148) gemm_tc_kernel<BN, 6><<<grid, 320, smem6, st>>>(tmA, tmW, p);
+        else gemm_tc_kernel<BN, 3><<<grid, 320, smem3, st>>>(tmA, tmW, p);
         return cudaGetLastError();
     }
     if (ctas <= 148)
-        return rg_launch_pdl(gemm_tc_kernel<BN, 6>, grid, dim3(192), smem6, st, tmA, tmW, p);
-    return rg_launch_pdl(gemm_tc_kernel<BN, 3>, grid, dim3(192), smem3, st, tmA, tmW, p);
+        return rg_launch_pdl(gemm_tc_kernel<BN, 6>, grid, dim3(320), smem6, st, tmA, tmW, p);
+    return rg_launch_pdl(gemm_tc_kernel<BN, 3>, grid, dim3(320), smem3, st, tmA, tmW, p);
 }
 
 cudaError_t rg_launch_split_bf16(const float* x, int ldx, void* out, int ldo, int lo_off, long long rows, int cols,

@@ -379,12 +379,18 @@ class ReGestureTransformer(nn.Module):
 
     # -- fused path -------------------------------------------------------------------------------------
     def prepare_batch(self, model_kwargs, B):
-        """K6 state + packed masks for a batch; cached on the identity of the xf_out tensors."""
+        """K6 state + packed masks for a batch.  The state is cached while the SAME xf_out tensor objects
+        (unchanged `_version`) are passed again -- the sampler calls this once per loop, `forward` once per
+        step.  The cache holds references to those tensors, so their storage cannot be recycled for a
+        different batch behind an identical data_ptr."""
         eng = self.rg_engine()
         xf = model_kwargs["xf_out"]
-        key = tuple((xf[c].data_ptr(), xf[c]._version, tuple(xf[c].shape)) for c in CFG.CONDS)
-        if self._state_cache[0] != key:
-            self._state_cache = (key, eng.precompute_state(xf))
+        ts = tuple(xf[c] for c in CFG.CONDS)
+        vs = tuple(t._version for t in ts)
+        cached = self._state_cache[0]
+        hit = cached is not None and all(a is b for a, b in zip(cached[0], ts)) and cached[1] == vs
+        if not hit:
+            self._state_cache = ((ts, vs), eng.precompute_state(xf))
         state = self._state_cache[1]
         dev = state.device
         mm = model_kwargs["motion_mask"]

@@ -275,3 +275,21 @@ def test_tc_batch_independence(tc_model, dev):
         sub = {k: v[3:4] for k, v in cond.items()}
         one = model(x[3:4].contiguous(), torch.full((1,), 300, device=dev), **_kw(model, sub, 1, dev))
     assert torch.equal(one, full[3:4])
+
+
+def test_state_cache_is_not_reused_across_batches(model, dev):
+    """Regression: the K6 state cache was keyed on data_ptr/_version, so a new batch whose condition
+    tensors landed on recycled storage silently reused the previous batch's cross-attention state."""
+    B = 2
+    x = S.synthetic_latents(B, seed=82).to(dev)
+    outs = []
+    for seed in (81, 83, 81):
+        kw = _kw(model, S.synthetic_conditions(B, seed=seed), B, dev)
+        with torch.no_grad():
+            outs.append(model(x, torch.full((B,), 300, device=dev), **kw).clone())
+        del kw                                   # storage goes back to the caching allocator
+    model._state_cache = (None, None)
+    kw = _kw(model, S.synthetic_conditions(B, seed=83), B, dev)
+    with torch.no_grad():
+        fresh = model(x, torch.full((B,), 300, device=dev), **kw)
+    assert torch.equal(outs[1], fresh) and torch.equal(outs[0], outs[2]) and not torch.equal(outs[0], outs[1])
