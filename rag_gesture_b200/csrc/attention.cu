@@ -308,17 +308,32 @@ __global__ void __launch_bounds__(TW * 32, 8) ca_core_kernel(const float* __rest
     }
 }
 
-// Stylization prologue of the three cross-attention blocks over Y[M,1536]: blockIdx.y = condition
-__global__ void __launch_bounds__(256) styl_rows3_kernel(const float* __restrict__ y, int ldy, RgStyl3 sp3,
+// Stylization prologue of the three cross-attention blocks over Y[M,1536]: blockIdx.y = condition;
+// 4 rows per warp with the parameters held in registers (see styl_rows_kernel)
+__global__ void __launch_bounds__(128) styl_rows3_kernel(const float* __restrict__ y, int ldy, RgStyl3 sp3,
                                                         int rows_per_clip, RgRowOut out, int M) {
     rg_pdl_launch();
     rg_pdl_wait();
-    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), c = blockIdx.y, lane = threadIdx.x & 31;
-    if (row >= M) return;
-    float4 v[4];
-    load_row(y + (long long)row * ldy + c * RG_D, lane, v);
-    rg_styl_row(v, sp3.p[c], row / rows_per_clip, lane);
-    rg_store_row_out(out, row, c * RG_D, lane, v);
+    constexpr int RPW = 4;
+    const int row0 = (blockIdx.x * 4 + (threadIdx.x >> 5)) * RPW, c = blockIdx.y, lane = threadIdx.x & 31;
+    if (row0 >= M) return;
+    float4 v[RPW][4];
+#pragma unroll
+    for (int i = 0; i < RPW; ++i)
+        if (row0 + i < M) load_row(y + (long long)(row0 + i) * ldy + c * RG_D, lane, v[i]);
+    const RgStylParams& sp = sp3.p[c];
+    RgStylRegs r;
+    int clip = row0 / rows_per_clip;
+    rg_styl_load(r, sp, clip, lane);
+#pragma unroll
+    for (int i = 0; i < RPW; ++i) {
+        const int row = row0 + i;
+        if (row >= M) break;
+        const int cl = row / rows_per_clip;
+        if (cl != clip && sp.ss_clip_stride != 0) { clip = cl; rg_styl_load(r, sp, clip, lane); }
+        rg_styl_apply(v[i], r);
+        rg_store_row_out(out, row, c * RG_D, lane, v[i]);
+    }
 }
 
 __global__ void __launch_bounds__(512, 2) ca_attn_kernel(const float* __restrict__ q3, int ldq,
@@ -488,7 +503,7 @@ cudaError_t rg_launch_styl_rows3(const float* y, int ldy, const RgStylParams* sp
     if (M <= 0) return cudaSuccess;
     RgStyl3 s3;
     for (int c = 0; c < 3; ++c) s3.p[c] = sp3[c];
-    return rg_launch_pdl(styl_rows3_kernel, dim3((M + 7) / 8, 3), dim3(256), 0, st, y, ldy, s3, rows_per_clip, out, M);
+    return rg_launch_pdl(styl_rows3_kernel, dim3((M + 15) / 16, 3), dim3(128), 0, st, y, ldy, s3, rows_per_clip, out, M);
 }
 
 cudaError_t rg_launch_kv_state(const float* kv, int ldkv, int k_off, int v_off, int n_tokens,

@@ -54,6 +54,31 @@ __device__ __forceinline__ float4 affine4(float4 v, float4 g, float4 b) {
     return make_float4(v.x * g.x + b.x, v.y * g.y + b.y, v.z * g.z + b.z, v.w * g.w + b.w);
 }
 
+// Stylization parameters of one block for this lane's 16 columns, kept in registers across rows
+struct RgStylRegs { float4 g[4], b[4], sc[4], sh[4]; };
+__device__ __forceinline__ void rg_styl_load(RgStylRegs& r, const RgStylParams& sp, int clip, int lane) {
+    const float* ss = sp.ss + (long long)clip * sp.ss_clip_stride;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        r.g[j] = __ldg(reinterpret_cast<const float4*>(sp.gamma) + lane + 32 * j);
+        r.b[j] = __ldg(reinterpret_cast<const float4*>(sp.beta) + lane + 32 * j);
+        r.sc[j] = __ldg(reinterpret_cast<const float4*>(ss) + lane + 32 * j);
+        r.sh[j] = __ldg(reinterpret_cast<const float4*>(ss + RG_D) + lane + 32 * j);
+    }
+}
+__device__ __forceinline__ void rg_styl_apply(float4 v[4], const RgStylRegs& r) {
+    rg_ln_normalize(v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float4 h = affine4(v[j], r.g[j], r.b[j]);
+        h.x = rg_silu(h.x * (1.0f + r.sc[j].x) + r.sh[j].x);
+        h.y = rg_silu(h.y * (1.0f + r.sc[j].y) + r.sh[j].y);
+        h.z = rg_silu(h.z * (1.0f + r.sc[j].z) + r.sh[j].z);
+        h.w = rg_silu(h.w * (1.0f + r.sc[j].w) + r.sh[j].w);
+        v[j] = h;
+    }
+}
+
 // shared with attention.cu: LN -> affine -> *(1+scale)+shift -> SiLU on a row held across a warp
 __device__ __forceinline__ void rg_styl_row(float4 v[4], const RgStylParams& sp, int clip, int lane) {
     rg_ln_normalize(v);

@@ -35,18 +35,33 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ 
     rg_store_row_out(out, row, 0, lane, v);
 }
 
-__global__ void __launch_bounds__(256) styl_rows_kernel(const float* __restrict__ y, int ldy,
+// Each warp takes RPW consecutive rows and keeps the block's 4 x 2 KB of parameters (gamma, beta, scale,
+// shift) in registers across them: re-reading them per row made this kernel move 5x its data.
+constexpr int RPW = 4;
+__global__ void __launch_bounds__(128) styl_rows_kernel(const float* __restrict__ y, int ldy,
                                                        RgStylParams sp, int rows_per_clip,
                                                        RgRowOut out, int M) {
     rg_pdl_launch();
     rg_pdl_wait();
-    const int row = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
+    const int row0 = (blockIdx.x * 4 + (threadIdx.x >> 5)) * RPW;
     const int lane = threadIdx.x & 31;
-    if (row >= M) return;
-    float4 v[4];
-    load_row(y + (long long)row * ldy, lane, v);
-    rg_styl_row(v, sp, row / rows_per_clip, lane);
-    rg_store_row_out(out, row, 0, lane, v);
+    if (row0 >= M) return;
+    float4 v[RPW][4];
+#pragma unroll
+    for (int i = 0; i < RPW; ++i)
+        if (row0 + i < M) load_row(y + (long long)(row0 + i) * ldy, lane, v[i]);
+    RgStylRegs r;
+    int clip = row0 / rows_per_clip;
+    rg_styl_load(r, sp, clip, lane);
+#pragma unroll
+    for (int i = 0; i < RPW; ++i) {
+        const int row = row0 + i;
+        if (row >= M) break;
+        const int c = row / rows_per_clip;
+        if (c != clip && sp.ss_clip_stride != 0) { clip = c; rg_styl_load(r, sp, clip, lane); }
+        rg_styl_apply(v[i], r);
+        rg_store_row_out(out, row, 0, lane, v[i]);
+    }
 }
 
 __global__ void silu_kernel(const float* __restrict__ x, float* __restrict__ out, long long n) {
@@ -209,7 +224,7 @@ cudaError_t rg_launch_ln_rows(const float* x, int ldx, const float* gamma, const
 cudaError_t rg_launch_styl_rows(const float* y, int ldy, RgStylParams sp, int rows_per_clip,
                                 RgRowOut out, int M, cudaStream_t st) {
     if (M <= 0) return cudaSuccess;
-    return rg_launch_pdl(styl_rows_kernel, dim3(row_blocks(M)), dim3(256), 0, st, y, ldy, sp, rows_per_clip, out, M);
+    return rg_launch_pdl(styl_rows_kernel, dim3((M + 4 * RPW - 1) / (4 * RPW)), dim3(128), 0, st, y, ldy, sp, rows_per_clip, out, M);
 }
 cudaError_t rg_launch_silu(const float* x, float* out, long long n, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
