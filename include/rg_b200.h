@@ -102,6 +102,11 @@ int rg_precompute_clip_state(rg_handle h, const float* xf_text, const float* xf_
 int rg_denoise(rg_handle h, const float* x, int B, int step_idx, int tau, const float* src_mask,
                const float* query_mask, const float* state, float* x0_out, void* stream);
 
+/* How many concurrent kernel chains ("lanes", contiguous clip ranges on separate streams, joined back
+ * onto the caller's stream before the call returns) one rg_denoise uses: 0 = automatic (currently 1),
+ * 1..4 fixed.  Results do not depend on the setting: clips never interact inside a step. */
+int rg_set_lanes(rg_handle h, int lanes);
+
 /* DDIM update (eta = 0), bit-exact fp32 op order of the reference:
  *   eps = (c0*x - x0)/c1 ; out = x0*ca + cb*eps ; direction -1: (ca,cb) = coef 2,3 (ddim_sample,
  *   gaussian_diffusion.py:983-1001); direction +1: coef 4,5 (ddim_reverse_sample :1032-1038).
@@ -140,6 +145,12 @@ int rg_op_linear_tc(const float* x, const float* W, const float* b, const float*
  * launch to evict L2); *median_ms receives the median launch time.  Synchronises. */
 int rg_probe_gemm_tc(const float* x, const float* W, const float* b, float* out, int M, int N, int K,
                      int split, int reps, void* flush_buf, int64_t flush_bytes, float* median_ms, void* stream);
+/* Diagnostics: one traced launch of the tcgen05 GEMM on zero operands (after 3 untraced ones).  trace_host
+ * receives 10 int64 per CTA (grid order x-fastest): clock64 at [0] entry, [1] prologue done, [2] producer
+ * past griddepcontrol.wait, [3] first operand stage landed, [4] last MMA committed, [5] accumulator visible
+ * to the epilogue, [6] TMEM drained to smem, [7] all stores issued; [8] globaltimer ns at entry, [9] SM id. */
+int rg_probe_gemm_trace(int M, int N, int K, int split, int with_pdl_pred, int64_t* trace_host,
+                        int64_t n_trace, void* stream);
 /* LayerNorm over 512-wide rows, eps 1e-5; gamma/beta may be NULL (no affine). */
 int rg_op_layernorm(const float* x, const float* gamma, const float* beta, float* out, int M,
                     void* stream);
@@ -159,6 +170,15 @@ int rg_op_self_attention(const float* qkv, const float* src_mask, const float* g
 int rg_op_cross_attention(const float* q, const float* state, const float* query_mask,
                           const float* gamma, const float* beta, const float* ss, int ss_per_clip,
                           float* out, int B, int T, void* stream);
+/* The attention cores of the fused denoiser without the Stylization prologue: Y before norm/scale/shift.
+ * mode 0: fp32 FMA; 1: TF32 mma.sync (the RG_PREC_BF16 tier); 2: 3xTF32 hi/lo split (RG_PREC_BF16X3).
+ * self: qkv [B*T,1536], src_mask [B,T] -> y [B*T,512].
+ * cross: q3 [B*T,1536] pre-softmax queries of the three conditions, state [B,3,16,32,32],
+ *        query_mask [3,B,T] or NULL -> y [B*T,1536]. */
+int rg_op_self_attention_core(const float* qkv, const float* src_mask, float* y, int B, int T, int mode,
+                              void* stream);
+int rg_op_cross_attention_core(const float* q3, const float* state, const float* query_mask, float* y,
+                               int B, int T, int mode, void* stream);
 /* K/V -> state for ONE condition/layer: kv [B*N,1024] = [key | value] projections. */
 int rg_op_kv_state(const float* kv, int n_tokens, int B, float* state, void* stream);
 

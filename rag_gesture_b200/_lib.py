@@ -26,6 +26,7 @@ SIGNATURES = {
     "rg_create": (_I, [C.POINTER(RgConfig), _I, C.POINTER(C.c_char_p), C.POINTER(_P), C.POINTER(_L),
                        C.POINTER(_P)]),
     "rg_destroy": (_I, [_P]),
+    "rg_set_lanes": (_I, [_P, _I]),
     "rg_set_schedule": (_I, [_P, _I, C.POINTER(C.c_int32), C.POINTER(_F), _P]),
     "rg_encode_conditions": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "rg_state_floats_per_clip": (_L, [_P]),
@@ -37,11 +38,14 @@ SIGNATURES = {
     "rg_op_linear": (_I, [_P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "rg_op_linear_tc": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "rg_probe_gemm_tc": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _L, C.POINTER(C.c_float), _P]),
+    "rg_probe_gemm_trace": (_I, [_I, _I, _I, _I, _I, C.POINTER(_L), _L, _P]),
     "rg_op_layernorm": (_I, [_P, _P, _P, _P, _I, _P]),
     "rg_op_silu": (_I, [_P, _P, _L, _P]),
     "rg_op_stylization_rows": (_I, [_P, _P, _P, _P, _I, _I, _P, _I, _P]),
     "rg_op_self_attention": (_I, [_P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _P]),
     "rg_op_cross_attention": (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _I, _I, _P]),
+    "rg_op_self_attention_core": (_I, [_P, _P, _P, _I, _I, _I, _P]),
+    "rg_op_cross_attention_core": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "rg_op_kv_state": (_I, [_P, _I, _I, _P, _P]),
     "rg_text_similarity": (_I, [_P, _P, _L, _I, _I, _P, _I, _P, _L, _P, _P]),
     "rg_knn_topk": (_I, [_P, _L, _I, _P, _I, _I, _L, _P, _P, _P]),

@@ -7,6 +7,7 @@
 // round-trip through HBM.  fp32 throughout: the -1e6 additive masks and LN statistics of the
 // reference only make sense in fp32.
 #include <math.h>
+#include <stdlib.h>
 #include "rg_common.cuh"
 #include "rg_rows.cuh"
 
@@ -170,8 +171,8 @@ struct HeadSmem {
 };
 
 template <int MAXN>
-__global__ void __launch_bounds__(TW * 32, 8) sa_core_kernel(const float* __restrict__ qkv,
-                                                         const float* __restrict__ src_mask,
+__global__ void __launch_bounds__(TW * 32, 8) sa_core_kernel(const float* qkv,
+                                                         const float* src_mask,
                                                          float* __restrict__ Y, int T) {
     __shared__ __align__(16) HeadSmem sm;
     rg_pdl_launch();
@@ -262,10 +263,10 @@ __global__ void __launch_bounds__(TW * 32, 8) sa_core_kernel(const float* __rest
 }
 
 template <int MAXN>
-__global__ void __launch_bounds__(TW * 32, 8) ca_core_kernel(const float* __restrict__ q3, int ldq,
+__global__ void __launch_bounds__(TW * 32, 8) ca_core_kernel(const float* q3, int ldq,
                                                          const float* __restrict__ state,
                                                          long long state_clip_stride, long long state_cond_stride,
-                                                         const float* __restrict__ qmask,
+                                                         const float* qmask,
                                                          long long qmask_cond_stride, float* __restrict__ Y,
                                                          int ldy, int T) {
     __shared__ __align__(16) float rows[RG_MAX_T][RG_HD];
@@ -308,9 +309,233 @@ __global__ void __launch_bounds__(TW * 32, 8) ca_core_kernel(const float* __rest
     }
 }
 
+// ---- tensor-core cores (mma.sync m16n8k8, TF32 operands, fp32 accumulate) --------------------------------
+// The per-head products are 43x32x32: far below a tcgen05 tile (M >= 64, one issuing thread per CTA), but
+// the warp-level mma.sync fits them exactly.  ONE WARP owns one (clip, head): everything stays in
+// registers, there is no shared memory and no barrier.  Fragment ownership (g = lane/4, t = lane%4):
+//   A (16x8, row): a0=(g,t) a1=(g+8,t) a2=(g,t+4) a3=(g+8,t+4);  B (8x8, col): b0=(k=t,n=g) b1=(k=t+4,n=g)
+//   C (16x8): c0=(g,2t) c1=(g,2t+1) c2=(g+8,2t) c3=(g+8,2t+1)
+// Reduction indices may be permuted freely as long as A and B agree, so thread t takes
+//   * feature reductions (32 = 4 k-steps): logical (ks, t) -> d = 8ks+2t, (ks, t+4) -> d = 8ks+2t+1
+//     (one float2 load per row and k-step, and exactly the columns of a C fragment), and
+//   * token reductions (16*MT tokens = 2*MT k-steps): thread group t owns tokens [t*4MT, (t+1)*4MT).
+// With A^T = (V*m)^T softmax_n(K) computed as the first product, its C fragments ARE the B fragments of
+// Y = softmax_d(Q) A: no transpose, no exchange.  Softmaxes reduce over 8 (features) or 4MT (tokens)
+// in-thread values plus two xor-shuffles over t.
+// SPLIT (bf16x3 tier): operands are split hi + lo in TF32 and three products accumulate (lo*hi, hi*lo,
+// hi*hi): fp32-class accuracy.  Unsplit (bf16 tier): operands rounded to TF32 (rel. 2^-11).
+__device__ __forceinline__ uint32_t f2tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void mma_tf32(float c[4], const uint32_t a[4], const uint32_t b[2]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+template <bool SPLIT>
+__device__ __forceinline__ void mma_f32(float c[4], const float a[4], const float b[2]) {
+    uint32_t ah[4], bh[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ah[i] = f2tf32(a[i]);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) bh[i] = f2tf32(b[i]);
+    if (SPLIT) {
+        uint32_t al[4], bl[2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) al[i] = f2tf32(a[i] - __uint_as_float(ah[i]));
+#pragma unroll
+        for (int i = 0; i < 2; ++i) bl[i] = f2tf32(b[i] - __uint_as_float(bh[i]));
+        mma_tf32(c, al, bh);
+        mma_tf32(c, ah, bl);
+    }
+    mma_tf32(c, ah, bh);
+}
+__device__ __forceinline__ float quad_max(float v) {
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+    return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+__device__ __forceinline__ float quad_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+// softmax over the 32 features of rows r0 / r1 held as 4 float2 per row across the 4 threads of a quad
+__device__ __forceinline__ void quad_row_softmax(float2 q[4]) {
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) mx = fmaxf(mx, fmaxf(q[k].x, q[k].y));
+    mx = quad_max(mx);
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { q[k].x = rg_exp(q[k].x - mx); q[k].y = rg_exp(q[k].y - mx); s += q[k].x + q[k].y; }
+    s = quad_sum(s);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { q[k].x = __fdividef(q[k].x, s); q[k].y = __fdividef(q[k].y, s); }
+}
+
+// Y[b, n, head*32 + l] = softmax_d(Q)[n, :] . (softmax_n(K + mask)^T (V * m))[:, l]   (efficient_attention.py:146-160)
+template <int MT, bool SPLIT>
+__global__ void __launch_bounds__(128) sa_core_mma_kernel(const float* qkv,
+                                                         const float* src_mask,
+                                                         float* __restrict__ Y, int T) {
+    rg_pdl_launch();
+    rg_pdl_wait();
+    constexpr int KS = 2 * MT, TPT = 2 * KS;             // token k-steps; tokens owned by one thread group
+    const int b = blockIdx.x, head = blockIdx.y * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const long long RS = 3 * RG_D;
+    const float* base = qkv + (long long)b * T * RS + head * RG_HD;
+    const float* mrow = src_mask + (long long)b * T;
+    const int n0 = t * TPT;
+    float mk[TPT], kk[TPT][4], vv[TPT][4];               // K[n][8j+g] (+ -1e6 mask), V[n][8j+g] * m
+#pragma unroll
+    for (int i = 0; i < TPT; ++i) mk[i] = (n0 + i < T) ? mrow[n0 + i] : 0.f;
+#pragma unroll
+    for (int i = 0; i < TPT; ++i) {
+        const float* row = base + (long long)(n0 + i) * RS + g;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            kk[i][j] = (n0 + i < T) ? row[RG_D + 8 * j] : 0.f;
+            vv[i][j] = (n0 + i < T) ? row[2 * RG_D + 8 * j] : 0.f;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < TPT; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            kk[i][j] = (n0 + i < T) ? kk[i][j] + (1.0f - mk[i]) * RG_NEG_MASK : -INFINITY;
+            vv[i][j] *= mk[i];
+        }
+    // softmax over the tokens, per feature column 8j+g, normalised here (a/s == sum((e/s) v) up to rounding)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < TPT; ++i) mx = fmaxf(mx, kk[i][j]);
+        mx = quad_max(mx);
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < TPT; ++i) { kk[i][j] = rg_exp(kk[i][j] - mx); s += kk[i][j]; }
+        const float r = __fdividef(1.0f, quad_sum(s));
+#pragma unroll
+        for (int i = 0; i < TPT; ++i) kk[i][j] *= r;
+    }
+    // A^T[l][d] = sum_n (V m)[n][l] E[n][d]:  M = l (2 tiles), N = d (4 tiles), K = tokens
+    float at[2][4][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) at[mt][nt][i] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+        const int i0 = 2 * ks, i1 = 2 * ks + 1;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            const float a[4] = {vv[i0][2 * mt], vv[i0][2 * mt + 1], vv[i1][2 * mt], vv[i1][2 * mt + 1]};
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const float bb[2] = {kk[i0][nt], kk[i1][nt]};
+                mma_f32<SPLIT>(at[mt][nt], a, bb);
+            }
+        }
+    }
+    // Y = softmax_d(Q) A, 16 query rows per tile; B fragments are the C fragments above
+    float* o = Y + (long long)b * T * RG_D + head * RG_HD + 2 * t;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+        const int r0 = 16 * mt + g, r1 = r0 + 8;
+        float2 q0[4], q1[4];
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            q0[ks] = r0 < T ? *reinterpret_cast<const float2*>(base + (long long)r0 * RS + 8 * ks + 2 * t) : make_float2(0.f, 0.f);
+            q1[ks] = r1 < T ? *reinterpret_cast<const float2*>(base + (long long)r1 * RS + 8 * ks + 2 * t) : make_float2(0.f, 0.f);
+        }
+        quad_row_softmax(q0);
+        quad_row_softmax(q1);
+        float y[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) y[nt][i] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            const float a[4] = {q0[ks].x, q1[ks].x, q0[ks].y, q1[ks].y};
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const float bb[2] = {at[nt >> 1][ks][2 * (nt & 1)], at[nt >> 1][ks][2 * (nt & 1) + 1]};
+                mma_f32<SPLIT>(y[nt], a, bb);
+            }
+        }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            if (r0 < T) *reinterpret_cast<float2*>(o + (long long)r0 * RG_D + 8 * nt) = make_float2(y[nt][0], y[nt][1]);
+            if (r1 < T) *reinterpret_cast<float2*>(o + (long long)r1 * RG_D + 8 * nt) = make_float2(y[nt][2], y[nt][3]);
+        }
+    }
+}
+
+// Y[b, n, c*512 + head*32 + l] = softmax_d(Q_c)[n, :] . state[b, c, head][:, l]  (+ -1e6 on rows with query_mask 0)
+template <int MT, bool SPLIT>
+__global__ void __launch_bounds__(128) ca_core_mma_kernel(const float* q3, int ldq,
+                                                         const float* __restrict__ state,
+                                                         long long state_clip_stride, long long state_cond_stride,
+                                                         const float* qmask,
+                                                         long long qmask_cond_stride, float* __restrict__ Y,
+                                                         int ldy, int T) {
+    rg_pdl_launch();
+    rg_pdl_wait();
+    const int b = blockIdx.x, c = blockIdx.y, head = blockIdx.z * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const float* Ap = state + (long long)b * state_clip_stride + (long long)c * state_cond_stride +
+                      (long long)head * RG_HD * RG_HD;
+    float bf[4][4][2];                                   // [ks][nt][j] = A[d = 8ks+2t+j][l = 8nt+g]
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) bf[ks][nt][j] = __ldg(Ap + (8 * ks + 2 * t + j) * RG_HD + 8 * nt + g);
+    const float* qb = q3 + (long long)b * T * ldq + c * RG_D + head * RG_HD + 2 * t;
+    const float* qm = qmask ? qmask + (long long)c * qmask_cond_stride + (long long)b * T : nullptr;
+    float* o = Y + (long long)b * T * ldy + c * RG_D + head * RG_HD + 2 * t;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+        const int r0 = 16 * mt + g, r1 = r0 + 8;
+        float2 q0[4], q1[4];
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            q0[ks] = r0 < T ? *reinterpret_cast<const float2*>(qb + (long long)r0 * ldq + 8 * ks) : make_float2(0.f, 0.f);
+            q1[ks] = r1 < T ? *reinterpret_cast<const float2*>(qb + (long long)r1 * ldq + 8 * ks) : make_float2(0.f, 0.f);
+        }
+        const float add0 = (qm && r0 < T) ? (1.0f - qm[r0]) * RG_NEG_MASK : 0.f;
+        const float add1 = (qm && r1 < T) ? (1.0f - qm[r1]) * RG_NEG_MASK : 0.f;
+        quad_row_softmax(q0);
+        quad_row_softmax(q1);
+        float y[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) y[nt][i] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            const float a[4] = {q0[ks].x, q1[ks].x, q0[ks].y, q1[ks].y};
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) mma_f32<SPLIT>(y[nt], a, bf[ks][nt]);
+        }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {      // fp32 add: y - 1e6 rounds to a 1/16 grid, as in the reference
+            if (r0 < T) *reinterpret_cast<float2*>(o + (long long)r0 * ldy + 8 * nt) = make_float2(y[nt][0] + add0, y[nt][1] + add0);
+            if (r1 < T) *reinterpret_cast<float2*>(o + (long long)r1 * ldy + 8 * nt) = make_float2(y[nt][2] + add1, y[nt][3] + add1);
+        }
+    }
+}
+
 // Stylization prologue of the three cross-attention blocks over Y[M,1536]: blockIdx.y = condition;
 // 4 rows per warp with the parameters held in registers (see styl_rows_kernel)
-__global__ void __launch_bounds__(128) styl_rows3_kernel(const float* __restrict__ y, int ldy, RgStyl3 sp3,
+__global__ void __launch_bounds__(128) styl_rows3_kernel(const float* y, int ldy, RgStyl3 sp3,
                                                         int rows_per_clip, RgRowOut out, int M) {
     rg_pdl_launch();
     rg_pdl_wait();
@@ -479,18 +704,47 @@ cudaError_t rg_launch_ca_attention(const float* q3, int ldq, const float* state,
     return cudaGetLastError();
 }
 
-cudaError_t rg_launch_sa_core(const float* qkv, const float* src_mask, float* Y, int B, int T, cudaStream_t st) {
+template <bool SPLIT>
+static cudaError_t launch_sa_mma(const float* qkv, const float* src_mask, float* Y, int B, int T, cudaStream_t st) {
+    const dim3 grid(B, RG_H / 4), block(128);
+    switch ((T + 15) / 16) {
+        case 1: return rg_launch_pdl(sa_core_mma_kernel<1, SPLIT>, grid, block, 0, st, qkv, src_mask, Y, T);
+        case 2: return rg_launch_pdl(sa_core_mma_kernel<2, SPLIT>, grid, block, 0, st, qkv, src_mask, Y, T);
+        case 3: return rg_launch_pdl(sa_core_mma_kernel<3, SPLIT>, grid, block, 0, st, qkv, src_mask, Y, T);
+        default: return rg_launch_pdl(sa_core_mma_kernel<4, SPLIT>, grid, block, 0, st, qkv, src_mask, Y, T);
+    }
+}
+template <bool SPLIT>
+static cudaError_t launch_ca_mma(const float* q3, int ldq, const float* state, long long scs, long long sds,
+                                 const float* qmask, long long qms, float* Y, int ldy, int B, int T, cudaStream_t st) {
+    const dim3 grid(B, 3, RG_H / 4), block(128);
+    switch ((T + 15) / 16) {
+        case 1: return rg_launch_pdl(ca_core_mma_kernel<1, SPLIT>, grid, block, 0, st, q3, ldq, state, scs, sds, qmask, qms, Y, ldy, T);
+        case 2: return rg_launch_pdl(ca_core_mma_kernel<2, SPLIT>, grid, block, 0, st, q3, ldq, state, scs, sds, qmask, qms, Y, ldy, T);
+        case 3: return rg_launch_pdl(ca_core_mma_kernel<3, SPLIT>, grid, block, 0, st, q3, ldq, state, scs, sds, qmask, qms, Y, ldy, T);
+        default: return rg_launch_pdl(ca_core_mma_kernel<4, SPLIT>, grid, block, 0, st, q3, ldq, state, scs, sds, qmask, qms, Y, ldy, T);
+    }
+}
+
+// mode 0: fp32 SIMT cores; 1: TF32 mma.sync; 2: 3xTF32 (hi/lo split) mma.sync
+cudaError_t rg_launch_sa_core(const float* qkv, const float* src_mask, float* Y, int B, int T, int mode, cudaStream_t st) {
     if (B <= 0) return cudaSuccess;
     if (T > RG_MAX_T) return cudaErrorInvalidValue;
+    if (mode == 1) return launch_sa_mma<false>(qkv, src_mask, Y, B, T, st);
+    if (mode == 2) return launch_sa_mma<true>(qkv, src_mask, Y, B, T, st);
     if (T <= 11 * TW) return rg_launch_pdl(sa_core_kernel<11>, dim3(B, RG_H), dim3(TW * 32), 0, st, qkv, src_mask, Y, T);
     return rg_launch_pdl(sa_core_kernel<16>, dim3(B, RG_H), dim3(TW * 32), 0, st, qkv, src_mask, Y, T);
 }
 
 cudaError_t rg_launch_ca_core(const float* q3, int ldq, const float* state, long long state_clip_stride,
                               long long state_cond_stride, const float* qmask, long long qmask_cond_stride,
-                              float* Y, int ldy, int B, int T, cudaStream_t st) {
+                              float* Y, int ldy, int B, int T, int mode, cudaStream_t st) {
     if (B <= 0) return cudaSuccess;
-    if (T > RG_MAX_T) return cudaErrorInvalidValue;
+    if (T > RG_MAX_T || (ldq % 2) || (ldy % 2)) return cudaErrorInvalidValue;
+    if (mode == 1)
+        return launch_ca_mma<false>(q3, ldq, state, state_clip_stride, state_cond_stride, qmask, qmask_cond_stride, Y, ldy, B, T, st);
+    if (mode == 2)
+        return launch_ca_mma<true>(q3, ldq, state, state_clip_stride, state_cond_stride, qmask, qmask_cond_stride, Y, ldy, B, T, st);
     if (T <= 11 * TW)
         return rg_launch_pdl(ca_core_kernel<11>, dim3(B, 3, RG_H), dim3(TW * 32), 0, st, q3, ldq, state,
                              state_clip_stride, state_cond_stride, qmask, qmask_cond_stride, Y, ldy, T);

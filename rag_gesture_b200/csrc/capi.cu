@@ -69,15 +69,23 @@ struct W16 {                 // bf16 operand planes [N, planes*K] (hi | lo) + it
 };
 struct LayerTc { W16 qkv, sa_o, caq, fold, w1, w2, ffn_o; float* b_fold; };
 
+#define RG_MAX_LANES 4
+struct Ws {                  // one lane's activation workspace (rows = clips * n_tokens of that lane)
+    long long rows;
+    float *h, *a, *big, *o3, *g, *y;
+    void *x16, *a16, *a16x, *h16, *g16;
+    CUtensorMap tm_x16, tm_a16, tm_a16x, tm_h16, tm_g16;
+};
+
 struct rg_model {
     rg_config cfg;
     // tensor-core path (cfg.precision != RG_PREC_FP32)
     int planes;              // 1: bf16 operands, 2: hi|lo planes (bf16x3)
+    int attn_mode_ca;
+    int attn_mode;           // attention cores: 0 fp32 SIMT, 1 TF32 mma.sync (bf16 tier), 2 3xTF32 (bf16x3 tier)
     std::vector<LayerTc> tc;
     W16 tc_joint, tc_out, tc_kv[3];
     void* kv_a16;
-    void *x16, *a16, *a16x, *h16, *g16;
-    CUtensorMap tm_x16, tm_a16, tm_a16x, tm_h16, tm_g16;
     int device;
     std::vector<void*> allocs;
     std::vector<Layer> layers;
@@ -94,9 +102,11 @@ struct rg_model {
     float* table;                         // [n_steps, L, 5, 1024]
     float* tau_row;                       // [L*5*1024] scratch for an off-table timestep
     int tau_cached;
-    // workspace
-    long long ws_rows;
-    float *h, *a, *big, *o3, *g, *y;
+    // workspaces: rg_denoise cuts a batch into `lanes` clip ranges that run as concurrent kernel chains
+    int lanes;                            // 0: automatic
+    Ws ws[RG_MAX_LANES];
+    cudaStream_t lane_st[RG_MAX_LANES];   // [0] unused: lane 0 runs on the caller's stream
+    cudaEvent_t ev_fork, ev_join[RG_MAX_LANES];
     long long kv_rows;
     float *kv_ln, *kv_buf;
     long long tt_rows;
@@ -192,6 +202,11 @@ extern "C" int64_t rg_launch_count(void) { return g_launches; }
 extern "C" int rg_destroy(rg_handle h) {
     if (!h) return 0;
     for (void* p : h->allocs) cudaFree(p);
+    for (int i = 0; i < RG_MAX_LANES; ++i) {
+        if (h->lane_st[i]) cudaStreamDestroy(h->lane_st[i]);
+        if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+    }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     delete h;
     return 0;
 }
@@ -219,11 +234,17 @@ extern "C" int rg_create(const rg_config* cfg, int n_tensors, const char* const*
     m->cfg = *cfg;
     cudaGetDevice(&m->device);
     m->n_steps = 0; m->table = nullptr; m->tau_row = nullptr; m->tau_cached = -1;
-    m->ws_rows = 0; m->h = m->a = m->big = m->o3 = m->g = m->y = nullptr;
+    memset(m->ws, 0, sizeof(m->ws));
+    m->lanes = 0; m->ev_fork = nullptr;
+    for (int i = 0; i < RG_MAX_LANES; ++i) { m->lane_st[i] = nullptr; m->ev_join[i] = nullptr; }
     m->kv_rows = 0; m->kv_ln = m->kv_buf = nullptr;
     m->tt_rows = 0; m->tt_emb = m->tt_t1 = m->tt_e = nullptr;
     m->planes = cfg->precision == RG_PREC_BF16X3 ? 2 : 1;
-    m->x16 = m->a16 = m->a16x = m->h16 = m->g16 = nullptr; m->kv_a16 = nullptr;
+    m->attn_mode = cfg->precision == RG_PREC_BF16X3 ? 2 : 1;
+    m->attn_mode_ca = m->attn_mode;
+    if (const char* e = getenv("RG_ATTN_MODE")) m->attn_mode = m->attn_mode_ca = atoi(e);      // diagnostics only
+    if (const char* e = getenv("RG_ATTN_MODE_CA")) m->attn_mode_ca = atoi(e);
+    m->kv_a16 = nullptr;
     const int D = RG_D, E = cfg->time_embed_dim, F = cfg->ffn_dim, L = cfg->num_layers, T = cfg->n_tokens;
     const long long DD = (long long)D * D;
     cudaStream_t st = 0;
@@ -417,31 +438,33 @@ extern "C" int rg_set_schedule(rg_handle m, int n_steps, const int32_t* timestep
 }
 
 // ---- workspaces ------------------------------------------------------------------------------
-static int ensure_ws(rg_model* m, long long rows) {
-    if (rows <= m->ws_rows) return 0;
-    float** bufs[6] = {&m->h, &m->a, &m->big, &m->o3, &m->g, &m->y};
+static int ensure_ws(rg_model* m, Ws& w, long long rows) {
+    if (rows <= w.rows) return 0;
+    float** bufs[6] = {&w.h, &w.a, &w.big, &w.o3, &w.g, &w.y};
     for (auto b : bufs) { dfree_one(m, *b); *b = nullptr; }
-    m->ws_rows = 0;
+    w.rows = 0;
     const int D = RG_D, F = m->cfg.ffn_dim;
-    if (dalloc(m, (void**)&m->h, (size_t)rows * D * sizeof(float))) return 1;
-    if (dalloc(m, (void**)&m->a, (size_t)rows * 3 * D * sizeof(float))) return 1;
-    if (dalloc(m, (void**)&m->big, (size_t)rows * 3 * D * sizeof(float))) return 1;
-    if (dalloc(m, (void**)&m->o3, (size_t)rows * 3 * D * sizeof(float))) return 1;
-    if (dalloc(m, (void**)&m->g, (size_t)rows * F * sizeof(float))) return 1;
-    if (dalloc(m, (void**)&m->y, (size_t)rows * D * sizeof(float))) return 1;
+    if (dalloc(m, (void**)&w.h, (size_t)rows * D * sizeof(float))) return 1;
+    if (dalloc(m, (void**)&w.a, (size_t)rows * 3 * D * sizeof(float))) return 1;
+    if (dalloc(m, (void**)&w.big, (size_t)rows * 3 * D * sizeof(float))) return 1;
+    if (dalloc(m, (void**)&w.o3, (size_t)rows * 3 * D * sizeof(float))) return 1;
+    if (dalloc(m, (void**)&w.g, (size_t)rows * F * sizeof(float))) return 1;
+    if (dalloc(m, (void**)&w.y, (size_t)rows * D * sizeof(float))) return 1;
     if (m->cfg.precision != RG_PREC_FP32) {
         const int P = m->planes;
-        void** b16[5] = {&m->x16, &m->a16, &m->a16x, &m->h16, &m->g16};
+        void** b16[5] = {&w.x16, &w.a16, &w.a16x, &w.h16, &w.g16};
         const int width[5] = {D, D, 4 * D, D, F};
-        CUtensorMap* tms[5] = {&m->tm_x16, &m->tm_a16, &m->tm_a16x, &m->tm_h16, &m->tm_g16};
+        CUtensorMap* tms[5] = {&w.tm_x16, &w.tm_a16, &w.tm_a16x, &w.tm_h16, &w.tm_g16};
         for (int i = 0; i < 5; ++i) {
             dfree_one(m, *b16[i]); *b16[i] = nullptr;
             if (dalloc(m, b16[i], (size_t)rows * width[i] * P * 2)) return 1;
             CU(cudaMemset(*b16[i], 0, (size_t)rows * width[i] * P * 2));
             CU(rg_make_tensor_map(tms[i], *b16[i], rows, (long long)width[i] * P, (long long)width[i] * P, 128));
         }
+        // the memsets run on the legacy stream, which non-blocking lane streams do not wait for
+        CU(cudaDeviceSynchronize());
     }
-    m->ws_rows = rows;
+    w.rows = rows;
     return 0;
 }
 
@@ -536,52 +559,109 @@ static int tc_gemm(rg_model* m, const CUtensorMap& tmA, int a_w, const W16& w, c
 
 // rg_denoise on the tensor cores: bf16 (or hi|lo bf16) operands, fp32 accumulation in TMEM, fp32
 // residual stream / softmaxes / LayerNorm statistics / -1e6 masks exactly as on the fp32 path.
-static int denoise_tc(rg_model* m, const float* x, int B, const float* ssrow, const float* src_mask,
-                      const float* query_mask, const float* state, float* x0_out, cudaStream_t st) {
+static int denoise_tc(rg_model* m, Ws& w, const float* x, int B, const float* ssrow, const float* src_mask,
+                      const float* query_mask, long long qm_cond_stride, const float* state, float* x0_out,
+                      cudaStream_t st) {
     const int D = RG_D, F = m->cfg.ffn_dim, L = m->cfg.num_layers, T = m->cfg.n_tokens, P = m->planes;
     const int M = B * T;
     const long long clip_stride = rg_state_floats_per_clip(m);
     const long long HS = (long long)RG_H * RG_HD * RG_HD;
     const int lo = P == 2;
-    LAUNCH(rg_launch_split_bf16(x, D, m->x16, D * P, lo ? D : 0, M, D, st));
-    if (tc_gemm(m, m->tm_x16, D, m->tc_joint, m->b_joint, M, D, D, RG_EPI_BIAS_POS, nullptr, m->h, D, nullptr, 0, st)) return 1;
+    LAUNCH(rg_launch_split_bf16(x, D, w.x16, D * P, lo ? D : 0, M, D, st));
+    if (tc_gemm(m, w.tm_x16, D, m->tc_joint, m->b_joint, M, D, D, RG_EPI_BIAS_POS, nullptr, w.h, D, nullptr, 0, st)) return 1;
     for (int l = 0; l < L; ++l) {
         const Layer& ly = m->layers[l];
         const LayerTc& t = m->tc[l];
         const float* ss = ssrow + (long long)l * 5 * 2 * D;
         // --- self-attention
-        LAUNCH(rg_launch_ln_rows(m->h, D, nullptr, nullptr, rg_out_b16(m->a16, D * P, lo ? D : 0), M, st));
-        if (tc_gemm(m, m->tm_a16, D, t.qkv, ly.bqkv, M, 3 * D, D, RG_EPI_BIAS, nullptr, m->big, 3 * D, nullptr, 0, st)) return 1;
+        LAUNCH(rg_launch_ln_rows(w.h, D, nullptr, nullptr, rg_out_b16(w.a16, D * P, lo ? D : 0), M, st));
+        if (tc_gemm(m, w.tm_a16, D, t.qkv, ly.bqkv, M, 3 * D, D, RG_EPI_BIAS, nullptr, w.big, 3 * D, nullptr, 0, st)) return 1;
         RgStylParams sp = {ly.sa_g, ly.sa_b, ss, 0};
-        LAUNCH(rg_launch_sa_core(m->big, src_mask, m->y, B, T, st));
-        LAUNCH(rg_launch_styl_rows(m->y, D, sp, T, rg_out_b16(m->a16, D * P, lo ? D : 0), M, st));
+        LAUNCH(rg_launch_sa_core(w.big, src_mask, w.y, B, T, m->attn_mode, st));
+        LAUNCH(rg_launch_styl_rows(w.y, D, sp, T, rg_out_b16(w.a16, D * P, lo ? D : 0), M, st));
         // h1 = h + proj(...): fp32 residual stream + its bf16 planes as the 4th K-block of the folded ca GEMM
         {
             RgGemmTc p;
             memset(&p, 0, sizeof(p));
             p.M = M; p.N = D; p.K = D; p.split = lo; p.a_lo_off = D; p.w_lo_off = D; p.groups = 1;
-            p.bias = ly.sa_bo; p.R = m->h; p.ldr = D; p.C32 = m->h; p.ldc32 = D;
-            p.C16_ = reinterpret_cast<__nv_bfloat16*>(m->a16x) + 3 * D; p.ldc16 = 4 * D * P; p.c16_lo_off = lo ? 4 * D : 0;
+            p.bias = ly.sa_bo; p.R = w.h; p.ldr = D; p.C32 = w.h; p.ldc32 = D;
+            p.C16_ = reinterpret_cast<__nv_bfloat16*>(w.a16x) + 3 * D; p.ldc16 = 4 * D * P; p.c16_lo_off = lo ? 4 * D : 0;
             p.epi = RG_EPI_BIAS_RESIDUAL;
-            LAUNCH(rg_launch_gemm_tc(m->tm_a16, t.sa_o.tm, p, st));
+            LAUNCH(rg_launch_gemm_tc(w.tm_a16, t.sa_o.tm, p, st));
         }
         // --- three cross-attentions on the same h, their projections and ca_mix folded into one GEMM
-        LAUNCH(rg_launch_ln_rows(m->h, D, nullptr, nullptr, rg_out_b16(m->a16, D * P, lo ? D : 0), M, st));
-        if (tc_gemm(m, m->tm_a16, D, t.caq, ly.bcaq, M, 3 * D, D, RG_EPI_BIAS, nullptr, m->big, 3 * D, nullptr, 0, st)) return 1;
+        LAUNCH(rg_launch_ln_rows(w.h, D, nullptr, nullptr, rg_out_b16(w.a16, D * P, lo ? D : 0), M, st));
+        if (tc_gemm(m, w.tm_a16, D, t.caq, ly.bcaq, M, 3 * D, D, RG_EPI_BIAS, nullptr, w.big, 3 * D, nullptr, 0, st)) return 1;
         RgStylParams sp3[3];
         for (int c = 0; c < 3; ++c) sp3[c] = {ly.ca_g + c * D, ly.ca_b + c * D, ss + (1 + c) * 2 * D, 0};
-        LAUNCH(rg_launch_ca_core(m->big, 3 * D, state + (long long)l * 3 * HS, clip_stride, HS, query_mask,
-                                 (long long)B * T, m->o3, 3 * D, B, T, st));
-        LAUNCH(rg_launch_styl_rows3(m->o3, 3 * D, sp3, T, rg_out_b16(m->a16x, 4 * D * P, lo ? 4 * D : 0), M, st));
-        if (tc_gemm(m, m->tm_a16x, 4 * D, t.fold, t.b_fold, M, D, 4 * D, RG_EPI_BIAS, nullptr, m->h, D, m->h16, D, st)) return 1;
+        LAUNCH(rg_launch_ca_core(w.big, 3 * D, state + (long long)l * 3 * HS, clip_stride, HS, query_mask,
+                                 qm_cond_stride, w.o3, 3 * D, B, T, m->attn_mode_ca, st));
+        LAUNCH(rg_launch_styl_rows3(w.o3, 3 * D, sp3, T, rg_out_b16(w.a16x, 4 * D * P, lo ? 4 * D : 0), M, st));
+        if (tc_gemm(m, w.tm_a16x, 4 * D, t.fold, t.b_fold, M, D, 4 * D, RG_EPI_BIAS, nullptr, w.h, D, w.h16, D, st)) return 1;
         // --- FFN
-        if (tc_gemm(m, m->tm_h16, D, t.w1, ly.b1, M, F, D, RG_EPI_BIAS_GELU, nullptr, nullptr, 0, m->g16, F, st)) return 1;
-        if (tc_gemm(m, m->tm_g16, F, t.w2, ly.b2, M, D, F, RG_EPI_BIAS, nullptr, m->y, D, nullptr, 0, st)) return 1;
+        if (tc_gemm(m, w.tm_h16, D, t.w1, ly.b1, M, F, D, RG_EPI_BIAS_GELU, nullptr, nullptr, 0, w.g16, F, st)) return 1;
+        if (tc_gemm(m, w.tm_g16, F, t.w2, ly.b2, M, D, F, RG_EPI_BIAS, nullptr, w.y, D, nullptr, 0, st)) return 1;
         RgStylParams spf = {ly.ffn_g, ly.ffn_b, ss + 4 * 2 * D, 0};
-        LAUNCH(rg_launch_styl_rows(m->y, D, spf, T, rg_out_b16(m->a16, D * P, lo ? D : 0), M, st));
-        if (tc_gemm(m, m->tm_a16, D, t.ffn_o, ly.ffn_bo, M, D, D, RG_EPI_BIAS_RESIDUAL, m->h, m->h, D, m->h16, D, st)) return 1;
+        LAUNCH(rg_launch_styl_rows(w.y, D, spf, T, rg_out_b16(w.a16, D * P, lo ? D : 0), M, st));
+        if (tc_gemm(m, w.tm_a16, D, t.ffn_o, ly.ffn_bo, M, D, D, RG_EPI_BIAS_RESIDUAL, w.h, w.h, D, w.h16, D, st)) return 1;
     }
-    return tc_gemm(m, m->tm_h16, D, m->tc_out, m->b_out, M, D, D, RG_EPI_BIAS, nullptr, x0_out, D, nullptr, 0, st);
+    return tc_gemm(m, w.tm_h16, D, m->tc_out, m->b_out, M, D, D, RG_EPI_BIAS, nullptr, x0_out, D, nullptr, 0, st);
+}
+
+// rg_denoise, fp32 SIMT tier (RG_PREC_FP32): one lane's clips.
+static int denoise_f32(rg_model* m, Ws& w, const float* x, int B, const float* ssrow, const float* src_mask,
+                       const float* query_mask, long long qm_cond_stride, const float* state, float* x0_out,
+                       cudaStream_t st) {
+    const int D = RG_D, F = m->cfg.ffn_dim, L = m->cfg.num_layers, T = m->cfg.n_tokens;
+    const int M = B * T;
+    const long long clip_stride = rg_state_floats_per_clip(m);
+    const long long HS = (long long)RG_H * RG_HD * RG_HD;
+
+    // h = joint_embed(x) + positional tables
+    {
+        RgGemm g = mk_gemm(x, D, m->W_joint, m->b_joint, w.h, D, M, D, D, RG_EPI_BIAS_POS);
+        g.pos = m->pos; g.pos_T = T;
+        LAUNCH(rg_launch_gemm_f32(g, st));
+    }
+    for (int l = 0; l < L; ++l) {
+        const Layer& ly = m->layers[l];
+        const float* ss = ssrow + (long long)l * 5 * 2 * D;
+        // --- self-attention
+        LAUNCH(rg_launch_ln_rows(w.h, D, nullptr, nullptr, rg_out_f32(w.a, D), M, st));
+        LAUNCH(rg_launch_gemm_f32(mk_gemm(w.a, D, ly.Wqkv, ly.bqkv, w.big, 3 * D, M, 3 * D, D, RG_EPI_BIAS), st));
+        RgStylParams sp = {ly.sa_g, ly.sa_b, ss, 0};
+        LAUNCH(rg_launch_sa_attention(w.big, src_mask, sp, nullptr, rg_out_f32(w.a, D), B, T, 1, st));
+        {
+            RgGemm g = mk_gemm(w.a, D, ly.sa_Wo, ly.sa_bo, w.h, D, M, D, D, RG_EPI_BIAS_RESIDUAL);
+            g.R = w.h; g.ldr = D;
+            LAUNCH(rg_launch_gemm_f32(g, st));
+        }
+        // --- three cross-attentions on the same h
+        LAUNCH(rg_launch_ln_rows(w.h, D, nullptr, nullptr, rg_out_f32(w.a, D), M, st));
+        LAUNCH(rg_launch_gemm_f32(mk_gemm(w.a, D, ly.Wcaq, ly.bcaq, w.big, 3 * D, M, 3 * D, D, RG_EPI_BIAS), st));
+        RgStylParams sp3[3];
+        for (int c = 0; c < 3; ++c) sp3[c] = {ly.ca_g + c * D, ly.ca_b + c * D, ss + (1 + c) * 2 * D, 0};
+        LAUNCH(rg_launch_ca_attention(w.big, 3 * D, state + (long long)l * 3 * HS, clip_stride, HS, query_mask,
+                                      qm_cond_stride, sp3, rg_out_f32(w.a, 3 * D), B, T, 3, st));
+        {
+            RgGemm g = mk_gemm(w.a, 3 * D, ly.ca_Wo, ly.ca_bo, w.o3, 3 * D, M, D, D, RG_EPI_BIAS_RESIDUAL);
+            g.groups = 3; g.a_g = D; g.w_g = (long long)D * D; g.b_g = D; g.c_g = D; g.R = w.h; g.ldr = D; g.r_g = 0;
+            LAUNCH(rg_launch_gemm_f32(g, st));
+        }
+        LAUNCH(rg_launch_gemm_f32(mk_gemm(w.o3, 3 * D, ly.Wmix, ly.bmix, w.h, D, M, D, 3 * D, RG_EPI_BIAS), st));
+        // --- FFN
+        LAUNCH(rg_launch_gemm_f32(mk_gemm(w.h, D, ly.W1, ly.b1, w.g, F, M, F, D, RG_EPI_BIAS_GELU), st));
+        LAUNCH(rg_launch_gemm_f32(mk_gemm(w.g, F, ly.W2, ly.b2, w.y, D, M, D, F, RG_EPI_BIAS), st));
+        RgStylParams spf = {ly.ffn_g, ly.ffn_b, ss + 4 * 2 * D, 0};
+        LAUNCH(rg_launch_styl_rows(w.y, D, spf, T, rg_out_f32(w.a, D), M, st));
+        {
+            RgGemm g = mk_gemm(w.a, D, ly.ffn_Wo, ly.ffn_bo, w.h, D, M, D, D, RG_EPI_BIAS_RESIDUAL);
+            g.R = w.h; g.ldr = D;
+            LAUNCH(rg_launch_gemm_f32(g, st));
+        }
+    }
+    LAUNCH(rg_launch_gemm_f32(mk_gemm(w.h, D, m->W_out, m->b_out, x0_out, D, M, D, D, RG_EPI_BIAS), st));
+    return 0;
 }
 
 extern "C" int rg_denoise(rg_handle m, const float* x, int B, int step_idx, int tau,
@@ -590,8 +670,7 @@ extern "C" int rg_denoise(rg_handle m, const float* x, int B, int step_idx, int 
     if (!m || !x || !src_mask || !state || !x0_out) return rg_fail("rg_denoise: null argument");
     if (B <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    const int D = RG_D, F = m->cfg.ffn_dim, L = m->cfg.num_layers, T = m->cfg.n_tokens;
-    const int M = B * T;
+    const int D = RG_D, L = m->cfg.num_layers, T = m->cfg.n_tokens;
     const long long NT = (long long)L * 5 * 2 * D;
     const float* ssrow;
     if (step_idx >= 0) {
@@ -604,56 +683,43 @@ extern "C" int rg_denoise(rg_handle m, const float* x, int B, int step_idx, int 
         }
         ssrow = m->tau_row;
     }
-    if (ensure_ws(m, M)) return 1;
-    if (m->cfg.precision != RG_PREC_FP32)
-        return denoise_tc(m, x, B, ssrow, src_mask, query_mask, state, x0_out, st);
+    // Lanes: clips are independent, so the batch can be cut into contiguous clip ranges whose kernel chains
+    // run concurrently on separate streams.  Measured on B200 this does NOT pay: the kernels are
+    // bound by shared L2->SM bandwidth, not by launch latency, so "automatic" is one lane; rg_set_lanes
+    // keeps the mechanism available for callers that share the GPU with other work.
+    int lanes = m->lanes > 0 ? m->lanes : 1;
+    if (lanes > RG_MAX_LANES) lanes = RG_MAX_LANES;
+    if (lanes > B) lanes = B;
+    const bool tc = m->cfg.precision != RG_PREC_FP32;
+    if (lanes > 1 && !m->ev_fork) {
+        CU(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+        for (int i = 1; i < RG_MAX_LANES; ++i) {
+            CU(cudaStreamCreateWithFlags(&m->lane_st[i], cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&m->ev_join[i], cudaEventDisableTiming));
+        }
+    }
+    if (lanes > 1) CU(cudaEventRecord(m->ev_fork, st));
     const long long clip_stride = rg_state_floats_per_clip(m);
-    const long long HS = (long long)RG_H * RG_HD * RG_HD;
+    int rc = 0;
+    for (int i = lanes - 1; i >= 0 && !rc; --i) {         // lane 0 (the caller's stream) is enqueued last
+        const int b0 = (int)((long long)B * i / lanes), b1 = (int)((long long)B * (i + 1) / lanes);
+        cudaStream_t ls = i ? m->lane_st[i] : st;
+        if (i) CU(cudaStreamWaitEvent(ls, m->ev_fork, 0));
+        if (ensure_ws(m, m->ws[i], (long long)(b1 - b0) * T)) return 1;
+        const long long r0 = (long long)b0 * T;
+        rc = (tc ? denoise_tc : denoise_f32)(m, m->ws[i], x + r0 * D, b1 - b0, ssrow, src_mask + r0,
+                                             query_mask ? query_mask + r0 : nullptr, (long long)B * T,
+                                             state + b0 * clip_stride, x0_out + r0 * D, ls);
+        if (i) CU(cudaEventRecord(m->ev_join[i], ls));
+    }
+    for (int i = 1; i < lanes; ++i) CU(cudaStreamWaitEvent(st, m->ev_join[i], 0));
+    return rc;
+}
 
-    // h = joint_embed(x) + positional tables
-    {
-        RgGemm g = mk_gemm(x, D, m->W_joint, m->b_joint, m->h, D, M, D, D, RG_EPI_BIAS_POS);
-        g.pos = m->pos; g.pos_T = T;
-        LAUNCH(rg_launch_gemm_f32(g, st));
-    }
-    for (int l = 0; l < L; ++l) {
-        const Layer& ly = m->layers[l];
-        const float* ss = ssrow + (long long)l * 5 * 2 * D;
-        // --- self-attention
-        LAUNCH(rg_launch_ln_rows(m->h, D, nullptr, nullptr, rg_out_f32(m->a, D), M, st));
-        LAUNCH(rg_launch_gemm_f32(mk_gemm(m->a, D, ly.Wqkv, ly.bqkv, m->big, 3 * D, M, 3 * D, D, RG_EPI_BIAS), st));
-        RgStylParams sp = {ly.sa_g, ly.sa_b, ss, 0};
-        LAUNCH(rg_launch_sa_attention(m->big, src_mask, sp, nullptr, rg_out_f32(m->a, D), B, T, 1, st));
-        {
-            RgGemm g = mk_gemm(m->a, D, ly.sa_Wo, ly.sa_bo, m->h, D, M, D, D, RG_EPI_BIAS_RESIDUAL);
-            g.R = m->h; g.ldr = D;
-            LAUNCH(rg_launch_gemm_f32(g, st));
-        }
-        // --- three cross-attentions on the same h
-        LAUNCH(rg_launch_ln_rows(m->h, D, nullptr, nullptr, rg_out_f32(m->a, D), M, st));
-        LAUNCH(rg_launch_gemm_f32(mk_gemm(m->a, D, ly.Wcaq, ly.bcaq, m->big, 3 * D, M, 3 * D, D, RG_EPI_BIAS), st));
-        RgStylParams sp3[3];
-        for (int c = 0; c < 3; ++c) sp3[c] = {ly.ca_g + c * D, ly.ca_b + c * D, ss + (1 + c) * 2 * D, 0};
-        LAUNCH(rg_launch_ca_attention(m->big, 3 * D, state + (long long)l * 3 * HS, clip_stride, HS, query_mask,
-                                      (long long)B * T, sp3, rg_out_f32(m->a, 3 * D), B, T, 3, st));
-        {
-            RgGemm g = mk_gemm(m->a, 3 * D, ly.ca_Wo, ly.ca_bo, m->o3, 3 * D, M, D, D, RG_EPI_BIAS_RESIDUAL);
-            g.groups = 3; g.a_g = D; g.w_g = (long long)D * D; g.b_g = D; g.c_g = D; g.R = m->h; g.ldr = D; g.r_g = 0;
-            LAUNCH(rg_launch_gemm_f32(g, st));
-        }
-        LAUNCH(rg_launch_gemm_f32(mk_gemm(m->o3, 3 * D, ly.Wmix, ly.bmix, m->h, D, M, D, 3 * D, RG_EPI_BIAS), st));
-        // --- FFN
-        LAUNCH(rg_launch_gemm_f32(mk_gemm(m->h, D, ly.W1, ly.b1, m->g, F, M, F, D, RG_EPI_BIAS_GELU), st));
-        LAUNCH(rg_launch_gemm_f32(mk_gemm(m->g, F, ly.W2, ly.b2, m->y, D, M, D, F, RG_EPI_BIAS), st));
-        RgStylParams spf = {ly.ffn_g, ly.ffn_b, ss + 4 * 2 * D, 0};
-        LAUNCH(rg_launch_styl_rows(m->y, D, spf, T, rg_out_f32(m->a, D), M, st));
-        {
-            RgGemm g = mk_gemm(m->a, D, ly.ffn_Wo, ly.ffn_bo, m->h, D, M, D, D, RG_EPI_BIAS_RESIDUAL);
-            g.R = m->h; g.ldr = D;
-            LAUNCH(rg_launch_gemm_f32(g, st));
-        }
-    }
-    LAUNCH(rg_launch_gemm_f32(mk_gemm(m->h, D, m->W_out, m->b_out, x0_out, D, M, D, D, RG_EPI_BIAS), st));
+extern "C" int rg_set_lanes(rg_handle m, int lanes) {
+    if (!m) return rg_fail("rg_set_lanes: null handle");
+    if (lanes < 0 || lanes > RG_MAX_LANES) return rg_fail("rg_set_lanes: lanes must be 0 (auto) .. %d", RG_MAX_LANES);
+    m->lanes = lanes;
     return 0;
 }
 
@@ -779,6 +845,40 @@ extern "C" int rg_probe_gemm_tc(const float* x, const float* W, const float* b, 
     cudaFree(a16); cudaFree(w16);
     return 0;
 }
+extern "C" int rg_probe_gemm_trace(int M, int N, int K, int split, int with_pdl_pred, int64_t* trace_host,
+                                   int64_t n_trace, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N % 128 || K % 64) return rg_fail("rg_probe_gemm_trace: bad shape");
+    const int planes = split ? 2 : 1;
+    const long long ctas = (long long)(N / 128) * ((M + 127) / 128);
+    if (n_trace < ctas * 10) return rg_fail("rg_probe_gemm_trace: trace buffer needs %lld entries", ctas * 10);
+    void *a16 = nullptr, *w16 = nullptr; float *out = nullptr, *res = nullptr; long long* tr = nullptr;
+    CU(cudaMalloc(&a16, (size_t)M * K * planes * 2));
+    CU(cudaMalloc(&w16, (size_t)N * K * planes * 2));
+    CU(cudaMalloc(&out, (size_t)M * N * 4));
+    CU(cudaMalloc(&res, (size_t)M * N * 4));
+    CU(cudaMalloc(&tr, (size_t)ctas * 10 * 8));
+    CU(cudaMemset(a16, 0, (size_t)M * K * planes * 2));
+    CU(cudaMemset(w16, 0, (size_t)N * K * planes * 2));
+    CU(cudaMemset(res, 0, (size_t)M * N * 4));
+    CUtensorMap tmA, tmW;
+    CU(rg_make_tensor_map(&tmA, a16, M, (long long)K * planes, (long long)K * planes, 128));
+    CU(rg_make_tensor_map(&tmW, w16, N, (long long)K * planes, (long long)K * planes, 128));
+    RgGemmTc p;
+    memset(&p, 0, sizeof(p));
+    p.M = M; p.N = N; p.K = K; p.split = split ? 1 : 0; p.a_lo_off = K; p.w_lo_off = K; p.groups = 1;
+    p.R = res; p.ldr = N; p.C32 = out; p.ldc32 = N; p.epi = RG_EPI_BIAS_RESIDUAL;
+    for (int i = 0; i < 4; ++i) {
+        // a predecessor in the chain (a row kernel rewriting A's producer buffer) so PDL overlap is as in rg_denoise
+        if (with_pdl_pred) LAUNCH(rg_launch_ln_rows(res, N, nullptr, nullptr, rg_out_f32(out, N), M < 64 ? M : 64, st));
+        p.trace = i == 3 ? tr : nullptr;
+        LAUNCH(rg_launch_gemm_tc(tmA, tmW, p, st));
+    }
+    CU(cudaStreamSynchronize(st));
+    CU(cudaMemcpy(trace_host, tr, (size_t)ctas * 10 * 8, cudaMemcpyDeviceToHost));
+    cudaFree(a16); cudaFree(w16); cudaFree(out); cudaFree(res); cudaFree(tr);
+    return 0;
+}
 extern "C" int rg_op_layernorm(const float* x, const float* gamma, const float* beta, float* out,
                                int M, void* stream) {
     LAUNCH(rg_launch_ln_rows(x, RG_D, gamma, beta, rg_out_f32(out, RG_D), M, (cudaStream_t)stream));
@@ -814,6 +914,22 @@ extern "C" int rg_op_cross_attention(const float* q, const float* state, const f
     sp[1] = sp[0]; sp[2] = sp[0];
     LAUNCH(rg_launch_ca_attention(q, RG_D, state, (long long)RG_H * RG_HD * RG_HD, 0, query_mask, 0, sp,
                                   rg_out_f32(out, RG_D), B, T, 1, (cudaStream_t)stream));
+    return 0;
+}
+extern "C" int rg_op_self_attention_core(const float* qkv, const float* src_mask, float* y, int B, int T, int mode,
+                                         void* stream) {
+    if (!qkv || !src_mask || !y) return rg_fail("rg_op_self_attention_core: null argument");
+    if (mode < 0 || mode > 2) return rg_fail("rg_op_self_attention_core: mode must be 0, 1 or 2");
+    LAUNCH(rg_launch_sa_core(qkv, src_mask, y, B, T, mode, (cudaStream_t)stream));
+    return 0;
+}
+extern "C" int rg_op_cross_attention_core(const float* q3, const float* state, const float* query_mask, float* y,
+                                          int B, int T, int mode, void* stream) {
+    if (!q3 || !state || !y) return rg_fail("rg_op_cross_attention_core: null argument");
+    if (mode < 0 || mode > 2) return rg_fail("rg_op_cross_attention_core: mode must be 0, 1 or 2");
+    const long long HS = (long long)RG_H * RG_HD * RG_HD;
+    LAUNCH(rg_launch_ca_core(q3, 3 * RG_D, state, 3 * HS, HS, query_mask, (long long)B * T, y, 3 * RG_D, B, T, mode,
+                             (cudaStream_t)stream));
     return 0;
 }
 extern "C" int rg_op_kv_state(const float* kv, int n_tokens, int B, float* state, void* stream) {

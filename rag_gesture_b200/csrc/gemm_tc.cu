@@ -111,6 +111,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     rg_pdl_launch();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    long long* tr = p.trace ? p.trace + ((long long)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 10 : nullptr;
+#define RG_STAMP(slot) do { if (tr) tr[slot] = clock64(); } while (0)
+    if (tr && threadIdx.x == 0) {
+        unsigned long long gt; unsigned sm;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+        tr[0] = clock64(); tr[8] = (long long)gt; tr[9] = sm;
+    }
     const int g = blockIdx.z;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const int nkb = p.K / BK;
@@ -134,6 +142,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_smem;
+    if (threadIdx.x == 0) RG_STAMP(1);
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -155,6 +164,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tma_load_2d(smem_u32(smem + j * STAGE_BYTES) + A_BYTES, &tmW, smem_u32(&full_bar[j]), kw, w_n0);
             }
             rg_pdl_wait();
+            RG_STAMP(2);
             for (int j = 0; j < pre; ++j) {
                 int ka, kw;
                 coords(j, ka, kw);
@@ -179,13 +189,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(smem_u32(&full_bar[s]), ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (elect_one()) {
+                if (j == 0) RG_STAMP(3);
                 const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
                 const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sb);
 #pragma unroll
                 for (int k = 0; k < BK / UMMA_K; ++k)      // +32 B per UMMA_K inside the 128 B swizzle row
                     umma_bf16(tmem_base, da + (k * UMMA_K * 2 >> 4), db + (k * UMMA_K * 2 >> 4), idesc, (j | k) != 0);
                 umma_commit(smem_u32(&empty_bar[s]));                   // frees the smem slot when the MMAs retire
-                if (j == total_kb - 1) umma_commit(smem_u32(&tmem_full_bar));
+                if (j == total_kb - 1) { umma_commit(smem_u32(&tmem_full_bar)); RG_STAMP(4); }
             }
             __syncwarp();
         }
@@ -201,6 +212,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         rg_pdl_wait();          // residual reads and all stores below touch buffers of the previous kernel
         mbar_wait(smem_u32(&tmem_full_bar), 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (threadIdx.x == 64) RG_STAMP(5);
         const int lg = warp & 3;                                        // TMEM lane group of this warp
         const int half = (warp - 2) >> 2;                               // which half of the tile's columns
         constexpr int HC = BN / 2, PITCH = HC + 4;
@@ -217,6 +229,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                                                   __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
         }
         __syncwarp();
+        if (threadIdx.x == 64) RG_STAMP(6);
         const int tcol = half * HC;                                     // first column of this warp inside the tile
         const float* bias = p.bias ? p.bias + g * p.b_goff + n0 + tcol : nullptr;
         const int cbase = g * p.c_goff + n0 + tcol;                     // ... in C
@@ -276,6 +289,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             }
         }
+        if (threadIdx.x == 64) RG_STAMP(7);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -283,10 +297,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN));
     }
+#undef RG_STAMP
 }
 
 // fp32 -> bf16 hi (and lo = bf16(x - hi)) planes; row-major, lo plane at column offset lo_off (0 = none)
-__global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ x, int ldx,
+__global__ void __launch_bounds__(256) split_bf16_kernel(const float* x, int ldx,
                                                         __nv_bfloat16* __restrict__ out, int ldo, int lo_off,
                                                         long long rows, int cols) {
     rg_pdl_launch();
@@ -362,11 +377,15 @@ cudaError_t rg_launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmW, co
 }
 
 cudaError_t rg_launch_split_bf16(const float* x, int ldx, void* out, int ldo, int lo_off, long long rows, int cols,
-                                 cudaStream_t st) {
+                                 cudaStream_t st, bool pdl) {
     if (rows <= 0) return cudaSuccess;
     if (cols % 4 || ldx % 4 || ldo % 4 || lo_off % 4) return cudaErrorInvalidValue;
     const long long n4 = rows * (cols / 4);
     const int blocks = (int)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
+    if (!pdl) {
+        split_bf16_kernel<<<blocks, 256, 0, st>>>(x, ldx, reinterpret_cast<__nv_bfloat16*>(out), ldo, lo_off, rows, cols);
+        return cudaGetLastError();
+    }
     return rg_launch_pdl(split_bf16_kernel, dim3(blocks), dim3(256), 0, st, x, ldx, reinterpret_cast<__nv_bfloat16*>(out),
                          ldo, lo_off, rows, cols);
 }

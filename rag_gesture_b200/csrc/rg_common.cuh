@@ -88,10 +88,10 @@ cudaError_t rg_launch_ca_attention(const float* q3, int ldq, const float* state,
                                    const float* qmask, long long qmask_cond_stride,
                                    const RgStylParams* sp3, RgRowOut out, int B, int T,
                                    int n_cond, cudaStream_t st);
-cudaError_t rg_launch_sa_core(const float* qkv, const float* src_mask, float* Y, int B, int T, cudaStream_t st);
+cudaError_t rg_launch_sa_core(const float* qkv, const float* src_mask, float* Y, int B, int T, int mode, cudaStream_t st);
 cudaError_t rg_launch_ca_core(const float* q3, int ldq, const float* state, long long state_clip_stride,
                               long long state_cond_stride, const float* qmask, long long qmask_cond_stride,
-                              float* Y, int ldy, int B, int T, cudaStream_t st);
+                              float* Y, int ldy, int B, int T, int mode, cudaStream_t st);
 cudaError_t rg_launch_styl_rows3(const float* y, int ldy, const RgStylParams* sp3, int rows_per_clip,
                                  RgRowOut out, int M, cudaStream_t st);
 cudaError_t rg_launch_kv_state(const float* kv, int ldkv, int k_off, int v_off, int n_tokens,
@@ -106,6 +106,11 @@ cudaError_t rg_launch_kv_state(const float* kv, int ldkv, int k_off, int v_off, 
 // instructions are no-ops.
 #ifdef __CUDACC__
 __device__ __forceinline__ void rg_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// RULE for every kernel launched with PDL: pointers to data the PREVIOUS kernel may have produced must not
+// be `const T* __restrict__`.  Such loads compile to ld.global.nc, which nvcc/ptxas treat as invariant and
+// hoist ABOVE griddepcontrol.wait -- reading the predecessor's output before it is written (seen on
+// sa_core_mma_kernel).  Plain loads are ordered by the "memory" clobber below.  tools/pdl_lint.py checks the
+// SASS of every kernel for global loads ahead of the wait and runs in the CPU test suite (tests/test_abi.py).
 __device__ __forceinline__ void rg_pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 template <typename... KArgs, typename... Args>

@@ -17,10 +17,12 @@ struct RgGemmTc {
     int c16_lo_off;
     int epi;                  // RgEpilogue
     int no_pdl;               // 1: W was produced by the preceding kernel -> plain (fully serialised) launch
+    long long* trace;         // diagnostics: 10 clock64/globaltimer stamps per CTA (rg_probe_gemm_trace), else null
 };
 
 cudaError_t rg_make_tensor_map(CUtensorMap* tm, const void* ptr, long long rows, long long cols, long long ld,
                                int box_rows);
 cudaError_t rg_launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmW, const RgGemmTc& p, cudaStream_t st);
+// pdl = false: plain launch, i.e. the kernel starts only after everything enqueued before it has completed
 cudaError_t rg_launch_split_bf16(const float* x, int ldx, void* out, int ldo, int lo_off, long long rows, int cols,
-                                 cudaStream_t st);
+                                 cudaStream_t st, bool pdl = true);

@@ -12,7 +12,7 @@ namespace {
 
 constexpr int ROWS_PER_BLOCK = 8;   // 8 warps
 
-__global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ x, int ldx,
+__global__ void __launch_bounds__(256) ln_rows_kernel(const float* x, int ldx,
                                                      const float* __restrict__ gamma,
                                                      const float* __restrict__ beta,
                                                      RgRowOut out, int M) {
@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ 
 // Each warp takes RPW consecutive rows and keeps the block's 4 x 2 KB of parameters (gamma, beta, scale,
 // shift) in registers across them: re-reading them per row made this kernel move 5x its data.
 constexpr int RPW = 4;
-__global__ void __launch_bounds__(128) styl_rows_kernel(const float* __restrict__ y, int ldy,
+__global__ void __launch_bounds__(128) styl_rows_kernel(const float* y, int ldy,
                                                        RgStylParams sp, int rows_per_clip,
                                                        RgRowOut out, int M) {
     rg_pdl_launch();
@@ -130,8 +130,8 @@ __global__ void __launch_bounds__(256) ddim_update_kernel(const float4* x, const
 
 // rows where in_seq has any non-zero entry are replaced by q_sample(in_seq, t, noise)
 __global__ void __launch_bounds__(256) blend_kernel(const float* x,
-                                                   const float* __restrict__ in_seq,
-                                                   const float* __restrict__ noise,
+                                                   const float* in_seq,
+                                                   const float* noise,
                                                    float* out, long long rows,
                                                    float s_ab, float s_1mab) {
     rg_pdl_launch();
@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(256) blend_kernel(const float* x,
 
 // `iters` steps of x <- x - lr * d/dx mse(x*m, in_seq) = x - (2 lr / numel) * m * (x*m - in_seq)
 __global__ void __launch_bounds__(256) guidance_kernel(float* __restrict__ x,
-                                                      const float* __restrict__ in_seq,
+                                                      const float* in_seq,
                                                       long long rows, int iters, float c) {
     const long long row = (long long)blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;

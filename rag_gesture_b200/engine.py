@@ -105,6 +105,10 @@ class DenoiserEngine:
                 xs.shape[1], B, _lib.ptr(state), _lib.stream_ptr()))
         return state.view(B, self.num_layers, 3, CFG.NUM_HEADS, 32, 32)
 
+    def set_lanes(self, lanes):
+        """Concurrent clip-range chains per denoise call: 0 = automatic, 1..4 fixed (rg_set_lanes)."""
+        _lib.check(self.lib.rg_set_lanes(self._h, int(lanes)))
+
     # -- per step -----------------------------------------------------------------------------------
     def denoise(self, x, src_mask, query_mask, state, step_idx=-1, tau=0, out=None):
         """x0 = model(x, t) for B clips sharing one timestep.  query_mask: [3,B,T] tensor or None."""

@@ -101,6 +101,29 @@ def cross_attention(q, state, query_mask, gamma, beta, ss):
     return out
 
 
+def self_attention_core(qkv, src_mask, mode=0):
+    """qkv [B,T,1536], src_mask [B,T] -> Y [B,T,512] before the Stylization prologue.
+    mode 0: fp32 FMA, 1: TF32 mma.sync, 2: 3xTF32 (hi/lo split)."""
+    qkv, src_mask = _prep(qkv, src_mask)
+    B, T = qkv.shape[0], qkv.shape[1]
+    out = torch.empty(B, T, D, device=qkv.device)
+    with torch.cuda.device(qkv.device):
+        _lib.check(_lib.load().rg_op_self_attention_core(_lib.ptr(qkv), _lib.ptr(src_mask), _lib.ptr(out), B, T,
+                                                         int(mode), _lib.stream_ptr()))
+    return out
+
+
+def cross_attention_core(q3, state, query_mask, mode=0):
+    """q3 [B,T,1536] (three conditions), state [B,3,16,32,32], query_mask [3,B,T] or None -> Y [B,T,1536]."""
+    q3, state, query_mask = _prep(q3, state, query_mask)
+    B, T = q3.shape[0], q3.shape[1]
+    out = torch.empty(B, T, 3 * D, device=q3.device)
+    with torch.cuda.device(q3.device):
+        _lib.check(_lib.load().rg_op_cross_attention_core(_lib.ptr(q3), _lib.ptr(state), _lib.ptr(query_mask),
+                                                          _lib.ptr(out), B, T, int(mode), _lib.stream_ptr()))
+    return out
+
+
 def kv_state(kv, B, n_tokens):
     """kv [B*N,1024] = [key | value] projections -> state [B,16,32,32]."""
     (kv,) = _prep(kv)

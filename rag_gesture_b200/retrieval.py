@@ -352,6 +352,35 @@ class RetrievalDatabase(nn.Module):
         self._sense_index = build_sense_index(self.idx_2_sense)
         self._sense_tables = ({}, {})      # (sense -> SenseTable, connective -> id)
         self._index, self._index_device = None, device
+        self._corpus, self._corpus_rows = None, None
+        self.corpus_budget_bytes = 64 << 30     # exemplar fields kept in HBM when the corpus fits
+
+    EXEMPLAR_KEYS = ("motion_upper", "motion_lower", "motion_face", "motion_hands", "trans", "facial", "contact",
+                     "motion_mask", "word", "audio", "speaker_id", "motion")
+
+    def exemplar_corpus(self, device):
+        """The exemplar fields of every database clip as [N_db, ...] device tensors, uploaded once (like the
+        text index): fetching the E exemplars of a batch is then one gather per field in HBM instead of E
+        dataset reads + a host stack + a pageable H2D copy per batch.  A real BEAT2 corpus is a few GB of
+        fp32 features; above `corpus_budget_bytes` the per-batch host path is used instead (returns None)."""
+        dev = torch.device(device)
+        if self._corpus is not None:
+            have = self._corpus["motion"].device
+            if have.type == dev.type and (dev.index is None or dev.index == have.index):
+                return self._corpus
+        names = list(self.idx_2_text.keys())
+        first = self.dataset[names[0]]
+        per_clip = sum(first[k].numel() * first[k].element_size() for k in self.EXEMPLAR_KEYS)
+        if per_clip * len(names) > self.corpus_budget_bytes:
+            return None
+        corpus = {k: torch.empty((len(names),) + tuple(first[k].shape), dtype=first[k].dtype, device=device)
+                  for k in self.EXEMPLAR_KEYS}
+        for lo in range(0, len(names), 64):                       # bounded host staging
+            smps = [self.dataset[nm] for nm in names[lo:lo + 64]]
+            for k in self.EXEMPLAR_KEYS:
+                corpus[k][lo:lo + len(smps)] = torch.stack([s_[k] for s_ in smps], 0).to(device)
+        self._corpus, self._corpus_rows = corpus, {nm: i for i, nm in enumerate(names)}
+        return corpus
 
     def text_index(self, device):
         if self._index is None or torch.device(self._index.device).type != torch.device(device).type:
@@ -478,10 +507,14 @@ class RetrievalDatabase(nn.Module):
         assert gesture_rep_encoder is not None or not jobs
         ex = {}
         if jobs:
-            smps = [self.dataset[name] for _, _, name in jobs]
-            keys = ("motion_upper", "motion_lower", "motion_face", "motion_hands", "trans", "facial", "contact",
-                    "motion_mask", "word", "audio", "speaker_id", "motion")
-            ex = {k: torch.stack([s_[k] for s_ in smps], 0).to(device, non_blocking=True) for k in keys}
+            keys = self.EXEMPLAR_KEYS
+            corpus = self.exemplar_corpus(device) if torch.device(device).type == "cuda" else None
+            if corpus is not None:
+                rows = torch.tensor([self._corpus_rows[name] for _, _, name in jobs], device=device)
+                ex = {k: corpus[k].index_select(0, rows) for k in keys}
+            else:
+                smps = [self.dataset[name] for _, _, name in jobs]
+                ex = {k: torch.stack([s_[k] for s_ in smps], 0).to(device, non_blocking=True) for k in keys}
             args = [ex[k] for k in keys[:8]]
             if hasattr(gesture_rep_encoder, "encode_many"):
                 lat_all, mask_all = gesture_rep_encoder.encode_many(*args)

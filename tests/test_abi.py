@@ -78,3 +78,21 @@ def test_registry_and_constructor_surface():
     reg = R.mogen_api.Registry("foreign")
     R.register_into(reg)
     assert reg.get("ReGestureTransformer") is R.ReGestureTransformer
+
+
+def test_no_global_load_above_pdl_wait():
+    """SASS lint (tools/pdl_lint.py): in every kernel that executes griddepcontrol.wait no global load is
+    scheduled ahead of it.  nvcc hoists ld.global.nc (`const T* __restrict__`) above the wait, which made a
+    PDL-launched kernel read its predecessor's output before it was written."""
+    import shutil
+    import sys
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import pdl_lint
+    from rag_gesture_b200 import build
+    report = pdl_lint.scan(build.lib_path() if hasattr(build, "lib_path") else os.path.join(
+        os.path.dirname(os.path.abspath(build.__file__)), "librg_b200.so"))
+    assert len(report) >= 10, "expected the PDL kernels of the step chain in the library"
+    bad = {k: v[:2] for k, v in report.items() if v and not any(a in k for a in pdl_lint.ALLOWED)}
+    assert not bad, bad

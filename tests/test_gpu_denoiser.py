@@ -293,3 +293,28 @@ def test_state_cache_is_not_reused_across_batches(model, dev):
     with torch.no_grad():
         fresh = model(x, torch.full((B,), 300, device=dev), **kw)
     assert torch.equal(outs[1], fresh) and torch.equal(outs[0], outs[2]) and not torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("which", ["fp32", "tc"])
+def test_lanes_do_not_change_results(which, model, tc_model, diffusion, dev):
+    """rg_set_lanes: cutting the batch into 1..4 concurrent clip-range chains is bit-identical
+    (ragged split 7 = 2+2+3 / 1+2+2+2 included), also across consecutive steps reusing the workspaces."""
+    mdl = model if which == "fp32" else tc_model[0]
+    eng = mdl.rg_engine(diffusion)
+    B = 7
+    kw = _kw(mdl, S.synthetic_conditions(B, seed=91), B, dev)
+    x = S.synthetic_latents(B, seed=92).to(dev)
+    outs = []
+    try:
+        for lanes in (1, 2, 3, 4, 0):
+            eng.set_lanes(lanes)
+            with torch.no_grad():
+                y = mdl(x, torch.full((B,), 300, device=dev), **kw)
+                y = mdl(y, torch.full((B,), 280, device=dev), **kw)
+            outs.append(y.clone())
+    finally:
+        eng.set_lanes(0)
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+    with pytest.raises(RuntimeError):
+        eng.set_lanes(9)

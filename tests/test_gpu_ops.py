@@ -193,3 +193,51 @@ def test_guidance_step_closed_form(dev, sd0):
     assert rel_l2(out, cur.detach()) < 1e-6
     assert torch.equal(out[~mask], x[~mask])
     eng.close()
+
+
+def _sa_core_ref(qkv, mask):
+    """float64 restatement of EfficientSelfAttention's core (efficient_attention.py:146-160)."""
+    B, T, _ = qkv.shape
+    q, k, v = [t.double().view(B, T, 16, 32) for t in qkv.split(512, dim=-1)]
+    m = mask.double().view(B, T, 1, 1)
+    k = torch.softmax(k + (1 - m) * -1000000.0, dim=1)
+    q = torch.softmax(q, dim=-1)
+    A = torch.einsum("bnhd,bnhl->bhdl", k, v * m)
+    return torch.einsum("bnhd,bhdl->bnhl", q, A).reshape(B, T, 512)
+
+
+@pytest.mark.parametrize("T", [3, 11, 23, 43, 49, 64])
+def test_attention_cores_mma_vs_fp32(dev, T):
+    """The mma.sync cores (TF32 and 3xTF32) against the fp32 cores and a float64 formula, for every
+    tile count MT = ceil(T/16) and ragged last tiles; masked key tokens and masked query rows included."""
+    from rag_gesture_b200 import ops
+    B = 5
+    g = torch.Generator().manual_seed(100 + T)
+    qkv = torch.randn(B, T, 1536, generator=g).to(dev)
+    mask = (torch.rand(B, T, generator=g) > 0.2).float()
+    mask[0] = 1
+    mask[:, 0] = 1
+    mask = mask.to(dev)
+    ref = _sa_core_ref(qkv, mask)
+    y0 = ops.self_attention_core(qkv, mask, 0)
+    for mode, tol in ((1, 2e-3), (2, 3e-6)):
+        y = ops.self_attention_core(qkv, mask, mode)
+        e, e0 = rel_l2(y.double(), ref), rel_l2(y0.double(), ref)
+        print(f"T={T} self core mode {mode}: rel-L2 vs f64 {e:.2e} (fp32 core {e0:.2e})")
+        assert e < tol and e0 < 3e-6
+    q3 = torch.randn(B, T, 1536, generator=g).to(dev)
+    state = (torch.randn(B, 3, 16, 32, 32, generator=g) * 0.1).to(dev)
+    qm = (torch.rand(3, B, T, generator=g) > 0.1).float().to(dev)
+    p = torch.softmax(q3.double().view(B, T, 3, 16, 32), dim=-1)
+    ref = torch.einsum("bnchd,bchdl->bnchl", p, state.double()).reshape(B, T, 1536)
+    for qmask in (None, qm):
+        z0 = ops.cross_attention_core(q3, state, qmask, 0)
+        for mode, tol in ((1, 2e-3), (2, 3e-6)):
+            z = ops.cross_attention_core(q3, state, qmask, mode)
+            if qmask is None:
+                assert rel_l2(z.double(), ref) < tol and rel_l2(z0.double(), ref) < 3e-6
+            else:
+                keep = qmask.permute(1, 2, 0).reshape(B, T, 3, 1).expand(B, T, 3, 512).reshape(B, T, 1536) > 0
+                assert rel_l2(z[keep].double(), ref[keep]) < tol
+                # masked rows: y - 1e6 in fp32, a 1/16 grid -> identical to the fp32 core unless y sits on a tie
+                assert (z[~keep] == z0[~keep]).float().mean() > 0.99 and (z[~keep] < -9e5).all()

@@ -168,3 +168,29 @@ def test_longform_prev_latent_chain(arch, dev):
     errs = (rel_l2(outs[0], torch.from_numpy(g["chain_w0"])), rel_l2(outs[1], torch.from_numpy(g["chain_w1"])))
     print("prev-latent chain (fp32 tier) rel-L2 vs reference: window 0 %.3g, window 1 %.3g" % errs)
     assert max(errs) < 1e-3
+
+
+def test_resident_corpus_matches_host_fetch(arch, dev):
+    """The HBM-resident exemplar corpus (one gather per field) yields the same prepared batch as the
+    per-batch host fetch + stack + H2D path it replaces."""
+    qs = S.SyntheticGestureDataset(N_QUERY, seed=8)
+    db = arch.model.database
+    gbs = []
+    for budget in (0, 64 << 30):
+        db.corpus_budget_bytes, db._corpus = budget, None
+        for d in (db.test_indexes, db.test_dbounds, db.test_qbounds):
+            d.clear()
+        batch = S.collate([qs[i] for i in [1, 2, 4, 7]])
+        batch["retrieval_method"] = "discourse"
+        batch["inference_kwargs"] = dict(use_inversion=True, insertion_guidance=True,
+                                         guidance_iters=[0] * 25 + list(range(25)), guidance_lr=0.1)
+        torch.manual_seed(5)
+        gbs.append(arch.prepare(**batch))
+        assert (db._corpus is None) == (budget == 0)
+    a, b = gbs
+    assert a.jobs == b.jobs and len(a.jobs) > 0 and a.windows == b.windows
+    for k in a.ex:
+        assert torch.equal(a.ex[k], b.ex[k]), k
+    ra, rb = a.model_kwargs["re_dict"], b.model_kwargs["re_dict"]
+    for k in ("raw_motion_latents", "raw_motion", "raw_trans", "raw_facial", "re_mask"):
+        assert torch.equal(ra[k], rb[k]), k

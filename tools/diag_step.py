@@ -44,6 +44,11 @@ for B in [int(b) for b in os.environ.get('DIAG_B', '64,96,160').split(',')]:
     sm = S.motion_mask(B).to(dev)
     qm = torch.stack([S.query_masks(B)[c] for c in C.CONDS], 0).to(dev).contiguous()
     out = torch.empty_like(x)
+    for lanes in [int(v) for v in os.environ.get("DIAG_LANES", "1,2,3,4").split(",")]:
+        eng.set_lanes(lanes)
+        t_dn, t_cpu = ev_time(lambda: eng.denoise(x, sm, qm, state, step_idx=10, out=out), reps)
+        print(f"B={B:4d} lanes={lanes}: rg_denoise {t_dn:7.3f} ms GPU ({t_cpu:6.3f} ms host enqueue)")
+    eng.set_lanes(0)
     t_dn, t_cpu = ev_time(lambda: eng.denoise(x, sm, qm, state, step_idx=10, out=out), reps)
     t_up, _ = ev_time(lambda: eng.ddim_update(x, out, 10, -1, out=out), reps)
     print(f"B={B:4d}: rg_denoise {t_dn:7.3f} ms GPU ({t_cpu:6.3f} ms host enqueue) = "
