@@ -148,8 +148,9 @@ int rg_probe_gemm_tc(const float* x, const float* W, const float* b, float* out,
 /* Diagnostics: one traced launch of the tcgen05 GEMM on zero operands (after 3 untraced ones).  trace_host
  * receives 10 int64 per CTA (grid order x-fastest): clock64 at [0] entry, [1] prologue done, [2] producer
  * past griddepcontrol.wait, [3] first operand stage landed, [4] last MMA committed, [5] accumulator visible
- * to the epilogue, [6] TMEM drained to smem, [7] all stores issued; [8] globaltimer ns at entry, [9] SM id. */
-int rg_probe_gemm_trace(int M, int N, int K, int split, int with_pdl_pred, int64_t* trace_host,
+ * to the epilogue, [6] TMEM drained to smem, [7] all stores issued; [8] globaltimer ns at entry, [9] SM id.
+ * epilogue 0: bias -> fp32; 1: bias + fp32 residual -> fp32; 2: bias + GELU -> bf16 planes. */
+int rg_probe_gemm_trace(int M, int N, int K, int split, int epilogue, int64_t* trace_host,
                         int64_t n_trace, void* stream);
 /* LayerNorm over 512-wide rows, eps 1e-5; gamma/beta may be NULL (no affine). */
 int rg_op_layernorm(const float* x, const float* gamma, const float* beta, float* out, int M,

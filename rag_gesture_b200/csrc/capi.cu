@@ -845,7 +845,7 @@ extern "C" int rg_probe_gemm_tc(const float* x, const float* W, const float* b, 
     cudaFree(a16); cudaFree(w16);
     return 0;
 }
-extern "C" int rg_probe_gemm_trace(int M, int N, int K, int split, int with_pdl_pred, int64_t* trace_host,
+extern "C" int rg_probe_gemm_trace(int M, int N, int K, int split, int epilogue, int64_t* trace_host,
                                    int64_t n_trace, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (N % 128 || K % 64) return rg_fail("rg_probe_gemm_trace: bad shape");
@@ -867,10 +867,10 @@ extern "C" int rg_probe_gemm_trace(int M, int N, int K, int split, int with_pdl_
     RgGemmTc p;
     memset(&p, 0, sizeof(p));
     p.M = M; p.N = N; p.K = K; p.split = split ? 1 : 0; p.a_lo_off = K; p.w_lo_off = K; p.groups = 1;
-    p.R = res; p.ldr = N; p.C32 = out; p.ldc32 = N; p.epi = RG_EPI_BIAS_RESIDUAL;
+    p.C32 = out; p.ldc32 = N; p.epi = RG_EPI_BIAS;
+    if (epilogue == 1) { p.R = res; p.ldr = N; p.epi = RG_EPI_BIAS_RESIDUAL; }
+    if (epilogue == 2) { p.C32 = nullptr; p.C16_ = res; p.ldc16 = N * planes; p.c16_lo_off = split ? N : 0; p.epi = RG_EPI_BIAS_GELU; }
     for (int i = 0; i < 4; ++i) {
-        // a predecessor in the chain (a row kernel rewriting A's producer buffer) so PDL overlap is as in rg_denoise
-        if (with_pdl_pred) LAUNCH(rg_launch_ln_rows(res, N, nullptr, nullptr, rg_out_f32(out, N), M < 64 ? M : 64, st));
         p.trace = i == 3 ? tr : nullptr;
         LAUNCH(rg_launch_gemm_tc(tmA, tmW, p, st));
     }

@@ -99,7 +99,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t v[32]) {
 
 // STAGES = 3: two CTAs per SM (grids above one wave); STAGES = 6: one CTA per SM with the whole K = 512
 // reduction in flight (small grids, where a tile's latency, not throughput, is what is measured).
-template <int BN, int STAGES>
+template <int BN, int STAGES, int EPI>
 __global__ void __launch_bounds__(320, STAGES <= 3 ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, RgGemmTc p) {
     extern __shared__ uint8_t smem_raw[];
@@ -230,61 +230,65 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         __syncwarp();
         if (threadIdx.x == 64) RG_STAMP(6);
+        // Row pass: 16 lanes x float4 cover the warp's 64 columns, so one instruction handles TWO rows and
+        // every global access is a 256-byte (fp32) / 128-byte (bf16) contiguous run.  The epilogue kind is a
+        // template parameter: this loop is ALU-bound (8 warps finish a 128x128 tile), branches and 64-bit
+        // address arithmetic per element were most of its instructions.
+        static_assert(HC == 64, "row pass assumes 64 columns per epilogue warp");
+        const int sub = lane >> 4, cc = (lane & 15) * 4;
         const int tcol = half * HC;                                     // first column of this warp inside the tile
-        const float* bias = p.bias ? p.bias + g * p.b_goff + n0 + tcol : nullptr;
-        const int cbase = g * p.c_goff + n0 + tcol;                     // ... in C
-        const int rbase = (p.r_grouped ? g * p.c_goff : 0) + n0 + tcol; // ... in R
-        constexpr int NV = HC / 64;                                     // float2 per lane per row
-        float2 bv[NV];
-#pragma unroll
-        for (int q = 0; q < NV; ++q)
-            bv[q] = bias ? __ldg(reinterpret_cast<const float2*>(bias + q * 64 + lane * 2)) : make_float2(0.f, 0.f);
-        const int row0 = m0 + lg * 32;
-        constexpr int RB = 8;                       // rows per batch: all shared/global loads first
+        const int cbase = g * p.c_goff + n0 + tcol + cc;                // ... in C
+        const float4 bv = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + g * p.b_goff + n0 + tcol + cc))
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+        const int row_first = m0 + lg * 32 + sub;
+        const float* rsrc = nullptr;                                    // residual / positional rows
+        long long rstep = 0;
+        if (EPI == RG_EPI_BIAS_RESIDUAL) {
+            rsrc = p.R + (long long)row_first * p.ldr + (p.r_grouped ? g * p.c_goff : 0) + n0 + tcol + cc;
+            rstep = 2ll * p.ldr;
+        }
+        float* c32 = p.C32 ? p.C32 + (long long)row_first * p.ldc32 + cbase : nullptr;
+        __nv_bfloat16* c16 = p.C16_ ? reinterpret_cast<__nv_bfloat16*>(p.C16_) + (long long)row_first * p.ldc16 + cbase : nullptr;
+        const float* srow = stage + sub * PITCH + cc;
+        constexpr int RB = 4;                       // row pairs per batch: all loads of a batch are issued first
 #pragma unroll 1
-        for (int r0 = 0; r0 < 32; r0 += RB) {
-            float2 f[RB][NV], rr[RB][NV];
+        for (int s0 = 0; s0 < 16; s0 += RB) {
+            float4 f[RB], rr[RB];
 #pragma unroll
             for (int i = 0; i < RB; ++i) {
-                const int row = row0 + r0 + i;
-#pragma unroll
-                for (int q = 0; q < NV; ++q) {
-                    const int cc = q * 64 + lane * 2;
-                    f[i][q] = *reinterpret_cast<const float2*>(stage + (r0 + i) * PITCH + cc);
-                    rr[i][q] = make_float2(0.f, 0.f);
-                    if (row < p.M) {
-                        if (p.epi == RG_EPI_BIAS_RESIDUAL)
-                            rr[i][q] = *reinterpret_cast<const float2*>(p.R + (long long)row * p.ldr + rbase + cc);
-                        else if (p.epi == RG_EPI_BIAS_POS)
-                            rr[i][q] = __ldg(reinterpret_cast<const float2*>(p.pos + (long long)(row % p.pos_T) * p.N + n0 + tcol + cc));
-                    }
+                const int row = row_first + 2 * (s0 + i);
+                f[i] = *reinterpret_cast<const float4*>(srow + 2 * (s0 + i) * PITCH);
+                rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row < p.M) {
+                    if (EPI == RG_EPI_BIAS_RESIDUAL)
+                        rr[i] = *reinterpret_cast<const float4*>(rsrc + (s0 + i) * rstep);
+                    else if (EPI == RG_EPI_BIAS_POS)
+                        rr[i] = __ldg(reinterpret_cast<const float4*>(p.pos + (long long)(row % p.pos_T) * p.N + n0 + tcol + cc));
                 }
             }
 #pragma unroll
             for (int i = 0; i < RB; ++i) {
-                const int row = row0 + r0 + i;
+                const int row = row_first + 2 * (s0 + i);
                 if (row >= p.M) break;
-#pragma unroll
-                for (int q = 0; q < NV; ++q) {
-                    const int cc = q * 64 + lane * 2;
-                    float2 v = f[i][q];
-                    v.x += bv[q].x + rr[i][q].x; v.y += bv[q].y + rr[i][q].y;
-                    if (p.epi == RG_EPI_BIAS_GELU) {
-                        v.x = rg_gelu_erf(v.x); v.y = rg_gelu_erf(v.y);
-                    } else if (p.epi == RG_EPI_BIAS_SILU) {
-                        v.x = rg_silu(v.x); v.y = rg_silu(v.y);
-                    }
-                    if (p.C32) *reinterpret_cast<float2*>(p.C32 + (long long)row * p.ldc32 + cbase + cc) = v;
-                    if (p.C16_) {
-                        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.C16_) + (long long)row * p.ldc16 + cbase + cc;
-                        const __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y);
-                        *reinterpret_cast<uint32_t*>(o) = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                        if (p.c16_lo_off) {
-                            const __nv_bfloat16 l0 = __float2bfloat16_rn(v.x - __bfloat162float(h0));
-                            const __nv_bfloat16 l1 = __float2bfloat16_rn(v.y - __bfloat162float(h1));
-                            *reinterpret_cast<uint32_t*>(o + p.c16_lo_off) =
-                                (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-                        }
+                float4 v = f[i];
+                v.x += bv.x + rr[i].x; v.y += bv.y + rr[i].y; v.z += bv.z + rr[i].z; v.w += bv.w + rr[i].w;
+                if (EPI == RG_EPI_BIAS_GELU) {
+                    v.x = rg_gelu_fast(v.x); v.y = rg_gelu_fast(v.y); v.z = rg_gelu_fast(v.z); v.w = rg_gelu_fast(v.w);
+                } else if (EPI == RG_EPI_BIAS_SILU) {
+                    v.x = rg_silu(v.x); v.y = rg_silu(v.y); v.z = rg_silu(v.z); v.w = rg_silu(v.w);
+                }
+                if (c32) *reinterpret_cast<float4*>(c32 + 2ll * (s0 + i) * p.ldc32) = v;
+                if (c16) {
+                    __nv_bfloat16* o = c16 + 2ll * (s0 + i) * p.ldc16;
+                    const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
+                    uint2 pk;
+                    pk.x = *reinterpret_cast<const uint32_t*>(&h01); pk.y = *reinterpret_cast<const uint32_t*>(&h23);
+                    *reinterpret_cast<uint2*>(o) = pk;
+                    if (p.c16_lo_off) {
+                        const __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - __low2float(h01), v.y - __high2float(h01));
+                        const __nv_bfloat162 l23 = __floats2bfloat162_rn(v.z - __low2float(h23), v.w - __high2float(h23));
+                        pk.x = *reinterpret_cast<const uint32_t*>(&l01); pk.y = *reinterpret_cast<const uint32_t*>(&l23);
+                        *reinterpret_cast<uint2*>(o + p.c16_lo_off) = pk;
                     }
                 }
             }
@@ -350,30 +354,46 @@ cudaError_t rg_make_tensor_map(CUtensorMap* tm, const void* ptr, long long rows,
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
-cudaError_t rg_launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmW, const RgGemmTc& p, cudaStream_t st) {
-    if (p.M <= 0 || p.N <= 0) return cudaSuccess;
+template <int STAGES, int EPI>
+static cudaError_t launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmW, const RgGemmTc& p, dim3 grid, cudaStream_t st) {
     constexpr int BN = 128;
-    if (p.K % BK || p.N % BN || (p.C32 && p.ldc32 % 4) || (p.C16_ && p.ldc16 % 8) || (p.R && p.ldr % 4))
-        return cudaErrorInvalidValue;
-    constexpr size_t STAGE = BM * BK * 2 + BN * BK * 2;
-    constexpr size_t smem3 = 3 * STAGE + 1024, smem6 = 6 * STAGE + 1024;
+    constexpr size_t smem = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<BN, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6);
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
-    dim3 grid(p.N / BN, (p.M + BM - 1) / BM, p.groups > 0 ? p.groups : 1);
-    const long long ctas = (long long)grid.x * grid.y * grid.z;
     if (p.no_pdl) {     // weight tiles are prefetched before griddepcontrol.wait: only valid for constant W
-        if (ctas <= 148) gemm_tc_kernel<BN, 6><<<grid, 320, smem6, st>>>(tmA, tmW, p);
-        else gemm_tc_kernel<BN, 3><<<grid, 320, smem3, st>>>(tmA, tmW, p);
+        gemm_tc_kernel<BN, STAGES, EPI><<<grid, 320, smem, st>>>(tmA, tmW, p);
         return cudaGetLastError();
     }
-    if (ctas <= 148)
-        return rg_launch_pdl(gemm_tc_kernel<BN, 6>, grid, dim3(320), smem6, st, tmA, tmW, p);
-    return rg_launch_pdl(gemm_tc_kernel<BN, 3>, grid, dim3(320), smem3, st, tmA, tmW, p);
+    return rg_launch_pdl(gemm_tc_kernel<BN, STAGES, EPI>, grid, dim3(320), smem, st, tmA, tmW, p);
+}
+template <int EPI>
+static cudaError_t launch_tc_epi(const CUtensorMap& tmA, const CUtensorMap& tmW, const RgGemmTc& p, dim3 grid, cudaStream_t st) {
+    // one CTA per SM with the whole K = 512 reduction in flight for grids below one wave, else two per SM
+    if ((long long)grid.x * grid.y * grid.z <= 148) return launch_tc<6, EPI>(tmA, tmW, p, grid, st);
+    return launch_tc<3, EPI>(tmA, tmW, p, grid, st);
+}
+
+cudaError_t rg_launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmW, const RgGemmTc& p, cudaStream_t st) {
+    if (p.M <= 0 || p.N <= 0) return cudaSuccess;
+    constexpr int BN = 128;
+    if (p.K % BK || p.N % BN || (p.C32 && p.ldc32 % 4) || (p.C16_ && p.ldc16 % 8) || (p.R && p.ldr % 4) ||
+        (p.C16_ && p.c16_lo_off % 4))
+        return cudaErrorInvalidValue;
+    if (p.epi == RG_EPI_BIAS_RESIDUAL && !p.R) return cudaErrorInvalidValue;
+    if (p.epi == RG_EPI_BIAS_POS && (!p.pos || p.pos_T <= 0)) return cudaErrorInvalidValue;
+    const dim3 grid(p.N / BN, (p.M + BM - 1) / BM, p.groups > 0 ? p.groups : 1);
+    switch (p.epi) {
+        case RG_EPI_BIAS: return launch_tc_epi<RG_EPI_BIAS>(tmA, tmW, p, grid, st);
+        case RG_EPI_BIAS_RESIDUAL: return launch_tc_epi<RG_EPI_BIAS_RESIDUAL>(tmA, tmW, p, grid, st);
+        case RG_EPI_BIAS_GELU: return launch_tc_epi<RG_EPI_BIAS_GELU>(tmA, tmW, p, grid, st);
+        case RG_EPI_BIAS_POS: return launch_tc_epi<RG_EPI_BIAS_POS>(tmA, tmW, p, grid, st);
+        case RG_EPI_BIAS_SILU: return launch_tc_epi<RG_EPI_BIAS_SILU>(tmA, tmW, p, grid, st);
+        default: return cudaErrorInvalidValue;
+    }
 }
 
 cudaError_t rg_launch_split_bf16(const float* x, int ldx, void* out, int ldo, int lo_off, long long rows, int cols,

@@ -141,6 +141,18 @@ __device__ __forceinline__ float rg_warp_max(float v) {
 // loops of every row/attention kernel; their error is far below every parity tier (tests).
 __device__ __forceinline__ float rg_exp(float v) { return __expf(v); }
 __device__ __forceinline__ float rg_silu(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+// GELU(erf) with erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7 absolute, ~15 instructions against
+// ~40 for erff): used in the tensor-core tiers' GEMM epilogue, where it was half of the epilogue's time.
+__device__ __forceinline__ float rg_gelu_fast(float v) {
+    const float x = v * 0.70710678118654752440f, ax = fabsf(x);
+    const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    const float e = fmaf(-p * t, __expf(-ax * ax), 1.0f);
+    return 0.5f * v * (1.0f + copysignf(e, x));
+}
 __device__ __forceinline__ float rg_gelu_erf(float v) {
     return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
 }
