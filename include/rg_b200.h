@@ -180,6 +180,15 @@ int rg_op_self_attention_core(const float* qkv, const float* src_mask, float* y,
                               void* stream);
 int rg_op_cross_attention_core(const float* q3, const float* state, const float* query_mask, float* y,
                                int B, int T, int mode, void* stream);
+/* The same cores fused with the Stylization prologue of proj_out (LayerNorm -> *(1+scale)+shift -> SiLU),
+ * as the tensor-core tiers run them: split 0 = TF32, 1 = 3xTF32.  ss = [scale(512) | shift(512)] rows:
+ * self: ss [1024] or [B,1024] (ss_per_clip); cross: gamma3/beta3 [3,512], ss3 [3,1024] or [B,3,1024].
+ * out: self [B*T,512], cross [B*T,1536] (fp32). */
+int rg_op_self_attention_tc(const float* qkv, const float* src_mask, const float* gamma, const float* beta,
+                            const float* ss, int ss_per_clip, float* out, int B, int T, int split, void* stream);
+int rg_op_cross_attention_tc(const float* q3, const float* state, const float* query_mask, const float* gamma3,
+                             const float* beta3, const float* ss3, int ss_per_clip, float* out, int B, int T,
+                             int split, void* stream);
 /* K/V -> state for ONE condition/layer: kv [B*N,1024] = [key | value] projections. */
 int rg_op_kv_state(const float* kv, int n_tokens, int B, float* state, void* stream);
 

@@ -46,6 +46,8 @@ SIGNATURES = {
     "rg_op_cross_attention": (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _I, _I, _P]),
     "rg_op_self_attention_core": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "rg_op_cross_attention_core": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
+    "rg_op_self_attention_tc": (_I, [_P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _P]),
+    "rg_op_cross_attention_tc": (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _P]),
     "rg_op_kv_state": (_I, [_P, _I, _I, _P, _P]),
     "rg_text_similarity": (_I, [_P, _P, _L, _I, _I, _P, _I, _P, _L, _P, _P]),
     "rg_knn_topk": (_I, [_P, _L, _I, _P, _I, _I, _L, _P, _P, _P]),

@@ -374,19 +374,13 @@ __device__ __forceinline__ void quad_row_softmax(float2 q[4]) {
     for (int k = 0; k < 4; ++k) { q[k].x = __fdividef(q[k].x, s); q[k].y = __fdividef(q[k].y, s); }
 }
 
-// Y[b, n, head*32 + l] = softmax_d(Q)[n, :] . (softmax_n(K + mask)^T (V * m))[:, l]   (efficient_attention.py:146-160)
+// y[mt][nt][*] = C fragments of softmax_d(Q) (softmax_n(K + mask)^T (V m)) for one (clip, head):
+// rows 16mt+g (+8), columns 8nt+2t (+1)   (efficient_attention.py:146-160)
 template <int MT, bool SPLIT>
-__global__ void __launch_bounds__(128) sa_core_mma_kernel(const float* qkv,
-                                                         const float* src_mask,
-                                                         float* __restrict__ Y, int T) {
-    rg_pdl_launch();
-    rg_pdl_wait();
+__device__ __forceinline__ void sa_head_frags(const float* base, const float* mrow, int T, int g, int t,
+                                              float (&y)[MT][4][4]) {
     constexpr int KS = 2 * MT, TPT = 2 * KS;             // token k-steps; tokens owned by one thread group
-    const int b = blockIdx.x, head = blockIdx.y * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    const int g = lane >> 2, t = lane & 3;
     const long long RS = 3 * RG_D;
-    const float* base = qkv + (long long)b * T * RS + head * RG_HD;
-    const float* mrow = src_mask + (long long)b * T;
     const int n0 = t * TPT;
     float mk[TPT], kk[TPT][4], vv[TPT][4];               // K[n][8j+g] (+ -1e6 mask), V[n][8j+g] * m
 #pragma unroll
@@ -443,7 +437,6 @@ __global__ void __launch_bounds__(128) sa_core_mma_kernel(const float* qkv,
         }
     }
     // Y = softmax_d(Q) A, 16 query rows per tile; B fragments are the C fragments above
-    float* o = Y + (long long)b * T * RG_D + head * RG_HD + 2 * t;
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
         const int r0 = 16 * mt + g, r1 = r0 + 8;
@@ -455,42 +448,26 @@ __global__ void __launch_bounds__(128) sa_core_mma_kernel(const float* qkv,
         }
         quad_row_softmax(q0);
         quad_row_softmax(q1);
-        float y[4][4];
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) y[nt][i] = 0.f;
+            for (int i = 0; i < 4; ++i) y[mt][nt][i] = 0.f;
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
             const float a[4] = {q0[ks].x, q1[ks].x, q0[ks].y, q1[ks].y};
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt) {
                 const float bb[2] = {at[nt >> 1][ks][2 * (nt & 1)], at[nt >> 1][ks][2 * (nt & 1) + 1]};
-                mma_f32<SPLIT>(y[nt], a, bb);
+                mma_f32<SPLIT>(y[mt][nt], a, bb);
             }
-        }
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-            if (r0 < T) *reinterpret_cast<float2*>(o + (long long)r0 * RG_D + 8 * nt) = make_float2(y[nt][0], y[nt][1]);
-            if (r1 < T) *reinterpret_cast<float2*>(o + (long long)r1 * RG_D + 8 * nt) = make_float2(y[nt][2], y[nt][3]);
         }
     }
 }
 
-// Y[b, n, c*512 + head*32 + l] = softmax_d(Q_c)[n, :] . state[b, c, head][:, l]  (+ -1e6 on rows with query_mask 0)
+// y = C fragments of softmax_d(Q_c) state[b, c, head]  (+ -1e6 on rows with query_mask 0) for one (clip, cond, head)
 template <int MT, bool SPLIT>
-__global__ void __launch_bounds__(128) ca_core_mma_kernel(const float* q3, int ldq,
-                                                         const float* __restrict__ state,
-                                                         long long state_clip_stride, long long state_cond_stride,
-                                                         const float* qmask,
-                                                         long long qmask_cond_stride, float* __restrict__ Y,
-                                                         int ldy, int T) {
-    rg_pdl_launch();
-    rg_pdl_wait();
-    const int b = blockIdx.x, c = blockIdx.y, head = blockIdx.z * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    const int g = lane >> 2, t = lane & 3;
-    const float* Ap = state + (long long)b * state_clip_stride + (long long)c * state_cond_stride +
-                      (long long)head * RG_HD * RG_HD;
+__device__ __forceinline__ void ca_head_frags(const float* qb, int ldq, const float* Ap, const float* qm, int T,
+                                              int g, int t, float (&y)[MT][4][4]) {
     float bf[4][4][2];                                   // [ks][nt][j] = A[d = 8ks+2t+j][l = 8nt+g]
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks)
@@ -498,9 +475,6 @@ __global__ void __launch_bounds__(128) ca_core_mma_kernel(const float* q3, int l
         for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
             for (int j = 0; j < 2; ++j) bf[ks][nt][j] = __ldg(Ap + (8 * ks + 2 * t + j) * RG_HD + 8 * nt + g);
-    const float* qb = q3 + (long long)b * T * ldq + c * RG_D + head * RG_HD + 2 * t;
-    const float* qm = qmask ? qmask + (long long)c * qmask_cond_stride + (long long)b * T : nullptr;
-    float* o = Y + (long long)b * T * ldy + c * RG_D + head * RG_HD + 2 * t;
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
         const int r0 = 16 * mt + g, r1 = r0 + 8;
@@ -514,23 +488,172 @@ __global__ void __launch_bounds__(128) ca_core_mma_kernel(const float* q3, int l
         const float add1 = (qm && r1 < T) ? (1.0f - qm[r1]) * RG_NEG_MASK : 0.f;
         quad_row_softmax(q0);
         quad_row_softmax(q1);
-        float y[4][4];
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) y[nt][i] = 0.f;
+            for (int i = 0; i < 4; ++i) y[mt][nt][i] = 0.f;
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
             const float a[4] = {q0[ks].x, q1[ks].x, q0[ks].y, q1[ks].y};
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) mma_f32<SPLIT>(y[nt], a, bf[ks][nt]);
+            for (int nt = 0; nt < 4; ++nt) mma_f32<SPLIT>(y[mt][nt], a, bf[ks][nt]);
         }
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {      // fp32 add: y - 1e6 rounds to a 1/16 grid, as in the reference
-            if (r0 < T) *reinterpret_cast<float2*>(o + (long long)r0 * ldy + 8 * nt) = make_float2(y[nt][0] + add0, y[nt][1] + add0);
-            if (r1 < T) *reinterpret_cast<float2*>(o + (long long)r1 * ldy + 8 * nt) = make_float2(y[nt][2] + add1, y[nt][3] + add1);
+            y[mt][nt][0] += add0; y[mt][nt][1] += add0; y[mt][nt][2] += add1; y[mt][nt][3] += add1;
         }
     }
+}
+
+template <int MT>
+__device__ __forceinline__ void store_frags(const float (&y)[MT][4][4], float* o, int ld, int T, int g) {
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+        const int r0 = 16 * mt + g, r1 = r0 + 8;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            if (r0 < T) *reinterpret_cast<float2*>(o + (long long)r0 * ld + 8 * nt) = make_float2(y[mt][nt][0], y[mt][nt][1]);
+            if (r1 < T) *reinterpret_cast<float2*>(o + (long long)r1 * ld + 8 * nt) = make_float2(y[mt][nt][2], y[mt][nt][3]);
+        }
+    }
+}
+
+// The cores alone (Y before the Stylization prologue): 4 heads per CTA, one per warp.
+template <int MT, bool SPLIT>
+__global__ void __launch_bounds__(128) sa_core_mma_kernel(const float* qkv, const float* src_mask,
+                                                         float* __restrict__ Y, int T) {
+    rg_pdl_launch();
+    rg_pdl_wait();
+    const int b = blockIdx.x, head = blockIdx.y * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    float y[MT][4][4];
+    sa_head_frags<MT, SPLIT>(qkv + (long long)b * T * (3 * RG_D) + head * RG_HD, src_mask + (long long)b * T, T, g, t, y);
+    store_frags<MT>(y, Y + (long long)b * T * RG_D + head * RG_HD + 2 * t, RG_D, T, g);
+}
+template <int MT, bool SPLIT>
+__global__ void __launch_bounds__(128) ca_core_mma_kernel(const float* q3, int ldq,
+                                                         const float* __restrict__ state,
+                                                         long long state_clip_stride, long long state_cond_stride,
+                                                         const float* qmask, long long qmask_cond_stride,
+                                                         float* __restrict__ Y, int ldy, int T) {
+    rg_pdl_launch();
+    rg_pdl_wait();
+    const int b = blockIdx.x, c = blockIdx.y, head = blockIdx.z * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    float y[MT][4][4];
+    ca_head_frags<MT, SPLIT>(q3 + (long long)b * T * ldq + c * RG_D + head * RG_HD + 2 * t, ldq,
+                             state + (long long)b * state_clip_stride + (long long)c * state_cond_stride + (long long)head * RG_HD * RG_HD,
+                             qmask ? qmask + (long long)c * qmask_cond_stride + (long long)b * T : nullptr, T, g, t, y);
+    store_frags<MT>(y, Y + (long long)b * T * ldy + c * RG_D + head * RG_HD + 2 * t, ldy, T, g);
+}
+
+// ---- cores fused with the Stylization prologue of proj_out ---------------------------------------------------
+// One CTA = one clip (x one condition), 16 warps = the 16 heads, so a token's whole 512-wide output row lives
+// in this CTA's registers: LayerNorm statistics are combined across the warps through shared memory (per-warp
+// mean / centred sum of squares over its 32 columns, merged with Chan's formula), then norm affine,
+// *(1+scale)+shift and SiLU are applied to the fragments and the rows go straight out as the bf16 operand
+// planes of the projection GEMM.  Saves the fp32 Y round trip and one kernel per attention block.
+template <int MT>
+__device__ __forceinline__ void styl_frags_store(float (&y)[MT][4][4], int T, int head, int g, int t,
+                                                 float2 (*part)[RG_H], float2* stat, const RgStylParams& sp,
+                                                 int clip, const RgRowOut& out, long long row_base, int col0) {
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float s = 0.f;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) s += y[mt][nt][2 * h] + y[mt][nt][2 * h + 1];
+            const float mw = quad_sum(s) * (1.0f / RG_HD);
+            float q = 0.f;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const float d0 = y[mt][nt][2 * h] - mw, d1 = y[mt][nt][2 * h + 1] - mw;
+                q += d0 * d0 + d1 * d1;
+            }
+            q = quad_sum(q);
+            const int r = 16 * mt + g + 8 * h;
+            if (t == 0 && r < T) part[r][head] = make_float2(mw, q);
+        }
+    __syncthreads();
+    if ((int)threadIdx.x < T) {
+        float mean = 0.f;
+#pragma unroll
+        for (int w = 0; w < RG_H; ++w) mean += part[threadIdx.x][w].x;
+        mean *= (1.0f / RG_H);
+        float m2 = 0.f;
+#pragma unroll
+        for (int w = 0; w < RG_H; ++w) {
+            const float2 pw = part[threadIdx.x][w];
+            const float d = pw.x - mean;
+            m2 += pw.y + (float)RG_HD * d * d;
+        }
+        stat[threadIdx.x] = make_float2(mean, 1.0f / sqrtf(m2 * (1.0f / RG_D) + 1e-5f));
+    }
+    __syncthreads();
+    const float* ss = sp.ss + (long long)clip * sp.ss_clip_stride;
+    float2 ga[4], be[4], sc[4], sh[4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+        const int col = head * RG_HD + 8 * nt + 2 * t;
+        ga[nt] = __ldg(reinterpret_cast<const float2*>(sp.gamma + col));
+        be[nt] = __ldg(reinterpret_cast<const float2*>(sp.beta + col));
+        sc[nt] = __ldg(reinterpret_cast<const float2*>(ss + col));
+        sh[nt] = __ldg(reinterpret_cast<const float2*>(ss + RG_D + col));
+    }
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int r = 16 * mt + g + 8 * h;
+            if (r >= T) continue;
+            const float2 st = stat[r];
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                float v0 = (y[mt][nt][2 * h] - st.x) * st.y, v1 = (y[mt][nt][2 * h + 1] - st.x) * st.y;
+                v0 = rg_silu((v0 * ga[nt].x + be[nt].x) * (1.0f + sc[nt].x) + sh[nt].x);
+                v1 = rg_silu((v1 * ga[nt].y + be[nt].y) * (1.0f + sc[nt].y) + sh[nt].y);
+                const long long off = (row_base + r) * out.ld + col0 + head * RG_HD + 8 * nt + 2 * t;
+                if (out.f32) {
+                    *reinterpret_cast<float2*>(out.f32 + off) = make_float2(v0, v1);
+                } else {
+                    const __nv_bfloat162 hh = __floats2bfloat162_rn(v0, v1);
+                    *reinterpret_cast<__nv_bfloat162*>(out.b16 + off) = hh;
+                    if (out.lo_off)
+                        *reinterpret_cast<__nv_bfloat162*>(out.b16 + off + out.lo_off) =
+                            __floats2bfloat162_rn(v0 - __low2float(hh), v1 - __high2float(hh));
+                }
+            }
+        }
+}
+
+template <int MT, bool SPLIT>
+__global__ void __launch_bounds__(512) sa_styl_mma_kernel(const float* qkv, const float* src_mask, RgStylParams sp,
+                                                         RgRowOut out, int T) {
+    __shared__ float2 part[RG_MAX_T][RG_H];
+    __shared__ float2 stat[RG_MAX_T];
+    rg_pdl_launch();
+    rg_pdl_wait();
+    const int b = blockIdx.x, head = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    float y[MT][4][4];
+    sa_head_frags<MT, SPLIT>(qkv + (long long)b * T * (3 * RG_D) + head * RG_HD, src_mask + (long long)b * T, T, g, t, y);
+    styl_frags_store<MT>(y, T, head, g, t, part, stat, sp, b, out, (long long)b * T, 0);
+}
+template <int MT, bool SPLIT>
+__global__ void __launch_bounds__(512) ca_styl_mma_kernel(const float* q3, int ldq, const float* __restrict__ state,
+                                                         long long state_clip_stride, long long state_cond_stride,
+                                                         const float* qmask, long long qmask_cond_stride, RgStyl3 sp3,
+                                                         RgRowOut out, int T) {
+    __shared__ float2 part[RG_MAX_T][RG_H];
+    __shared__ float2 stat[RG_MAX_T];
+    rg_pdl_launch();
+    rg_pdl_wait();
+    const int b = blockIdx.x, c = blockIdx.y, head = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    float y[MT][4][4];
+    ca_head_frags<MT, SPLIT>(q3 + (long long)b * T * ldq + c * RG_D + head * RG_HD + 2 * t, ldq,
+                             state + (long long)b * state_clip_stride + (long long)c * state_cond_stride + (long long)head * RG_HD * RG_HD,
+                             qmask ? qmask + (long long)c * qmask_cond_stride + (long long)b * T : nullptr, T, g, t, y);
+    styl_frags_store<MT>(y, T, head, g, t, part, stat, sp3.p[c], b, out, (long long)b * T, c * RG_D);
 }
 
 // Stylization prologue of the three cross-attention blocks over Y[M,1536]: blockIdx.y = condition;
@@ -724,6 +847,46 @@ static cudaError_t launch_ca_mma(const float* q3, int ldq, const float* state, l
         case 3: return rg_launch_pdl(ca_core_mma_kernel<3, SPLIT>, grid, block, 0, st, q3, ldq, state, scs, sds, qmask, qms, Y, ldy, T);
         default: return rg_launch_pdl(ca_core_mma_kernel<4, SPLIT>, grid, block, 0, st, q3, ldq, state, scs, sds, qmask, qms, Y, ldy, T);
     }
+}
+
+template <bool SPLIT>
+static cudaError_t launch_sa_styl(const float* qkv, const float* src_mask, RgStylParams sp, RgRowOut out, int B, int T,
+                                  cudaStream_t st) {
+    const dim3 grid(B), block(512);
+    switch ((T + 15) / 16) {
+        case 1: return rg_launch_pdl(sa_styl_mma_kernel<1, SPLIT>, grid, block, 0, st, qkv, src_mask, sp, out, T);
+        case 2: return rg_launch_pdl(sa_styl_mma_kernel<2, SPLIT>, grid, block, 0, st, qkv, src_mask, sp, out, T);
+        case 3: return rg_launch_pdl(sa_styl_mma_kernel<3, SPLIT>, grid, block, 0, st, qkv, src_mask, sp, out, T);
+        default: return rg_launch_pdl(sa_styl_mma_kernel<4, SPLIT>, grid, block, 0, st, qkv, src_mask, sp, out, T);
+    }
+}
+template <bool SPLIT>
+static cudaError_t launch_ca_styl(const float* q3, int ldq, const float* state, long long scs, long long sds,
+                                  const float* qmask, long long qms, RgStyl3 s3, RgRowOut out, int B, int T, cudaStream_t st) {
+    const dim3 grid(B, 3), block(512);
+    switch ((T + 15) / 16) {
+        case 1: return rg_launch_pdl(ca_styl_mma_kernel<1, SPLIT>, grid, block, 0, st, q3, ldq, state, scs, sds, qmask, qms, s3, out, T);
+        case 2: return rg_launch_pdl(ca_styl_mma_kernel<2, SPLIT>, grid, block, 0, st, q3, ldq, state, scs, sds, qmask, qms, s3, out, T);
+        case 3: return rg_launch_pdl(ca_styl_mma_kernel<3, SPLIT>, grid, block, 0, st, q3, ldq, state, scs, sds, qmask, qms, s3, out, T);
+        default: return rg_launch_pdl(ca_styl_mma_kernel<4, SPLIT>, grid, block, 0, st, q3, ldq, state, scs, sds, qmask, qms, s3, out, T);
+    }
+}
+// attention core + Stylization prologue in one kernel (tensor-core tiers): split = 3xTF32
+cudaError_t rg_launch_sa_styl(const float* qkv, const float* src_mask, RgStylParams sp, RgRowOut out, int B, int T,
+                              int split, cudaStream_t st) {
+    if (B <= 0) return cudaSuccess;
+    if (T > RG_MAX_T || (out.ld % 2) || (out.lo_off % 2)) return cudaErrorInvalidValue;
+    return split ? launch_sa_styl<true>(qkv, src_mask, sp, out, B, T, st) : launch_sa_styl<false>(qkv, src_mask, sp, out, B, T, st);
+}
+cudaError_t rg_launch_ca_styl(const float* q3, int ldq, const float* state, long long state_clip_stride,
+                              long long state_cond_stride, const float* qmask, long long qmask_cond_stride,
+                              const RgStylParams* sp3, RgRowOut out, int B, int T, int split, cudaStream_t st) {
+    if (B <= 0) return cudaSuccess;
+    if (T > RG_MAX_T || (ldq % 2) || (out.ld % 2) || (out.lo_off % 2)) return cudaErrorInvalidValue;
+    RgStyl3 s3;
+    for (int c = 0; c < 3; ++c) s3.p[c] = sp3[c];
+    return split ? launch_ca_styl<true>(q3, ldq, state, state_clip_stride, state_cond_stride, qmask, qmask_cond_stride, s3, out, B, T, st)
+                 : launch_ca_styl<false>(q3, ldq, state, state_clip_stride, state_cond_stride, qmask, qmask_cond_stride, s3, out, B, T, st);
 }
 
 // mode 0: fp32 SIMT cores; 1: TF32 mma.sync; 2: 3xTF32 (hi/lo split) mma.sync

@@ -577,8 +577,15 @@ static int denoise_tc(rg_model* m, Ws& w, const float* x, int B, const float* ss
         LAUNCH(rg_launch_ln_rows(w.h, D, nullptr, nullptr, rg_out_b16(w.a16, D * P, lo ? D : 0), M, st));
         if (tc_gemm(m, w.tm_a16, D, t.qkv, ly.bqkv, M, 3 * D, D, RG_EPI_BIAS, nullptr, w.big, 3 * D, nullptr, 0, st)) return 1;
         RgStylParams sp = {ly.sa_g, ly.sa_b, ss, 0};
-        LAUNCH(rg_launch_sa_core(w.big, src_mask, w.y, B, T, m->attn_mode, st));
-        LAUNCH(rg_launch_styl_rows(w.y, D, sp, T, rg_out_b16(w.a16, D * P, lo ? D : 0), M, st));
+        // mma.sync core + Stylization prologue in one kernel (one CTA per clip): measured faster than core +
+        // row kernel for the single-pass TF32 cores up to ~128 clips; the 3xTF32 variant is register-bound
+        const bool fuse_styl = m->attn_mode == 1 && B <= 128;
+        if (fuse_styl) {
+            LAUNCH(rg_launch_sa_styl(w.big, src_mask, sp, rg_out_b16(w.a16, D * P, lo ? D : 0), B, T, m->attn_mode == 2, st));
+        } else {
+            LAUNCH(rg_launch_sa_core(w.big, src_mask, w.y, B, T, m->attn_mode, st));
+            LAUNCH(rg_launch_styl_rows(w.y, D, sp, T, rg_out_b16(w.a16, D * P, lo ? D : 0), M, st));
+        }
         // h1 = h + proj(...): fp32 residual stream + its bf16 planes as the 4th K-block of the folded ca GEMM
         {
             RgGemmTc p;
@@ -594,9 +601,14 @@ static int denoise_tc(rg_model* m, Ws& w, const float* x, int B, const float* ss
         if (tc_gemm(m, w.tm_a16, D, t.caq, ly.bcaq, M, 3 * D, D, RG_EPI_BIAS, nullptr, w.big, 3 * D, nullptr, 0, st)) return 1;
         RgStylParams sp3[3];
         for (int c = 0; c < 3; ++c) sp3[c] = {ly.ca_g + c * D, ly.ca_b + c * D, ss + (1 + c) * 2 * D, 0};
-        LAUNCH(rg_launch_ca_core(w.big, 3 * D, state + (long long)l * 3 * HS, clip_stride, HS, query_mask,
-                                 qm_cond_stride, w.o3, 3 * D, B, T, m->attn_mode_ca, st));
-        LAUNCH(rg_launch_styl_rows3(w.o3, 3 * D, sp3, T, rg_out_b16(w.a16x, 4 * D * P, lo ? 4 * D : 0), M, st));
+        if (m->attn_mode_ca == 1 && B <= 128) {
+            LAUNCH(rg_launch_ca_styl(w.big, 3 * D, state + (long long)l * 3 * HS, clip_stride, HS, query_mask, qm_cond_stride,
+                                     sp3, rg_out_b16(w.a16x, 4 * D * P, lo ? 4 * D : 0), B, T, m->attn_mode_ca == 2, st));
+        } else {
+            LAUNCH(rg_launch_ca_core(w.big, 3 * D, state + (long long)l * 3 * HS, clip_stride, HS, query_mask,
+                                     qm_cond_stride, w.o3, 3 * D, B, T, m->attn_mode_ca, st));
+            LAUNCH(rg_launch_styl_rows3(w.o3, 3 * D, sp3, T, rg_out_b16(w.a16x, 4 * D * P, lo ? 4 * D : 0), M, st));
+        }
         if (tc_gemm(m, w.tm_a16x, 4 * D, t.fold, t.b_fold, M, D, 4 * D, RG_EPI_BIAS, nullptr, w.h, D, w.h16, D, st)) return 1;
         // --- FFN
         if (tc_gemm(m, w.tm_h16, D, t.w1, ly.b1, M, F, D, RG_EPI_BIAS_GELU, nullptr, nullptr, 0, w.g16, F, st)) return 1;
@@ -930,6 +942,25 @@ extern "C" int rg_op_cross_attention_core(const float* q3, const float* state, c
     const long long HS = (long long)RG_H * RG_HD * RG_HD;
     LAUNCH(rg_launch_ca_core(q3, 3 * RG_D, state, 3 * HS, HS, query_mask, (long long)B * T, y, 3 * RG_D, B, T, mode,
                              (cudaStream_t)stream));
+    return 0;
+}
+extern "C" int rg_op_self_attention_tc(const float* qkv, const float* src_mask, const float* gamma, const float* beta,
+                                       const float* ss, int ss_per_clip, float* out, int B, int T, int split,
+                                       void* stream) {
+    if (!qkv || !src_mask || !gamma || !beta || !ss || !out) return rg_fail("rg_op_self_attention_tc: null argument");
+    RgStylParams sp = {gamma, beta, ss, ss_per_clip ? 2ll * RG_D : 0};
+    LAUNCH(rg_launch_sa_styl(qkv, src_mask, sp, rg_out_f32(out, RG_D), B, T, split, (cudaStream_t)stream));
+    return 0;
+}
+extern "C" int rg_op_cross_attention_tc(const float* q3, const float* state, const float* query_mask,
+                                        const float* gamma3, const float* beta3, const float* ss3, int ss_per_clip,
+                                        float* out, int B, int T, int split, void* stream) {
+    if (!q3 || !state || !gamma3 || !beta3 || !ss3 || !out) return rg_fail("rg_op_cross_attention_tc: null argument");
+    const long long HS = (long long)RG_H * RG_HD * RG_HD;
+    RgStylParams sp3[3];
+    for (int c = 0; c < 3; ++c) sp3[c] = {gamma3 + c * RG_D, beta3 + c * RG_D, ss3 + c * 2 * RG_D, ss_per_clip ? 6ll * RG_D : 0};
+    LAUNCH(rg_launch_ca_styl(q3, 3 * RG_D, state, 3 * HS, HS, query_mask, (long long)B * T, sp3, rg_out_f32(out, 3 * RG_D), B, T,
+                             split, (cudaStream_t)stream));
     return 0;
 }
 extern "C" int rg_op_kv_state(const float* kv, int n_tokens, int B, float* state, void* stream) {

@@ -92,6 +92,11 @@ cudaError_t rg_launch_sa_core(const float* qkv, const float* src_mask, float* Y,
 cudaError_t rg_launch_ca_core(const float* q3, int ldq, const float* state, long long state_clip_stride,
                               long long state_cond_stride, const float* qmask, long long qmask_cond_stride,
                               float* Y, int ldy, int B, int T, int mode, cudaStream_t st);
+cudaError_t rg_launch_sa_styl(const float* qkv, const float* src_mask, RgStylParams sp, RgRowOut out, int B, int T,
+                              int split, cudaStream_t st);
+cudaError_t rg_launch_ca_styl(const float* q3, int ldq, const float* state, long long state_clip_stride,
+                              long long state_cond_stride, const float* qmask, long long qmask_cond_stride,
+                              const RgStylParams* sp3, RgRowOut out, int B, int T, int split, cudaStream_t st);
 cudaError_t rg_launch_styl_rows3(const float* y, int ldy, const RgStylParams* sp3, int rows_per_clip,
                                  RgRowOut out, int M, cudaStream_t st);
 cudaError_t rg_launch_kv_state(const float* kv, int ldkv, int k_off, int v_off, int n_tokens,

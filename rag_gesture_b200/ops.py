@@ -124,6 +124,31 @@ def cross_attention_core(q3, state, query_mask, mode=0):
     return out
 
 
+def self_attention_tc(qkv, src_mask, gamma, beta, ss, split=False):
+    """Fused mma.sync core + Stylization prologue: qkv [B,T,1536] -> stylised rows [B,T,512] (fp32)."""
+    qkv, src_mask, gamma, beta, ss = _prep(qkv, src_mask, gamma, beta, ss)
+    B, T = qkv.shape[0], qkv.shape[1]
+    out = torch.empty(B, T, D, device=qkv.device)
+    with torch.cuda.device(qkv.device):
+        _lib.check(_lib.load().rg_op_self_attention_tc(
+            _lib.ptr(qkv), _lib.ptr(src_mask), _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(ss), int(ss.dim() > 1),
+            _lib.ptr(out), B, T, int(split), _lib.stream_ptr()))
+    return out
+
+
+def cross_attention_tc(q3, state, query_mask, gamma3, beta3, ss3, split=False):
+    """Fused core + Stylization for the three conditions: q3 [B,T,1536], state [B,3,16,32,32], query_mask
+    [3,B,T] or None, gamma3/beta3 [3,512], ss3 [3,1024] or [B,3,1024] -> [B,T,1536] (fp32)."""
+    q3, state, query_mask, gamma3, beta3, ss3 = _prep(q3, state, query_mask, gamma3, beta3, ss3)
+    B, T = q3.shape[0], q3.shape[1]
+    out = torch.empty(B, T, 3 * D, device=q3.device)
+    with torch.cuda.device(q3.device):
+        _lib.check(_lib.load().rg_op_cross_attention_tc(
+            _lib.ptr(q3), _lib.ptr(state), _lib.ptr(query_mask), _lib.ptr(gamma3), _lib.ptr(beta3), _lib.ptr(ss3),
+            int(ss3.dim() > 2), _lib.ptr(out), B, T, int(split), _lib.stream_ptr()))
+    return out
+
+
 def kv_state(kv, B, n_tokens):
     """kv [B*N,1024] = [key | value] projections -> state [B,16,32,32]."""
     (kv,) = _prep(kv)

@@ -241,3 +241,37 @@ def test_attention_cores_mma_vs_fp32(dev, T):
                 assert rel_l2(z[keep].double(), ref[keep]) < tol
                 # masked rows: y - 1e6 in fp32, a 1/16 grid -> identical to the fp32 core unless y sits on a tie
                 assert (z[~keep] == z0[~keep]).float().mean() > 0.99 and (z[~keep] < -9e5).all()
+
+
+@pytest.mark.parametrize("T", [11, 23, 43, 64])
+def test_fused_attention_stylization_tc(dev, T):
+    """sa_styl / ca_styl (mma.sync core + Stylization prologue in one kernel, LayerNorm statistics merged
+    across the 16 head-warps) == core followed by the row kernel; shared and per-clip scale/shift."""
+    from rag_gesture_b200 import ops
+    B = 4
+    g = torch.Generator().manual_seed(200 + T)
+    qkv = torch.randn(B, T, 1536, generator=g).to(dev)
+    mask = (torch.rand(B, T, generator=g) > 0.2).float()
+    mask[:, 0] = 1
+    mask = mask.to(dev)
+    gamma = (1 + 0.1 * torch.randn(3, 512, generator=g)).to(dev)
+    beta = (0.1 * torch.randn(3, 512, generator=g)).to(dev)
+    for per_clip in (False, True):
+        ss = (0.3 * torch.randn(*((B, 3, 1024) if per_clip else (3, 1024)), generator=g)).to(dev)
+        ss0 = ss[:, 0].contiguous() if per_clip else ss[0].contiguous()
+        for split, tol in ((False, 2e-3), (True, 5e-6)):
+            ref = ops.stylization_rows(ops.self_attention_core(qkv, mask, 0).view(B * T, 512), gamma[0], beta[0], ss0, T)
+            got = ops.self_attention_tc(qkv, mask, gamma[0], beta[0], ss0, split)
+            assert rel_l2(got.view(B * T, 512), ref) < tol
+        q3 = torch.randn(B, T, 1536, generator=g).to(dev)
+        state = (torch.randn(B, 3, 16, 32, 32, generator=g) * 0.1).to(dev)
+        qm = (torch.rand(3, B, T, generator=g) > 0.1).float().to(dev)
+        y = ops.cross_attention_core(q3, state, qm, 0).view(B * T, 3, 512)
+        ref = torch.stack([ops.stylization_rows(y[:, c].contiguous(), gamma[c], beta[c],
+                                                ss[:, c].contiguous() if per_clip else ss[c].contiguous(), T)
+                           for c in range(3)], 1).view(B, T, 1536)
+        keep = qm.permute(1, 2, 0).reshape(B, T, 3, 1).expand(B, T, 3, 512).reshape(B, T, 1536) > 0
+        for split, tol in ((False, 2e-3), (True, 5e-6)):
+            got = ops.cross_attention_tc(q3, state, qm, gamma, beta, ss, split)
+            assert rel_l2(got[keep], ref[keep]) < tol
+            assert torch.isfinite(got).all()
