@@ -11,7 +11,8 @@ E retrieved exemplars, 50 insertion-guided sampling steps  =  50 * (B + E) clip-
   value : the device-resident loops (K6 state + inversion + guided sampling), CUDA-event timed;
   e2e   : MotionDiffusion.forward(**host_batch) -- pinned-host inputs, H2D, retrieval, codec, loops,
           decode, D2H of the latents -- the call tools/visualize.py:200 makes.
-Also reported: the exact fp32 kNN sweep of configs[3] (queries/s, HBM roofline) under "knn".
+Also reported under "knn": the kNN sweep of configs[3] (queries/s at Q = 1, 8, 64, 4096; HBM roofline of the
+exact scan, tensor roofline of the large-batch similarity kernel).
 --impl reference times the reference's algorithm (oracle/ port: as-written op sequence, exemplars
 inverted one by one at B=1) on the host cores.
 """
@@ -196,7 +197,7 @@ def run_b200(args):
 
     # ---- roofline of the dominant kernel family: the dense GEMMs of one denoiser evaluation --------------
     roof = gemm_roofline(arch, [B, E], dev, flush, tc_sus, peak_src, args.precision)
-    knn = knn_bench(args, dev, rank, world, hbm_peak, peak_src, flush)
+    knn = knn_bench(args, dev, rank, world, hbm_peak, tc_sus, peak_src, flush)
 
     if rank == 0:
         line = {
@@ -296,20 +297,27 @@ def gemm_roofline_tc(n_clips, dev, flush, tc_peak, peak_src, split):
             "per_shape_tflops": per, "executed_flop_multiplier": 3 if split else 1}
 
 
-def knn_bench(args, dev, rank, world, hbm_peak, peak_src, flush):
-    """configs[3] sweep point: 1M x 768 fp32 embeddings row-sharded over the ranks, top-8, Q=8
-    (one pass over the shard: the HBM-bound regime) through sharded_knn (all-gather + merge)."""
+def knn_bench(args, dev, rank, world, hbm_peak, tc_peak, peak_src, flush):
+    """configs[3]: 1M x 768 fp32 embeddings row-sharded over the ranks, top-8, sweep Q in {1, 8, 64, 4096}
+    through sharded_knn (local top-k, all-gather, merge).  Q <= 8: the exact scan, one pass over the shard
+    (HBM-bound); Q > 8: the tensor-core path (bf16 similarity GEMM, certified over-selection, exact fp32
+    re-score; bit-identical results).  Two rooflines: the scan kernel alone against HBM, knn_tc_kernel
+    alone against the bf16 tensor peak."""
+    import ctypes
     import torch.distributed as dist
-    from rag_gesture_b200.parallel import shard_range, sharded_knn
+    from rag_gesture_b200 import _lib
+    from rag_gesture_b200.parallel import KnnIndex, shard_range, sharded_knn
     n_total, dim, k = args.knn_n, 768, 8
     lo, hi = shard_range(n_total, rank, world)
     g = torch.Generator(device=dev).manual_seed(42 + rank)
     db = torch.nn.functional.normalize(torch.randn(hi - lo, dim, device=dev, generator=g), dim=1)
+    index = KnnIndex(db)
     out = {}
-    for Q in (8, 1, 64):
+    uncert = 0
+    for Q in (8, 1, 64, 4096):
         q = torch.nn.functional.normalize(torch.randn(Q, dim, device=dev, generator=torch.Generator(device=dev).manual_seed(43)), dim=1)
         for _ in range(2):
-            sharded_knn(db, q, k, n_total)
+            sharded_knn(db, q, k, n_total, index=index)
         ts = []
         for _ in range(5):
             flush.zero_()
@@ -318,7 +326,7 @@ def knn_bench(args, dev, rank, world, hbm_peak, peak_src, flush):
                 dist.barrier()
             a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            sharded_knn(db, q, k, n_total)
+            sharded_knn(db, q, k, n_total, index=index)
             e.record()
             torch.cuda.synchronize()
             t = torch.tensor([a.elapsed_time(e) / 1e3], device=dev, dtype=torch.float64)
@@ -326,26 +334,41 @@ def knn_bench(args, dev, rank, world, hbm_peak, peak_src, flush):
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ts.append(float(t))
         t = statistics.median(ts)
-        passes = (Q + 7) // 8
-        gbs = passes * (hi - lo) * dim * 4 / t / 1e9           # the shard is streamed once per 8 queries
-        out[f"q{Q}"] = {"queries_per_sec": round(Q / t, 1), "ms": round(t * 1e3, 3), "hbm_gbs": round(gbs, 1),
-                        "frac_hbm": round(gbs / hbm_peak, 4)}
-    head = out["q8"]
-    # the scan kernel alone (what the HBM roofline is about): CUDA events around the launch only
-    import ctypes
-    from rag_gesture_b200 import _lib
+        row = {"queries_per_sec": round(Q / t, 1), "ms": round(t * 1e3, 3)}
+        if Q <= KnnIndex.min_queries:
+            gbs = (hi - lo) * dim * 4 / t / 1e9               # the fp32 shard is streamed once
+            row.update(path="exact scan", hbm_gbs=round(gbs, 1), frac_hbm=round(gbs / hbm_peak, 4))
+        else:
+            tf = 2.0 * Q * (hi - lo) * dim / t / 1e12
+            row.update(path="tcgen05 + certified re-score", tflops=round(tf, 1), frac_tensor=round(tf / tc_peak, 4),
+                       uncertified=index.last_uncertified)
+            uncert += index.last_uncertified
+        out[f"q{Q}"] = row
+    # the kernels alone (what the rooflines are about): CUDA events around the launch only
+    lib = _lib.load()
     q8 = torch.nn.functional.normalize(torch.randn(8, dim, device=dev), dim=1)
     ms = ctypes.c_float()
-    _lib.check(_lib.load().rg_probe_knn_scan(_lib.ptr(db), hi - lo, dim, _lib.ptr(q8), 8, k, 5, _lib.ptr(flush),
-                                             flush.numel(), ctypes.byref(ms), _lib.stream_ptr()))
-    head = dict(head, hbm_gbs=round((hi - lo) * dim * 4 / (ms.value / 1e3) / 1e9, 1), scan_ms=round(ms.value, 3))
-    head["frac_hbm"] = round(head["hbm_gbs"] / hbm_peak, 4)
-    return {"queries_per_sec": head["queries_per_sec"], "n": n_total, "dim": dim, "k": k, "q": 8, "ms": head["ms"],
-            "sweep": out,
+    _lib.check(lib.rg_probe_knn_scan(_lib.ptr(db), hi - lo, dim, _lib.ptr(q8), 8, k, 5, _lib.ptr(flush),
+                                     flush.numel(), ctypes.byref(ms), _lib.stream_ptr()))
+    scan_gbs = (hi - lo) * dim * 4 / (ms.value / 1e3) / 1e9
+    q4k = torch.nn.functional.normalize(torch.randn(4096, dim, device=dev), dim=1)
+    ms_tc = ctypes.c_float()
+    _lib.check(lib.rg_probe_knn_tc(index.handle, _lib.ptr(q4k), 4096, 5, _lib.ptr(flush), flush.numel(),
+                                   ctypes.byref(ms_tc), _lib.stream_ptr()))
+    tc_tf = 2.0 * 4096 * (hi - lo) * dim / (ms_tc.value / 1e3) / 1e12
+    head = out["q4096"]
+    index.close()
+    return {"queries_per_sec": head["queries_per_sec"], "n": n_total, "dim": dim, "k": k, "q": 4096, "ms": head["ms"],
+            "uncertified_queries": uncert, "sweep": out,
             "roofline": {"bound": "hbm", "kernel": "knn_scan768_kernel<8> alone (exact fp32, 8 queries, 1 pass over the shard)",
-                         "launch_ms": head["scan_ms"],
-                         "achieved": head["hbm_gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": head["frac_hbm"],
-                         "peak_source": peak_src, "bytes_per_launch": (hi - lo) * dim * 4}}
+                         "launch_ms": round(ms.value, 3), "achieved": round(scan_gbs, 1), "peak": hbm_peak, "unit": "GB/s",
+                         "frac": round(scan_gbs / hbm_peak, 4), "peak_source": peak_src,
+                         "bytes_per_launch": (hi - lo) * dim * 4},
+            "roofline_tc": {"bound": "tensor", "kernel": "knn_tc_kernel alone (tcgen05 bf16 similarity of 4096 queries x shard, "
+                            "top-16 per (query, chunk) selected in the epilogue; scores never leave the SM)",
+                            "launch_ms": round(ms_tc.value, 3), "achieved": round(tc_tf, 1), "peak": tc_peak,
+                            "unit": "TFLOP/s", "frac": round(tc_tf / tc_peak, 4), "peak_source": f"{peak_src} bf16 sustained",
+                            "flop_per_launch": 2.0 * 4096 * (hi - lo) * dim}}
 
 
 # ---- the reference's algorithm on the host cores ------------------------------------------------------

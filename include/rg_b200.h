@@ -216,6 +216,28 @@ int rg_probe_knn_scan(const float* db, int64_t n, int dim, const float* queries,
 int rg_knn_merge(const int64_t* idx_parts, const float* score_parts, int parts, int q, int k,
                  int64_t* out_idx, float* out_score, void* stream);
 
+/* ---- large query batches: tensor-core similarity + certified over-selection (knn_tc.cu) ----
+ * Same contract and bit-identical results as rg_knn_topk, for the Q = 4096 sweep of configs[3] where one exact
+ * pass per 8 queries would stream the shard 512 times.  The reference has no batched path that is used
+ * (sort_sidx_by_textsimilarity_batched, rag/utils.py:135-168, is dead code with a different ranking); the
+ * operation replaced is the per-candidate loop of rag/utils.py:107-118 applied to many queries at once.
+ *
+ * rg_knn_index_create: one-off bf16 copy of the shard [n, dim] (dim % 64 == 0, n < 2^31-256) and its largest
+ * row norm; owns 2*n*dim bytes of device memory until rg_knn_index_destroy.  `db` is only read during the call.
+ * rg_knn_topk_tc: S = Q*D^T on tcgen05 (bf16 operands, fp32 TMEM accumulators) with the top-16 of every
+ * (query, chunk) selected in the epilogue, exact fp32 re-score of the best 64 candidates per query in the
+ * summation order of rg_knn_topk, and a per-query error-bound certificate; queries without one are re-run
+ * through rg_knn_topk and counted in *n_uncertified (may be NULL).  `db` must be the fp32 shard the index
+ * was built from.  Synchronises `stream` once (reads the uncertified count). */
+int rg_knn_index_create(const float* db, int64_t n, int dim, void** index, void* stream);
+int rg_knn_index_destroy(void* index);
+int rg_knn_topk_tc(void* index, const float* db, const float* queries, int q, int k, int64_t idx_base,
+                   int64_t* out_idx, float* out_score, int32_t* n_uncertified, void* stream);
+/* Measurement probe: times ONLY knn_tc_kernel (`reps` launches, CUDA events on `stream`, flush_buf overwritten
+ * before each) -> *median_ms; algorithmic work of one launch = 2*q*n*dim flop. */
+int rg_probe_knn_tc(void* index, const float* queries, int q, int reps, void* flush_buf, int64_t flush_bytes,
+                    float* median_ms, void* stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

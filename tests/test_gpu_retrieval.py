@@ -113,6 +113,67 @@ def test_knn_merge_matches_single_shard(dev):
     assert torch.equal(mi, full_i) and torch.equal(ms, full_s)
 
 
+@pytest.mark.parametrize("N,Q,k,dim", [(20000, 300, 8, 768), (4099, 64, 8, 768), (100000, 1000, 8, 768),
+                                         (777, 130, 16, 768), (40, 9, 8, 768), (5, 12, 8, 768),
+                                         (3001, 257, 8, 256), (9000, 33, 32, 768)])
+def test_knn_topk_tc_bit_identical(dev, N, Q, k, dim):
+    """Tensor-core path (bf16 similarity GEMM + over-selection + certified exact re-score) == the exact
+    fp32 scan, indices AND scores bit for bit, including duplicate rows (tie -> lower index), shards
+    smaller than k, ragged last tiles (N % 256, Q % 256 != 0) and a generic dim."""
+    from rag_gesture_b200.parallel import KnnIndex, knn_topk
+    g = torch.Generator().manual_seed(N + Q)
+    db = torch.nn.functional.normalize(torch.randn(N, dim, generator=g), dim=1)
+    qs = torch.nn.functional.normalize(torch.randn(Q, dim, generator=g), dim=1)
+    if N == 777:
+        db[500:520] = db[100:120]
+    db, qs = db.to(dev), qs.to(dev)
+    index = KnnIndex(db)
+    idx, sc = knn_topk(db, qs, k, idx_base=1000, index=index)
+    ref_idx, ref_sc = knn_topk(db, qs, k, idx_base=1000)
+    assert torch.equal(idx, ref_idx)
+    assert torch.equal(sc, ref_sc)
+    if k <= 16 and N != 777:
+        assert index.last_uncertified == 0            # random unit-norm data: every query is certified
+    index.close()
+
+
+def test_knn_topk_tc_unnormalised_and_fallback(dev):
+    """Un-normalised features with a wide norm spread (the reference ranks raw BERT sums, rag/utils.py:104-118)
+    and a clustered database where 40 near-duplicates of each query sit in one chunk: the certificate must
+    refuse (k-th exact score is not separated from the bound) and the exact fallback must give the answer."""
+    from rag_gesture_b200.parallel import KnnIndex, knn_topk
+    g = torch.Generator().manual_seed(11)
+    db = torch.randn(30000, 768, generator=g) * (0.2 + 3 * torch.rand(30000, 1, generator=g))
+    qs = torch.randn(40, 768, generator=g) * 2.5
+    # cluster: rows 256..295 are tiny perturbations of query 0 -> 40 candidates of one chunk above everything
+    db[256:296] = qs[0] + 1e-3 * torch.randn(40, 768, generator=g)
+    db, qs = db.to(dev), qs.to(dev)
+    index = KnnIndex(db)
+    idx, sc = knn_topk(db, qs, 32, index=index)
+    ref_idx, ref_sc = knn_topk(db, qs, 32)
+    assert torch.equal(idx, ref_idx) and torch.equal(sc, ref_sc)
+    assert index.last_uncertified >= 1
+    index.close()
+
+
+def test_knn_tc_sharded_merge(dev):
+    """8 tensor-core shard indexes + the merge kernel == the unsharded exact scan."""
+    from rag_gesture_b200.parallel import KnnIndex, _cuda_merge, knn_topk, shard_range
+    g = torch.Generator().manual_seed(4)
+    db = torch.nn.functional.normalize(torch.randn(40003, 768, generator=g), dim=1).to(dev)
+    qs = torch.nn.functional.normalize(torch.randn(200, 768, generator=g), dim=1).to(dev)
+    full_i, full_s = knn_topk(db, qs, 8)
+    parts_i, parts_s = [], []
+    for r in range(8):
+        lo, hi = shard_range(db.shape[0], r, 8)
+        shard = db[lo:hi].contiguous()
+        i, s = knn_topk(shard, qs, 8, idx_base=lo, index=KnnIndex(shard))
+        parts_i.append(i)
+        parts_s.append(s)
+    mi, ms = _cuda_merge(torch.stack(parts_i), torch.stack(parts_s), 8)
+    assert torch.equal(mi, full_i) and torch.equal(ms, full_s)
+
+
 @pytest.fixture(scope="module")
 def arch(dev):
     import rag_gesture_b200 as R
