@@ -44,7 +44,7 @@ constexpr int KP = 16;             // candidates kept per (query, chunk)
 constexpr int RESCORE = 64;        // candidates re-scored exactly per query
 constexpr int MAX_CHUNKS = 256;    // chunks * KP <= 4096 entries sorted per query
 constexpr int STAGE_BYTES = (TQ + TN) * BK * 2;                    // 64 KB
-constexpr int LIST_BYTES = TQ * KP * (int)(sizeof(float) + sizeof(int));   // 32 KB
+constexpr int LIST_BYTES = TQ * (KP * (int)(sizeof(float) + sizeof(int)) + (int)sizeof(int));   // 33 KB
 constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + LIST_BYTES;
 constexpr int N_EPI_WARPS = 8;
 constexpr long long IDX_NONE = 0x7fffffffffffffffLL;
@@ -61,18 +61,24 @@ struct KnnTcParams {
     int* cand_idx;
 };
 
-__device__ __noinline__ float cand_insert(float* ls, int* li, float v, int id) {
-    int j = KP - 1;
-    while (j > 0) {
-        const float u = ls[(j - 1) * TQ];
-        if (!(u < v)) break;
-        ls[j * TQ] = u;
-        li[j * TQ] = li[(j - 1) * TQ];
-        --j;
+// Candidate list of one query thread: KP (score, row) pairs, UNSORTED, in shared memory ([KP][TQ]: the
+// thread index is the fastest dimension, so every access is conflict-free), plus the slot of its minimum.
+// A new candidate overwrites the minimum; the new minimum (= the thread's threshold) is found with KP
+// independent loads.  One out-of-line copy: 256 call sites sit in the unrolled epilogue loop.
+__device__ __noinline__ float cand_replace(float* ls, int* li, int* lslot, float v, int id, int n_rows, float thr) {
+    if (id >= n_rows) return thr;              // TMA zero fill of the last, partial database tile
+    const int slot = *lslot;
+    ls[slot * TQ] = v;
+    li[slot * TQ] = id;
+    float m = ls[0];
+    int ms = 0;
+#pragma unroll
+    for (int j = 1; j < KP; ++j) {
+        const float u = ls[j * TQ];
+        if (u < m) { m = u; ms = j; }
     }
-    ls[j * TQ] = v;
-    li[j * TQ] = id;
-    return ls[(KP - 1) * TQ];
+    *lslot = ms;
+    return m;
 }
 
 __global__ void __launch_bounds__(320, 1)
@@ -81,6 +87,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     float* list_s = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);     // [KP][TQ]
     int* list_i = reinterpret_cast<int*>(list_s + KP * TQ);
+    int* list_slot = list_i + KP * TQ;                                         // [TQ] slot of the minimum
     __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar, tmem_empty_bar;
     __shared__ uint32_t tmem_base_smem;
 
@@ -166,6 +173,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         const int qrow = half * 128 + lg * 32 + lane;  // query row inside the tile
         float* ls = list_s + qrow;
         int* li = list_i + qrow;
+        int* lslot = list_slot + qrow;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + half * TN;
         uint32_t tl = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -174,12 +182,12 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             const int t1 = min(t0 + p.tiles_per_chunk, p.tiles_total);
 #pragma unroll
             for (int j = 0; j < KP; ++j) { ls[j * TQ] = -INFINITY; li[j * TQ] = -1; }
+            *lslot = 0;
             float thr = -INFINITY;
             for (int t = t0; t < t1; ++t, ++tl) {
                 mbar_wait(smem_u32(&tmem_full_bar), tl & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const int row0 = t * TN;
-                const int valid = p.n_rows - row0;     // rows >= valid are TMA zero fill
 #pragma unroll 1
                 for (int c = 0; c < TN / 64; ++c) {
                     uint32_t v0[32], v1[32];
@@ -194,12 +202,12 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
                         const float s = __uint_as_float(v0[i]);
-                        if (s > thr && c * 64 + i < valid) thr = cand_insert(ls, li, s, row0 + c * 64 + i);
+                        if (s > thr) thr = cand_replace(ls, li, lslot, s, row0 + c * 64 + i, p.n_rows, thr);
                     }
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
                         const float s = __uint_as_float(v1[i]);
-                        if (s > thr && c * 64 + 32 + i < valid) thr = cand_insert(ls, li, s, row0 + c * 64 + 32 + i);
+                        if (s > thr) thr = cand_replace(ls, li, lslot, s, row0 + c * 64 + 32 + i, p.n_rows, thr);
                     }
                 }
             }
@@ -302,10 +310,14 @@ knn_tc_finish_kernel(const float* __restrict__ db, int dim, const float* __restr
         si[e] = id;
     }
     __syncthreads();
-    // rows outside the lists: a FULL list bounds them by its last entry
+    // rows outside the lists: a FULL list (unsorted) bounds them by its minimum
     float mt = -INFINITY;
-    for (int c = tid; c < chunks; c += 256)
-        if (si[c * KP + KP - 1] >= 0) mt = fmaxf(mt, sa[c * KP + KP - 1]);
+    for (int c = tid; c < chunks; c += 256) {
+        float mn = INFINITY;
+        bool full = true;
+        for (int j = 0; j < KP; ++j) { full = full && si[c * KP + j] >= 0; mn = fminf(mn, sa[c * KP + j]); }
+        if (full) mt = fmaxf(mt, mn);
+    }
     const float m_max = block_reduce(mt, true, red, warp, lane);
     const int n_valid = (int)(block_reduce((float)n_valid_t, false, red, warp, lane) + 0.5f);
     const float* qv = queries + (size_t)q * dim;
@@ -393,11 +405,11 @@ Plan make_plan(long long n, int q) {
     Plan pl;
     pl.tiles_total = (int)((n + TN - 1) / TN);
     pl.q_tiles = (q + TQ - 1) / TQ;
-    // about four waves of items over 148 SMs, chunks <= MAX_CHUNKS (the finish kernel sorts chunks*KP entries)
-    int chunks = (148 * 4 + pl.q_tiles - 1) / pl.q_tiles;
+    // ONE wave of items over the 148 SMs: a list costs ~KP*ln(rows/KP) replacements per chunk, so long chunks
+    // keep the epilogue (which the single-buffered accumulator serialises with the MMAs) short.  The CTAs that
+    // run concurrently are the q_tiles tiles of the same few chunks: a database tile is fetched from DRAM once.
+    int chunks = std::max(1, 148 / pl.q_tiles);
     chunks = std::max(1, std::min(chunks, std::min(MAX_CHUNKS, pl.tiles_total)));
-    if (pl.q_tiles * chunks > 148)          // whole waves: round the item count down to a multiple of 148
-        chunks = std::max(1, (pl.q_tiles * chunks / 148) * 148 / pl.q_tiles);
     pl.tiles_per_chunk = (pl.tiles_total + chunks - 1) / chunks;
     pl.chunks = (pl.tiles_total + pl.tiles_per_chunk - 1) / pl.tiles_per_chunk;
     pl.grid = std::min(148, pl.q_tiles * pl.chunks);
