@@ -44,14 +44,15 @@ constexpr int KP = 16;             // candidates kept per (query, chunk)
 constexpr int RESCORE = 64;        // candidates re-scored exactly per query
 constexpr int MAX_CHUNKS = 256;    // chunks * KP <= 4096 entries sorted per query
 constexpr int STAGE_BYTES = (TQ + TN) * BK * 2;                    // 64 KB
-constexpr int LIST_BYTES = TQ * (KP * (int)(sizeof(float) + sizeof(int)) + (int)sizeof(int));   // 33 KB
+constexpr int LIST_BYTES = TQ * KP * (int)(sizeof(float) + sizeof(int));   // 32 KB
 constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + LIST_BYTES;
 constexpr int N_EPI_WARPS = 8;
 constexpr long long IDX_NONE = 0x7fffffffffffffffLL;
 // |approx - exact| <= C_EPS * |q| * |d|: 2u + u^2 with u = 2^-8 (two bf16 roundings per product), plus the
 // fp32 accumulation error of both sums (<= 2 * 768 * 2^-23 relative to sum|q_i d_i| at dim 768; scaled with
 // dim below), plus slack for the fp32 rounding of the norms themselves.
-constexpr float C_EPS_BF16 = 0.0078125f + 0.0000153f;
+// The slot bits in the stored scores move a score / threshold by at most 2^-19 relative (|score| <= |q||d|).
+constexpr float C_EPS_BF16 = 0.0078125f + 0.0000153f + 0.0000077f;
 
 struct KnnTcParams {
     int n_rows, q_total, nkb;
@@ -62,23 +63,26 @@ struct KnnTcParams {
 };
 
 // Candidate list of one query thread: KP (score, row) pairs, UNSORTED, in shared memory ([KP][TQ]: the
-// thread index is the fastest dimension, so every access is conflict-free), plus the slot of its minimum.
-// A new candidate overwrites the minimum; the new minimum (= the thread's threshold) is found with KP
-// independent loads.  One out-of-line copy: 256 call sites sit in the unrolled epilogue loop.
-__device__ __noinline__ float cand_replace(float* ls, int* li, int* lslot, float v, int id, int n_rows, float thr) {
+// thread index is the fastest dimension, so every access is conflict-free).  The low 4 mantissa bits of a
+// stored score hold its slot number (a 2^-19 relative perturbation, charged to the certificate's eps), so
+// the minimum of the list -- the thread's threshold `thr` -- also names the slot a new candidate overwrites,
+// and the new minimum is one 4-level FMNMX tree over KP independent loads (no compare/select chain).
+// One out-of-line copy: 256 call sites sit in the unrolled epilogue loop.
+static_assert(KP == 16, "slot number is kept in 4 mantissa bits");
+__device__ __forceinline__ float slot_init(int j) { return __uint_as_float(0xff7ffff0u | (unsigned)j); }   // ~ -FLT_MAX
+__device__ __noinline__ float cand_replace(float* ls, int* li, float v, int id, int n_rows, float thr) {
     if (id >= n_rows) return thr;              // TMA zero fill of the last, partial database tile
-    const int slot = *lslot;
-    ls[slot * TQ] = v;
+    const int slot = (int)(__float_as_uint(thr) & 15u);
+    ls[slot * TQ] = __uint_as_float((__float_as_uint(v) & ~15u) | (unsigned)slot);
     li[slot * TQ] = id;
-    float m = ls[0];
-    int ms = 0;
+    float u[KP];
 #pragma unroll
-    for (int j = 1; j < KP; ++j) {
-        const float u = ls[j * TQ];
-        if (u < m) { m = u; ms = j; }
-    }
-    *lslot = ms;
-    return m;
+    for (int j = 0; j < KP; ++j) u[j] = ls[j * TQ];
+#pragma unroll
+    for (int w = KP / 2; w >= 1; w >>= 1)
+#pragma unroll
+        for (int j = 0; j < w; ++j) u[j] = fminf(u[j], u[j + w]);
+    return u[0];
 }
 
 __global__ void __launch_bounds__(320, 1)
@@ -87,7 +91,6 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     float* list_s = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);     // [KP][TQ]
     int* list_i = reinterpret_cast<int*>(list_s + KP * TQ);
-    int* list_slot = list_i + KP * TQ;                                         // [TQ] slot of the minimum
     __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar, tmem_empty_bar;
     __shared__ uint32_t tmem_base_smem;
 
@@ -173,7 +176,6 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         const int qrow = half * 128 + lg * 32 + lane;  // query row inside the tile
         float* ls = list_s + qrow;
         int* li = list_i + qrow;
-        int* lslot = list_slot + qrow;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + half * TN;
         uint32_t tl = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -181,9 +183,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             const int t0 = ch * p.tiles_per_chunk;
             const int t1 = min(t0 + p.tiles_per_chunk, p.tiles_total);
 #pragma unroll
-            for (int j = 0; j < KP; ++j) { ls[j * TQ] = -INFINITY; li[j * TQ] = -1; }
-            *lslot = 0;
-            float thr = -INFINITY;
+            for (int j = 0; j < KP; ++j) { ls[j * TQ] = slot_init(j); li[j * TQ] = -1; }
+            float thr = slot_init(KP - 1);          // the most negative of the initial entries
             for (int t = t0; t < t1; ++t, ++tl) {
                 mbar_wait(smem_u32(&tmem_full_bar), tl & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -199,15 +200,23 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                         __syncwarp();
                         if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar));
                     }
+                    // four scores per branch: the common case (none above the threshold) costs a 3-input max
+                    // tree and one compare; only a group with a hit is examined element by element
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const float s = __uint_as_float(v0[i]);
-                        if (s > thr) thr = cand_replace(ls, li, lslot, s, row0 + c * 64 + i, p.n_rows, thr);
-                    }
+                    for (int h = 0; h < 2; ++h) {
+                        const uint32_t* v = h ? v1 : v0;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const float s = __uint_as_float(v1[i]);
-                        if (s > thr) thr = cand_replace(ls, li, lslot, s, row0 + c * 64 + 32 + i, p.n_rows, thr);
+                        for (int i = 0; i < 32; i += 4) {
+                            const float s0 = __uint_as_float(v[i]), s1 = __uint_as_float(v[i + 1]);
+                            const float s2 = __uint_as_float(v[i + 2]), s3 = __uint_as_float(v[i + 3]);
+                            if (fmaxf(fmaxf(s0, s1), fmaxf(s2, s3)) > thr) {
+                                const int r = row0 + c * 64 + h * 32 + i;
+                                if (s0 > thr) thr = cand_replace(ls, li, s0, r, p.n_rows, thr);
+                                if (s1 > thr) thr = cand_replace(ls, li, s1, r + 1, p.n_rows, thr);
+                                if (s2 > thr) thr = cand_replace(ls, li, s2, r + 2, p.n_rows, thr);
+                                if (s3 > thr) thr = cand_replace(ls, li, s3, r + 3, p.n_rows, thr);
+                            }
+                        }
                     }
                 }
             }
