@@ -78,7 +78,10 @@ class MotionDiffusion(nn.Module):
         return self.finish(gb, output)
 
     # ---- stage 1: host logic + codec + retrieval (everything that is not the denoising loops) ----
-    def prepare(self, **kwargs):
+    def prepare(self, defer_conditions=False, **kwargs):
+        """defer_conditions=True leaves out the one engine call of this stage (the text/audio/speaker
+        pre-projection of the B clips); `encode_clip_conditions(gb)` adds it later.  GuidedPipeline uses
+        this to run the stage on a worker thread without touching the denoiser handle."""
         if self.training:
             raise NotImplementedError("rg_b200 is inference-only; call model.eval()")
         kwargs = self._scatter(kwargs)
@@ -120,7 +123,11 @@ class MotionDiffusion(nn.Module):
         kwargs.update({"motion_mask": motion_mask, "text": kwargs["word"], "raw_text": kwargs["raw_word"],
                        "text_times": kwargs["text_segments"]})
         with torch.no_grad():
-            model_kwargs = self.model.get_precompute_condition(device=device, **kwargs)
+            if defer_conditions:
+                model_kwargs = self.model.get_precompute_condition(device=device, xf_out={}, **kwargs)
+                gb.cond_inputs = (kwargs["text"], kwargs["audio"], kwargs["speaker_ids"])
+            else:
+                model_kwargs = self.model.get_precompute_condition(device=device, **kwargs)
         model_kwargs["query_mask"] = query_masks
         model_kwargs["motion_mask"] = motion_mask
         model_kwargs["sample_idx"] = kwargs.get("sample_idx", None)
@@ -147,6 +154,16 @@ class MotionDiffusion(nn.Module):
                 gb.ex_query_mask = {c: m[clip_of] for c, m in query_masks.items()}
                 gb.windows = [(retrieval_dict["retr_startends"][b][q], retrieval_dict["query_startends"][b][q])
                               for b, q in gb.jobs]
+        return gb
+
+    def encode_clip_conditions(self, gb):
+        """The deferred part of prepare(defer_conditions=True): xf_text / xf_audio / xf_spk of the B clips."""
+        if gb.cond_inputs is not None:
+            text, audio, spk = gb.cond_inputs
+            with torch.no_grad():
+                gb.model_kwargs["xf_out"] = self.model.rg_engine().encode_conditions(
+                    text.to(gb.device), audio.to(gb.device), spk.to(gb.device))
+            gb.cond_inputs = None
         return gb
 
     def mask_prev_latent(self, prev):
@@ -235,7 +252,80 @@ class MotionDiffusion(nn.Module):
 class GuidedBatch:
     """Device-resident inputs of one guided batch between MotionDiffusion.prepare and run_prepared."""
     jobs, ex, ex_query_mask, windows, outpaint_seq, prev_latent, inv = (), None, None, (), None, None, None
+    cond_inputs = None
 
     def clip_steps(self, num_timesteps):
         """Work of the batch in the metric's unit: 50 * (B + E)."""
         return num_timesteps * (self.shape[0] + len(self.jobs))
+
+
+def _record_streams(obj, stream, _seen=None):
+    """Tell the caching allocator that every CUDA tensor reachable from `obj` is also used on `stream`."""
+    _seen = set() if _seen is None else _seen
+    if id(obj) in _seen:
+        return
+    _seen.add(id(obj))
+    if torch.is_tensor(obj):
+        if obj.is_cuda:
+            obj.record_stream(stream)
+    elif isinstance(obj, dict):
+        for v in obj.values():
+            _record_streams(v, stream, _seen)
+    elif isinstance(obj, (list, tuple)):
+        for v in obj:
+            _record_streams(v, stream, _seen)
+    elif isinstance(obj, GuidedBatch):
+        _record_streams(vars(obj), stream, _seen)
+
+
+class GuidedPipeline:
+    """Throughput form of `for batch in loader: model(**batch)` (tools/visualize.py:189-200): while the
+    denoising loops of batch i run, a worker thread executes stage 1 of batch i+1 -- H2D of the pinned host
+    batch, codec encode, discourse retrieval with its text-similarity ranking, exemplar fetch and encode -- on
+    a side stream.  Results are identical to sequential forward() calls: the worker never touches the
+    denoiser handle (the clip pre-projection is deferred to the main thread), it alone draws from the CPU
+    generator (codec rsample noise) and the main thread alone from the CUDA generator (sampler noise), so the
+    draw order of every generator is the sequential one.
+
+        for results in GuidedPipeline(model).run(loader): ...
+    """
+
+    def __init__(self, arch):
+        import sys
+        self.arch = arch
+        self.device = arch.model.out.weight.device
+        if self.device.type != "cuda":
+            raise RuntimeError("rg_b200: GuidedPipeline needs the model on a CUDA device (no CPU fallback)")
+        self.side = torch.cuda.Stream(self.device)
+        # the main thread re-acquires the GIL after every C-ABI call; keep the worker's time slices short
+        if sys.getswitchinterval() > 5e-4:
+            sys.setswitchinterval(5e-4)
+
+    def _stage1(self, kwargs, main, after):
+        with torch.cuda.device(self.device), torch.cuda.stream(self.side):
+            if after is not None:
+                self.side.wait_event(after)        # blocks freed by an earlier batch are not reused early
+            gb = self.arch.prepare(defer_conditions=True, **kwargs)
+            ready = self.side.record_event()
+        _record_streams(gb, main)
+        return gb, ready
+
+    def run(self, batches):
+        """batches: iterable of forward() keyword dicts (host or device tensors).  Yields the result dict of
+        each batch in order; at most one batch is prepared ahead."""
+        from concurrent.futures import ThreadPoolExecutor
+        main = torch.cuda.current_stream(self.device)
+        it = iter(batches)
+        try:
+            first = next(it)
+        except StopIteration:
+            return
+        with ThreadPoolExecutor(max_workers=1, thread_name_prefix="rg-stage1") as pool:
+            fut = pool.submit(self._stage1, dict(first), main, None)
+            while fut is not None:
+                gb, ready = fut.result()
+                nxt = next(it, None)
+                fut = pool.submit(self._stage1, dict(nxt), main, main.record_event()) if nxt is not None else None
+                main.wait_event(ready)
+                self.arch.encode_clip_conditions(gb)
+                yield self.arch.finish(gb, self.arch.run_prepared(gb))

@@ -255,3 +255,42 @@ def test_resident_corpus_matches_host_fetch(arch, dev):
     ra, rb = a.model_kwargs["re_dict"], b.model_kwargs["re_dict"]
     for k in ("raw_motion_latents", "raw_motion", "raw_trans", "raw_facial", "re_mask"):
         assert torch.equal(ra[k], rb[k]), k
+
+
+def test_guided_pipeline_equals_sequential_forward(arch, dev):
+    """GuidedPipeline (stage 1 of batch i+1 on a worker thread + side stream while batch i's loops run) gives
+    bit-identical results to sequential MotionDiffusion.forward calls: same host batches, same seeds."""
+    from rag_gesture_b200.architecture import GuidedPipeline
+    qs = S.SyntheticGestureDataset(N_QUERY, seed=8)
+    arch.diffusion_test.noise_fn = None          # sampler noise from the CUDA generator (main thread)
+
+    def batches():
+        for ids in ([1, 2, 4], [7, 8], [10, 11, 12, 13], [20]):
+            b = S.collate([qs[i] for i in ids])
+            for k, v in b.items():
+                if torch.is_tensor(v):
+                    b[k] = v.pin_memory()
+            b["retrieval_method"] = "discourse"
+            b["inference_kwargs"] = dict(use_inversion=True, outpaint=False, inversion_start_time=-1,
+                                         insertion_guidance=True, guidance_iters=[0] * 25 + list(range(25)),
+                                         guidance_lr=0.1)
+            yield b
+
+    def reset():
+        db = arch.model.database
+        for d in (db.test_indexes, db.test_dbounds, db.test_qbounds):
+            d.clear()
+        torch.manual_seed(5)
+        torch.cuda.manual_seed(6)
+
+    def grab(r):
+        return {k: r[k].cpu() for k in ("prev_latentout", "pred_upper", "pred_hands")}
+
+    reset()
+    seq = [grab(arch(**b)) for b in batches()]
+    reset()
+    pipe = [grab(r) for r in GuidedPipeline(arch).run(batches())]
+    assert len(pipe) == len(seq) == 4
+    for a, b in zip(seq, pipe):
+        for k in a:
+            assert torch.equal(a[k], b[k]), k
