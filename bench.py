@@ -169,7 +169,13 @@ def run_b200(args):
     if args.ncu_steps:
         return ncu_pass(args, arch, batch, dev)
     # ---- value: device-resident loops -------------------------------------------------------------
-    gb = arch.prepare(**dict(batch, inference_kwargs=infer_kwargs()))
+    # K prepared batches (inputs, exemplars and retrieval results resident in HBM) through
+    # MotionDiffusion.run_many: pass k = guided loop of batch k-1 fused level by level with the inversion loop
+    # of batch k's exemplars (one kernel chain per level for both); the un-fused head (inversion of batch 0)
+    # and tail (guided loop of batch K-1) are inside the timed region.  "sequential" = run_prepared per batch.
+    n_gb = max(2, args.steps)
+    gbs = [arch.prepare(**dict(batch, inference_kwargs=infer_kwargs())) for _ in range(n_gb)]
+    gb = gbs[0]
     E = len(gb.jobs)
     clip_steps = gb.clip_steps(STEPS)
     sampler = ClockSampler(local)
@@ -177,13 +183,27 @@ def run_b200(args):
 
     def hot():
         out_holder["x"] = arch.run_prepared(gb)
+    t_seq = timed(hot, args.steps, args.warmup)
+    for _ in range(max(1, args.warmup // 2)):
+        arch.run_many(gbs[:2])
+    barrier()
+    flush.zero_()
     n0 = launch_count()
-    t_hot = timed(hot, args.steps, args.warmup)
-    launches = (launch_count() - n0) // (args.steps + args.warmup)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    out_holder["x"] = arch.run_many(gbs[:args.steps])
+    b.record()
+    barrier()
+    launches = (launch_count() - n0) // args.steps
+    t = torch.tensor([a.elapsed_time(b) / 1e3], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t_hot = float(t)
     total_steps = torch.tensor([clip_steps], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(total_steps)
     value = float(total_steps) * args.steps / t_hot
+    value_seq = float(total_steps) * args.steps / t_seq
 
     # ---- e2e: the public API with host buffers ---------------------------------------------------------
     # Every step: H2D of that step's pinned host batch, retrieval from scratch (caches cleared), codec,
@@ -245,7 +265,12 @@ def run_b200(args):
                        "precision": {"bf16": "tcgen05 bf16 operands, fp32 TMEM accumulate (parity tier rel-L2 <= 2e-2)",
                                      "bf16x3": "tcgen05 hi+lo bf16 split, 3 products (parity tier rel-L2 <= 1e-3)",
                                      "fp32": "fp32 FMA GEMMs (exact tier)"}[args.precision],
-                       "l2": "256 MiB flush between timed iterations; fp32 weights (564 MB) exceed L2",
+                       "l2": "256 MiB flush before the timed region; each pass streams bf16 weights (77 MB) + K6 state "
+                             "(250 MB) + activations, i.e. more than the 126 MB L2",
+                       "schedule": "run_many: guided loop of batch k-1 fused with the inversion loop of batch k "
+                                   "(rg_denoise_groups); head and tail passes un-fused, inside the timed region",
+                       "sequential": {"value": round(value_seq, 2), "ms_per_step": round(1e3 * t_seq / args.steps, 3),
+                                      "api": "run_prepared per batch: inversion loop, then guided loop"},
                        "parallelism": f"clips sharded over {world} GPU(s), no collective in the loop"},
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes(batch),
                     "d2h_bytes_per_step": host_out.numel() * 4, "ms_per_step": round(1e3 * t_e2e / args.steps, 3),

@@ -102,6 +102,16 @@ int rg_precompute_clip_state(rg_handle h, const float* xf_text, const float* xf_
 int rg_denoise(rg_handle h, const float* x, int B, int step_idx, int tau, const float* src_mask,
                const float* query_mask, const float* state, float* x0_out, void* stream);
 
+/* The same evaluation for a batch made of `n_groups` (<= 8) consecutive clip ranges, each at its OWN schedule
+ * level: clips [sum(group_clips[:g]), +group_clips[g]) are evaluated at step_idx group_step_idx[g] (host arrays).
+ * The reference never mixes timesteps in a batch (gaussian_diffusion.py:1283 fills `t` with one value); no op of
+ * the denoiser couples clips, so every clip's output equals what rg_denoise gives it in a single-level batch.
+ * Used to run the guided sampling of one batch and the DDIM inversion of the next batch's exemplars as ONE
+ * kernel chain (the per-kernel fixed cost is paid once for both). */
+int rg_denoise_groups(rg_handle h, const float* x, int B, int n_groups, const int32_t* group_clips,
+                      const int32_t* group_step_idx, const float* src_mask, const float* query_mask,
+                      const float* state, float* x0_out, void* stream);
+
 /* How many concurrent kernel chains ("lanes", contiguous clip ranges on separate streams, joined back
  * onto the caller's stream before the call returns) one rg_denoise uses: 0 = automatic (currently 1),
  * 1..4 fixed.  Results do not depend on the setting: clips never interact inside a step. */

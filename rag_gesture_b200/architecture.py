@@ -200,29 +200,38 @@ class MotionDiffusion(nn.Module):
             off += len(gb.jobs)
 
     # ---- stage 2: the hot path proper, device-resident inputs -> output latents ---------------------
+    def _guided_inputs(self, gb):
+        """start_noise and the per-level insertion targets of a batch whose exemplars are inverted (gb.inv):
+        upper-body and hands windows of the inverted latents placed at the query windows (:394-407)."""
+        diff, (B, T, D), device = self.diffusion_test, gb.shape, gb.device
+        n = (T - 3) // 4
+        start_noise = diff._randn((B, T, D), device)
+        inv_per_t = torch.zeros(diff.num_timesteps, B, T, D, device=device) if gb.use_guidance else None
+        if gb.jobs:
+            inv = gb.inv
+            for e, ((b, _), ((r0, r1), (q0, q1))) in enumerate(zip(gb.jobs, gb.windows)):
+                assert r1 - r0 == q1 - q0
+                for o in (0, n + 1):                    # upper body and hands only
+                    start_noise[b, o + q0:o + q1] = inv[gb.inversion_start_time, e, o + r0:o + r1]
+                    if gb.use_guidance:
+                        inv_per_t[:, b, o + q0:o + q1] = inv[:, e, o + r0:o + r1]
+        if gb.use_guidance and gb.use_prev and gb.prev_latent is not None:
+            inv_per_t[:, :, [0, n + 1, 2 * n + 2, 3 * n + 3], :] = 0
+        return start_noise, inv_per_t
+
     def run_prepared(self, gb, keep_inversion=False):
         """K6 state for the B clips and E exemplars, ONE batched 50-step inversion of the exemplars,
         window insertion, 50 guided (or plain) sampling steps: 50 * (B + E) clip-steps."""
-        diff, (B, T, D), device = self.diffusion_test, gb.shape, gb.device
-        n = (T - 3) // 4
+        diff, (B, T, D) = self.diffusion_test, gb.shape
         start_noise, inv_per_t = None, None
         if gb.use_inversion:
-            start_noise = diff._randn((B, T, D), device)
-            if gb.use_guidance:
-                inv_per_t = torch.zeros(diff.num_timesteps, B, T, D, device=device)
             if gb.jobs:
+                # the reference draws start_noise before it inverts (:300); inversion draws nothing, so the
+                # order of the two does not change any generator's sequence
                 self.invert_many([gb])
-                inv = gb.inv
-                for e, ((b, _), ((r0, r1), (q0, q1))) in enumerate(zip(gb.jobs, gb.windows)):
-                    assert r1 - r0 == q1 - q0
-                    for o in (0, n + 1):                    # upper body and hands only (:394-407)
-                        start_noise[b, o + q0:o + q1] = inv[gb.inversion_start_time, e, o + r0:o + r1]
-                        if gb.use_guidance:
-                            inv_per_t[:, b, o + q0:o + q1] = inv[:, e, o + r0:o + r1]
-                if not keep_inversion:
-                    gb.inv = None                           # a GuidedBatch re-run (bench) inverts again
-            if gb.use_guidance and gb.use_prev and gb.prev_latent is not None:
-                inv_per_t[:, :, [0, n + 1, 2 * n + 2, 3 * n + 3], :] = 0
+            start_noise, inv_per_t = self._guided_inputs(gb)
+            if not keep_inversion:
+                gb.inv = None                           # a GuidedBatch re-run (bench) inverts again
         self.model._state_cache = (None, None)
         if gb.use_guidance:
             output = diff.ddim_guided_sample_loop(
@@ -238,6 +247,50 @@ class MotionDiffusion(nn.Module):
         if getattr(self.model, "post_process") is not None:
             output = self.model.post_process(output)
         return output
+
+    def run_pass(self, gb_guided=None, gb_invert=None):
+        """One pass of the two-batch software pipeline: the guided sampling of `gb_guided` (exemplars already
+        inverted by the previous pass) and the DDIM inversion of `gb_invert`'s exemplars as ONE kernel chain
+        per level (SpacedDiffusion.ddim_guided_and_reverse_loops).  Either may be None (first / last pass).
+        Falls back to the separate loops whenever the pair is not an insertion-guided pair.  Returns the
+        output latents of gb_guided (or None); sets gb_invert.inv."""
+        g, v = gb_guided, gb_invert
+        fusable = (g is not None and v is not None and g is not v and g.use_guidance and g.use_inversion
+                   and v.use_inversion and len(v.jobs) > 0 and v.inv is None and not g.extra and not v.extra
+                   and (not g.jobs or g.inv is not None))
+        if not fusable:
+            if v is not None:
+                self.invert_many([v])
+            return self.run_prepared(g) if g is not None else None
+        diff, (B, T, D), device = self.diffusion_test, g.shape, g.device
+        start_noise, inv_per_t = self._guided_inputs(g)
+        g.inv = None
+        with torch.no_grad():
+            ex_kwargs = self.model.get_precompute_condition(device=device, text=v.ex["retr_text"], audio=v.ex["retr_audio"],
+                                                            speaker_ids=v.ex["retr_spkid"], re_dict=1)
+        ex_kwargs["query_mask"] = v.ex_query_mask
+        ex_kwargs["motion_mask"] = v.ex["retr_motion_mask"]
+        output, inv = diff.ddim_guided_and_reverse_loops(
+            self.model,
+            guided=dict(shape=(B, T, D), noise=start_noise, model_kwargs=g.model_kwargs,
+                        in_seq=g.prev_latent if g.use_prev else None, guidance_iters=g.guidance_iters,
+                        inverted_latent_list=inv_per_t, guidance_lr=g.guidance_lr),
+            reverse=dict(start_img=v.ex["retr_motion_latent"], model_kwargs=ex_kwargs))
+        v.inv = torch.stack(inv, 0)
+        if getattr(self.model, "post_process") is not None:
+            output = self.model.post_process(output)
+        return output
+
+    def run_many(self, gbs):
+        """Outputs of a list of prepared batches through the two-batch pipeline: pass k runs the guided loop
+        of batch k-1 together with the inversion of batch k."""
+        outs, prev = [], None
+        for gb in list(gbs) + [None]:
+            out = self.run_pass(prev, gb)
+            if prev is not None:
+                outs.append(out)
+            prev = gb
+        return outs
 
     # ---- stage 3: decode ---------------------------------------------------------------------------------
     def finish(self, gb, output):
@@ -282,7 +335,8 @@ class GuidedPipeline:
     """Throughput form of `for batch in loader: model(**batch)` (tools/visualize.py:189-200): while the
     denoising loops of batch i run, a worker thread executes stage 1 of batch i+1 -- H2D of the pinned host
     batch, codec encode, discourse retrieval with its text-similarity ranking, exemplar fetch and encode -- on
-    a side stream.  Results are identical to sequential forward() calls: the worker never touches the
+    a side stream, and the inversion loop of batch i+1's exemplars is fused level by level with the guided loop
+    of batch i (MotionDiffusion.run_pass).  Results are identical to sequential forward() calls: the worker never touches the
     denoiser handle (the clip pre-projection is deferred to the main thread), it alone draws from the CPU
     generator (codec rsample noise) and the main thread alone from the CUDA generator (sampler noise), so the
     draw order of every generator is the sequential one.
@@ -322,10 +376,16 @@ class GuidedPipeline:
             return
         with ThreadPoolExecutor(max_workers=1, thread_name_prefix="rg-stage1") as pool:
             fut = pool.submit(self._stage1, dict(first), main, None)
-            while fut is not None:
-                gb, ready = fut.result()
-                nxt = next(it, None)
-                fut = pool.submit(self._stage1, dict(nxt), main, main.record_event()) if nxt is not None else None
-                main.wait_event(ready)
-                self.arch.encode_clip_conditions(gb)
-                yield self.arch.finish(gb, self.arch.run_prepared(gb))
+            cur = None                              # prepared + inverted, waiting for its guided pass
+            while fut is not None or cur is not None:
+                gb = None
+                if fut is not None:
+                    gb, ready = fut.result()
+                    nxt = next(it, None)
+                    fut = pool.submit(self._stage1, dict(nxt), main, main.record_event()) if nxt is not None else None
+                    main.wait_event(ready)
+                    self.arch.encode_clip_conditions(gb)
+                out = self.arch.run_pass(cur, gb)   # guided loop of `cur` fused with the inversion of `gb`
+                if cur is not None:
+                    yield self.arch.finish(cur, out)
+                cur = gb

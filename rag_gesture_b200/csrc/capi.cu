@@ -102,6 +102,8 @@ struct rg_model {
     float* table;                         // [n_steps, L, 5, 1024]
     float* tau_row;                       // [L*5*1024] scratch for an off-table timestep
     int tau_cached;
+    float* ss_rep;                        // [ss_rep_clips, L*5*1024] per-clip table rows (rg_denoise_groups)
+    long long ss_rep_clips;
     // workspaces: rg_denoise cuts a batch into `lanes` clip ranges that run as concurrent kernel chains
     int lanes;                            // 0: automatic
     Ws ws[RG_MAX_LANES];
@@ -233,7 +235,7 @@ extern "C" int rg_create(const rg_config* cfg, int n_tensors, const char* const*
     memset(&m->cfg, 0, sizeof(m->cfg));
     m->cfg = *cfg;
     cudaGetDevice(&m->device);
-    m->n_steps = 0; m->table = nullptr; m->tau_row = nullptr; m->tau_cached = -1;
+    m->n_steps = 0; m->table = nullptr; m->tau_row = nullptr; m->tau_cached = -1; m->ss_rep = nullptr; m->ss_rep_clips = 0;
     memset(m->ws, 0, sizeof(m->ws));
     m->lanes = 0; m->ev_fork = nullptr;
     for (int i = 0; i < RG_MAX_LANES; ++i) { m->lane_st[i] = nullptr; m->ev_join[i] = nullptr; }
@@ -559,9 +561,9 @@ static int tc_gemm(rg_model* m, const CUtensorMap& tmA, int a_w, const W16& w, c
 
 // rg_denoise on the tensor cores: bf16 (or hi|lo bf16) operands, fp32 accumulation in TMEM, fp32
 // residual stream / softmaxes / LayerNorm statistics / -1e6 masks exactly as on the fp32 path.
-static int denoise_tc(rg_model* m, Ws& w, const float* x, int B, const float* ssrow, const float* src_mask,
-                      const float* query_mask, long long qm_cond_stride, const float* state, float* x0_out,
-                      cudaStream_t st) {
+static int denoise_tc(rg_model* m, Ws& w, const float* x, int B, const float* ssrow, long long ss_stride,
+                      const float* src_mask, const float* query_mask, long long qm_cond_stride, const float* state,
+                      float* x0_out, cudaStream_t st) {
     const int D = RG_D, F = m->cfg.ffn_dim, L = m->cfg.num_layers, T = m->cfg.n_tokens, P = m->planes;
     const int M = B * T;
     const long long clip_stride = rg_state_floats_per_clip(m);
@@ -576,7 +578,7 @@ static int denoise_tc(rg_model* m, Ws& w, const float* x, int B, const float* ss
         // --- self-attention
         LAUNCH(rg_launch_ln_rows(w.h, D, nullptr, nullptr, rg_out_b16(w.a16, D * P, lo ? D : 0), M, st));
         if (tc_gemm(m, w.tm_a16, D, t.qkv, ly.bqkv, M, 3 * D, D, RG_EPI_BIAS, nullptr, w.big, 3 * D, nullptr, 0, st)) return 1;
-        RgStylParams sp = {ly.sa_g, ly.sa_b, ss, 0};
+        RgStylParams sp = {ly.sa_g, ly.sa_b, ss, ss_stride};
         // mma.sync core + Stylization prologue in one kernel (one CTA per clip): measured faster than core +
         // row kernel for the single-pass TF32 cores up to ~128 clips; the 3xTF32 variant is register-bound
         const bool fuse_styl = m->attn_mode == 1 && B <= 128;
@@ -600,7 +602,7 @@ static int denoise_tc(rg_model* m, Ws& w, const float* x, int B, const float* ss
         LAUNCH(rg_launch_ln_rows(w.h, D, nullptr, nullptr, rg_out_b16(w.a16, D * P, lo ? D : 0), M, st));
         if (tc_gemm(m, w.tm_a16, D, t.caq, ly.bcaq, M, 3 * D, D, RG_EPI_BIAS, nullptr, w.big, 3 * D, nullptr, 0, st)) return 1;
         RgStylParams sp3[3];
-        for (int c = 0; c < 3; ++c) sp3[c] = {ly.ca_g + c * D, ly.ca_b + c * D, ss + (1 + c) * 2 * D, 0};
+        for (int c = 0; c < 3; ++c) sp3[c] = {ly.ca_g + c * D, ly.ca_b + c * D, ss + (1 + c) * 2 * D, ss_stride};
         if (m->attn_mode_ca == 1 && B <= 128) {
             LAUNCH(rg_launch_ca_styl(w.big, 3 * D, state + (long long)l * 3 * HS, clip_stride, HS, query_mask, qm_cond_stride,
                                      sp3, rg_out_b16(w.a16x, 4 * D * P, lo ? 4 * D : 0), B, T, m->attn_mode_ca == 2, st));
@@ -613,7 +615,7 @@ static int denoise_tc(rg_model* m, Ws& w, const float* x, int B, const float* ss
         // --- FFN
         if (tc_gemm(m, w.tm_h16, D, t.w1, ly.b1, M, F, D, RG_EPI_BIAS_GELU, nullptr, nullptr, 0, w.g16, F, st)) return 1;
         if (tc_gemm(m, w.tm_g16, F, t.w2, ly.b2, M, D, F, RG_EPI_BIAS, nullptr, w.y, D, nullptr, 0, st)) return 1;
-        RgStylParams spf = {ly.ffn_g, ly.ffn_b, ss + 4 * 2 * D, 0};
+        RgStylParams spf = {ly.ffn_g, ly.ffn_b, ss + 4 * 2 * D, ss_stride};
         LAUNCH(rg_launch_styl_rows(w.y, D, spf, T, rg_out_b16(w.a16, D * P, lo ? D : 0), M, st));
         if (tc_gemm(m, w.tm_a16, D, t.ffn_o, ly.ffn_bo, M, D, D, RG_EPI_BIAS_RESIDUAL, w.h, w.h, D, w.h16, D, st)) return 1;
     }
@@ -621,9 +623,9 @@ static int denoise_tc(rg_model* m, Ws& w, const float* x, int B, const float* ss
 }
 
 // rg_denoise, fp32 SIMT tier (RG_PREC_FP32): one lane's clips.
-static int denoise_f32(rg_model* m, Ws& w, const float* x, int B, const float* ssrow, const float* src_mask,
-                       const float* query_mask, long long qm_cond_stride, const float* state, float* x0_out,
-                       cudaStream_t st) {
+static int denoise_f32(rg_model* m, Ws& w, const float* x, int B, const float* ssrow, long long ss_stride,
+                       const float* src_mask, const float* query_mask, long long qm_cond_stride, const float* state,
+                       float* x0_out, cudaStream_t st) {
     const int D = RG_D, F = m->cfg.ffn_dim, L = m->cfg.num_layers, T = m->cfg.n_tokens;
     const int M = B * T;
     const long long clip_stride = rg_state_floats_per_clip(m);
@@ -641,7 +643,7 @@ static int denoise_f32(rg_model* m, Ws& w, const float* x, int B, const float* s
         // --- self-attention
         LAUNCH(rg_launch_ln_rows(w.h, D, nullptr, nullptr, rg_out_f32(w.a, D), M, st));
         LAUNCH(rg_launch_gemm_f32(mk_gemm(w.a, D, ly.Wqkv, ly.bqkv, w.big, 3 * D, M, 3 * D, D, RG_EPI_BIAS), st));
-        RgStylParams sp = {ly.sa_g, ly.sa_b, ss, 0};
+        RgStylParams sp = {ly.sa_g, ly.sa_b, ss, ss_stride};
         LAUNCH(rg_launch_sa_attention(w.big, src_mask, sp, nullptr, rg_out_f32(w.a, D), B, T, 1, st));
         {
             RgGemm g = mk_gemm(w.a, D, ly.sa_Wo, ly.sa_bo, w.h, D, M, D, D, RG_EPI_BIAS_RESIDUAL);
@@ -652,7 +654,7 @@ static int denoise_f32(rg_model* m, Ws& w, const float* x, int B, const float* s
         LAUNCH(rg_launch_ln_rows(w.h, D, nullptr, nullptr, rg_out_f32(w.a, D), M, st));
         LAUNCH(rg_launch_gemm_f32(mk_gemm(w.a, D, ly.Wcaq, ly.bcaq, w.big, 3 * D, M, 3 * D, D, RG_EPI_BIAS), st));
         RgStylParams sp3[3];
-        for (int c = 0; c < 3; ++c) sp3[c] = {ly.ca_g + c * D, ly.ca_b + c * D, ss + (1 + c) * 2 * D, 0};
+        for (int c = 0; c < 3; ++c) sp3[c] = {ly.ca_g + c * D, ly.ca_b + c * D, ss + (1 + c) * 2 * D, ss_stride};
         LAUNCH(rg_launch_ca_attention(w.big, 3 * D, state + (long long)l * 3 * HS, clip_stride, HS, query_mask,
                                       qm_cond_stride, sp3, rg_out_f32(w.a, 3 * D), B, T, 3, st));
         {
@@ -664,7 +666,7 @@ static int denoise_f32(rg_model* m, Ws& w, const float* x, int B, const float* s
         // --- FFN
         LAUNCH(rg_launch_gemm_f32(mk_gemm(w.h, D, ly.W1, ly.b1, w.g, F, M, F, D, RG_EPI_BIAS_GELU), st));
         LAUNCH(rg_launch_gemm_f32(mk_gemm(w.g, F, ly.W2, ly.b2, w.y, D, M, D, F, RG_EPI_BIAS), st));
-        RgStylParams spf = {ly.ffn_g, ly.ffn_b, ss + 4 * 2 * D, 0};
+        RgStylParams spf = {ly.ffn_g, ly.ffn_b, ss + 4 * 2 * D, ss_stride};
         LAUNCH(rg_launch_styl_rows(w.y, D, spf, T, rg_out_f32(w.a, D), M, st));
         {
             RgGemm g = mk_gemm(w.a, D, ly.ffn_Wo, ly.ffn_bo, w.h, D, M, D, D, RG_EPI_BIAS_RESIDUAL);
@@ -719,13 +721,64 @@ extern "C" int rg_denoise(rg_handle m, const float* x, int B, int step_idx, int 
         if (i) CU(cudaStreamWaitEvent(ls, m->ev_fork, 0));
         if (ensure_ws(m, m->ws[i], (long long)(b1 - b0) * T)) return 1;
         const long long r0 = (long long)b0 * T;
-        rc = (tc ? denoise_tc : denoise_f32)(m, m->ws[i], x + r0 * D, b1 - b0, ssrow, src_mask + r0,
+        rc = (tc ? denoise_tc : denoise_f32)(m, m->ws[i], x + r0 * D, b1 - b0, ssrow, 0, src_mask + r0,
                                              query_mask ? query_mask + r0 : nullptr, (long long)B * T,
                                              state + b0 * clip_stride, x0_out + r0 * D, ls);
         if (i) CU(cudaEventRecord(m->ev_join[i], ls));
     }
     for (int i = 1; i < lanes; ++i) CU(cudaStreamWaitEvent(st, m->ev_join[i], 0));
     return rc;
+}
+
+// broadcast one table row to `n_clips` consecutive per-clip rows
+__global__ void __launch_bounds__(256) rep_rows_kernel(const float4* __restrict__ row, float4* __restrict__ out,
+                                                      long long n4_row, long long n4_total) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4_total; i += stride)
+        out[i] = __ldg(row + i % n4_row);
+}
+
+extern "C" int rg_denoise_groups(rg_handle m, const float* x, int B, int n_groups, const int32_t* group_clips,
+                                 const int32_t* group_step_idx, const float* src_mask, const float* query_mask,
+                                 const float* state, float* x0_out, void* stream) {
+    if (!m || !x || !src_mask || !state || !x0_out || !group_clips || !group_step_idx)
+        return rg_fail("rg_denoise_groups: null argument");
+    if (n_groups < 1 || n_groups > 8) return rg_fail("rg_denoise_groups: 1..8 groups");
+    int total = 0;
+    for (int g = 0; g < n_groups; ++g) {
+        if (group_clips[g] < 0) return rg_fail("rg_denoise_groups: negative group size");
+        if (group_step_idx[g] < 0 || group_step_idx[g] >= m->n_steps)
+            return rg_fail("rg_denoise_groups: step_idx %d outside the schedule (%d steps)", group_step_idx[g], m->n_steps);
+        total += group_clips[g];
+    }
+    if (total != B) return rg_fail("rg_denoise_groups: group sizes sum to %d, B = %d", total, B);
+    if (B <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int D = RG_D, L = m->cfg.num_layers, T = m->cfg.n_tokens;
+    const long long NT = (long long)L * 5 * 2 * D;
+    if (B > m->ss_rep_clips) {
+        dfree_one(m, m->ss_rep);
+        m->ss_rep = nullptr; m->ss_rep_clips = 0;
+        if (dalloc(m, (void**)&m->ss_rep, (size_t)B * NT * sizeof(float))) return 1;
+        m->ss_rep_clips = B;
+    }
+    long long b0 = 0;
+    for (int g = 0; g < n_groups; ++g) {
+        const long long n4 = (long long)group_clips[g] * NT / 4;
+        if (n4 > 0) {
+            const int blocks = (int)std::min<long long>((n4 + 255) / 256, 148 * 8);
+            rep_rows_kernel<<<blocks, 256, 0, st>>>(
+                reinterpret_cast<const float4*>(m->table + (long long)group_step_idx[g] * NT),
+                reinterpret_cast<float4*>(m->ss_rep + b0 * NT), NT / 4, n4);
+            CU(cudaGetLastError());
+            rg_count_launch(1);
+        }
+        b0 += group_clips[g];
+    }
+    if (ensure_ws(m, m->ws[0], (long long)B * T)) return 1;
+    const bool tc = m->cfg.precision != RG_PREC_FP32;
+    return (tc ? denoise_tc : denoise_f32)(m, m->ws[0], x, B, m->ss_rep, NT, src_mask, query_mask, (long long)B * T,
+                                           state, x0_out, st);
 }
 
 extern "C" int rg_set_lanes(rg_handle m, int lanes) {

@@ -261,6 +261,63 @@ class SpacedDiffusion:
                 img, x0 = self._forward_step(eng, prep, img, i, in_seq)
                 yield {"sample": img, "pred_xstart": x0}
 
+    def ddim_guided_and_reverse_loops(self, model, guided, reverse):
+        """The guided sampling loop of one batch and the DDIM inversion loop of ANOTHER batch's exemplars
+        advanced together: pass j evaluates the clips at level S-1-j and the exemplars at level j in ONE
+        denoiser call (rg_denoise_groups), so the per-kernel fixed costs of the 100-kernel chain are paid once
+        for both.  Per clip the arithmetic, and the order of the noise draws (only the guided loop draws),
+        are those of ddim_guided_sample_loop / ddim_reverse_sample_loop: results are bit-identical.
+
+        guided  = dict(shape, noise, model_kwargs, in_seq, guidance_iters, inverted_latent_list, guidance_lr)
+        reverse = dict(start_img, model_kwargs)
+        -> (final guided sample [B,T,D], list of S inverted latents [E,T,D])"""
+        S = self.num_timesteps
+        eng = self._engine(model)
+        B, (T, D) = guided["shape"][0], guided["shape"][1:]
+        inv_list, g_iters = guided["inverted_latent_list"], guided["guidance_iters"]
+        if inv_list is None:
+            raise ValueError("inverted_latent_list must be provided for guided sampling")
+        assert len(g_iters) == len(inv_list)
+        start = reverse["start_img"].float().contiguous()
+        E, device = start.shape[0], start.device
+        # K6 state of both groups (each through the model's own cache logic), then one joint batch
+        model._state_cache = (None, None)
+        pg = model.prepare_batch(guided["model_kwargs"], B)
+        model._state_cache = (None, None)
+        pr = model.prepare_batch(reverse["model_kwargs"], E)
+        model._state_cache = (None, None)
+        src_mask = torch.cat([pg.src_mask, pr.src_mask], 0)
+        qm = None
+        if pg.query_mask is not None and pr.query_mask is not None:
+            qm = torch.cat([pg.query_mask, pr.query_mask], 1).contiguous()
+        elif pg.query_mask is not None or pr.query_mask is not None:
+            raise NotImplementedError("both groups need a query_mask, or neither")
+        state = torch.cat([pg.state, pr.state], 0)
+        del pg, pr
+        img = guided["noise"] if guided["noise"] is not None else self._randn(guided["shape"], device)
+        xj = torch.empty(B + E, T, D, device=device)
+        xj[:B].copy_(img.float())
+        xj[B:].copy_(start)
+        x0 = torch.empty_like(xj)
+        samples = torch.empty(S, E, T, D, device=device)
+        in_seq, first = guided.get("in_seq", None), S - 1
+        with torch.no_grad():
+            for j in range(S):
+                i = S - 1 - j
+                if i != first:
+                    in_seq = inv_list[i]
+                    g = int(g_iters[i])
+                    if g > 0 and not self.skip_dead_guidance:
+                        eng.guidance_steps(xj[:B], in_seq.contiguous(), g, guided.get("guidance_lr", 0.1))
+                if in_seq is not None:
+                    eng.blend_in_seq(xj[:B], in_seq.contiguous(), self._randn(in_seq.shape, device), i, out=xj[:B])
+                eng.denoise_groups(xj, src_mask, qm, state, [(B, i), (E, j)], out=x0)
+                self._randn((B, T, D), device)      # randn_like(x) of :991 -- sigma = 0, value unused
+                eng.ddim_update(xj[:B], x0[:B], i, -1, out=xj[:B])
+                eng.ddim_update(xj[B:], x0[B:], j, +1, out=samples[j])
+                xj[B:].copy_(samples[j])
+        return xj[:B].clone(), list(samples.unbind(0))
+
     def p_sample_loop(self, *a, **k):
         raise NotImplementedError("DDPM ancestral sampling is outside the rg_b200 hot path (inference_type='ddim')")
 

@@ -125,6 +125,24 @@ class DenoiserEngine:
                 _lib.ptr(query_mask), _lib.ptr(state), _lib.ptr(out), _lib.stream_ptr()))
         return out
 
+    def denoise_groups(self, x, src_mask, query_mask, state, groups, out=None):
+        """One evaluation of a batch made of consecutive clip ranges at DIFFERENT schedule levels:
+        groups = [(n_clips, step_idx), ...] (rg_denoise_groups).  Per clip identical to denoise()."""
+        _lib.require_cuda(x, src_mask, state)
+        assert x.is_contiguous() and x.dtype == torch.float32
+        B = x.shape[0]
+        assert state.shape[0] == B and sum(n for n, _ in groups) == B, "groups / state do not match x"
+        if out is None:
+            out = torch.empty_like(x)
+        n = len(groups)
+        clips = (C.c_int32 * n)(*[int(g[0]) for g in groups])
+        steps = (C.c_int32 * n)(*[int(g[1]) for g in groups])
+        with torch.cuda.device(x.device):
+            _lib.check(self.lib.rg_denoise_groups(self._h, _lib.ptr(x), B, n, clips, steps, _lib.ptr(src_mask),
+                                                  _lib.ptr(query_mask), _lib.ptr(state), _lib.ptr(out),
+                                                  _lib.stream_ptr()))
+        return out
+
     def ddim_update(self, x, x0, step_idx, direction, out=None):
         if out is None:
             out = torch.empty_like(x)

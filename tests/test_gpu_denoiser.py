@@ -318,3 +318,65 @@ def test_lanes_do_not_change_results(which, model, tc_model, diffusion, dev):
         assert torch.equal(o, outs[0])
     with pytest.raises(RuntimeError):
         eng.set_lanes(9)
+
+
+@pytest.mark.parametrize("which", ["fp32", "tc"])
+def test_denoise_groups_equals_per_level_calls(which, model, tc_model, diffusion, dev):
+    """rg_denoise_groups: a batch whose clip ranges sit at DIFFERENT schedule levels gives every clip exactly
+    what a single-level rg_denoise gives it (ragged groups 3 + 1 + 4, levels 49 / 0 / 17), for the fp32 and the
+    tensor-core tiers; bad group tables are refused."""
+    mdl = model if which == "fp32" else tc_model[0]
+    eng = mdl.rg_engine(diffusion)
+    B, groups = 8, [(3, 49), (1, 0), (4, 17)]
+    kw = _kw(mdl, S.synthetic_conditions(B, seed=61), B, dev)
+    prep = mdl.prepare_batch(kw, B)
+    x = S.synthetic_latents(B, seed=62).to(dev)
+    joint = eng.denoise_groups(x, prep.src_mask, prep.query_mask, prep.state, groups)
+    b0 = 0
+    for n, step in groups:
+        sl = slice(b0, b0 + n)
+        qm = prep.query_mask[:, sl].contiguous()
+        ref = eng.denoise(x[sl].contiguous(), prep.src_mask[sl].contiguous(), qm, prep.state[sl].contiguous(), step_idx=step)
+        assert torch.equal(joint[sl], ref), (n, step)
+        b0 += n
+    with pytest.raises(RuntimeError):
+        eng.denoise_groups(x, prep.src_mask, prep.query_mask, prep.state, [(4, 1), (4, 50)])    # level outside the schedule
+
+
+def test_fused_guided_and_reverse_loops_bit_identical(model, diffusion, dev):
+    """ddim_guided_and_reverse_loops (guided sampling of one batch + inversion of another batch's exemplars, one
+    kernel chain per level) == ddim_guided_sample_loop and ddim_reverse_sample_loop run separately, bit for bit,
+    with the same noise tape."""
+    B, E, T, D, n = 2, 3, C.N_TOKENS, C.LATENT_DIM, C.N_CHUNKS
+    kwg = _kw(model, S.synthetic_conditions(B, seed=71), B, dev)
+    kwr = _kw(model, S.synthetic_conditions(E, seed=72), E, dev)
+    start_img = S.synthetic_latents(E, seed=73, scale=0.5).to(dev)
+    inv_list = torch.zeros(50, B, T, D, device=dev)
+    inv_list[:, 0, 2:5] = S.synthetic_latents(50, seed=74)[:, 2:5].to(dev)
+    inv_list[:, 1, n + 3:n + 8] = S.synthetic_latents(50, seed=75)[:, 3:8].to(dev)
+    iters = [0] * 25 + list(range(25))
+
+    def start_noise(tape):
+        s = tape.randn((B, T, D), dev)
+        nz = inv_list[49] != 0
+        s[nz] = inv_list[49][nz]
+        return s
+
+    tape = S.NoiseTape(55)
+    diffusion.noise_fn = tape.randn
+    ref_g = diffusion.ddim_guided_sample_loop(model, (B, T, D), noise=start_noise(tape), clip_denoised=False,
+                                              model_kwargs=kwg, eta=0, in_seq=None, guidance_iters=iters,
+                                              inverted_latent_list=inv_list, guidance_lr=0.1)
+    ref_r = diffusion.ddim_reverse_sample_loop(model, start_img=start_img, clip_denoised=False, model_kwargs=kwr,
+                                               eta=0, return_all_timesteps=True)
+    tape = S.NoiseTape(55)
+    diffusion.noise_fn = tape.randn
+    out_g, out_r = diffusion.ddim_guided_and_reverse_loops(
+        model, guided=dict(shape=(B, T, D), noise=start_noise(tape), model_kwargs=kwg, in_seq=None,
+                           guidance_iters=iters, inverted_latent_list=inv_list, guidance_lr=0.1),
+        reverse=dict(start_img=start_img, model_kwargs=kwr))
+    diffusion.noise_fn = None
+    assert torch.equal(out_g, ref_g)
+    assert len(out_r) == len(ref_r) == 50
+    for a, b in zip(out_r, ref_r):
+        assert torch.equal(a, b)
