@@ -82,6 +82,7 @@ struct rg_model {
     // tensor-core path (cfg.precision != RG_PREC_FP32)
     int planes;              // 1: bf16 operands, 2: hi|lo planes (bf16x3)
     int attn_mode_ca;
+    int fuse_styl_max;       // largest batch (clips) that takes the attention kernels fused with the Stylization prologue
     int attn_mode;           // attention cores: 0 fp32 SIMT, 1 TF32 mma.sync (bf16 tier), 2 3xTF32 (bf16x3 tier)
     std::vector<LayerTc> tc;
     W16 tc_joint, tc_out, tc_kv[3];
@@ -246,6 +247,8 @@ extern "C" int rg_create(const rg_config* cfg, int n_tensors, const char* const*
     m->attn_mode_ca = m->attn_mode;
     if (const char* e = getenv("RG_ATTN_MODE")) m->attn_mode = m->attn_mode_ca = atoi(e);      // diagnostics only
     if (const char* e = getenv("RG_ATTN_MODE_CA")) m->attn_mode_ca = atoi(e);
+    m->fuse_styl_max = 128;
+    if (const char* e = getenv("RG_FUSE_STYL_MAX")) m->fuse_styl_max = atoi(e);
     m->kv_a16 = nullptr;
     const int D = RG_D, E = cfg->time_embed_dim, F = cfg->ffn_dim, L = cfg->num_layers, T = cfg->n_tokens;
     const long long DD = (long long)D * D;
@@ -581,7 +584,7 @@ static int denoise_tc(rg_model* m, Ws& w, const float* x, int B, const float* ss
         RgStylParams sp = {ly.sa_g, ly.sa_b, ss, ss_stride};
         // mma.sync core + Stylization prologue in one kernel (one CTA per clip): measured faster than core +
         // row kernel for the single-pass TF32 cores up to ~128 clips; the 3xTF32 variant is register-bound
-        const bool fuse_styl = m->attn_mode == 1 && B <= 128;
+        const bool fuse_styl = m->attn_mode == 1 && B <= m->fuse_styl_max;
         if (fuse_styl) {
             LAUNCH(rg_launch_sa_styl(w.big, src_mask, sp, rg_out_b16(w.a16, D * P, lo ? D : 0), B, T, m->attn_mode == 2, st));
         } else {
@@ -603,7 +606,7 @@ static int denoise_tc(rg_model* m, Ws& w, const float* x, int B, const float* ss
         if (tc_gemm(m, w.tm_a16, D, t.caq, ly.bcaq, M, 3 * D, D, RG_EPI_BIAS, nullptr, w.big, 3 * D, nullptr, 0, st)) return 1;
         RgStylParams sp3[3];
         for (int c = 0; c < 3; ++c) sp3[c] = {ly.ca_g + c * D, ly.ca_b + c * D, ss + (1 + c) * 2 * D, ss_stride};
-        if (m->attn_mode_ca == 1 && B <= 128) {
+        if (m->attn_mode_ca == 1 && B <= m->fuse_styl_max) {
             LAUNCH(rg_launch_ca_styl(w.big, 3 * D, state + (long long)l * 3 * HS, clip_stride, HS, query_mask, qm_cond_stride,
                                      sp3, rg_out_b16(w.a16x, 4 * D * P, lo ? 4 * D : 0), B, T, m->attn_mode_ca == 2, st));
         } else {
