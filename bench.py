@@ -228,10 +228,21 @@ def run_b200(args):
 
     pipe = GuidedPipeline(arch)
 
+    host_bufs = [host_out, torch.empty_like(host_out).pin_memory()]
+
     def e2e_pipelined(n):
-        for res in pipe.run(fresh_batch() for _ in range(n)):
-            host_out.copy_(res["prev_latentout"], non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+        # the consumer copies batch k's latents to pinned host memory asynchronously and waits for that copy
+        # one batch later, so the device never drains between passes
+        pending = None
+        for k, res in enumerate(pipe.run(fresh_batch() for _ in range(n))):
+            host_bufs[k % 2].copy_(res["prev_latentout"], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            if pending is not None:
+                pending.synchronize()
+            pending = ev
+        if pending is not None:
+            pending.synchronize()
     e2e_pipelined(max(2, args.warmup // 2))
     barrier()
     flush.zero_()

@@ -112,6 +112,22 @@ int rg_denoise_groups(rg_handle h, const float* x, int B, int n_groups, const in
                       const int32_t* group_step_idx, const float* src_mask, const float* query_mask,
                       const float* state, float* x0_out, void* stream);
 
+/* S consecutive levels of the samplers in ONE call (the host thread is then free for the next batch's
+ * retrieval; per level this enqueues exactly what the single-step entry points would):
+ *   clips     xj[0:B]   : guided / plain sampling, levels S-1 .. 0 (ddim_guided_sample_loop / ddim_sample_loop,
+ *                         gaussian_diffusion.py:1233-1395, 1042-1135): in_seq = in_seq0 at level S-1 and, when
+ *                         inv_list [S,B,T,512] is given, inv_list[i] at every level i below it (else in_seq0 at
+ *                         every level); a non-NULL in_seq is blended with noise[j] (j = S-1-i, [S,B,T,512]);
+ *                         guidance_iters[i] dead gradient steps are executed only if run_dead_guidance;
+ *   exemplars xj[B:B+E] : DDIM inversion, levels 0 .. S-1 (ddim_reverse_sample_loop, :1137-1230); the latent
+ *                         after level j is written to samples_out[j] ([S,E,T,512]).
+ * Pass j evaluates both ranges in one kernel chain (rg_denoise_groups).  B or E may be 0.  src_mask [B+E,T],
+ * query_mask [3,B+E,T] or NULL, state for B+E clips, x0_scratch [B+E,T,512].  xj holds the results. */
+int rg_run_levels(rg_handle h, int S, float* xj, int B, int E, const float* in_seq0, const float* inv_list,
+                  const float* noise, const int32_t* guidance_iters, float guidance_lr, int run_dead_guidance,
+                  const float* src_mask, const float* query_mask, const float* state, float* samples_out,
+                  float* x0_scratch, void* stream);
+
 /* How many concurrent kernel chains ("lanes", contiguous clip ranges on separate streams, joined back
  * onto the caller's stream before the call returns) one rg_denoise uses: 0 = automatic (currently 1),
  * 1..4 fixed.  Results do not depend on the setting: clips never interact inside a step. */

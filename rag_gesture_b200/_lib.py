@@ -33,6 +33,7 @@ SIGNATURES = {
     "rg_precompute_clip_state": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "rg_denoise": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P]),
     "rg_denoise_groups": (_I, [_P, _P, _I, _I, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _P, _P, _P, _P, _P]),
+    "rg_run_levels": (_I, [_P, _I, _P, _I, _I, _P, _P, _P, C.POINTER(C.c_int32), _F, _I, _P, _P, _P, _P, _P, _P]),
     "rg_ddim_update": (_I, [_P, _P, _P, _I, _I, _P, _L, _P]),
     "rg_blend_in_seq": (_I, [_P, _P, _P, _P, _I, _P, _L, _P]),
     "rg_guidance_steps": (_I, [_P, _P, _P, _L, _I, _F, _L, _P]),

@@ -190,9 +190,12 @@ class MotionDiffusion(nn.Module):
                                                             speaker_ids=cat("retr_spkid"), re_dict=1)
         ex_kwargs["query_mask"] = {c: torch.cat([gb.ex_query_mask[c] for gb in todo], 0) for c in CFG.CONDS}
         ex_kwargs["motion_mask"] = cat("retr_motion_mask")
-        inv = diff.ddim_reverse_sample_loop(self.model, start_img=cat("retr_motion_latent"), clip_denoised=False,
-                                            progress=False, model_kwargs=ex_kwargs, eta=0,
-                                            return_all_timesteps=True, **todo[0].extra)
+        if todo[0].extra:       # unknown sampler keywords: let the step-by-step loop accept or refuse them
+            inv = diff.ddim_reverse_sample_loop(self.model, start_img=cat("retr_motion_latent"), clip_denoised=False,
+                                                progress=False, model_kwargs=ex_kwargs, eta=0,
+                                                return_all_timesteps=True, **todo[0].extra)
+        else:                   # all levels in one library call
+            _, inv = diff.run_levels(self.model, reverse=dict(start_img=cat("retr_motion_latent"), model_kwargs=ex_kwargs))
         inv = torch.stack(inv, 0)                       # [steps, E_total, T, D], clean -> noisy
         off = 0
         for gb in todo:
@@ -233,7 +236,16 @@ class MotionDiffusion(nn.Module):
             if not keep_inversion:
                 gb.inv = None                           # a GuidedBatch re-run (bench) inverts again
         self.model._state_cache = (None, None)
-        if gb.use_guidance:
+        noise = start_noise if gb.use_inversion else None
+        if not gb.extra:        # all levels in one library call (rg_run_levels)
+            if gb.use_guidance:
+                spec = dict(in_seq=gb.prev_latent if gb.use_prev else None, guidance_iters=gb.guidance_iters,
+                            inverted_latent_list=inv_per_t, guidance_lr=gb.guidance_lr)
+            else:
+                spec = dict(in_seq=gb.prev_latent if gb.use_prev else (gb.outpaint_seq if gb.use_outpaint else None))
+            output, _ = diff.run_levels(self.model, guided=dict(shape=(B, T, D), noise=noise,
+                                                                model_kwargs=gb.model_kwargs, **spec))
+        elif gb.use_guidance:
             output = diff.ddim_guided_sample_loop(
                 self.model, (B, T, D), noise=start_noise if gb.use_inversion else None, clip_denoised=False,
                 progress=False, model_kwargs=gb.model_kwargs, eta=0,
@@ -345,15 +357,15 @@ class GuidedPipeline:
     """
 
     def __init__(self, arch):
-        import sys
         self.arch = arch
         self.device = arch.model.out.weight.device
         if self.device.type != "cuda":
             raise RuntimeError("rg_b200: GuidedPipeline needs the model on a CUDA device (no CPU fallback)")
         self.side = torch.cuda.Stream(self.device)
-        # the main thread re-acquires the GIL after every C-ABI call; keep the worker's time slices short
-        if sys.getswitchinterval() > 5e-4:
-            sys.setswitchinterval(5e-4)
+        # The main thread re-acquires the GIL after every C-ABI call (about 10 per level); while the worker runs
+        # Python it may wait one switch interval each time.  At the default 5 ms -- even at 0.5 ms -- that is
+        # longer than a level takes on the GPU and the launch queue runs dry; 50 us keeps it full.
+        self.switch_interval = 5e-5
 
     def _stage1(self, kwargs, main, after):
         with torch.cuda.device(self.device), torch.cuda.stream(self.side):
@@ -367,13 +379,22 @@ class GuidedPipeline:
     def run(self, batches):
         """batches: iterable of forward() keyword dicts (host or device tensors).  Yields the result dict of
         each batch in order; at most one batch is prepared ahead."""
-        from concurrent.futures import ThreadPoolExecutor
+        import sys
         main = torch.cuda.current_stream(self.device)
         it = iter(batches)
         try:
             first = next(it)
         except StopIteration:
             return
+        old_interval = sys.getswitchinterval()
+        sys.setswitchinterval(min(old_interval, self.switch_interval))
+        try:
+            yield from self._run(it, first, main)
+        finally:
+            sys.setswitchinterval(old_interval)
+
+    def _run(self, it, first, main):
+        from concurrent.futures import ThreadPoolExecutor
         with ThreadPoolExecutor(max_workers=1, thread_name_prefix="rg-stage1") as pool:
             fut = pool.submit(self._stage1, dict(first), main, None)
             cur = None                              # prepared + inverted, waiting for its guided pass

@@ -822,6 +822,46 @@ extern "C" int rg_guidance_steps(rg_handle, float* x, const float* in_seq, int64
     return 0;
 }
 
+// ---- whole loops in one call ------------------------------------------------------------------
+extern "C" int rg_run_levels(rg_handle m, int S, float* xj, int B, int E, const float* in_seq0,
+                             const float* inv_list, const float* noise, const int32_t* guidance_iters,
+                             float guidance_lr, int run_dead_guidance, const float* src_mask,
+                             const float* query_mask, const float* state, float* samples_out,
+                             float* x0_scratch, void* stream) {
+    if (!m || !xj || !src_mask || !state || !x0_scratch) return rg_fail("rg_run_levels: null argument");
+    if (B < 0 || E < 0 || B + E <= 0) return rg_fail("rg_run_levels: empty batch");
+    if (S < 1 || S > m->n_steps) return rg_fail("rg_run_levels: S = %d outside the schedule (%d steps)", S, m->n_steps);
+    if (E > 0 && !samples_out) return rg_fail("rg_run_levels: samples_out is required with exemplars");
+    if (B > 0 && (in_seq0 || inv_list) && !noise) return rg_fail("rg_run_levels: blend noise is required with in_seq");
+    const int T = m->cfg.n_tokens, D = RG_D;
+    const long long clip = (long long)T * D, nB = (long long)B * clip, nE = (long long)E * clip;
+    float* xe = xj + nB;
+    for (int j = 0; j < S; ++j) {
+        const int i = S - 1 - j;                       // guided level (descending); j = inversion level (ascending)
+        if (B > 0) {
+            const float* in_seq = (inv_list && i != S - 1) ? inv_list + (long long)i * nB : in_seq0;
+            if (in_seq) {
+                if (inv_list && i != S - 1 && run_dead_guidance && guidance_iters && guidance_iters[i] > 0)
+                    if (rg_guidance_steps(m, xj, in_seq, (long long)B * T, guidance_iters[i], guidance_lr, nB, stream)) return 1;
+                if (rg_blend_in_seq(m, xj, in_seq, noise + (long long)j * nB, i, xj, (long long)B * T, stream)) return 1;
+            }
+        }
+        if (B > 0 && E > 0) {
+            const int32_t clips[2] = {B, E}, steps[2] = {i, j};
+            if (rg_denoise_groups(m, xj, B + E, 2, clips, steps, src_mask, query_mask, state, x0_scratch, stream)) return 1;
+        } else {
+            if (rg_denoise(m, xj, B + E, B > 0 ? i : j, 0, src_mask, query_mask, state, x0_scratch, stream)) return 1;
+        }
+        if (B > 0 && rg_ddim_update(m, xj, x0_scratch, i, -1, xj, nB, stream)) return 1;
+        if (E > 0) {
+            float* sj = samples_out + (long long)j * nE;
+            if (rg_ddim_update(m, xe, x0_scratch + nB, j, +1, sj, nE, stream)) return 1;
+            CU(cudaMemcpyAsync(xe, sj, (size_t)nE * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+        }
+    }
+    return 0;
+}
+
 // ---- op-level entry points -------------------------------------------------------------------
 extern "C" int rg_op_linear(const float* x, int ldx, const float* W, const float* b,
                             const float* residual, float* out, int M, int N, int K, int epilogue,

@@ -261,62 +261,84 @@ class SpacedDiffusion:
                 img, x0 = self._forward_step(eng, prep, img, i, in_seq)
                 yield {"sample": img, "pred_xstart": x0}
 
-    def ddim_guided_and_reverse_loops(self, model, guided, reverse):
-        """The guided sampling loop of one batch and the DDIM inversion loop of ANOTHER batch's exemplars
-        advanced together: pass j evaluates the clips at level S-1-j and the exemplars at level j in ONE
-        denoiser call (rg_denoise_groups), so the per-kernel fixed costs of the 100-kernel chain are paid once
-        for both.  Per clip the arithmetic, and the order of the noise draws (only the guided loop draws),
-        are those of ddim_guided_sample_loop / ddim_reverse_sample_loop: results are bit-identical.
+    def run_levels(self, model, guided=None, reverse=None):
+        """All S levels of a sampling loop and/or an inversion loop in ONE call into the library
+        (rg_run_levels), the form MotionDiffusion uses on the hot path:
 
-        guided  = dict(shape, noise, model_kwargs, in_seq, guidance_iters, inverted_latent_list, guidance_lr)
-        reverse = dict(start_img, model_kwargs)
-        -> (final guided sample [B,T,D], list of S inverted latents [E,T,D])"""
+        guided  = dict(shape, noise, model_kwargs, in_seq, guidance_iters=None, inverted_latent_list=None,
+                       guidance_lr=0.1): ddim_guided_sample_loop when inverted_latent_list is given, else
+                       ddim_sample_loop (in_seq blended at every level);
+        reverse = dict(start_img, model_kwargs): ddim_reverse_sample_loop(return_all_timesteps=True) of ANOTHER
+                  batch's exemplars; pass j evaluates the clips at level S-1-j and the exemplars at level j in one
+                  kernel chain (rg_denoise_groups), so the fixed costs of the ~100-kernel chain are paid once.
+        -> (final sample [B,T,D] or None, list of S inverted latents [E,T,D] or None)
+
+        Per clip the arithmetic equals the step-by-step loops of this class.  All Gaussian draws of the loop are
+        made up front in the loop's order (per level: randn_like(in_seq) if there is one, then the unused
+        randn_like(x) of gaussian_diffusion.py:991), so any generator / noise tape sees the same sequence."""
         S = self.num_timesteps
         eng = self._engine(model)
-        B, (T, D) = guided["shape"][0], guided["shape"][1:]
-        inv_list, g_iters = guided["inverted_latent_list"], guided["guidance_iters"]
-        if inv_list is None:
-            raise ValueError("inverted_latent_list must be provided for guided sampling")
-        assert len(g_iters) == len(inv_list)
-        start = reverse["start_img"].float().contiguous()
-        E, device = start.shape[0], start.device
-        # K6 state of both groups (each through the model's own cache logic), then one joint batch
+        B = E = 0
+        parts = []
+        if guided is not None:
+            B = guided["shape"][0]
+            model._state_cache = (None, None)
+            parts.append(model.prepare_batch(guided["model_kwargs"], B))
+        if reverse is not None:
+            start = reverse["start_img"].float().contiguous()
+            E = start.shape[0]
+            model._state_cache = (None, None)
+            parts.append(model.prepare_batch(reverse["model_kwargs"], E))
         model._state_cache = (None, None)
-        pg = model.prepare_batch(guided["model_kwargs"], B)
-        model._state_cache = (None, None)
-        pr = model.prepare_batch(reverse["model_kwargs"], E)
-        model._state_cache = (None, None)
-        src_mask = torch.cat([pg.src_mask, pr.src_mask], 0)
-        qm = None
-        if pg.query_mask is not None and pr.query_mask is not None:
-            qm = torch.cat([pg.query_mask, pr.query_mask], 1).contiguous()
-        elif pg.query_mask is not None or pr.query_mask is not None:
-            raise NotImplementedError("both groups need a query_mask, or neither")
-        state = torch.cat([pg.state, pr.state], 0)
-        del pg, pr
-        img = guided["noise"] if guided["noise"] is not None else self._randn(guided["shape"], device)
+        assert parts, "run_levels needs a guided and/or a reverse part"
+        device = parts[0].state.device
+        if len(parts) == 2:
+            if (parts[0].query_mask is None) != (parts[1].query_mask is None):
+                raise NotImplementedError("both groups need a query_mask, or neither")
+            src_mask = torch.cat([p.src_mask for p in parts], 0)
+            qm = None if parts[0].query_mask is None else torch.cat([p.query_mask for p in parts], 1).contiguous()
+            state = torch.cat([p.state for p in parts], 0)
+        else:
+            src_mask, qm, state = parts[0].src_mask, parts[0].query_mask, parts[0].state
+        del parts
+        T, D = eng.n_tokens, eng.latent_dim
         xj = torch.empty(B + E, T, D, device=device)
-        xj[:B].copy_(img.float())
-        xj[B:].copy_(start)
-        x0 = torch.empty_like(xj)
-        samples = torch.empty(S, E, T, D, device=device)
-        in_seq, first = guided.get("in_seq", None), S - 1
-        with torch.no_grad():
+        in_seq0 = inv_list = noise = g_iters = samples = None
+        lr = 0.1
+        if guided is not None:
+            img = guided.get("noise", None)
+            xj[:B].copy_((img if img is not None else self._randn(guided["shape"], device)).float())
+            in_seq0, inv_list = guided.get("in_seq", None), guided.get("inverted_latent_list", None)
+            g_iters, lr = guided.get("guidance_iters", None), guided.get("guidance_lr", 0.1)
+            if inv_list is not None:
+                if g_iters is None:
+                    g_iters = [1] * S
+                assert len(g_iters) == len(inv_list) == S
+                inv_list = inv_list.float().contiguous()
+            if in_seq0 is not None:
+                in_seq0 = in_seq0.float().contiguous()
+            if in_seq0 is not None or inv_list is not None:
+                noise = torch.empty(S, B, T, D, device=device)
             for j in range(S):
-                i = S - 1 - j
-                if i != first:
-                    in_seq = inv_list[i]
-                    g = int(g_iters[i])
-                    if g > 0 and not self.skip_dead_guidance:
-                        eng.guidance_steps(xj[:B], in_seq.contiguous(), g, guided.get("guidance_lr", 0.1))
-                if in_seq is not None:
-                    eng.blend_in_seq(xj[:B], in_seq.contiguous(), self._randn(in_seq.shape, device), i, out=xj[:B])
-                eng.denoise_groups(xj, src_mask, qm, state, [(B, i), (E, j)], out=x0)
+                if (inv_list is not None and j != 0) or in_seq0 is not None:
+                    noise[j].copy_(self._randn((B, T, D), device))
                 self._randn((B, T, D), device)      # randn_like(x) of :991 -- sigma = 0, value unused
-                eng.ddim_update(xj[:B], x0[:B], i, -1, out=xj[:B])
-                eng.ddim_update(xj[B:], x0[B:], j, +1, out=samples[j])
-                xj[B:].copy_(samples[j])
-        return xj[:B].clone(), list(samples.unbind(0))
+        if reverse is not None:
+            xj[B:].copy_(start)
+            samples = torch.empty(S, E, T, D, device=device)
+        with torch.no_grad():
+            eng.run_levels(S, xj, B, E, src_mask, qm, state, in_seq0=in_seq0, inv_list=inv_list, noise=noise,
+                           guidance_iters=g_iters, guidance_lr=lr, run_dead_guidance=not self.skip_dead_guidance,
+                           samples_out=samples)
+        return (xj[:B].clone() if guided is not None else None,
+                list(samples.unbind(0)) if reverse is not None else None)
+
+    def ddim_guided_and_reverse_loops(self, model, guided, reverse):
+        """Guided sampling of one batch + DDIM inversion of another batch's exemplars, one kernel chain per
+        level (see run_levels)."""
+        if guided.get("inverted_latent_list", None) is None:
+            raise ValueError("inverted_latent_list must be provided for guided sampling")
+        return self.run_levels(model, guided=guided, reverse=reverse)
 
     def p_sample_loop(self, *a, **k):
         raise NotImplementedError("DDPM ancestral sampling is outside the rg_b200 hot path (inference_type='ddim')")

@@ -143,6 +143,29 @@ class DenoiserEngine:
                                                   _lib.stream_ptr()))
         return out
 
+    def run_levels(self, S, xj, B, E, src_mask, query_mask, state, in_seq0=None, inv_list=None, noise=None,
+                   guidance_iters=None, guidance_lr=0.1, run_dead_guidance=False, samples_out=None):
+        """rg_run_levels: S levels of guided/plain sampling for xj[:B] and of DDIM inversion for xj[B:B+E] in one
+        C call (one kernel chain per level for both ranges).  xj is updated in place."""
+        _lib.require_cuda(xj, src_mask, state)
+        for t in (xj, in_seq0, inv_list, noise, samples_out):
+            assert t is None or (t.is_contiguous() and t.dtype == torch.float32)
+        assert xj.shape[0] == B + E == state.shape[0] == src_mask.shape[0]
+        assert inv_list is None or tuple(inv_list.shape) == (S, B) + tuple(xj.shape[1:])
+        assert noise is None or tuple(noise.shape) == (S, B) + tuple(xj.shape[1:])
+        assert E == 0 or tuple(samples_out.shape) == (S, E) + tuple(xj.shape[1:])
+        gi = None
+        if guidance_iters is not None:
+            assert len(guidance_iters) >= S
+            gi = (C.c_int32 * len(guidance_iters))(*[int(g) for g in guidance_iters])
+        x0 = torch.empty_like(xj)
+        with torch.cuda.device(xj.device):
+            _lib.check(self.lib.rg_run_levels(self._h, int(S), _lib.ptr(xj), int(B), int(E), _lib.ptr(in_seq0),
+                                              _lib.ptr(inv_list), _lib.ptr(noise), gi, float(guidance_lr),
+                                              int(bool(run_dead_guidance)), _lib.ptr(src_mask), _lib.ptr(query_mask),
+                                              _lib.ptr(state), _lib.ptr(samples_out), _lib.ptr(x0), _lib.stream_ptr()))
+        return xj
+
     def ddim_update(self, x, x0, step_idx, direction, out=None):
         if out is None:
             out = torch.empty_like(x)

@@ -380,3 +380,49 @@ def test_fused_guided_and_reverse_loops_bit_identical(model, diffusion, dev):
     assert len(out_r) == len(ref_r) == 50
     for a, b in zip(out_r, ref_r):
         assert torch.equal(a, b)
+
+
+def test_run_levels_equals_step_loops(model, diffusion, dev):
+    """SpacedDiffusion.run_levels (all 50 levels inside one rg_run_levels call) == the step-by-step loops with the
+    reference's names, bit for bit and with the same noise-tape consumption: inversion only, plain sampling
+    with and without an in_seq blended at every level, guided sampling with the dead gradient steps executed."""
+    B, E, T, D, n = 2, 2, C.N_TOKENS, C.LATENT_DIM, C.N_CHUNKS
+    kwg = _kw(model, S.synthetic_conditions(B, seed=81), B, dev)
+    kwr = _kw(model, S.synthetic_conditions(E, seed=82), E, dev)
+    start_img = S.synthetic_latents(E, seed=83, scale=0.5).to(dev)
+    ref_r = diffusion.ddim_reverse_sample_loop(model, start_img=start_img, clip_denoised=False, model_kwargs=kwr,
+                                               eta=0, return_all_timesteps=True)
+    _, out_r = diffusion.run_levels(model, reverse=dict(start_img=start_img, model_kwargs=kwr))
+    assert all(torch.equal(a, b) for a, b in zip(out_r, ref_r)) and len(out_r) == 50
+
+    prev = torch.zeros(B, T, D)
+    prev[:, [0, n + 1, 2 * n + 2, 3 * n + 3]] = S.synthetic_latents(B, seed=84)[:, [9, 20, 31, 42]]
+    for in_seq in (None, prev.to(dev)):
+        tape = S.NoiseTape(7)
+        diffusion.noise_fn = tape.randn
+        ref = diffusion.ddim_sample_loop(model, (B, T, D), clip_denoised=False, model_kwargs=kwg, eta=0, in_seq=in_seq)
+        tail_ref = tape.randn((4,), dev)
+        tape = S.NoiseTape(7)
+        diffusion.noise_fn = tape.randn
+        out, _ = diffusion.run_levels(model, guided=dict(shape=(B, T, D), noise=None, model_kwargs=kwg, in_seq=in_seq))
+        assert torch.equal(out, ref)
+        assert torch.equal(tape.randn((4,), dev), tail_ref)         # the tape was consumed identically
+
+    inv_list = torch.zeros(50, B, T, D, device=dev)
+    inv_list[:, 0, 2:5] = S.synthetic_latents(50, seed=85)[:, 2:5].to(dev)
+    iters = [0] * 25 + list(range(25))
+    try:
+        diffusion.skip_dead_guidance = False
+        tape = S.NoiseTape(8)
+        diffusion.noise_fn = tape.randn
+        ref = diffusion.ddim_guided_sample_loop(model, (B, T, D), noise=None, clip_denoised=False, model_kwargs=kwg,
+                                                eta=0, in_seq=prev.to(dev), guidance_iters=iters,
+                                                inverted_latent_list=inv_list, guidance_lr=0.1)
+        tape = S.NoiseTape(8)
+        diffusion.noise_fn = tape.randn
+        out, _ = diffusion.run_levels(model, guided=dict(shape=(B, T, D), noise=None, model_kwargs=kwg,
+                                                         in_seq=prev.to(dev), guidance_iters=iters,
+                                                         inverted_latent_list=inv_list, guidance_lr=0.1))
+        assert torch.equal(out, ref)
+    finally:
+        diffusion.noise_fn, diffusion.skip_dead_guidance = None, True
