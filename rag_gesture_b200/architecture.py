@@ -212,12 +212,25 @@ class MotionDiffusion(nn.Module):
         inv_per_t = torch.zeros(diff.num_timesteps, B, T, D, device=device) if gb.use_guidance else None
         if gb.jobs:
             inv = gb.inv
+            src, dst = [], []                           # (exemplar, row) -> (clip, row), in the reference's order
             for e, ((b, _), ((r0, r1), (q0, q1))) in enumerate(zip(gb.jobs, gb.windows)):
                 assert r1 - r0 == q1 - q0
                 for o in (0, n + 1):                    # upper body and hands only
-                    start_noise[b, o + q0:o + q1] = inv[gb.inversion_start_time, e, o + r0:o + r1]
+                    src += [(e, o + r) for r in range(r0, r1)]
+                    dst += [(b, o + q) for q in range(q0, q1)]
+            if len(set(dst)) == len(dst):               # disjoint windows: one gather/scatter per tensor
+                if dst:
+                    ei, ri, bi, qi = (torch.tensor(v, dtype=torch.int64, device=device)
+                                      for v in (*zip(*src), *zip(*dst)))
+                    start_noise[bi, qi] = inv[gb.inversion_start_time][ei, ri]
                     if gb.use_guidance:
-                        inv_per_t[:, b, o + q0:o + q1] = inv[:, e, o + r0:o + r1]
+                        inv_per_t[:, bi, qi] = inv[:, ei, ri]
+            else:                                       # overlapping windows: later exemplars overwrite earlier ones
+                for e, ((b, _), ((r0, r1), (q0, q1))) in enumerate(zip(gb.jobs, gb.windows)):
+                    for o in (0, n + 1):
+                        start_noise[b, o + q0:o + q1] = inv[gb.inversion_start_time, e, o + r0:o + r1]
+                        if gb.use_guidance:
+                            inv_per_t[:, b, o + q0:o + q1] = inv[:, e, o + r0:o + r1]
         if gb.use_guidance and gb.use_prev and gb.prev_latent is not None:
             inv_per_t[:, :, [0, n + 1, 2 * n + 2, 3 * n + 3], :] = 0
         return start_noise, inv_per_t
@@ -362,15 +375,16 @@ class GuidedPipeline:
         if self.device.type != "cuda":
             raise RuntimeError("rg_b200: GuidedPipeline needs the model on a CUDA device (no CPU fallback)")
         self.side = torch.cuda.Stream(self.device)
-        # The main thread re-acquires the GIL after every C-ABI call (about 10 per level); while the worker runs
-        # Python it may wait one switch interval each time.  At the default 5 ms -- even at 0.5 ms -- that is
-        # longer than a level takes on the GPU and the launch queue runs dry; 50 us keeps it full.
-        self.switch_interval = 5e-5
+        # The main thread re-acquires the GIL after every blocking call; while the worker runs Python it may
+        # wait one switch interval each time (default 5 ms).  The loops are one C call per pass
+        # (rg_run_levels), so a moderate interval is enough; very short ones (50 us) make both threads thrash.
+        self.switch_interval = 5e-4
 
-    def _stage1(self, kwargs, main, after):
+    def _stage1(self, kwargs, main):
+        # No wait on the main stream here: the consumer may be a whole pass ahead of the device, and the
+        # host-side waits of this stage (text-similarity ranks) would then stall behind that pass.  Memory
+        # handed to the main stream is protected by record_stream below.
         with torch.cuda.device(self.device), torch.cuda.stream(self.side):
-            if after is not None:
-                self.side.wait_event(after)        # blocks freed by an earlier batch are not reused early
             gb = self.arch.prepare(defer_conditions=True, **kwargs)
             ready = self.side.record_event()
         _record_streams(gb, main)
@@ -396,14 +410,14 @@ class GuidedPipeline:
     def _run(self, it, first, main):
         from concurrent.futures import ThreadPoolExecutor
         with ThreadPoolExecutor(max_workers=1, thread_name_prefix="rg-stage1") as pool:
-            fut = pool.submit(self._stage1, dict(first), main, None)
+            fut = pool.submit(self._stage1, dict(first), main)
             cur = None                              # prepared + inverted, waiting for its guided pass
             while fut is not None or cur is not None:
                 gb = None
                 if fut is not None:
                     gb, ready = fut.result()
                     nxt = next(it, None)
-                    fut = pool.submit(self._stage1, dict(nxt), main, main.record_event()) if nxt is not None else None
+                    fut = pool.submit(self._stage1, dict(nxt), main) if nxt is not None else None
                     main.wait_event(ready)
                     self.arch.encode_clip_conditions(gb)
                 out = self.arch.run_pass(cur, gb)   # guided loop of `cur` fused with the inversion of `gb`
