@@ -1,8 +1,8 @@
 """Latent codec seam (GestureRepEncoder, diffusion_transformer.py:130-330).
 
-The 4 body-part TransformerVAEs are an ADJACENT component: frozen, run twice per batch
-and once per exemplar, and their hyper-parameter YAMLs + checkpoints are not in the reference repo.
-The hot path only needs an object with `.encode(...) -> (latents [B,43,512], mask [B,43])`,
+The 4 body-part TransformerVAEs (rag_gesture_b200/vae.py) are an ADJACENT component: frozen,
+run twice per batch and once per exemplar batch; their hyper-parameter YAMLs + checkpoints are not in the
+reference repo.  The hot path only needs an object with `.encode(...) -> (latents [B,43,512], mask [B,43])`,
 `.decode(latents) -> 7 pose tensors`, `.vae_latent_dim`, `.body_part_cat_axis`, `.frame_chunk_size`.
 `SyntheticGestureCodec` is such an object with fixed random linear maps per 15-frame chunk; it is
 what the golden pipeline fixtures, the tests and bench.py use on BOTH sides (it is injected into the
@@ -81,9 +81,10 @@ class SyntheticGestureCodec(nn.Module):
 
 
 def build_codec(vae_cfg, body_part_cat_axis="time"):
+    """vae_cfg with `upper_cfg / hands_cfg / face_cfg / lowertrans_cfg` YAML paths (the reference's config,
+    basegesture_len150_beat.py:78-81) -> the four TransformerVAEs (rag_gesture_b200.vae.GestureRepEncoder,
+    checkpoints loaded); without them -> the synthetic stand-in used by the fixtures and bench.py."""
     if any(k in vae_cfg for k in ("upper_cfg", "hands_cfg", "face_cfg", "lowertrans_cfg")):
-        raise NotImplementedError(
-            "loading the 4 TransformerVAE checkpoints (vae_cfg *_cfg yaml paths) is the next widening "
-            "step (SURVEY 8f.1); pass gesture_rep_encoder=<your GestureRepEncoder> to "
-            "ReGestureTransformer, or a vae_cfg without *_cfg paths for the synthetic codec")
+        from .vae import GestureRepEncoder
+        return GestureRepEncoder(vae_cfg, body_part_cat_axis)
     return SyntheticGestureCodec(vae_cfg, body_part_cat_axis)

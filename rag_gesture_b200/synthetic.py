@@ -122,6 +122,42 @@ def synthetic_state_dict(seed=0, normal_scale=False):
     return sd
 
 
+VAE_PART_FEATS = {"upper": 13 * 6, "hands": 30 * 6, "face": 1 * 6 + 100, "lowertrans": 9 * 6 + 3 + 4}
+
+
+def vae_args(part, latent_dim=64, num_heads=2, ff_size=128, num_layers=3, arch="all_encoder",
+             position_embedding="learned", vae_dist="normal", pre_norm=False, activation="gelu"):
+    """Hyper-parameter dict of one body-part TransformerVAE (the keys of the reference's VAE YAMLs,
+    gesture_vae.py:31-97; the shipped YAMLs and checkpoints are not in the reference repo)."""
+    return dict(latent_dim=latent_dim, frame_chunk_size=C.FRAME_CHUNK, decoder_arch=arch,
+                position_embedding=position_embedding, num_frames=C.MAX_SEQ_LEN, num_heads=num_heads,
+                ff_size=ff_size, dropout=0.1, transformer_activation=activation,
+                transformer_normalize_before=pre_norm, num_layers=num_layers, nfeats=VAE_PART_FEATS[part],
+                vae_dist=vae_dist, test_ckpt=f"ckpt/{part}_vae.bin")
+
+
+def synthetic_vae_state_dict(shapes, seed):
+    """Key-ordered deterministic weights for a TransformerVAE given {key: shape} of its state dict."""
+    g = torch.Generator().manual_seed(int(seed))
+    sd = OrderedDict()
+    for k in sorted(shapes):
+        shp = tuple(shapes[k])
+        r = torch.randn(shp, generator=g, dtype=torch.float32)
+        parts = k.split(".")
+        if k.endswith(".pe"):
+            v = 0.1 * r
+        elif len(parts) >= 2 and "norm" in parts[-2] and k.endswith("weight"):
+            v = 1.0 + 0.1 * r
+        elif k.endswith("bias"):
+            v = 0.05 * r
+        elif k == "global_motion_token":
+            v = 0.5 * r
+        else:
+            v = r * (1.0 / math.sqrt(shp[-1]))
+        sd[k] = v.contiguous()
+    return sd
+
+
 def synthetic_conditions(n_clips, seed=1234, first_clip=0):
     """Per-clip condition features of the len150@15fps shape: BERT-like
     `word` [B,150,768], wav2vec-like `audio` [B,499,768], `speaker_ids` [B,150] int64.

@@ -328,8 +328,89 @@ def gen_rotation(ns):
     save("rotation_crossfade", prev=prev, new=new, out=out, six=to6(prev))
 
 
+VAE_VARIANTS = {
+    "a": dict(arch="all_encoder", position_embedding="learned", vae_dist="normal", pre_norm=False, activation="gelu"),
+    "b": dict(arch="encoder_decoder", position_embedding="sine", vae_dist="multivariate_normal", pre_norm=True,
+              activation="relu", num_layers=2),
+}
+
+
+def codec_inputs(B, seed):
+    """Synthetic SMPL-X style inputs of GestureRepEncoder.encode (axis-angle parts, translation, expressions,
+    contacts), len150."""
+    g = torch.Generator().manual_seed(seed)
+    r = lambda *shape, s=1.0: s * torch.randn(*shape, generator=g)
+    F = C.MAX_SEQ_LEN
+    return dict(motion_upper=r(B, F, 39, s=0.4), motion_lower=r(B, F, 27, s=0.4), motion_face=r(B, F, 3, s=0.2),
+                motion_hands=r(B, F, 90, s=0.3), motion_transl=r(B, F, 3, s=0.5), motion_facial=r(B, F, 100, s=0.5),
+                motion_contact=(r(B, F, 4) > 0).float(), motion_mask=torch.ones(B, F))
+
+
+def write_vae_files(root, variant, seed0, shapes_of):
+    """YAML + checkpoint per body part, laid out as load_vae expects (diffusion_transformer.py:151-167);
+    every second checkpoint carries DataParallel's 'module.' prefix."""
+    import yaml
+    cfg = {"frame_chunk_size": C.FRAME_CHUNK, "latent_dim": 64}
+    for i, part in enumerate(("upper", "hands", "face", "lowertrans")):
+        args = S.vae_args(part, **VAE_VARIANTS[variant])
+        d = os.path.join(root, part)
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, "cfg.yaml"), "w") as f:
+            yaml.safe_dump(args, f)
+        sd = S.synthetic_vae_state_dict(shapes_of(args), seed0 + i)
+        if i % 2:
+            sd = {"module." + k: v for k, v in sd.items()}
+        torch.save({"model_state": sd}, os.path.join(d, os.path.basename(args["test_ckpt"])))
+        cfg[f"{part}_cfg"] = os.path.join(d, "cfg.yaml")
+    return cfg
+
+
+def gen_codec(ns):
+    """TransformerVAE (both decoder architectures / position embeddings / distributions) and GestureRepEncoder
+    of the unmodified reference on synthetic weights (rag_gesture_b200.synthetic.synthetic_vae_state_dict)."""
+    import importlib
+    import json
+    import tempfile
+    from argparse import Namespace
+    gv = importlib.import_module("mogen.models.transformers.gesture_vae")
+    out = {}
+    for name, var in VAE_VARIANTS.items():
+        args = S.vae_args("upper", **var)
+        ref = gv.TransformerVAE(Namespace(**args)).eval()
+        shapes = {k: tuple(v.shape) for k, v in ref.state_dict().items()}
+        ref.load_state_dict(S.synthetic_vae_state_dict(shapes, 100))
+        x = 0.5 * torch.randn(3, C.MAX_SEQ_LEN, args["nfeats"], generator=torch.Generator().manual_seed(5))
+        with torch.no_grad():
+            torch.manual_seed(21)
+            z, _ = ref.encode_to_dist(x)
+            rec = ref.decode(z)
+            torch.manual_seed(22)
+            lengths = [150, 120, 45]
+            z_r, _ = ref.encode_to_dist(x, lengths)
+            rec_r = ref.decode(z_r, lengths)
+        out.update({f"{name}_keys": json.dumps({k: list(v) for k, v in shapes.items()}), f"{name}_z": z,
+                    f"{name}_rec": rec[:, ::5], f"{name}_z_ragged": z_r, f"{name}_rec_ragged": rec_r[:, ::5],
+                    f"{name}_in_digest": digest(x)})
+    with tempfile.TemporaryDirectory() as root:
+        def shapes_of(args):
+            return {k: tuple(v.shape) for k, v in gv.TransformerVAE(Namespace(**args)).state_dict().items()}
+        cfg = write_vae_files(root, "a", 200, shapes_of)
+        enc = ns.dt.GestureRepEncoder(cfg, "time").eval()
+        inp = codec_inputs(2, 31)
+        with torch.no_grad():
+            torch.manual_seed(41)
+            motion, mask = enc.encode(**{k: v.clone() for k, v in inp.items()})
+            dec = enc.decode(motion)
+            torch.manual_seed(42)                                  # exemplars are encoded one by one at B=1
+            singles = [enc.encode(**{k: v[e:e + 1].clone() for k, v in inp.items()})[0] for e in range(2)]
+        out.update(enc_motion=motion, enc_mask=mask, enc_single=torch.cat(singles, 0), enc_in_digest=digest(*inp.values()))
+        for k, v in zip(("upper", "lower", "face", "hands", "transl", "exps", "contact"), dec):
+            out[f"dec_{k}"] = v[:, ::10]
+    save("codec_vae", **out)
+
+
 GROUPS = {"rotation": gen_rotation, "schedule": gen_schedule, "denoiser": gen_denoiser, "loops": gen_loops,
-          "retrieval": gen_retrieval, "pipeline": gen_pipeline}
+          "retrieval": gen_retrieval, "pipeline": gen_pipeline, "codec": gen_codec}
 
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
