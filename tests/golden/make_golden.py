@@ -346,13 +346,13 @@ def codec_inputs(B, seed):
                 motion_contact=(r(B, F, 4) > 0).float(), motion_mask=torch.ones(B, F))
 
 
-def write_vae_files(root, variant, seed0, shapes_of):
+def write_vae_files(root, variant, seed0, shapes_of, latent_dim=64):
     """YAML + checkpoint per body part, laid out as load_vae expects (diffusion_transformer.py:151-167);
     every second checkpoint carries DataParallel's 'module.' prefix."""
     import yaml
-    cfg = {"frame_chunk_size": C.FRAME_CHUNK, "latent_dim": 64}
+    cfg = {"frame_chunk_size": C.FRAME_CHUNK, "latent_dim": latent_dim}
     for i, part in enumerate(("upper", "hands", "face", "lowertrans")):
-        args = S.vae_args(part, **VAE_VARIANTS[variant])
+        args = S.vae_args(part, latent_dim=latent_dim, **VAE_VARIANTS[variant])
         d = os.path.join(root, part)
         os.makedirs(d, exist_ok=True)
         with open(os.path.join(d, "cfg.yaml"), "w") as f:

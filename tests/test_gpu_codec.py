@@ -1,0 +1,75 @@
+"""The TransformerVAE codec on the device and inside MotionDiffusion.forward (vae_cfg with YAML paths, as the
+reference's config has them).  Needs a GPU."""
+import importlib.util
+import os
+
+import pytest
+import torch
+
+from conftest import GOLDEN, rel_l2
+from rag_gesture_b200 import config as C
+from rag_gesture_b200 import synthetic as S
+from rag_gesture_b200.vae import GestureRepEncoder, TransformerVAE
+
+pytestmark = pytest.mark.gpu
+_spec = importlib.util.spec_from_file_location("make_golden_codec", os.path.join(GOLDEN, "make_golden.py"))
+
+
+@pytest.fixture(scope="module")
+def mg():
+    m = importlib.util.module_from_spec(_spec)
+    _spec.loader.exec_module(m)
+    return m
+
+
+def test_vae_device_matches_host(mg):
+    """Same weights, inputs and eps: the fused-attention path on CUDA == the CPU path pinned to the reference."""
+    dev = torch.device("cuda:0")
+    for name in ("a", "b"):
+        vae = TransformerVAE(S.vae_args("hands", **mg.VAE_VARIANTS[name])).eval()
+        vae.load_state_dict(S.synthetic_vae_state_dict({k: tuple(v.shape) for k, v in vae.state_dict().items()}, 7))
+        g = torch.Generator().manual_seed(9)
+        x, eps = 0.5 * torch.randn(4, 150, 180, generator=g), torch.randn(40, 1, 64, generator=g)
+        with torch.no_grad():
+            z, _ = vae.encode_to_dist(x, [150, 150, 90, 30], eps=eps)
+            rec = vae.decode(z, [150, 150, 90, 30])
+            vd = vae.to(dev)
+            zd, _ = vd.encode_to_dist(x.to(dev), [150, 150, 90, 30], eps=eps.to(dev))
+            recd = vd.decode(zd, [150, 150, 90, 30])
+        assert rel_l2(zd.cpu(), z) < 1e-4 and rel_l2(recd.cpu(), rec) < 1e-4, name
+
+
+def test_forward_with_transformer_vae_codec(mg, tmp_path):
+    """build_architecture with the reference-style vae_cfg (four YAML + checkpoint pairs): encode -> plain DDIM
+    on the CUDA path -> decode; deterministic under fixed seeds, finite, reference output shapes."""
+    import rag_gesture_b200 as R
+    dev = torch.device("cuda:0")
+
+    def shapes_of(args):
+        return {k: tuple(v.shape) for k, v in TransformerVAE(args).state_dict().items()}
+    vae_cfg = mg.write_vae_files(str(tmp_path), "a", 300, shapes_of, latent_dim=C.LATENT_DIM)
+    cfg = C.model_cfg()
+    cfg["model"]["vae_cfg"] = vae_cfg
+    arch = R.build_architecture(cfg, database=None)
+    assert isinstance(arch.model.gesture_rep_encoder, GestureRepEncoder)
+    missing, unexpected = arch.model.load_state_dict(S.synthetic_state_dict(0), strict=False)
+    assert not unexpected and all(k.startswith("gesture_rep_encoder.") for k in missing)
+    arch = arch.to(dev).eval()
+    qs = S.SyntheticGestureDataset(4, seed=8)
+    outs = []
+    for _ in range(2):
+        batch = S.collate([qs[i] for i in (0, 2)])
+        batch["inference_kwargs"] = {}
+        torch.manual_seed(3)
+        torch.cuda.manual_seed(4)
+        res = arch(**batch)
+        outs.append({k: res[k].cpu() for k in ("prev_latentout", "pred_upper", "pred_lower", "pred_facepose",
+                                               "pred_hands", "pred_transl", "pred_exps")})
+    a, b = outs
+    assert tuple(a["prev_latentout"].shape) == (2, 43, 512) and tuple(a["pred_upper"].shape) == (2, 150, 39)
+    assert tuple(a["pred_lower"].shape) == (2, 150, 27) and tuple(a["pred_hands"].shape) == (2, 150, 90)
+    assert tuple(a["pred_facepose"].shape) == (2, 150, 3) and tuple(a["pred_exps"].shape) == (2, 150, 100)
+    assert tuple(a["pred_transl"].shape) == (2, 150, 3)
+    for k in a:
+        assert bool(torch.isfinite(a[k]).all()), k
+        assert torch.equal(a[k], b[k]), k

@@ -55,6 +55,12 @@ def _worker(rank, world, port, n_total):
         idx, sc = sharded_knn(db[lo:hi], q, 4, n_total, local_topk=_oracle_topk, merge=_oracle_merge)
         ref_i, ref_s = _oracle_topk(db, q, 4, 0)
         assert torch.equal(idx, ref_i) and torch.allclose(sc, ref_s)
+        # a per-shard index object (KnnIndex on the GPU box) takes the place of the local scan
+        class ShardIndex:
+            def topk(self, queries, k, idx_base=0):
+                return _oracle_topk(db[lo:hi], queries, k, idx_base)
+        idx2, sc2 = sharded_knn(db[lo:hi], q, 4, n_total, merge=_oracle_merge, index=ShardIndex())
+        assert torch.equal(idx2, ref_i) and torch.allclose(sc2, ref_s)
         # clip shards: each rank "samples" its own clips, the gather restores clip order
         n_clips = 7
         clo, chi = shard_range(n_clips, rank, world)
