@@ -448,6 +448,19 @@ cudaError_t launch_tc_scan(const KnnIndex* ix, const __nv_bfloat16* q16, int q, 
 
 int next_pow2(int v) { int p = 2; while (p < v) p <<= 1; return p; }
 
+// stream-ordered scratch released on every exit path of the entry points below
+struct Scratch {
+    cudaStream_t st;
+    std::vector<void*> ptrs;
+    explicit Scratch(cudaStream_t s) : st(s) {}
+    ~Scratch() { for (void* p : ptrs) cudaFreeAsync(p, st); }
+    template <typename T> cudaError_t get(T** p, size_t bytes) {
+        cudaError_t e = cudaMallocAsync((void**)p, bytes ? bytes : 4, st);
+        if (e == cudaSuccess) ptrs.push_back(*p);
+        return e;
+    }
+};
+
 }  // namespace
 
 extern "C" int rg_knn_index_create(const float* db, int64_t n, int dim, void** index, void* stream) {
@@ -498,13 +511,14 @@ extern "C" int rg_knn_topk_tc(void* index, const float* db, const float* queries
     const int dim = ix->dim;
     const Plan pl = make_plan(ix->n, q);
     const int nc = pl.chunks * KP, ncp = next_pow2(nc);
+    Scratch scratch(st);
     __nv_bfloat16* q16 = nullptr;
     float* cand_score = nullptr;
     int *cand_idx = nullptr, *fail = nullptr;          // fail[0] = count, fail[1..] = query ids
-    RG_CU(cudaMallocAsync((void**)&q16, (size_t)q * dim * 2, st));
-    RG_CU(cudaMallocAsync((void**)&cand_score, (size_t)q * nc * sizeof(float), st));
-    RG_CU(cudaMallocAsync((void**)&cand_idx, (size_t)q * nc * sizeof(int), st));
-    RG_CU(cudaMallocAsync((void**)&fail, (size_t)(q + 1) * sizeof(int), st));
+    RG_CU(scratch.get(&q16, (size_t)q * dim * 2));
+    RG_CU(scratch.get(&cand_score, (size_t)q * nc * sizeof(float)));
+    RG_CU(scratch.get(&cand_idx, (size_t)q * nc * sizeof(int)));
+    RG_CU(scratch.get(&fail, (size_t)(q + 1) * sizeof(int)));
     RG_CU(cudaMemsetAsync(fail, 0, sizeof(int), st));
     const long long n4 = (long long)q * dim / 4;
     knn_to_bf16_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(queries, q16, n4);
@@ -528,20 +542,17 @@ extern "C" int rg_knn_topk_tc(void* index, const float* db, const float* queries
     if (nf > 0) {
         // exact scan for the queries without a certificate
         float* qbuf = nullptr; long long* tidx = nullptr; float* tsc = nullptr;
-        RG_CU(cudaMallocAsync((void**)&qbuf, (size_t)nf * dim * sizeof(float), st));
-        RG_CU(cudaMallocAsync((void**)&tidx, (size_t)nf * k * sizeof(long long), st));
-        RG_CU(cudaMallocAsync((void**)&tsc, (size_t)nf * k * sizeof(float), st));
+        RG_CU(scratch.get(&qbuf, (size_t)nf * dim * sizeof(float)));
+        RG_CU(scratch.get(&tidx, (size_t)nf * k * sizeof(long long)));
+        RG_CU(scratch.get(&tsc, (size_t)nf * k * sizeof(float)));
         knn_gather_queries_kernel<<<nf, 256, 0, st>>>(queries, fail + 1, dim, qbuf);
         RG_CU(cudaGetLastError());
         if (rg_knn_topk(db, ix->n, dim, qbuf, nf, k, idx_base, (int64_t*)tidx, tsc, stream)) return 1;
         knn_scatter_results_kernel<<<nf, 32, 0, st>>>(tidx, tsc, fail + 1, k, (long long*)out_idx, out_score);
         RG_CU(cudaGetLastError());
         rg_count_launch(2);
-        RG_CU(cudaFreeAsync(qbuf, st)); RG_CU(cudaFreeAsync(tidx, st)); RG_CU(cudaFreeAsync(tsc, st));
     }
     if (n_uncertified) *n_uncertified = nf;
-    RG_CU(cudaFreeAsync(q16, st)); RG_CU(cudaFreeAsync(cand_score, st));
-    RG_CU(cudaFreeAsync(cand_idx, st)); RG_CU(cudaFreeAsync(fail, st));
     return 0;
 }
 

@@ -328,6 +328,33 @@ def gen_rotation(ns):
     save("rotation_crossfade", prev=prev, new=new, out=out, six=to6(prev))
 
 
+def gen_postprocess(ns):
+    """tools/visualize.py:204-291 restated with the reference's rotation_conversions: part recomposition by the
+    dataset's 0/1 masks and the 15 -> 30 fps interpolation in 6D space."""
+    import importlib
+    rc = importlib.import_module("mogen.models.utils.rotation_conversions")
+    g = torch.Generator().manual_seed(12)
+    bs, n, J = 2, 20, 55
+    perm = torch.randperm(J, generator=g)
+    masks = {}
+    for name, cnt, off in (("upper", 13, 0), ("lower", 9, 13), ("hands", 30, 22), ("face", 1, 52)):
+        m = np.zeros(J * 3)
+        for j in perm[off:off + cnt].tolist():
+            m[3 * j:3 * j + 3] = 1
+        masks[name] = m
+    parts = {k: 0.6 * torch.randn(bs, n, int(m.sum()), generator=g) for k, m in masks.items()}
+    facial, trans = torch.randn(bs, n, 100, generator=g), torch.randn(bs, n, 3, generator=g)
+    motion = torch.zeros(bs, n, J * 3)
+    for k in ("upper", "lower", "hands", "face"):
+        motion[..., masks[k].astype(bool)] = parts[k]
+    up = lambda x: torch.nn.functional.interpolate(x.permute(0, 2, 1), scale_factor=30 / 15, mode="linear").permute(0, 2, 1)
+    six = rc.matrix_to_rotation_6d(rc.axis_angle_to_matrix(motion.reshape(bs, n, J, 3))).reshape(bs, n, J * 6)
+    six = up(six)
+    aa = rc.matrix_to_axis_angle(rc.rotation_6d_to_matrix(six.reshape(bs, 2 * n, J, 6))).reshape(bs, 2 * n, J * 3)
+    save("postprocess", motion=motion, aa30=aa, facial30=up(facial), trans30=up(trans), facial=facial, trans=trans,
+         **{f"mask_{k}": v for k, v in masks.items()}, **{f"part_{k}": v for k, v in parts.items()})
+
+
 VAE_VARIANTS = {
     "a": dict(arch="all_encoder", position_embedding="learned", vae_dist="normal", pre_norm=False, activation="gelu"),
     "b": dict(arch="encoder_decoder", position_embedding="sine", vae_dist="multivariate_normal", pre_norm=True,
@@ -410,7 +437,7 @@ def gen_codec(ns):
 
 
 GROUPS = {"rotation": gen_rotation, "schedule": gen_schedule, "denoiser": gen_denoiser, "loops": gen_loops,
-          "retrieval": gen_retrieval, "pipeline": gen_pipeline, "codec": gen_codec}
+          "retrieval": gen_retrieval, "pipeline": gen_pipeline, "codec": gen_codec, "postprocess": gen_postprocess}
 
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
