@@ -390,7 +390,11 @@ def gemm_roofline_tc(n_clips, dev, flush, tc_peak, peak_src, split):
     return {"bound": "tensor", "kernel": "gemm_tc_kernel<128,*> (tcgen05.mma kind::f16, TMA-fed, TMEM accumulator; all "
             "GEMM launches of one inversion + one sampling evaluation, time-weighted, L2 flushed before each)",
             "achieved": round(ach, 1), "peak": tc_peak, "unit": "TFLOP/s", "frac": round(ach / tc_peak, 4),
-            "traffic": None, "peak_source": f"{peak_src} bf16 sustained", "rows": [c * 43 for c in n_clips],
+            # dram__bytes_read+write of ONE launch of the costliest shape (qkv / ca_q, N=1536, M=4128) from the
+            # committed ncu --set full capture (profiles/ncu_full_gemm_s3_r01.txt); its algorithmic DRAM bytes are
+            # A 4.2 MB + W 1.6 MB (the fp32 output stays in L2 for the next kernel): no re-reads
+            "traffic": 5832704, "traffic_source": "profiles/ncu_full_gemm_s3_r01.txt, gemm_tc_kernel<128,3,0> grid (12,33)",
+            "peak_source": f"{peak_src} bf16 sustained", "rows": [c * 43 for c in n_clips],
             "per_shape_tflops": per, "executed_flop_multiplier": 3 if split else 1}
 
 
@@ -465,6 +469,9 @@ def knn_bench(args, dev, rank, world, hbm_peak, tc_peak, peak_src, flush):
                             "top-16 per (query, chunk) selected in the epilogue; scores never leave the SM)",
                             "launch_ms": round(ms_tc.value, 3), "achieved": round(tc_tf, 1), "peak": tc_peak,
                             "unit": "TFLOP/s", "frac": round(tc_tf / tc_peak, 4), "peak_source": f"{peak_src} bf16 sustained",
+                            # ncu --set full at N = 1M, Q = 4096 (profiles/ncu_full_knn_tc_r01.txt): the bf16 shard
+                            # (1.536 GB) is read from DRAM once, candidates written once
+                            "traffic": 1544255000 + 7865600 if (hi - lo) == 1_000_000 else None,
                             "flop_per_launch": 2.0 * 4096 * (hi - lo) * dim}}
 
 
