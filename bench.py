@@ -261,6 +261,8 @@ def run_b200(args):
 
     # ---- roofline of the dominant kernel family: the dense GEMMs of one denoiser evaluation --------------
     roof = gemm_roofline(arch, [B, E], dev, flush, tc_sus, peak_src, args.precision)
+    if args.precision != "fp32":
+        roof = gemm_chain_roofline(arch, [B, E], dev, flush, tc_sus, roof)
     knn = knn_bench(args, dev, rank, world, hbm_peak, tc_sus, peak_src, flush)
 
     if rank == 0:
@@ -358,6 +360,67 @@ def gemm_roofline(arch, n_clips, dev, flush, tc_peak, peak_src, precision):
             "frac": round(ach / tc_peak, 4), "traffic": None, "peak_source": f"{peak_src} bf16 sustained",
             "rows": M, "per_shape_tflops": per,
             "note": "exact fp32 tier runs on CUDA cores; the tcgen05 bf16 path is the next kernel"}
+
+
+def gemm_chain_roofline(arch, n_clips, dev, flush, tc_peak, isolated):
+    """The dense contractions as they run INSIDE a step: rg_probe_gemm_only makes rg_denoise launch only its
+    GEMMs -- the model's own weights (a different matrix per layer), the step's shapes, epilogues and
+    programmatic-dependent-launch chain -- and 10 such evaluations are timed back to back with CUDA events on
+    the launching stream (one L2 flush before them, as in the loop where weights stay L2-resident between
+    levels).  achieved = algorithmic GEMM flops (3.291 GFLOP per clip-step) / that time, over the inversion
+    (E clips) and the sampling (B clips) row counts.  The isolated, L2-flushed per-launch figures stay in
+    `isolated`; `gemm_share` is GEMM-only time / full evaluation time (ncu launch list: 67 %)."""
+    from rag_gesture_b200 import _lib, synthetic as S
+    from rag_gesture_b200 import config as C
+    lib = _lib.load()
+    eng = arch.model.rg_engine(arch.diffusion_test)
+
+    def evals(fn, n):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n / 1e3
+
+    tot_t, tot_f, per, share = 0.0, 0.0, {}, {}
+    for clips in n_clips:
+        if clips <= 0:
+            continue
+        cond = S.synthetic_conditions(clips, seed=5)
+        xf = eng.encode_conditions(cond["word"].to(dev), cond["audio"].to(dev), cond["speaker_ids"].to(dev))
+        state = eng.precompute_state(xf)
+        x, sm = S.synthetic_latents(clips, seed=6).to(dev), S.motion_mask(clips).to(dev)
+        qm = torch.stack([S.query_masks(clips)[c] for c in C.CONDS], 0).to(dev).contiguous()
+        out = torch.empty_like(x)
+        step = lambda: eng.denoise(x, sm, qm, state, step_idx=10, out=out)
+        for _ in range(3):
+            step()
+        t_full = evals(step, 10)
+        _lib.check(lib.rg_probe_gemm_only(eng._h, 1))
+        try:
+            for _ in range(2):
+                step()
+            t_gemm = evals(step, 10)
+        finally:
+            _lib.check(lib.rg_probe_gemm_only(eng._h, 0))
+        flops = GEMM_GFLOP_PER_CLIP_STEP * 1e9 * clips
+        per[f"M{clips * 43}"] = round(flops / t_gemm / 1e12, 1)
+        share[f"M{clips * 43}"] = round(t_gemm / t_full, 3)
+        tot_t += t_gemm
+        tot_f += flops
+    ach = tot_f / tot_t / 1e12
+    return {"bound": "tensor", "kernel": "gemm_tc_kernel<128,*> (tcgen05.mma kind::f16, TMA-fed, TMEM accumulator): the 106 GEMM "
+            "launches of one denoiser evaluation as their own PDL chain (rg_probe_gemm_only), 10 evaluations back to back",
+            "achieved": round(ach, 1), "peak": tc_peak, "unit": "TFLOP/s", "frac": round(ach / tc_peak, 4),
+            "traffic": isolated.get("traffic"), "traffic_source": isolated.get("traffic_source"),
+            "peak_source": isolated.get("peak_source"), "rows": isolated.get("rows"), "in_chain_tflops": per,
+            "gemm_share": share, "executed_flop_multiplier": isolated.get("executed_flop_multiplier"),
+            "isolated": {"achieved": isolated["achieved"], "frac": isolated["frac"],
+                         "how": "every shape launched alone, L2 flushed before each launch, time-weighted",
+                         "per_shape_tflops": isolated["per_shape_tflops"]}}
 
 
 def gemm_roofline_tc(n_clips, dev, flush, tc_peak, peak_src, split):

@@ -171,6 +171,11 @@ int rg_op_linear_tc(const float* x, const float* W, const float* b, const float*
  * launch to evict L2); *median_ms receives the median launch time.  Synchronises. */
 int rg_probe_gemm_tc(const float* x, const float* W, const float* b, float* out, int M, int N, int K,
                      int split, int reps, void* flush_buf, int64_t flush_bytes, float* median_ms, void* stream);
+/* Measurement probe for bench.py's roofline: while on, rg_denoise / rg_denoise_groups of this handle (tensor-core
+ * tiers) launch ONLY their dense contractions -- the same programmatic-dependent-launch chain, weights, shapes and
+ * epilogues as in the step, without the attention and row kernels between them (outputs are then meaningless).
+ * Time a few evaluations with CUDA events, then switch it off. */
+int rg_probe_gemm_only(rg_handle h, int on);
 /* Diagnostics: one traced launch of the tcgen05 GEMM on zero operands (after 3 untraced ones).  trace_host
  * receives 10 int64 per CTA (grid order x-fastest): clock64 at [0] entry, [1] prologue done, [2] producer
  * past griddepcontrol.wait, [3] first operand stage landed, [4] last MMA committed, [5] accumulator visible

@@ -82,6 +82,7 @@ struct rg_model {
     // tensor-core path (cfg.precision != RG_PREC_FP32)
     int planes;              // 1: bf16 operands, 2: hi|lo planes (bf16x3)
     int attn_mode_ca;
+    int gemm_only;           // measurement probe (rg_probe_gemm_only): rg_denoise launches its GEMMs only
     int fuse_styl_max;       // largest batch (clips) that takes the attention kernels fused with the Stylization prologue
     int attn_mode;           // attention cores: 0 fp32 SIMT, 1 TF32 mma.sync (bf16 tier), 2 3xTF32 (bf16x3 tier)
     std::vector<LayerTc> tc;
@@ -247,6 +248,7 @@ extern "C" int rg_create(const rg_config* cfg, int n_tensors, const char* const*
     m->attn_mode_ca = m->attn_mode;
     if (const char* e = getenv("RG_ATTN_MODE")) m->attn_mode = m->attn_mode_ca = atoi(e);      // diagnostics only
     if (const char* e = getenv("RG_ATTN_MODE_CA")) m->attn_mode_ca = atoi(e);
+    m->gemm_only = 0;
     m->fuse_styl_max = 128;
     if (const char* e = getenv("RG_FUSE_STYL_MAX")) m->fuse_styl_max = atoi(e);
     m->kv_a16 = nullptr;
@@ -572,20 +574,24 @@ static int denoise_tc(rg_model* m, Ws& w, const float* x, int B, const float* ss
     const long long clip_stride = rg_state_floats_per_clip(m);
     const long long HS = (long long)RG_H * RG_HD * RG_HD;
     const int lo = P == 2;
-    LAUNCH(rg_launch_split_bf16(x, D, w.x16, D * P, lo ? D : 0, M, D, st));
+    // gemm_only (roofline probe): the dense contractions of the evaluation as the same PDL chain, same weights,
+    // shapes and epilogues, without the attention / row kernels between them (their inputs are then stale data)
+    const bool all = !m->gemm_only;
+    if (all) LAUNCH(rg_launch_split_bf16(x, D, w.x16, D * P, lo ? D : 0, M, D, st));
     if (tc_gemm(m, w.tm_x16, D, m->tc_joint, m->b_joint, M, D, D, RG_EPI_BIAS_POS, nullptr, w.h, D, nullptr, 0, st)) return 1;
     for (int l = 0; l < L; ++l) {
         const Layer& ly = m->layers[l];
         const LayerTc& t = m->tc[l];
         const float* ss = ssrow + (long long)l * 5 * 2 * D;
         // --- self-attention
-        LAUNCH(rg_launch_ln_rows(w.h, D, nullptr, nullptr, rg_out_b16(w.a16, D * P, lo ? D : 0), M, st));
+        if (all) LAUNCH(rg_launch_ln_rows(w.h, D, nullptr, nullptr, rg_out_b16(w.a16, D * P, lo ? D : 0), M, st));
         if (tc_gemm(m, w.tm_a16, D, t.qkv, ly.bqkv, M, 3 * D, D, RG_EPI_BIAS, nullptr, w.big, 3 * D, nullptr, 0, st)) return 1;
         RgStylParams sp = {ly.sa_g, ly.sa_b, ss, ss_stride};
         // mma.sync core + Stylization prologue in one kernel (one CTA per clip): measured faster than core +
         // row kernel for the single-pass TF32 cores up to ~128 clips; the 3xTF32 variant is register-bound
         const bool fuse_styl = m->attn_mode == 1 && B <= m->fuse_styl_max;
-        if (fuse_styl) {
+        if (!all) {
+        } else if (fuse_styl) {
             LAUNCH(rg_launch_sa_styl(w.big, src_mask, sp, rg_out_b16(w.a16, D * P, lo ? D : 0), B, T, m->attn_mode == 2, st));
         } else {
             LAUNCH(rg_launch_sa_core(w.big, src_mask, w.y, B, T, m->attn_mode, st));
@@ -602,11 +608,12 @@ static int denoise_tc(rg_model* m, Ws& w, const float* x, int B, const float* ss
             LAUNCH(rg_launch_gemm_tc(w.tm_a16, t.sa_o.tm, p, st));
         }
         // --- three cross-attentions on the same h, their projections and ca_mix folded into one GEMM
-        LAUNCH(rg_launch_ln_rows(w.h, D, nullptr, nullptr, rg_out_b16(w.a16, D * P, lo ? D : 0), M, st));
+        if (all) LAUNCH(rg_launch_ln_rows(w.h, D, nullptr, nullptr, rg_out_b16(w.a16, D * P, lo ? D : 0), M, st));
         if (tc_gemm(m, w.tm_a16, D, t.caq, ly.bcaq, M, 3 * D, D, RG_EPI_BIAS, nullptr, w.big, 3 * D, nullptr, 0, st)) return 1;
         RgStylParams sp3[3];
         for (int c = 0; c < 3; ++c) sp3[c] = {ly.ca_g + c * D, ly.ca_b + c * D, ss + (1 + c) * 2 * D, ss_stride};
-        if (m->attn_mode_ca == 1 && B <= m->fuse_styl_max) {
+        if (!all) {
+        } else if (m->attn_mode_ca == 1 && B <= m->fuse_styl_max) {
             LAUNCH(rg_launch_ca_styl(w.big, 3 * D, state + (long long)l * 3 * HS, clip_stride, HS, query_mask, qm_cond_stride,
                                      sp3, rg_out_b16(w.a16x, 4 * D * P, lo ? 4 * D : 0), B, T, m->attn_mode_ca == 2, st));
         } else {
@@ -619,7 +626,7 @@ static int denoise_tc(rg_model* m, Ws& w, const float* x, int B, const float* ss
         if (tc_gemm(m, w.tm_h16, D, t.w1, ly.b1, M, F, D, RG_EPI_BIAS_GELU, nullptr, nullptr, 0, w.g16, F, st)) return 1;
         if (tc_gemm(m, w.tm_g16, F, t.w2, ly.b2, M, D, F, RG_EPI_BIAS, nullptr, w.y, D, nullptr, 0, st)) return 1;
         RgStylParams spf = {ly.ffn_g, ly.ffn_b, ss + 4 * 2 * D, ss_stride};
-        LAUNCH(rg_launch_styl_rows(w.y, D, spf, T, rg_out_b16(w.a16, D * P, lo ? D : 0), M, st));
+        if (all) LAUNCH(rg_launch_styl_rows(w.y, D, spf, T, rg_out_b16(w.a16, D * P, lo ? D : 0), M, st));
         if (tc_gemm(m, w.tm_a16, D, t.ffn_o, ly.ffn_bo, M, D, D, RG_EPI_BIAS_RESIDUAL, w.h, w.h, D, w.h16, D, st)) return 1;
     }
     return tc_gemm(m, w.tm_h16, D, m->tc_out, m->b_out, M, D, D, RG_EPI_BIAS, nullptr, x0_out, D, nullptr, 0, st);
@@ -951,6 +958,11 @@ extern "C" int rg_probe_gemm_tc(const float* x, const float* W, const float* b, 
     *median_ms = ts[ts.size() / 2];
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaFree(a16); cudaFree(w16);
+    return 0;
+}
+extern "C" int rg_probe_gemm_only(rg_handle m, int on) {
+    if (!m) return rg_fail("rg_probe_gemm_only: null handle");
+    m->gemm_only = on ? 1 : 0;
     return 0;
 }
 extern "C" int rg_probe_gemm_trace(int M, int N, int K, int split, int epilogue, int64_t* trace_host,
