@@ -16,9 +16,13 @@
 //  4. Queries without a certificate (adversarial data, k > KP clusters, NaNs) are re-run through the exact
 //     scan by rg_knn_topk_tc; their number is returned.  For unit-norm N(0,1) data none fail.
 //
-// Roofline: tensor pipe.  Operand traffic per item tile is (256+256)*768*2 B = 768 KB from L2 per
-// 100.7 MFLOP, so the L2->SM feed (~42 B/clk/SM with all SMs pulling) bounds the kernel near 2/3 of the
-// bf16 peak; DRAM sees the bf16 shard about once (concurrent CTAs share database tiles through L2).
+// Work decomposition: ONE wave of items (q_tiles x chunks ~ 148), so a list sees a long chunk (a running top-KP
+// costs ~KP*ln(rows/KP) replacements) and the CTAs running together are the q_tiles tiles of the same few chunks:
+// a database tile comes from DRAM once (ncu: 1.544 GB read for the 1.536 GB shard, L2 hit 95 %).
+// Roofline: tensor pipe.  Operands are 768 KB from L2 per 100.7 MFLOP tile; the accumulators are single-buffered
+// (two of them fill TMEM), so the epilogue serialises with the MMAs and its length decides the rest: with the
+// branch-per-4-scores test and the FMNMX-tree list update the kernel runs at 1277 TF/s = 92 % of the measured
+// sustained bf16 peak (4096 x 1M x 768 in 4.93 ms).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <math.h>
