@@ -92,10 +92,12 @@ class KnnIndex:
         _lib.require_cuda(queries)
         if self.handle is None:
             raise RuntimeError("KnnIndex: already closed")
+        if queries.dim() != 2 or queries.shape[1] != self.db.shape[1]:
+            raise ValueError(f"KnnIndex.topk: queries must be [Q, {self.db.shape[1]}]")
+        queries = queries.to(torch.float32).contiguous()
         q = queries.shape[0]
         if q <= self.min_queries:
             return _cuda_local_topk(self.db, queries, k, idx_base)
-        queries = queries.contiguous()
         idx = torch.empty(q, k, dtype=torch.int64, device=queries.device)
         sc = torch.empty(q, k, device=queries.device)
         nf = ctypes.c_int32(0)
