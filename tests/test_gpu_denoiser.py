@@ -96,13 +96,17 @@ def test_denoiser_module_path_matches_fused(model, dev):
     assert rel_l2(out_m, out_f) < 2e-5
 
 
-def test_normal_scale_row_groups(golden, dev):
-    """Cross-attention values at ordinary scale: rows 20/30 get y - 1e6 rounded to a 1/16 grid
-    (efficient_attention.py:98), a discontinuous function; every other row group must still agree."""
+@pytest.mark.parametrize("tier", ["fp32", "bf16x3", "bf16"])
+def test_normal_scale_row_groups(tier, golden, dev):
+    """Cross-attention values at ordinary scale (the regime of a trained checkpoint): rows 20/30 get
+    y - 1e6 rounded to a 1/16 grid (efficient_attention.py:98), a discontinuous function; every other
+    row group must still agree.  Rows 20/30 and the other rows are reported separately per tier."""
+    from rag_gesture_b200 import _lib as L
     from rag_gesture_b200 import mogen_api as M
+    prec = {"fp32": L.PREC_FP32, "bf16x3": L.PREC_BF16X3, "bf16": L.PREC_BF16}[tier]
     g = golden("denoiser_step_normal_scale")
     sd = S.synthetic_state_dict(1, normal_scale=True)
-    m = M.build_submodule(C.denoiser_cfg(), database=None, use_retrieval_for_test=False)
+    m = M.build_submodule(dict(C.denoiser_cfg(), precision=prec), database=None, use_retrieval_for_test=False)
     m.load_state_dict(sd, strict=False)
     m = m.to(dev).eval()
     B = 2
@@ -112,12 +116,13 @@ def test_normal_scale_row_groups(golden, dev):
         out = m(x, torch.full((B,), 514, device=dev), **kw).cpu()
     ref = torch.from_numpy(g["x0_t514"])
     rows = [r for r in range(C.N_TOKENS) if r not in (20, 30)]
-    print("normal-scale rel-L2: other rows %.3g, rows 20/30 %.3g" % (
-        rel_l2(out[:, rows], ref[:, rows]), rel_l2(out[:, [20, 30]], ref[:, [20, 30]])))
-    # measured on B200: 1.0e-2 / 4.8e-2 -- a handful of 1/16-grid roundings flip between any two
-    # fp32 implementations (also CPU vs GPU runs of the reference itself); see DESIGN.md
-    assert rel_l2(out[:, rows], ref[:, rows]) < 5e-2
-    assert rel_l2(out, ref) < 2e-1
+    e_other, e_2030 = rel_l2(out[:, rows], ref[:, rows]), rel_l2(out[:, [20, 30]], ref[:, [20, 30]])
+    print("normal-scale (%s tier) rel-L2: other rows %.3g, rows 20/30 %.3g" % (tier, e_other, e_2030))
+    # measured on B200 (fp32 tier): 1.0e-2 / 4.8e-2 -- a handful of 1/16-grid roundings flip between any two
+    # fp32 implementations (also CPU vs GPU runs of the reference itself); see DESIGN.md.  The bf16 tier rounds
+    # the GEMM operands to 2^-9, which moves more elements across a grid line: its bound is wider.
+    assert e_other < (1e-1 if tier == "bf16" else 5e-2)
+    assert rel_l2(out, ref) < (3e-1 if tier == "bf16" else 2e-1)
 
 
 def test_plain_ddim_loop_config1(model, diffusion, golden, dev):
@@ -165,7 +170,9 @@ def test_reverse_loop_batched_equals_single(model, diffusion, dev):
     assert torch.equal(all3[1:2], single)
 
 
-def test_guided_loop_and_dead_guidance(model, diffusion, golden, dev):
+def _guided_loop_check(model, diffusion, golden, dev, tol_loop, tier):
+    """Guided loop with insertion guidance (gaussian_diffusion.py:1233-1395) and the long-form
+    prev-latent blend vs the unmodified reference's golden trajectory, for one precision tier."""
     gg = golden("ddim_guided_b2")
     inv, kw1 = _inverted(model, diffusion, dev)
     B, T, D, n = 2, C.N_TOKENS, C.LATENT_DIM, C.N_CHUNKS
@@ -187,8 +194,8 @@ def test_guided_loop_and_dead_guidance(model, diffusion, golden, dev):
     diffusion.noise_fn, diffusion.skip_dead_guidance = None, True
     assert torch.equal(finals[0], finals[1])            # executing the gradient steps changes nothing
     err = rel_l2(finals[0], torch.from_numpy(gg["final"]))
-    print(f"guided loop (fp32 tier) rel-L2 vs reference: {err:.3g}")
-    assert err < TOL_LOOP
+    print(f"guided loop ({tier} tier) rel-L2 vs reference: {err:.3g}")
+    assert err < tol_loop
 
     # long-form mode: prev_latent blended on every step of the plain loop
     prev = torch.zeros(1, T, D)
@@ -198,7 +205,13 @@ def test_guided_loop_and_dead_guidance(model, diffusion, golden, dev):
     fp = diffusion.ddim_sample_loop(model, (1, T, D), clip_denoised=False, model_kwargs=kw1, eta=0,
                                     in_seq=prev.to(dev)).cpu()
     diffusion.noise_fn = None
-    assert rel_l2(fp, torch.from_numpy(gg["final_prev_latent_b1"])) < TOL_LOOP
+    err_p = rel_l2(fp, torch.from_numpy(gg["final_prev_latent_b1"]))
+    print(f"prev-latent loop ({tier} tier) rel-L2 vs reference: {err_p:.3g}")
+    assert err_p < tol_loop
+
+
+def test_guided_loop_and_dead_guidance(model, diffusion, golden, dev):
+    _guided_loop_check(model, diffusion, golden, dev, TOL_LOOP, "fp32")
 
 
 def test_batch_sizes_and_ragged(model, diffusion, dev):
@@ -261,6 +274,39 @@ def test_tc_loops_vs_golden(tc_model, diffusion, golden, dev):
     err_r = rel_l2(inv.cpu(), torch.from_numpy(gr["inv49"]))
     print(f"precision {model.precision}: plain loop rel-L2 {err:.3g}, reverse loop {err_r:.3g}")
     assert err < tol_loop and err_r < tol_loop
+
+
+def test_tc_guided_loop_vs_golden(tc_model, diffusion, golden, dev):
+    """The guided loop (insertion guidance, dead gradient steps) and the prev-latent loop on the tensor-core
+    tiers against the reference's golden trajectory: bf16x3 <= 1e-3, bf16 <= 2e-2 (north_star)."""
+    model, _, tol_loop = tc_model
+    _guided_loop_check(model, diffusion, golden, dev, tol_loop, {2: "bf16x3", 1: "bf16"}.get(model.precision, "tc"))
+
+
+def test_tc_bench_shape_groups_vs_oracle(tc_model, diffusion, dev):
+    """The benched shape: B = 64 clips at guided level i together with E = 96 exemplars at inversion level j
+    through rg_denoise_groups (one kernel chain, M = 6880 rows: the persistent 2-CTA GEMM path), a sample of
+    clips from both groups against the CPU oracle (reference algorithm as written, fp32)."""
+    from oracle import denoiser as OD
+    model, tol_step, _ = tc_model
+    eng = model.rg_engine(diffusion)
+    B, E = 64, 96
+    cond = S.synthetic_conditions(B + E, seed=101)
+    kw = _kw(model, cond, B + E, dev)
+    prep = model.prepare_batch(kw, B + E)
+    x = S.synthetic_latents(B + E, seed=102).to(dev)
+    li, lj = 37, 12
+    out = eng.denoise_groups(x, prep.src_mask, prep.query_mask, prep.state, [(B, li), (E, lj)]).cpu()
+    sd = {k: v.cpu() for k, v in model.state_dict().items()}
+    tmap = diffusion.timestep_map
+    for b in (0, 63, 64, 131, 159):
+        sub = {k: v[b:b + 1] for k, v in cond.items()}
+        xf = OD.encode_conditions(sd, sub["word"], sub["audio"], sub["speaker_ids"])
+        tau = int(tmap[li if b < B else lj])
+        ref = OD.denoiser_forward(sd, x[b:b + 1].cpu(), torch.full((1,), tau), S.motion_mask(1), xf, S.query_masks(1))
+        err = rel_l2(out[b:b + 1], ref)
+        print(f"precision {model.precision} bench shape clip {b} (tau {tau}): rel-L2 {err:.3g}")
+        assert err < tol_step, (b, err)
 
 
 def test_tc_batch_independence(tc_model, dev):

@@ -217,8 +217,7 @@ def _cpu_noise(shape, device):
     return torch.randn(*shape).to(device)     # global CPU generator, like the reference run
 
 
-def test_full_guided_batch_vs_reference(arch, dev):
-    """configs[1] in miniature: B=3, discourse retrieval, batched inversion, insertion guidance."""
+def _full_guided_batch(arch, dev, tol, tier):
     g = np.load(os.path.join(GOLDEN, "pipeline_b3.npz"))
     qs = S.SyntheticGestureDataset(N_QUERY, seed=8)
     batch = S.collate([qs[i] for i in [1, 2, 4]])
@@ -226,6 +225,9 @@ def test_full_guided_batch_vs_reference(arch, dev):
     batch["inference_kwargs"] = dict(use_inversion=True, outpaint=False, inversion_start_time=-1,
                                      insertion_guidance=True, guidance_iters=[0] * 25 + list(range(25)),
                                      guidance_lr=0.1)
+    db = arch.model.database
+    for d in (db.test_indexes, db.test_dbounds, db.test_qbounds):
+        d.clear()
     arch.diffusion_test.noise_fn = _cpu_noise
     torch.manual_seed(2024)
     res = arch(**batch)
@@ -234,14 +236,17 @@ def test_full_guided_batch_vs_reference(arch, dev):
     errs = (rel_l2(res["prev_latentout"].cpu(), torch.from_numpy(g["prev_latentout"])),
             rel_l2(res["pred_upper"][:, ::10].cpu(), torch.from_numpy(g["pred_upper"])),
             rel_l2(res["pred_hands"][:, ::10].cpu(), torch.from_numpy(g["pred_hands"])))
-    print("full guided batch (fp32 tier) rel-L2 vs reference: latents %.3g, upper %.3g, hands %.3g" % errs)
-    assert max(errs) < 1e-3          # north_star fp32 tier
+    print("full guided batch (%s tier) rel-L2 vs reference: latents %.3g, upper %.3g, hands %.3g" % ((tier,) + errs))
+    assert max(errs) < tol
     assert tuple(res["pred_lower"].shape) == (3, 150, 27) and tuple(res["pred_exps"].shape) == (3, 150, 100)
 
 
-def test_longform_prev_latent_chain(arch, dev):
+def _prev_latent_chain(arch, dev, tol, tier):
     g = np.load(os.path.join(GOLDEN, "pipeline_b3.npz"))
     qs = S.SyntheticGestureDataset(N_QUERY, seed=8)
+    db = arch.model.database
+    for d in (db.test_indexes, db.test_dbounds, db.test_qbounds):
+        d.clear()
     arch.diffusion_test.noise_fn = _cpu_noise
     prev = None
     torch.manual_seed(77)
@@ -255,8 +260,45 @@ def test_longform_prev_latent_chain(arch, dev):
         prev = arch(**bw)["prev_latentout"]
         outs.append(prev.cpu())
     errs = (rel_l2(outs[0], torch.from_numpy(g["chain_w0"])), rel_l2(outs[1], torch.from_numpy(g["chain_w1"])))
-    print("prev-latent chain (fp32 tier) rel-L2 vs reference: window 0 %.3g, window 1 %.3g" % errs)
-    assert max(errs) < 1e-3
+    print("prev-latent chain (%s tier) rel-L2 vs reference: window 0 %.3g, window 1 %.3g" % ((tier,) + errs))
+    assert max(errs) < tol
+
+
+def test_full_guided_batch_vs_reference(arch, dev):
+    """configs[1] in miniature: B=3, discourse retrieval, batched inversion, insertion guidance."""
+    _full_guided_batch(arch, dev, 1e-3, "fp32")          # north_star fp32 tier
+
+
+def test_longform_prev_latent_chain(arch, dev):
+    _prev_latent_chain(arch, dev, 1e-3, "fp32")
+
+
+@pytest.fixture(scope="module", params=[("bf16x3", 1e-3), ("bf16", 2e-2)], ids=["bf16x3", "bf16"])
+def arch_tc(request, dev):
+    """The same architecture on the tensor-core tiers (tcgen05 GEMMs): bf16x3 is held to the fp32 tier's
+    tolerance, bf16 (what bench.py runs) to north_star's 2e-2."""
+    import rag_gesture_b200 as R
+    from rag_gesture_b200 import _lib as L
+    tier, tol = request.param
+    cfg = C.model_cfg()
+    cfg["use_retrieval_for_test"] = True
+    cfg["model"]["precision"] = {"bf16x3": L.PREC_BF16X3, "bf16": L.PREC_BF16}[tier]
+    m = R.build_architecture(cfg, database=S.SyntheticGestureDataset(N_DB, seed=7))
+    missing, unexpected = m.model.load_state_dict(S.synthetic_state_dict(0), strict=False)
+    assert not unexpected
+    return m.to(dev).eval(), tol, tier
+
+
+def test_tc_full_guided_batch_vs_reference(arch_tc, dev):
+    """The whole guided batch (retrieval, batched inversion, insertion guidance, decode) on the tensor-core
+    tiers against the unmodified reference's golden outputs."""
+    m, tol, tier = arch_tc
+    _full_guided_batch(m, dev, tol, tier)
+
+
+def test_tc_longform_prev_latent_chain(arch_tc, dev):
+    m, tol, tier = arch_tc
+    _prev_latent_chain(m, dev, tol, tier)
 
 
 def test_resident_corpus_matches_host_fetch(arch, dev):
