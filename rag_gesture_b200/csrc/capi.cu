@@ -75,6 +75,8 @@ struct Ws {                  // one lane's activation workspace (rows = clips * 
     float *h, *a, *big, *o3, *g, *y;
     void *x16, *a16, *a16x, *h16, *g16;
     CUtensorMap tm_x16, tm_a16, tm_a16x, tm_h16, tm_g16;
+    // TMA-store maps of the GEMM outputs (2-CTA persistent kernel, gemm2_tc.cu)
+    CUtensorMap ts_h, ts_big, ts_y, ts_h16, ts_a16x, ts_g16;
 };
 
 struct rg_model {
@@ -468,6 +470,12 @@ static int ensure_ws(rg_model* m, Ws& w, long long rows) {
             CU(cudaMemset(*b16[i], 0, (size_t)rows * width[i] * P * 2));
             CU(rg_make_tensor_map(tms[i], *b16[i], rows, (long long)width[i] * P, (long long)width[i] * P, 128));
         }
+        CU(rg_make_store_map(&w.ts_h, w.h, rows, D, D, 4));
+        CU(rg_make_store_map(&w.ts_big, w.big, rows, 3 * D, 3 * D, 4));
+        CU(rg_make_store_map(&w.ts_y, w.y, rows, D, D, 4));
+        CU(rg_make_store_map(&w.ts_h16, w.h16, rows, (long long)D * P, (long long)D * P, 2));
+        CU(rg_make_store_map(&w.ts_a16x, w.a16x, rows, (long long)4 * D * P, (long long)4 * D * P, 2));
+        CU(rg_make_store_map(&w.ts_g16, w.g16, rows, (long long)F * P, (long long)F * P, 2));
         // the memsets run on the legacy stream, which non-blocking lane streams do not wait for
         CU(cudaDeviceSynchronize());
     }
@@ -477,6 +485,7 @@ static int ensure_ws(rg_model* m, Ws& w, long long rows) {
 
 static int tc_gemm(rg_model* m, const CUtensorMap& tmA, int a_w, const W16& w, const float* bias, int M, int N,
                    int K, int epi, const float* R, float* C32, int ldc32, void* C16, int c16_w, cudaStream_t st,
+                   const CUtensorMap* s32 = nullptr, const CUtensorMap* s16 = nullptr,
                    int groups = 1, int a_goff = 0, int w_goff = 0, int bc_goff = 0);
 
 extern "C" int64_t rg_state_floats_per_clip(rg_handle m) {
@@ -552,7 +561,7 @@ extern "C" int rg_precompute_clip_state(rg_handle m, const float* xf_text, const
 // one tcgen05 GEMM: A (bf16 planes, tensor map tmA, plane width a_w) x W16 -> fp32 and/or bf16 planes
 static int tc_gemm(rg_model* m, const CUtensorMap& tmA, int a_w, const W16& w, const float* bias, int M, int N,
                    int K, int epi, const float* R, float* C32, int ldc32, void* C16, int c16_w, cudaStream_t st,
-                   int groups, int a_goff, int w_goff, int bc_goff) {
+                   const CUtensorMap* s32, const CUtensorMap* s16, int groups, int a_goff, int w_goff, int bc_goff) {
     RgGemmTc p;
     memset(&p, 0, sizeof(p));
     p.M = M; p.N = N; p.K = K; p.split = m->planes == 2; p.a_lo_off = a_w; p.w_lo_off = w.K;
@@ -560,6 +569,7 @@ static int tc_gemm(rg_model* m, const CUtensorMap& tmA, int a_w, const W16& w, c
     p.bias = bias; p.R = R; p.ldr = RG_D; p.pos = m->pos; p.pos_T = m->cfg.n_tokens;
     p.C32 = C32; p.ldc32 = ldc32; p.C16_ = C16; p.ldc16 = c16_w * m->planes;
     p.c16_lo_off = m->planes == 2 ? c16_w : 0; p.epi = epi;
+    p.tmC32 = s32; p.tmC16 = s16;
     LAUNCH(rg_launch_gemm_tc(tmA, w.tm, p, st));
     return 0;
 }
@@ -578,14 +588,14 @@ static int denoise_tc(rg_model* m, Ws& w, const float* x, int B, const float* ss
     // shapes and epilogues, without the attention / row kernels between them (their inputs are then stale data)
     const bool all = !m->gemm_only;
     if (all) LAUNCH(rg_launch_split_bf16(x, D, w.x16, D * P, lo ? D : 0, M, D, st));
-    if (tc_gemm(m, w.tm_x16, D, m->tc_joint, m->b_joint, M, D, D, RG_EPI_BIAS_POS, nullptr, w.h, D, nullptr, 0, st)) return 1;
+    if (tc_gemm(m, w.tm_x16, D, m->tc_joint, m->b_joint, M, D, D, RG_EPI_BIAS_POS, nullptr, w.h, D, nullptr, 0, st, &w.ts_h)) return 1;
     for (int l = 0; l < L; ++l) {
         const Layer& ly = m->layers[l];
         const LayerTc& t = m->tc[l];
         const float* ss = ssrow + (long long)l * 5 * 2 * D;
         // --- self-attention
         if (all) LAUNCH(rg_launch_ln_rows(w.h, D, nullptr, nullptr, rg_out_b16(w.a16, D * P, lo ? D : 0), M, st));
-        if (tc_gemm(m, w.tm_a16, D, t.qkv, ly.bqkv, M, 3 * D, D, RG_EPI_BIAS, nullptr, w.big, 3 * D, nullptr, 0, st)) return 1;
+        if (tc_gemm(m, w.tm_a16, D, t.qkv, ly.bqkv, M, 3 * D, D, RG_EPI_BIAS, nullptr, w.big, 3 * D, nullptr, 0, st, &w.ts_big)) return 1;
         RgStylParams sp = {ly.sa_g, ly.sa_b, ss, ss_stride};
         // mma.sync core + Stylization prologue in one kernel (one CTA per clip): measured faster than core +
         // row kernel for the single-pass TF32 cores up to ~128 clips; the 3xTF32 variant is register-bound
@@ -605,11 +615,12 @@ static int denoise_tc(rg_model* m, Ws& w, const float* x, int B, const float* ss
             p.bias = ly.sa_bo; p.R = w.h; p.ldr = D; p.C32 = w.h; p.ldc32 = D;
             p.C16_ = reinterpret_cast<__nv_bfloat16*>(w.a16x) + 3 * D; p.ldc16 = 4 * D * P; p.c16_lo_off = lo ? 4 * D : 0;
             p.epi = RG_EPI_BIAS_RESIDUAL;
+            p.tmC32 = &w.ts_h; p.tmC16 = &w.ts_a16x; p.c16_col0 = 3 * D;
             LAUNCH(rg_launch_gemm_tc(w.tm_a16, t.sa_o.tm, p, st));
         }
         // --- three cross-attentions on the same h, their projections and ca_mix folded into one GEMM
         if (all) LAUNCH(rg_launch_ln_rows(w.h, D, nullptr, nullptr, rg_out_b16(w.a16, D * P, lo ? D : 0), M, st));
-        if (tc_gemm(m, w.tm_a16, D, t.caq, ly.bcaq, M, 3 * D, D, RG_EPI_BIAS, nullptr, w.big, 3 * D, nullptr, 0, st)) return 1;
+        if (tc_gemm(m, w.tm_a16, D, t.caq, ly.bcaq, M, 3 * D, D, RG_EPI_BIAS, nullptr, w.big, 3 * D, nullptr, 0, st, &w.ts_big)) return 1;
         RgStylParams sp3[3];
         for (int c = 0; c < 3; ++c) sp3[c] = {ly.ca_g + c * D, ly.ca_b + c * D, ss + (1 + c) * 2 * D, ss_stride};
         if (!all) {
@@ -621,15 +632,20 @@ static int denoise_tc(rg_model* m, Ws& w, const float* x, int B, const float* ss
                                      qm_cond_stride, w.o3, 3 * D, B, T, m->attn_mode_ca, st));
             LAUNCH(rg_launch_styl_rows3(w.o3, 3 * D, sp3, T, rg_out_b16(w.a16x, 4 * D * P, lo ? 4 * D : 0), M, st));
         }
-        if (tc_gemm(m, w.tm_a16x, 4 * D, t.fold, t.b_fold, M, D, 4 * D, RG_EPI_BIAS, nullptr, w.h, D, w.h16, D, st)) return 1;
+        if (tc_gemm(m, w.tm_a16x, 4 * D, t.fold, t.b_fold, M, D, 4 * D, RG_EPI_BIAS, nullptr, w.h, D, w.h16, D, st, &w.ts_h, &w.ts_h16)) return 1;
         // --- FFN
-        if (tc_gemm(m, w.tm_h16, D, t.w1, ly.b1, M, F, D, RG_EPI_BIAS_GELU, nullptr, nullptr, 0, w.g16, F, st)) return 1;
-        if (tc_gemm(m, w.tm_g16, F, t.w2, ly.b2, M, D, F, RG_EPI_BIAS, nullptr, w.y, D, nullptr, 0, st)) return 1;
+        if (tc_gemm(m, w.tm_h16, D, t.w1, ly.b1, M, F, D, RG_EPI_BIAS_GELU, nullptr, nullptr, 0, w.g16, F, st, nullptr, &w.ts_g16)) return 1;
+        if (tc_gemm(m, w.tm_g16, F, t.w2, ly.b2, M, D, F, RG_EPI_BIAS, nullptr, w.y, D, nullptr, 0, st, &w.ts_y)) return 1;
         RgStylParams spf = {ly.ffn_g, ly.ffn_b, ss + 4 * 2 * D, ss_stride};
         if (all) LAUNCH(rg_launch_styl_rows(w.y, D, spf, T, rg_out_b16(w.a16, D * P, lo ? D : 0), M, st));
-        if (tc_gemm(m, w.tm_a16, D, t.ffn_o, ly.ffn_bo, M, D, D, RG_EPI_BIAS_RESIDUAL, w.h, w.h, D, w.h16, D, st)) return 1;
+        if (tc_gemm(m, w.tm_a16, D, t.ffn_o, ly.ffn_bo, M, D, D, RG_EPI_BIAS_RESIDUAL, w.h, w.h, D, w.h16, D, st, &w.ts_h, &w.ts_h16)) return 1;
     }
-    return tc_gemm(m, w.tm_h16, D, m->tc_out, m->b_out, M, D, D, RG_EPI_BIAS, nullptr, x0_out, D, nullptr, 0, st);
+    // x0_out is the caller's buffer: its store map is built per call (host-side encode, no device work)
+    CUtensorMap ts_out;
+    const bool out_map = (reinterpret_cast<uintptr_t>(x0_out) & 15) == 0;
+    if (out_map) CU(rg_make_store_map(&ts_out, x0_out, M, D, D, 4));
+    return tc_gemm(m, w.tm_h16, D, m->tc_out, m->b_out, M, D, D, RG_EPI_BIAS, nullptr, x0_out, D, nullptr, 0, st,
+                   out_map ? &ts_out : nullptr);
 }
 
 // rg_denoise, fp32 SIMT tier (RG_PREC_FP32): one lane's clips.
@@ -917,6 +933,12 @@ extern "C" int rg_op_linear_tc(const float* x, const float* W, const float* b, c
     p.bias = b; p.R = residual; p.ldr = N; p.C32 = out; p.ldc32 = N;
     p.C16_ = out_bf16; p.ldc16 = N * planes; p.c16_lo_off = split ? N : 0; p.epi = epi;
     p.no_pdl = 1;       // W planes were written by the split kernel just above
+    CUtensorMap ts32, ts16;
+    if (out && (reinterpret_cast<uintptr_t>(out) & 15) == 0) { CU(rg_make_store_map(&ts32, out, M, N, N, 4)); p.tmC32 = &ts32; }
+    if (out_bf16 && (reinterpret_cast<uintptr_t>(out_bf16) & 15) == 0) {
+        CU(rg_make_store_map(&ts16, out_bf16, M, (long long)N * planes, (long long)N * planes, 2));
+        p.tmC16 = &ts16;
+    }
     LAUNCH(rg_launch_gemm_tc(tmA, tmW, p, st));
     CU(cudaFreeAsync(a16, st));
     CU(cudaFreeAsync(w16, st));
@@ -958,6 +980,12 @@ extern "C" int rg_probe_gemm_tc(const float* x, const float* W, const float* b, 
     *median_ms = ts[ts.size() / 2];
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaFree(a16); cudaFree(w16);
+    return 0;
+}
+extern "C" int rg_set_gemm_kernel(int mode, int min_rows) {
+    if (mode < 0 || mode > 2) return rg_fail("rg_set_gemm_kernel: mode must be 0 (auto), 1 (128x128 tiles) or 2 (2-CTA persistent)");
+    rg_gemm_kernel_mode = mode;
+    if (min_rows > 0) rg_gemm2_min_rows = min_rows;
     return 0;
 }
 extern "C" int rg_probe_gemm_only(rg_handle m, int on) {

@@ -1,0 +1,416 @@
+// Persistent 2-CTA tcgen05 GEMM  C[M,N] = A[M,K] * W[N,K]^T (+ epilogue)  for the denoiser's large-M launches
+// (the fused guided+inversion level: M = (B + E) * 43 = 6880 rows).
+//
+// Why a second kernel: with 128x128 tiles (gemm_tc.cu) every tile pulls 64 flop per operand byte out of L2, and at
+// ~42 B/clk/SM of L2->SM bandwidth (6.3 KB/clk chip-wide) the K = 512 GEMMs of a denoiser layer are bound by that,
+// not by the tensor pipe.  Here a CTA PAIR (cluster of 2, tcgen05.mma.cta_group::2) owns a 256 x 256
+// output tile: each CTA stages its own 128 rows of A and HALF of the 256 weight rows per K-block, the pair's
+// UMMA 256x256x16 reads both halves -> 128 flop per operand byte (half the L2 traffic per flop), and the weight
+// tile is fetched once per 256 rows instead of once per 128.
+//
+//   * persistent: grid = 2 * min(tiles, resident pairs); each pair walks tiles t = pair, pair + n_pairs, ...
+//   * TMEM: all 512 columns = 2 accumulator stages of 256 fp32 columns, so the epilogue of tile i overlaps the
+//     main loop of tile i + 1 (tmem_full / tmem_empty mbarriers; the peer CTA's epilogue warps arrive remotely
+//     on the leader's tmem_empty barrier);
+//   * operands: cp.async.bulk.tensor.2d.cta_group::2 (TMA, 128-byte swizzle) into a 4-stage (3 in split mode)
+//     ring of 32 KB per CTA; both CTAs' loads complete on the LEADER's full barrier (2 x 32 KB expected), the
+//     leader's single MMA thread issues for the pair and tcgen05.commit multicasts slot-free / accumulator-ready
+//     to both CTAs;
+//   * epilogue (8 warps per CTA; two warps share a TMEM lane group and split the columns): tcgen05.ld 64 columns ->
+//     bias / residual / positional / GELU in registers -> 128B-swizzled staging tiles in shared memory ->
+//     TMA STORE (cp.async.bulk.tensor.2d.global.shared::cta, SASS UTMASTG) of fp32 and/or bf16 (hi | lo) tiles:
+//     no per-thread global stores, row clipping by the tensor map;
+//   * under PDL the weight tiles of the first stages are requested before griddepcontrol.wait (as gemm_tc.cu).
+//
+// "split" (RG_PREC_BF16X3): three passes A_hi*W_hi + A_lo*W_hi + A_hi*W_lo into the same accumulator.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#include "rg_common.cuh"
+#include "rg_gemm_tc.h"
+#include "rg_tcgen05.cuh"
+
+namespace {
+
+using namespace rg_tc;
+
+constexpr int BM = 128;             // rows per CTA (256 per pair)
+constexpr int BN = 256;             // columns per pair tile; each CTA stages BN/2 weight rows
+constexpr int BK = 64;
+constexpr int EPI_WARPS = 8;
+constexpr int THREADS = 64 + 32 * EPI_WARPS;
+constexpr int A_BYTES = BM * BK * 2, B_BYTES = (BN / 2) * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// bounded wait: a protocol error traps instead of hanging the device
+__device__ __forceinline__ void mbar_wait_g(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0, spins = 0;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (!ok && ++spins > (1u << 24)) __trap();
+    } while (!ok);
+}
+// TMA load issued by either CTA of the pair; completes on the mbarrier at cluster address `bar` (the leader's)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+// arrives (once the MMAs issued so far have retired) on the barrier at the same offset in both CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+template <int SPLIT, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                const __grid_constant__ CUtensorMap tmC32, const __grid_constant__ CUtensorMap tmC16, RgGemmTc p) {
+    constexpr int STAGES = SPLIT ? 3 : 4;
+    constexpr int EPI_BYTES = SPLIT ? 16384 : 12288;        // per epilogue warp: 2 fp32 + bf16 hi (+ lo) tiles of 4 KB
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar[2], tmem_empty_bar[2];
+    __shared__ uint32_t tmem_base_smem;
+
+    rg_pdl_launch();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const int tiles_n = p.N / BN, tiles_m = (p.M + 2 * BM - 1) / (2 * BM), total = tiles_m * tiles_n;
+    const int nkb = p.K / BK;
+    const int total_kb = SPLIT ? 3 * nkb : nkb;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmC32)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmC16)) : "memory");
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+            for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(&tmem_full_bar[a]), 1); mbar_init(smem_u32(&tmem_empty_bar[a]), 2 * EPI_WARPS); }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();                                 // barrier inits + TMEM visible to both CTAs of the pair
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs): own 128 rows of A, own half of the 256 weight rows =====
+        if (elect_one()) {
+            auto coords = [&](int j, int& ka, int& kw) {
+                const int pass = SPLIT ? j / nkb : 0, kb = j - pass * nkb;      // pass 0: hi*hi, 1: lo*hi, 2: hi*lo
+                ka = (pass == 1 ? p.a_lo_off : 0) + kb * BK;
+                kw = (pass == 2 ? p.w_lo_off : 0) + kb * BK;
+            };
+            uint32_t full_leader[STAGES];
+#pragma unroll
+            for (int s = 0; s < STAGES; ++s) full_leader[s] = mapa_u32(smem_u32(&full_bar[s]), 0);
+            int it = 0, j0 = 0;
+            if (pair < total) {
+                // weights do not depend on the previous kernel: request the first tiles before the PDL wait
+                const int w_row = (pair % tiles_n) * BN + (int)rank * (BN / 2), a_row = (pair / tiles_n) * 2 * BM + (int)rank * BM;
+                const int pre = total_kb < STAGES ? total_kb : STAGES;
+                for (int j = 0; j < pre; ++j) {
+                    int ka, kw;
+                    coords(j, ka, kw);
+                    if (rank == 0) mbar_expect_tx(smem_u32(&full_bar[j]), 2 * STAGE_BYTES);
+                    tma_load_2d_pair(smem_u32(smem + j * STAGE_BYTES) + A_BYTES, &tmW, full_leader[j], kw, w_row);
+                }
+                rg_pdl_wait();
+                for (int j = 0; j < pre; ++j) {
+                    int ka, kw;
+                    coords(j, ka, kw);
+                    tma_load_2d_pair(smem_u32(smem + j * STAGE_BYTES), &tmA, full_leader[j], ka, a_row);
+                }
+                it = pre; j0 = pre;
+            } else {
+                rg_pdl_wait();
+            }
+            for (int t = pair; t < total; t += n_pairs) {
+                const int w_row = (t % tiles_n) * BN + (int)rank * (BN / 2), a_row = (t / tiles_n) * 2 * BM + (int)rank * BM;
+                for (int j = j0; j < total_kb; ++j, ++it) {
+                    const int s = it % STAGES, ph = (it / STAGES) & 1;
+                    mbar_wait_g(smem_u32(&empty_bar[s]), ph ^ 1);
+                    int ka, kw;
+                    coords(j, ka, kw);
+                    const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+                    if (rank == 0) mbar_expect_tx(smem_u32(&full_bar[s]), 2 * STAGE_BYTES);
+                    tma_load_2d_pair(sa, &tmA, full_leader[s], ka, a_row);
+                    tma_load_2d_pair(sa + A_BYTES, &tmW, full_leader[s], kw, w_row);
+                }
+                j0 = 0;
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: one thread of the leader CTA issues for the pair =====
+        if (rank == 0) {
+            const uint32_t idesc = make_idesc(2 * BM, BN);
+            int it = 0, tl = 0;
+            for (int t = pair; t < total; t += n_pairs, ++tl) {
+                const int acc = tl & 1, aph = (tl >> 1) & 1;
+                mbar_wait_g(smem_u32(&tmem_empty_bar[acc]), aph ^ 1);      // both CTAs' epilogues drained this stage
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int j = 0; j < total_kb; ++j, ++it) {
+                    const int s = it % STAGES, ph = (it / STAGES) & 1;
+                    mbar_wait_g(smem_u32(&full_bar[s]), ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (elect_one()) {
+                        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
+                        const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sb);
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k)
+                            umma_bf16_pair(d_tmem, da + (k * UMMA_K * 2 >> 4), db + (k * UMMA_K * 2 >> 4), idesc, (j | k) != 0);
+                        umma_commit_pair(smem_u32(&empty_bar[s]));
+                        if (j == total_kb - 1) umma_commit_pair(smem_u32(&tmem_full_bar[acc]));
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else {
+        // ===== epilogue (8 warps per CTA) =====
+        rg_pdl_wait();                                  // residual reads / stores touch the previous kernel's buffers
+        const int ew = warp - 2, lg = warp & 3, half = ew >> 2;
+        const uint32_t stg = smem_u32(smem + STAGES * STAGE_BYTES + ew * EPI_BYTES);
+        const uint32_t s_f0 = stg, s_f1 = stg + 4096, s_h = stg + 8192, s_l = stg + 12288;
+        const uint32_t row_off = lane * 128, sw = lane & 7;
+        const uint32_t tmem_empty_leader[2] = {mapa_u32(smem_u32(&tmem_empty_bar[0]), 0), mapa_u32(smem_u32(&tmem_empty_bar[1]), 0)};
+        const bool has32 = p.C32 != nullptr, has16 = p.C16_ != nullptr, lo16 = SPLIT && p.c16_lo_off != 0;
+        int tl = 0;
+        for (int t = pair; t < total; t += n_pairs, ++tl) {
+            const int acc = tl & 1, aph = (tl >> 1) & 1;
+            const int m0 = (t / tiles_n) * 2 * BM + (int)rank * BM, n0 = (t % tiles_n) * BN;
+            const int row = m0 + lg * 32 + lane;
+            const bool row_ok = row < p.M;
+            mbar_wait_g(smem_u32(&tmem_full_bar[acc]), aph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int itc = 0; itc < 2; ++itc) {
+                const int ncol = n0 + half * 128 + itc * 64;
+                const uint32_t ta = tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + acc * BN + half * 128 + itc * 64;
+                uint32_t v[64];
+                tmem_ld32(ta, v);
+                tmem_ld32(ta + 32, v + 32);
+                float4 rr[16];
+                if (EPI == RG_EPI_BIAS_RESIDUAL || EPI == RG_EPI_BIAS_POS) {
+                    const float* src = EPI == RG_EPI_BIAS_RESIDUAL ? p.R + (long long)row * p.ldr + ncol
+                                                                   : p.pos + (long long)(row % p.pos_T) * p.N + ncol;
+#pragma unroll
+                    for (int q = 0; q < 16; ++q)
+                        rr[q] = row_ok ? *reinterpret_cast<const float4*>(src + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (itc == 1) {                         // accumulator stage fully read by this warp: hand it back
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    if (lane == 0) mbar_arrive_remote(tmem_empty_leader[acc]);
+                }
+                // the TMA stores of the previous iteration must have finished READING the staging tiles
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncwarp();
+#pragma unroll
+                for (int qq = 0; qq < 8; ++qq) {        // 8 columns per step = one 16-byte bf16 chunk, two fp32 chunks
+                    float f[8];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int q = 2 * qq + h;
+                        const float4 bv = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + ncol + 4 * q))
+                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+                        float4 ad = bv;                 // acc + (bias + residual): the op order of gemm_tc.cu (bit-identical)
+                        if (EPI == RG_EPI_BIAS_RESIDUAL || EPI == RG_EPI_BIAS_POS) {
+                            ad.x += rr[q].x; ad.y += rr[q].y; ad.z += rr[q].z; ad.w += rr[q].w;
+                        }
+                        float4 x = make_float4(__uint_as_float(v[4 * q]) + ad.x, __uint_as_float(v[4 * q + 1]) + ad.y,
+                                               __uint_as_float(v[4 * q + 2]) + ad.z, __uint_as_float(v[4 * q + 3]) + ad.w);
+                        if (EPI == RG_EPI_BIAS_GELU) {
+                            x.x = rg_gelu_fast(x.x); x.y = rg_gelu_fast(x.y); x.z = rg_gelu_fast(x.z); x.w = rg_gelu_fast(x.w);
+                        } else if (EPI == RG_EPI_BIAS_SILU) {
+                            x.x = rg_silu(x.x); x.y = rg_silu(x.y); x.z = rg_silu(x.z); x.w = rg_silu(x.w);
+                        }
+                        f[4 * h] = x.x; f[4 * h + 1] = x.y; f[4 * h + 2] = x.z; f[4 * h + 3] = x.w;
+                        if (has32) {                    // fp32 tile: 32 columns per 128-byte row, chunk = 4 floats
+                            const uint32_t dst = (q < 8 ? s_f0 : s_f1) + row_off + ((static_cast<uint32_t>(q & 7) ^ sw) << 4);
+                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w) : "memory");
+                        }
+                    }
+                    if (has16) {                        // bf16 tile: 64 columns per 128-byte row, chunk = 8 bf16
+                        const uint32_t h0 = pack_bf16(f[0], f[1]), h1 = pack_bf16(f[2], f[3]), h2 = pack_bf16(f[4], f[5]), h3 = pack_bf16(f[6], f[7]);
+                        const uint32_t off = row_off + ((static_cast<uint32_t>(qq) ^ sw) << 4);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(s_h + off), "r"(h0), "r"(h1), "r"(h2), "r"(h3) : "memory");
+                        if (lo16) {
+                            uint32_t l[4];
+                            const uint32_t hh[4] = {h0, h1, h2, h3};
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const __nv_bfloat162 hb = *reinterpret_cast<const __nv_bfloat162*>(&hh[i]);
+                                l[i] = pack_bf16(f[2 * i] - __low2float(hb), f[2 * i + 1] - __high2float(hb));
+                            }
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(s_l + off), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
+                        }
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> visible to TMA
+                __syncwarp();
+                if (lane == 0) {
+                    const int r0 = m0 + lg * 32;
+                    if (has32) {
+                        tma_store_2d(&tmC32, s_f0, p.c32_col0 + ncol, r0);
+                        tma_store_2d(&tmC32, s_f1, p.c32_col0 + ncol + 32, r0);
+                    }
+                    if (has16) {
+                        tma_store_2d(&tmC16, s_h, p.c16_col0 + ncol, r0);
+                        if (lo16) tma_store_2d(&tmC16, s_l, p.c16_col0 + p.c16_lo_off + ncol, r0);
+                    }
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            }
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores complete before exit
+    }
+    __syncwarp();                                       // reconverge the role branches before the aligned barrier
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();                                 // nobody exits while the peer may still signal / read us
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode2 = nullptr;
+
+template <int SPLIT, int EPI>
+cudaError_t launch2(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmC32, const CUtensorMap& tmC16,
+                    const RgGemmTc& p, cudaStream_t st) {
+    constexpr int STAGES = SPLIT ? 3 : 4;
+    constexpr int EPI_BYTES = SPLIT ? 16384 : 12288;
+    constexpr size_t smem = (size_t)STAGES * STAGE_BYTES + (size_t)EPI_WARPS * EPI_BYTES + 1024;
+    auto kern = gemm2_tc_kernel<SPLIT, EPI>;
+    static int max_pairs = 0;                   // resident CTA pairs (one CTA per SM)
+    static int max_pairs_dev = -1;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (max_pairs_dev != dev) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        cudaLaunchConfig_t q = {};
+        q.gridDim = dim3(2 * 74); q.blockDim = dim3(THREADS); q.dynamicSmemBytes = smem;
+        int n = 0;
+        e = cudaOccupancyMaxActiveClusters(&n, kern, &q);
+        if (e != cudaSuccess || n < 1) { cudaGetLastError(); n = 74; }     // any grid is correct; this only sizes it
+        max_pairs = n > 74 ? 74 : n;
+        max_pairs_dev = dev;
+    }
+    const int tiles = (p.N / BN) * ((p.M + 2 * BM - 1) / (2 * BM));
+    const int pairs = tiles < max_pairs ? tiles : max_pairs;
+    const dim3 grid(2 * pairs);
+    if (p.no_pdl) {
+        kern<<<grid, THREADS, smem, st>>>(tmA, tmW, tmC32, tmC16, p);
+        return cudaGetLastError();
+    }
+    return rg_launch_pdl(kern, grid, dim3(THREADS), smem, st, tmA, tmW, tmC32, tmC16, p);
+}
+
+template <int SPLIT>
+cudaError_t launch2_epi(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& c32, const CUtensorMap& c16,
+                        const RgGemmTc& p, cudaStream_t st) {
+    switch (p.epi) {
+        case RG_EPI_BIAS: return launch2<SPLIT, RG_EPI_BIAS>(tmA, tmW, c32, c16, p, st);
+        case RG_EPI_BIAS_RESIDUAL: return launch2<SPLIT, RG_EPI_BIAS_RESIDUAL>(tmA, tmW, c32, c16, p, st);
+        case RG_EPI_BIAS_GELU: return launch2<SPLIT, RG_EPI_BIAS_GELU>(tmA, tmW, c32, c16, p, st);
+        case RG_EPI_BIAS_POS: return launch2<SPLIT, RG_EPI_BIAS_POS>(tmA, tmW, c32, c16, p, st);
+        case RG_EPI_BIAS_SILU: return launch2<SPLIT, RG_EPI_BIAS_SILU>(tmA, tmW, c32, c16, p, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace
+
+// Row-major [rows, cols] tensor with pitch ld (elements) as a TMA STORE destination of the epilogue: box = one
+// 128-byte swizzle row (32 fp32 / 64 bf16 columns) x 32 rows (one epilogue warp's TMEM lane group).
+cudaError_t rg_make_store_map(CUtensorMap* tm, const void* ptr, long long rows, long long cols, long long ld, int elem_bytes) {
+    if (!g_encode2) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+        if (e != cudaSuccess) return e;
+        if (q != cudaDriverEntryPointSuccess || !fn) return cudaErrorNotSupported;
+        g_encode2 = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    if (elem_bytes != 2 && elem_bytes != 4) return cudaErrorInvalidValue;
+    if ((ld * elem_bytes) % 16 || (reinterpret_cast<uintptr_t>(ptr) & 15)) return cudaErrorInvalidValue;
+    const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t gstr[1] = {(cuuint64_t)ld * elem_bytes};
+    const cuuint32_t box[2] = {(cuuint32_t)(128 / elem_bytes), 32};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode2(tm, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                           const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+bool rg_gemm2_eligible(const RgGemmTc& p) {
+    return p.N % BN == 0 && p.K % BK == 0 && p.groups <= 1 && !p.trace && (p.C32 || p.C16_) &&
+           (!p.C32 || p.tmC32) && (!p.C16_ || p.tmC16) && (!p.R || (p.ldr % 4 == 0)) &&
+           (p.epi != RG_EPI_BIAS_POS || (p.N % 4 == 0 && p.pos && p.pos_T > 0));
+}
+
+// tmA: box 64 x 128 rows over A; tmW: box 64 x 128 rows over W (each CTA stages half of a 256-row weight tile);
+// p.tmC32 / p.tmC16: store maps (rg_make_store_map) of the outputs in use.
+cudaError_t rg_launch_gemm2_tc(const CUtensorMap& tmA, const CUtensorMap& tmW, const RgGemmTc& p, cudaStream_t st) {
+    if (p.M <= 0 || p.N <= 0) return cudaSuccess;
+    if (!rg_gemm2_eligible(p)) return cudaErrorInvalidValue;
+    if (p.epi == RG_EPI_BIAS_RESIDUAL && !p.R) return cudaErrorInvalidValue;
+    const CUtensorMap& c32 = p.tmC32 ? *p.tmC32 : tmA;      // unused maps still need a valid descriptor
+    const CUtensorMap& c16 = p.tmC16 ? *p.tmC16 : tmA;
+    return p.split ? launch2_epi<1>(tmA, tmW, c32, c16, p, st) : launch2_epi<0>(tmA, tmW, c32, c16, p, st);
+}

@@ -305,7 +305,16 @@ static cudaError_t launch_tc_epi(const CUtensorMap& tmA, const CUtensorMap& tmW,
     return launch_tc<3, EPI>(tmA, tmW, p, grid, st);
 }
 
+int rg_gemm_kernel_mode = 0;
+int rg_gemm2_min_rows = 4096;
+
 cudaError_t rg_launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmW, const RgGemmTc& p, cudaStream_t st) {
+    if (rg_gemm_kernel_mode != 1 && rg_gemm2_eligible(p) && (rg_gemm_kernel_mode == 2 || p.M >= rg_gemm2_min_rows))
+        return rg_launch_gemm2_tc(tmA, tmW, p, st);
+    return rg_launch_gemm1_tc(tmA, tmW, p, st);
+}
+
+cudaError_t rg_launch_gemm1_tc(const CUtensorMap& tmA, const CUtensorMap& tmW, const RgGemmTc& p, cudaStream_t st) {
     if (p.M <= 0 || p.N <= 0) return cudaSuccess;
     constexpr int BN = 128;
     if (p.K % BK || p.N % BN || (p.C32 && p.ldc32 % 4) || (p.C16_ && p.ldc16 % 8) || (p.R && p.ldr % 4) ||

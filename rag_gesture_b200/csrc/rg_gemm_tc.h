@@ -18,11 +18,24 @@ struct RgGemmTc {
     int epi;                  // RgEpilogue
     int no_pdl;               // 1: W was produced by the preceding kernel -> plain (fully serialised) launch
     long long* trace;         // diagnostics: 10 clock64/globaltimer stamps per CTA (rg_probe_gemm_trace), else null
+    // 2-CTA persistent kernel (gemm2_tc.cu): TMA-store maps of the outputs in use (rg_make_store_map; host pointers,
+    // copied into the launch) and the first column of this GEMM's output inside each map
+    const CUtensorMap* tmC32; const CUtensorMap* tmC16;
+    int c32_col0, c16_col0;
 };
 
 cudaError_t rg_make_tensor_map(CUtensorMap* tm, const void* ptr, long long rows, long long cols, long long ld,
                                int box_rows);
+// Dispatch: the persistent 2-CTA kernel (gemm2_tc.cu) when the launch is eligible (store maps given, N % 256 == 0, one
+// group) and large enough (rg_gemm_kernel_mode), else the 128x128 one-tile-per-CTA kernel (gemm_tc.cu).
 cudaError_t rg_launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmW, const RgGemmTc& p, cudaStream_t st);
+cudaError_t rg_launch_gemm1_tc(const CUtensorMap& tmA, const CUtensorMap& tmW, const RgGemmTc& p, cudaStream_t st);
+cudaError_t rg_launch_gemm2_tc(const CUtensorMap& tmA, const CUtensorMap& tmW, const RgGemmTc& p, cudaStream_t st);
+bool rg_gemm2_eligible(const RgGemmTc& p);
+cudaError_t rg_make_store_map(CUtensorMap* tm, const void* ptr, long long rows, long long cols, long long ld, int elem_bytes);
+// 0: automatic (2-CTA kernel from rg_gemm2_min_rows rows on), 1: always the 128x128 kernel, 2: the 2-CTA kernel whenever eligible
+extern int rg_gemm_kernel_mode;
+extern int rg_gemm2_min_rows;
 // pdl = false: plain launch, i.e. the kernel starts only after everything enqueued before it has completed
 cudaError_t rg_launch_split_bf16(const float* x, int ldx, void* out, int ldo, int lo_off, long long rows, int cols,
                                  cudaStream_t st, bool pdl = true);

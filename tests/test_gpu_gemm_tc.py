@@ -56,3 +56,66 @@ def test_epilogues_and_outputs(dev, M, N, K):
     assert rel_l2(hi + lo, out3.cpu()) < 1e-5 and rel_l2(hi, out3.cpu()) < 4e-3
     _, o16b = ops.linear_tc(xd, wd, bd, want_bf16=True)
     assert torch.equal(o16b.cpu(), ops.linear_tc(xd, wd, bd).cpu().to(torch.bfloat16))
+
+
+# ---- the persistent 2-CTA kernel (gemm2_tc.cu: cta_group::2, 256x256 pair tiles, TMEM double buffering, TMA store) ----
+SHAPES2 = [(256, 256, 64),        # one tile, one K block
+           (1, 512, 512),         # one row: the peer CTA's rows are entirely out of bounds
+           (300, 512, 512),       # second M tile: 44 valid rows in the leader, none in the peer
+           (6880, 512, 512),      # the fused level (160 clips): 54 tiles, ragged last tile
+           (6880, 1536, 512),     # 162 tiles over <= 74 pairs: 2-3 tiles per pair, both accumulator stages
+           (6880, 512, 2048),     # the folded cross-attention GEMM: 32 K blocks, ring wraps 8 times
+           (6880, 1024, 512), (6880, 512, 1024),
+           (20000, 1024, 512)]    # 316 tiles: 4-5 tiles per pair, accumulator phases flip twice
+
+
+@pytest.fixture()
+def gemm2(dev):
+    from rag_gesture_b200 import ops
+    ops.set_gemm_kernel(2)
+    yield ops
+    ops.set_gemm_kernel(0)
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES2)
+def test_gemm2_bit_identical_to_gemm1(dev, gemm2, M, N, K):
+    """Both kernels accumulate the K blocks in the same order into an fp32 TMEM accumulator and run the same
+    epilogue arithmetic: every output (fp32, bf16 hi, bf16 lo) must agree bit for bit, for both tiers."""
+    from rag_gesture_b200 import _lib
+    ops = gemm2
+    g = torch.Generator().manual_seed(M + 5 * N + K)
+    x, w = torch.randn(M, K, generator=g).to(dev), (torch.randn(N, K, generator=g) / K ** 0.5).to(dev)
+    b, r = torch.randn(N, generator=g).to(dev), torch.randn(M, N, generator=g).to(dev)
+    for split in (False, True):
+        for kw in (dict(), dict(residual=r), dict(epilogue=_lib.OP_GELU), dict(bias_none=True)):
+            bias = None if kw.pop("bias_none", False) else b
+            ops.set_gemm_kernel(2)
+            o2, h2 = ops.linear_tc(x, w, bias, split=split, want_bf16=True, **kw)
+            ops.set_gemm_kernel(1)
+            o1, h1 = ops.linear_tc(x, w, bias, split=split, want_bf16=True, **kw)
+            assert torch.equal(o2, o1), (split, kw)
+            assert torch.equal(h2, h1), (split, kw)
+    ops.set_gemm_kernel(2)
+    ref = F.linear(_bf(x.cpu()), _bf(w.cpu()), b.cpu().double())
+    assert rel_l2(ops.linear_tc(x, w, b).cpu(), ref) < 2e-6
+
+
+def test_gemm2_outputs_one_at_a_time(dev, gemm2):
+    """fp32-only and bf16-only launches (the denoiser's qkv / ffn1 shapes) and in-place residual (C32 == R)."""
+    from rag_gesture_b200 import _lib
+    ops = gemm2
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(3)
+    M, N, K = 700, 512, 512
+    x, w = torch.randn(M, K, generator=g).to(dev), (torch.randn(N, K, generator=g) / K ** 0.5).to(dev)
+    b, r = torch.randn(N, generator=g).to(dev), torch.randn(M, N, generator=g).to(dev)
+    ref = ops.linear_tc(x, w, b, residual=r)
+    h = r.clone()
+    with torch.cuda.device(dev):
+        _lib.check(lib.rg_op_linear_tc(_lib.ptr(x), _lib.ptr(w), _lib.ptr(b), _lib.ptr(h), _lib.ptr(h), None, M, N, K,
+                                       _lib.OP_RESIDUAL, 0, _lib.stream_ptr()))
+        o16 = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        _lib.check(lib.rg_op_linear_tc(_lib.ptr(x), _lib.ptr(w), _lib.ptr(b), None, None, _lib.ptr(o16), M, N, K,
+                                       _lib.OP_GELU, 0, _lib.stream_ptr()))
+    assert torch.equal(h, ref)
+    assert torch.equal(o16, ops.linear_tc(x, w, b, epilogue=_lib.OP_GELU).to(torch.bfloat16))
