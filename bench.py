@@ -132,6 +132,8 @@ def run_b200(args):
 
     from rag_gesture_b200 import _lib
     prec = {"bf16": _lib.PREC_BF16, "bf16x3": _lib.PREC_BF16X3, "fp32": _lib.PREC_FP32}[args.precision]
+    if args.gemm_kernel or args.gemm2_min_rows:
+        _lib.check(_lib.load().rg_set_gemm_kernel(args.gemm_kernel, args.gemm2_min_rows))
     cfg = C.model_cfg()
     cfg["use_retrieval_for_test"] = True
     cfg["model"]["precision"] = prec
@@ -262,7 +264,7 @@ def run_b200(args):
     # ---- roofline of the dominant kernel family: the dense GEMMs of one denoiser evaluation --------------
     roof = gemm_roofline(arch, [B, E], dev, flush, tc_sus, peak_src, args.precision)
     if args.precision != "fp32":
-        roof = gemm_chain_roofline(arch, [B, E], dev, flush, tc_sus, roof)
+        roof = gemm_chain_roofline(arch, [B, E], dev, flush, tc_sus, roof, args.steps)
     knn = knn_bench(args, dev, rank, world, hbm_peak, tc_sus, peak_src, flush)
 
     if rank == 0:
@@ -362,14 +364,16 @@ def gemm_roofline(arch, n_clips, dev, flush, tc_peak, peak_src, precision):
             "note": "exact fp32 tier runs on CUDA cores; the tcgen05 bf16 path is the next kernel"}
 
 
-def gemm_chain_roofline(arch, n_clips, dev, flush, tc_peak, isolated):
+def gemm_chain_roofline(arch, n_clips, dev, flush, tc_peak, isolated, k_steps=2):
     """The dense contractions as they run INSIDE a step: rg_probe_gemm_only makes rg_denoise launch only its
     GEMMs -- the model's own weights (a different matrix per layer), the step's shapes, epilogues and
     programmatic-dependent-launch chain -- and 10 such evaluations are timed back to back with CUDA events on
     the launching stream (one L2 flush before them, as in the loop where weights stay L2-resident between
-    levels).  achieved = algorithmic GEMM flops (3.291 GFLOP per clip-step) / that time, over the inversion
-    (E clips) and the sampling (B clips) row counts.  The isolated, L2-flushed per-launch figures stay in
-    `isolated`; `gemm_share` is GEMM-only time / full evaluation time (ncu launch list: 67 %)."""
+    levels).  achieved = algorithmic GEMM flops (3.291 GFLOP per clip-step) / that time, over the row counts the
+    timed region of `value` launches, weighted by how often: per level one evaluation of E clips (head pass:
+    inversion only), K-1 evaluations of B+E clips (fused guided + inversion passes: the persistent 2-CTA kernel)
+    and one of B clips (tail pass).  The isolated, L2-flushed per-launch figures stay in `isolated`;
+    `gemm_share` is GEMM-only time / full evaluation time."""
     from rag_gesture_b200 import _lib, synthetic as S
     from rag_gesture_b200 import config as C
     lib = _lib.load()
@@ -386,7 +390,9 @@ def gemm_chain_roofline(arch, n_clips, dev, flush, tc_peak, isolated):
         return a.elapsed_time(b) / n / 1e3
 
     tot_t, tot_f, per, share = 0.0, 0.0, {}, {}
-    for clips in n_clips:
+    B_, E_ = n_clips
+    mix = [(E_, 1), (B_ + E_, max(1, k_steps - 1)), (B_, 1)]
+    for clips, weight in mix:
         if clips <= 0:
             continue
         cond = S.synthetic_conditions(clips, seed=5)
@@ -409,11 +415,13 @@ def gemm_chain_roofline(arch, n_clips, dev, flush, tc_peak, isolated):
         flops = GEMM_GFLOP_PER_CLIP_STEP * 1e9 * clips
         per[f"M{clips * 43}"] = round(flops / t_gemm / 1e12, 1)
         share[f"M{clips * 43}"] = round(t_gemm / t_full, 3)
-        tot_t += t_gemm
-        tot_f += flops
+        tot_t += t_gemm * weight
+        tot_f += flops * weight
     ach = tot_f / tot_t / 1e12
-    return {"bound": "tensor", "kernel": "gemm_tc_kernel<128,*> (tcgen05.mma kind::f16, TMA-fed, TMEM accumulator): the 106 GEMM "
+    return {"bound": "tensor", "kernel": "gemm2_tc_kernel (persistent 2-CTA tcgen05.mma cta_group::2 kind::f16, 256x256 pair tiles, TMA-fed, "
+            "2 TMEM accumulator stages, TMA-store epilogue) from 4096 rows on, gemm_tc_kernel<128,*> below: the 58 GEMM "
             "launches of one denoiser evaluation as their own PDL chain (rg_probe_gemm_only), 10 evaluations back to back",
+            "mix": {f"M{c * 43}": w for c, w in mix},
             "achieved": round(ach, 1), "peak": tc_peak, "unit": "TFLOP/s", "frac": round(ach / tc_peak, 4),
             "traffic": isolated.get("traffic"), "traffic_source": isolated.get("traffic_source"),
             "peak_source": isolated.get("peak_source"), "rows": isolated.get("rows"), "in_chain_tflops": per,
@@ -622,6 +630,9 @@ if __name__ == "__main__":
     ap.add_argument("--knn-n", type=int, default=1_000_000)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--ncu-steps", type=int, default=0, help="profiling pass: loops cut to S levels, nothing timed")
+    ap.add_argument("--gemm-kernel", type=int, default=0, choices=[0, 1, 2],
+                    help="rg_set_gemm_kernel: 0 automatic, 1 always the 128x128 kernel, 2 the 2-CTA kernel when eligible")
+    ap.add_argument("--gemm2-min-rows", type=int, default=0, help="row threshold of the automatic choice (0: library default)")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

@@ -132,6 +132,11 @@ int rg_run_levels(rg_handle h, int S, float* xj, int B, int E, const float* in_s
  * onto the caller's stream before the call returns) one rg_denoise uses: 0 = automatic (currently 1),
  * 1..4 fixed.  Results do not depend on the setting: clips never interact inside a step. */
 int rg_set_lanes(rg_handle h, int lanes);
+/* CUDA graphs of the evaluation chain (default on; RG_GRAPHS=0 in the environment also disables them).  The
+ * ~100 kernel launches of one rg_denoise / rg_denoise_groups evaluation depend only on buffer addresses and B:
+ * the second call with the same addresses captures them (programmatic-dependent-launch edges included) and
+ * later calls replay the graph with one cudaGraphLaunch.  Results are bit-identical either way. */
+int rg_set_graphs(rg_handle h, int on);
 
 /* DDIM update (eta = 0), bit-exact fp32 op order of the reference:
  *   eps = (c0*x - x0)/c1 ; out = x0*ca + cb*eps ; direction -1: (ca,cb) = coef 2,3 (ddim_sample,

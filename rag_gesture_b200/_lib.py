@@ -27,6 +27,7 @@ SIGNATURES = {
                        C.POINTER(_P)]),
     "rg_destroy": (_I, [_P]),
     "rg_set_lanes": (_I, [_P, _I]),
+    "rg_set_graphs": (_I, [_P, _I]),
     "rg_set_schedule": (_I, [_P, _I, C.POINTER(C.c_int32), C.POINTER(_F), _P]),
     "rg_encode_conditions": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "rg_state_floats_per_clip": (_L, [_P]),

@@ -117,6 +117,20 @@ struct rg_model {
     float *kv_ln, *kv_buf;
     long long tt_rows;
     float *tt_emb, *tt_t1, *tt_e;
+    // CUDA graphs of the evaluation chain (one per distinct set of buffer addresses; see run_eval)
+    int use_graphs;
+    float* ss_one;                        // [L*5*1024]: the current level's table row at a fixed address
+    cudaStream_t cap_st;                  // capture happens here (the caller's stream may be the legacy stream)
+    struct EvalGraph {
+        const void *x, *src_mask, *qmask, *state, *x0, *ss;
+        long long ss_stride, qm_stride;
+        int B, gemm_only, kmode, kmin;
+        cudaGraphExec_t exec;
+        long long launches;
+        unsigned long long last_use;
+    };
+    std::vector<EvalGraph> graphs;
+    unsigned long long graph_clock;
 };
 
 static int dalloc(rg_model* m, void** p, size_t bytes) {
@@ -205,8 +219,16 @@ extern "C" const char* rg_last_error(void) { return g_err; }
 extern "C" int rg_abi_version(void) { return RG_ABI_VERSION; }
 extern "C" int64_t rg_launch_count(void) { return g_launches; }
 
+static void drop_graphs(rg_model* m) {
+    for (auto& g : m->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    m->graphs.clear();
+}
+
 extern "C" int rg_destroy(rg_handle h) {
     if (!h) return 0;
+    drop_graphs(h);
+    if (h->cap_st) cudaStreamDestroy(h->cap_st);
     for (void* p : h->allocs) cudaFree(p);
     for (int i = 0; i < RG_MAX_LANES; ++i) {
         if (h->lane_st[i]) cudaStreamDestroy(h->lane_st[i]);
@@ -245,6 +267,8 @@ extern "C" int rg_create(const rg_config* cfg, int n_tensors, const char* const*
     for (int i = 0; i < RG_MAX_LANES; ++i) { m->lane_st[i] = nullptr; m->ev_join[i] = nullptr; }
     m->kv_rows = 0; m->kv_ln = m->kv_buf = nullptr;
     m->tt_rows = 0; m->tt_emb = m->tt_t1 = m->tt_e = nullptr;
+    m->use_graphs = 1; m->ss_one = nullptr; m->cap_st = nullptr; m->graph_clock = 0;
+    if (const char* e = getenv("RG_GRAPHS")) m->use_graphs = atoi(e);
     m->planes = cfg->precision == RG_PREC_BF16X3 ? 2 : 1;
     m->attn_mode = cfg->precision == RG_PREC_BF16X3 ? 2 : 1;
     m->attn_mode_ca = m->attn_mode;
@@ -370,6 +394,7 @@ extern "C" int rg_create(const rg_config* cfg, int n_tensors, const char* const*
     dfree_one(m, tmpW); dfree_one(m, tmpb); dfree_one(m, tmpg); dfree_one(m, tmpbe);
     dfree_one(m, seq); dfree_one(m, glob);
     TRY(dalloc(m, (void**)&m->tau_row, (size_t)L * 5 * 2 * D * sizeof(float)));
+    TRY(dalloc(m, (void**)&m->ss_one, (size_t)L * 5 * 2 * D * sizeof(float)));
     if (cfg->precision != RG_PREC_FP32) {
         m->tc.resize(L);
         TRY(make_w16(m, m->W_joint, D, D, &m->tc_joint));
@@ -449,6 +474,10 @@ extern "C" int rg_set_schedule(rg_handle m, int n_steps, const int32_t* timestep
 // ---- workspaces ------------------------------------------------------------------------------
 static int ensure_ws(rg_model* m, Ws& w, long long rows) {
     if (rows <= w.rows) return 0;
+    if (!m->graphs.empty()) {               // captured launches point into the buffers that are about to move
+        CU(cudaDeviceSynchronize());
+        drop_graphs(m);
+    }
     float** bufs[6] = {&w.h, &w.a, &w.big, &w.o3, &w.g, &w.y};
     for (auto b : bufs) { dfree_one(m, *b); *b = nullptr; }
     w.rows = 0;
@@ -704,6 +733,87 @@ static int denoise_f32(rg_model* m, Ws& w, const float* x, int B, const float* s
     return 0;
 }
 
+// broadcast one table row to `n_clips` consecutive per-clip rows
+__global__ void __launch_bounds__(256) rep_rows_kernel(const float4* __restrict__ row, float4* __restrict__ out,
+                                                      long long n4_row, long long n4_total) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4_total; i += stride)
+        out[i] = __ldg(row + i % n4_row);
+}
+
+static int rep_rows(const float* row, float* out, long long n4_row, long long n4_total, cudaStream_t st) {
+    if (n4_total <= 0) return 0;
+    const int blocks = (int)std::min<long long>((n4_total + 255) / 256, 148 * 8);
+    rep_rows_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(row), reinterpret_cast<float4*>(out), n4_row, n4_total);
+    CU(cudaGetLastError());
+    rg_count_launch(1);
+    return 0;
+}
+
+// One denoiser evaluation of lane 0's workspace.  The ~100 launches of the chain depend only on buffer ADDRESSES
+// (latents, masks, state, output, the (scale|shift) rows at `ss`) and on B: the first call with a given set runs
+// them directly, the second captures the same call sequence into a CUDA graph (PDL edges included), later calls
+// replay it -- one cudaGraphLaunch instead of ~100 cudaLaunchKernelEx (host enqueue was the limit at B = 1 and
+// at 8 ranks per host).  Graphs die with the workspace (ensure_ws) and are evicted LRU beyond 16.
+static int run_eval(rg_model* m, const float* x, int B, const float* ss, long long ss_stride, const float* src_mask,
+                    const float* query_mask, long long qm_stride, const float* state, float* x0_out, cudaStream_t st) {
+    const bool tc = m->cfg.precision != RG_PREC_FP32;
+    auto direct = [&]() {
+        return (tc ? denoise_tc : denoise_f32)(m, m->ws[0], x, B, ss, ss_stride, src_mask, query_mask, qm_stride, state,
+                                               x0_out, st);
+    };
+    if (!m->use_graphs) return direct();
+    rg_model::EvalGraph key = {x, src_mask, query_mask, state, x0_out, ss, ss_stride, qm_stride, B, m->gemm_only,
+                               rg_gemm_kernel_mode, rg_gemm2_min_rows, nullptr, 0, 0};
+    rg_model::EvalGraph* hit = nullptr;
+    for (auto& g : m->graphs)
+        if (g.x == key.x && g.src_mask == key.src_mask && g.qmask == key.qmask && g.state == key.state && g.x0 == key.x0 &&
+            g.ss == key.ss && g.ss_stride == key.ss_stride && g.qm_stride == key.qm_stride && g.B == key.B &&
+            g.gemm_only == key.gemm_only && g.kmode == key.kmode && g.kmin == key.kmin) { hit = &g; break; }
+    if (!hit) {                                     // first sight: run directly (also performs every one-off init)
+        if (m->graphs.size() >= 16) {
+            size_t old = 0;
+            for (size_t i = 1; i < m->graphs.size(); ++i)
+                if (m->graphs[i].last_use < m->graphs[old].last_use) old = i;
+            if (m->graphs[old].exec) {
+                // the exec may still be running on the caller's stream
+                CU(cudaStreamSynchronize(st));
+                cudaGraphExecDestroy(m->graphs[old].exec);
+            }
+            m->graphs.erase(m->graphs.begin() + old);
+        }
+        key.last_use = ++m->graph_clock;
+        m->graphs.push_back(key);
+        return direct();
+    }
+    hit->last_use = ++m->graph_clock;
+    if (!hit->exec) {
+        if (!m->cap_st) CU(cudaStreamCreateWithFlags(&m->cap_st, cudaStreamNonBlocking));
+        cudaGraph_t graph = nullptr;
+        const long long l0 = g_launches;
+        cudaError_t e = cudaStreamBeginCapture(m->cap_st, cudaStreamCaptureModeThreadLocal);
+        int rc = 1;
+        if (e == cudaSuccess) {
+            rc = (tc ? denoise_tc : denoise_f32)(m, m->ws[0], x, B, ss, ss_stride, src_mask, query_mask, qm_stride, state,
+                                                 x0_out, m->cap_st);
+            e = cudaStreamEndCapture(m->cap_st, &graph);
+        }
+        hit->launches = g_launches - l0;
+        g_launches = l0;                            // nothing ran yet
+        if (rc == 0 && e == cudaSuccess && graph) e = cudaGraphInstantiate(&hit->exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        if (rc != 0 || e != cudaSuccess || !hit->exec) {   // capture not possible here: stay on direct launches
+            cudaGetLastError();
+            hit->exec = nullptr;
+            m->use_graphs = 0;
+            return direct();
+        }
+    }
+    CU(cudaGraphLaunch(hit->exec, st));
+    g_launches += hit->launches;
+    return 0;
+}
+
 extern "C" int rg_denoise(rg_handle m, const float* x, int B, int step_idx, int tau,
                           const float* src_mask, const float* query_mask, const float* state,
                           float* x0_out, void* stream) {
@@ -731,6 +841,15 @@ extern "C" int rg_denoise(rg_handle m, const float* x, int B, int step_idx, int 
     if (lanes > RG_MAX_LANES) lanes = RG_MAX_LANES;
     if (lanes > B) lanes = B;
     const bool tc = m->cfg.precision != RG_PREC_FP32;
+    if (lanes == 1) {
+        if (ensure_ws(m, m->ws[0], (long long)B * T)) return 1;
+        const float* row = ssrow;
+        if (m->use_graphs && step_idx >= 0) {       // the level's row at an address that does not change per level
+            if (rep_rows(ssrow, m->ss_one, NT / 4, NT / 4, st)) return 1;
+            row = m->ss_one;
+        }
+        return run_eval(m, x, B, row, 0, src_mask, query_mask, (long long)B * T, state, x0_out, st);
+    }
     if (lanes > 1 && !m->ev_fork) {
         CU(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
         for (int i = 1; i < RG_MAX_LANES; ++i) {
@@ -754,14 +873,6 @@ extern "C" int rg_denoise(rg_handle m, const float* x, int B, int step_idx, int 
     }
     for (int i = 1; i < lanes; ++i) CU(cudaStreamWaitEvent(st, m->ev_join[i], 0));
     return rc;
-}
-
-// broadcast one table row to `n_clips` consecutive per-clip rows
-__global__ void __launch_bounds__(256) rep_rows_kernel(const float4* __restrict__ row, float4* __restrict__ out,
-                                                      long long n4_row, long long n4_total) {
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4_total; i += stride)
-        out[i] = __ldg(row + i % n4_row);
 }
 
 extern "C" int rg_denoise_groups(rg_handle m, const float* x, int B, int n_groups, const int32_t* group_clips,
@@ -790,21 +901,12 @@ extern "C" int rg_denoise_groups(rg_handle m, const float* x, int B, int n_group
     }
     long long b0 = 0;
     for (int g = 0; g < n_groups; ++g) {
-        const long long n4 = (long long)group_clips[g] * NT / 4;
-        if (n4 > 0) {
-            const int blocks = (int)std::min<long long>((n4 + 255) / 256, 148 * 8);
-            rep_rows_kernel<<<blocks, 256, 0, st>>>(
-                reinterpret_cast<const float4*>(m->table + (long long)group_step_idx[g] * NT),
-                reinterpret_cast<float4*>(m->ss_rep + b0 * NT), NT / 4, n4);
-            CU(cudaGetLastError());
-            rg_count_launch(1);
-        }
+        if (rep_rows(m->table + (long long)group_step_idx[g] * NT, m->ss_rep + b0 * NT, NT / 4,
+                     (long long)group_clips[g] * NT / 4, st)) return 1;
         b0 += group_clips[g];
     }
     if (ensure_ws(m, m->ws[0], (long long)B * T)) return 1;
-    const bool tc = m->cfg.precision != RG_PREC_FP32;
-    return (tc ? denoise_tc : denoise_f32)(m, m->ws[0], x, B, m->ss_rep, NT, src_mask, query_mask, (long long)B * T,
-                                           state, x0_out, st);
+    return run_eval(m, x, B, m->ss_rep, NT, src_mask, query_mask, (long long)B * T, state, x0_out, st);
 }
 
 extern "C" int rg_set_lanes(rg_handle m, int lanes) {
@@ -980,6 +1082,11 @@ extern "C" int rg_probe_gemm_tc(const float* x, const float* W, const float* b, 
     *median_ms = ts[ts.size() / 2];
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaFree(a16); cudaFree(w16);
+    return 0;
+}
+extern "C" int rg_set_graphs(rg_handle m, int on) {
+    if (!m) return rg_fail("rg_set_graphs: null handle");
+    m->use_graphs = on ? 1 : 0;
     return 0;
 }
 extern "C" int rg_set_gemm_kernel(int mode, int min_rows) {

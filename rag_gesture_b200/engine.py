@@ -109,6 +109,10 @@ class DenoiserEngine:
         """Concurrent clip-range chains per denoise call: 0 = automatic, 1..4 fixed (rg_set_lanes)."""
         _lib.check(self.lib.rg_set_lanes(self._h, int(lanes)))
 
+    def set_graphs(self, on):
+        """CUDA-graph replay of the evaluation chain (rg_set_graphs); on by default."""
+        _lib.check(self.lib.rg_set_graphs(self._h, int(bool(on))))
+
     # -- per step -----------------------------------------------------------------------------------
     def denoise(self, x, src_mask, query_mask, state, step_idx=-1, tau=0, out=None):
         """x0 = model(x, t) for B clips sharing one timestep.  query_mask: [3,B,T] tensor or None."""

@@ -472,3 +472,48 @@ def test_run_levels_equals_step_loops(model, diffusion, dev):
         assert torch.equal(out, ref)
     finally:
         diffusion.noise_fn, diffusion.skip_dead_guidance = None, True
+
+
+@pytest.mark.parametrize("which", ["fp32", "tc"])
+def test_graph_replay_is_bit_identical(which, model, tc_model, diffusion, dev):
+    """rg_set_graphs: the evaluation chain replayed from a CUDA graph (second and later calls on the same
+    buffers) == direct launches, for single-level and grouped evaluations, across levels (the level's table
+    row is re-staged outside the graph), after the workspace grew (graphs are dropped), and over a whole
+    run_levels loop."""
+    mdl = model if which == "fp32" else tc_model[0]
+    eng = mdl.rg_engine(diffusion)
+    B = 6
+    kw = _kw(mdl, S.synthetic_conditions(B, seed=111), B, dev)
+    prep = mdl.prepare_batch(kw, B)
+    x = S.synthetic_latents(B, seed=112).to(dev)
+    out = torch.empty_like(x)
+    try:
+        eng.set_graphs(False)
+        ref = {lvl: eng.denoise(x, prep.src_mask, prep.query_mask, prep.state, step_idx=lvl).clone() for lvl in (3, 30, 49)}
+        ref_g = eng.denoise_groups(x, prep.src_mask, prep.query_mask, prep.state, [(2, 5), (4, 44)]).clone()
+        eng.set_graphs(True)
+        for rep in range(3):                        # direct, capture + replay, replay
+            for lvl in (3, 30, 49):
+                eng.denoise(x, prep.src_mask, prep.query_mask, prep.state, step_idx=lvl, out=out)
+                assert torch.equal(out, ref[lvl]), (rep, lvl)
+            eng.denoise_groups(x, prep.src_mask, prep.query_mask, prep.state, [(2, 5), (4, 44)], out=out)
+            assert torch.equal(out, ref_g), rep
+        # a larger batch grows the workspace: captured graphs must not be replayed on the moved buffers
+        B2 = 40
+        kw2 = _kw(mdl, S.synthetic_conditions(B2, seed=113), B2, dev)
+        prep2 = mdl.prepare_batch(kw2, B2)
+        x2 = S.synthetic_latents(B2, seed=114).to(dev)
+        big = [eng.denoise(x2, prep2.src_mask, prep2.query_mask, prep2.state, step_idx=7).clone() for _ in range(3)]
+        assert torch.equal(big[0], big[1]) and torch.equal(big[0], big[2])
+        for rep in range(2):
+            eng.denoise(x, prep.src_mask, prep.query_mask, prep.state, step_idx=30, out=out)
+            assert torch.equal(out, ref[30])
+        # whole loops: 50 levels on the same buffers (level 0 direct, level 1 captures, 48 replays)
+        start = S.synthetic_latents(B, seed=115, scale=0.5).to(dev)
+        kwr = dict(kw)
+        _, inv_g = diffusion.run_levels(mdl, reverse=dict(start_img=start, model_kwargs=kwr))
+        eng.set_graphs(False)
+        _, inv_d = diffusion.run_levels(mdl, reverse=dict(start_img=start, model_kwargs=kwr))
+        assert all(torch.equal(a, b) for a, b in zip(inv_g, inv_d))
+    finally:
+        eng.set_graphs(True)
