@@ -132,8 +132,8 @@ def run_b200(args):
 
     from rag_gesture_b200 import _lib
     prec = {"bf16": _lib.PREC_BF16, "bf16x3": _lib.PREC_BF16X3, "fp32": _lib.PREC_FP32}[args.precision]
-    if args.gemm_kernel or args.gemm2_min_rows:
-        _lib.check(_lib.load().rg_set_gemm_kernel(args.gemm_kernel, args.gemm2_min_rows))
+    if args.gemm_kernel or args.gemm2_min_rows or args.gemm2_persist_tiles:
+        _lib.check(_lib.load().rg_set_gemm_kernel(args.gemm_kernel, args.gemm2_min_rows, args.gemm2_persist_tiles))
     cfg = C.model_cfg()
     cfg["use_retrieval_for_test"] = True
     cfg["model"]["precision"] = prec
@@ -633,6 +633,7 @@ if __name__ == "__main__":
     ap.add_argument("--gemm-kernel", type=int, default=0, choices=[0, 1, 2],
                     help="rg_set_gemm_kernel: 0 automatic, 1 always the 128x128 kernel, 2 the 2-CTA kernel when eligible")
     ap.add_argument("--gemm2-min-rows", type=int, default=0, help="row threshold of the automatic choice (0: library default)")
+    ap.add_argument("--gemm2-persist-tiles", type=int, default=0, help="pair tiles from which the 2-CTA kernel is persistent (0: default)")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

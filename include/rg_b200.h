@@ -181,14 +181,16 @@ int rg_probe_gemm_tc(const float* x, const float* W, const float* b, float* out,
  * epilogues as in the step, without the attention and row kernels between them (outputs are then meaningless).
  * Time a few evaluations with CUDA events, then switch it off. */
 int rg_probe_gemm_only(rg_handle h, int on);
-/* Which tcgen05 GEMM kernel the tensor-core tiers launch (process-wide; results are identical up to fp32
- * summation order inside the tensor core, i.e. bit-identical: both accumulate K in the same order in TMEM):
- *   mode 0 (default): automatic -- the persistent 2-CTA kernel (256x256 tile per CTA pair, cta_group::2, TMEM
- *          double buffering, TMA-store epilogue) for launches of at least `min_rows` rows whose N is a multiple
- *          of 256, the 128x128 one-tile-per-CTA kernel otherwise;
+/* Which tcgen05 GEMM kernel the tensor-core tiers launch (process-wide; results are bit-identical: all kernels
+ * accumulate the K blocks in the same order in an fp32 TMEM accumulator and share the epilogue arithmetic):
+ *   mode 0 (default): automatic -- the 2-CTA kernel (256x256 tile per CTA pair, tcgen05.mma.cta_group::2, TMA-store
+ *          epilogue) for launches of at least `min_rows` rows whose N is a multiple of 256, the 128x128
+ *          one-tile-per-CTA kernel otherwise;
  *   mode 1: always the 128x128 kernel;   mode 2: the 2-CTA kernel whenever the shape allows.
- * min_rows <= 0 keeps the current threshold (default 4096).  Used by the parity tests and bench.py. */
-int rg_set_gemm_kernel(int mode, int min_rows);
+ * The 2-CTA kernel runs one tile per pair with two CTAs per SM below `persist_tiles` pair tiles, and as a persistent
+ * kernel with two TMEM accumulator stages from there on.  min_rows / persist_tiles <= 0 keep the current values
+ * (defaults 16384 / 296).  Used by the parity tests and bench.py. */
+int rg_set_gemm_kernel(int mode, int min_rows, int persist_tiles);
 /* Diagnostics: one traced launch of the tcgen05 GEMM on zero operands (after 3 untraced ones).  trace_host
  * receives 10 int64 per CTA (grid order x-fastest): clock64 at [0] entry, [1] prologue done, [2] producer
  * past griddepcontrol.wait, [3] first operand stage landed, [4] last MMA committed, [5] accumulator visible

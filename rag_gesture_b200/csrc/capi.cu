@@ -124,7 +124,7 @@ struct rg_model {
     struct EvalGraph {
         const void *x, *src_mask, *qmask, *state, *x0, *ss;
         long long ss_stride, qm_stride;
-        int B, gemm_only, kmode, kmin;
+        int B, gemm_only, kmode, kmin, kpt;
         cudaGraphExec_t exec;
         long long launches;
         unsigned long long last_use;
@@ -764,12 +764,12 @@ static int run_eval(rg_model* m, const float* x, int B, const float* ss, long lo
     };
     if (!m->use_graphs) return direct();
     rg_model::EvalGraph key = {x, src_mask, query_mask, state, x0_out, ss, ss_stride, qm_stride, B, m->gemm_only,
-                               rg_gemm_kernel_mode, rg_gemm2_min_rows, nullptr, 0, 0};
+                               rg_gemm_kernel_mode, rg_gemm2_min_rows, rg_gemm2_persist_tiles, nullptr, 0, 0};
     rg_model::EvalGraph* hit = nullptr;
     for (auto& g : m->graphs)
         if (g.x == key.x && g.src_mask == key.src_mask && g.qmask == key.qmask && g.state == key.state && g.x0 == key.x0 &&
             g.ss == key.ss && g.ss_stride == key.ss_stride && g.qm_stride == key.qm_stride && g.B == key.B &&
-            g.gemm_only == key.gemm_only && g.kmode == key.kmode && g.kmin == key.kmin) { hit = &g; break; }
+            g.gemm_only == key.gemm_only && g.kmode == key.kmode && g.kmin == key.kmin && g.kpt == key.kpt) { hit = &g; break; }
     if (!hit) {                                     // first sight: run directly (also performs every one-off init)
         if (m->graphs.size() >= 16) {
             size_t old = 0;
@@ -1089,10 +1089,11 @@ extern "C" int rg_set_graphs(rg_handle m, int on) {
     m->use_graphs = on ? 1 : 0;
     return 0;
 }
-extern "C" int rg_set_gemm_kernel(int mode, int min_rows) {
-    if (mode < 0 || mode > 2) return rg_fail("rg_set_gemm_kernel: mode must be 0 (auto), 1 (128x128 tiles) or 2 (2-CTA persistent)");
+extern "C" int rg_set_gemm_kernel(int mode, int min_rows, int persist_tiles) {
+    if (mode < 0 || mode > 2) return rg_fail("rg_set_gemm_kernel: mode must be 0 (auto), 1 (128x128 tiles) or 2 (2-CTA tiles)");
     rg_gemm_kernel_mode = mode;
     if (min_rows > 0) rg_gemm2_min_rows = min_rows;
+    if (persist_tiles > 0) rg_gemm2_persist_tiles = persist_tiles;
     return 0;
 }
 extern "C" int rg_probe_gemm_only(rg_handle m, int on) {
@@ -1106,31 +1107,42 @@ extern "C" int rg_probe_gemm_trace(int M, int N, int K, int split, int epilogue,
     if (N % 128 || K % 64) return rg_fail("rg_probe_gemm_trace: bad shape");
     const int planes = split ? 2 : 1;
     const long long ctas = (long long)(N / 128) * ((M + 127) / 128);
-    if (n_trace < ctas * 10) return rg_fail("rg_probe_gemm_trace: trace buffer needs %lld entries", ctas * 10);
+    // 2-CTA kernel (rg_set_gemm_kernel mode 2): 16 globaltimer stamps per CTA, the last TWO launches of the chain
+    const bool k2 = rg_gemm_kernel_mode == 2 && N % 256 == 0;
+    const long long need = k2 ? 2 * ctas * 10 : ctas * 10;
+    if (n_trace < need) return rg_fail("rg_probe_gemm_trace: trace buffer needs %lld entries", need);
     void *a16 = nullptr, *w16 = nullptr; float *out = nullptr, *res = nullptr; long long* tr = nullptr;
     CU(cudaMalloc(&a16, (size_t)M * K * planes * 2));
     CU(cudaMalloc(&w16, (size_t)N * K * planes * 2));
     CU(cudaMalloc(&out, (size_t)M * N * 4));
     CU(cudaMalloc(&res, (size_t)M * N * 4));
-    CU(cudaMalloc(&tr, (size_t)ctas * 10 * 8));
+    CU(cudaMalloc(&tr, (size_t)need * 8));
+    CU(cudaMemset(tr, 0, (size_t)need * 8));
     CU(cudaMemset(a16, 0, (size_t)M * K * planes * 2));
     CU(cudaMemset(w16, 0, (size_t)N * K * planes * 2));
     CU(cudaMemset(res, 0, (size_t)M * N * 4));
-    CUtensorMap tmA, tmW;
+    CUtensorMap tmA, tmW, ts32, ts16;
     CU(rg_make_tensor_map(&tmA, a16, M, (long long)K * planes, (long long)K * planes, 128));
     CU(rg_make_tensor_map(&tmW, w16, N, (long long)K * planes, (long long)K * planes, 128));
+    CU(rg_make_store_map(&ts32, out, M, N, N, 4));
+    CU(rg_make_store_map(&ts16, res, M, (long long)N * planes, (long long)N * planes, 2));
     RgGemmTc p;
     memset(&p, 0, sizeof(p));
     p.M = M; p.N = N; p.K = K; p.split = split ? 1 : 0; p.a_lo_off = K; p.w_lo_off = K; p.groups = 1;
-    p.C32 = out; p.ldc32 = N; p.epi = RG_EPI_BIAS;
+    p.C32 = out; p.ldc32 = N; p.epi = RG_EPI_BIAS; p.tmC32 = &ts32;
     if (epilogue == 1) { p.R = res; p.ldr = N; p.epi = RG_EPI_BIAS_RESIDUAL; }
-    if (epilogue == 2) { p.C32 = nullptr; p.C16_ = res; p.ldc16 = N * planes; p.c16_lo_off = split ? N : 0; p.epi = RG_EPI_BIAS_GELU; }
-    for (int i = 0; i < 4; ++i) {
-        p.trace = i == 3 ? tr : nullptr;
+    if (epilogue == 2) {
+        p.C32 = nullptr; p.tmC32 = nullptr; p.C16_ = res; p.tmC16 = &ts16; p.ldc16 = N * planes; p.c16_lo_off = split ? N : 0;
+        p.epi = RG_EPI_BIAS_GELU;
+    }
+    for (int i = 0; i < 6; ++i) {
+        p.trace = nullptr;
+        if (k2 && i >= 4) p.trace = tr + (long long)(i - 4) * ctas * 10;
+        if (!k2 && i == 5) p.trace = tr;
         LAUNCH(rg_launch_gemm_tc(tmA, tmW, p, st));
     }
     CU(cudaStreamSynchronize(st));
-    CU(cudaMemcpy(trace_host, tr, (size_t)ctas * 10 * 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(trace_host, tr, (size_t)need * 8, cudaMemcpyDeviceToHost));
     cudaFree(a16); cudaFree(w16); cudaFree(out); cudaFree(res); cudaFree(tr);
     return 0;
 }

@@ -8,10 +8,17 @@
 // UMMA 256x256x16 reads both halves -> 128 flop per operand byte (half the L2 traffic per flop), and the weight
 // tile is fetched once per 256 rows instead of once per 128.
 //
-//   * persistent: grid = 2 * min(tiles, resident pairs); each pair walks tiles t = pair, pair + n_pairs, ...
-//   * TMEM: all 512 columns = 2 accumulator stages of 256 fp32 columns, so the epilogue of tile i overlaps the
-//     main loop of tile i + 1 (tmem_full / tmem_empty mbarriers; the peer CTA's epilogue warps arrive remotely
-//     on the leader's tmem_empty barrier);
+//   Two instantiations of one kernel (template ACCS = accumulator stages):
+//   * ACCS = 2, persistent: grid = 2 * min(tiles, resident pairs), one CTA per SM; each pair walks tiles
+//     t = pair, pair + n_pairs, ...; all 512 TMEM columns = 2 accumulator stages of 256 fp32 columns, so the
+//     epilogue of tile i overlaps the main loop of tile i + 1 (tmem_full / tmem_empty mbarriers; the peer CTA's
+//     epilogue warps arrive remotely on the leader's tmem_empty barrier); dedicated epilogue staging.  For
+//     launches with many tiles per pair.
+//   * ACCS = 1, one tile per pair: grid = 2 * tiles, 256 TMEM columns and a 96 KB ring that the epilogue reuses
+//     as its staging area, so TWO CTAs fit on an SM: under programmatic dependent launch the next GEMM's CTAs are
+//     already resident (barriers initialised, TMEM allocated, weight tiles in flight) while this one drains --
+//     the denoiser's launches have 1-3 tiles per pair, where that overlap is worth more than double buffering
+//     (measured: DESIGN 6);
 //   * operands: cp.async.bulk.tensor.2d.cta_group::2 (TMA, 128-byte swizzle) into a 4-stage (3 in split mode)
 //     ring of 32 KB per CTA; both CTAs' loads complete on the LEADER's full barrier (2 x 32 KB expected), the
 //     leader's single MMA thread issues for the pair and tcgen05.commit multicasts slot-free / accumulator-ready
@@ -38,8 +45,11 @@ using namespace rg_tc;
 constexpr int BM = 128;             // rows per CTA (256 per pair)
 constexpr int BN = 256;             // columns per pair tile; each CTA stages BN/2 weight rows
 constexpr int BK = 64;
-constexpr int EPI_WARPS = 8;
-constexpr int THREADS = 64 + 32 * EPI_WARPS;
+// epilogue warps per CTA: 8 (two per TMEM lane group, splitting the columns) in the persistent variant, 4 in the
+// one-tile-per-pair variant, where two CTAs share an SM and 170 registers per thread avoid spilling the 64-column
+// accumulator + residual registers
+__host__ __device__ constexpr int epi_warps(int accs) { return accs == 1 ? 4 : 8; }
+__host__ __device__ constexpr int threads_of(int accs) { return 64 + 32 * epi_warps(accs); }
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = (BN / 2) * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -100,20 +110,37 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     return *reinterpret_cast<const uint32_t*>(&h);
 }
 
-template <int SPLIT, int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+constexpr int EPI_BYTES = 12288;    // per epilogue warp: two fp32 tiles + one bf16 tile (hi, then lo) of 4 KB
+
+__device__ __forceinline__ long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return (long long)t;
+}
+
+template <int SPLIT, int EPI, int ACCS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(threads_of(ACCS), ACCS == 1 ? 2 : 1)
 gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                 const __grid_constant__ CUtensorMap tmC32, const __grid_constant__ CUtensorMap tmC16, RgGemmTc p) {
-    constexpr int STAGES = SPLIT ? 3 : 4;
-    constexpr int EPI_BYTES = SPLIT ? 16384 : 12288;        // per epilogue warp: 2 fp32 + bf16 hi (+ lo) tiles of 4 KB
+    constexpr int STAGES = ACCS == 1 ? 3 : 4;
+    constexpr int TMEM_COLS = ACCS * BN;
+    constexpr int EPI_WARPS = epi_warps(ACCS);
+    constexpr int WCOLS = BN / (EPI_WARPS / 4);          // columns per epilogue warp
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar[2], tmem_empty_bar[2];
+    __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar[ACCS], tmem_empty_bar[ACCS];
     __shared__ uint32_t tmem_base_smem;
 
     rg_pdl_launch();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
+    long long* tr = p.trace ? p.trace + (long long)blockIdx.x * 16 : nullptr;     // diagnostics (rg_probe_gemm_trace)
+#define RG_STAMP(slot) do { if (tr) tr[slot] = gtime(); } while (0)
+    if (tr && threadIdx.x == 0) {
+        unsigned sm;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+        tr[0] = gtime(); tr[10] = sm;
+    }
     const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
     const int tiles_n = p.N / BN, tiles_m = (p.M + 2 * BM - 1) / (2 * BM), total = tiles_m * tiles_n;
     const int nkb = p.K / BK;
@@ -128,17 +155,18 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (warp == 1) {
         if (lane == 0) {
             for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
-            for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(&tmem_full_bar[a]), 1); mbar_init(smem_u32(&tmem_empty_bar[a]), 2 * EPI_WARPS); }
+            for (int a = 0; a < ACCS; ++a) { mbar_init(smem_u32(&tmem_full_bar[a]), 1); mbar_init(smem_u32(&tmem_empty_bar[a]), 2 * EPI_WARPS); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
-        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(512));
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     cluster_sync_all();                                 // barrier inits + TMEM visible to both CTAs of the pair
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_smem;
+    if (threadIdx.x == 0) RG_STAMP(1);
 
     if (warp == 0) {
         // ===== TMA producer (both CTAs): own 128 rows of A, own half of the 256 weight rows =====
@@ -186,6 +214,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 }
                 j0 = 0;
             }
+            RG_STAMP(3);
         }
     } else if (warp == 1) {
         // ===== MMA issuer: one thread of the leader CTA issues for the pair =====
@@ -193,7 +222,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const uint32_t idesc = make_idesc(2 * BM, BN);
             int it = 0, tl = 0;
             for (int t = pair; t < total; t += n_pairs, ++tl) {
-                const int acc = tl & 1, aph = (tl >> 1) & 1;
+                const int acc = tl % ACCS, aph = (tl / ACCS) & 1;
                 mbar_wait_g(smem_u32(&tmem_empty_bar[acc]), aph ^ 1);      // both CTAs' epilogues drained this stage
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d_tmem = tmem_base + acc * BN;
@@ -202,39 +231,42 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     mbar_wait_g(smem_u32(&full_bar[s]), ph);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     if (elect_one()) {
+                        if (it == 0) RG_STAMP(4);
                         const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
                         const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sb);
 #pragma unroll
                         for (int k = 0; k < BK / UMMA_K; ++k)
                             umma_bf16_pair(d_tmem, da + (k * UMMA_K * 2 >> 4), db + (k * UMMA_K * 2 >> 4), idesc, (j | k) != 0);
                         umma_commit_pair(smem_u32(&empty_bar[s]));
-                        if (j == total_kb - 1) umma_commit_pair(smem_u32(&tmem_full_bar[acc]));
+                        if (j == total_kb - 1) { umma_commit_pair(smem_u32(&tmem_full_bar[acc])); RG_STAMP(5); }
                     }
                     __syncwarp();
                 }
             }
         }
     } else {
-        // ===== epilogue (8 warps per CTA) =====
+        // ===== epilogue (EPI_WARPS warps per CTA) =====
         rg_pdl_wait();                                  // residual reads / stores touch the previous kernel's buffers
         const int ew = warp - 2, lg = warp & 3, half = ew >> 2;
-        const uint32_t stg = smem_u32(smem + STAGES * STAGE_BYTES + ew * EPI_BYTES);
-        const uint32_t s_f0 = stg, s_f1 = stg + 4096, s_h = stg + 8192, s_l = stg + 12288;
+        // ACCS == 1: one tile per pair, so once tmem_full fires the operand ring is idle in both CTAs: stage there
+        const uint32_t stg = smem_u32(smem + (ACCS == 1 ? 0 : STAGES * STAGE_BYTES) + ew * EPI_BYTES);
+        const uint32_t s_f0 = stg, s_f1 = stg + 4096, s_h = stg + 8192;
         const uint32_t row_off = lane * 128, sw = lane & 7;
         const uint32_t tmem_empty_leader[2] = {mapa_u32(smem_u32(&tmem_empty_bar[0]), 0), mapa_u32(smem_u32(&tmem_empty_bar[1]), 0)};
         const bool has32 = p.C32 != nullptr, has16 = p.C16_ != nullptr, lo16 = SPLIT && p.c16_lo_off != 0;
         int tl = 0;
         for (int t = pair; t < total; t += n_pairs, ++tl) {
-            const int acc = tl & 1, aph = (tl >> 1) & 1;
+            const int acc = tl % ACCS, aph = (tl / ACCS) & 1;
             const int m0 = (t / tiles_n) * 2 * BM + (int)rank * BM, n0 = (t % tiles_n) * BN;
             const int row = m0 + lg * 32 + lane;
             const bool row_ok = row < p.M;
             mbar_wait_g(smem_u32(&tmem_full_bar[acc]), aph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (threadIdx.x == 64 && tl == 0) RG_STAMP(6);
 #pragma unroll 1
-            for (int itc = 0; itc < 2; ++itc) {
-                const int ncol = n0 + half * 128 + itc * 64;
-                const uint32_t ta = tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + acc * BN + half * 128 + itc * 64;
+            for (int itc = 0; itc < WCOLS / 64; ++itc) {
+                const int ncol = n0 + half * WCOLS + itc * 64;
+                const uint32_t ta = tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + acc * BN + half * WCOLS + itc * 64;
                 uint32_t v[64];
                 tmem_ld32(ta, v);
                 tmem_ld32(ta + 32, v + 32);
@@ -247,7 +279,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         rr[q] = row_ok ? *reinterpret_cast<const float4*>(src + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (itc == 1) {                         // accumulator stage fully read by this warp: hand it back
+                if (itc == WCOLS / 64 - 1) {            // accumulator stage fully read by this warp: hand it back
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     if (lane == 0) mbar_arrive_remote(tmem_empty_leader[acc]);
                 }
@@ -283,42 +315,57 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         const uint32_t h0 = pack_bf16(f[0], f[1]), h1 = pack_bf16(f[2], f[3]), h2 = pack_bf16(f[4], f[5]), h3 = pack_bf16(f[6], f[7]);
                         const uint32_t off = row_off + ((static_cast<uint32_t>(qq) ^ sw) << 4);
                         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(s_h + off), "r"(h0), "r"(h1), "r"(h2), "r"(h3) : "memory");
-                        if (lo16) {
-                            uint32_t l[4];
+                        if (lo16) {                     // lo = bf16(x - hi): kept in the accumulator registers for the second store
                             const uint32_t hh[4] = {h0, h1, h2, h3};
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
                                 const __nv_bfloat162 hb = *reinterpret_cast<const __nv_bfloat162*>(&hh[i]);
-                                l[i] = pack_bf16(f[2 * i] - __low2float(hb), f[2 * i + 1] - __high2float(hb));
+                                v[4 * qq + i] = pack_bf16(f[2 * i] - __low2float(hb), f[2 * i + 1] - __high2float(hb));
                             }
-                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(s_l + off), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
                         }
                     }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> visible to TMA
                 __syncwarp();
+                const int r0 = m0 + lg * 32;
                 if (lane == 0) {
-                    const int r0 = m0 + lg * 32;
                     if (has32) {
                         tma_store_2d(&tmC32, s_f0, p.c32_col0 + ncol, r0);
                         tma_store_2d(&tmC32, s_f1, p.c32_col0 + ncol + 32, r0);
                     }
-                    if (has16) {
-                        tma_store_2d(&tmC16, s_h, p.c16_col0 + ncol, r0);
-                        if (lo16) tma_store_2d(&tmC16, s_l, p.c16_col0 + p.c16_lo_off + ncol, r0);
-                    }
+                    if (has16) tma_store_2d(&tmC16, s_h, p.c16_col0 + ncol, r0);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                if (has16 && lo16) {                    // the lo plane goes through the same 4 KB tile once the hi store has read it
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    __syncwarp();
+#pragma unroll
+                    for (int qq = 0; qq < 8; ++qq) {
+                        const uint32_t off = row_off + ((static_cast<uint32_t>(qq) ^ sw) << 4);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(s_h + off), "r"(v[4 * qq]), "r"(v[4 * qq + 1]),
+                                     "r"(v[4 * qq + 2]), "r"(v[4 * qq + 3]) : "memory");
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tmC16, s_h, p.c16_col0 + p.c16_lo_off + ncol, r0);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
                 }
             }
         }
+        if (threadIdx.x == 64) RG_STAMP(7);
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores complete before exit
+        if (threadIdx.x == 64) RG_STAMP(8);
     }
     __syncwarp();                                       // reconverge the role branches before the aligned barrier
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     cluster_sync_all();                                 // nobody exits while the peer may still signal / read us
+    if (threadIdx.x == 0) RG_STAMP(9);
+#undef RG_STAMP
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
     }
 }
 
@@ -327,31 +374,34 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode2 = nullptr;
 
-template <int SPLIT, int EPI>
+template <int SPLIT, int EPI, int ACCS>
 cudaError_t launch2(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmC32, const CUtensorMap& tmC16,
                     const RgGemmTc& p, cudaStream_t st) {
-    constexpr int STAGES = SPLIT ? 3 : 4;
-    constexpr int EPI_BYTES = SPLIT ? 16384 : 12288;
-    constexpr size_t smem = (size_t)STAGES * STAGE_BYTES + (size_t)EPI_WARPS * EPI_BYTES + 1024;
-    auto kern = gemm2_tc_kernel<SPLIT, EPI>;
-    static int max_pairs = 0;                   // resident CTA pairs (one CTA per SM)
-    static int max_pairs_dev = -1;
+    constexpr int STAGES = ACCS == 1 ? 3 : 4;
+    constexpr int EPI_WARPS = epi_warps(ACCS), THREADS = threads_of(ACCS);
+    constexpr size_t smem = (size_t)STAGES * STAGE_BYTES + (ACCS == 1 ? 0 : (size_t)EPI_WARPS * EPI_BYTES) + 1024;
+    static_assert(ACCS == 2 || STAGES * STAGE_BYTES >= EPI_WARPS * EPI_BYTES, "the ring must hold the epilogue staging");
+    auto kern = gemm2_tc_kernel<SPLIT, EPI, ACCS>;
+    static int max_pairs = 0;                   // resident CTA pairs of the persistent variant (one CTA per SM)
+    static int attr_dev = -1;
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    if (max_pairs_dev != dev) {
+    if (attr_dev != dev) {
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        cudaLaunchConfig_t q = {};
-        q.gridDim = dim3(2 * 74); q.blockDim = dim3(THREADS); q.dynamicSmemBytes = smem;
-        int n = 0;
-        e = cudaOccupancyMaxActiveClusters(&n, kern, &q);
-        if (e != cudaSuccess || n < 1) { cudaGetLastError(); n = 74; }     // any grid is correct; this only sizes it
-        max_pairs = n > 74 ? 74 : n;
-        max_pairs_dev = dev;
+        if (ACCS == 2) {
+            cudaLaunchConfig_t q = {};
+            q.gridDim = dim3(2 * 74); q.blockDim = dim3(THREADS); q.dynamicSmemBytes = smem;
+            int n = 0;
+            e = cudaOccupancyMaxActiveClusters(&n, kern, &q);
+            if (e != cudaSuccess || n < 1) { cudaGetLastError(); n = 74; }     // any grid is correct; this only sizes it
+            max_pairs = n > 74 ? 74 : n;
+        }
+        attr_dev = dev;
     }
     const int tiles = (p.N / BN) * ((p.M + 2 * BM - 1) / (2 * BM));
-    const int pairs = tiles < max_pairs ? tiles : max_pairs;
+    const int pairs = ACCS == 1 ? tiles : (tiles < max_pairs ? tiles : max_pairs);
     const dim3 grid(2 * pairs);
     if (p.no_pdl) {
         kern<<<grid, THREADS, smem, st>>>(tmA, tmW, tmC32, tmC16, p);
@@ -360,15 +410,15 @@ cudaError_t launch2(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtens
     return rg_launch_pdl(kern, grid, dim3(THREADS), smem, st, tmA, tmW, tmC32, tmC16, p);
 }
 
-template <int SPLIT>
+template <int SPLIT, int ACCS>
 cudaError_t launch2_epi(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& c32, const CUtensorMap& c16,
                         const RgGemmTc& p, cudaStream_t st) {
     switch (p.epi) {
-        case RG_EPI_BIAS: return launch2<SPLIT, RG_EPI_BIAS>(tmA, tmW, c32, c16, p, st);
-        case RG_EPI_BIAS_RESIDUAL: return launch2<SPLIT, RG_EPI_BIAS_RESIDUAL>(tmA, tmW, c32, c16, p, st);
-        case RG_EPI_BIAS_GELU: return launch2<SPLIT, RG_EPI_BIAS_GELU>(tmA, tmW, c32, c16, p, st);
-        case RG_EPI_BIAS_POS: return launch2<SPLIT, RG_EPI_BIAS_POS>(tmA, tmW, c32, c16, p, st);
-        case RG_EPI_BIAS_SILU: return launch2<SPLIT, RG_EPI_BIAS_SILU>(tmA, tmW, c32, c16, p, st);
+        case RG_EPI_BIAS: return launch2<SPLIT, RG_EPI_BIAS, ACCS>(tmA, tmW, c32, c16, p, st);
+        case RG_EPI_BIAS_RESIDUAL: return launch2<SPLIT, RG_EPI_BIAS_RESIDUAL, ACCS>(tmA, tmW, c32, c16, p, st);
+        case RG_EPI_BIAS_GELU: return launch2<SPLIT, RG_EPI_BIAS_GELU, ACCS>(tmA, tmW, c32, c16, p, st);
+        case RG_EPI_BIAS_POS: return launch2<SPLIT, RG_EPI_BIAS_POS, ACCS>(tmA, tmW, c32, c16, p, st);
+        case RG_EPI_BIAS_SILU: return launch2<SPLIT, RG_EPI_BIAS_SILU, ACCS>(tmA, tmW, c32, c16, p, st);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -399,7 +449,7 @@ cudaError_t rg_make_store_map(CUtensorMap* tm, const void* ptr, long long rows, 
 }
 
 bool rg_gemm2_eligible(const RgGemmTc& p) {
-    return p.N % BN == 0 && p.K % BK == 0 && p.groups <= 1 && !p.trace && (p.C32 || p.C16_) &&
+    return p.N % BN == 0 && p.K % BK == 0 && p.groups <= 1 && (p.C32 || p.C16_) &&
            (!p.C32 || p.tmC32) && (!p.C16_ || p.tmC16) && (!p.R || (p.ldr % 4 == 0)) &&
            (p.epi != RG_EPI_BIAS_POS || (p.N % 4 == 0 && p.pos && p.pos_T > 0));
 }
@@ -412,5 +462,9 @@ cudaError_t rg_launch_gemm2_tc(const CUtensorMap& tmA, const CUtensorMap& tmW, c
     if (p.epi == RG_EPI_BIAS_RESIDUAL && !p.R) return cudaErrorInvalidValue;
     const CUtensorMap& c32 = p.tmC32 ? *p.tmC32 : tmA;      // unused maps still need a valid descriptor
     const CUtensorMap& c16 = p.tmC16 ? *p.tmC16 : tmA;
-    return p.split ? launch2_epi<1>(tmA, tmW, c32, c16, p, st) : launch2_epi<0>(tmA, tmW, c32, c16, p, st);
+    // many tiles per pair: persistent with two accumulator stages; else one tile per pair, two CTAs per SM
+    const int tiles = (p.N / BN) * ((p.M + 2 * BM - 1) / (2 * BM));
+    if (tiles >= rg_gemm2_persist_tiles)
+        return p.split ? launch2_epi<1, 2>(tmA, tmW, c32, c16, p, st) : launch2_epi<0, 2>(tmA, tmW, c32, c16, p, st);
+    return p.split ? launch2_epi<1, 1>(tmA, tmW, c32, c16, p, st) : launch2_epi<0, 1>(tmA, tmW, c32, c16, p, st);
 }

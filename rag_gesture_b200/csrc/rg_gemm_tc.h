@@ -36,6 +36,7 @@ cudaError_t rg_make_store_map(CUtensorMap* tm, const void* ptr, long long rows, 
 // 0: automatic (2-CTA kernel from rg_gemm2_min_rows rows on), 1: always the 128x128 kernel, 2: the 2-CTA kernel whenever eligible
 extern int rg_gemm_kernel_mode;
 extern int rg_gemm2_min_rows;
+extern int rg_gemm2_persist_tiles;   // 2-CTA kernel: from this many pair tiles on the persistent variant runs
 // pdl = false: plain launch, i.e. the kernel starts only after everything enqueued before it has completed
 cudaError_t rg_launch_split_bf16(const float* x, int ldx, void* out, int ldo, int lo_off, long long rows, int cols,
                                  cudaStream_t st, bool pdl = true);

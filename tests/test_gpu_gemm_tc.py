@@ -69,12 +69,14 @@ SHAPES2 = [(256, 256, 64),        # one tile, one K block
            (20000, 1024, 512)]    # 316 tiles: 4-5 tiles per pair, accumulator phases flip twice
 
 
-@pytest.fixture()
-def gemm2(dev):
+@pytest.fixture(params=[1, 10 ** 6], ids=["persistent", "one_tile_per_pair"])
+def gemm2(request, dev):
+    """Both variants of the 2-CTA kernel: persistent with two TMEM accumulator stages (persist_tiles = 1: always),
+    and one tile per pair with two CTAs per SM (persist_tiles = 1e6: never persistent)."""
     from rag_gesture_b200 import ops
-    ops.set_gemm_kernel(2)
+    ops.set_gemm_kernel(2, 0, request.param)
     yield ops
-    ops.set_gemm_kernel(0)
+    ops.set_gemm_kernel(0, 0, 296)
 
 
 @pytest.mark.parametrize("M,N,K", SHAPES2)
