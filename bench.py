@@ -266,6 +266,50 @@ def run_b200(args):
     if args.precision != "fp32":
         roof = gemm_chain_roofline(arch, [B, E], dev, flush, tc_sus, roof, args.steps)
     knn = knn_bench(args, dev, rank, world, hbm_peak, tc_sus, peak_src, flush)
+    if rank == 0 and world == 1 and args.cpu_seconds > 0:
+        knn["cpu_baseline"] = knn_cpu_baselines(n_full=args.knn_n, seconds=min(10.0, args.cpu_seconds))
+
+    # ---- configs[0]: one clip, plain 50-step DDIM, no retrieval (latency; CUDA-graph replay of the chain) ----
+    def plain_b1():
+        kw1 = arch.model.get_precompute_condition(device=dev, text=batch["word"][:1].to(dev), audio=batch["audio"][:1].to(dev),
+                                                  speaker_ids=batch["speaker_ids"][:1].to(dev), re_dict=1)
+        qm1 = torch.ones(1, C.N_TOKENS, device=dev)
+        qm1[:, C.QUERY_MASK_ZERO_ROWS] = 0
+        kw1 = dict(xf_out=kw1["xf_out"], re_dict=None, sample_idx=None, query_mask={c: qm1 for c in C.CONDS},
+                   motion_mask=S.motion_mask(1).to(dev))
+        arch.model._state_cache = (None, None)
+        return arch.diffusion_test.ddim_sample_loop(arch.model, (1, C.N_TOKENS, C.LATENT_DIM), clip_denoised=False,
+                                                    model_kwargs=kw1, eta=0)
+    t_b1 = timed(plain_b1, 5, 3) / 5
+    configs0 = {"workload": "configs[0]: 1 clip, plain 50-step DDIM, no retrieval (condition encode + K6 state + loop)",
+                "seconds_per_clip": round(t_b1, 5), "clip_steps_per_sec": round(STEPS / t_b1, 1),
+                "us_per_evaluation": round(1e6 * t_b1 / STEPS, 1)}
+
+    # ---- the other precision tiers on the same device-resident batches (value only, 2 batches) ----------------
+    tiers = {}
+    if rank == 0 and world == 1:
+        for tier in ("bf16x3", "fp32"):
+            if tier == args.precision:
+                continue
+            cfg_t = C.model_cfg()
+            cfg_t["use_retrieval_for_test"] = True
+            cfg_t["model"]["precision"] = {"bf16": _lib.PREC_BF16, "bf16x3": _lib.PREC_BF16X3, "fp32": _lib.PREC_FP32}[tier]
+            arch_t = R.build_architecture(cfg_t, database=arch.model.database.dataset)
+            arch_t.model.load_state_dict(S.synthetic_state_dict(0), strict=False)
+            arch_t = arch_t.to(dev).eval()
+            gbs_t = [arch_t.prepare(**dict(batch, inference_kwargs=infer_kwargs())) for _ in range(2)]
+            arch_t.run_many(gbs_t)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            arch_t.run_many(gbs_t)
+            b.record()
+            torch.cuda.synchronize()
+            tt = a.elapsed_time(b) / 1e3
+            tiers[tier] = {"value": round(2 * gbs_t[0].clip_steps(STEPS) / tt, 1), "unit": UNIT, "ms_per_step": round(1e3 * tt / 2, 2),
+                           "parity": "rel-L2 <= 1e-3 vs reference (tests)", "batches": 2}
+            del arch_t, gbs_t
+            torch.cuda.empty_cache()
 
     if rank == 0:
         line = {
@@ -294,6 +338,7 @@ def run_b200(args):
                              "api": "MotionDiffusion.forward(**host_batch), one synchronous call per step"}},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
             "cpu_baseline": cpu_baseline(sample_seconds=args.cpu_seconds), "knn": knn,
+            "configs0": configs0, "tiers": tiers,
             "gflop_per_clip_step": GFLOP_PER_CLIP_STEP,
             "achieved_tflops_loop": round(value * GFLOP_PER_CLIP_STEP / 1e3 / world, 2),
         }
@@ -583,39 +628,183 @@ def cpu_reference_sample(n_clips, n_exemplars, n_steps, threads):
     return (n_clips + n_exemplars) * n_steps, time.perf_counter() - t0
 
 
+class _ShapeOnlyCodec(torch.nn.Module):
+    """Stand-in for the reference's GestureRepEncoder (needs VAE yaml + checkpoints that are not in the repo);
+    the denoiser and the sampling loops never call it (tests/golden/make_golden.py uses the same one)."""
+
+    def __init__(self, vae_cfg, body_part_cat_axis="time"):
+        super().__init__()
+        self.vae_latent_dim = vae_cfg["latent_dim"]
+        self.body_part_cat_axis = body_part_cat_axis
+
+
+_REF = {}
+
+
+def reference_modules():
+    """The UNMODIFIED reference (oracle/refshim.py: /root/reference here, oracle/_ref on the GPU box), its
+    ReGestureTransformer with the synthetic weights and its SpacedDiffusion; None when it is not available."""
+    if "ns" in _REF:
+        return _REF["ns"]
+    _REF["ns"] = None
+    try:
+        from oracle import refshim
+        from rag_gesture_b200 import config as C
+        from rag_gesture_b200 import synthetic as S
+        if not refshim.available():
+            return None
+        ns = refshim.load()
+        ns.dt.GestureRepEncoder = _ShapeOnlyCodec
+        cfg = C.denoiser_cfg()
+        cfg.pop("type")
+        model = ns.rg.ReGestureTransformer(**cfg, database=None, use_retrieval_for_test=False)
+        missing, unexpected = model.load_state_dict(S.synthetic_state_dict(0), strict=False)
+        assert not missing and not unexpected, (missing, unexpected)
+        ns.model, ns.diffusion = model.eval(), ns.arch.build_diffusion(C.diffusion_test_cfg())
+        _REF["ns"] = ns
+    except Exception as e:                                  # noqa: BLE001  (report, then fall back to the port)
+        sys.stderr.write(f"bench.py: reference not importable ({type(e).__name__}: {e}); using the oracle port\n")
+    return _REF["ns"]
+
+
+def reference_sample(n_clips, n_exemplars, threads, plain=False):
+    """Bounded sample of configs[1] executed by the reference's OWN code (gaussian_diffusion.py:1137
+    ddim_reverse_sample_loop once per exemplar at B=1, as diffusion_architecture.py:323-354 does, then :1233
+    ddim_guided_sample_loop with decreasing_till_25 insertion guidance -- autograd gradient steps included), all
+    50 levels.  plain=True: configs[0], ddim_sample_loop at B=n_clips.  Returns (clip_steps, seconds)."""
+    from rag_gesture_b200 import config as C
+    from rag_gesture_b200 import synthetic as S
+    ns = reference_modules()
+    model, diff = ns.model, ns.diffusion
+    torch.set_num_threads(threads)
+    T, D, n = C.N_TOKENS, C.LATENT_DIM, C.N_CHUNKS
+
+    def kwargs(cond, B):
+        pc = model.get_precompute_condition(device="cpu", text=cond["word"], audio=cond["audio"],
+                                            speaker_ids=cond["speaker_ids"], re_dict=1)
+        return dict(xf_out=pc["xf_out"], re_dict=None, query_mask=S.query_masks(B), motion_mask=S.motion_mask(B),
+                    sample_idx=None)
+    cond = S.synthetic_conditions(n_clips + n_exemplars, seed=5)
+    t0 = time.perf_counter()
+    cb = {k: v[:n_clips] for k, v in cond.items()}
+    if plain:
+        with torch.no_grad():
+            diff.ddim_sample_loop(model, (n_clips, T, D), clip_denoised=False, model_kwargs=kwargs(cb, n_clips), eta=0)
+        return n_clips * STEPS, time.perf_counter() - t0
+    inv_list = torch.zeros(STEPS, n_clips, T, D)
+    with torch.no_grad():
+        for e in range(n_exemplars):
+            c1 = {k: v[n_clips + e:n_clips + e + 1] for k, v in cond.items()}
+            inv = diff.ddim_reverse_sample_loop(model, start_img=S.synthetic_latents(1, seed=6 + e, scale=0.5),
+                                                clip_denoised=False, model_kwargs=kwargs(c1, 1), eta=0,
+                                                return_all_timesteps=True)
+            inv = torch.cat(inv, 0)
+            b = e % n_clips
+            inv_list[:, b, 2:5] = inv[:, 4:7]
+            inv_list[:, b, n + 3:n + 6] = inv[:, n + 5:n + 8]
+        kw = kwargs(cb, n_clips)
+    start = torch.randn(n_clips, T, D)
+    nz = inv_list[-1] != 0
+    start[nz] = inv_list[-1][nz]
+    with torch.inference_mode(False):
+        diff.ddim_guided_sample_loop(model, (n_clips, T, D), noise=start, clip_denoised=False, model_kwargs=kw, eta=0,
+                                     in_seq=None, guidance_iters=list(GUIDANCE), inverted_latent_list=inv_list,
+                                     guidance_lr=0.1)
+    return (n_clips + n_exemplars) * STEPS, time.perf_counter() - t0
+
+
+def cpu_sample(n_clips, n_exemplars, threads):
+    """(clip_steps, seconds, kind): the unmodified reference when it is available, else the oracle port."""
+    if reference_modules() is not None:
+        return reference_sample(n_clips, n_exemplars, threads) + ("reference",)
+    return cpu_reference_sample(n_clips, n_exemplars, STEPS, threads) + ("port",)
+
+
+def _cpu_sample_text(kind, n_clips, n_exemplars, cs, dt, threads):
+    what = ("the UNMODIFIED reference (mogen.models: ReGestureTransformer + SpacedDiffusion.ddim_reverse_sample_loop per "
+            "exemplar at B=1 + ddim_guided_sample_loop with autograd insertion guidance)" if kind == "reference"
+            else "oracle port of the reference algorithm")
+    return (f"{what}: {n_exemplars} exemplars inverted at B=1 + {n_clips} clips guided, all 50 DDIM levels = {cs} "
+            f"clip-steps in {dt:.1f} s, torch CPU fp32, {threads} threads")
+
+
+def cpu_sizes(sample_seconds, threads):
+    """Clips / exemplars of the bounded sample: the B : E ratio of configs[1] (64 : 96), scaled so that all 50
+    levels take about `sample_seconds`."""
+    cs, dt, _ = cpu_sample(2, 3, threads)                       # calibration = warm-up: 250 clip-steps
+    rate = cs / dt
+    units = max(1, min(8, int(rate * sample_seconds / STEPS / 5)))      # 1 unit = 2 clips + 3 exemplars
+    return 2 * units, 3 * units
+
+
 def cpu_baseline(sample_seconds=15.0):
     threads = os.cpu_count() or 1
-    cpu_reference_sample(2, 1, 1, threads)                      # warm-up (allocations, weights)
-    cs, dt = cpu_reference_sample(8, 4, 1, threads)             # calibrate: 12 clip-steps
-    n_steps = max(1, min(STEPS, int(sample_seconds / max(dt, 1e-3))))
-    cs, dt = cpu_reference_sample(8, 4, n_steps, threads)
-    return {"value": round(cs / dt, 2), "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"oracle port of the reference algorithm: 4 exemplars inverted at B=1 + 8 clips guided, "
-                      f"{n_steps} of 50 DDIM levels each = {cs} clip-steps in {dt:.1f} s"}
+    nc, ne = cpu_sizes(sample_seconds, threads)
+    cs, dt, kind = cpu_sample(nc, ne, threads)
+    out = {"value": round(cs / dt, 2), "unit": UNIT, "cores": threads, "kind": kind,
+           "sample": _cpu_sample_text(kind, nc, ne, cs, dt, threads)}
+    if kind == "reference":                                     # configs[0] on the host cores, next to the GPU latency
+        cs0, dt0 = reference_sample(1, 0, threads, plain=True)
+        out["configs0_plain_ddim_b1"] = {"seconds": round(dt0, 3), "clip_steps_per_sec": round(cs0 / dt0, 2)}
+    return out
+
+
+def knn_cpu_baselines(n_full=1_000_000, dim=768, k=8, seconds=10.0):
+    """(i) the reference's own ranking, sort_sidx_by_textsimilarity (rag/utils.py:86-132), on a
+    10k-entry slice (entries/s); (ii) the strong baseline, fp32 torch.mm + torch.topk(k=8) over the full 1M x 768
+    database on all host cores (queries/s), on a bounded number of queries."""
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    out = {"cores": threads}
+    g = torch.Generator().manual_seed(42)
+    ns = reference_modules()
+    n_slice, Td = 10_000, 32
+    feats = torch.randn(n_slice, Td, dim, generator=g)
+    q = torch.randn(Td, dim, generator=g)
+    if ns is not None:
+        cache = {f"e{i}": [feats[i], 0] for i in range(n_slice)}
+        names = list(cache.keys())
+        t0 = time.perf_counter()
+        order = ns.rag_utils.sort_sidx_by_textsimilarity(names, q, cache)
+        dt = time.perf_counter() - t0
+        out["text_similarity_reference"] = {"entries_per_sec": round(n_slice / dt, 1), "entries": n_slice, "tokens": Td,
+                                            "seconds": round(dt, 2), "kind": "reference",
+                                            "fn": "sort_sidx_by_textsimilarity (rag/utils.py:86)", "top": order[0]}
+    db = torch.nn.functional.normalize(torch.randn(n_full, dim, generator=g), dim=1)
+    qs = torch.nn.functional.normalize(torch.randn(64, dim, generator=g), dim=1)
+    torch.topk(qs[:8] @ db.T, k, dim=1)                         # warm-up
+    t0, nq = time.perf_counter(), 0
+    while time.perf_counter() - t0 < seconds and nq < 4096:
+        torch.topk(qs @ db.T, k, dim=1)
+        nq += qs.shape[0]
+    dt = time.perf_counter() - t0
+    out["mm_topk_fp32"] = {"queries_per_sec": round(nq / dt, 1), "n": n_full, "dim": dim, "k": k, "queries": nq,
+                           "seconds": round(dt, 2), "kind": "torch.mm + torch.topk, fp32, all host cores"}
+    return out
 
 
 def run_reference(args):
+    """`--impl reference`: the reference's own CPU implementation of the path on the host cores, same metric and
+    config; each step is a bounded sample of the configs[1] workload (all 50 levels of both loops)."""
     rank, world, _ = dist_env()
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    for _ in range(args.warmup):
-        cpu_reference_sample(2, 1, 1, threads)
-    cs_tot, t_tot = 0, 0.0
-    cs1, dt1 = cpu_reference_sample(8, 4, 1, threads)
-    n_steps = max(1, min(STEPS, int(args.cpu_seconds / max(dt1, 1e-3) / max(1, args.steps))))
+    nc, ne = cpu_sizes(args.cpu_seconds / max(1, args.steps), threads)
+    for _ in range(min(args.warmup, 1)):                        # the calibration run above already warmed up
+        cpu_sample(1, 1, threads)
+    cs_tot, t_tot, kind = 0, 0.0, "port"
     for _ in range(args.steps):
-        cs, dt = cpu_reference_sample(8, 4, n_steps, threads)
+        cs, dt, kind = cpu_sample(nc, ne, threads)
         cs_tot, t_tot = cs_tot + cs, t_tot + dt
     v = cs_tot / t_tot
-    sample = (f"per step: 4 exemplars inverted at B=1 + 8 clips guided, {n_steps} of 50 DDIM levels "
-              f"(oracle port of the reference algorithm, torch CPU fp32, {threads} threads)")
+    sample = "per step: " + _cpu_sample_text(kind, nc, ne, cs_tot // args.steps, t_tot / args.steps, threads)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": round(v, 2), "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * t_tot / args.steps, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "configs[1] guided DDIM (bounded sample of the same workload on host cores)"},
-        "cpu_baseline": {"value": round(v, 2), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": round(v, 2), "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": round(v, 2), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}), flush=True)
 
