@@ -561,6 +561,24 @@ def knn_bench(args, dev, rank, world, hbm_peak, tc_peak, peak_src, flush):
                        uncertified=index.last_uncertified)
             uncert += index.last_uncertified
         out[f"q{Q}"] = row
+    # the sharded result checked on the hardware it ran on: every rank all-gathers the shards (3 GB at 1M rows),
+    # runs the UNSHARDED exact scan for a query sample and compares indices and scores bit for bit
+    same = None
+    if world > 1 and n_total % world == 0:
+        from rag_gesture_b200.parallel import knn_topk
+        full = torch.empty(n_total, dim, device=dev)
+        dist.all_gather_into_tensor(full, db)
+        ok = True
+        for Q in (8, 64):
+            qv = torch.nn.functional.normalize(torch.randn(Q, dim, device=dev, generator=torch.Generator(device=dev).manual_seed(44)), dim=1)
+            si, ss = sharded_knn(db, qv, k, n_total, index=index)
+            ui, us = knn_topk(full, qv, k)
+            ok = ok and torch.equal(si, ui) and torch.equal(ss, us)
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        same = bool(flag.item())
+        del full
+        torch.cuda.empty_cache()
     # the kernels alone (what the rooflines are about): CUDA events around the launch only
     lib = _lib.load()
     q8 = torch.nn.functional.normalize(torch.randn(8, dim, device=dev), dim=1)
@@ -576,7 +594,7 @@ def knn_bench(args, dev, rank, world, hbm_peak, tc_peak, peak_src, flush):
     head = out["q4096"]
     index.close()
     return {"queries_per_sec": head["queries_per_sec"], "n": n_total, "dim": dim, "k": k, "q": 4096, "ms": head["ms"],
-            "uncertified_queries": uncert, "sweep": out,
+            "uncertified_queries": uncert, "sharded_equals_unsharded": same, "sweep": out,
             "roofline": {"bound": "hbm", "kernel": "knn_scan768_kernel<8> alone (exact fp32, 8 queries, 1 pass over the shard)",
                          "launch_ms": round(ms.value, 3), "achieved": round(scan_gbs, 1), "peak": hbm_peak, "unit": "GB/s",
                          "frac": round(scan_gbs / hbm_peak, 4), "peak_source": peak_src,

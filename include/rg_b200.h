@@ -261,6 +261,10 @@ int rg_probe_knn_scan(const float* db, int64_t n, int dim, const float* queries,
 /* Merge `parts` per-shard candidate lists [parts,q,k] (as all-gathered) into the global top-k. */
 int rg_knn_merge(const int64_t* idx_parts, const float* score_parts, int parts, int q, int k,
                  int64_t* out_idx, float* out_score, void* stream);
+/* The same merge over the packed buffer that parallel.sharded_knn all-gathers in ONE collective: per rank one
+ * block of part_stride_bytes (>= 12*q*k, multiple of 8) holding [idx int64 q*k | score fp32 q*k]. */
+int rg_knn_merge_packed(const void* packed, int64_t part_stride_bytes, int parts, int q, int k,
+                        int64_t* out_idx, float* out_score, void* stream);
 
 /* ---- large query batches: tensor-core similarity + certified over-selection (knn_tc.cu) ----
  * Same contract and bit-identical results as rg_knn_topk, for the Q = 4096 sweep of configs[3] where one exact

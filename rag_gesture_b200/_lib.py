@@ -58,6 +58,7 @@ SIGNATURES = {
     "rg_knn_topk": (_I, [_P, _L, _I, _P, _I, _I, _L, _P, _P, _P]),
     "rg_probe_knn_scan": (_I, [_P, _L, _I, _P, _I, _I, _I, _P, _L, C.POINTER(C.c_float), _P]),
     "rg_knn_merge": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
+    "rg_knn_merge_packed": (_I, [_P, _L, _I, _I, _I, _P, _P, _P]),
     "rg_knn_index_create": (_I, [_P, _L, _I, C.POINTER(_P), _P]),
     "rg_knn_index_destroy": (_I, [_P]),
     "rg_knn_topk_tc": (_I, [_P, _P, _P, _I, _I, _L, _P, _P, C.POINTER(C.c_int32), _P]),

@@ -361,10 +361,18 @@ class GuidedPipeline:
     denoising loops of batch i run, a worker thread executes stage 1 of batch i+1 -- H2D of the pinned host
     batch, codec encode, discourse retrieval with its text-similarity ranking, exemplar fetch and encode -- on
     a side stream, and the inversion loop of batch i+1's exemplars is fused level by level with the guided loop
-    of batch i (MotionDiffusion.run_pass).  Results are identical to sequential forward() calls: the worker never touches the
-    denoiser handle (the clip pre-projection is deferred to the main thread), it alone draws from the CPU
-    generator (codec rsample noise) and the main thread alone from the CUDA generator (sampler noise), so the
-    draw order of every generator is the sequential one.
+    of batch i (MotionDiffusion.run_pass).  The worker never touches the denoiser handle (the clip
+    pre-projection is deferred to the main thread).
+
+    Random streams.  The sampler noise is drawn by the main thread from the default CUDA generator.  The codec's
+    rsample noise is drawn by the worker: a codec that draws from the CPU generator (SyntheticGestureCodec) is
+    the only user of that generator, so results are bit-identical to sequential forward() calls.  The
+    TransformerVAE codec (vae.GestureRepEncoder) draws ON THE DEVICE; sharing the default CUDA generator between
+    the two threads would make the interleaving depend on thread timing, so for the duration of run() the codec
+    gets its own device generator (`codec.generator`, seeded from torch.cuda.initial_seed() unless the caller
+    installed one).  Results are then reproducible run to run, and equal to sequential forward() calls made with
+    the same `codec.generator` installed -- but NOT to sequential calls that draw codec and sampler noise from
+    the one default generator, as the reference does.
 
         for results in GuidedPipeline(model).run(loader): ...
     """
@@ -379,6 +387,13 @@ class GuidedPipeline:
         # wait one switch interval each time (default 5 ms).  The loops are one C call per pass
         # (rg_run_levels), so a moderate interval is enough; very short ones (50 us) make both threads thrash.
         self.switch_interval = 5e-4
+
+    @staticmethod
+    def codec_generator(device, seed=None):
+        """The device generator GuidedPipeline gives a device-drawing codec (see the class docstring)."""
+        g = torch.Generator(device=device)
+        g.manual_seed((torch.cuda.initial_seed() if seed is None else int(seed)) ^ 0x5DEECE66D)
+        return g
 
     def _stage1(self, kwargs, main):
         # No wait on the main stream here: the consumer may be a whole pass ahead of the device, and the
@@ -402,10 +417,16 @@ class GuidedPipeline:
             return
         old_interval = sys.getswitchinterval()
         sys.setswitchinterval(min(old_interval, self.switch_interval))
+        codec = self.arch.model.gesture_rep_encoder
+        own_gen = getattr(codec, "draws_on_device", False) and getattr(codec, "generator", None) is None
+        if own_gen:
+            codec.generator = self.codec_generator(self.device)
         try:
             yield from self._run(it, first, main)
         finally:
             sys.setswitchinterval(old_interval)
+            if own_gen:
+                codec.generator = None
 
     def _run(self, it, first, main):
         from concurrent.futures import ThreadPoolExecutor

@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <map>
 #include <string>
 #include <vector>
@@ -17,7 +18,7 @@
 
 // ---------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
-static long long g_launches = 0;
+static std::atomic<long long> g_launches{0};     // the pipeline's worker thread launches concurrently
 
 int rg_fail(const char* fmt, ...) {
     va_list ap;
@@ -28,15 +29,15 @@ int rg_fail(const char* fmt, ...) {
 }
 void rg_count_launch(int n) { g_launches += n; }
 void rg_keep_mempool() {
-    static int done_for = -1;
+    static std::atomic<unsigned long long> done_mask{0};      // one bit per device
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev == done_for) return;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || (done_mask.load() >> dev & 1)) return;
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
         unsigned long long keep = ~0ull;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
-    done_for = dev;
+    done_mask.fetch_or(1ull << dev);
 }
 
 #define CU(expr)                                                                              \
@@ -799,7 +800,7 @@ static int run_eval(rg_model* m, const float* x, int B, const float* ss, long lo
             e = cudaStreamEndCapture(m->cap_st, &graph);
         }
         hit->launches = g_launches - l0;
-        g_launches = l0;                            // nothing ran yet
+        g_launches -= hit->launches;                // nothing ran yet (other threads may have counted meanwhile)
         if (rc == 0 && e == cudaSuccess && graph) e = cudaGraphInstantiate(&hit->exec, graph, 0);
         if (graph) cudaGraphDestroy(graph);
         if (rc != 0 || e != cudaSuccess || !hit->exec) {   // capture not possible here: stay on direct launches

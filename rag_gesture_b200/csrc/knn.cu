@@ -276,9 +276,12 @@ static cudaError_t launch_scan768(const float* db, long long n, const float* que
     return cudaGetLastError();
 }
 
-// one warp per query: merge parts*k candidates
-__global__ void __launch_bounds__(256) knn_merge_kernel(const long long* __restrict__ idx_parts,
-                                                       const float* __restrict__ score_parts,
+// one warp per query: merge parts*k candidates.  Part p's lists start p * part_stride BYTES after the base pointers
+// (two separate [parts,Q,k] arrays, or the packed all-gather buffer of parallel.sharded_knn: per rank one block
+// [idx int64 Q*k | score fp32 Q*k]).
+__global__ void __launch_bounds__(256) knn_merge_kernel(const char* __restrict__ idx_parts,
+                                                       const char* __restrict__ score_parts,
+                                                       long long idx_stride, long long score_stride,
                                                        int parts, int q_total, int k, long long idx_base,
                                                        long long* __restrict__ out_idx,
                                                        float* __restrict__ out_score) {
@@ -288,10 +291,11 @@ __global__ void __launch_bounds__(256) knn_merge_kernel(const long long* __restr
     float bs = -INFINITY;
     long long bi = IDX_NONE;
     for (int p = 0; p < parts; ++p) {
-        const long long base = ((long long)p * q_total + q) * k;
+        const long long* ip = reinterpret_cast<const long long*>(idx_parts + p * idx_stride) + (long long)q * k;
+        const float* sp = reinterpret_cast<const float*>(score_parts + p * score_stride) + (long long)q * k;
         // read k candidates at once, then insert one by one (warp-uniform loop)
-        const long long cid = lane < k ? idx_parts[base + lane] : IDX_NONE;
-        const float cs = lane < k ? score_parts[base + lane] : -INFINITY;
+        const long long cid = lane < k ? ip[lane] : IDX_NONE;
+        const float cs = lane < k ? sp[lane] : -INFINITY;
         for (int j = 0; j < k; ++j) {
             const long long id = __shfl_sync(0xffffffffu, cid, j);
             const float s = __shfl_sync(0xffffffffu, cs, j);
@@ -325,7 +329,24 @@ extern "C" int rg_knn_merge(const int64_t* idx_parts, const float* score_parts, 
     if (k < 1 || k > 32) return rg_fail("rg_knn_merge: k must be in [1,32]");
     if (q <= 0) return 0;
     knn_merge_kernel<<<(q + KNN_WARPS - 1) / KNN_WARPS, 256, 0, (cudaStream_t)stream>>>(
-        (const long long*)idx_parts, score_parts, parts, q, k, 0, (long long*)out_idx, out_score);
+        (const char*)idx_parts, (const char*)score_parts, (long long)q * k * 8, (long long)q * k * 4, parts, q, k, 0,
+        (long long*)out_idx, out_score);
+    RG_CU(cudaGetLastError());
+    rg_count_launch(1);
+    return 0;
+}
+
+extern "C" int rg_knn_merge_packed(const void* packed, int64_t part_stride_bytes, int parts, int q, int k,
+                                   int64_t* out_idx, float* out_score, void* stream) {
+    if (k < 1 || k > 32) return rg_fail("rg_knn_merge_packed: k must be in [1,32]");
+    if (!packed || !out_idx || !out_score) return rg_fail("rg_knn_merge_packed: null argument");
+    if (part_stride_bytes < (int64_t)q * k * 12 || part_stride_bytes % 8)
+        return rg_fail("rg_knn_merge_packed: part stride %lld too small or not a multiple of 8", (long long)part_stride_bytes);
+    if (q <= 0) return 0;
+    const char* base = (const char*)packed;
+    knn_merge_kernel<<<(q + KNN_WARPS - 1) / KNN_WARPS, 256, 0, (cudaStream_t)stream>>>(
+        base, base + (long long)q * k * 8, part_stride_bytes, part_stride_bytes, parts, q, k, 0, (long long*)out_idx,
+        out_score);
     RG_CU(cudaGetLastError());
     rg_count_launch(1);
     return 0;
@@ -346,10 +367,15 @@ extern "C" int rg_knn_topk(const float* db, int64_t n, int dim, const float* que
     if (n < (long long)blocks * rows_per_iter) blocks = (int)((n + rows_per_iter - 1) / rows_per_iter);
     if (blocks < 1) blocks = 1;
     const long long rows_per_block = (n + blocks - 1) / blocks;
-    long long* part_idx = nullptr;
-    float* part_score = nullptr;
-    RG_CU(cudaMallocAsync((void**)&part_idx, (size_t)blocks * q * k * sizeof(long long), st));
-    RG_CU(cudaMallocAsync((void**)&part_score, (size_t)blocks * q * k * sizeof(float), st));
+    struct AsyncScratch {        // stream-ordered scratch, released on every exit path
+        cudaStream_t st; void* p = nullptr;
+        explicit AsyncScratch(cudaStream_t s) : st(s) {}
+        ~AsyncScratch() { if (p) cudaFreeAsync(p, st); }
+    } s_idx(st), s_score(st);
+    RG_CU(cudaMallocAsync(&s_idx.p, (size_t)blocks * q * k * sizeof(long long), st));
+    RG_CU(cudaMallocAsync(&s_score.p, (size_t)blocks * q * k * sizeof(float), st));
+    long long* part_idx = static_cast<long long*>(s_idx.p);
+    float* part_score = static_cast<float*>(s_score.p);
     const size_t smem = (size_t)KNN_QT * dim * sizeof(float) + (size_t)KNN_WARPS * KNN_QT * 32 * (sizeof(float) + sizeof(long long));
     if (!fast) RG_CU(cudaFuncSetAttribute(knn_scan_kernel<KNN_QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int q0 = 0; q0 < q;) {
@@ -368,12 +394,11 @@ extern "C" int rg_knn_topk(const float* db, int64_t n, int dim, const float* que
         }
         rg_count_launch(1);
     }
-    knn_merge_kernel<<<(q + KNN_WARPS - 1) / KNN_WARPS, 256, 0, st>>>(part_idx, part_score, blocks, q, k,
-                                                                      idx_base, (long long*)out_idx, out_score);
+    knn_merge_kernel<<<(q + KNN_WARPS - 1) / KNN_WARPS, 256, 0, st>>>(
+        (const char*)part_idx, (const char*)part_score, (long long)q * k * 8, (long long)q * k * 4, blocks, q, k, idx_base,
+        (long long*)out_idx, out_score);
     RG_CU(cudaGetLastError());
     rg_count_launch(1);
-    RG_CU(cudaFreeAsync(part_idx, st));
-    RG_CU(cudaFreeAsync(part_score, st));
     return 0;
 }
 

@@ -408,6 +408,7 @@ struct KnnIndex {
     uint32_t magic;
     long long n;
     int dim;
+    const float* db;        // the fp32 shard the index was built from (the exact re-score reads it)
     __nv_bfloat16* db16;
     float* dmax;
     CUtensorMap tmD;
@@ -436,11 +437,14 @@ cudaError_t launch_tc_scan(const KnnIndex* ix, const __nv_bfloat16* q16, int q, 
     CUtensorMap tmQ;
     cudaError_t e = rg_make_tensor_map(&tmQ, q16, q, ix->dim, ix->dim, TQ);
     if (e != cudaSuccess) return e;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static bool attr_done[64] = {};              // function attributes are per device
+    int dev = 0;
+    e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
         e = cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        if (dev >= 0 && dev < 64) attr_done[dev] = true;
     }
     KnnTcParams p;
     p.n_rows = (int)ix->n; p.q_total = q; p.nkb = ix->dim / BK;
@@ -474,7 +478,7 @@ extern "C" int rg_knn_index_create(const float* db, int64_t n, int dim, void** i
     if (dim < BK || dim % BK) return rg_fail("rg_knn_index_create: dim must be a multiple of 64");
     cudaStream_t st = (cudaStream_t)stream;
     KnnIndex* ix = new KnnIndex();
-    ix->magic = KNN_MAGIC; ix->n = n; ix->dim = dim; ix->db16 = nullptr; ix->dmax = nullptr;
+    ix->magic = KNN_MAGIC; ix->n = n; ix->dim = dim; ix->db = db; ix->db16 = nullptr; ix->dmax = nullptr;
     cudaError_t e = cudaMalloc((void**)&ix->db16, (size_t)n * dim * 2);
     if (e == cudaSuccess) e = cudaMalloc((void**)&ix->dmax, sizeof(float));
     if (e == cudaSuccess) e = cudaMemsetAsync(ix->dmax, 0, sizeof(float), st);
@@ -508,6 +512,7 @@ extern "C" int rg_knn_topk_tc(void* index, const float* db, const float* queries
     KnnIndex* ix = reinterpret_cast<KnnIndex*>(index);
     if (!ix || ix->magic != KNN_MAGIC) return rg_fail("rg_knn_topk_tc: not an index handle");
     if (!db || !queries || !out_idx || !out_score) return rg_fail("rg_knn_topk_tc: null argument");
+    if (db != ix->db) return rg_fail("rg_knn_topk_tc: db is not the shard this index was built from");
     if (k < 1 || k > 32) return rg_fail("rg_knn_topk_tc: k must be in [1,32]");
     if (n_uncertified) *n_uncertified = 0;
     if (q <= 0) return 0;
@@ -532,11 +537,9 @@ extern "C" int rg_knn_topk_tc(void* index, const float* db, const float* queries
     // fp32 accumulation error of both sums grows with the reduction length
     const float c_eps = (C_EPS_BF16 + 2.5e-7f * (float)dim) * 1.01f;
     const size_t fsm = (size_t)ncp * 8;
-    static size_t fsm_set = 0;
-    if (fsm > 48 * 1024 && fsm > fsm_set) {
+    // per-device function attribute: set whenever it is needed (cheap, and correct on every device of the process)
+    if (fsm > 48 * 1024)
         RG_CU(cudaFuncSetAttribute(knn_tc_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
-        fsm_set = fsm;
-    }
     knn_tc_finish_kernel<<<q, 256, fsm, st>>>(db, dim, queries, cand_score, cand_idx, pl.chunks, ncp, k, idx_base,
                                                ix->dmax, c_eps, (long long*)out_idx, out_score, fail, fail + 1);
     RG_CU(cudaGetLastError());

@@ -170,9 +170,22 @@ class DenoiserEngine:
                                               _lib.ptr(state), _lib.ptr(samples_out), _lib.ptr(x0), _lib.stream_ptr()))
         return xj
 
+    @staticmethod
+    def _f32(*tensors, like=None):
+        """The kernels read raw fp32: refuse other dtypes / layouts / sizes instead of reading out of bounds."""
+        for t in tensors:
+            if t is None:
+                continue
+            _lib.require_cuda(t)
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError(f"rg_b200: expected a contiguous float32 CUDA tensor, got {t.dtype}, contiguous={t.is_contiguous()}")
+            if like is not None and t.numel() != like.numel():
+                raise ValueError(f"rg_b200: tensor of {t.numel()} elements where {like.numel()} are expected")
+
     def ddim_update(self, x, x0, step_idx, direction, out=None):
         if out is None:
             out = torch.empty_like(x)
+        self._f32(x, x0, out, like=x)
         with torch.cuda.device(x.device):
             _lib.check(self.lib.rg_ddim_update(self._h, _lib.ptr(x), _lib.ptr(x0), int(step_idx),
                                                int(direction), _lib.ptr(out), x.numel(),
@@ -182,6 +195,7 @@ class DenoiserEngine:
     def blend_in_seq(self, x, in_seq, noise, step_idx, out=None):
         if out is None:
             out = torch.empty_like(x)
+        self._f32(x, in_seq, noise, out, like=x)
         rows = x.numel() // self.latent_dim
         with torch.cuda.device(x.device):
             _lib.check(self.lib.rg_blend_in_seq(self._h, _lib.ptr(x), _lib.ptr(in_seq),
@@ -190,6 +204,7 @@ class DenoiserEngine:
         return out
 
     def guidance_steps(self, x, in_seq, iters, lr, numel=None):
+        self._f32(x, in_seq, like=x)
         rows = x.numel() // self.latent_dim
         with torch.cuda.device(x.device):
             _lib.check(self.lib.rg_guidance_steps(self._h, _lib.ptr(x), _lib.ptr(in_seq), rows,

@@ -96,12 +96,32 @@ class LongformSynthesizer:
     def __init__(self, arch, window=CFG.MAX_SEQ_LEN, overlap=15, fps=CFG.MOTION_FPS):
         self.arch, self.window, self.overlap, self.fps = arch, window, overlap, fps
 
+    @staticmethod
+    def _window_names(batch, cidx):
+        """Every window must retrieve its own exemplars: RetrievalDatabase.retrieve caches by sample_name, and
+        the reference renames each chunk ('/0' -> '/{cidx}', tools/longform_synthesis.py:347).  Applied here so a
+        window_fn that returns the stream's name for every window cannot silently reuse window 0's exemplars."""
+        names = batch.get("sample_name")
+        if names is None:
+            return batch
+        single = isinstance(names, str)
+        out = []
+        for nm in ([names] if single else list(names)):
+            head, sep, tail = str(nm).rpartition("/")
+            out.append(f"{head}/{cidx}" if sep and tail.isdigit() else f"{nm}/{cidx}")
+        batch["sample_name"] = out[0] if single else out
+        return batch
+
     def run(self, n_frames, window_fn, inference_kwargs, batch_inversions=True):
+        """batch_inversions=True prepares every window (codec encodes, retrieval) and inverts all exemplars in
+        one batched reverse loop BEFORE the first start_noise is drawn; the reference interleaves encode /
+        start_noise / sampling window by window, so same-seed runs of the two modes draw different noise (each
+        mode is reproducible on its own; batch_inversions=False keeps the reference's order)."""
         starts = chunk_starts(n_frames, self.window, self.overlap)
         arch = self.arch
         prepared = []
         for cidx, f0 in enumerate(starts):
-            batch = dict(window_fn(cidx, f0, f0 + self.window))
+            batch = self._window_names(dict(window_fn(cidx, f0, f0 + self.window)), cidx)
             ik = dict(inference_kwargs, use_prev_latent=True, prev_latent=None)
             batch["inference_kwargs"] = ik
             if not batch_inversions:

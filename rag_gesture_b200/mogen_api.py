@@ -304,11 +304,19 @@ class ReGestureTransformer(nn.Module):
 
     # -- engine lifetime: rebuilt when weights move or change (load_state_dict, .to(), .cuda()) ------
     def _weights_key(self):
-        """Cheap fingerprint of the parameter set: bumped by load_state_dict / .to() / .cuda() (hooks
-        below) plus identity+version of the first and last tensors (in-place edits of the others are
-        not detected: call `invalidate_engine()` after such edits)."""
-        a, b = self.joint_embed.weight, self.out.weight
-        return (self._epoch, a.data_ptr(), a._version, b.data_ptr(), b._version)
+        """Fingerprint of the parameter set the packed device engine was built from: the epoch bumped by this
+        module's load_state_dict / .to() / .cuda() hooks plus the storage address and in-place version counter of
+        EVERY denoiser parameter and buffer (about 400 tensors, a few hundred microseconds).  A checkpoint loaded
+        through a parent module (MotionDiffusion.load_state_dict, mmcv load_checkpoint), a strict=False partial
+        load or an in-place edit of any tensor therefore rebuilds the engine.  (Edits that bypass the version
+        counter, e.g. through .data, still need `invalidate_engine()`.)"""
+        ptr = ver = 0
+        for name, t in self.state_dict(keep_vars=True).items():
+            if name.startswith(("gesture_rep_encoder.", "database.")):
+                continue
+            ptr = (ptr * 1000003 + t.data_ptr()) & 0xFFFFFFFFFFFFFFFF
+            ver += t._version
+        return (self._epoch, ptr, ver)
 
     def invalidate_engine(self):
         self._epoch += 1
@@ -336,9 +344,12 @@ class ReGestureTransformer(nn.Module):
                                           text_dim=self._text_dim, num_speakers=self.num_speakers,
                                           precision=self.precision, device=dev)
             self._engine_key, self._sched_key, self._state_cache = key, None, (None, None)
-        if diffusion is not None and self._sched_key != id(diffusion):
-            self._engine.set_schedule(diffusion.timestep_map, diffusion.coef_table())
-            self._sched_key = id(diffusion)
+        if diffusion is not None:
+            # keyed on the schedule's CONTENT (timestep map + alpha-bar table): id() can alias after garbage collection
+            skey = (tuple(int(t) for t in diffusion.timestep_map), diffusion.alphas_cumprod.tobytes())
+            if self._sched_key != skey:
+                self._engine.set_schedule(diffusion.timestep_map, diffusion.coef_table())
+                self._sched_key = skey
         return self._engine
 
     # -- conditions (raggesture.py:957-1013) -----------------------------------------------------------

@@ -37,17 +37,56 @@ def gather_clips(local, n_total, group=None):
     return torch.cat([o[: hi - lo] for o, (lo, hi) in zip(out, sizes)], 0)
 
 
-def _cuda_local_topk(db_shard, queries, k, idx_base):
+def _check_knn_inputs(db_shard, queries):
+    """The kernels read raw fp32 rows: refuse anything else instead of reading out of bounds."""
+    if db_shard.dtype != torch.float32 or queries.dtype != torch.float32:
+        raise ValueError(f"kNN operands must be float32 (got {db_shard.dtype}, {queries.dtype})")
+    if db_shard.dim() != 2 or queries.dim() != 2 or db_shard.shape[1] != queries.shape[1]:
+        raise ValueError(f"kNN operands must be [n, dim] and [Q, dim] (got {tuple(db_shard.shape)}, {tuple(queries.shape)})")
+
+
+def _out_pair(q, k, device, out):
+    if out is None:
+        return torch.empty(q, k, dtype=torch.int64, device=device), torch.empty(q, k, device=device)
+    idx, sc = out
+    assert idx.dtype == torch.int64 and sc.dtype == torch.float32 and idx.is_contiguous() and sc.is_contiguous()
+    assert tuple(idx.shape) == (q, k) == tuple(sc.shape)
+    return idx, sc
+
+
+def _cuda_local_topk(db_shard, queries, k, idx_base, out=None):
     from . import _lib
     lib = _lib.load()
     _lib.require_cuda(db_shard, queries)
+    _check_knn_inputs(db_shard, queries)
     q = queries.shape[0]
-    idx = torch.empty(q, k, dtype=torch.int64, device=queries.device)
-    sc = torch.empty(q, k, device=queries.device)
+    idx, sc = _out_pair(q, k, queries.device, out)
     with torch.cuda.device(queries.device):
         _lib.check(lib.rg_knn_topk(_lib.ptr(db_shard.contiguous()), db_shard.shape[0], db_shard.shape[1],
                                    _lib.ptr(queries.contiguous()), q, k, idx_base, _lib.ptr(idx),
                                    _lib.ptr(sc), _lib.stream_ptr()))
+    return idx, sc
+
+
+def packed_stride(q, k):
+    """Bytes per rank in the packed exchange buffer: [idx int64 q*k | score fp32 q*k], rounded up to 16."""
+    return (12 * q * k + 15) // 16 * 16
+
+
+def packed_views(buf, q, k):
+    """(idx int64 [q,k], score fp32 [q,k]) views into one rank's block of the packed buffer (uint8)."""
+    n = q * k
+    return buf[:8 * n].view(torch.int64).view(q, k), buf[8 * n:12 * n].view(torch.float32).view(q, k)
+
+
+def _cuda_merge_packed(recv, world, q, k):
+    from . import _lib
+    lib = _lib.load()
+    idx = torch.empty(q, k, dtype=torch.int64, device=recv.device)
+    sc = torch.empty(q, k, device=recv.device)
+    with torch.cuda.device(recv.device):
+        _lib.check(lib.rg_knn_merge_packed(_lib.ptr(recv), packed_stride(q, k), world, q, k, _lib.ptr(idx),
+                                           _lib.ptr(sc), _lib.stream_ptr()))
     return idx, sc
 
 
@@ -85,8 +124,9 @@ class KnnIndex:
             _lib.check(lib.rg_knn_index_create(_lib.ptr(self.db), self.db.shape[0], self.db.shape[1],
                                                ctypes.byref(self.handle), _lib.stream_ptr()))
 
-    def topk(self, queries, k, idx_base=0):
-        """(idx int64 [Q,k], score fp32 [Q,k]) == knn_topk(self.db, queries, k, idx_base), bit for bit."""
+    def topk(self, queries, k, idx_base=0, out=None):
+        """(idx int64 [Q,k], score fp32 [Q,k]) == knn_topk(self.db, queries, k, idx_base), bit for bit.
+        `out` = (idx, score) tensors to write into (the packed exchange buffer of sharded_knn)."""
         import ctypes
         _lib = self._lib
         _lib.require_cuda(queries)
@@ -97,9 +137,8 @@ class KnnIndex:
         queries = queries.to(torch.float32).contiguous()
         q = queries.shape[0]
         if q <= self.min_queries:
-            return _cuda_local_topk(self.db, queries, k, idx_base)
-        idx = torch.empty(q, k, dtype=torch.int64, device=queries.device)
-        sc = torch.empty(q, k, device=queries.device)
+            return _cuda_local_topk(self.db, queries, k, idx_base, out=out)
+        idx, sc = _out_pair(q, k, queries.device, out)
         nf = ctypes.c_int32(0)
         with torch.cuda.device(queries.device):
             _lib.check(_lib.load().rg_knn_topk_tc(self.handle, _lib.ptr(self.db), _lib.ptr(queries), q, k, idx_base,
@@ -127,19 +166,37 @@ def knn_topk(db, queries, k, idx_base=0, index=None):
     return _cuda_local_topk(db, queries, k, idx_base)
 
 
-def sharded_knn(db_shard, queries, k, n_total, group=None, local_topk=_cuda_local_topk, merge=_cuda_merge,
-                index=None):
+def sharded_knn(db_shard, queries, k, n_total, group=None, local_topk=None, merge=None, index=None):
     """Top-k over a row-sharded database.  `db_shard` holds rows shard_range(n_total, rank, world);
-    `queries` are replicated.  One all-gather of 12*Q*k bytes per rank, then the merge kernel.
-    `local_topk` / `merge` are injectable so the CPU (gloo) tests can exercise the exchange; `index`
-    (a KnnIndex of this rank's shard) selects the tensor-core local top-k for large query batches."""
+    `queries` are replicated.  Each rank writes its local top-k (global indices) straight into its block of a
+    packed buffer [idx int64 Q*k | score fp32 Q*k]; ONE all_gather_into_tensor (12*Q*k bytes per rank) moves
+    all of them, and the merge kernel (rg_knn_merge_packed) reads the gathered blocks in place.
+    `local_topk(db_shard, queries, k, idx_base)` / `merge(idx_parts, score_parts, k)` are injectable so the CPU
+    (gloo) tests can exercise the same exchange; `index` (a KnnIndex of this rank's shard) selects the
+    tensor-core local top-k for large query batches."""
     rank, world = _world(group)
     lo, _ = shard_range(n_total, rank, world)
-    idx, sc = index.topk(queries, k, lo) if index is not None else local_topk(db_shard, queries, k, lo)
+    q = queries.shape[0]
     if world == 1:
-        return idx, sc
-    idx_all = [torch.empty_like(idx) for _ in range(world)]
-    sc_all = [torch.empty_like(sc) for _ in range(world)]
-    dist.all_gather(idx_all, idx, group=group)
-    dist.all_gather(sc_all, sc, group=group)
-    return merge(torch.stack(idx_all, 0), torch.stack(sc_all, 0), k)
+        if index is not None:
+            return index.topk(queries, k, lo)
+        return (local_topk or _cuda_local_topk)(db_shard, queries, k, lo)
+    stride = packed_stride(q, k)
+    send = torch.zeros(stride, dtype=torch.uint8, device=queries.device)
+    idx, sc = packed_views(send, q, k)
+    if index is not None and local_topk is None and hasattr(index, "handle"):
+        index.topk(queries, k, lo, out=(idx, sc))
+    elif local_topk is None and index is None:
+        _cuda_local_topk(db_shard, queries, k, lo, out=(idx, sc))
+    else:                                       # injected stand-ins return fresh tensors
+        i, s = index.topk(queries, k, lo) if index is not None else local_topk(db_shard, queries, k, lo)
+        idx.copy_(i)
+        sc.copy_(s)
+    recv = torch.empty(world * stride, dtype=torch.uint8, device=queries.device)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    if merge is None and recv.is_cuda:
+        return _cuda_merge_packed(recv, world, q, k)
+    parts = [packed_views(recv[r * stride:(r + 1) * stride], q, k) for r in range(world)]
+    idx_parts = torch.stack([p[0] for p in parts], 0)
+    score_parts = torch.stack([p[1] for p in parts], 0)
+    return (merge or _cuda_merge)(idx_parts, score_parts, k)

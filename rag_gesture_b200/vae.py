@@ -201,7 +201,7 @@ class TransformerVAE(nn.Module):
         mu, raw = latent[:, 0:1], latent[:, 1:]
         scale = raw.exp().pow(0.5) if self.dist_type == "normal" else F.softplus(raw) + 1e-8
         if eps is None:                         # what Normal / MultivariateNormal .rsample() draw
-            eps = torch.empty(mu.shape, dtype=mu.dtype, device=mu.device).normal_()
+            eps = torch.empty(mu.shape, dtype=mu.dtype, device=mu.device).normal_(generator=getattr(self, "generator", None))
         return mu + scale * eps, Namespace(loc=mu, scale=scale)
 
     def encode_to_dist(self, features, lengths=None, eps=None):
@@ -245,6 +245,8 @@ class GestureRepEncoder(nn.Module):
     """diffusion_transformer.py:130-330: SMPL-X axis-angle body parts <-> [B, 4*n_chunks+3, D] latents with zero
     separator tokens (body_part_cat_axis="time") or concatenated along features (otherwise)."""
     PARTS = ("upper", "hands", "face", "lowertrans")      # order of the sampling draws in encode
+    draws_on_device = True      # rsample noise comes from a CUDA generator: `generator` (None = the default one)
+    generator = None
 
     def __init__(self, vae_cfg, body_part_cat_axis="time", vaes=None):
         super().__init__()
@@ -309,7 +311,12 @@ class GestureRepEncoder(nn.Module):
                motion_contact, motion_mask):
         feats = self._features(motion_upper, motion_lower, motion_face, motion_hands, motion_transl, motion_facial,
                                motion_contact)
-        z = {p: getattr(self, f"{p}_vae").encode_to_dist(feats[p])[0] for p in self.PARTS}
+        gen = getattr(self, "generator", None)
+        z = {}
+        for p in self.PARTS:                     # draw order upper, hands, face, lowertrans as in the reference
+            mu_shape = (feats[p].shape[0] * (feats[p].shape[1] // self.frame_chunk_size), 1, self.vae_latent_dim)
+            eps = torch.empty(mu_shape, device=feats[p].device).normal_(generator=gen) if gen is not None else None
+            z[p] = getattr(self, f"{p}_vae").encode_to_dist(feats[p], eps=eps)[0]
         return self._assemble(z, motion_mask)
 
     @torch.no_grad()
@@ -322,7 +329,8 @@ class GestureRepEncoder(nn.Module):
                                motion_contact)
         E, n = motion_upper.shape[0], motion_upper.shape[1] // self.frame_chunk_size
         dev, D = motion_upper.device, self.vae_latent_dim
-        eps = torch.stack([torch.stack([torch.empty(n, 1, D, device=dev).normal_() for _ in self.PARTS], 0)
+        gen = getattr(self, "generator", None)
+        eps = torch.stack([torch.stack([torch.empty(n, 1, D, device=dev).normal_(generator=gen) for _ in self.PARTS], 0)
                            for _ in range(E)], 0)                        # [E, 4, n, 1, D]
         z = {p: getattr(self, f"{p}_vae").encode_to_dist(feats[p], eps=eps[:, i].reshape(E * n, 1, D))[0]
              for i, p in enumerate(self.PARTS)}

@@ -73,3 +73,47 @@ def test_forward_with_transformer_vae_codec(mg, tmp_path):
     for k in a:
         assert bool(torch.isfinite(a[k]).all()), k
         assert torch.equal(a[k], b[k]), k
+
+
+def test_pipeline_with_vae_codec_is_reproducible_and_matches_sequential(mg, tmp_path):
+    """the VAE codec draws its rsample noise on the device.  GuidedPipeline gives it its own generator, so
+    (a) two pipeline runs with the same seeds agree bit for bit (no dependence on thread timing) and (b) they equal
+    sequential forward() calls made with the same codec generator installed."""
+    import rag_gesture_b200 as R
+    from rag_gesture_b200.architecture import GuidedPipeline
+    dev = torch.device("cuda:0")
+
+    def shapes_of(args):
+        return {k: tuple(v.shape) for k, v in TransformerVAE(args).state_dict().items()}
+    cfg = C.model_cfg()
+    cfg["model"]["vae_cfg"] = mg.write_vae_files(str(tmp_path), "a", 300, shapes_of, latent_dim=C.LATENT_DIM)
+    arch = R.build_architecture(cfg, database=None)
+    arch.model.load_state_dict(S.synthetic_state_dict(0), strict=False)
+    arch = arch.to(dev).eval()
+    codec = arch.model.gesture_rep_encoder
+    assert codec.draws_on_device and codec.generator is None
+    qs = S.SyntheticGestureDataset(8, seed=8)
+
+    def batches():
+        for ids in ([0, 2], [1], [3, 4, 5]):
+            b = S.collate([qs[i] for i in ids])
+            b["inference_kwargs"] = {}
+            yield b
+
+    def seed():
+        torch.manual_seed(3)
+        torch.cuda.manual_seed(4)
+
+    runs = []
+    for _ in range(2):
+        seed()
+        runs.append([r["prev_latentout"].cpu() for r in GuidedPipeline(arch).run(batches())])
+        assert codec.generator is None                      # restored after run()
+    assert all(torch.equal(a, b) for a, b in zip(*runs))
+    seed()
+    codec.generator = GuidedPipeline.codec_generator(dev)
+    try:
+        seq = [arch(**b)["prev_latentout"].cpu() for b in batches()]
+    finally:
+        codec.generator = None
+    assert len(seq) == 3 and all(torch.equal(a, b) for a, b in zip(seq, runs[0]))

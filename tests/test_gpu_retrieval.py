@@ -202,6 +202,35 @@ def test_knn_tc_sharded_merge(dev):
     assert torch.equal(mi, full_i) and torch.equal(ms, full_s)
 
 
+def test_knn_packed_merge_equals_unsharded(dev):
+    """The packed exchange layout of sharded_knn (per rank [idx int64 Q*k | score fp32 Q*k], local top-k written in
+    place, rg_knn_merge_packed reading the gathered blocks) == the unsharded exact scan; odd Q*k (stride padding)."""
+    from rag_gesture_b200.parallel import (KnnIndex, _cuda_local_topk, _cuda_merge_packed, knn_topk, packed_stride,
+                                           packed_views, shard_range)
+    g = torch.Generator().manual_seed(14)
+    db = torch.nn.functional.normalize(torch.randn(30011, 768, generator=g), dim=1).to(dev)
+    for Q, k, world in ((5, 3, 8), (200, 8, 4), (1, 8, 2)):
+        qs = torch.nn.functional.normalize(torch.randn(Q, 768, generator=g), dim=1).to(dev)
+        full_i, full_s = knn_topk(db, qs, k)
+        stride = packed_stride(Q, k)
+        assert stride % 16 == 0 and stride >= 12 * Q * k
+        recv = torch.zeros(world * stride, dtype=torch.uint8, device=dev)
+        for r in range(world):
+            lo, hi = shard_range(db.shape[0], r, world)
+            shard = db[lo:hi].contiguous()
+            out = packed_views(recv[r * stride:(r + 1) * stride], Q, k)
+            if Q > 8:
+                index = KnnIndex(shard)
+                index.topk(qs, k, lo, out=out)
+                index.close()
+            else:
+                _cuda_local_topk(shard, qs, k, lo, out=out)
+        mi, ms = _cuda_merge_packed(recv, world, Q, k)
+        assert torch.equal(mi, full_i) and torch.equal(ms, full_s), (Q, k, world)
+    with pytest.raises(ValueError):
+        knn_topk(db.double(), qs.double(), 8)             # raw fp32 kernels refuse other dtypes
+
+
 @pytest.fixture(scope="module")
 def arch(dev):
     import rag_gesture_b200 as R
