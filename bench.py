@@ -269,6 +269,9 @@ def run_b200(args):
     if rank == 0 and world == 1 and args.cpu_seconds > 0:
         knn["cpu_baseline"] = knn_cpu_baselines(n_full=args.knn_n, seconds=min(10.0, args.cpu_seconds))
 
+    # ---- configs[4]: long-form synthesis, a 10-minute stream (67 windows of 150 frames, 15 overlapping) -------
+    longform = longform_bench(args, arch, dev, rank, world, barrier) if args.longform_seconds > 0 else None
+
     # ---- configs[0]: one clip, plain 50-step DDIM, no retrieval (latency; CUDA-graph replay of the chain) ----
     def plain_b1():
         kw1 = arch.model.get_precompute_condition(device=dev, text=batch["word"][:1].to(dev), audio=batch["audio"][:1].to(dev),
@@ -338,7 +341,7 @@ def run_b200(args):
                              "api": "MotionDiffusion.forward(**host_batch), one synchronous call per step"}},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
             "cpu_baseline": cpu_baseline(sample_seconds=args.cpu_seconds), "knn": knn,
-            "configs0": configs0, "tiers": tiers,
+            "configs0": configs0, "tiers": tiers, "longform": longform,
             "gflop_per_clip_step": GFLOP_PER_CLIP_STEP,
             "achieved_tflops_loop": round(value * GFLOP_PER_CLIP_STEP / 1e3 / world, 2),
         }
@@ -346,6 +349,57 @@ def run_b200(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def longform_bench(args, arch, dev, rank, world, barrier):
+    """configs[4]: one synthetic audio stream of --longform-seconds (default 600 s = 9000 frames = 67 windows) through
+    LongformSynthesizer.  (a) ONE stream on all GPUs: retrieval + DDIM inversions of the windows sharded over the
+    ranks, one all-gather of the window payloads, the B=1 sampling chain (prev-latent dependency) on rank 0
+    (SURVEY 8e row 4); (b) replicas: every rank its own stream (N streams at once).  Device-synchronised wall
+    clock, max over ranks."""
+    import torch.distributed as dist
+    from rag_gesture_b200 import longform as LF
+    from rag_gesture_b200 import synthetic as S
+    n_frames = int(args.longform_seconds * 15)
+    qs = S.SyntheticGestureDataset(96, seed=9)
+    db = arch.model.database
+
+    def window_fn(c, f0, f1):
+        b = S.collate([qs[c % len(qs)]])
+        b["retrieval_method"] = "discourse"
+        return b
+
+    def clear():
+        for d in (db.test_indexes, db.test_dbounds, db.test_qbounds):
+            d.clear()
+    lf = LF.LongformSynthesizer(arch)
+    n_win = len(LF.chunk_starts(n_frames))
+
+    def timed_run(fn):
+        clear()
+        barrier()
+        t0 = time.perf_counter()
+        fn()
+        torch.cuda.synchronize()
+        t = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+    warm = 150 + 135 * max(2 * world - 1, 3)                    # a short stream: graph capture, corpus upload
+    lf.run_sharded(warm, window_fn, infer_kwargs())
+    phases = {}
+    t_stream = timed_run(lambda: lf.run_sharded(n_frames, window_fn, infer_kwargs(), timings=phases))
+    out = {"workload": f"configs[4]: {args.longform_seconds:.0f} s stream @ 15 fps = {n_frames} frames, {n_win} windows of 150 "
+                       "frames (15 overlap), discourse retrieval + inversion + insertion guidance per window, prev-latent chain",
+           "windows": n_win, "one_stream": {"seconds": round(t_stream, 3), "windows_per_sec": round(n_win / t_stream, 2),
+                                            "x_realtime": round(args.longform_seconds / t_stream, 1),
+                                            "phases_rank0_s": {k: round(v, 3) for k, v in phases.items()},
+                                            "partition": f"windows' retrieval + inversions sharded over {world} GPU(s), chain on rank 0"}}
+    if world > 1:
+        t_rep = timed_run(lambda: lf.run(n_frames, window_fn, infer_kwargs(), batch_inversions=True))
+        out["replicas"] = {"streams": world, "seconds": round(t_rep, 3), "windows_per_sec": round(world * n_win / t_rep, 2),
+                           "x_realtime": round(world * args.longform_seconds / t_rep, 1)}
+    return out
 
 
 def ncu_pass(args, arch, batch, dev):
@@ -837,6 +891,7 @@ if __name__ == "__main__":
     ap.add_argument("--knn-n", type=int, default=1_000_000)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--ncu-steps", type=int, default=0, help="profiling pass: loops cut to S levels, nothing timed")
+    ap.add_argument("--longform-seconds", type=float, default=600.0, help="configs[4] stream length (0: skip)")
     ap.add_argument("--gemm-kernel", type=int, default=0, choices=[0, 1, 2],
                     help="rg_set_gemm_kernel: 0 automatic, 1 always the 128x128 kernel, 2 the 2-CTA kernel when eligible")
     ap.add_argument("--gemm2-min-rows", type=int, default=0, help="row threshold of the automatic choice (0: library default)")

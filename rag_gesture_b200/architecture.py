@@ -203,12 +203,17 @@ class MotionDiffusion(nn.Module):
             off += len(gb.jobs)
 
     # ---- stage 2: the hot path proper, device-resident inputs -> output latents ---------------------
-    def _guided_inputs(self, gb):
-        """start_noise and the per-level insertion targets of a batch whose exemplars are inverted (gb.inv):
-        upper-body and hands windows of the inverted latents placed at the query windows (:394-407)."""
+    def insertion_targets(self, gb):
+        """The deterministic part of the guided loop's inputs for a batch whose exemplars are inverted (gb.inv):
+        upper-body and hands windows of the inverted latents placed at the query windows (:394-407).  Returns
+        (start_rows [B,T,D], start_mask [B,T,D] bool, inv_per_t [S,B,T,D] or None): start_noise takes
+        start_rows where start_mask is set; inv_per_t are the per-level insertion targets.  No RNG is drawn
+        here, so a rank that owns the window can compute them and ship them to the rank that samples
+        (LongformSynthesizer)."""
         diff, (B, T, D), device = self.diffusion_test, gb.shape, gb.device
         n = (T - 3) // 4
-        start_noise = diff._randn((B, T, D), device)
+        start_rows = torch.zeros(B, T, D, device=device)
+        start_mask = torch.zeros(B, T, D, dtype=torch.bool, device=device)
         inv_per_t = torch.zeros(diff.num_timesteps, B, T, D, device=device) if gb.use_guidance else None
         if gb.jobs:
             inv = gb.inv
@@ -222,16 +227,29 @@ class MotionDiffusion(nn.Module):
                 if dst:
                     ei, ri, bi, qi = (torch.tensor(v, dtype=torch.int64, device=device)
                                       for v in (*zip(*src), *zip(*dst)))
-                    start_noise[bi, qi] = inv[gb.inversion_start_time][ei, ri]
+                    start_rows[bi, qi] = inv[gb.inversion_start_time][ei, ri]
+                    start_mask[bi, qi] = True
                     if gb.use_guidance:
                         inv_per_t[:, bi, qi] = inv[:, ei, ri]
             else:                                       # overlapping windows: later exemplars overwrite earlier ones
                 for e, ((b, _), ((r0, r1), (q0, q1))) in enumerate(zip(gb.jobs, gb.windows)):
                     for o in (0, n + 1):
-                        start_noise[b, o + q0:o + q1] = inv[gb.inversion_start_time, e, o + r0:o + r1]
+                        start_rows[b, o + q0:o + q1] = inv[gb.inversion_start_time, e, o + r0:o + r1]
+                        start_mask[b, o + q0:o + q1] = True
                         if gb.use_guidance:
                             inv_per_t[:, b, o + q0:o + q1] = inv[:, e, o + r0:o + r1]
+        return start_rows, start_mask, inv_per_t
+
+    def _guided_inputs(self, gb):
+        """start_noise and the per-level insertion targets of a batch: the one RNG draw of this stage
+        (start_noise, :300) plus insertion_targets (computed here, or shipped in gb.targets)."""
+        diff, (B, T, D), device = self.diffusion_test, gb.shape, gb.device
+        n = (T - 3) // 4
+        start_noise = diff._randn((B, T, D), device)
+        start_rows, start_mask, inv_per_t = gb.targets if gb.targets is not None else self.insertion_targets(gb)
+        start_noise = torch.where(start_mask, start_rows, start_noise)
         if gb.use_guidance and gb.use_prev and gb.prev_latent is not None:
+            inv_per_t = inv_per_t.clone() if gb.targets is not None else inv_per_t
             inv_per_t[:, :, [0, n + 1, 2 * n + 2, 3 * n + 3], :] = 0
         return start_noise, inv_per_t
 
@@ -241,7 +259,7 @@ class MotionDiffusion(nn.Module):
         diff, (B, T, D) = self.diffusion_test, gb.shape
         start_noise, inv_per_t = None, None
         if gb.use_inversion:
-            if gb.jobs:
+            if gb.jobs and gb.targets is None:
                 # the reference draws start_noise before it inverts (:300); inversion draws nothing, so the
                 # order of the two does not change any generator's sequence
                 self.invert_many([gb])
@@ -331,6 +349,7 @@ class GuidedBatch:
     """Device-resident inputs of one guided batch between MotionDiffusion.prepare and run_prepared."""
     jobs, ex, ex_query_mask, windows, outpaint_seq, prev_latent, inv = (), None, None, (), None, None, None
     cond_inputs = None
+    targets = None          # (start_rows, start_mask, inv_per_t) computed elsewhere (insertion_targets on another rank)
 
     def clip_steps(self, num_timesteps):
         """Work of the batch in the metric's unit: 50 * (B + E)."""

@@ -10,6 +10,12 @@ DDIM inversions of all windows do not depend on the chain.  `LongformSynthesizer
   2. runs the guided sampling chain window by window,
   3. cross-fades consecutive windows linearly over the overlap: rotations in 6D space, expressions and
      translation directly (:431-478).
+On several GPUs (torch.distributed initialised) step 1 is SHARDED: rank r prepares and inverts
+the windows shard_range(n_windows, r, world), turns the inverted latents into per-level insertion targets
+(MotionDiffusion.insertion_targets: deterministic, no RNG), and ONE all-gather (parallel.gather_clips: ~6 MB per
+window over NVLink) hands every window's targets and pre-projected conditions to the chain rank, which runs step
+2 (B = 1, CUDA-graph replay of the evaluation chain) and step 3.  The other ranks are free for other streams
+("replicas only" for the chain).
 BERT / wav2vec feature extraction per window is out of scope: the caller supplies per-window features.
 """
 import torch
@@ -112,6 +118,116 @@ class LongformSynthesizer:
         batch["sample_name"] = out[0] if single else out
         return batch
 
+    # ---- window payload: what the chain rank needs from the rank that prepared the window ------------------
+    PAYLOAD = ("inv_per_t", "start_rows", "start_mask", "xf_text", "xf_audio", "xf_spk", "motion_mask")
+
+    def pack_window(self, gb):
+        """One prepared + inverted window (B = 1) as a flat fp32 vector: insertion targets, pre-projected
+        conditions and the motion mask.  Returns (vector, shapes)."""
+        arch = self.arch
+        arch.encode_clip_conditions(gb)
+        start_rows, start_mask, inv_per_t = arch.insertion_targets(gb)
+        xf = gb.model_kwargs["xf_out"]
+        parts = dict(inv_per_t=inv_per_t, start_rows=start_rows, start_mask=start_mask.float(),
+                     xf_text=xf["xf_text"], xf_audio=xf["xf_audio"], xf_spk=xf["xf_spk"],
+                     motion_mask=gb.model_kwargs["motion_mask"])
+        shapes = {k: tuple(parts[k].shape) for k in self.PAYLOAD}
+        return torch.cat([parts[k].float().reshape(-1) for k in self.PAYLOAD]), shapes
+
+    def unpack_window(self, vec, shapes, template):
+        """The GuidedBatch of a window prepared elsewhere: `template` (any locally prepared window) supplies the
+        flags; tensors come from the payload."""
+        from .architecture import GuidedBatch
+        out, off = {}, 0
+        for k in self.PAYLOAD:
+            n = 1
+            for d in shapes[k]:
+                n *= d
+            out[k] = vec[off:off + n].reshape(shapes[k])
+            off += n
+        gb = GuidedBatch()
+        for f in ("use_outpaint", "use_inversion", "inversion_start_time", "use_guidance", "guidance_iters", "guidance_lr",
+                  "shape", "device"):
+            setattr(gb, f, getattr(template, f))
+        gb.use_prev, gb.prev_latent, gb.extra, gb.jobs, gb.results = True, None, {}, (), {}
+        qm = template.model_kwargs["query_mask"]
+        gb.model_kwargs = dict(xf_out={k: out[k].contiguous() for k in ("xf_text", "xf_audio", "xf_spk")}, re_dict=None,
+                               sample_idx=None, query_mask=qm, motion_mask=out["motion_mask"].contiguous())
+        gb.targets = (out["start_rows"].contiguous(), out["start_mask"] > 0.5, out["inv_per_t"].contiguous())
+        return gb
+
+    def _chain(self, windows, starts):
+        """Steps 2 and 3: the serial sampling chain over prepared windows (exemplars inverted or targets shipped)
+        and the cross-fade of consecutive windows."""
+        arch = self.arch
+        outs, prev, latents = None, None, []
+        for item in windows:
+            item.use_prev, item.prev_latent = True, arch.mask_prev_latent(prev)
+            res = arch.finish(item, arch.run_prepared(item))
+            prev = res["prev_latentout"]
+            latents.append(prev)
+            outs = self._append(outs, {k: res[k] for k in self.ROT_KEYS + self.LIN_KEYS})
+        outs["latents"] = torch.cat(latents, 0)
+        outs["window_starts"] = starts
+        return outs
+
+    def _append(self, outs, cur):
+        if outs is None:
+            return cur
+        ov = self.overlap
+        for k in cur:
+            fade = crossfade_rotations if k in self.ROT_KEYS else crossfade_linear
+            head = fade(outs[k][:, -ov:], cur[k][:, :ov])
+            outs[k] = torch.cat([outs[k][:, :-ov], head, cur[k][:, ov:]], dim=1)
+        return outs
+
+    def run_sharded(self, n_frames, window_fn, inference_kwargs, group=None, chain_rank=0, timings=None):
+        """Multi-GPU form of run(batch_inversions=True) (module docstring): windows' retrieval + inversions sharded
+        over the ranks, one all-gather of the window payloads, the chain on `chain_rank`.  Returns the result dict
+        on the chain rank and None elsewhere.  With one process it equals run(batch_inversions=True).
+        `timings` (a dict) receives host-clock seconds of the phases, each closed by a device synchronise."""
+        import time
+        from .parallel import _world, gather_clips, shard_range
+
+        def stamp(name, t0):
+            if timings is not None:
+                torch.cuda.synchronize()
+                timings[name] = timings.get(name, 0.0) + time.perf_counter() - t0
+            return time.perf_counter()
+        t = time.perf_counter()
+        rank, world = _world(group)
+        starts = chunk_starts(n_frames, self.window, self.overlap)
+        n_win = len(starts)
+        lo, hi = shard_range(n_win, rank, world)
+        arch = self.arch
+        mine = []
+        for cidx in range(lo, hi):
+            batch = self._window_names(dict(window_fn(cidx, starts[cidx], starts[cidx] + self.window)), cidx)
+            batch["inference_kwargs"] = dict(inference_kwargs, use_prev_latent=True, prev_latent=None)
+            mine.append(arch.prepare(**batch))
+        if not mine:
+            raise RuntimeError("run_sharded: more ranks than windows; use fewer ranks for this stream")
+        t = stamp("prepare", t)
+        arch.invert_many(mine)                      # this rank's exemplars, one batched reverse loop
+        t = stamp("invert", t)
+        if world == 1:
+            out = self._chain(mine, starts)
+            stamp("chain", t)
+            return out
+        packed = [self.pack_window(gb) for gb in mine]
+        shapes = packed[0][1]
+        local = torch.stack([v for v, _ in packed], 0)
+        full = gather_clips(local, n_win, group)    # [n_win, payload] on every rank, window order
+        t = stamp("exchange", t)
+        if rank != chain_rank:
+            return None
+        windows = [mine[c - lo] if lo <= c < hi else self.unpack_window(full[c], shapes, mine[0]) for c in range(n_win)]
+        for gb in mine:                             # shipped and local windows take the same code path
+            gb.targets, gb.inv = arch.insertion_targets(gb), None
+        out = self._chain(windows, starts)
+        stamp("chain", t)
+        return out
+
     def run(self, n_frames, window_fn, inference_kwargs, batch_inversions=True):
         """batch_inversions=True prepares every window (codec encodes, retrieval) and inverts all exemplars in
         one batched reverse loop BEFORE the first start_noise is drawn; the reference interleaves encode /
@@ -131,25 +247,14 @@ class LongformSynthesizer:
             prepared.append(gb)
         if batch_inversions:
             arch.invert_many(prepared)              # one batched reverse loop for every window's exemplars
+            return self._chain(prepared, starts)
         outs, prev, latents = None, None, []
-        for cidx, item in enumerate(prepared):
-            if batch_inversions:
-                item.use_prev, item.prev_latent = True, arch.mask_prev_latent(prev)
-                res = arch.finish(item, arch.run_prepared(item))
-            else:
-                item["inference_kwargs"]["prev_latent"] = prev
-                res = arch(**item)
+        for item in prepared:                       # the reference's order: window by window
+            item["inference_kwargs"]["prev_latent"] = prev
+            res = arch(**item)
             prev = res["prev_latentout"]
             latents.append(prev)
-            cur = {k: res[k] for k in self.ROT_KEYS + self.LIN_KEYS}
-            if outs is None:
-                outs = cur
-                continue
-            ov = self.overlap
-            for k in cur:
-                fade = crossfade_rotations if k in self.ROT_KEYS else crossfade_linear
-                head = fade(outs[k][:, -ov:], cur[k][:, :ov])
-                outs[k] = torch.cat([outs[k][:, :-ov], head, cur[k][:, ov:]], dim=1)
+            outs = self._append(outs, {k: res[k] for k in self.ROT_KEYS + self.LIN_KEYS})
         outs["latents"] = torch.cat(latents, 0)
         outs["window_starts"] = starts
         return outs

@@ -103,6 +103,45 @@ def test_three_window_stream(arch):
     assert tuple(out2["latents"].shape) == tuple(out["latents"].shape)
 
 
+@pytest.mark.gpu
+def test_shipped_windows_equal_local_chain(arch):
+    """a window prepared + inverted on ANOTHER rank reaches the chain rank as a flat payload
+    (insertion targets, pre-projected conditions, motion mask).  Packing every window and sampling the chain from
+    the unpacked payloads gives bit-identical latents and poses to run(batch_inversions=True); run_sharded with one
+    process is the same computation."""
+    qs = S.SyntheticGestureDataset(48, seed=8)
+    db = arch.model.database
+
+    def fresh():
+        for d in (db.test_indexes, db.test_dbounds, db.test_qbounds):
+            d.clear()
+        torch.manual_seed(5)
+        torch.cuda.manual_seed(6)
+    n_frames = 150 + 2 * 135
+    lf = LF.LongformSynthesizer(arch)
+    fresh()
+    ref = lf.run(n_frames, _window_fn(qs), IK, batch_inversions=True)
+    fresh()
+    one = lf.run_sharded(n_frames, _window_fn(qs), IK)
+    assert torch.equal(one["latents"], ref["latents"]) and torch.equal(one["pred_upper"], ref["pred_upper"])
+    # simulated shipping: every window goes through pack -> unpack
+    fresh()
+    starts = LF.chunk_starts(n_frames)
+    gbs = []
+    for cidx, f0 in enumerate(starts):
+        b = lf._window_names(dict(_window_fn(qs)(cidx, f0, f0 + 150)), cidx)
+        b["inference_kwargs"] = dict(IK, use_prev_latent=True, prev_latent=None)
+        gbs.append(arch.prepare(**b))
+    assert sum(len(g.jobs) for g in gbs) >= 2
+    arch.invert_many(gbs)
+    packed = [lf.pack_window(gb) for gb in gbs]
+    assert len({v.numel() for v, _ in packed}) == 1             # fixed-size payloads: one all-gather moves them
+    shipped = [lf.unpack_window(v.clone(), shp, gbs[0]) for v, shp in packed]
+    out = lf._chain(shipped, starts)
+    for k in ("latents", "pred_upper", "pred_hands", "pred_transl", "pred_exps"):
+        assert torch.equal(out[k], ref[k]), k
+
+
 def test_postprocess_recompose_and_upsample_vs_reference():
     """postprocess.recompose_motion / upsample_motion against tools/visualize.py:204-291 executed with the
     reference's rotation_conversions (tests/golden/make_golden.py group "postprocess")."""

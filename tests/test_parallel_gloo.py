@@ -71,6 +71,88 @@ def _worker(rank, world, port, n_total):
         dist.destroy_process_group()
 
 
+class _FakeArch:
+    """CPU stand-in with the MotionDiffusion methods LongformSynthesizer.run_sharded drives; every result is a
+    deterministic function of the window index and the previous latent, so any mistake in sharding, payload
+    order or shipping changes the output."""
+
+    class _Diff:
+        num_timesteps = 4
+
+    diffusion_test = _Diff()
+
+    def prepare(self, **batch):
+        from rag_gesture_b200.architecture import GuidedBatch
+        c = float(batch["cidx"])
+        gb = GuidedBatch()
+        gb.use_outpaint, gb.use_inversion, gb.inversion_start_time, gb.use_guidance = False, True, -1, True
+        gb.guidance_iters, gb.guidance_lr, gb.shape, gb.device, gb.extra = [0] * 4, 0.1, (1, 7, 8), torch.device("cpu"), {}
+        gb.jobs, gb.c = ((0, "w"),), c
+        xf = {k: torch.full((1, 3, 8), c + i) for i, k in enumerate(("xf_text", "xf_audio", "xf_spk"))}
+        gb.model_kwargs = dict(xf_out=xf, query_mask={"q": torch.ones(1, 7)}, motion_mask=torch.full((1, 7), c + 1))
+        return gb
+
+    def invert_many(self, gbs):
+        for gb in gbs:
+            gb.inv = torch.full((4, 1, 7, 8), gb.c)
+
+    def encode_clip_conditions(self, gb):       # prepare() already encoded them (defer_conditions=False)
+        return gb
+
+    def insertion_targets(self, gb):
+        rows = gb.inv[-1].clone()
+        mask = torch.zeros(1, 7, 8, dtype=torch.bool)
+        mask[:, 2:4] = True
+        return rows, mask, gb.inv.clone()
+
+    def mask_prev_latent(self, prev):
+        return None if prev is None else prev * 0.5
+
+    def run_prepared(self, gb):
+        rows, mask, inv = gb.targets if gb.targets is not None else self.insertion_targets(gb)
+        x = torch.where(mask, rows, torch.zeros_like(rows)) + inv.sum(0) + gb.model_kwargs["xf_out"]["xf_audio"].mean()
+        x = x + gb.model_kwargs["motion_mask"].unsqueeze(-1)
+        return x if gb.prev_latent is None else x + gb.prev_latent
+
+    def finish(self, gb, out):
+        res = {"prev_latentout": out}
+        res.update({k: out[:, :, :6].repeat(1, 22, 1)[:, :150] for k in
+                    ("pred_upper", "pred_lower", "pred_hands", "pred_facepose", "pred_exps", "pred_transl")})
+        return res
+
+
+def _longform_worker(rank, world, port, n_frames, ref_path):
+    from rag_gesture_b200 import longform as LF
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        out = LF.LongformSynthesizer(_FakeArch()).run_sharded(n_frames, lambda c, f0, f1: {"cidx": c}, {}, chain_rank=1)
+        if rank == 1:
+            ref = torch.load(ref_path)
+            assert out["window_starts"] == ref["window_starts"]
+            for k in ("latents", "pred_upper", "pred_exps"):
+                assert torch.equal(out[k], ref[k]), k
+        else:
+            assert out is None
+    finally:
+        dist.destroy_process_group()
+
+
+def test_longform_sharded_world2_gloo(tmp_path):
+    """LongformSynthesizer.run_sharded at world_size 2 (windows 0-2 prepared by rank 0, 3-5 by rank 1, chain on rank
+    1) == the single-process run: shard ranges, payload packing, the all-gather and the chain order."""
+    from rag_gesture_b200 import longform as LF
+    n_frames = 150 + 4 * 135
+    ref = LF.LongformSynthesizer(_FakeArch()).run_sharded(n_frames, lambda c, f0, f1: {"cidx": c}, {})
+    assert len(ref["window_starts"]) == 6          # [0] + range(135, 690, 135): the reference formula (:263)
+    path = str(tmp_path / "ref.pt")
+    torch.save(ref, path)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_longform_worker, args=(2, port, n_frames, path), nprocs=2, join=True)
+
+
 def test_world2_gloo():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
