@@ -837,7 +837,7 @@ def knn_cpu_baselines(n_full=1_000_000, dim=768, k=8, seconds=10.0):
         cache = {f"e{i}": [feats[i], 0] for i in range(n_slice)}
         names = list(cache.keys())
         t0 = time.perf_counter()
-        order = ns.rag_utils.sort_sidx_by_textsimilarity(names, q, cache)
+        order = ns.rag_utils.sort_sidx_by_textsimilarity(names, "", q, cache)
         dt = time.perf_counter() - t0
         out["text_similarity_reference"] = {"entries_per_sec": round(n_slice / dt, 1), "entries": n_slice, "tokens": Td,
                                             "seconds": round(dt, 2), "kind": "reference",
