@@ -80,6 +80,41 @@ def test_registry_and_constructor_surface():
     assert reg.get("ReGestureTransformer") is R.ReGestureTransformer
 
 
+def test_drop_in_through_the_reference_builder():
+    """The seam a mogen user crosses (tools/visualize.py:138-141): the B200 classes re-registered into the
+    REFERENCE's own registry (mogen/models/builder.py:11-36, imported unmodified through oracle/refshim.py), then
+    `build_architecture(cfg.model, database=...)` of the reference builds OUR MotionDiffusion / ReGestureTransformer /
+    attention classes from the shipped config dict, and a reference-keyed state dict loads into it (construction
+    only: no GPU here)."""
+    from oracle import refshim
+    if not refshim.available():
+        pytest.skip("reference tree not present (neither /root/reference nor oracle/_ref)")
+    import rag_gesture_b200 as R
+    from rag_gesture_b200 import config as C
+    from rag_gesture_b200 import synthetic as S
+    ns = refshim.load()
+    saved = dict(ns.builder.MODELS._module_dict)
+    try:
+        R.register_into(ns.builder.MODELS)
+        assert ns.builder.MODELS.get("MotionDiffusion") is R.MotionDiffusion
+        assert ns.builder.ATTENTIONS.get("EfficientCrossAttention") is R.EfficientCrossAttention
+        cfg = C.model_cfg()
+        cfg["use_retrieval_for_test"] = True
+        arch = ns.builder.build_architecture(cfg, database=S.SyntheticGestureDataset(16, seed=7))
+        assert type(arch) is R.MotionDiffusion and type(arch.model) is R.ReGestureTransformer
+        assert type(arch.model.temporal_decoder_blocks[0].sa_block) is R.EfficientSelfAttention
+        sd = S.synthetic_state_dict(0)
+        missing, unexpected = arch.model.load_state_dict(sd, strict=False)
+        assert not unexpected and all(k.startswith(("gesture_rep_encoder.", "database.")) for k in missing), (missing, unexpected)
+        # and the reference's own submodule builder hands back our denoiser for the config's `model` block
+        den = ns.builder.build_submodule(C.denoiser_cfg(), database=None, use_retrieval_for_test=False)
+        assert type(den) is R.ReGestureTransformer
+        assert set(k for k in den.state_dict() if not k.startswith("gesture_rep_encoder.")) == set(S.denoiser_param_shapes())
+    finally:
+        ns.builder.MODELS._module_dict.clear()
+        ns.builder.MODELS._module_dict.update(saved)
+
+
 def test_no_global_load_above_pdl_wait():
     """SASS lint (tools/pdl_lint.py): in every kernel that executes griddepcontrol.wait no global load is
     scheduled ahead of it.  nvcc hoists ld.global.nc (`const T* __restrict__`) above the wait, which made a
