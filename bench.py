@@ -265,6 +265,7 @@ def run_b200(args):
     roof = gemm_roofline(arch, [B, E], dev, flush, tc_sus, peak_src, args.precision)
     if args.precision != "fp32":
         roof = gemm_chain_roofline(arch, [B, E], dev, flush, tc_sus, roof, args.steps)
+    elementwise = elementwise_roofline(arch, dev, hbm_peak, peak_src)
     knn = knn_bench(args, dev, rank, world, hbm_peak, tc_sus, peak_src, flush)
     if rank == 0 and world == 1 and args.cpu_seconds > 0:
         knn["cpu_baseline"] = knn_cpu_baselines(n_full=args.knn_n, seconds=min(10.0, args.cpu_seconds))
@@ -341,7 +342,7 @@ def run_b200(args):
                              "api": "MotionDiffusion.forward(**host_batch), one synchronous call per step"}},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
             "cpu_baseline": cpu_baseline(sample_seconds=args.cpu_seconds), "knn": knn,
-            "configs0": configs0, "tiers": tiers, "longform": longform,
+            "configs0": configs0, "tiers": tiers, "longform": longform, "elementwise": elementwise,
             "gflop_per_clip_step": GFLOP_PER_CLIP_STEP,
             "achieved_tflops_loop": round(value * GFLOP_PER_CLIP_STEP / 1e3 / world, 2),
         }
@@ -349,6 +350,42 @@ def run_b200(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def elementwise_roofline(arch, dev, hbm_peak, peak_src):
+    """K8 / K9: the DDIM update (3 fp32 tensors: x, x0 in, x' out) and the insertion blend (per row: in_seq in for the
+    row mask, then noise OR x in, x out = 3 tensors' worth of bytes) timed alone on inputs larger than L2 (2048
+    clips = 180 MB per tensor), CUDA events, algorithmic bytes / time against the measured HBM copy bandwidth."""
+    from rag_gesture_b200 import config as C
+    eng = arch.model.rg_engine(arch.diffusion_test)
+    n_clips = 2048
+    shape = (n_clips, C.N_TOKENS, C.LATENT_DIM)
+    x, x0, noise = (torch.randn(shape, device=dev) for _ in range(3))
+    in_seq = torch.zeros(shape, device=dev)
+    in_seq[:, 2:9] = 1.0
+    out = torch.empty(shape, device=dev)
+    bytes_t = x.numel() * 4
+
+    def ev(fn):
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(5):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b) / 1e3)
+        return statistics.median(ts)
+    t_up = ev(lambda: eng.ddim_update(x, x0, 10, -1, out=out))
+    t_bl = ev(lambda: eng.blend_in_seq(x, in_seq, noise, 10, out=out))
+    res = {}
+    for name, t, n_t in (("ddim_update_kernel", t_up, 3), ("blend_kernel", t_bl, 3)):
+        gbs = n_t * bytes_t / t / 1e9
+        res[name] = {"bound": "hbm", "achieved": round(gbs, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(gbs / hbm_peak, 4),
+                     "launch_ms": round(t * 1e3, 3), "bytes_per_launch": n_t * bytes_t, "tensors": n_t, "peak_source": peak_src}
+    return res
 
 
 def longform_bench(args, arch, dev, rank, world, barrier):
