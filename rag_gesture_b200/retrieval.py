@@ -574,3 +574,140 @@ class RetrievalDatabase(nn.Module):
             raw_facial=raw_f.view(B, R, self.max_seq_len, 100).contiguous(),
             raw_sample_names=names_out, raw_type2words=all_t2w, raw_latent_mask=raw_latent_mask,
             retr_startends=all_rse, query_startends=all_qse, retr_uncropped_latents=all_lat)
+
+
+# ---- rule scoring sharded over DB rows ---------------------------------------------------------
+class ShardedDiscourseRetriever:
+    """discourse_retrieval with the DATABASE ROWS partitioned over the ranks: rank r scores only the samples
+    shard_range(N, r, world) of the ASCII-ordered database (rule scores: SenseTable over its rows; tie-breaks:
+    text similarity against ITS block of text features), keeps its 10 best candidates per query point under the
+    total order the reference's tier logic induces -- (score desc, text similarity desc, database order asc): tiers
+    are runs of equal score, a tier is ordered by similarity with a stable sort (rag/discourse_retrieval.py:215-246,
+    rag/utils.py:127-129) -- and ONE all-gather of [queries, 10] x (score, similarity, row, bound entry) per rank
+    (320 bytes per query point) lets every rank merge the global top 10.  The top 10 of a union is the top 10 of the
+    per-shard top 10s, so names, order and bounds equal the unsharded function's (tests/test_parallel_gloo.py).
+
+    Queries of all ranks are exchanged first (one all_gather_object of the small annotation tuples plus one padded
+    all-gather of the text features), so each rank scores every query against its rows: the per-rank rule-scoring
+    work and text-feature memory are 1/world of the unsharded ones; the annotation dicts themselves stay replicated
+    (a few MB)."""
+    K = 10
+
+    def __init__(self, db, group=None, sim_fn=None):
+        from .parallel import _world, shard_range
+        self.db, self.group = db, group
+        self.rank, self.world = _world(group)
+        self.names = list(db.idx_2_text.keys())
+        self.grow = {n: i for i, n in enumerate(self.names)}
+        lo, hi = shard_range(len(self.names), self.rank, self.world)
+        self.lo, self.hi = lo, hi
+        mine = set(self.names[lo:hi])
+        self.sense_index = {s: [n for n in ns if n in mine] for s, ns in db._sense_index.items()}
+        self.tables, self.conn_ids = {}, {}
+        self._index, self._sim_fn = None, sim_fn
+
+    def _sims(self, query_feat, names):
+        if self._sim_fn is not None:
+            return self._sim_fn(query_feat, names)
+        if self._index is None:                     # this rank's block of the text features only
+            mine = self.names[self.lo:self.hi]
+            dev = query_feat.device if query_feat.is_cuda else (self.db._index_device or "cuda")
+            self._index = TextSimilarityIndex(mine, [self.db.idx_2_text[n][0] for n in mine], dev)
+        rows = [self._index.row[n] for n in names]
+        return self._index.scores(query_feat, rows).double().cpu().numpy()
+
+    def _scored(self, sense, conn, speaker_id, q_prom):
+        """(table, score, bound entry, candidate rows of the table): every row of this shard that ties with or beats
+        its K-th best score can still reach the global top K."""
+        import numpy as np
+        if sense not in self.tables:
+            self.tables[sense] = SenseTable(sense, self.sense_index.get(sense, []), self.db.idx_2_sense,
+                                            self.db.idx_2_prominence, self.conn_ids)
+        tab = self.tables[sense]
+        if not len(tab.names):
+            return tab, None, None, []
+        sc, top = tab.score(self.conn_ids.get(conn), speaker_id, q_prom)
+        order = np.argsort(-sc, kind="stable")
+        cut = sc[order[min(self.K, len(order)) - 1]]
+        return tab, sc, top, [int(i) for i in order if sc[i] >= cut]
+
+    def local_candidates(self, points, query_feat):
+        """points: [(sense, conn, speaker_id, q_prom)] of ONE query (they share its text feature).  Returns one
+        [K, 4] float64 block per point: (score, similarity, global row, bound entry) of this shard's best K, -inf
+        padded.  The similarity of every candidate is computed here (one launch per query): whether it decides
+        anything is only known after the merge, when the global tiers are."""
+        import numpy as np
+        scored = [self._scored(*p) for p in points]
+        flat = [tab.names[i] for tab, _, _, cand in scored for i in cand]
+        sims = self._sims(query_feat, flat) if flat else []
+        out, pos = [], 0
+        for tab, sc, top, cand in scored:
+            blk = np.full((self.K, 4), -np.inf)
+            sm = {i: float(sims[pos + j]) for j, i in enumerate(cand)}
+            pos += len(cand)
+            keyed = sorted(cand, key=lambda i: (-sc[i], -sm[i], self.grow[tab.names[i]]))[:self.K]
+            for j, i in enumerate(keyed):
+                blk[j] = (sc[i], sm[i], self.grow[tab.names[i]], int(top[i]))
+            out.append(blk)
+        return out
+
+    def retrieve(self, queries):
+        """queries: this rank's list of dict(discourse, prominence, speaker_id, encoded_text).  Returns, per query,
+        the (sample_indexes, d_bounds, query_bounds) triple of discourse_retrieval."""
+        import numpy as np
+        import torch.distributed as dist
+        meta = [(q["discourse"], q["prominence"], q["speaker_id"], tuple(q["encoded_text"].shape)) for q in queries]
+        feats = [q["encoded_text"] for q in queries]
+        if self.world > 1:
+            all_meta = [None] * self.world
+            dist.all_gather_object(all_meta, meta, group=self.group)
+            n_max = max(len(m) for m in all_meta)
+            t_max = max((s[3][0] for m in all_meta for s in m), default=1)
+            dim = feats[0].shape[1] if feats else 768
+            dev = feats[0].device if feats else torch.device("cpu")
+            send = torch.zeros(n_max, t_max, dim, device=dev)
+            for i, f in enumerate(feats):
+                send[i, :f.shape[0]] = f
+            recv = torch.empty(self.world * n_max, t_max, dim, device=dev)
+            dist.all_gather_into_tensor(recv, send, group=self.group)
+            all_q = [(r, i, m[i], recv[r * n_max + i, :m[i][3][0]]) for r, m in enumerate(all_meta) for i in range(len(m))]
+        else:
+            all_q = [(0, i, meta[i], feats[i]) for i in range(len(meta))]
+        # every query point of every rank against this rank's rows
+        points, blocks = [], []
+        for r, i, (disc, prom, spk, _), feat in all_q:
+            senses, conns = [d[1] for d in disc], [d[0] for d in disc]
+            if not disc:
+                continue
+            q_prom = map_conns_to_prominence(conns, prom)
+            pts = [(sense, conn, spk, None if q_prom[qi] is None else float(q_prom[qi][1]))
+                   for qi, (sense, conn) in enumerate(zip(senses, conns))]
+            points += [(r, i, qi) for qi in range(len(pts))]
+            blocks += self.local_candidates(pts, feat)
+        local = torch.from_numpy(np.stack(blocks, 0)) if blocks else torch.zeros(0, self.K, 4, dtype=torch.float64)
+        if self.world > 1:
+            dev = feats[0].device if feats else torch.device("cpu")
+            send = local.to(dev).contiguous()
+            recv = torch.empty((self.world,) + tuple(send.shape), dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(recv.view(-1), send.view(-1), group=self.group)
+            cands = recv.permute(1, 0, 2, 3).reshape(len(points), self.world * self.K, 4).cpu().numpy()
+        else:
+            cands = local.numpy()
+        out = [({}, {}, {}) for _ in queries]
+        for p, (r, i, qi) in enumerate(points):
+            if r != self.rank:
+                continue
+            c = cands[p]
+            c = c[np.isfinite(c[:, 0])]
+            order = np.lexsort((c[:, 2], -c[:, 1], -c[:, 0]))[:self.K]  # score desc, similarity desc, DB order asc
+            disc = queries[i]["discourse"]
+            names = [self.names[int(c[j, 2])] for j in order]
+            si, db_, qb = out[i]
+            si[qi] = names
+            db_[qi] = {}
+            for j, nm in zip(order, names):
+                b = self.db.idx_2_discbounds[nm][int(c[j, 3])]
+                db_[qi][nm] = (b[1], b[0], round(b[4], 3), round(b[5], 3))
+            d = disc[qi]
+            qb[qi] = (d[0].lower(), d[1], d[6], d[7])
+        return out

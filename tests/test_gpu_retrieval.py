@@ -62,6 +62,24 @@ def test_discourse_retrieval_vs_reference(db, dev):
         assert json.loads(json.dumps({str(k): v for k, v in bounds.items()})) == g["bounds"], i
 
 
+def test_sharded_retriever_vs_reference(db, dev):
+    """ShardedDiscourseRetriever on the device (its own block of the text features through rg_text_similarity, the
+    merge under (score, similarity, DB order)) against the reference's golden lists and bounds for all 48 queries."""
+    from rag_gesture_b200.retrieval import ShardedDiscourseRetriever
+    with open(os.path.join(GOLDEN, "retrieval.json")) as f:
+        gold = json.load(f)
+    qs = S.SyntheticGestureDataset(N_QUERY, seed=8)
+    queries = []
+    for i in range(N_QUERY):
+        spk, disc, prom, _, _ = qs.annotations(i)
+        queries.append(dict(discourse=disc, prominence=prom, speaker_id=spk, encoded_text=qs.text_feature(i).to(dev)))
+    got = ShardedDiscourseRetriever(db).retrieve(queries)
+    for i, (idx, bounds, qb) in enumerate(got):
+        g = gold["queries"][i]
+        assert {str(k): v for k, v in idx.items()} == g["indexes"], i
+        assert json.loads(json.dumps({str(k): v for k, v in bounds.items()})) == g["bounds"], i
+
+
 @pytest.mark.parametrize("N,Q,k", [(20000, 1, 8), (20000, 5, 8), (4099, 64, 8), (777, 9, 32), (40, 3, 8), (5, 2, 8)])
 def test_knn_topk_exact(dev, N, Q, k):
     """Retrieved indices bit-exact against the float64 oracle unless the oracle itself reports an

@@ -153,6 +153,67 @@ def test_longform_sharded_world2_gloo(tmp_path):
     mp.spawn(_longform_worker, args=(2, port, n_frames, path), nprocs=2, join=True)
 
 
+class _CpuTextIndex:
+    """CPU stand-in for TextSimilarityIndex (the kernels need a GPU): same score definition
+    (mean(diag(Q D^T)) over min(Tq, Td) tokens, rag/utils.py:107-118) and the same stable ranking."""
+
+    def __init__(self, db):
+        self.names = list(db.idx_2_text.keys())
+        self.row = {n: i for i, n in enumerate(self.names)}
+        self.feats = [db.idx_2_text[n][0] for n in self.names]
+
+    def score(self, q, name):
+        f = self.feats[self.row[name]]
+        m = min(q.shape[0], f.shape[0])
+        return float((q[:m] * f[:m]).sum(1).mean())
+
+    def rank(self, query, rows, k):
+        sc = [self.score(query, self.names[r]) for r in rows]
+        return [rows[j] for j in sorted(range(len(rows)), key=lambda j: -sc[j])[:k]]
+
+
+def _retrieval_worker(rank, world, port, n_db, n_q):
+    from rag_gesture_b200 import config as C
+    from rag_gesture_b200 import synthetic as S
+    from rag_gesture_b200.retrieval import RetrievalDatabase, ShardedDiscourseRetriever, discourse_retrieval
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        db = RetrievalDatabase(dataset=S.SyntheticGestureDataset(n_db, seed=7), **C.retrieval_cfg()).eval()
+        cpu_index = _CpuTextIndex(db)
+        qs = S.SyntheticGestureDataset(n_q, seed=8)
+        mine = list(range(rank, n_q, world))                    # each rank asks for different clips
+        queries = []
+        for i in mine:
+            spk, disc, prom, _, _ = qs.annotations(i)
+            queries.append(dict(discourse=disc, prominence=prom, speaker_id=spk, encoded_text=qs.text_feature(i)))
+        sharded = ShardedDiscourseRetriever(db, sim_fn=lambda q, names: [cpu_index.score(q, n) for n in names])
+        assert sharded.hi - sharded.lo in (n_db // world, n_db // world + 1)
+        got = sharded.retrieve(queries)
+        n_points = 0
+        for q, (si, bounds, qb) in zip(queries, got):
+            ref_si, ref_b, ref_qb = discourse_retrieval(
+                text="", discourse=q["discourse"], prominence=q["prominence"], speaker_id=q["speaker_id"],
+                db_idx_2_sense=db.idx_2_sense, db_idx_2_discbounds=db.idx_2_discbounds,
+                db_idx_2_prominence=db.idx_2_prominence, encoded_text=q["encoded_text"], text_feat_cache=db.idx_2_text,
+                index=cpu_index, sense_index=db._sense_index, sense_tables=db._sense_tables)
+            assert si == ref_si and bounds == ref_b and qb == ref_qb
+            n_points += len(si)
+        assert n_points > 0
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_rule_scoring_world2_gloo():
+    """rule scores + text-similarity tie-breaks over a ROW-SHARDED database (each rank scores
+    every rank's query points against its half of the rows, one all-gather of 10 candidates per point, merge under
+    (score desc, similarity desc, DB order)) == the unsharded discourse_retrieval: names, order and bounds."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_retrieval_worker, args=(2, port, 600, 12), nprocs=2, join=True)
+
+
 def test_world2_gloo():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
