@@ -143,7 +143,7 @@ class LongformSynthesizer:
             n = 1
             for d in shapes[k]:
                 n *= d
-            out[k] = vec[off:off + n].reshape(shapes[k])
+            out[k] = vec[off:off + n].reshape(shapes[k]).clone()     # own storage: the kernels need 16-byte aligned rows
             off += n
         gb = GuidedBatch()
         for f in ("use_outpaint", "use_inversion", "inversion_start_time", "use_guidance", "guidance_iters", "guidance_lr",
