@@ -527,7 +527,7 @@ def gemm_chain_roofline(arch, n_clips, dev, flush, tc_peak, isolated, k_steps=2)
 
     tot_t, tot_f, per, share = 0.0, 0.0, {}, {}
     B_, E_ = n_clips
-    mix = [(E_, 1), (B_ + E_, max(1, k_steps - 1)), (B_, 1)]
+    mix = [(E_, 1), (B_, 1), (B_ + E_, max(1, k_steps - 1))]          # the fused level last: reused below
     for clips, weight in mix:
         if clips <= 0:
             continue
@@ -554,10 +554,27 @@ def gemm_chain_roofline(arch, n_clips, dev, flush, tc_peak, isolated, k_steps=2)
         tot_t += t_gemm * weight
         tot_f += flops * weight
     ach = tot_f / tot_t / 1e12
-    return {"bound": "tensor", "kernel": "gemm2_tc_kernel (persistent 2-CTA tcgen05.mma cta_group::2 kind::f16, 256x256 pair tiles, TMA-fed, "
-            "2 TMEM accumulator stages, TMA-store epilogue) from 4096 rows on, gemm_tc_kernel<128,*> below: the 58 GEMM "
-            "launches of one denoiser evaluation as their own PDL chain (rg_probe_gemm_only), 10 evaluations back to back",
-            "mix": {f"M{c * 43}": w for c, w in mix},
+    # the same probe with the 2-CTA kernel forced (cta_group::2, 256x256 pair tiles, TMA-store epilogue), fused shape
+    two_cta = {}
+    try:
+        for name, pt in (("persistent_2acc", 1), ("one_tile_per_pair", 10 ** 6)):
+            _lib.check(lib.rg_set_gemm_kernel(2, 0, pt))
+            for _ in range(3):
+                step()
+            _lib.check(lib.rg_probe_gemm_only(eng._h, 1))
+            try:
+                for _ in range(2):
+                    step()
+                t2 = evals(step, 10)
+            finally:
+                _lib.check(lib.rg_probe_gemm_only(eng._h, 0))
+            two_cta[name] = {"rows": clips * 43, "tflops": round(GEMM_GFLOP_PER_CLIP_STEP * 1e9 * clips / t2 / 1e12, 1)}
+    finally:
+        _lib.check(lib.rg_set_gemm_kernel(0, 0, 296))
+    return {"bound": "tensor", "kernel": "gemm_tc_kernel<128,*> (tcgen05.mma cta_group::1 kind::f16, 128x128 tiles, TMA-fed, TMEM "
+            "accumulator, two CTAs per SM): the 58 GEMM launches of one denoiser evaluation as their own PDL chain "
+            "(rg_probe_gemm_only), replayed from the CUDA graph, 10 evaluations back to back",
+            "mix": {f"M{c * 43}": w for c, w in mix}, "gemm2_tc_kernel_same_probe": two_cta,
             "achieved": round(ach, 1), "peak": tc_peak, "unit": "TFLOP/s", "frac": round(ach / tc_peak, 4),
             "traffic": isolated.get("traffic"), "traffic_source": isolated.get("traffic_source"),
             "peak_source": isolated.get("peak_source"), "rows": isolated.get("rows"), "in_chain_tflops": per,
