@@ -554,6 +554,33 @@ def gemm_chain_roofline(arch, n_clips, dev, flush, tc_peak, isolated, k_steps=2)
         tot_t += t_gemm * weight
         tot_f += flops * weight
     ach = tot_f / tot_t / 1e12
+    # Second roofline of the same chain: bytes that cross L2 <-> SM.  With 128x128 tiles every tile pulls its A and W
+    # panels (bf16) out of L2 = 64 flop per operand byte, and writes fp32 / bf16 outputs (+ reads the fp32 residual).
+    # Denominator: an L2-resident copy (24 MB buffers, read + write bytes) measured here, like the HBM figure.
+    def chain_l2_bytes(M):
+        tiles_m = (M + 127) // 128
+        layer = [(1536, 512, 4, 0), (512, 512, 6, 4), (1536, 512, 4, 0), (512, 2048, 6, 0), (1024, 512, 2, 0),
+                 (512, 1024, 4, 0), (512, 512, 6, 4)]             # (N, K, output bytes / element, residual bytes / element)
+        tot = 0
+        for N, K, ob, rb in layer * C.NUM_LAYERS + [(512, 512, 4, 0), (512, 512, 4, 0)]:
+            tot += tiles_m * (N // 128) * (128 * K * 2 + 128 * K * 2) + M * N * (ob + rb)
+        return tot
+    src, dst = torch.empty(24 << 20, dtype=torch.uint8, device=dev), torch.empty(24 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(5):
+        dst.copy_(src)
+    a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a_.record()
+    for _ in range(50):
+        dst.copy_(src)
+    b_.record()
+    torch.cuda.synchronize()
+    l2_copy = 50 * 2 * src.numel() / (a_.elapsed_time(b_) / 1e3) / 1e9
+    l2_ach = chain_l2_bytes(clips * 43) / t_gemm / 1e9          # the fused level (measured last)
+    l2 = {"bound": "l2", "achieved": round(l2_ach, 1), "peak": round(l2_copy, 1), "unit": "GB/s", "frac": round(l2_ach / l2_copy, 3),
+          "rows": clips * 43, "peak_source": "measured here: torch copy between two 24 MB (L2-resident) buffers, read + write bytes",
+          "bytes_per_evaluation": chain_l2_bytes(clips * 43),
+          "note": "operand panels re-read per 128x128 tile (64 flop/B) + outputs + residual: the chain moves this through L2 "
+                  "at the copy rate, i.e. the dense GEMMs of the step are L2-bandwidth-bound, not tensor-bound"}
     # the same probe with the 2-CTA kernel forced (cta_group::2, 256x256 pair tiles, TMA-store epilogue), fused shape
     two_cta = {}
     try:
@@ -574,7 +601,7 @@ def gemm_chain_roofline(arch, n_clips, dev, flush, tc_peak, isolated, k_steps=2)
     return {"bound": "tensor", "kernel": "gemm_tc_kernel<128,*> (tcgen05.mma cta_group::1 kind::f16, 128x128 tiles, TMA-fed, TMEM "
             "accumulator, two CTAs per SM): the 58 GEMM launches of one denoiser evaluation as their own PDL chain "
             "(rg_probe_gemm_only), replayed from the CUDA graph, 10 evaluations back to back",
-            "mix": {f"M{c * 43}": w for c, w in mix}, "gemm2_tc_kernel_same_probe": two_cta,
+            "mix": {f"M{c * 43}": w for c, w in mix}, "gemm2_tc_kernel_same_probe": two_cta, "l2_roofline": l2,
             "achieved": round(ach, 1), "peak": tc_peak, "unit": "TFLOP/s", "frac": round(ach / tc_peak, 4),
             "traffic": isolated.get("traffic"), "traffic_source": isolated.get("traffic_source"),
             "peak_source": isolated.get("peak_source"), "rows": isolated.get("rows"), "in_chain_tflops": per,
