@@ -341,7 +341,10 @@ def run_b200(args):
                     "sync": {"value": round(e2e_sync_value, 2), "ms_per_step": round(1e3 * t_sync / args.steps, 3),
                              "api": "MotionDiffusion.forward(**host_batch), one synchronous call per step"}},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
-            "cpu_baseline": cpu_baseline(sample_seconds=args.cpu_seconds), "knn": knn,
+            # the reference's own CPU code next to the GPU number: at N = 1 only (the other ranks would sit in a collective
+            # while rank 0 computes for tens of seconds; the driver's reference arm covers every N)
+            "cpu_baseline": cpu_baseline(sample_seconds=args.cpu_seconds) if world == 1 and args.cpu_seconds > 0 else None,
+            "knn": knn,
             "configs0": configs0, "tiers": tiers, "longform": longform, "elementwise": elementwise,
             "gflop_per_clip_step": GFLOP_PER_CLIP_STEP,
             "achieved_tflops_loop": round(value * GFLOP_PER_CLIP_STEP / 1e3 / world, 2),
@@ -943,6 +946,7 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)              # torchrun exports OMP_NUM_THREADS=1: undo it before the first CPU op
     nc, ne = cpu_sizes(args.cpu_seconds / max(1, args.steps), threads)
     for _ in range(min(args.warmup, 1)):                        # the calibration run above already warmed up
         cpu_sample(1, 1, threads)
