@@ -158,6 +158,28 @@ def synthetic_vae_state_dict(shapes, seed):
     return sd
 
 
+def write_vae_files(root, seed0=300, latent_dim=512, **vae_kw):
+    """Synthetic YAML + checkpoint per body part, laid out as the reference's load_vae expects
+    (diffusion_transformer.py:151-167): the shipped VAE YAMLs / checkpoints are not in the reference repo, so the
+    bench's `e2e.vae_codec` figure and the codec tests build the four TransformerVAEs from these files.  Returns the
+    `vae_cfg` dict for the denoiser config."""
+    import os
+    import yaml
+    from .vae import TransformerVAE
+    cfg = {"frame_chunk_size": C.FRAME_CHUNK, "latent_dim": latent_dim}
+    for i, part in enumerate(("upper", "hands", "face", "lowertrans")):
+        args = vae_args(part, latent_dim=latent_dim, **vae_kw)
+        d = os.path.join(root, part)
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, "cfg.yaml"), "w") as f:
+            yaml.safe_dump(args, f)
+        shapes = {k: tuple(v.shape) for k, v in TransformerVAE(args).state_dict().items()}
+        torch.save({"model_state": synthetic_vae_state_dict(shapes, seed0 + i)},
+                   os.path.join(d, os.path.basename(args["test_ckpt"])))      # load_vae looks next to the YAML
+        cfg[f"{part}_cfg"] = os.path.join(d, "cfg.yaml")
+    return cfg
+
+
 def synthetic_conditions(n_clips, seed=1234, first_clip=0):
     """Per-clip condition features of the len150@15fps shape: BERT-like
     `word` [B,150,768], wav2vec-like `audio` [B,499,768], `speaker_ids` [B,150] int64.
