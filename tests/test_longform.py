@@ -164,3 +164,31 @@ def test_postprocess_recompose_and_upsample_vs_reference():
     assert rel_l2(aa, t("aa30")) < 1e-4
     with pytest.raises(ValueError):
         upsample_motion(motion, t("facial"), t("trans"), 15, 40)
+
+
+@pytest.mark.gpu
+def test_postprocess_and_crossfade_on_device(golden):
+    """SURVEY 8f.3 on the device: recomposition, 15->30 fps up-sampling and the 6D cross-fade run on CUDA tensors
+    (they follow the decode on the GPU in MotionDiffusion / LongformSynthesizer) and agree with the reference's
+    golden outputs like the host path does."""
+    import os
+    import numpy as np
+    from conftest import GOLDEN, rel_l2
+    from rag_gesture_b200.postprocess import recompose_motion, upsample_motion
+    dev = torch.device("cuda:0")
+    g = np.load(os.path.join(GOLDEN, "postprocess.npz"))
+    t = lambda k: torch.from_numpy(g[k]).to(dev)
+    motion = recompose_motion(t("part_upper"), t("part_lower"), t("part_hands"), t("part_face"),
+                              g["mask_upper"], g["mask_lower"], g["mask_hands"], g["mask_face"])
+    assert motion.is_cuda and torch.equal(motion.cpu(), torch.from_numpy(g["motion"]))
+    aa, facial, trans = upsample_motion(motion, t("facial"), t("trans"), 15, 30)
+    assert aa.is_cuda and torch.allclose(facial.cpu(), torch.from_numpy(g["facial30"]), atol=1e-6)
+    assert torch.allclose(trans.cpu(), torch.from_numpy(g["trans30"]), atol=1e-6)
+    Ra = LF.axis_angle_to_matrix(aa.reshape(2, 40, 55, 3)).cpu()
+    Rb = LF.axis_angle_to_matrix(torch.from_numpy(g["aa30"]).reshape(2, 40, 55, 3))
+    assert rel_l2(Ra, Rb) < 1e-5
+    gc = golden("rotation_crossfade")
+    out = LF.crossfade_rotations(torch.from_numpy(gc["prev"]).to(dev), torch.from_numpy(gc["new"]).to(dev))
+    R1 = LF.axis_angle_to_matrix(out.reshape(2, 15, 7, 3)).cpu()
+    R2 = LF.axis_angle_to_matrix(torch.from_numpy(gc["out"]).reshape(2, 15, 7, 3))
+    assert torch.allclose(R1, R2, atol=2e-5)
