@@ -306,14 +306,19 @@ class ReGestureTransformer(nn.Module):
     def _weights_key(self):
         """Fingerprint of the parameter set the packed device engine was built from: the epoch bumped by this
         module's load_state_dict / .to() / .cuda() hooks plus the storage address and in-place version counter of
-        EVERY denoiser parameter and buffer (about 400 tensors, a few hundred microseconds).  A checkpoint loaded
-        through a parent module (MotionDiffusion.load_state_dict, mmcv load_checkpoint), a strict=False partial
-        load or an in-place edit of any tensor therefore rebuilds the engine.  (Edits that bypass the version
-        counter, e.g. through .data, still need `invalidate_engine()`.)"""
+        EVERY denoiser parameter and buffer.  A checkpoint loaded through a parent module
+        (MotionDiffusion.load_state_dict, mmcv load_checkpoint: in-place copies into the same Parameter objects), a
+        strict=False partial load or an in-place edit of any tensor therefore rebuilds the engine.  The tensor list
+        is collected once per epoch (walking state_dict() costs ~2 ms; this runs on every rg_engine() call, i.e.
+        several times per batch), the fingerprint itself is ~100 us.  Edits that bypass the version counter (through
+        .data) or that REPLACE a Parameter object need `invalidate_engine()`."""
+        cached = getattr(self, "_key_tensors", None)
+        if cached is None or cached[0] != self._epoch:
+            tensors = [t for name, t in self.state_dict(keep_vars=True).items()
+                       if not name.startswith(("gesture_rep_encoder.", "database."))]
+            cached = self._key_tensors = (self._epoch, tensors)
         ptr = ver = 0
-        for name, t in self.state_dict(keep_vars=True).items():
-            if name.startswith(("gesture_rep_encoder.", "database.")):
-                continue
+        for t in cached[1]:
             ptr = (ptr * 1000003 + t.data_ptr()) & 0xFFFFFFFFFFFFFFFF
             ver += t._version
         return (self._epoch, ptr, ver)
@@ -346,7 +351,14 @@ class ReGestureTransformer(nn.Module):
             self._engine_key, self._sched_key, self._state_cache = key, None, (None, None)
         if diffusion is not None:
             # keyed on the schedule's CONTENT (timestep map + alpha-bar table): id() can alias after garbage collection
-            skey = (tuple(int(t) for t in diffusion.timestep_map), diffusion.alphas_cumprod.tobytes())
+            skey = getattr(diffusion, "_rg_sched_key", None)
+            if skey is None or skey[0] != len(diffusion.timestep_map):
+                skey = (len(diffusion.timestep_map), tuple(int(t) for t in diffusion.timestep_map),
+                        diffusion.alphas_cumprod.tobytes())
+                try:
+                    diffusion._rg_sched_key = skey      # content hash computed once per schedule object
+                except AttributeError:
+                    pass
             if self._sched_key != skey:
                 self._engine.set_schedule(diffusion.timestep_map, diffusion.coef_table())
                 self._sched_key = skey

@@ -517,3 +517,35 @@ def test_graph_replay_is_bit_identical(which, model, tc_model, diffusion, dev):
         assert all(torch.equal(a, b) for a, b in zip(inv_g, inv_d))
     finally:
         eng.set_graphs(True)
+
+
+def test_engine_follows_weight_changes(dev, sd0):
+    """the packed device engine is rebuilt when ANY parameter changes -- an in-place edit of a middle
+    layer, and a checkpoint loaded through a PARENT module (whose load_state_dict never calls the child's
+    override) -- not only when the first / last tensor does."""
+    import rag_gesture_b200 as R
+    arch = R.build_architecture(C.model_cfg(), database=None)
+    arch.model.load_state_dict(sd0, strict=False)
+    arch = arch.to(dev).eval()
+    m = arch.model
+    B = 2
+    kw = _kw(m, S.synthetic_conditions(B, seed=121), B, dev)
+    x = S.synthetic_latents(B, seed=122).to(dev)
+    t = torch.full((B,), 300, device=dev)
+    with torch.no_grad():
+        base = m(x, t, **kw).clone()
+        m.temporal_decoder_blocks[3].ffn.linear1.weight.mul_(1.5)          # in-place edit of a middle layer
+        edited = m(x, t, **kw).clone()
+    assert not torch.equal(base, edited)
+    sd1 = S.synthetic_state_dict(5)
+    arch.load_state_dict({"model." + k: v for k, v in sd1.items()}, strict=False)   # through the parent
+    with torch.no_grad():
+        m._state_cache = (None, None)
+        kw = _kw(m, S.synthetic_conditions(B, seed=121), B, dev)
+        other = m(x, t, **kw).clone()
+    ref = R.build_submodule(C.denoiser_cfg(), database=None, use_retrieval_for_test=False)
+    ref.load_state_dict(sd1, strict=False)
+    ref = ref.to(dev).eval()
+    with torch.no_grad():
+        want = ref(x, t, **_kw(ref, S.synthetic_conditions(B, seed=121), B, dev))
+    assert torch.equal(other, want)
