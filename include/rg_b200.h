@@ -181,6 +181,10 @@ int rg_probe_gemm_tc(const float* x, const float* W, const float* b, float* out,
  * epilogues as in the step, without the attention and row kernels between them (outputs are then meaningless).
  * Time a few evaluations with CUDA events, then switch it off. */
 int rg_probe_gemm_only(rg_handle h, int on);
+/* Measurement probe for bench.py's second GEMM roofline: read bandwidth L2 -> SMs.  Every SM streams `buf`
+ * (bytes <= ~64 MB so that it stays L2-resident) `passes` times with 128-bit loads; *gb_per_s receives
+ * bytes * passes / CUDA-event time.  Synchronises. */
+int rg_probe_l2_read(const void* buf, int64_t bytes, int passes, float* gb_per_s, void* stream);
 /* Which tcgen05 GEMM kernel the tensor-core tiers launch (process-wide; results are bit-identical: all kernels
  * accumulate the K blocks in the same order in an fp32 TMEM accumulator and share the epilogue arithmetic):
  *   mode 0 (default): automatic -- the 2-CTA kernel (256x256 tile per CTA pair, tcgen05.mma.cta_group::2, TMA-store

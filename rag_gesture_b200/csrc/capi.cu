@@ -89,7 +89,7 @@ struct rg_model {
     int fuse_styl_max;       // largest batch (clips) that takes the attention kernels fused with the Stylization prologue
     int attn_mode;           // attention cores: 0 fp32 SIMT, 1 TF32 mma.sync (bf16 tier), 2 3xTF32 (bf16x3 tier)
     std::vector<LayerTc> tc;
-    W16 tc_joint, tc_out, tc_kv[3];
+    W16 tc_joint, tc_out, tc_kv[3], tc_text, tc_audio;
     void* kv_a16;
     int device;
     std::vector<void*> allocs;
@@ -400,6 +400,10 @@ extern "C" int rg_create(const rg_config* cfg, int n_tensors, const char* const*
         m->tc.resize(L);
         TRY(make_w16(m, m->W_joint, D, D, &m->tc_joint));
         TRY(make_w16(m, m->W_out, D, D, &m->tc_out));
+        if (cfg->text_dim % 64 == 0) {          // condition pre-projections on the tensor cores too
+            TRY(make_w16(m, m->W_text, D, cfg->text_dim, &m->tc_text));
+            TRY(make_w16(m, m->W_audio, D, cfg->text_dim, &m->tc_audio));
+        }
         for (int c = 0; c < 3; ++c) TRY(make_w16(m, m->Wkv_all[c], L * 2 * D, D, &m->tc_kv[c]));
         for (int l = 0; l < L; ++l) {
             const Layer& ly = m->layers[l];
@@ -529,10 +533,36 @@ extern "C" int rg_encode_conditions(rg_handle m, const float* word, const float*
     if (!m) return rg_fail("rg_encode_conditions: null handle");
     cudaStream_t st = (cudaStream_t)stream;
     const int D = RG_D, TD = m->cfg.text_dim;
-    if (word && xf_text)
-        LAUNCH(rg_launch_gemm_f32(mk_gemm(word, TD, m->W_text, m->b_text, xf_text, D, B * n_text, D, TD, RG_EPI_BIAS), st));
-    if (audio && xf_audio)
-        LAUNCH(rg_launch_gemm_f32(mk_gemm(audio, TD, m->W_audio, m->b_audio, xf_audio, D, B * n_audio, D, TD, RG_EPI_BIAS), st));
+    // text_pre_proj / audio_pre_proj (diffusion_transformer.py:544-606): 2*rows*512*768 flop per condition, once per
+    // clip.  Tensor-core tiers: the rows are split into bf16 planes and go through the tcgen05 GEMM (12 K blocks);
+    // the fp32 tier keeps the FMA GEMM.
+    const bool tc = m->cfg.precision != RG_PREC_FP32 && TD % 64 == 0;
+    const float* src[2] = {word, audio};
+    float* dst[2] = {xf_text, xf_audio};
+    const int nrow[2] = {B * n_text, B * n_audio};
+    const float* Wf[2] = {m->W_text, m->W_audio};
+    const float* bf[2] = {m->b_text, m->b_audio};
+    const W16* Wt[2] = {&m->tc_text, &m->tc_audio};
+    for (int c = 0; c < 2; ++c) {
+        if (!src[c] || !dst[c] || nrow[c] <= 0) continue;
+        if (!tc) {
+            LAUNCH(rg_launch_gemm_f32(mk_gemm(src[c], TD, Wf[c], bf[c], dst[c], D, nrow[c], D, TD, RG_EPI_BIAS), st));
+            continue;
+        }
+        const int P = m->planes;
+        rg_keep_mempool();
+        void* a16 = nullptr;
+        CU(cudaMallocAsync(&a16, (size_t)nrow[c] * TD * P * 2, st));
+        int rc = 0;
+        cudaError_t e = rg_launch_split_bf16(src[c], TD, a16, TD * P, P == 2 ? TD : 0, nrow[c], TD, st);
+        CUtensorMap tmA;
+        if (e == cudaSuccess) { ++g_launches; e = rg_make_tensor_map(&tmA, a16, nrow[c], (long long)TD * P, (long long)TD * P, 128); }
+        if (e == cudaSuccess)
+            rc = tc_gemm(m, tmA, TD, *Wt[c], bf[c], nrow[c], D, TD, RG_EPI_BIAS, nullptr, dst[c], D, nullptr, 0, st);
+        cudaFreeAsync(a16, st);                 // stream-ordered: released after the GEMM that reads it
+        if (e != cudaSuccess) return rg_fail("rg_encode_conditions: %s", cudaGetErrorString(e));
+        if (rc) return 1;
+    }
     if (spk_ids && xf_spk)
         LAUNCH(rg_launch_gather_rows(m->spk_table, (const long long*)spk_ids, xf_spk, (long long)B * n_spk,
                                      m->cfg.num_speakers, st));
@@ -1083,6 +1113,41 @@ extern "C" int rg_probe_gemm_tc(const float* x, const float* W, const float* b, 
     *median_ms = ts[ts.size() / 2];
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaFree(a16); cudaFree(w16);
+    return 0;
+}
+// L2 -> SM read bandwidth probe: every SM streams an L2-resident buffer with 128-bit loads, `passes` times
+__global__ void __launch_bounds__(512) l2_read_kernel(const float4* __restrict__ p, long long n4, int passes, float* sink) {
+    float acc = 0.f;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (int it = 0; it < passes; ++it)
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += 4 * stride) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = (i + u * stride < n4) ? __ldcg(p + i + u * stride) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc += v[u].x + v[u].y + v[u].z + v[u].w;
+        }
+    if (acc == 1.2345e-30f) *sink = acc;        // keeps the loads alive
+}
+extern "C" int rg_probe_l2_read(const void* buf, int64_t bytes, int passes, float* gb_per_s, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!buf || bytes < 1024 || passes < 1 || !gb_per_s) return rg_fail("rg_probe_l2_read: bad argument");
+    float* sink = nullptr;
+    CU(cudaMalloc((void**)&sink, 4));
+    const long long n4 = bytes / 16;
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    l2_read_kernel<<<148 * 2, 512, 0, st>>>((const float4*)buf, n4, 2, sink);       // warm: the buffer now sits in L2
+    CU(cudaEventRecord(e0, st));
+    l2_read_kernel<<<148 * 2, 512, 0, st>>>((const float4*)buf, n4, passes, sink);
+    CU(cudaEventRecord(e1, st));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    *gb_per_s = (float)((double)n4 * 16.0 * passes / (ms * 1e-3) / 1e9);
+    rg_count_launch(2);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
     return 0;
 }
 extern "C" int rg_set_graphs(rg_handle m, int on) {
