@@ -37,6 +37,8 @@ B_PER_GPU, N_DB, STEPS = 64, 4096, 50
 GFLOP_PER_CLIP_STEP = 3.348          # algorithmic, invariants hoisted
 GEMM_GFLOP_PER_CLIP_STEP = 3.291     # dense-GEMM share of the above
 GUIDANCE = [0] * 25 + list(range(25))   # decreasing_till_25 (tools/visualize.py:90-91)
+WORKLOAD = ("configs[1]: 64 clips/GPU guided DDIM (discourse retrieval, inversion + insertion guidance "
+            "decreasing_till_25, len150@15fps)")
 
 
 def peaks():
@@ -360,8 +362,7 @@ def run_b200(args):
             "warmup": args.warmup, "ms_per_step": round(1e3 * t_hot / args.steps, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": {"bf16": "bf16", "bf16x3": "bf16x3", "fp32": "f32"}[args.precision],
             "data": "synthetic",
-            "config": {"workload": "configs[1]: 64 clips/GPU guided DDIM (discourse retrieval, inversion + "
-                                   "insertion guidance decreasing_till_25, len150@15fps)",
+            "config": {"workload": WORKLOAD,
                        "clips_per_gpu": B, "exemplars_rank0": E, "clip_steps_per_step_rank0": clip_steps,
                        "db_entries": N_DB, "ddim_steps": STEPS,
                        "precision": {"bf16": "tcgen05 bf16 operands, fp32 TMEM accumulate (parity tier rel-L2 <= 2e-2)",
@@ -925,11 +926,14 @@ def _cpu_sample_text(kind, n_clips, n_exemplars, cs, dt, threads):
 
 
 def cpu_sizes(sample_seconds, threads):
-    """Clips / exemplars of the bounded sample: the B : E ratio of configs[1] (64 : 96), scaled so that all 50
-    levels take about `sample_seconds`."""
-    cs, dt, _ = cpu_sample(2, 3, threads)                       # calibration = warm-up: 250 clip-steps
+    """Clips / exemplars of the bounded sample: the B : E ratio of configs[1] (64 : 96) where the budget allows,
+    scaled so that all 50 levels of both loops take about `sample_seconds`; never below 1 clip + 1 exemplar."""
+    cs, dt, _ = cpu_sample(1, 1, threads)                       # calibration = warm-up: 100 clip-steps
     rate = cs / dt
-    units = max(1, min(8, int(rate * sample_seconds / STEPS / 5)))      # 1 unit = 2 clips + 3 exemplars
+    budget = rate * sample_seconds / STEPS                      # clips + exemplars that fit
+    if budget < 4:
+        return 1, 1
+    units = max(1, min(8, int(budget / 5)))                     # 1 unit = 2 clips + 3 exemplars
     return 2 * units, 3 * units
 
 
@@ -987,7 +991,8 @@ def run_reference(args):
         return
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)              # torchrun exports OMP_NUM_THREADS=1: undo it before the first CPU op
-    nc, ne = cpu_sizes(args.cpu_seconds / max(1, args.steps), threads)
+    # whole run (K steps) bounded to about 2.5 minutes of host time; each step is one sample of both loops
+    nc, ne = cpu_sizes(max(args.cpu_seconds, 150.0) / max(1, args.steps), threads)
     for _ in range(min(args.warmup, 1)):                        # the calibration run above already warmed up
         cpu_sample(1, 1, threads)
     cs_tot, t_tot, kind = 0, 0.0, "port"
@@ -1000,7 +1005,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": round(v, 2), "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * t_tot / args.steps, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1] guided DDIM (bounded sample of the same workload on host cores)"},
+        "config": {"workload": WORKLOAD, "clips_per_gpu": B_PER_GPU, "db_entries": N_DB, "ddim_steps": STEPS,
+                   "sample": f"bounded sample of that workload on the host cores: {nc} clips + {ne} exemplars per step, all 50 "
+                             "levels of the inversion and the guided loop (reference's own code, no retrieval kernels)"},
         "cpu_baseline": {"value": round(v, 2), "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": round(v, 2), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}), flush=True)
