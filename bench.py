@@ -134,8 +134,8 @@ def run_b200(args):
 
     from rag_gesture_b200 import _lib
     prec = {"bf16": _lib.PREC_BF16, "bf16x3": _lib.PREC_BF16X3, "fp32": _lib.PREC_FP32}[args.precision]
-    if args.gemm_kernel or args.gemm2_min_rows or args.gemm2_persist_tiles:
-        _lib.check(_lib.load().rg_set_gemm_kernel(args.gemm_kernel, args.gemm2_min_rows, args.gemm2_persist_tiles))
+    if args.gemm_kernel or args.gemm2_min_rows or args.gemm2_persist_tiles or args.pair128_min_rows:
+        _lib.check(_lib.load().rg_set_gemm_kernel(args.gemm_kernel, args.gemm2_min_rows, args.gemm2_persist_tiles, args.pair128_min_rows))
     cfg = C.model_cfg()
     cfg["use_retrieval_for_test"] = True
     cfg["model"]["precision"] = prec
@@ -626,7 +626,7 @@ def gemm_chain_roofline(arch, n_clips, dev, flush, tc_peak, isolated, k_steps=2)
     two_cta = {}
     try:
         for name, pt in (("persistent_2acc", 1), ("one_tile_per_pair", 10 ** 6)):
-            _lib.check(lib.rg_set_gemm_kernel(2, 0, pt))
+            _lib.check(lib.rg_set_gemm_kernel(2, 0, pt, 0))
             for _ in range(3):
                 step()
             _lib.check(lib.rg_probe_gemm_only(eng._h, 1))
@@ -638,7 +638,7 @@ def gemm_chain_roofline(arch, n_clips, dev, flush, tc_peak, isolated, k_steps=2)
                 _lib.check(lib.rg_probe_gemm_only(eng._h, 0))
             two_cta[name] = {"rows": clips * 43, "tflops": round(GEMM_GFLOP_PER_CLIP_STEP * 1e9 * clips / t2 / 1e12, 1)}
     finally:
-        _lib.check(lib.rg_set_gemm_kernel(0, 0, 296))
+        _lib.check(lib.rg_set_gemm_kernel(0, 0, 296, 0))
     return {"bound": "tensor", "kernel": "gemm_tc_kernel<128,*> (tcgen05.mma cta_group::1 kind::f16, 128x128 tiles, TMA-fed, TMEM "
             "accumulator, two CTAs per SM): the 58 GEMM launches of one denoiser evaluation as their own PDL chain "
             "(rg_probe_gemm_only), replayed from the CUDA graph, 10 evaluations back to back",
@@ -1024,7 +1024,8 @@ if __name__ == "__main__":
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--ncu-steps", type=int, default=0, help="profiling pass: loops cut to S levels, nothing timed")
     ap.add_argument("--longform-seconds", type=float, default=600.0, help="configs[4] stream length (0: skip)")
-    ap.add_argument("--gemm-kernel", type=int, default=0, choices=[0, 1, 2],
+    ap.add_argument("--pair128-min-rows", type=int, default=0, help="row threshold of the pair128 kernel (0: library default)")
+    ap.add_argument("--gemm-kernel", type=int, default=0, choices=[0, 1, 2, 3],
                     help="rg_set_gemm_kernel: 0 automatic, 1 always the 128x128 kernel, 2 the 2-CTA kernel when eligible")
     ap.add_argument("--gemm2-min-rows", type=int, default=0, help="row threshold of the automatic choice (0: library default)")
     ap.add_argument("--gemm2-persist-tiles", type=int, default=0, help="pair tiles from which the 2-CTA kernel is persistent (0: default)")

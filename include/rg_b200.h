@@ -187,14 +187,16 @@ int rg_probe_gemm_only(rg_handle h, int on);
 int rg_probe_l2_read(const void* buf, int64_t bytes, int passes, float* gb_per_s, void* stream);
 /* Which tcgen05 GEMM kernel the tensor-core tiers launch (process-wide; results are bit-identical: all kernels
  * accumulate the K blocks in the same order in an fp32 TMEM accumulator and share the epilogue arithmetic):
- *   mode 0 (default): automatic -- the 2-CTA kernel (256x256 tile per CTA pair, tcgen05.mma.cta_group::2, TMA-store
- *          epilogue) for launches of at least `min_rows` rows whose N is a multiple of 256, the 128x128
- *          one-tile-per-CTA kernel otherwise;
- *   mode 1: always the 128x128 kernel;   mode 2: the 2-CTA kernel whenever the shape allows.
- * The 2-CTA kernel runs one tile per pair with two CTAs per SM below `persist_tiles` pair tiles, and as a persistent
- * kernel with two TMEM accumulator stages from there on.  min_rows / persist_tiles <= 0 keep the current values
- * (defaults 16384 / 296).  Used by the parity tests and bench.py. */
-int rg_set_gemm_kernel(int mode, int min_rows, int persist_tiles);
+ *   mode 0 (default): automatic -- by row count: the pair128 kernel from `pair128_min_rows` rows on, the 2-CTA 256x256
+ *          kernel from `min_rows` rows on (N a multiple of 256), the 128x128 one-tile-per-CTA kernel otherwise;
+ *   mode 1: always the 128x128 kernel (tcgen05.mma.cta_group::1, 64 flop per operand byte);
+ *   mode 2: the 2-CTA 256x256 kernel whenever the shape allows (cta_group::2, 128 flop/B, TMA-store epilogue; one tile
+ *          per pair with two CTAs per SM below `persist_tiles` pair tiles, persistent with two TMEM accumulator stages
+ *          from there on);
+ *   mode 3: the pair128 kernel whenever the shape allows (cta_group::2, a CTA pair shares each 128-row weight tile:
+ *          85 flop/B, the 128x128 kernel's epilogue and CTA count).
+ * Arguments <= 0 keep the current thresholds.  Used by the parity tests and bench.py. */
+int rg_set_gemm_kernel(int mode, int min_rows, int persist_tiles, int pair128_min_rows);
 /* Diagnostics: one traced launch of the tcgen05 GEMM on zero operands (after 3 untraced ones).  trace_host
  * receives 10 int64 per CTA (grid order x-fastest): clock64 at [0] entry, [1] prologue done, [2] producer
  * past griddepcontrol.wait, [3] first operand stage landed, [4] last MMA committed, [5] accumulator visible

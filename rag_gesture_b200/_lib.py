@@ -43,7 +43,7 @@ SIGNATURES = {
     "rg_probe_gemm_tc": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _L, C.POINTER(C.c_float), _P]),
     "rg_probe_gemm_only": (_I, [_P, _I]),
     "rg_probe_l2_read": (_I, [_P, _L, _I, C.POINTER(C.c_float), _P]),
-    "rg_set_gemm_kernel": (_I, [_I, _I, _I]),
+    "rg_set_gemm_kernel": (_I, [_I, _I, _I, _I]),
     "rg_probe_gemm_trace": (_I, [_I, _I, _I, _I, _I, C.POINTER(_L), _L, _P]),
     "rg_op_layernorm": (_I, [_P, _P, _P, _P, _I, _P]),
     "rg_op_silu": (_I, [_P, _P, _L, _P]),

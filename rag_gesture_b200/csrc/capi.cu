@@ -63,9 +63,10 @@ struct Layer {
     float *ffn_g, *ffn_b, *ffn_Wo, *ffn_bo;
 };
 
-struct W16 {                 // bf16 operand planes [N, planes*K] (hi | lo) + its TMA descriptor
+struct W16 {                 // bf16 operand planes [N, planes*K] (hi | lo) + its TMA descriptors
     void* ptr;
-    CUtensorMap tm;
+    CUtensorMap tm;          // box 64 x 128 rows
+    CUtensorMap tm64;        // box 64 x 64 rows: half a weight tile per CTA of a pair (gemm_pair128_kernel)
     int N, K;
 };
 struct LayerTc { W16 qkv, sa_o, caq, fold, w1, w2, ffn_o; float* b_fold; };
@@ -125,7 +126,7 @@ struct rg_model {
     struct EvalGraph {
         const void *x, *src_mask, *qmask, *state, *x0, *ss;
         long long ss_stride, qm_stride;
-        int B, gemm_only, kmode, kmin, kpt;
+        int B, gemm_only, kmode, kmin, kpt, kp128;
         cudaGraphExec_t exec;
         long long launches;
         unsigned long long last_use;
@@ -187,6 +188,7 @@ static int make_w16(rg_model* m, const float* W, int N, int K, W16* out) {
     CU(rg_launch_split_bf16(W, K, out->ptr, K * P, P == 2 ? K : 0, N, K, 0));
     ++g_launches;
     CU(rg_make_tensor_map(&out->tm, out->ptr, N, (long long)K * P, (long long)K * P, 128));
+    CU(rg_make_tensor_map(&out->tm64, out->ptr, N, (long long)K * P, (long long)K * P, 64));
     out->N = N; out->K = K;
     return 0;
 }
@@ -629,7 +631,7 @@ static int tc_gemm(rg_model* m, const CUtensorMap& tmA, int a_w, const W16& w, c
     p.bias = bias; p.R = R; p.ldr = RG_D; p.pos = m->pos; p.pos_T = m->cfg.n_tokens;
     p.C32 = C32; p.ldc32 = ldc32; p.C16_ = C16; p.ldc16 = c16_w * m->planes;
     p.c16_lo_off = m->planes == 2 ? c16_w : 0; p.epi = epi;
-    p.tmC32 = s32; p.tmC16 = s16;
+    p.tmC32 = s32; p.tmC16 = s16; p.tmW64 = &w.tm64;
     LAUNCH(rg_launch_gemm_tc(tmA, w.tm, p, st));
     return 0;
 }
@@ -675,7 +677,7 @@ static int denoise_tc(rg_model* m, Ws& w, const float* x, int B, const float* ss
             p.bias = ly.sa_bo; p.R = w.h; p.ldr = D; p.C32 = w.h; p.ldc32 = D;
             p.C16_ = reinterpret_cast<__nv_bfloat16*>(w.a16x) + 3 * D; p.ldc16 = 4 * D * P; p.c16_lo_off = lo ? 4 * D : 0;
             p.epi = RG_EPI_BIAS_RESIDUAL;
-            p.tmC32 = &w.ts_h; p.tmC16 = &w.ts_a16x; p.c16_col0 = 3 * D;
+            p.tmC32 = &w.ts_h; p.tmC16 = &w.ts_a16x; p.c16_col0 = 3 * D; p.tmW64 = &t.sa_o.tm64;
             LAUNCH(rg_launch_gemm_tc(w.tm_a16, t.sa_o.tm, p, st));
         }
         // --- three cross-attentions on the same h, their projections and ca_mix folded into one GEMM
@@ -795,12 +797,12 @@ static int run_eval(rg_model* m, const float* x, int B, const float* ss, long lo
     };
     if (!m->use_graphs) return direct();
     rg_model::EvalGraph key = {x, src_mask, query_mask, state, x0_out, ss, ss_stride, qm_stride, B, m->gemm_only,
-                               rg_gemm_kernel_mode, rg_gemm2_min_rows, rg_gemm2_persist_tiles, nullptr, 0, 0};
+                               rg_gemm_kernel_mode, rg_gemm2_min_rows, rg_gemm2_persist_tiles, rg_pair128_min_rows, nullptr, 0, 0};
     rg_model::EvalGraph* hit = nullptr;
     for (auto& g : m->graphs)
         if (g.x == key.x && g.src_mask == key.src_mask && g.qmask == key.qmask && g.state == key.state && g.x0 == key.x0 &&
             g.ss == key.ss && g.ss_stride == key.ss_stride && g.qm_stride == key.qm_stride && g.B == key.B &&
-            g.gemm_only == key.gemm_only && g.kmode == key.kmode && g.kmin == key.kmin && g.kpt == key.kpt) { hit = &g; break; }
+            g.gemm_only == key.gemm_only && g.kmode == key.kmode && g.kmin == key.kmin && g.kpt == key.kpt && g.kp128 == key.kp128) { hit = &g; break; }
     if (!hit) {                                     // first sight: run directly (also performs every one-off init)
         if (m->graphs.size() >= 16) {
             size_t old = 0;
@@ -1066,7 +1068,9 @@ extern "C" int rg_op_linear_tc(const float* x, const float* W, const float* b, c
     p.bias = b; p.R = residual; p.ldr = N; p.C32 = out; p.ldc32 = N;
     p.C16_ = out_bf16; p.ldc16 = N * planes; p.c16_lo_off = split ? N : 0; p.epi = epi;
     p.no_pdl = 1;       // W planes were written by the split kernel just above
-    CUtensorMap ts32, ts16;
+    CUtensorMap ts32, ts16, tmW64;
+    CU(rg_make_tensor_map(&tmW64, w16, N, (long long)K * planes, (long long)K * planes, 64));
+    p.tmW64 = &tmW64;
     if (out && (reinterpret_cast<uintptr_t>(out) & 15) == 0) { CU(rg_make_store_map(&ts32, out, M, N, N, 4)); p.tmC32 = &ts32; }
     if (out_bf16 && (reinterpret_cast<uintptr_t>(out_bf16) & 15) == 0) {
         CU(rg_make_store_map(&ts16, out_bf16, M, (long long)N * planes, (long long)N * planes, 2));
@@ -1155,11 +1159,13 @@ extern "C" int rg_set_graphs(rg_handle m, int on) {
     m->use_graphs = on ? 1 : 0;
     return 0;
 }
-extern "C" int rg_set_gemm_kernel(int mode, int min_rows, int persist_tiles) {
-    if (mode < 0 || mode > 2) return rg_fail("rg_set_gemm_kernel: mode must be 0 (auto), 1 (128x128 tiles) or 2 (2-CTA tiles)");
+extern "C" int rg_set_gemm_kernel(int mode, int min_rows, int persist_tiles, int pair128_min_rows) {
+    if (mode < 0 || mode > 3)
+        return rg_fail("rg_set_gemm_kernel: mode must be 0 (auto), 1 (128x128 tiles), 2 (2-CTA 256x256 tiles) or 3 (pair128)");
     rg_gemm_kernel_mode = mode;
     if (min_rows > 0) rg_gemm2_min_rows = min_rows;
     if (persist_tiles > 0) rg_gemm2_persist_tiles = persist_tiles;
+    if (pair128_min_rows > 0) rg_pair128_min_rows = pair128_min_rows;
     return 0;
 }
 extern "C" int rg_probe_gemm_only(rg_handle m, int on) {

@@ -369,6 +369,219 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
 }
 
+// ---- 2-CTA kernel with a SHARED WEIGHT TILE and the 128x128 kernel's epilogue ("pair128") ------------------------
+// A CTA pair owns 256 rows x 128 columns: each CTA keeps a 128 x 128 fp32 accumulator (128 TMEM columns, the same
+// epilogue work and the same CTA count as gemm_tc_kernel), stages its own 128 rows of A but only 64 of the tile's
+// 128 weight rows per K block -- tcgen05.mma.cta_group::2 (UMMA 256x128x16) reads both halves.  Operand bytes per
+// CTA and K block drop from 32 KB to 24 KB (64 -> 85 flop per operand byte) and every weight tile is fetched once
+// per 256 rows: the chain is L2-bound, so that is where the time is.  4-stage ring of 24 KB, two CTAs per
+// SM, weight tiles requested before griddepcontrol.wait; epilogue: TMEM -> registers -> transpose through the idle
+// ring -> coalesced 256-byte row segments (bias / residual / pos loads and all stores contiguous), identical
+// arithmetic and operation order to gemm_tc_kernel, hence bit-identical results.
+constexpr int P_BN = 128, P_STAGES = 4;
+constexpr int P_A_BYTES = BM * BK * 2, P_B_BYTES = (P_BN / 2) * BK * 2, P_STAGE_BYTES = P_A_BYTES + P_B_BYTES;
+
+template <int SPLIT, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 2)
+gemm_pair128_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, RgGemmTc p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ __align__(8) uint64_t full_bar[P_STAGES], empty_bar[P_STAGES], tmem_full_bar;
+    __shared__ uint32_t tmem_base_smem;
+
+    rg_pdl_launch();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1;
+    const int tiles_n = p.N / P_BN;
+    const int m_pair = pair / tiles_n, n_tile = pair - m_pair * tiles_n;
+    const int m0 = m_pair * 2 * BM + (int)rank * BM, n0 = n_tile * P_BN;
+    const int nkb = p.K / BK;
+    const int total_kb = SPLIT ? 3 * nkb : nkb;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < P_STAGES; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+            mbar_init(smem_u32(&tmem_full_bar), 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(P_BN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs) =====
+        if (elect_one()) {
+            auto coords = [&](int j, int& ka, int& kw) {
+                const int pass = SPLIT ? j / nkb : 0, kb = j - pass * nkb;
+                ka = (pass == 1 ? p.a_lo_off : 0) + kb * BK;
+                kw = (pass == 2 ? p.w_lo_off : 0) + kb * BK;
+            };
+            auto full_leader = [&](int s) { return mapa_u32(smem_u32(&full_bar[s]), 0); };
+            const int w_row = n0 + (int)rank * (P_BN / 2);
+            const int pre = total_kb < P_STAGES ? total_kb : P_STAGES;
+            for (int j = 0; j < pre; ++j) {
+                int ka, kw;
+                coords(j, ka, kw);
+                if (rank == 0) mbar_expect_tx(smem_u32(&full_bar[j]), 2 * P_STAGE_BYTES);
+                tma_load_2d_pair(smem_u32(smem + j * P_STAGE_BYTES) + P_A_BYTES, &tmW, full_leader(j), kw, w_row);
+            }
+            rg_pdl_wait();
+            for (int j = 0; j < pre; ++j) {
+                int ka, kw;
+                coords(j, ka, kw);
+                tma_load_2d_pair(smem_u32(smem + j * P_STAGE_BYTES), &tmA, full_leader(j), ka, m0);
+            }
+            for (int j = pre; j < total_kb; ++j) {
+                const int s = j % P_STAGES, ph = (j / P_STAGES) & 1;
+                mbar_wait_g(smem_u32(&empty_bar[s]), ph ^ 1);
+                int ka, kw;
+                coords(j, ka, kw);
+                const uint32_t sa = smem_u32(smem + s * P_STAGE_BYTES);
+                if (rank == 0) mbar_expect_tx(smem_u32(&full_bar[s]), 2 * P_STAGE_BYTES);
+                tma_load_2d_pair(sa, &tmA, full_leader(s), ka, m0);
+                tma_load_2d_pair(sa + P_A_BYTES, &tmW, full_leader(s), kw, w_row);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (leader CTA) =====
+        if (rank == 0) {
+            const uint32_t idesc = make_idesc(2 * BM, P_BN);
+            for (int j = 0; j < total_kb; ++j) {
+                const int s = j % P_STAGES, ph = (j / P_STAGES) & 1;
+                mbar_wait_g(smem_u32(&full_bar[s]), ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (elect_one()) {
+                    const uint32_t sa = smem_u32(smem + s * P_STAGE_BYTES), sb = sa + P_A_BYTES;
+                    const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sb);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k)
+                        umma_bf16_pair(tmem_base, da + (k * UMMA_K * 2 >> 4), db + (k * UMMA_K * 2 >> 4), idesc, (j | k) != 0);
+                    umma_commit_pair(smem_u32(&empty_bar[s]));
+                    if (j == total_kb - 1) umma_commit_pair(smem_u32(&tmem_full_bar));
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ===== epilogue (8 warps): the row pass of gemm_tc_kernel =====
+        rg_pdl_wait();
+        mbar_wait_g(smem_u32(&tmem_full_bar), 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int lg = warp & 3, half = (warp - 2) >> 2;
+        constexpr int HC = P_BN / 2, PITCH = HC + 4;
+        float* stage = reinterpret_cast<float*>(smem) + ((warp - 2) * 32) * PITCH;     // the ring is idle in both CTAs now
+#pragma unroll 1
+        for (int c = 0; c < HC / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + half * HC + c * 32, v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            float* dst = stage + lane * PITCH + c * 32;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4)
+                *reinterpret_cast<float4*>(dst + i) = make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]),
+                                                                  __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+        }
+        __syncwarp();
+        const int sub = lane >> 4, cc = (lane & 15) * 4;
+        const int tcol = half * HC;
+        const int cbase = n0 + tcol + cc;
+        const float4 bv = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + tcol + cc)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const int row_first = m0 + lg * 32 + sub;
+        const float* rsrc = nullptr;
+        long long rstep = 0;
+        if (EPI == RG_EPI_BIAS_RESIDUAL) {
+            rsrc = p.R + (long long)row_first * p.ldr + n0 + tcol + cc;
+            rstep = 2ll * p.ldr;
+        }
+        float* c32 = p.C32 ? p.C32 + (long long)row_first * p.ldc32 + cbase : nullptr;
+        __nv_bfloat16* c16 = p.C16_ ? reinterpret_cast<__nv_bfloat16*>(p.C16_) + (long long)row_first * p.ldc16 + cbase : nullptr;
+        const float* srow = stage + sub * PITCH + cc;
+        constexpr int RB = 4;
+#pragma unroll 1
+        for (int s0 = 0; s0 < 16; s0 += RB) {
+            float4 f[RB], rr[RB];
+#pragma unroll
+            for (int i = 0; i < RB; ++i) {
+                const int row = row_first + 2 * (s0 + i);
+                f[i] = *reinterpret_cast<const float4*>(srow + 2 * (s0 + i) * PITCH);
+                rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row < p.M) {
+                    if (EPI == RG_EPI_BIAS_RESIDUAL)
+                        rr[i] = *reinterpret_cast<const float4*>(rsrc + (s0 + i) * rstep);
+                    else if (EPI == RG_EPI_BIAS_POS)
+                        rr[i] = __ldg(reinterpret_cast<const float4*>(p.pos + (long long)(row % p.pos_T) * p.N + n0 + tcol + cc));
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < RB; ++i) {
+                const int row = row_first + 2 * (s0 + i);
+                if (row >= p.M) break;
+                float4 v = f[i];
+                v.x += bv.x + rr[i].x; v.y += bv.y + rr[i].y; v.z += bv.z + rr[i].z; v.w += bv.w + rr[i].w;
+                if (EPI == RG_EPI_BIAS_GELU) {
+                    v.x = rg_gelu_fast(v.x); v.y = rg_gelu_fast(v.y); v.z = rg_gelu_fast(v.z); v.w = rg_gelu_fast(v.w);
+                } else if (EPI == RG_EPI_BIAS_SILU) {
+                    v.x = rg_silu(v.x); v.y = rg_silu(v.y); v.z = rg_silu(v.z); v.w = rg_silu(v.w);
+                }
+                if (c32) *reinterpret_cast<float4*>(c32 + 2ll * (s0 + i) * p.ldc32) = v;
+                if (c16) {
+                    __nv_bfloat16* o = c16 + 2ll * (s0 + i) * p.ldc16;
+                    const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
+                    uint2 pk;
+                    pk.x = *reinterpret_cast<const uint32_t*>(&h01); pk.y = *reinterpret_cast<const uint32_t*>(&h23);
+                    *reinterpret_cast<uint2*>(o) = pk;
+                    if (p.c16_lo_off) {
+                        const __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - __low2float(h01), v.y - __high2float(h01));
+                        const __nv_bfloat162 l23 = __floats2bfloat162_rn(v.z - __low2float(h23), v.w - __high2float(h23));
+                        pk.x = *reinterpret_cast<const uint32_t*>(&l01); pk.y = *reinterpret_cast<const uint32_t*>(&l23);
+                        *reinterpret_cast<uint2*>(o + p.c16_lo_off) = pk;
+                    }
+                }
+            }
+        }
+    }
+    __syncwarp();
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(P_BN));
+    }
+}
+
+template <int SPLIT, int EPI>
+cudaError_t launch_pair128(const CUtensorMap& tmA, const CUtensorMap& tmW64, const RgGemmTc& p, cudaStream_t st) {
+    constexpr size_t smem = (size_t)P_STAGES * P_STAGE_BYTES + 1024;
+    static_assert(P_STAGES * P_STAGE_BYTES >= 8 * 32 * (P_BN / 2 + 4) * 4, "the ring must hold the epilogue staging");
+    auto kern = gemm_pair128_kernel<SPLIT, EPI>;
+    static bool attr_done[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) attr_done[dev] = true;
+    }
+    const int pairs = (p.N / P_BN) * ((p.M + 2 * BM - 1) / (2 * BM));
+    const dim3 grid(2 * pairs);
+    if (p.no_pdl) {
+        kern<<<grid, 320, smem, st>>>(tmA, tmW64, p);
+        return cudaGetLastError();
+    }
+    return rg_launch_pdl(kern, grid, dim3(320), smem, st, tmA, tmW64, p);
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -446,6 +659,32 @@ cudaError_t rg_make_store_map(CUtensorMap* tm, const void* ptr, long long rows, 
                            const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+bool rg_gemm_pair128_eligible(const RgGemmTc& p) {
+    return p.tmW64 != nullptr && p.N % P_BN == 0 && p.K % BK == 0 && p.groups <= 1 && !p.trace && (p.C32 || p.C16_) &&
+           (!p.C32 || p.ldc32 % 4 == 0) && (!p.C16_ || (p.ldc16 % 8 == 0 && p.c16_lo_off % 4 == 0)) && (!p.R || p.ldr % 4 == 0);
+}
+
+// tmA: box 64 x 128 rows over A; p.tmW64: box 64 x 64 rows over W (each CTA stages half of a 128-row weight tile)
+cudaError_t rg_launch_gemm_pair128(const CUtensorMap& tmA, const RgGemmTc& p, cudaStream_t st) {
+    if (p.M <= 0 || p.N <= 0) return cudaSuccess;
+    if (!rg_gemm_pair128_eligible(p)) return cudaErrorInvalidValue;
+    if (p.epi == RG_EPI_BIAS_RESIDUAL && !p.R) return cudaErrorInvalidValue;
+    if (p.epi == RG_EPI_BIAS_POS && (!p.pos || p.pos_T <= 0)) return cudaErrorInvalidValue;
+    const CUtensorMap& w = *p.tmW64;
+#define RG_P128(SP)                                                                                      \
+    switch (p.epi) {                                                                                     \
+        case RG_EPI_BIAS: return launch_pair128<SP, RG_EPI_BIAS>(tmA, w, p, st);                         \
+        case RG_EPI_BIAS_RESIDUAL: return launch_pair128<SP, RG_EPI_BIAS_RESIDUAL>(tmA, w, p, st);       \
+        case RG_EPI_BIAS_GELU: return launch_pair128<SP, RG_EPI_BIAS_GELU>(tmA, w, p, st);               \
+        case RG_EPI_BIAS_POS: return launch_pair128<SP, RG_EPI_BIAS_POS>(tmA, w, p, st);                 \
+        case RG_EPI_BIAS_SILU: return launch_pair128<SP, RG_EPI_BIAS_SILU>(tmA, w, p, st);               \
+        default: return cudaErrorInvalidValue;                                                           \
+    }
+    if (p.split) { RG_P128(1) }
+    RG_P128(0)
+#undef RG_P128
 }
 
 bool rg_gemm2_eligible(const RgGemmTc& p) {

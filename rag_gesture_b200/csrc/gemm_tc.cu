@@ -309,8 +309,12 @@ int rg_gemm_kernel_mode = 0;
 int rg_gemm2_min_rows = 16384;     // measured on B200: below ~11k rows the 128x128 kernel's shorter epilogue tail wins
 int rg_gemm2_persist_tiles = 296;
 
+int rg_pair128_min_rows = 1 << 30;   // set from measurements (capi.cu / rg_set_gemm_kernel)
+
 cudaError_t rg_launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmW, const RgGemmTc& p, cudaStream_t st) {
-    if (rg_gemm_kernel_mode != 1 && rg_gemm2_eligible(p) && (rg_gemm_kernel_mode == 2 || (p.M >= rg_gemm2_min_rows && !p.trace)))
+    if (rg_gemm_pair128_eligible(p) && (rg_gemm_kernel_mode == 3 || (rg_gemm_kernel_mode == 0 && p.M >= rg_pair128_min_rows)))
+        return rg_launch_gemm_pair128(tmA, p, st);
+    if (rg_gemm_kernel_mode != 1 && rg_gemm_kernel_mode != 3 && rg_gemm2_eligible(p) && (rg_gemm_kernel_mode == 2 || (p.M >= rg_gemm2_min_rows && !p.trace)))
         return rg_launch_gemm2_tc(tmA, tmW, p, st);
     return rg_launch_gemm1_tc(tmA, tmW, p, st);
 }

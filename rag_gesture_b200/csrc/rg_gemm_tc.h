@@ -22,6 +22,9 @@ struct RgGemmTc {
     // copied into the launch) and the first column of this GEMM's output inside each map
     const CUtensorMap* tmC32; const CUtensorMap* tmC16;
     int c32_col0, c16_col0;
+    // pair128 kernel (gemm_pair128_kernel): the weight operand's map with a 64-row box (each CTA of a pair stages half
+    // of a 128-row weight tile); null = not available for this weight
+    const CUtensorMap* tmW64;
 };
 
 cudaError_t rg_make_tensor_map(CUtensorMap* tm, const void* ptr, long long rows, long long cols, long long ld,
@@ -32,8 +35,11 @@ cudaError_t rg_launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmW, co
 cudaError_t rg_launch_gemm1_tc(const CUtensorMap& tmA, const CUtensorMap& tmW, const RgGemmTc& p, cudaStream_t st);
 cudaError_t rg_launch_gemm2_tc(const CUtensorMap& tmA, const CUtensorMap& tmW, const RgGemmTc& p, cudaStream_t st);
 bool rg_gemm2_eligible(const RgGemmTc& p);
+cudaError_t rg_launch_gemm_pair128(const CUtensorMap& tmA, const RgGemmTc& p, cudaStream_t st);
+bool rg_gemm_pair128_eligible(const RgGemmTc& p);
+extern int rg_pair128_min_rows;   // automatic choice: launches of at least this many rows take the pair128 kernel
 cudaError_t rg_make_store_map(CUtensorMap* tm, const void* ptr, long long rows, long long cols, long long ld, int elem_bytes);
-// 0: automatic (2-CTA kernel from rg_gemm2_min_rows rows on), 1: always the 128x128 kernel, 2: the 2-CTA kernel whenever eligible
+// 0: automatic, 1: always the 128x128 kernel, 2: the 2-CTA 256x256 kernel whenever eligible, 3: the pair128 kernel whenever eligible
 extern int rg_gemm_kernel_mode;
 extern int rg_gemm2_min_rows;
 extern int rg_gemm2_persist_tiles;   // 2-CTA kernel: from this many pair tiles on the persistent variant runs

@@ -47,10 +47,11 @@ def linear_tc(x, weight, bias=None, residual=None, epilogue=_lib.OP_NONE, split=
     return (out, o16) if want_bf16 else out
 
 
-def set_gemm_kernel(mode=0, min_rows=0, persist_tiles=0):
-    """rg_set_gemm_kernel: 0 automatic, 1 the 128x128 one-tile-per-CTA kernel, 2 the 2-CTA kernel whenever the
-    shape allows (N % 256 == 0); persist_tiles: pair-tile count from which its persistent variant runs."""
-    _lib.check(_lib.load().rg_set_gemm_kernel(int(mode), int(min_rows), int(persist_tiles)))
+def set_gemm_kernel(mode=0, min_rows=0, persist_tiles=0, pair128_min_rows=0):
+    """rg_set_gemm_kernel: 0 automatic, 1 the 128x128 one-tile-per-CTA kernel, 2 the 2-CTA 256x256 kernel whenever
+    the shape allows (N % 256 == 0; persist_tiles: pair-tile count from which its persistent variant runs), 3 the
+    pair128 kernel (a CTA pair shares each weight tile).  Thresholds <= 0 are left as they are."""
+    _lib.check(_lib.load().rg_set_gemm_kernel(int(mode), int(min_rows), int(persist_tiles), int(pair128_min_rows)))
 
 
 def layernorm(x, gamma=None, beta=None):

@@ -69,13 +69,32 @@ SHAPES2 = [(256, 256, 64),        # one tile, one K block
            (20000, 1024, 512)]    # 316 tiles: 4-5 tiles per pair, accumulator phases flip twice
 
 
-@pytest.fixture(params=[1, 10 ** 6], ids=["persistent", "one_tile_per_pair"])
+class _Forced:
+    """ops with set_gemm_kernel(<any>) re-forcing the kernel under test (the tests switch between it and mode 1)."""
+
+    def __init__(self, ops, mode, persist_tiles):
+        self._ops, self._mode, self._pt = ops, mode, persist_tiles
+
+    def set_gemm_kernel(self, mode, *a):
+        if mode == 1:
+            self._ops.set_gemm_kernel(1)
+        else:
+            self._ops.set_gemm_kernel(self._mode, 0, self._pt)
+
+    def __getattr__(self, name):
+        return getattr(self._ops, name)
+
+
+@pytest.fixture(params=[(2, 1), (2, 10 ** 6), (3, 0)], ids=["persistent", "one_tile_per_pair", "pair128"])
 def gemm2(request, dev):
-    """Both variants of the 2-CTA kernel: persistent with two TMEM accumulator stages (persist_tiles = 1: always),
-    and one tile per pair with two CTAs per SM (persist_tiles = 1e6: never persistent)."""
+    """The cta_group::2 kernels: the 256x256 kernel persistent with two TMEM accumulator stages (persist_tiles = 1:
+    always) and one tile per pair with two CTAs per SM (persist_tiles = 1e6: never persistent), and the pair128 kernel
+    (a CTA pair shares each 128-row weight tile, 128x128 epilogue)."""
     from rag_gesture_b200 import ops
-    ops.set_gemm_kernel(2, 0, request.param)
-    yield ops
+    mode, pt = request.param
+    f = _Forced(ops, mode, pt)
+    f.set_gemm_kernel(mode)
+    yield f
     ops.set_gemm_kernel(0, 0, 296)
 
 

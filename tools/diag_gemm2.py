@@ -44,14 +44,14 @@ for B in [int(b) for b in os.environ.get("DIAG_B", "32,64,96,160,256").split(","
     out = torch.empty_like(x)
     step = lambda: eng.denoise(x, sm, qm, state, step_idx=10, out=out)
     res = {}
-    for mode, pt in ((1, 0), (2, 1), (2, 10 ** 6)):
+    for mode, pt in ((1, 0), (3, 0), (2, 1), (2, 10 ** 6)):
         ops.set_gemm_kernel(mode, 0, pt)
         t_full = ev_time(step, reps)
         res[(mode, pt)] = out.clone()
         _lib.check(lib.rg_probe_gemm_only(eng._h, 1))
         t_gemm = ev_time(step, reps)
         _lib.check(lib.rg_probe_gemm_only(eng._h, 0))
-        name = {(1, 0): "128x128      ", (2, 1): "2cta persist ", (2, 10 ** 6): "2cta one-tile"}[(mode, pt)]
+        name = {(1, 0): "128x128      ", (3, 0): "pair128      ", (2, 1): "2cta persist ", (2, 10 ** 6): "2cta one-tile"}[(mode, pt)]
         print(f"B={B:4d} M={B * 43:6d} kernel {name}: evaluation {t_full:7.3f} ms, GEMM-only chain {t_gemm:7.3f} ms = "
               f"{B * 3.291 / t_gemm:7.1f} TFLOP/s algorithmic", flush=True)
     ops.set_gemm_kernel(0, 0, 296)
