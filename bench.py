@@ -620,13 +620,14 @@ def gemm_chain_roofline(arch, n_clips, dev, flush, tc_peak, isolated, k_steps=2)
           "rows": clips * 43, "peak_source": "measured here: rg_probe_l2_read, all SMs streaming a 48 MB L2-resident buffer with 128-bit loads",
           "bytes_per_evaluation": chain_l2_bytes(clips * 43),
           "note": "tile-level bytes (operand panels re-read per 128x128 tile = 64 flop/B, + outputs + residual) over the chain's "
-                  "time, against the measured L2->SM read rate: the dense GEMMs of the step sit at the L2 bound, not the "
-                  "tensor bound (requests of the two CTAs sharing an SM for the same panel can merge, so the ratio may pass 1)"}
+                  "time, against the measured L2->SM read rate.  High, but kernels with 25 % / 50 % fewer operand bytes "
+                  "(gemm2_tc_kernel_same_probe) are not faster: ~6 us of per-launch latency x 58 launches is the other "
+                  "~40 % of the chain (DESIGN 6)"}
     # the same probe with the 2-CTA kernel forced (cta_group::2, 256x256 pair tiles, TMA-store epilogue), fused shape
     two_cta = {}
     try:
-        for name, pt in (("persistent_2acc", 1), ("one_tile_per_pair", 10 ** 6)):
-            _lib.check(lib.rg_set_gemm_kernel(2, 0, pt, 0))
+        for name, mode, pt in (("pair128_shared_weight_tile", 3, 0), ("pair256_persistent_2acc", 2, 1), ("pair256_one_tile_per_pair", 2, 10 ** 6)):
+            _lib.check(lib.rg_set_gemm_kernel(mode, 0, pt, 0))
             for _ in range(3):
                 step()
             _lib.check(lib.rg_probe_gemm_only(eng._h, 1))
