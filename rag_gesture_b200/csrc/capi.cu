@@ -111,7 +111,8 @@ struct rg_model {
     float* ss_rep;                        // [ss_rep_clips, L*5*1024] per-clip table rows (rg_denoise_groups)
     long long ss_rep_clips;
     // workspaces: rg_denoise cuts a batch into `lanes` clip ranges that run as concurrent kernel chains
-    int lanes;                            // 0: automatic
+    int lanes;                            // 0: automatic (2 lanes from auto_lane_clips clips on)
+    int auto_lane_clips;
     Ws ws[RG_MAX_LANES];
     cudaStream_t lane_st[RG_MAX_LANES];   // [0] unused: lane 0 runs on the caller's stream
     cudaEvent_t ev_fork, ev_join[RG_MAX_LANES];
@@ -126,7 +127,7 @@ struct rg_model {
     struct EvalGraph {
         const void *x, *src_mask, *qmask, *state, *x0, *ss;
         long long ss_stride, qm_stride;
-        int B, gemm_only, kmode, kmin, kpt, kp128;
+        int B, gemm_only, kmode, kmin, kpt, kp128, lanes;
         cudaGraphExec_t exec;
         long long launches;
         unsigned long long last_use;
@@ -266,7 +267,8 @@ extern "C" int rg_create(const rg_config* cfg, int n_tensors, const char* const*
     cudaGetDevice(&m->device);
     m->n_steps = 0; m->table = nullptr; m->tau_row = nullptr; m->tau_cached = -1; m->ss_rep = nullptr; m->ss_rep_clips = 0;
     memset(m->ws, 0, sizeof(m->ws));
-    m->lanes = 0; m->ev_fork = nullptr;
+    m->lanes = 0; m->ev_fork = nullptr; m->auto_lane_clips = 128;
+    if (const char* e = getenv("RG_AUTO_LANE_CLIPS")) m->auto_lane_clips = atoi(e);
     for (int i = 0; i < RG_MAX_LANES; ++i) { m->lane_st[i] = nullptr; m->ev_join[i] = nullptr; }
     m->kv_rows = 0; m->kv_ln = m->kv_buf = nullptr;
     m->tt_rows = 0; m->tt_emb = m->tt_t1 = m->tt_e = nullptr;
@@ -783,26 +785,73 @@ static int rep_rows(const float* row, float* out, long long n4_row, long long n4
     return 0;
 }
 
-// One denoiser evaluation of lane 0's workspace.  The ~100 launches of the chain depend only on buffer ADDRESSES
-// (latents, masks, state, output, the (scale|shift) rows at `ss`) and on B: the first call with a given set runs
-// them directly, the second captures the same call sequence into a CUDA graph (PDL edges included), later calls
-// replay it -- one cudaGraphLaunch instead of ~100 cudaLaunchKernelEx (host enqueue was the limit at B = 1 and
-// at 8 ranks per host).  Graphs die with the workspace (ensure_ws) and are evicted LRU beyond 16.
-static int run_eval(rg_model* m, const float* x, int B, const float* ss, long long ss_stride, const float* src_mask,
-                    const float* query_mask, long long qm_stride, const float* state, float* x0_out, cudaStream_t st) {
+// Lanes: clips are independent, so the batch can be cut into contiguous clip ranges whose kernel chains run
+// concurrently on separate streams (fork / join with events; inside a stream capture the lane streams join the
+// capture).  While one lane sits in a launch's fixed latency (PDL release, first operand stage, epilogue tail: ~6 us
+// per GEMM) the other lane's kernels run.  Measured on B200 at 160 clips: 1.60 ms -> 1.51 ms with 2 lanes,
+// 1.66 ms with 4; below ~128 clips one lane is best (the kernels no longer fill the SMs when halved).
+static int lanes_for(rg_model* m, int B) {
+    int lanes = m->lanes > 0 ? m->lanes : (B >= m->auto_lane_clips ? 2 : 1);
+    if (lanes > RG_MAX_LANES) lanes = RG_MAX_LANES;
+    if (lanes > B) lanes = B;
+    return lanes < 1 ? 1 : lanes;
+}
+static int eval_lanes(rg_model* m, int lanes, const float* x, int B, const float* ss, long long ss_stride,
+                      const float* src_mask, const float* query_mask, long long qm_stride, const float* state,
+                      float* x0_out, cudaStream_t st) {
     const bool tc = m->cfg.precision != RG_PREC_FP32;
-    auto direct = [&]() {
+    const int D = RG_D, T = m->cfg.n_tokens;
+    if (lanes <= 1)
         return (tc ? denoise_tc : denoise_f32)(m, m->ws[0], x, B, ss, ss_stride, src_mask, query_mask, qm_stride, state,
                                                x0_out, st);
-    };
+    if (!m->ev_fork) {
+        CU(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+        for (int i = 1; i < RG_MAX_LANES; ++i) {
+            CU(cudaStreamCreateWithFlags(&m->lane_st[i], cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&m->ev_join[i], cudaEventDisableTiming));
+        }
+    }
+    CU(cudaEventRecord(m->ev_fork, st));
+    const long long clip_stride = rg_state_floats_per_clip(m);
+    int rc = 0;
+    for (int i = lanes - 1; i >= 0 && !rc; --i) {         // lane 0 (the caller's stream) is enqueued last
+        const int b0 = (int)((long long)B * i / lanes), b1 = (int)((long long)B * (i + 1) / lanes);
+        cudaStream_t ls = i ? m->lane_st[i] : st;
+        if (i) CU(cudaStreamWaitEvent(ls, m->ev_fork, 0));
+        const long long r0 = (long long)b0 * T;
+        rc = (tc ? denoise_tc : denoise_f32)(m, m->ws[i], x + r0 * D, b1 - b0, ss + (long long)b0 * ss_stride, ss_stride,
+                                             src_mask + r0, query_mask ? query_mask + r0 : nullptr, qm_stride,
+                                             state + b0 * clip_stride, x0_out + r0 * D, ls);
+        if (i) CU(cudaEventRecord(m->ev_join[i], ls));
+    }
+    for (int i = 1; i < lanes; ++i) CU(cudaStreamWaitEvent(st, m->ev_join[i], 0));
+    return rc;
+}
+
+// One denoiser evaluation.  The ~100 launches of the chain depend only on buffer ADDRESSES (latents, masks, state,
+// output, the (scale|shift) rows at `ss`), on B and on the lane count: the first call with a given set runs them
+// directly, the second captures the same call sequence into a CUDA graph (PDL edges and the lanes' fork / join
+// included), later calls replay it -- one cudaGraphLaunch instead of ~100 cudaLaunchKernelEx (host enqueue was the
+// limit at B = 1 and at 8 ranks per host).  Graphs die with the workspace (ensure_ws) and are evicted
+// LRU beyond 16.
+static int run_eval(rg_model* m, const float* x, int B, const float* ss, long long ss_stride, const float* src_mask,
+                    const float* query_mask, long long qm_stride, const float* state, float* x0_out, cudaStream_t st) {
+    const int lanes = lanes_for(m, B), T = m->cfg.n_tokens;
+    for (int i = 0; i < lanes; ++i) {               // before any capture: growing a workspace drops the graphs
+        const int b0 = (int)((long long)B * i / lanes), b1 = (int)((long long)B * (i + 1) / lanes);
+        if (ensure_ws(m, m->ws[i], (long long)(b1 - b0) * T)) return 1;
+    }
+    auto direct = [&]() { return eval_lanes(m, lanes, x, B, ss, ss_stride, src_mask, query_mask, qm_stride, state, x0_out, st); };
     if (!m->use_graphs) return direct();
     rg_model::EvalGraph key = {x, src_mask, query_mask, state, x0_out, ss, ss_stride, qm_stride, B, m->gemm_only,
-                               rg_gemm_kernel_mode, rg_gemm2_min_rows, rg_gemm2_persist_tiles, rg_pair128_min_rows, nullptr, 0, 0};
+                               rg_gemm_kernel_mode, rg_gemm2_min_rows, rg_gemm2_persist_tiles, rg_pair128_min_rows, lanes,
+                               nullptr, 0, 0};
     rg_model::EvalGraph* hit = nullptr;
     for (auto& g : m->graphs)
         if (g.x == key.x && g.src_mask == key.src_mask && g.qmask == key.qmask && g.state == key.state && g.x0 == key.x0 &&
             g.ss == key.ss && g.ss_stride == key.ss_stride && g.qm_stride == key.qm_stride && g.B == key.B &&
-            g.gemm_only == key.gemm_only && g.kmode == key.kmode && g.kmin == key.kmin && g.kpt == key.kpt && g.kp128 == key.kp128) { hit = &g; break; }
+            g.gemm_only == key.gemm_only && g.kmode == key.kmode && g.kmin == key.kmin && g.kpt == key.kpt &&
+            g.kp128 == key.kp128 && g.lanes == key.lanes) { hit = &g; break; }
     if (!hit) {                                     // first sight: run directly (also performs every one-off init)
         if (m->graphs.size() >= 16) {
             size_t old = 0;
@@ -827,8 +876,7 @@ static int run_eval(rg_model* m, const float* x, int B, const float* ss, long lo
         cudaError_t e = cudaStreamBeginCapture(m->cap_st, cudaStreamCaptureModeThreadLocal);
         int rc = 1;
         if (e == cudaSuccess) {
-            rc = (tc ? denoise_tc : denoise_f32)(m, m->ws[0], x, B, ss, ss_stride, src_mask, query_mask, qm_stride, state,
-                                                 x0_out, m->cap_st);
+            rc = eval_lanes(m, lanes, x, B, ss, ss_stride, src_mask, query_mask, qm_stride, state, x0_out, m->cap_st);
             e = cudaStreamEndCapture(m->cap_st, &graph);
         }
         hit->launches = g_launches - l0;
@@ -866,46 +914,12 @@ extern "C" int rg_denoise(rg_handle m, const float* x, int B, int step_idx, int 
         }
         ssrow = m->tau_row;
     }
-    // Lanes: clips are independent, so the batch can be cut into contiguous clip ranges whose kernel chains
-    // run concurrently on separate streams.  Measured on B200 this does NOT pay: the kernels are
-    // bound by shared L2->SM bandwidth, not by launch latency, so "automatic" is one lane; rg_set_lanes
-    // keeps the mechanism available for callers that share the GPU with other work.
-    int lanes = m->lanes > 0 ? m->lanes : 1;
-    if (lanes > RG_MAX_LANES) lanes = RG_MAX_LANES;
-    if (lanes > B) lanes = B;
-    const bool tc = m->cfg.precision != RG_PREC_FP32;
-    if (lanes == 1) {
-        if (ensure_ws(m, m->ws[0], (long long)B * T)) return 1;
-        const float* row = ssrow;
-        if (m->use_graphs && step_idx >= 0) {       // the level's row at an address that does not change per level
-            if (rep_rows(ssrow, m->ss_one, NT / 4, NT / 4, st)) return 1;
-            row = m->ss_one;
-        }
-        return run_eval(m, x, B, row, 0, src_mask, query_mask, (long long)B * T, state, x0_out, st);
+    const float* row = ssrow;
+    if (m->use_graphs && step_idx >= 0) {           // the level's row at an address that does not change per level
+        if (rep_rows(ssrow, m->ss_one, NT / 4, NT / 4, st)) return 1;
+        row = m->ss_one;
     }
-    if (lanes > 1 && !m->ev_fork) {
-        CU(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
-        for (int i = 1; i < RG_MAX_LANES; ++i) {
-            CU(cudaStreamCreateWithFlags(&m->lane_st[i], cudaStreamNonBlocking));
-            CU(cudaEventCreateWithFlags(&m->ev_join[i], cudaEventDisableTiming));
-        }
-    }
-    if (lanes > 1) CU(cudaEventRecord(m->ev_fork, st));
-    const long long clip_stride = rg_state_floats_per_clip(m);
-    int rc = 0;
-    for (int i = lanes - 1; i >= 0 && !rc; --i) {         // lane 0 (the caller's stream) is enqueued last
-        const int b0 = (int)((long long)B * i / lanes), b1 = (int)((long long)B * (i + 1) / lanes);
-        cudaStream_t ls = i ? m->lane_st[i] : st;
-        if (i) CU(cudaStreamWaitEvent(ls, m->ev_fork, 0));
-        if (ensure_ws(m, m->ws[i], (long long)(b1 - b0) * T)) return 1;
-        const long long r0 = (long long)b0 * T;
-        rc = (tc ? denoise_tc : denoise_f32)(m, m->ws[i], x + r0 * D, b1 - b0, ssrow, 0, src_mask + r0,
-                                             query_mask ? query_mask + r0 : nullptr, (long long)B * T,
-                                             state + b0 * clip_stride, x0_out + r0 * D, ls);
-        if (i) CU(cudaEventRecord(m->ev_join[i], ls));
-    }
-    for (int i = 1; i < lanes; ++i) CU(cudaStreamWaitEvent(st, m->ev_join[i], 0));
-    return rc;
+    return run_eval(m, x, B, row, 0, src_mask, query_mask, (long long)B * T, state, x0_out, st);
 }
 
 extern "C" int rg_denoise_groups(rg_handle m, const float* x, int B, int n_groups, const int32_t* group_clips,
@@ -938,7 +952,6 @@ extern "C" int rg_denoise_groups(rg_handle m, const float* x, int B, int n_group
                      (long long)group_clips[g] * NT / 4, st)) return 1;
         b0 += group_clips[g];
     }
-    if (ensure_ws(m, m->ws[0], (long long)B * T)) return 1;
     return run_eval(m, x, B, m->ss_rep, NT, src_mask, query_mask, (long long)B * T, state, x0_out, st);
 }
 

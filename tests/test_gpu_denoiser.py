@@ -498,6 +498,15 @@ def test_graph_replay_is_bit_identical(which, model, tc_model, diffusion, dev):
                 assert torch.equal(out, ref[lvl]), (rep, lvl)
             eng.denoise_groups(x, prep.src_mask, prep.query_mask, prep.state, [(2, 5), (4, 44)], out=out)
             assert torch.equal(out, ref_g), rep
+        # two lanes (concurrent clip-range chains, forked and joined inside the captured graph; ragged split 6 = 3 + 3
+        # for the level call, and a group boundary inside a lane for the grouped call)
+        eng.set_lanes(2)
+        for rep in range(3):
+            eng.denoise(x, prep.src_mask, prep.query_mask, prep.state, step_idx=30, out=out)
+            assert torch.equal(out, ref[30]), ("lanes", rep)
+            eng.denoise_groups(x, prep.src_mask, prep.query_mask, prep.state, [(2, 5), (4, 44)], out=out)
+            assert torch.equal(out, ref_g), ("lanes", rep)
+        eng.set_lanes(0)
         # a larger batch grows the workspace: captured graphs must not be replayed on the moved buffers
         B2 = 40
         kw2 = _kw(mdl, S.synthetic_conditions(B2, seed=113), B2, dev)
@@ -517,6 +526,7 @@ def test_graph_replay_is_bit_identical(which, model, tc_model, diffusion, dev):
         assert all(torch.equal(a, b) for a, b in zip(inv_g, inv_d))
     finally:
         eng.set_graphs(True)
+        eng.set_lanes(0)
 
 
 def test_engine_follows_weight_changes(dev, sd0):
