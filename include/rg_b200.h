@@ -130,7 +130,7 @@ int rg_run_levels(rg_handle h, int S, float* xj, int B, int E, const float* in_s
 
 /* How many concurrent kernel chains ("lanes", contiguous clip ranges on separate streams, joined back
  * onto the caller's stream before the call returns; inside the CUDA graph they are parallel branches) one
- * rg_denoise / rg_denoise_groups evaluation uses: 0 = automatic (2 lanes from 128 clips on -- each lane's kernels
+ * rg_denoise / rg_denoise_groups evaluation uses: 0 = automatic (2 lanes from 64 clips on -- each lane's kernels
  * run while the other lane sits in a launch's fixed latency -- else 1), 1..4 fixed.  Results do not depend on the
  * setting: clips never interact inside a step. */
 int rg_set_lanes(rg_handle h, int lanes);

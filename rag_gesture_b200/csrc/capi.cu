@@ -267,7 +267,7 @@ extern "C" int rg_create(const rg_config* cfg, int n_tensors, const char* const*
     cudaGetDevice(&m->device);
     m->n_steps = 0; m->table = nullptr; m->tau_row = nullptr; m->tau_cached = -1; m->ss_rep = nullptr; m->ss_rep_clips = 0;
     memset(m->ws, 0, sizeof(m->ws));
-    m->lanes = 0; m->ev_fork = nullptr; m->auto_lane_clips = 128;
+    m->lanes = 0; m->ev_fork = nullptr; m->auto_lane_clips = 64;
     if (const char* e = getenv("RG_AUTO_LANE_CLIPS")) m->auto_lane_clips = atoi(e);
     for (int i = 0; i < RG_MAX_LANES; ++i) { m->lane_st[i] = nullptr; m->ev_join[i] = nullptr; }
     m->kv_rows = 0; m->kv_ln = m->kv_buf = nullptr;
@@ -788,8 +788,9 @@ static int rep_rows(const float* row, float* out, long long n4_row, long long n4
 // Lanes: clips are independent, so the batch can be cut into contiguous clip ranges whose kernel chains run
 // concurrently on separate streams (fork / join with events; inside a stream capture the lane streams join the
 // capture).  While one lane sits in a launch's fixed latency (PDL release, first operand stage, epilogue tail: ~6 us
-// per GEMM) the other lane's kernels run.  Measured on B200 at 160 clips: 1.60 ms -> 1.51 ms with 2 lanes,
-// 1.66 ms with 4; below ~128 clips one lane is best (the kernels no longer fill the SMs when halved).
+// per GEMM) the other lane's kernels run.  Measured on B200, graph-replayed grouped evaluation, 1 / 2 / 3
+// lanes (tools/diag_lanes.py): 64 clips 0.895 / 0.874 / 0.881 ms, 96: 1.037 / 1.029 / 1.057, 128: 1.331 / 1.213 /
+// 1.242, 160: 1.626 / 1.478 / 1.501, 224: 2.433 / 1.902 / 2.031 -> automatic = 2 lanes from 64 clips on.
 static int lanes_for(rg_model* m, int B) {
     int lanes = m->lanes > 0 ? m->lanes : (B >= m->auto_lane_clips ? 2 : 1);
     if (lanes > RG_MAX_LANES) lanes = RG_MAX_LANES;
