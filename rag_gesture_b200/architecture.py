@@ -225,8 +225,13 @@ class MotionDiffusion(nn.Module):
                     dst += [(b, o + q) for q in range(q0, q1)]
             if len(set(dst)) == len(dst):               # disjoint windows: one gather/scatter per tensor
                 if dst:
-                    ei, ri, bi, qi = (torch.tensor(v, dtype=torch.int64, device=device)
-                                      for v in (*zip(*src), *zip(*dst)))
+                    # one pinned, asynchronous copy of the four index lists: torch.tensor(list, device=cuda) is a
+                    # blocking pageable copy that makes the host wait for everything enqueued before it (the whole
+                    # previous pass), so the host could never run ahead of the device
+                    idx = torch.tensor([*zip(*src), *zip(*dst)], dtype=torch.int64)
+                    if device.type == "cuda":
+                        idx = idx.pin_memory()
+                    ei, ri, bi, qi = idx.to(device, non_blocking=True).unbind(0)
                     start_rows[bi, qi] = inv[gb.inversion_start_time][ei, ri]
                     start_mask[bi, qi] = True
                     if gb.use_guidance:

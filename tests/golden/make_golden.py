@@ -313,6 +313,25 @@ def gen_pipeline(ns):
          chain_w0=outs[0], chain_w1=outs[1])
 
 
+def gen_outpaint(ns):
+    """The outpaint branch of MotionDiffusion.forward (diffusion_architecture.py:279-283,472): no inversion, no
+    guidance; the retrieved exemplar latents placed at their query windows (`raw_motion_latents`) are blended into
+    the sample on every step of the plain DDIM loop."""
+    ds = S.SyntheticGestureDataset(N_DB, seed=7)
+    qs = S.SyntheticGestureDataset(N_QUERY, seed=8)
+    arch = build_reference_architecture(ns, ds, S.synthetic_state_dict(0))
+    batch = S.collate([qs[i] for i in [9, 14]])
+    batch["retrieval_method"] = "discourse"
+    batch["inference_kwargs"] = dict(outpaint=True, use_inversion=False, insertion_guidance=False)
+    torch.manual_seed(4242)
+    with torch.no_grad():
+        res = arch(**batch)
+    seq = res["retrieval_dict"]["raw_motion_latents"]
+    print("outpaint: rows with an exemplar latent:", int((seq != 0).any(-1).sum()))
+    save("pipeline_outpaint_b2", prev_latentout=res["prev_latentout"], pred_upper=res["pred_upper"][:, ::10],
+         n_rows=np.array(int((seq != 0).any(-1).sum())))
+
+
 def gen_rotation(ns):
     """6D cross-fade of tools/longform_synthesis.py:449-471 with the reference's rotation_conversions."""
     import importlib
@@ -437,7 +456,8 @@ def gen_codec(ns):
 
 
 GROUPS = {"rotation": gen_rotation, "schedule": gen_schedule, "denoiser": gen_denoiser, "loops": gen_loops,
-          "retrieval": gen_retrieval, "pipeline": gen_pipeline, "codec": gen_codec, "postprocess": gen_postprocess}
+          "retrieval": gen_retrieval, "pipeline": gen_pipeline, "outpaint": gen_outpaint, "codec": gen_codec,
+          "postprocess": gen_postprocess}
 
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())

@@ -348,6 +348,37 @@ def test_tc_longform_prev_latent_chain(arch_tc, dev):
     _prev_latent_chain(m, dev, tol, tier)
 
 
+def _outpaint_batch(arch, dev, tol, tier):
+    g = np.load(os.path.join(GOLDEN, "pipeline_outpaint_b2.npz"))
+    qs = S.SyntheticGestureDataset(N_QUERY, seed=8)
+    batch = S.collate([qs[i] for i in [9, 14]])
+    batch["retrieval_method"] = "discourse"
+    batch["inference_kwargs"] = dict(outpaint=True, use_inversion=False, insertion_guidance=False)
+    db = arch.model.database
+    for d in (db.test_indexes, db.test_dbounds, db.test_qbounds):
+        d.clear()
+    arch.diffusion_test.noise_fn = _cpu_noise
+    torch.manual_seed(4242)
+    res = arch(**batch)
+    seq = res["retrieval_dict"]["raw_motion_latents"]
+    assert int((seq != 0).any(-1).sum()) == int(g["n_rows"]) > 0
+    errs = (rel_l2(res["prev_latentout"].cpu(), torch.from_numpy(g["prev_latentout"])),
+            rel_l2(res["pred_upper"][:, ::10].cpu(), torch.from_numpy(g["pred_upper"])))
+    print("outpaint batch (%s tier) rel-L2 vs reference: latents %.3g, upper %.3g" % ((tier,) + errs))
+    assert max(errs) < tol
+
+
+def test_outpaint_batch_vs_reference(arch, dev):
+    """The outpaint branch (diffusion_architecture.py:279-283,472): exemplar latents blended on every step of the
+    plain loop, against the unmodified reference's output (tests/golden/make_golden.py outpaint)."""
+    _outpaint_batch(arch, dev, 1e-3, "fp32")
+
+
+def test_tc_outpaint_batch_vs_reference(arch_tc, dev):
+    m, tol, tier = arch_tc
+    _outpaint_batch(m, dev, tol, tier)
+
+
 def test_resident_corpus_matches_host_fetch(arch, dev):
     """The HBM-resident exemplar corpus (one gather per field) yields the same prepared batch as the
     per-batch host fetch + stack + H2D path it replaces."""
