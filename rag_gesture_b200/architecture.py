@@ -161,8 +161,7 @@ class MotionDiffusion(nn.Module):
         if gb.cond_inputs is not None:
             text, audio, spk = gb.cond_inputs
             with torch.no_grad():
-                gb.model_kwargs["xf_out"] = self.model.rg_engine().encode_conditions(
-                    text.to(gb.device), audio.to(gb.device), spk.to(gb.device))
+                gb.model_kwargs["xf_out"] = self.model.encode_all_conditions(text, audio, spk, gb.device)
             gb.cond_inputs = None
         return gb
 

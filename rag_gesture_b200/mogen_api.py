@@ -373,8 +373,20 @@ class ReGestureTransformer(nn.Module):
 
     def encode_spks(self, spk_ids, device):
         if self.num_speakers == 1:
-            raise NotImplementedError("num_speakers == 1 (the _spk2 config) is not supported")
+            # diffusion_transformer.py:545-546, shape quirk included: zeros [B, B, latent] (B "speaker tokens").  All
+            # tokens are equal, so the cross-attention state does not depend on their number and batching the
+            # exemplars' inversions (one zeros [E, E, latent] instead of E times [1, 1, latent]) changes nothing.
+            return torch.zeros((spk_ids.shape[0], spk_ids.shape[0], self.latent_dim), device=device)
         return self.rg_engine().encode_conditions(speaker_ids=spk_ids.to(device))["xf_spk"]
+
+    def encode_all_conditions(self, text, audio, speaker_ids, device):
+        """xf_text / xf_audio / xf_spk of a batch in one library call (raggesture.py:978-987)."""
+        eng = self.rg_engine()
+        if self.num_speakers == 1:
+            xf = eng.encode_conditions(text.to(device), audio.to(device), None)
+            xf["xf_spk"] = self.encode_spks(speaker_ids, device)
+            return xf
+        return eng.encode_conditions(text.to(device), audio.to(device), speaker_ids.to(device))
 
     def get_precompute_condition(self, text=None, raw_text=None, text_features=None, audio=None,
                                  raw_audio=None, discourse=None, prominence=None, speaker_ids=None,
@@ -382,10 +394,8 @@ class ReGestureTransformer(nn.Module):
                                  re_dict=None, device=None, sample_idx=None, sample_name=None,
                                  retrieval_method="gesture_type", **kwargs):
         if xf_out is None:
-            if self.num_speakers == 1:
-                raise NotImplementedError("num_speakers == 1 (the _spk2 config) is not supported")
             device = device if device is not None else self.out.weight.device
-            xf_out = self.rg_engine().encode_conditions(text.to(device), audio.to(device), speaker_ids.to(device))
+            xf_out = self.encode_all_conditions(text, audio, speaker_ids, device)
         output = {"xf_out": xf_out}
         if re_dict is None and self.database is not None:
             retr_conditions = dict(text=raw_text, audio=raw_audio, text_enc=text, text_features=text_features,

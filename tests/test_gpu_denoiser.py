@@ -559,3 +559,28 @@ def test_engine_follows_weight_changes(dev, sd0):
     with torch.no_grad():
         want = ref(x, t, **_kw(ref, S.synthetic_conditions(B, seed=121), B, dev))
     assert torch.equal(other, want)
+
+
+def test_single_speaker_config(dev, sd0):
+    """num_speakers == 1 (diffusion_transformer.py:545-546): the speaker condition is zeros [B, B, latent] -- the
+    reference's shape, quirk included -- and the evaluation matches the oracle run on exactly that tensor."""
+    from oracle import denoiser as OD
+    from rag_gesture_b200 import mogen_api as M
+    cfg = dict(C.denoiser_cfg(), speaker_embedding=dict(num_speakers=1))
+    sd = dict(sd0)
+    sd["speaker_embedding.weight"] = sd0["speaker_embedding.weight"][:1].clone()
+    m = M.build_submodule(cfg, database=None, use_retrieval_for_test=False)
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected
+    m = m.to(dev).eval()
+    B = 3
+    cond = S.synthetic_conditions(B, seed=131)
+    kw = _kw(m, cond, B, dev)
+    assert tuple(kw["xf_out"]["xf_spk"].shape) == (B, B, C.LATENT_DIM) and not bool(kw["xf_out"]["xf_spk"].any())
+    x = S.synthetic_latents(B, seed=132).to(dev)
+    with torch.no_grad():
+        out = m(x, torch.full((B,), 514, device=dev), **kw).cpu()
+    xf = OD.encode_conditions(sd0, cond["word"], cond["audio"], cond["speaker_ids"])
+    xf["xf_spk"] = torch.zeros(B, B, C.LATENT_DIM)
+    ref = OD.denoiser_forward(sd, x.cpu(), torch.full((B,), 514), S.motion_mask(B), xf, S.query_masks(B))
+    assert rel_l2(out, ref) < TOL_STEP
