@@ -153,6 +153,13 @@ int rg_ddim_update(rg_handle h, const float* x, const float* x0, int step_idx, i
 int rg_blend_in_seq(rg_handle h, const float* x, const float* in_seq, const float* noise,
                     int step_idx, float* out, int64_t rows, void* stream);
 
+/* 2-branch mixing of ReGestureTransformer.forward_test with scale_func_cfg (raggesture.py:1087-1111): out2 [2B,T,512]
+ * holds the text-branch rows first, then the "none"-branch rows (same clips evaluated against the unconditional
+ * cross-attention state); coef [B,4] (device) = (both, text, retr, none) per clip, joint_scale [T] (device) = the
+ * per-body-part scale of each token row.  out [B,T,512] = x_text*both*js + x_text*text*js + x_none*retr/js +
+ * x_none*none/js, every product and sum rounded to fp32 in that order. */
+int rg_mix_branches(rg_handle h, const float* out2, int B, const float* coef, const float* joint_scale, float* out,
+                    void* stream);
 /* `iters` closed-form gradient steps of the insertion guidance (gaussian_diffusion.py:1351-1378):
  * x <- x - lr * grad_x mse(x * m, in_seq), m = any(in_seq != 0, -1); numel = B*T*512 of the batch the
  * reference would have run (mse_loss 'mean').  In place. */

@@ -144,6 +144,51 @@ def denoiser_forward(sd, motion, timesteps, motion_mask, xf_out, query_mask, num
     return _lin(sd, "out", h)
 
 
+def scale_func_retr(scale_func_cfg, timestep, rng):
+    """raggesture.py:925-954: the four mixing coefficients; above t = 100 one of two sets is drawn with
+    rng.randint(0, 1) (the reference uses Python's global `random`)."""
+    w = (1 - (1000 - timestep) / 1000) * scale_func_cfg["coarse_scale"] + 1
+    if timestep > 100:
+        if rng.randint(0, 1) == 0:
+            return dict(both_coef=w, text_coef=0, retr_coef=1 - w, none_coef=0)
+        return dict(both_coef=0, text_coef=w, retr_coef=0, none_coef=1 - w)
+    both, text, retr = scale_func_cfg["both_coef"], scale_func_cfg["text_coef"], scale_func_cfg["retr_coef"]
+    return dict(both_coef=both, text_coef=text, retr_coef=retr, none_coef=1 - both - text - retr)
+
+
+def joint_scale_mask(per_joint_scale, T=43):
+    """raggesture.py:910-921: one scale per token row (separator rows keep 1)."""
+    n = (T - 3) // 4
+    m = torch.ones(T)
+    m[0:n] = per_joint_scale["upper"]
+    m[n + 1:2 * n + 1] = per_joint_scale["hands"]
+    m[2 * n + 2:3 * n + 2] = per_joint_scale["face"]
+    m[3 * n + 3:T] = per_joint_scale["lowertransl"]
+    return m
+
+
+def denoiser_forward_two_branch(sd, motion, timesteps, motion_mask, xf_out, query_mask, scale_func_cfg,
+                                per_joint_scale, rng, num_heads=16, num_layers=8):
+    """forward_test with scale_func_cfg set (raggesture.py:1041-1111): the batch is evaluated twice -- cond_type 1
+    (text branch) and cond_type 0 ("none" branch: keys - 1e6, values of the zeroed condition) -- and mixed with
+    scale_func_retr's coefficients and the per-row joint scale, in the reference's operation order."""
+    B, T, D = motion.shape
+    src_mask = motion_mask.clone().unsqueeze(-1).repeat(2, 1, 1)
+    emb = _lin(sd, "time_embed.2", F.silu(_lin(sd, "time_embed.0", timestep_embedding(timesteps, D)))).repeat(2, 1)
+    h = embed_latents(sd, motion).repeat(2, 1, 1)
+    xf = {k: v.repeat(2, 1, 1) for k, v in xf_out.items()}
+    qm = {k: v.repeat(2, 1) for k, v in query_mask.items()} if query_mask is not None else None
+    cond_type = torch.cat([torch.zeros(B, 1, 1) + 1, torch.zeros(B, 1, 1)], 0)
+    for l in range(num_layers):
+        h = decoder_layer(sd, f"temporal_decoder_blocks.{l}", h, xf, emb, src_mask, qm, cond_type, num_heads)
+    out = _lin(sd, "out", h)
+    c = scale_func_retr(scale_func_cfg, int(timesteps[0]), rng)
+    out_text, out_none = out[:B].contiguous(), out[B:].contiguous()
+    js = joint_scale_mask(per_joint_scale, T).unsqueeze(0).unsqueeze(-1).expand(B, -1, D)
+    return (out_text * c["both_coef"] * js + out_text * c["text_coef"] * js
+            + out_none * c["retr_coef"] * (1 / js) + out_none * c["none_coef"] * (1 / js))
+
+
 class OracleDenoiser:
     """Callable with the reference denoiser's call signature (gaussian_diffusion.py:529-534), so
     oracle/diffusion.py drives it the way SpacedDiffusion drives ReGestureTransformer."""

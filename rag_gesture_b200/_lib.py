@@ -38,6 +38,7 @@ SIGNATURES = {
     "rg_ddim_update": (_I, [_P, _P, _P, _I, _I, _P, _L, _P]),
     "rg_blend_in_seq": (_I, [_P, _P, _P, _P, _I, _P, _L, _P]),
     "rg_guidance_steps": (_I, [_P, _P, _P, _L, _I, _F, _L, _P]),
+    "rg_mix_branches": (_I, [_P, _P, _I, _P, _P, _P, _P]),
     "rg_op_linear": (_I, [_P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "rg_op_linear_tc": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "rg_probe_gemm_tc": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _L, C.POINTER(C.c_float), _P]),

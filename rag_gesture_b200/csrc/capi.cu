@@ -987,6 +987,15 @@ extern "C" int rg_blend_in_seq(rg_handle m, const float* x, const float* in_seq,
     return 0;
 }
 
+extern "C" int rg_mix_branches(rg_handle m, const float* out2, int B, const float* coef, const float* joint_scale,
+                               float* out, void* stream) {
+    if (!m || !out2 || !coef || !joint_scale || !out) return rg_fail("rg_mix_branches: null argument");
+    if (B <= 0) return 0;
+    LAUNCH(rg_launch_mix_branches(out2, coef, joint_scale, out, (long long)B * m->cfg.n_tokens, m->cfg.n_tokens,
+                                  (cudaStream_t)stream));
+    return 0;
+}
+
 extern "C" int rg_guidance_steps(rg_handle, float* x, const float* in_seq, int64_t rows, int iters,
                                  float lr, int64_t numel, void* stream) {
     if (iters <= 0) return 0;

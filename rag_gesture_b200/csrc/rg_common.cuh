@@ -72,6 +72,8 @@ cudaError_t rg_launch_ddim_update(const float* x, const float* x0, float* out, l
                                   cudaStream_t st);
 cudaError_t rg_launch_blend(const float* x, const float* in_seq, const float* noise, float* out,
                             long long rows, float s_ab, float s_1mab, cudaStream_t st);
+cudaError_t rg_launch_mix_branches(const float* out2, const float* coef, const float* joint_scale, float* out,
+                                   long long rows, int T, cudaStream_t st);
 cudaError_t rg_launch_guidance(float* x, const float* in_seq, long long rows, int iters,
                                float lr_2_over_n, cudaStream_t st);
 cudaError_t rg_launch_transpose_sq(const float* in, float* out, int n, cudaStream_t st);

@@ -259,6 +259,41 @@ cudaError_t rg_launch_blend(const float* x, const float* in_seq, const float* no
     if (rows <= 0) return cudaSuccess;
     return rg_launch_pdl(blend_kernel, dim3(row_blocks(rows)), dim3(256), 0, st, x, in_seq, noise, out, rows, s_ab, s_1mab);
 }
+// 2-branch mixing of forward_test (raggesture.py:1087-1111): rows [0,B*T) of `out2` = text branch, rows [B*T,2*B*T) =
+// "none" branch; per clip four coefficients (both, text, retr, none), per token row the joint scale.  Products and sums
+// in the reference's order, each rounded to fp32 (no FMA contraction).
+__global__ void __launch_bounds__(256) mix_branches_kernel(const float* out2, const float* __restrict__ coef,
+                                                          const float* __restrict__ joint_scale, float* out,
+                                                          long long rows, int T) {
+    const long long row = (long long)blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const long long clip = row / T;
+    const float js = joint_scale[row - clip * T], ijs = __fdiv_rn(1.0f, js);
+    const float both = coef[clip * 4], text = coef[clip * 4 + 1], retr = coef[clip * 4 + 2], none = coef[clip * 4 + 3];
+    float4 a[4], b[4];
+    load_row(out2 + row * RG_D, lane, a);
+    load_row(out2 + (rows + row) * RG_D, lane, b);
+    auto mix = [&](float xt, float xn) {
+        float r = __fmul_rn(__fmul_rn(xt, both), js);
+        r = __fadd_rn(r, __fmul_rn(__fmul_rn(xt, text), js));
+        r = __fadd_rn(r, __fmul_rn(__fmul_rn(xn, retr), ijs));
+        return __fadd_rn(r, __fmul_rn(__fmul_rn(xn, none), ijs));
+    };
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        a[j].x = mix(a[j].x, b[j].x); a[j].y = mix(a[j].y, b[j].y);
+        a[j].z = mix(a[j].z, b[j].z); a[j].w = mix(a[j].w, b[j].w);
+    }
+    store_row(out + row * RG_D, lane, a);
+}
+
+cudaError_t rg_launch_mix_branches(const float* out2, const float* coef, const float* joint_scale, float* out,
+                                   long long rows, int T, cudaStream_t st) {
+    if (rows <= 0) return cudaSuccess;
+    mix_branches_kernel<<<row_blocks(rows), 256, 0, st>>>(out2, coef, joint_scale, out, rows, T);
+    return cudaGetLastError();
+}
 cudaError_t rg_launch_guidance(float* x, const float* in_seq, long long rows, int iters,
                                float lr_2_over_n, cudaStream_t st) {
     if (rows <= 0 || iters <= 0) return cudaSuccess;

@@ -151,7 +151,7 @@ class SpacedDiffusion:
         self._check(clip_denoised, denoised_fn, cond_fn, eta, pre_seq)
         eng = self._engine(model)
         prep = model.prepare_batch(model_kwargs, x.shape[0])
-        out = self._forward_step(eng, prep, x, self._uniform_step(t), in_seq)
+        out = self._forward_step(eng, prep, x, self._uniform_step(t), in_seq, model)
         return {"sample": out[0], "pred_xstart": out[1]}
 
     def ddim_reverse_sample(self, model, x, t, clip_denoised=True, denoised_fn=None,
@@ -160,14 +160,22 @@ class SpacedDiffusion:
         eng = self._engine(model)
         prep = model.prepare_batch(model_kwargs, x.shape[0])
         i = self._uniform_step(t)
-        x0 = eng.denoise(x, prep.src_mask, prep.query_mask, prep.state, step_idx=i)
+        x0 = self._x0(model, eng, prep, x, i)
         return {"sample": eng.ddim_update(x, x0, i, +1), "pred_xstart": x0}
 
-    def _forward_step(self, eng, prep, x, i, in_seq):
+    @staticmethod
+    def _x0(model, eng, prep, x, i, coefs=None):
+        """One denoiser evaluation at schedule level i: the single-branch engine call, or -- when the model was built
+        with scale_func_cfg -- both branches of forward_test and their mix (ReGestureTransformer.two_branch_x0)."""
+        if getattr(model, "two_branch", False):
+            return model.two_branch_x0(eng, prep, x, step_idx=i, coefs=coefs)
+        return eng.denoise(x, prep.src_mask, prep.query_mask, prep.state, step_idx=i)
+
+    def _forward_step(self, eng, prep, x, i, in_seq, model=None):
         """blend (if in_seq) -> denoise -> x_{t-1}; draws noise in the order of :945 then :991."""
         if in_seq is not None:
             x = eng.blend_in_seq(x, in_seq.contiguous(), self._randn(in_seq.shape, x.device), i)
-        x0 = eng.denoise(x, prep.src_mask, prep.query_mask, prep.state, step_idx=i)
+        x0 = self._x0(model, eng, prep, x, i)
         self._randn(x.shape, x.device)      # randn_like(x) of :991 -- sigma = 0, value unused
         return eng.ddim_update(x, x0, i, -1), x0
 
@@ -193,7 +201,7 @@ class SpacedDiffusion:
         prep = model.prepare_batch(model_kwargs, shape[0])
         with torch.no_grad():
             for i in reversed(range(self.num_timesteps)):
-                img, x0 = self._forward_step(eng, prep, img, i, in_seq)
+                img, x0 = self._forward_step(eng, prep, img, i, in_seq, model)
                 yield {"sample": img, "pred_xstart": x0}
 
     def ddim_reverse_sample_loop(self, model, start_img, clip_denoised=True, denoised_fn=None,
@@ -209,9 +217,19 @@ class SpacedDiffusion:
         img = start_img.float().contiguous()
         prep = model.prepare_batch(model_kwargs, img.shape[0])
         samples = []
+        coefs = None
+        if getattr(model, "two_branch", False) and img.shape[0] > 1:
+            # 2-branch mode draws a coefficient set per evaluation above t = 100 (Python's `random`).  The reference
+            # inverts exemplar by exemplar (E loops at B = 1), so exemplar e's 50 draws come before exemplar e+1's:
+            # the batched loop pre-draws the table in that order and hands every level its column.
+            rows = []
+            for _ in range(img.shape[0]):
+                cs = [model.scale_func_retr(int(eng.timestep_map[i])) for i in range(self.num_timesteps)]
+                rows.append([[c["both_coef"], c["text_coef"], c["retr_coef"], c["none_coef"]] for c in cs])
+            coefs = torch.tensor(rows, dtype=torch.float32)            # [E, S, 4]
         with torch.no_grad():
             for i in range(self.num_timesteps):
-                x0 = eng.denoise(img, prep.src_mask, prep.query_mask, prep.state, step_idx=i)
+                x0 = self._x0(model, eng, prep, img, i, None if coefs is None else coefs[:, i])
                 img = eng.ddim_update(img, x0, i, +1)
                 if return_all_timesteps:
                     samples.append(img)
@@ -258,7 +276,7 @@ class SpacedDiffusion:
                     g = int(guidance_iters[i])
                     if g > 0 and not self.skip_dead_guidance:
                         img = eng.guidance_steps(img.clone(), in_seq.contiguous(), g, guidance_lr)
-                img, x0 = self._forward_step(eng, prep, img, i, in_seq)
+                img, x0 = self._forward_step(eng, prep, img, i, in_seq, model)
                 yield {"sample": img, "pred_xstart": x0}
 
     def run_levels(self, model, guided=None, reverse=None):
@@ -278,6 +296,22 @@ class SpacedDiffusion:
         randn_like(x) of gaussian_diffusion.py:991), so any generator / noise tape sees the same sequence."""
         S = self.num_timesteps
         eng = self._engine(model)
+        if getattr(model, "two_branch", False):
+            # 2-branch mode mixes two evaluations per level on the host side of the ABI: the step-by-step loops
+            out_g = out_r = None
+            if reverse is not None:                 # the reference inverts first (diffusion_architecture.py:323-354)
+                out_r = self.ddim_reverse_sample_loop(model, start_img=reverse["start_img"], clip_denoised=False,
+                                                      model_kwargs=reverse["model_kwargs"], eta=0, return_all_timesteps=True)
+            if guided is not None:
+                kw = dict(noise=guided.get("noise", None), clip_denoised=False, model_kwargs=guided["model_kwargs"], eta=0,
+                          in_seq=guided.get("in_seq", None))
+                if guided.get("inverted_latent_list", None) is not None:
+                    out_g = self.ddim_guided_sample_loop(model, guided["shape"], guidance_iters=guided.get("guidance_iters", None),
+                                                         inverted_latent_list=guided["inverted_latent_list"],
+                                                         guidance_lr=guided.get("guidance_lr", 0.1), **kw)
+                else:
+                    out_g = self.ddim_sample_loop(model, guided["shape"], **kw)
+            return out_g, out_r
         B = E = 0
         parts = []
         if guided is not None:

@@ -203,6 +203,18 @@ class DenoiserEngine:
                                                 rows, _lib.stream_ptr()))
         return out
 
+    def mix_branches(self, out2, coefs, joint_scale, out=None):
+        """rg_mix_branches: out2 [2B,T,D] (text rows, then "none" rows), coefs [B,4], joint_scale [T] -> [B,T,D]."""
+        self._f32(out2, coefs, joint_scale)
+        B = out2.shape[0] // 2
+        assert coefs.shape == (B, 4) and joint_scale.numel() == self.n_tokens
+        if out is None:
+            out = torch.empty((B,) + tuple(out2.shape[1:]), device=out2.device)
+        with torch.cuda.device(out2.device):
+            _lib.check(self.lib.rg_mix_branches(self._h, _lib.ptr(out2), B, _lib.ptr(coefs), _lib.ptr(joint_scale),
+                                                _lib.ptr(out), _lib.stream_ptr()))
+        return out
+
     def guidance_steps(self, x, in_seq, iters, lr, numel=None):
         self._f32(x, in_seq, like=x)
         rows = x.numel() // self.latent_dim

@@ -250,10 +250,9 @@ class ReGestureTransformer(nn.Module):
                  gesture_rep_encoder=None, precision=_lib.PREC_FP32):
         super().__init__()
         assert not retrieval_train
-        if scale_func_cfg is not None or per_joint_scale is not None:
-            raise NotImplementedError(
-                "scale_func_cfg / per_joint_scale (2-branch mixing) crashes in the reference as shipped "
-                "(raggesture.py:1102) and is out of scope here (SURVEY 8f.4); pass scale_func_cfg=None")
+        # 2-branch mode (raggesture.py:908-921): scale_func_cfg switches it on; the reference builds
+        # joint_scale_mask only when per_joint_scale is given and otherwise raises AttributeError in the first
+        # forward_test (:1102) -- the shipped config does exactly that.  Mirrored: see two_branch_x0.
         if body_part_cat_axis != "time":
             raise NotImplementedError("Only time axis is supported for body part categorization")
         for enc, nm in ((text_encoder, "text"), (audio_encoder, "audio")):
@@ -262,7 +261,15 @@ class ReGestureTransformer(nn.Module):
         self.input_feats, self.latent_dim, self.num_layers = input_feats, latent_dim, num_layers
         self.time_embed_dim, self.frame_chunk_size = time_embed_dim, frame_chunk_size
         self.body_part_cat_axis = body_part_cat_axis
-        self.scale_func_cfg, self.per_joint_scale = None, None
+        self.scale_func_cfg, self.per_joint_scale = scale_func_cfg, per_joint_scale
+        if per_joint_scale is not None:
+            T = 43                                      # hard-coded in the reference (:911)
+            n = (T - 3) // 4
+            self.joint_scale_mask = torch.ones(T)
+            self.joint_scale_mask[0:n] = per_joint_scale["upper"]
+            self.joint_scale_mask[n + 1:2 * n + 1] = per_joint_scale["hands"]
+            self.joint_scale_mask[2 * n + 2:3 * n + 2] = per_joint_scale["face"]
+            self.joint_scale_mask[3 * n + 3:T] = per_joint_scale["lowertransl"]
         self.precision = precision
         # latent codec (adjacent component): any object with encode/decode/vae_latent_dim
         if gesture_rep_encoder is None and vae_cfg is not None:
@@ -431,7 +438,65 @@ class ReGestureTransformer(nn.Module):
         qm = model_kwargs.get("query_mask", None)
         if qm is not None:
             qm = torch.stack([qm[c].to(device=dev, dtype=torch.float32) for c in CFG.CONDS], 0).contiguous()
+        if self.two_branch:
+            # forward_test repeats the batch (:1058-1072): text branch, then the "none" branch, whose cross-attention
+            # sees keys - 1e6 and the values of a zeroed condition, i.e. the state A[d][l] = value.bias[l]
+            state = torch.cat([state, self._none_state(dev).expand(B, -1, -1, -1, -1, -1)], 0).contiguous()
+            src_mask = src_mask.repeat(2, 1)
+            qm = None if qm is None else qm.repeat(1, 2, 1).contiguous()
         return PreparedBatch(src_mask, qm, state)
+
+    # -- 2-branch mode (raggesture.py:925-954, 1041-1111) ------------------------------------------------------------
+    @property
+    def two_branch(self):
+        return self.scale_func_cfg is not None
+
+    def scale_func_retr(self, timestep):
+        """The four mixing coefficients (:925-954); above t = 100 one of two sets is drawn with Python's global
+        `random`, as in the reference."""
+        import random
+        cfg = self.scale_func_cfg
+        w = (1 - (1000 - timestep) / 1000) * cfg["coarse_scale"] + 1
+        if timestep > 100:
+            if random.randint(0, 1) == 0:
+                return {"both_coef": w, "text_coef": 0, "retr_coef": 1 - w, "none_coef": 0}
+            return {"both_coef": 0, "text_coef": w, "retr_coef": 0, "none_coef": 1 - w}
+        both, text, retr = cfg["both_coef"], cfg["text_coef"], cfg["retr_coef"]
+        return {"both_coef": both, "text_coef": text, "retr_coef": retr, "none_coef": 1 - both - text - retr}
+
+    def _none_state(self, dev):
+        """[1, L, 3, H, 32, 32]: the K6 state of the "none" branch.  With cond_type 0 every value row is value.bias and
+        the key softmax still sums to one over the tokens (efficient_attention.py:83-89), so A[d][l] = value.bias[l]
+        for every d, whatever the condition is."""
+        key = self._weights_key()
+        cached = getattr(self, "_none_state_cache", None)
+        if cached is None or cached[0] != key or cached[1].device != dev:
+            H = self._num_heads
+            rows = []
+            for blk in self.temporal_decoder_blocks:
+                per_cond = [blk.ca_blocks[c].value.bias.detach().float().view(H, 1, -1).expand(H, self.latent_dim // H, -1)
+                            for c in CFG.CONDS]
+                rows.append(torch.stack(per_cond, 0))
+            cached = self._none_state_cache = (key, torch.stack(rows, 0).unsqueeze(0).to(dev).contiguous())
+        return cached[1]
+
+    def two_branch_x0(self, eng, prep, x, step_idx=-1, tau=0, coefs=None):
+        """forward_test with scale_func_cfg: both branches in ONE evaluation of 2B clips, then rg_mix_branches.
+        `coefs` [B,4] (both, text, retr, none per clip) overrides the per-call draw: the batched inversion loop draws
+        them exemplar by exemplar in the order the reference's per-exemplar loops would."""
+        if not hasattr(self, "joint_scale_mask"):
+            raise AttributeError("'ReGestureTransformer' object has no attribute 'joint_scale_mask' (scale_func_cfg "
+                                 "without per_joint_scale: the reference fails the same way, raggesture.py:1102)")
+        B = x.shape[0]
+        if coefs is None:
+            t_orig = int(tau) if step_idx < 0 else int(eng.timestep_map[step_idx])
+            c = self.scale_func_retr(t_orig)
+            coefs = torch.tensor([[c["both_coef"], c["text_coef"], c["retr_coef"], c["none_coef"]]],
+                                 dtype=torch.float32).expand(B, 4)
+        coefs = coefs.to(device=x.device, dtype=torch.float32).contiguous()
+        js = self.joint_scale_mask.to(device=x.device, dtype=torch.float32).contiguous()
+        out2 = eng.denoise(x.repeat(2, 1, 1), prep.src_mask, prep.query_mask, prep.state, step_idx=step_idx, tau=tau)
+        return eng.mix_branches(out2, coefs, js)
 
     def forward(self, motion, timesteps, motion_mask=None, **kwargs):
         """motion [B,T,D], timesteps [B] on the ORIGINAL 0..999 scale (all equal) -> x0 [B,T,D]."""
@@ -447,6 +512,8 @@ class ReGestureTransformer(nn.Module):
         cond = self.get_precompute_condition(device=motion.device, **kwargs)
         prep = self.prepare_batch({"xf_out": cond["xf_out"], "motion_mask": motion_mask,
                                    "query_mask": copy.copy(kwargs.get("query_mask", None))}, B)
+        if self.two_branch:
+            return self.two_branch_x0(self.rg_engine(), prep, motion.float().contiguous(), step_idx=-1, tau=tau)
         return self.rg_engine().denoise(motion, prep.src_mask, prep.query_mask, prep.state, step_idx=-1, tau=tau)
 
     # -- module path (raggesture.py:1041-1113 single branch) ------------------------------------------------

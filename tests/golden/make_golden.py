@@ -332,6 +332,47 @@ def gen_outpaint(ns):
          n_rows=np.array(int((seq != 0).any(-1).sum())))
 
 
+TWO_BRANCH = dict(scale_func_cfg=dict(coarse_scale=6.5, both_coef=0.52351, text_coef=-0.28419, retr_coef=2.39872),
+                  per_joint_scale=dict(upper=1.2, hands=0.9, face=1.0, lowertransl=1.1))
+
+
+def gen_two_branch(ns):
+    """The 2-branch mode of forward_test (raggesture.py:925-954,1041-1111): text branch + "none" branch (keys - 1e6,
+    values of a zeroed condition) mixed with scale_func_retr's coefficients and the per-body-part joint scale.  The
+    shipped config sets scale_func_cfg but not per_joint_scale and crashes (AttributeError :1102); with
+    per_joint_scale given the reference runs.  random.randint picks the coefficient set above t = 100: Python's
+    `random` is seeded before every call / loop."""
+    import random
+    ns.dt.GestureRepEncoder = ShapeOnlyCodec
+    cfg = C.denoiser_cfg()
+    cfg.pop("type")
+    cfg.update(TWO_BRANCH)
+    sd = S.synthetic_state_dict(0)
+    model = ns.rg.ReGestureTransformer(**cfg, database=None, use_retrieval_for_test=False)
+    model.load_state_dict(sd, strict=False)
+    model.eval()
+    diff = build_reference_diffusion(ns)
+    B, T, D = 2, C.N_TOKENS, C.LATENT_DIM
+    cond, x = S.synthetic_conditions(B, seed=11), S.synthetic_latents(B, seed=12)
+    kw = model_kwargs_for(model, cond, B)
+    outs = {}
+    with torch.no_grad():
+        for tau in (50, 514, 999):
+            random.seed(7 + tau)
+            outs[f"x0_t{tau}"] = model(x, torch.full((B,), tau, dtype=torch.int64),
+                                       **{k: (dict(v) if isinstance(v, dict) else v) for k, v in kw.items()})
+        cond1 = S.synthetic_conditions(1, seed=21)
+        kw1 = model_kwargs_for(model, cond1, 1)
+        torch.manual_seed(31)
+        random.seed(32)
+        outs["plain_final"] = diff.ddim_sample_loop(model, (1, T, D), clip_denoised=False, model_kwargs=kw1, eta=0)
+        random.seed(33)
+        inv = diff.ddim_reverse_sample_loop(model, start_img=S.synthetic_latents(1, seed=22, scale=0.5),
+                                            clip_denoised=False, model_kwargs=kw1, eta=0, return_all_timesteps=True)
+        outs["inv49"] = inv[-1]
+    save("denoiser_two_branch", **outs)
+
+
 def gen_rotation(ns):
     """6D cross-fade of tools/longform_synthesis.py:449-471 with the reference's rotation_conversions."""
     import importlib
@@ -456,7 +497,8 @@ def gen_codec(ns):
 
 
 GROUPS = {"rotation": gen_rotation, "schedule": gen_schedule, "denoiser": gen_denoiser, "loops": gen_loops,
-          "retrieval": gen_retrieval, "pipeline": gen_pipeline, "outpaint": gen_outpaint, "codec": gen_codec,
+          "retrieval": gen_retrieval, "pipeline": gen_pipeline, "outpaint": gen_outpaint, "two_branch": gen_two_branch,
+          "codec": gen_codec,
           "postprocess": gen_postprocess}
 
 if __name__ == "__main__":

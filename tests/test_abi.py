@@ -71,9 +71,14 @@ def test_registry_and_constructor_surface():
     assert R.build_attention(None) is None
     sa = R.build_attention(dict(cfg["model"]["sa_block_cfg"]))
     assert isinstance(sa, R.EfficientSelfAttention) and hasattr(sa, "proj_out")
-    with pytest.raises(NotImplementedError):       # the shipped scale_func_cfg crashes in the reference too
-        bad = dict(cfg["model"], scale_func_cfg=dict(coarse_scale=6.5, both_coef=0.5, text_coef=-0.3, retr_coef=2.4))
-        R.build_submodule(bad, database=None, use_retrieval_for_test=False)
+    # the shipped config sets scale_func_cfg without per_joint_scale: like the reference, the module builds and the
+    # first 2-branch forward_test fails for want of joint_scale_mask (raggesture.py:1102; checked on the GPU)
+    shipped = dict(cfg["model"], scale_func_cfg=dict(coarse_scale=6.5, both_coef=0.5, text_coef=-0.3, retr_coef=2.4))
+    two = R.build_submodule(dict(shipped), database=None, use_retrieval_for_test=False)     # build_submodule pops 'type'
+    assert two.two_branch and not hasattr(two, "joint_scale_mask")
+    ok = R.build_submodule(dict(shipped, per_joint_scale=dict(upper=1.2, hands=0.9, face=1.0, lowertransl=1.1)),
+                           database=None, use_retrieval_for_test=False)
+    assert ok.two_branch and float(ok.joint_scale_mask[0]) == pytest.approx(1.2) and float(ok.joint_scale_mask[10]) == 1.0
     # re-registration into a foreign registry (what a mogen user does)
     reg = R.mogen_api.Registry("foreign")
     R.register_into(reg)

@@ -584,3 +584,59 @@ def test_single_speaker_config(dev, sd0):
     xf["xf_spk"] = torch.zeros(B, B, C.LATENT_DIM)
     ref = OD.denoiser_forward(sd, x.cpu(), torch.full((B,), 514), S.motion_mask(B), xf, S.query_masks(B))
     assert rel_l2(out, ref) < TOL_STEP
+
+
+TWO_BRANCH = dict(scale_func_cfg=dict(coarse_scale=6.5, both_coef=0.52351, text_coef=-0.28419, retr_coef=2.39872),
+                  per_joint_scale=dict(upper=1.2, hands=0.9, face=1.0, lowertransl=1.1))
+
+
+@pytest.mark.parametrize("tier", ["fp32", "bf16x3", "bf16"])
+def test_two_branch_mode_vs_reference(tier, golden, dev, sd0, diffusion):
+    """forward_test with scale_func_cfg (raggesture.py:925-954,1041-1111) -- the batch evaluated as text
+    branch + "none" branch in one 2B-clip chain and mixed by rg_mix_branches -- against the unmodified reference run
+    with per_joint_scale set (make_golden.py two_branch): single evaluations below and above t = 100 (the random
+    coefficient set, Python's `random` seeded like the reference run), a plain 50-step loop and an inversion loop."""
+    import random
+    from rag_gesture_b200 import _lib as L
+    from rag_gesture_b200 import mogen_api as M
+    prec, tol_step, tol_loop = {"fp32": (L.PREC_FP32, 1e-4, 1e-3), "bf16x3": (L.PREC_BF16X3, 1e-4, 1e-3),
+                                "bf16": (L.PREC_BF16, 1e-2, 2e-2)}[tier]
+    g = golden("denoiser_two_branch")
+    m = M.build_submodule(dict(C.denoiser_cfg(), precision=prec, **TWO_BRANCH), database=None, use_retrieval_for_test=False)
+    m.load_state_dict(sd0, strict=False)
+    m = m.to(dev).eval()
+    B = 2
+    kw = _kw(m, S.synthetic_conditions(B, seed=11), B, dev)
+    x = S.synthetic_latents(B, seed=12).to(dev)
+    with torch.no_grad():
+        for tau in (50, 514, 999):
+            random.seed(7 + tau)
+            out = m(x, torch.full((B,), tau, device=dev), **kw).cpu()
+            err = rel_l2(out, torch.from_numpy(g[f"x0_t{tau}"]))
+            print(f"two-branch ({tier} tier) tau {tau}: rel-L2 {err:.3g}")
+            assert err < tol_step, tau
+    kw1 = _kw(m, S.synthetic_conditions(1, seed=21), 1, dev)
+    diffusion.noise_fn = lambda shape, device: torch.randn(*shape).to(device)      # global CPU generator, like the reference
+    try:
+        torch.manual_seed(31)
+        random.seed(32)
+        final = diffusion.ddim_sample_loop(m, (1, C.N_TOKENS, C.LATENT_DIM), clip_denoised=False, model_kwargs=kw1, eta=0).cpu()
+        random.seed(33)
+        inv = diffusion.ddim_reverse_sample_loop(m, start_img=S.synthetic_latents(1, seed=22, scale=0.5).to(dev),
+                                                 clip_denoised=False, model_kwargs=kw1, eta=0, return_all_timesteps=True)
+        # the whole-loop entry point falls back to the step-by-step loops in this mode: same draws, same result
+        random.seed(33)
+        _, inv2 = diffusion.run_levels(m, reverse=dict(start_img=S.synthetic_latents(1, seed=22, scale=0.5).to(dev), model_kwargs=kw1))
+    finally:
+        diffusion.noise_fn = None
+    e1, e2 = rel_l2(final, torch.from_numpy(g["plain_final"])), rel_l2(inv[-1].cpu(), torch.from_numpy(g["inv49"]))
+    print(f"two-branch ({tier} tier): plain loop rel-L2 {e1:.3g}, reverse loop {e2:.3g}")
+    assert e1 < tol_loop and e2 < tol_loop
+    assert torch.equal(inv2[-1], inv[-1])
+    # scale_func_cfg without per_joint_scale: the reference's AttributeError (raggesture.py:1102)
+    bad = M.build_submodule(dict(C.denoiser_cfg(), scale_func_cfg=TWO_BRANCH["scale_func_cfg"]), database=None,
+                            use_retrieval_for_test=False)
+    bad.load_state_dict(sd0, strict=False)
+    bad = bad.to(dev).eval()
+    with pytest.raises(AttributeError), torch.no_grad():
+        bad(x, torch.full((B,), 50, device=dev), **_kw(bad, S.synthetic_conditions(B, seed=11), B, dev))

@@ -120,3 +120,22 @@ def test_reverse_and_guided_loops(golden, sd0):
     torch.manual_seed(999)
     fp = diff.ddim_sample_loop(model, (1, T, D), model_kwargs=kw, in_seq=prev)
     assert rel_l2(fp, torch.from_numpy(gg["final_prev_latent_b1"])) < 2e-4
+
+
+def test_two_branch_oracle_vs_reference(golden, sd0):
+    """forward_test's 2-branch mode (scale_func_cfg + per_joint_scale) restated in the oracle against the unmodified
+    reference (make_golden.py two_branch), incl. the random coefficient set above t = 100."""
+    import random
+    from oracle import denoiser as OD
+    from rag_gesture_b200 import synthetic as S
+    TWO = dict(scale_func_cfg=dict(coarse_scale=6.5, both_coef=0.52351, text_coef=-0.28419, retr_coef=2.39872),
+               per_joint_scale=dict(upper=1.2, hands=0.9, face=1.0, lowertransl=1.1))
+    g = golden("denoiser_two_branch")
+    B = 2
+    cond, x = S.synthetic_conditions(B, seed=11), S.synthetic_latents(B, seed=12)
+    xf = OD.encode_conditions(sd0, cond["word"], cond["audio"], cond["speaker_ids"])
+    for tau in (50, 514, 999):
+        random.seed(7 + tau)
+        out = OD.denoiser_forward_two_branch(sd0, x, torch.full((B,), tau), S.motion_mask(B), xf, S.query_masks(B),
+                                             TWO["scale_func_cfg"], TWO["per_joint_scale"], random)
+        assert rel_l2(out, torch.from_numpy(g[f"x0_t{tau}"])) < 2e-5, tau
