@@ -86,14 +86,11 @@ class TextSimilarityIndex:
                                               _lib.ptr(sub), n_out, _lib.ptr(out), _lib.stream_ptr()))
         return out
 
-    def rank(self, query, rows, k):
-        """First k of `rows` ordered by similarity, descending, ties in given order (the stable
-        `sorted(..., reverse=True)` of rag/utils.py:127-129).  rows: list of DB row indices."""
-        if not rows:
-            return []
+    def _rank_launch(self, query, rows, k):
+        """Enqueue the two kernels that rank `rows` against `query` (no synchronisation): -> device int64 [32]
+        holding positions into `rows` in rank order."""
         k = min(k, len(rows))
         sc = self.scores(query, rows).view(1, 1, -1)
-        order = []
         lib = _lib.load()
         # top-k of one candidate list == merge of ceil(n/32) "parts" of 32 candidates
         n = sc.shape[-1]
@@ -108,25 +105,85 @@ class TextSimilarityIndex:
         with torch.cuda.device(self.device):
             _lib.check(lib.rg_knn_merge(_lib.ptr(idx.contiguous()), _lib.ptr(sc.contiguous().view(-1)),
                                         parts, 1, 32, _lib.ptr(out_i), _lib.ptr(out_s), _lib.stream_ptr()))
-        for j in out_i[:k].tolist():
-            order.append(rows[j])
-        return order
+        return out_i, k
+
+    def rank(self, query, rows, k):
+        """First k of `rows` ordered by similarity, descending, ties in given order (the stable
+        `sorted(..., reverse=True)` of rag/utils.py:127-129).  rows: list of DB row indices."""
+        if not rows:
+            return []
+        out_i, k = self._rank_launch(query, rows, k)
+        return [rows[j] for j in out_i[:k].tolist()]
+
+    def rank_many(self, requests):
+        """[(query, rows, k), ...] -> [ranked rows, ...]: every request's kernels are enqueued first, then ONE
+        device-to-host copy and synchronisation serves all of them (a batch of clips asks ~80 times; one round trip
+        each was a third of the host time of the retrieval stage)."""
+        launched = [None if not rows else self._rank_launch(q, rows, k) for q, rows, k in requests]
+        live = [x for x in launched if x is not None]
+        if not live:
+            return [[] for _ in requests]
+        host = torch.stack([o for o, _ in live], 0).cpu().tolist()
+        out, it = [], iter(host)
+        for (q, rows, _), l in zip(requests, launched):
+            out.append([] if l is None else [rows[j] for j in next(it)[:l[1]]])
+        return out
 
 
 def discourse_retrieval(text, discourse, prominence, speaker_id, db_idx_2_sense, db_idx_2_discbounds,
                         db_idx_2_prominence, encoded_text, text_feat_cache, index=None, sense_index=None,
                         sense_tables=None):
-    """Rule-based discourse retrieval, same arguments and return triple as
+    """Rule-based discourse retrieval for ONE clip: drives the generator below, answering each ranking request as it
+    comes (one device round trip per request).  Same arguments and return triple as the reference function."""
+    if index is None and len(discourse):
+        names = list(text_feat_cache.keys())
+        index = TextSimilarityIndex(names, [text_feat_cache[n][0] for n in names], encoded_text.device
+                                    if encoded_text.is_cuda else "cuda")
+    gen = discourse_retrieval_steps(text, discourse, prominence, speaker_id, db_idx_2_sense, db_idx_2_discbounds,
+                                    db_idx_2_prominence, encoded_text, text_feat_cache, index, sense_index, sense_tables)
+    try:
+        req = next(gen)
+        while True:
+            req = gen.send(index.rank(*req))
+    except StopIteration as done:
+        return done.value
+
+
+def discourse_retrieval_many(queries, index, **shared):
+    """The same for a BATCH of clips (`queries`: list of per-clip keyword dicts): all clips advance together and
+    the ranking requests of a round go to the device in one batch (TextSimilarityIndex.rank_many), so a batch
+    costs 2-3 round trips instead of one per tie-break.  Results are identical to per-clip calls."""
+    gens = [discourse_retrieval_steps(index=index, **q, **shared) for q in queries]
+    results, pending = [None] * len(gens), {}
+    for i, g in enumerate(gens):
+        try:
+            pending[i] = next(g)
+        except StopIteration as done:
+            results[i] = done.value
+    while pending:
+        order = list(pending)
+        reqs = [pending[i] for i in order]
+        answers = index.rank_many(reqs) if hasattr(index, "rank_many") else [index.rank(*r) for r in reqs]
+        for i, ans in zip(order, answers):
+            try:
+                pending[i] = gens[i].send(ans)
+            except StopIteration as done:
+                results[i] = done.value
+                del pending[i]
+    return results
+
+
+def discourse_retrieval_steps(text, discourse, prominence, speaker_id, db_idx_2_sense, db_idx_2_discbounds,
+                              db_idx_2_prominence, encoded_text, text_feat_cache, index=None, sense_index=None,
+                              sense_tables=None):
+    """Generator core: yields (query features, DB rows, k) whenever a score tier needs its text-similarity order and
+    receives the ranked rows; returns the result triple.  Rule-based discourse retrieval, same return triple as
     rag/discourse_retrieval.py:8-316:  ({q: [sample names]}, {q: {name: (conn, sense, start, end)}},
     {q: (conn_lower, sense, conn_start, conn_end)}).  `index` (TextSimilarityIndex) and `sense_index`
     are supplied by RetrievalDatabase; without them they are built on the fly from the dicts."""
     sample_indexes, d_bounds = {}, {}
     if len(discourse) == 0:
         return sample_indexes, d_bounds, {}
-    if index is None:
-        names = list(text_feat_cache.keys())
-        index = TextSimilarityIndex(names, [text_feat_cache[n][0] for n in names], encoded_text.device
-                                    if encoded_text.is_cuda else "cuda")
     if sense_index is None:
         sense_index = build_sense_index(db_idx_2_sense)
     senses = [d[1] for d in discourse]
@@ -171,10 +228,11 @@ def discourse_retrieval(text, discourse, prominence, speaker_id, db_idx_2_sense,
                 rows = [index.row[names[i]] for i in tier]
                 back = {r: i for r, i in zip(rows, tier)}
                 if len(tier) <= 32:
-                    tier = [back[r] for r in index.rank(encoded_text, rows, len(tier))]
+                    ranked_rows = yield (encoded_text, rows, len(tier))
+                    tier = [back[r] for r in ranked_rows]
                 else:
                     # only the first 32 by similarity can reach the top 10; the rest keep tier order
-                    head = index.rank(encoded_text, rows, 32)
+                    head = yield (encoded_text, rows, 32)
                     hs = set(head)
                     tier = [back[r] for r in head] + [i for r, i in zip(rows, tier) if r not in hs]
             ranked += tier
@@ -399,34 +457,74 @@ class RetrievalDatabase(nn.Module):
         assert retr_method in ["gesture_type", "discourse", "llm"]
         if self.training:
             raise NotImplementedError("Not released for training for retrieval")
-        if idx in self.test_indexes and idx is not None:
-            hit = self.test_indexes[idx]
-            if retr_method not in hit:
-                print(f"WARNUNG: Retrieval method {retr_method} not found for idx {idx}")
-                return {}, {}, {}
-            sample_indexes = hit[retr_method]
-            # the reference reads the bounds from the wrong dict here (raggesture.py:365, SURVEY
-            # quirk 7); the cache is keyed identically, so serve the right one
-            sample_bounds, query_bounds = self.test_dbounds[idx][retr_method], self.test_qbounds[idx][retr_method]
+        hit = self._cached(retr_method, idx)
+        if hit is not None:
+            return hit
+        args = {"text": text, "speaker_id": speaker_id, "encoded_text": text_features,
+                "text_feat_cache": self.idx_2_text}
+        if retr_method == "discourse":
+            args.update(discourse=discourse, prominence=prominence, db_idx_2_sense=self.idx_2_sense,
+                        db_idx_2_discbounds=self.idx_2_discbounds, db_idx_2_prominence=self.idx_2_prominence)
+        elif retr_method == "gesture_type":
+            args.update(gesture_labels=gesture_labels, db_idx_2_gesture_labels=self.idx_2_gesture_labels)
         else:
-            args = {"text": text, "speaker_id": speaker_id, "encoded_text": text_features,
-                    "text_feat_cache": self.idx_2_text}
-            if retr_method == "discourse":
-                args.update(discourse=discourse, prominence=prominence, db_idx_2_sense=self.idx_2_sense,
-                            db_idx_2_discbounds=self.idx_2_discbounds, db_idx_2_prominence=self.idx_2_prominence)
-            elif retr_method == "gesture_type":
-                args.update(gesture_labels=gesture_labels, db_idx_2_gesture_labels=self.idx_2_gesture_labels)
-            else:
-                args.update(text_times=text_times, db_idx_2_gesture_labels=self.idx_2_gesture_labels,
-                            prominence=prominence, db_idx_2_prominence=self.idx_2_gestprom)
-            sample_indexes, sample_bounds, query_bounds = self.retrieval_method[retr_method](**args)
-            for d in (self.train_indexes, self.train_dbounds, self.train_qbounds):
-                d[idx] = {}
-            self.test_indexes[idx] = {retr_method: sample_indexes}
-            self.test_dbounds[idx] = {retr_method: sample_bounds}
-            self.test_qbounds[idx] = {retr_method: query_bounds}
-        data = {q: [s for s in names if s != idx][: self.num_retrieval] for q, names in sample_indexes.items()}
-        return data, sample_bounds, query_bounds
+            args.update(text_times=text_times, db_idx_2_gesture_labels=self.idx_2_gesture_labels,
+                        prominence=prominence, db_idx_2_prominence=self.idx_2_gestprom)
+        return self._store(retr_method, idx, self.retrieval_method[retr_method](**args))
+
+    def retrieve_many(self, retr_method, clips):
+        """`retrieve` for a batch: clips = [dict(text, text_features, audio, discourse, gesture_labels, text_times,
+        prominence, speaker_id, idx)].  Discourse retrieval of the clips that are not cached runs through
+        discourse_retrieval_many (their tie-break rankings share 2-3 device round trips); everything else, and the
+        caching behaviour, is `retrieve`'s.  Same results, clip by clip."""
+        assert retr_method in ["gesture_type", "discourse", "llm"]
+        if self.training:
+            raise NotImplementedError("Not released for training for retrieval")
+        out = [self._cached(retr_method, c.get("idx")) for c in clips]
+        miss = [i for i, o in enumerate(out) if o is None]
+        if retr_method == "discourse" and len(miss) > 1 and self.retrieval_method["discourse"] == self._discourse:
+            q0 = clips[miss[0]]["text_features"]
+            dev = q0.device if q0.is_cuda else (self._index_device or "cuda")
+            queries = [dict(text=clips[i]["text"], discourse=clips[i]["discourse"], prominence=clips[i]["prominence"],
+                            speaker_id=clips[i]["speaker_id"], encoded_text=clips[i]["text_features"]) for i in miss]
+            res = discourse_retrieval_many(queries, self.text_index(dev), sense_index=self._sense_index,
+                                           sense_tables=self._sense_tables, db_idx_2_sense=self.idx_2_sense,
+                                           db_idx_2_discbounds=self.idx_2_discbounds,
+                                           db_idx_2_prominence=self.idx_2_prominence, text_feat_cache=self.idx_2_text)
+            for i, r in zip(miss, res):
+                cached = self._cached(retr_method, clips[i].get("idx"))     # a repeated idx inside the batch
+                out[i] = cached if cached is not None else self._store(retr_method, clips[i].get("idx"), r)
+        else:
+            for i in miss:
+                c = clips[i]
+                out[i] = self.retrieve(retr_method, c["text"], c["text_features"], c["audio"], c["discourse"],
+                                       c["gesture_labels"], c["text_times"], c["prominence"], c["speaker_id"], c.get("idx"))
+        return out
+
+    def _cached(self, retr_method, idx):
+        if idx is None or idx not in self.test_indexes:
+            return None
+        hit = self.test_indexes[idx]
+        if retr_method not in hit:
+            print(f"WARNUNG: Retrieval method {retr_method} not found for idx {idx}")
+            return {}, {}, {}
+        sample_indexes = hit[retr_method]
+        # the reference reads the bounds from the wrong dict here (raggesture.py:365, SURVEY
+        # quirk 7); the cache is keyed identically, so serve the right one
+        sample_bounds, query_bounds = self.test_dbounds[idx][retr_method], self.test_qbounds[idx][retr_method]
+        return self._select(sample_indexes, idx), sample_bounds, query_bounds
+
+    def _store(self, retr_method, idx, triple):
+        sample_indexes, sample_bounds, query_bounds = triple
+        for d in (self.train_indexes, self.train_dbounds, self.train_qbounds):
+            d[idx] = {}
+        self.test_indexes[idx] = {retr_method: sample_indexes}
+        self.test_dbounds[idx] = {retr_method: sample_bounds}
+        self.test_qbounds[idx] = {retr_method: query_bounds}
+        return self._select(sample_indexes, idx), sample_bounds, query_bounds
+
+    def _select(self, sample_indexes, idx):
+        return {q: [s for s in names if s != idx][: self.num_retrieval] for q, names in sample_indexes.items()}
 
     def place_window(self, query_bound, retr_bound, retrieval_method, prev_end):
         """Exemplar seconds -> (exemplar chunk window, query chunk window) or None (SURVEY App. D;
@@ -488,13 +586,13 @@ class RetrievalDatabase(nn.Module):
         ref = self.dataset[0]
         # ---- phase 1: which exemplar for which query point --------------------------------------
         decided, jobs = [], []                      # jobs: (clip, q, name) in the reference's visiting order
-        for b in range(B):
-            retr_indexes, retr_bounds, query_bounds = self.retrieve(
-                retrieval_method, text=conditions["text"][b], text_features=conditions["text_features"][b],
-                audio=conditions["audio"][b], discourse=conditions["discourse"][b],
-                gesture_labels=conditions["gesture_labels"][b], text_times=conditions["text_times"][b],
-                prominence=conditions["prominence"][b], speaker_id=conditions["speaker_ids"][b, 0].item(),
-                idx=idx[b] if idx is not None else None)
+        spk = conditions["speaker_ids"][:, 0].tolist()        # one device read for the batch
+        clips = [dict(text=conditions["text"][b], text_features=conditions["text_features"][b],
+                      audio=conditions["audio"][b], discourse=conditions["discourse"][b],
+                      gesture_labels=conditions["gesture_labels"][b], text_times=conditions["text_times"][b],
+                      prominence=conditions["prominence"][b], speaker_id=spk[b],
+                      idx=idx[b] if idx is not None else None) for b in range(B)]
+        for b, (retr_indexes, retr_bounds, query_bounds) in enumerate(self.retrieve_many(retrieval_method, clips)):
             decided.append((retr_indexes, retr_bounds, query_bounds))
             for q, names in retr_indexes.items():
                 if len(names) == 0 or q not in query_bounds:
