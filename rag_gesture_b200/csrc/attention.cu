@@ -715,9 +715,11 @@ __global__ void __launch_bounds__(512, 2) ca_attn_kernel(const float* __restrict
 }
 
 // state[b][set][h][d][l] = sum_n softmax_n(K[b,n,h,d]) * V[b,n,h,l]   (K6; efficient_attention.py:78-89)
-// One CTA (256 threads) per (clip, head, set).  Pass 1: column max of K over the N tokens.  Pass 2:
-// tiles of 64 tokens staged in shared memory with coalesced 128-bit loads; exp(K - max) is evaluated
-// once per element, then E^T V (32x32 outputs, 4 per thread) accumulates from shared memory.
+// One CTA (256 threads) per (clip, head, set), ONE pass over K and V (they are read from HBM exactly once: the
+// [rows, 8192] fp32 buffer of a chunk is ~1 GB, far beyond L2): tiles of 64 tokens staged in shared memory with
+// coalesced 128-bit loads, column softmax kept online -- running maximum m[d] and sum s[d] per feature column; when a
+// tile raises the maximum, the accumulator row A[d][:] and s[d] are rescaled by exp(m_old - m_new) -- then
+// E = exp(K - m) once per element and E^T V (32x32 outputs, 4 per thread) accumulates from shared memory.
 constexpr int KV_TILE = 64;
 __global__ void __launch_bounds__(256) kv_state_kernel(const float* __restrict__ kv, int ldkv,
                                                       int k_off, int v_off, int N,
@@ -727,36 +729,19 @@ __global__ void __launch_bounds__(256) kv_state_kernel(const float* __restrict__
     __shared__ __align__(16) float Es[KV_TILE][RG_HD + 1];   // +1: column reads in the product are conflict-free
     __shared__ __align__(16) float Vs[KV_TILE][RG_HD];
     __shared__ float red[8][RG_HD];
-    __shared__ float kmax_s[RG_HD], ksum_s[RG_HD];
+    __shared__ float m_s[RG_HD], scale_s[RG_HD], sum_s[RG_HD];
     const int b = blockIdx.x, h = blockIdx.y, set = blockIdx.z;
     const int tid = threadIdx.x, lane = tid & 31, wg = tid >> 5;
     const float* rows = kv + (long long)b * N * ldkv + (long long)set * kv_set_stride;
     const float* kbase = rows + k_off + h * RG_HD;
     const float* vbase = rows + v_off + h * RG_HD;
-    // pass 1: column max (lane = column, 8 warps stride over tokens, 4 loads in flight per thread)
-    float m = -INFINITY;
-    for (int n0 = wg; n0 < N; n0 += 32) {
-        float t[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) t[i] = (n0 + 8 * i < N) ? kbase[(long long)(n0 + 8 * i) * ldkv + lane] : -INFINITY;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) m = fmaxf(m, t[i]);
-    }
-    red[wg][lane] = m;
-    __syncthreads();
-    if (wg == 0) {
-#pragma unroll
-        for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i][lane]);
-        kmax_s[lane] = m;
-        ksum_s[lane] = 0.f;
-    }
-    __syncthreads();
-    // pass 2
+    if (tid < RG_HD) { m_s[tid] = -INFINITY; sum_s[tid] = 0.f; }
     const int d = tid >> 3, l4 = (tid & 7) * 4;          // this thread's outputs: A[d][l4..l4+3]
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    float colsum = 0.f;                                    // partial sum of exp for column (tid & 31) ...
     const int ld_row = tid >> 3, ld_c4 = (tid & 7) * 4;    // tile loader: 32 rows x 8 float4 per pass
+    __syncthreads();
     for (int n0 = 0; n0 < N; n0 += KV_TILE) {
+        // raw K and V of the tile -> shared memory
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             const int r = ld_row + half * 32, n = n0 + r;
@@ -765,11 +750,32 @@ __global__ void __launch_bounds__(256) kv_state_kernel(const float* __restrict__
                 kq = *reinterpret_cast<const float4*>(kbase + (long long)n * ldkv + ld_c4);
                 vq = *reinterpret_cast<const float4*>(vbase + (long long)n * ldkv + ld_c4);
             }
-            Es[r][ld_c4 + 0] = expf(kq.x - kmax_s[ld_c4 + 0]);
-            Es[r][ld_c4 + 1] = expf(kq.y - kmax_s[ld_c4 + 1]);
-            Es[r][ld_c4 + 2] = expf(kq.z - kmax_s[ld_c4 + 2]);
-            Es[r][ld_c4 + 3] = expf(kq.w - kmax_s[ld_c4 + 3]);
+            Es[r][ld_c4 + 0] = kq.x; Es[r][ld_c4 + 1] = kq.y; Es[r][ld_c4 + 2] = kq.z; Es[r][ld_c4 + 3] = kq.w;
             *reinterpret_cast<float4*>(&Vs[r][ld_c4]) = vq;
+        }
+        __syncthreads();
+        // column maximum of the tile (lane = column, 8 warps stride over the tile's rows)
+        float m = -INFINITY;
+#pragma unroll
+        for (int r = wg; r < KV_TILE; r += 8) m = fmaxf(m, Es[r][lane]);
+        red[wg][lane] = m;
+        __syncthreads();
+        if (wg == 0) {
+#pragma unroll
+            for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i][lane]);
+            const float mo = m_s[lane], mn = fmaxf(mo, m);
+            scale_s[lane] = (mo == -INFINITY) ? 0.f : expf(mo - mn);       // first tile: nothing accumulated yet
+            m_s[lane] = mn;
+        }
+        __syncthreads();
+        // rescale what was accumulated under the old maximum, then exponentiate the tile in place
+        const float sc = scale_s[d];
+        acc.x *= sc; acc.y *= sc; acc.z *= sc; acc.w *= sc;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int r = ld_row + half * 32;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) Es[r][ld_c4 + c] = expf(Es[r][ld_c4 + c] - m_s[ld_c4 + c]);    // exp(-inf) = 0 pads
         }
         __syncthreads();
 #pragma unroll 8
@@ -780,14 +786,14 @@ __global__ void __launch_bounds__(256) kv_state_kernel(const float* __restrict__
             acc.z = fmaf(e, v.z, acc.z); acc.w = fmaf(e, v.w, acc.w);
         }
         if (tid < RG_HD) {
+            float colsum = 0.f;
 #pragma unroll 8
             for (int r = 0; r < KV_TILE; ++r) colsum += Es[r][tid];
+            sum_s[tid] = sum_s[tid] * scale_s[tid] + colsum;
         }
         __syncthreads();
     }
-    if (tid < RG_HD) ksum_s[tid] = colsum;
-    __syncthreads();
-    const float s = ksum_s[d];
+    const float s = sum_s[d];
     float* o = state + (long long)b * state_clip_stride + (long long)set * state_set_stride +
                ((long long)h * RG_HD + d) * RG_HD + l4;
     *reinterpret_cast<float4*>(o) = make_float4(acc.x / s, acc.y / s, acc.z / s, acc.w / s);
