@@ -477,6 +477,23 @@ def longform_bench(args, arch, dev, rank, world, barrier):
                                             "x_realtime": round(args.longform_seconds / t_stream, 1),
                                             "phases_rank0_s": {k: round(v, 3) for k, v in phases.items()},
                                             "partition": f"windows' retrieval + inversions sharded over {world} GPU(s), chain on rank 0"}}
+    # several streams per GPU: their chains advance together, one batch of S clips per window index
+    n_streams = 8
+
+    def stream_fn(si):
+        def fn(c, f0, f1):
+            b = S.collate([qs[(c + 11 * si) % len(qs)]])
+            b["retrieval_method"] = "discourse"
+            return b
+        return fn
+    fns = [stream_fn(si) for si in range(n_streams)]
+    lf.run_streams(150 + 135 * 2, fns, infer_kwargs())
+    t_multi = timed_run(lambda: lf.run_streams(n_frames, fns, infer_kwargs()))
+    out["streams_per_gpu"] = {"streams": n_streams * world, "per_gpu": n_streams, "seconds": round(t_multi, 3),
+                              "windows_per_sec": round(world * n_streams * n_win / t_multi, 2),
+                              "x_realtime": round(world * n_streams * args.longform_seconds / t_multi, 1),
+                              "how": "LongformSynthesizer.run_streams: the prev-latent chains of 8 independent streams per GPU "
+                                     "as one batch of 8 clips per window (an evaluation at B = 1 is latency-bound)"}
     if world > 1:
         t_rep = timed_run(lambda: lf.run(n_frames, window_fn, infer_kwargs(), batch_inversions=True))
         out["replicas"] = {"streams": world, "seconds": round(t_rep, 3), "windows_per_sec": round(world * n_win / t_rep, 2),

@@ -156,6 +156,50 @@ class LongformSynthesizer:
         gb.targets = (out["start_rows"].contiguous(), out["start_mask"] > 0.5, out["inv_per_t"].contiguous())
         return gb
 
+    def merge_windows(self, vecs, shapes, template):
+        """ONE GuidedBatch of S clips from the payloads of S windows (the same window index of S independent
+        streams): the chain of several streams then runs as one batch per window -- at B = 1 an evaluation is
+        latency-bound (~100 dependent kernels), so S streams cost about the time of one."""
+        gbs = [self.unpack_window(v, shapes, template) for v in vecs]
+        if len(gbs) == 1:
+            return gbs[0]
+        gb = gbs[0]
+        S = len(gbs)
+        gb.shape = (S,) + tuple(template.shape[1:])
+        xf = {k: torch.cat([g.model_kwargs["xf_out"][k] for g in gbs], 0) for k in ("xf_text", "xf_audio", "xf_spk")}
+        qm = {c: m[:1].expand(S, -1).contiguous() for c, m in template.model_kwargs["query_mask"].items()}
+        gb.model_kwargs = dict(xf_out=xf, re_dict=None, sample_idx=None, query_mask=qm,
+                               motion_mask=torch.cat([g.model_kwargs["motion_mask"] for g in gbs], 0))
+        gb.targets = (torch.cat([g.targets[0] for g in gbs], 0), torch.cat([g.targets[1] for g in gbs], 0),
+                      torch.cat([g.targets[2] for g in gbs], 1))
+        return gb
+
+    def run_streams(self, n_frames, window_fns, inference_kwargs):
+        """S independent streams of the same length on ONE GPU: every stream's windows are prepared, all their
+        exemplars inverted in one batched loop, and the S prev-latent chains advance together, one batch of S clips
+        per window index.  Returns the result dict with a leading stream dimension (pred_* [S, frames, ...],
+        latents [n_windows * S, 43, 512] window-major).  Per stream the arithmetic equals run(batch_inversions=True);
+        the start noise of a window is drawn for the S streams at once."""
+        starts = chunk_starts(n_frames, self.window, self.overlap)
+        arch = self.arch
+        per_stream = []
+        for si, fn in enumerate(window_fns):
+            gbs = []
+            for cidx, f0 in enumerate(starts):
+                batch = self._window_names(dict(fn(cidx, f0, f0 + self.window)), cidx)
+                if batch.get("sample_name") is not None:        # streams must not share retrieval-cache entries
+                    nm = batch["sample_name"]
+                    batch["sample_name"] = [f"s{si}:{x}" for x in nm] if isinstance(nm, (list, tuple)) else f"s{si}:{nm}"
+                batch["inference_kwargs"] = dict(inference_kwargs, use_prev_latent=True, prev_latent=None)
+                gbs.append(arch.prepare(**batch))
+            per_stream.append(gbs)
+        arch.invert_many([gb for gbs in per_stream for gb in gbs])
+        packed = [[self.pack_window(gb) for gb in gbs] for gbs in per_stream]
+        shapes, template = packed[0][0][1], per_stream[0][0]
+        merged = [self.merge_windows([packed[si][c][0] for si in range(len(per_stream))], shapes, template)
+                  for c in range(len(starts))]
+        return self._chain(merged, starts)
+
     def _chain(self, windows, starts):
         """Steps 2 and 3: the serial sampling chain over prepared windows (exemplars inverted or targets shipped)
         and the cross-fade of consecutive windows."""

@@ -142,6 +142,51 @@ def test_shipped_windows_equal_local_chain(arch):
         assert torch.equal(out[k], ref[k]), k
 
 
+@pytest.mark.gpu
+def test_streams_batched_chain_equals_single_streams(arch):
+    """run_streams: the prev-latent chains of S independent streams advance as ONE batch of S clips per window.  With
+    a noise source that does not depend on the draw order (constant per shape), every stream's latents and poses
+    equal its own single-stream run bit for bit (no op couples clips)."""
+    qs = S.SyntheticGestureDataset(48, seed=8)
+    db = arch.model.database
+
+    def fn_of(offset):
+        def fn(cidx, f0, f1):
+            b = S.collate([qs[offset + cidx]])
+            b["retrieval_method"] = "discourse"
+            return b
+        return fn
+
+    def const_noise(shape, device):
+        g = torch.Generator().manual_seed(1234)
+        one = torch.randn(shape[1:], generator=g)
+        return one.expand(shape).contiguous().to(device)
+
+    def fresh():
+        for d in (db.test_indexes, db.test_dbounds, db.test_qbounds):
+            d.clear()
+        torch.manual_seed(5)
+    n_frames = 150 + 2 * 135
+    lf = LF.LongformSynthesizer(arch)
+    arch.diffusion_test.noise_fn = const_noise
+    try:
+        singles = []
+        for off in (3, 11, 20):
+            fresh()
+            singles.append(lf.run(n_frames, fn_of(off), IK, batch_inversions=True))
+        fresh()
+        multi = lf.run_streams(n_frames, [fn_of(3), fn_of(11), fn_of(20)], IK)
+    finally:
+        arch.diffusion_test.noise_fn = None
+    n_win = len(multi["window_starts"])
+    assert tuple(multi["latents"].shape) == (3 * n_win, 43, 512) and multi["pred_upper"].shape[0] == 3
+    lat = multi["latents"].view(n_win, 3, 43, 512)
+    for si, one in enumerate(singles):
+        assert torch.equal(lat[:, si], one["latents"]), si
+        for k in ("pred_upper", "pred_hands", "pred_transl", "pred_exps"):
+            assert torch.equal(multi[k][si:si + 1], one[k]), (si, k)
+
+
 def test_postprocess_recompose_and_upsample_vs_reference():
     """postprocess.recompose_motion / upsample_motion against tools/visualize.py:204-291 executed with the
     reference's rotation_conversions (tests/golden/make_golden.py group "postprocess")."""
