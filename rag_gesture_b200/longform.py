@@ -187,9 +187,6 @@ class LongformSynthesizer:
             gbs = []
             for cidx, f0 in enumerate(starts):
                 batch = self._window_names(dict(fn(cidx, f0, f0 + self.window)), cidx)
-                if batch.get("sample_name") is not None:        # streams must not share retrieval-cache entries
-                    nm = batch["sample_name"]
-                    batch["sample_name"] = [f"s{si}:{x}" for x in nm] if isinstance(nm, (list, tuple)) else f"s{si}:{nm}"
                 batch["inference_kwargs"] = dict(inference_kwargs, use_prev_latent=True, prev_latent=None)
                 gbs.append(arch.prepare(**batch))
             per_stream.append(gbs)
