@@ -146,7 +146,7 @@ def test_shipped_windows_equal_local_chain(arch):
 def test_streams_batched_chain_equals_single_streams(arch):
     """run_streams: the prev-latent chains of S independent streams advance as ONE batch of S clips per window.  With
     a noise source that does not depend on the draw order (constant per shape), every stream's latents and poses
-    equal its own single-stream run bit for bit (no op couples clips)."""
+    equal its own single-stream run (latents bit for bit: no op couples clips)."""
     qs = S.SyntheticGestureDataset(48, seed=8)
     db = arch.model.database
 
