@@ -183,8 +183,10 @@ def test_streams_batched_chain_equals_single_streams(arch):
     lat = multi["latents"].view(n_win, 3, 43, 512)
     for si, one in enumerate(singles):
         assert torch.equal(lat[:, si], one["latents"]), si
+        # the stand-in codec decodes with library matmuls, whose kernel choice depends on the batch size: the decoded
+        # poses agree to fp32 rounding, the latents (this library's path) bit for bit
         for k in ("pred_upper", "pred_hands", "pred_transl", "pred_exps"):
-            assert torch.equal(multi[k][si:si + 1], one[k]), (si, k)
+            assert torch.allclose(multi[k][si:si + 1], one[k], rtol=1e-4, atol=1e-4), (si, k)
 
 
 def test_postprocess_recompose_and_upsample_vs_reference():
