@@ -191,6 +191,30 @@ def test_streams_batched_chain_equals_single_streams(arch):
         #  discontinuous near angle pi: the stand-in codec's unbounded "axis-angles" hit that, so they are not compared)
 
 
+def test_postprocess_recompose_and_upsample_vs_reference():
+    """postprocess.recompose_motion / upsample_motion against tools/visualize.py:204-291 executed with the
+    reference's rotation_conversions (tests/golden/make_golden.py group "postprocess")."""
+    import os
+    import numpy as np
+    from conftest import GOLDEN, rel_l2
+    from rag_gesture_b200.postprocess import recompose_motion, upsample_motion
+    g = np.load(os.path.join(GOLDEN, "postprocess.npz"))
+    t = lambda k: torch.from_numpy(g[k])
+    motion = recompose_motion(t("part_upper"), t("part_lower"), t("part_hands"), t("part_face"),
+                              g["mask_upper"], g["mask_lower"], g["mask_hands"], g["mask_face"])
+    assert torch.equal(motion, t("motion"))
+    aa, facial, trans = upsample_motion(motion, t("facial"), t("trans"), 15, 30)
+    assert tuple(aa.shape) == (2, 40, 165)
+    assert torch.equal(facial, t("facial30")) and torch.equal(trans, t("trans30"))
+    # axis-angle of the same rotation: compare as rotation matrices (sign/branch conventions near pi differ)
+    from rag_gesture_b200.longform import axis_angle_to_matrix
+    Ra, Rb = axis_angle_to_matrix(aa.reshape(2, 40, 55, 3)), axis_angle_to_matrix(t("aa30").reshape(2, 40, 55, 3))
+    assert rel_l2(Ra, Rb) < 1e-5
+    assert rel_l2(aa, t("aa30")) < 1e-4
+    with pytest.raises(ValueError):
+        upsample_motion(motion, t("facial"), t("trans"), 15, 40)
+
+
 @pytest.mark.gpu
 def test_postprocess_and_crossfade_on_device(golden):
     """SURVEY 8f.3 on the device: recomposition, 15->30 fps up-sampling and the 6D cross-fade run on CUDA tensors
