@@ -162,19 +162,22 @@ def test_streams_batched_chain_equals_single_streams(arch):
         one = torch.randn(shape[1:], generator=g)
         return one.expand(shape).contiguous().to(device)
 
-    def fresh():
+    def fresh(seed):
         for d in (db.test_indexes, db.test_dbounds, db.test_qbounds):
             d.clear()
-        torch.manual_seed(5)
+        if seed:
+            torch.manual_seed(5)
     n_frames = 150 + 2 * 135
     lf = LF.LongformSynthesizer(arch)
     arch.diffusion_test.noise_fn = const_noise
     try:
+        # the codec's rsample noise comes from the CPU generator in encode order: stream by stream in both runs,
+        # so the generator is seeded once per run, not once per stream
         singles = []
-        for off in (3, 11, 20):
-            fresh()
+        for k, off in enumerate((3, 11, 20)):
+            fresh(seed=(k == 0))
             singles.append(lf.run(n_frames, fn_of(off), IK, batch_inversions=True))
-        fresh()
+        fresh(seed=True)
         multi = lf.run_streams(n_frames, [fn_of(3), fn_of(11), fn_of(20)], IK)
     finally:
         arch.diffusion_test.noise_fn = None
