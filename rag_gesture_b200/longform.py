@@ -183,7 +183,12 @@ class LongformSynthesizer:
         starts = chunk_starts(n_frames, self.window, self.overlap)
         arch = self.arch
         per_stream = []
+        db = getattr(arch.model, "database", None)
         for si, fn in enumerate(window_fns):
+            # _window_names gives window c of EVERY stream the name ".../c": the retrieval cache (keyed by name) must
+            # not serve one stream's exemplars to another
+            for cache in ((db.test_indexes, db.test_dbounds, db.test_qbounds) if db is not None else ()):
+                cache.clear()
             gbs = []
             for cidx, f0 in enumerate(starts):
                 batch = self._window_names(dict(fn(cidx, f0, f0 + self.window)), cidx)
