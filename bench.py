@@ -701,9 +701,9 @@ def gemm_roofline_tc(n_clips, dev, flush, tc_peak, peak_src, split):
             "GEMM launches of one inversion + one sampling evaluation, time-weighted, L2 flushed before each)",
             "achieved": round(ach, 1), "peak": tc_peak, "unit": "TFLOP/s", "frac": round(ach / tc_peak, 4),
             # dram__bytes_read+write of ONE launch of the costliest shape (qkv / ca_q, N=1536, M=4128) from the
-            # committed ncu --set full capture (profiles/ncu_full_gemm_s3_r01.txt); its algorithmic DRAM bytes are
+            # committed ncu --set full capture (profiles/ncu_full_gemm_tc_r02.txt); its algorithmic DRAM bytes are
             # A 4.2 MB + W 1.6 MB (the fp32 output stays in L2 for the next kernel): no re-reads
-            "traffic": 5832704, "traffic_source": "profiles/ncu_full_gemm_s3_r01.txt, gemm_tc_kernel<128,3,0> grid (12,33)",
+            "traffic": 5832704, "traffic_source": "profiles/ncu_full_gemm_tc_r02.txt, gemm_tc_kernel<128,3,0> grid (12,33)",
             "peak_source": f"{peak_src} bf16 sustained", "rows": [c * 43 for c in n_clips],
             "per_shape_tflops": per, "executed_flop_multiplier": 3 if split else 1}
 
