@@ -730,7 +730,7 @@ __global__ void __launch_bounds__(256) kv_state_kernel(const float* __restrict__
     __shared__ __align__(16) float Vs[KV_TILE][RG_HD];
     __shared__ float red[8][RG_HD];
     __shared__ float m_s[RG_HD], scale_s[RG_HD], sum_s[RG_HD];
-    const int b = blockIdx.x, h = blockIdx.y, set = blockIdx.z;
+    const int h = blockIdx.x, set = blockIdx.y, b = blockIdx.z;
     const int tid = threadIdx.x, lane = tid & 31, wg = tid >> 5;
     const float* rows = kv + (long long)b * N * ldkv + (long long)set * kv_set_stride;
     const float* kbase = rows + k_off + h * RG_HD;
@@ -933,7 +933,9 @@ cudaError_t rg_launch_kv_state(const float* kv, int ldkv, int k_off, int v_off, 
                                float* state, long long state_clip_stride, int B, int n_sets,
                                int kv_set_stride, long long state_set_stride, cudaStream_t st) {
     if (B <= 0 || n_tokens <= 0) return cudaSuccess;
-    kv_state_kernel<<<dim3(B, RG_H, n_sets), 256, 0, st>>>(kv, ldkv, k_off, v_off, n_tokens, state,
+    // grid order: (head, set) fastest, clip slowest -- CTAs that are resident together then read neighbouring 128-byte
+    // slices of the SAME rows of the [rows, sets * 1024] buffer (whole DRAM pages), not the same slice of different rows
+    kv_state_kernel<<<dim3(RG_H, n_sets, B), 256, 0, st>>>(kv, ldkv, k_off, v_off, n_tokens, state,
                                                             state_clip_stride, kv_set_stride,
                                                             state_set_stride);
     return cudaGetLastError();
