@@ -721,13 +721,15 @@ __global__ void __launch_bounds__(512, 2) ca_attn_kernel(const float* __restrict
 // tile raises the maximum, the accumulator row A[d][:] and s[d] are rescaled by exp(m_old - m_new) -- then
 // E = exp(K - m) once per element and E^T V (32x32 outputs, 4 per thread) accumulates from shared memory.
 constexpr int KV_TILE = 64;
+constexpr int KV_EP = RG_HD + 4;        // row pitch of the E tile: 16-byte aligned rows for the 128-bit reads of the product
 __global__ void __launch_bounds__(256) kv_state_kernel(const float* __restrict__ kv, int ldkv,
                                                       int k_off, int v_off, int N,
                                                       float* __restrict__ state,
                                                       long long state_clip_stride,
                                                       int kv_set_stride, long long state_set_stride) {
-    __shared__ __align__(16) float Es[KV_TILE][RG_HD + 1];   // +1: column reads in the product are conflict-free
+    __shared__ __align__(16) float Es[KV_TILE][KV_EP];
     __shared__ __align__(16) float Vs[KV_TILE][RG_HD];
+    __shared__ __align__(16) float part[4][RG_HD][RG_HD];      // per token-quarter partial products, summed at the end
     __shared__ float red[8][RG_HD];
     __shared__ float m_s[RG_HD], scale_s[RG_HD], sum_s[RG_HD];
     const int h = blockIdx.x, set = blockIdx.y, b = blockIdx.z;
@@ -736,8 +738,16 @@ __global__ void __launch_bounds__(256) kv_state_kernel(const float* __restrict__
     const float* kbase = rows + k_off + h * RG_HD;
     const float* vbase = rows + v_off + h * RG_HD;
     if (tid < RG_HD) { m_s[tid] = -INFINITY; sum_s[tid] = 0.f; }
-    const int d = tid >> 3, l4 = (tid & 7) * 4;          // this thread's outputs: A[d][l4..l4+3]
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    // The product E^T V is issue-bound when every thread owns 4 outputs (1 + 1 shared loads per 4 FMAs): here a
+    // thread owns a 4 x 4 block A[d4..d4+3][l4..l4+3] (2 x 128-bit shared loads per 16 FMAs) for a QUARTER of the
+    // tile's tokens; the four quarters are summed through shared memory once, at the end.
+    const int grp = tid >> 6, t64 = tid & 63;
+    const int d4 = (t64 >> 3) * 4, l4 = (t64 & 7) * 4;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
     const int ld_row = tid >> 3, ld_c4 = (tid & 7) * 4;    // tile loader: 32 rows x 8 float4 per pass
     __syncthreads();
     for (int n0 = 0; n0 < N; n0 += KV_TILE) {
@@ -750,7 +760,7 @@ __global__ void __launch_bounds__(256) kv_state_kernel(const float* __restrict__
                 kq = *reinterpret_cast<const float4*>(kbase + (long long)n * ldkv + ld_c4);
                 vq = *reinterpret_cast<const float4*>(vbase + (long long)n * ldkv + ld_c4);
             }
-            Es[r][ld_c4 + 0] = kq.x; Es[r][ld_c4 + 1] = kq.y; Es[r][ld_c4 + 2] = kq.z; Es[r][ld_c4 + 3] = kq.w;
+            *reinterpret_cast<float4*>(&Es[r][ld_c4]) = kq;
             *reinterpret_cast<float4*>(&Vs[r][ld_c4]) = vq;
         }
         __syncthreads();
@@ -769,21 +779,31 @@ __global__ void __launch_bounds__(256) kv_state_kernel(const float* __restrict__
         }
         __syncthreads();
         // rescale what was accumulated under the old maximum, then exponentiate the tile in place
-        const float sc = scale_s[d];
-        acc.x *= sc; acc.y *= sc; acc.z *= sc; acc.w *= sc;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float sc = scale_s[d4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] *= sc;
+        }
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             const int r = ld_row + half * 32;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) Es[r][ld_c4 + c] = expf(Es[r][ld_c4 + c] - m_s[ld_c4 + c]);    // exp(-inf) = 0 pads
+            float4 e = *reinterpret_cast<const float4*>(&Es[r][ld_c4]);
+            e.x = expf(e.x - m_s[ld_c4 + 0]); e.y = expf(e.y - m_s[ld_c4 + 1]);       // exp(-inf) = 0 pads
+            e.z = expf(e.z - m_s[ld_c4 + 2]); e.w = expf(e.w - m_s[ld_c4 + 3]);
+            *reinterpret_cast<float4*>(&Es[r][ld_c4]) = e;
         }
         __syncthreads();
-#pragma unroll 8
-        for (int r = 0; r < KV_TILE; ++r) {
-            const float e = Es[r][d];
+#pragma unroll 4
+        for (int rr = 0; rr < KV_TILE / 4; ++rr) {
+            const int r = grp * (KV_TILE / 4) + rr;
+            const float4 e = *reinterpret_cast<const float4*>(&Es[r][d4]);
             const float4 v = *reinterpret_cast<const float4*>(&Vs[r][l4]);
-            acc.x = fmaf(e, v.x, acc.x); acc.y = fmaf(e, v.y, acc.y);
-            acc.z = fmaf(e, v.z, acc.z); acc.w = fmaf(e, v.w, acc.w);
+            const float ee[4] = {e.x, e.y, e.z, e.w}, vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ee[i], vv[j], acc[i][j]);
         }
         if (tid < RG_HD) {
             float colsum = 0.f;
@@ -793,10 +813,21 @@ __global__ void __launch_bounds__(256) kv_state_kernel(const float* __restrict__
         }
         __syncthreads();
     }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        *reinterpret_cast<float4*>(&part[grp][d4 + i][l4]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    __syncthreads();
+    const int d = tid >> 3, lo4 = (tid & 7) * 4;            // final pass: A[d][lo4..lo4+3], quarters in fixed order
+    float4 a = *reinterpret_cast<const float4*>(&part[0][d][lo4]);
+#pragma unroll
+    for (int g = 1; g < 4; ++g) {
+        const float4 p = *reinterpret_cast<const float4*>(&part[g][d][lo4]);
+        a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
+    }
     const float s = sum_s[d];
     float* o = state + (long long)b * state_clip_stride + (long long)set * state_set_stride +
-               ((long long)h * RG_HD + d) * RG_HD + l4;
-    *reinterpret_cast<float4*>(o) = make_float4(acc.x / s, acc.y / s, acc.z / s, acc.w / s);
+               ((long long)h * RG_HD + d) * RG_HD + lo4;
+    *reinterpret_cast<float4*>(o) = make_float4(a.x / s, a.y / s, a.z / s, a.w / s);
 }
 
 }  // namespace
