@@ -117,7 +117,7 @@ def h2d_bytes(batch):
     return n
 
 
-def run_b200(args):
+def run_b200(args, emit):
     import torch.distributed as dist
     import rag_gesture_b200 as R
     from rag_gesture_b200 import config as C
@@ -171,7 +171,7 @@ def run_b200(args):
         return float(t)
 
     if args.ncu_steps:
-        return ncu_pass(args, arch, batch, dev)
+        return ncu_pass(args, arch, batch, dev, emit)
     # ---- value: device-resident loops -------------------------------------------------------------
     # K prepared batches (inputs, exemplars and retrieval results resident in HBM) through
     # MotionDiffusion.run_many: pass k = guided loop of batch k-1 fused level by level with the inversion loop
@@ -391,7 +391,7 @@ def run_b200(args):
             "gflop_per_clip_step": GFLOP_PER_CLIP_STEP,
             "achieved_tflops_loop": round(value * GFLOP_PER_CLIP_STEP / 1e3 / world, 2),
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -501,7 +501,7 @@ def longform_bench(args, arch, dev, rank, world, barrier):
     return out
 
 
-def ncu_pass(args, arch, batch, dev):
+def ncu_pass(args, arch, batch, dev, emit):
     """`bench.py --ncu-steps S`: the SAME guided batch with both loops cut to their first S DDIM levels, one
     exact kNN pass and one tensor-core kNN call, nothing timed -- the command profiled under ncu (which
     serialises every launch it intercepts: the full 10k-launch step takes tens of minutes there)."""
@@ -522,8 +522,7 @@ def ncu_pass(args, arch, batch, dev):
         q = torch.nn.functional.normalize(torch.randn(Q, 768, device=dev, generator=g), dim=1)
         knn_topk(db, q, 8, index=index)
     torch.cuda.synchronize()
-    print(json.dumps({"ncu_pass": True, "ddim_levels": S, "clips": B_PER_GPU, "exemplars": len(gb.jobs),
-                      "knn_n": args.knn_n}), flush=True)
+    emit({"ncu_pass": True, "ddim_levels": S, "clips": B_PER_GPU, "exemplars": len(gb.jobs), "knn_n": args.knn_n})
 
 
 def gemm_roofline(arch, n_clips, dev, flush, tc_peak, peak_src, precision):
@@ -1001,7 +1000,7 @@ def knn_cpu_baselines(n_full=1_000_000, dim=768, k=8, seconds=10.0):
     return out
 
 
-def run_reference(args):
+def run_reference(args, emit):
     """`--impl reference`: the reference's own CPU implementation of the path on the host cores, same metric and
     config; each step is a bounded sample of the configs[1] workload (all 50 levels of both loops)."""
     rank, world, _ = dist_env()
@@ -1019,7 +1018,7 @@ def run_reference(args):
         cs_tot, t_tot = cs_tot + cs, t_tot + dt
     v = cs_tot / t_tot
     sample = "per step: " + _cpu_sample_text(kind, nc, ne, cs_tot // args.steps, t_tot / args.steps, threads)
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": round(v, 2), "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * t_tot / args.steps, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -1028,7 +1027,7 @@ def run_reference(args):
                              "levels of the inversion and the guided loop (reference's own code, no retrieval kernels)"},
         "cpu_baseline": {"value": round(v, 2), "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": round(v, 2), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0}), flush=True)
+        "gpu_launches": 0})
 
 
 if __name__ == "__main__":
@@ -1048,7 +1047,13 @@ if __name__ == "__main__":
     ap.add_argument("--gemm2-min-rows", type=int, default=0, help="row threshold of the automatic choice (0: library default)")
     ap.add_argument("--gemm2-persist-tiles", type=int, default=0, help="pair tiles from which the 2-CTA kernel is persistent (0: default)")
     a = ap.parse_args()
+    # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version line on the first
+    # communicator), so fd 1 points at stderr while the run lasts and the JSON lines go to the saved descriptor.
+    sys.stdout.flush()
+    _real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    _emit = lambda obj: print(json.dumps(obj), file=_real_stdout, flush=True)
     if a.impl == "reference":
-        run_reference(a)
+        run_reference(a, _emit)
     else:
-        run_b200(a)
+        run_b200(a, _emit)
