@@ -105,7 +105,8 @@ def install_stubs():
     _mod("fairseq")
     _mod("librosa")
     fw = _mod("fuzzywuzzy")
-    fw.fuzz = _mod("fuzzywuzzy.fuzz")
+    from . import fuzz_ratio                                   # restated third-party function, see its header
+    fw.fuzz = _mod("fuzzywuzzy.fuzz", partial_ratio=fuzz_ratio.partial_ratio)
     k = _mod("kornia")
     k.filters = _mod("kornia.filters")
     k.filters.kernels = _mod("kornia.filters.kernels", laplacian_1d=lambda *a, **kw: None)
@@ -137,6 +138,7 @@ def load():
     ns.dt = importlib.import_module("mogen.models.transformers.diffusion_transformer")
     ns.rag_utils = importlib.import_module("mogen.models.transformers.rag.utils")
     ns.discourse = importlib.import_module("mogen.models.transformers.rag.discourse_retrieval")
+    ns.gesture_type = importlib.import_module("mogen.models.transformers.rag.gesture_type_retrieval")
     ns.rg = importlib.import_module("mogen.models.transformers.raggesture")
     ns.arch = importlib.import_module("mogen.models.architectures.diffusion_architecture")
     import torch

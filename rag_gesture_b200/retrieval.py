@@ -13,7 +13,9 @@ B200-first differences in HOW, not WHAT:
     hence the same score tiers;
   * the on-disk LMDB+pyarrow cache (raggesture.py:90-154) is out of scope: dicts are built from the
     dataset in memory, keyed and ordered like LMDB returns them (ASCII-sorted sample names).
-`retrieval_method` keeps the reference's keys; "gesture_type" and "llm" raise.
+`retrieval_method` keeps the reference's keys: "discourse" and "gesture_type" (rag/gesture_type_retrieval.py, with
+the word-similarity fall-back the shipped reference always takes, wordsim.py) are served; "llm" raises (it needs an
+OpenAI endpoint).
 """
 import copy
 import ctypes as C
@@ -22,6 +24,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
+from .wordsim import word_similarity
 
 
 def _clean(s):
@@ -130,17 +133,9 @@ class TextSimilarityIndex:
         return out
 
 
-def discourse_retrieval(text, discourse, prominence, speaker_id, db_idx_2_sense, db_idx_2_discbounds,
-                        db_idx_2_prominence, encoded_text, text_feat_cache, index=None, sense_index=None,
-                        sense_tables=None):
-    """Rule-based discourse retrieval for ONE clip: drives the generator below, answering each ranking request as it
-    comes (one device round trip per request).  Same arguments and return triple as the reference function."""
-    if index is None and len(discourse):
-        names = list(text_feat_cache.keys())
-        index = TextSimilarityIndex(names, [text_feat_cache[n][0] for n in names], encoded_text.device
-                                    if encoded_text.is_cuda else "cuda")
-    gen = discourse_retrieval_steps(text, discourse, prominence, speaker_id, db_idx_2_sense, db_idx_2_discbounds,
-                                    db_idx_2_prominence, encoded_text, text_feat_cache, index, sense_index, sense_tables)
+def _drive(gen, index):
+    """Run one retrieval generator to its result triple, answering each ranking request as it comes (one device
+    round trip per request)."""
     try:
         req = next(gen)
         while True:
@@ -149,11 +144,9 @@ def discourse_retrieval(text, discourse, prominence, speaker_id, db_idx_2_sense,
         return done.value
 
 
-def discourse_retrieval_many(queries, index, **shared):
-    """The same for a BATCH of clips (`queries`: list of per-clip keyword dicts): all clips advance together and
-    the ranking requests of a round go to the device in one batch (TextSimilarityIndex.rank_many), so a batch
-    costs 2-3 round trips instead of one per tie-break.  Results are identical to per-clip calls."""
-    gens = [discourse_retrieval_steps(index=index, **q, **shared) for q in queries]
+def _drive_many(gens, index):
+    """Advance a batch of retrieval generators together: the ranking requests of a round go to the device in one
+    batch (TextSimilarityIndex.rank_many), so a batch of clips costs 2-3 round trips instead of one per tie-break."""
     results, pending = [None] * len(gens), {}
     for i, g in enumerate(gens):
         try:
@@ -171,6 +164,61 @@ def discourse_retrieval_many(queries, index, **shared):
                 results[i] = done.value
                 del pending[i]
     return results
+
+
+def _index_for(index, text_feat_cache, encoded_text):
+    if index is not None:
+        return index
+    names = list(text_feat_cache.keys())
+    return TextSimilarityIndex(names, [text_feat_cache[n][0] for n in names],
+                               encoded_text.device if encoded_text.is_cuda else "cuda")
+
+
+def _rank_tiers(sc, names, index, encoded_text):
+    """Generator: candidate positions ordered as the reference's tier logic orders them -- equal-score tiers, best
+    first (stable: DB order inside a tier); a tier with several members is ordered by text similarity; stop once
+    10 are collected (rag/discourse_retrieval.py:215-246, rag/gesture_type_retrieval.py:124-146).  Yields
+    (query features, DB rows, k) per tie-break and receives the ranked rows; returns at most 10 positions."""
+    import numpy as np
+    order = np.argsort(-sc, kind="stable")
+    ranked, pos = [], 0
+    while pos < len(order) and len(ranked) < 10:
+        end_ = pos + 1
+        while end_ < len(order) and sc[order[end_]] == sc[order[pos]]:
+            end_ += 1
+        tier = order[pos:end_].tolist()
+        if len(tier) > 1:
+            rows = [index.row[names[i]] for i in tier]
+            back = {r: i for r, i in zip(rows, tier)}
+            if len(tier) <= 32:
+                ranked_rows = yield (encoded_text, rows, len(tier))
+                tier = [back[r] for r in ranked_rows]
+            else:
+                # only the first 32 by similarity can reach the top 10; the rest keep tier order
+                head = yield (encoded_text, rows, 32)
+                hs = set(head)
+                tier = [back[r] for r in head] + [i for r, i in zip(rows, tier) if r not in hs]
+        ranked += tier
+        pos = end_
+    return ranked[:10]
+
+
+def discourse_retrieval(text, discourse, prominence, speaker_id, db_idx_2_sense, db_idx_2_discbounds,
+                        db_idx_2_prominence, encoded_text, text_feat_cache, index=None, sense_index=None,
+                        sense_tables=None):
+    """Rule-based discourse retrieval for ONE clip: drives the generator below.  Same arguments and return triple
+    as the reference function."""
+    if len(discourse):
+        index = _index_for(index, text_feat_cache, encoded_text)
+    return _drive(discourse_retrieval_steps(text, discourse, prominence, speaker_id, db_idx_2_sense,
+                                            db_idx_2_discbounds, db_idx_2_prominence, encoded_text, text_feat_cache,
+                                            index, sense_index, sense_tables), index)
+
+
+def discourse_retrieval_many(queries, index, **shared):
+    """The same for a BATCH of clips (`queries`: list of per-clip keyword dicts).  Results are identical to
+    per-clip calls."""
+    return _drive_many([discourse_retrieval_steps(index=index, **q, **shared) for q in queries], index)
 
 
 def discourse_retrieval_steps(text, discourse, prominence, speaker_id, db_idx_2_sense, db_idx_2_discbounds,
@@ -215,34 +263,90 @@ def discourse_retrieval_steps(text, discourse, prominence, speaker_id, db_idx_2_
             names = [n for n, _ in scored]
             sc = np.array([v for _, v in scored], dtype=np.float64)
             bound_of = lambda i: bounds_of[names[i]]
-        # equal-score tiers, best first (stable: DB order inside a tier); a tier with several members is
-        # ordered by text similarity; stop once 10 are collected (rag/discourse_retrieval.py:215-246)
-        order = np.argsort(-sc, kind="stable")
-        ranked, pos = [], 0
-        while pos < len(order) and len(ranked) < 10:
-            end_ = pos + 1
-            while end_ < len(order) and sc[order[end_]] == sc[order[pos]]:
-                end_ += 1
-            tier = order[pos:end_].tolist()
-            if len(tier) > 1:
-                rows = [index.row[names[i]] for i in tier]
-                back = {r: i for r, i in zip(rows, tier)}
-                if len(tier) <= 32:
-                    ranked_rows = yield (encoded_text, rows, len(tier))
-                    tier = [back[r] for r in ranked_rows]
-                else:
-                    # only the first 32 by similarity can reach the top 10; the rest keep tier order
-                    head = yield (encoded_text, rows, 32)
-                    hs = set(head)
-                    tier = [back[r] for r in head] + [i for r, i in zip(rows, tier) if r not in hs]
-            ranked += tier
-            pos = end_
-        ranked = ranked[:10]
+        ranked = yield from _rank_tiers(sc, names, index, encoded_text)
         sample_indexes[qi] = [names[i] for i in ranked]
         d_bounds[qi] = {}
         for i in ranked:
             b = bound_of(i)
             d_bounds[qi][names[i]] = (b[1], b[0], round(b[4], 3), round(b[5], 3))
+    assert len(d_bounds) == len(sample_indexes) == len(query_bounds)
+    return sample_indexes, d_bounds, query_bounds
+
+
+def build_type_index(db_idx_2_gesture_labels):
+    """gesture type -> [(sample name, speaker, [(position among the sample's non-beat labels, word), ...]), ...] in
+    DB order: the samples a query label of that type can score against, instead of a walk over every sample per
+    query label (rag/gesture_type_retrieval.py:47)."""
+    out = {}
+    for name, entry in db_idx_2_gesture_labels.items():
+        spk, per_type = entry[0], {}
+        for j, g in enumerate(x for x in entry[1:] if x["name"] != "beat"):
+            per_type.setdefault(g["name"], []).append((j, g["word"]))
+        for t, rel in per_type.items():
+            out.setdefault(t, []).append((name, spk, rel))
+    return out
+
+
+def gesture_type_retrieval(text, gesture_labels, speaker_id, db_idx_2_gesture_labels, encoded_text, text_feat_cache,
+                           index=None, type_index=None, word_model=None, sim_cache=None):
+    """Retrieval by semantic gesture label for ONE clip; same arguments and return triple as
+    rag/gesture_type_retrieval.py:8-178."""
+    if any(g["name"] != "beat" for g in gesture_labels):
+        index = _index_for(index, text_feat_cache, encoded_text)
+    return _drive(gesture_type_retrieval_steps(text, gesture_labels, speaker_id, db_idx_2_gesture_labels,
+                                               encoded_text, text_feat_cache, index, type_index, word_model,
+                                               sim_cache), index)
+
+
+def gesture_type_retrieval_many(queries, index, **shared):
+    return _drive_many([gesture_type_retrieval_steps(index=index, **q, **shared) for q in queries], index)
+
+
+def gesture_type_retrieval_steps(text, gesture_labels, speaker_id, db_idx_2_gesture_labels, encoded_text,
+                                 text_feat_cache, index=None, type_index=None, word_model=None, sim_cache=None):
+    """Generator core (ranking requests as in discourse_retrieval_steps).  Per non-beat query label, every DB
+    sample holding a label of the same type scores 2, +2 for the query's speaker, +5 when one of those labels
+    carries the query's word, else + 3 / (1 + 2 * similarity) of the most similar word (the reference's formula:
+    it DEcreases with the similarity, rag/gesture_type_retrieval.py:108-110); the chosen label's bounds travel
+    with the sample.  -> ({q: [names]}, {q: {name: (word, type, start, end)}}, {q: (word_lower, type, start, end)})."""
+    import numpy as np
+    labels = [g for g in gesture_labels if g["name"] != "beat"]
+    sample_indexes, d_bounds = {}, {}
+    if len(labels) == 0:
+        return sample_indexes, d_bounds, {}
+    if type_index is None:
+        type_index = build_type_index(db_idx_2_gesture_labels)
+    sim_cache = {} if sim_cache is None else sim_cache
+    query_bounds = {qi: (g["word"].lower(), g["name"], g["start"], g["end"]) for qi, g in enumerate(labels)}
+    for qi, g in enumerate(labels):
+        q_word, cands = g["word"], type_index.get(g["name"], [])
+        names = [c[0] for c in cands]
+        sc, top = np.zeros(len(cands)), [0] * len(cands)
+        for i, (_, spk, rel) in enumerate(cands):
+            score = 2
+            if spk == speaker_id:
+                score += 2
+            words = [w for _, w in rel]
+            if q_word in words:
+                score += 5
+                top[i] = rel[words.index(q_word)][0]
+            else:
+                sims = []
+                for w in words:
+                    key = (w, q_word)
+                    if key not in sim_cache:
+                        sim_cache[key] = word_similarity(w, q_word, word_model)
+                    sims.append(sim_cache[key])
+                j = int(np.argmax(sims))
+                top[i] = rel[j][0]
+                score += 3 / (1 + 2 * sims[j])
+            sc[i] = score
+        ranked = yield from _rank_tiers(sc, names, index, encoded_text)
+        sample_indexes[qi] = [names[i] for i in ranked]
+        d_bounds[qi] = {}
+        for i in ranked:
+            b = [x for x in db_idx_2_gesture_labels[names[i]][1:] if x["name"] != "beat"][top[i]]
+            d_bounds[qi][names[i]] = (b["word"], b["name"], round(b["start"], 3), round(b["end"], 3))
     assert len(d_bounds) == len(sample_indexes) == len(query_bounds)
     return sample_indexes, d_bounds, query_bounds
 
@@ -374,8 +478,9 @@ class RetrievalDatabase(nn.Module):
         self.latent_dim, self.text_latent_dim = latent_dim, text_latent_dim
         self.max_seq_len, self.motion_fps, self.motion_framechunksize = max_seq_len, motion_fps, motion_framechunksize
         self.dataset = dataset
-        self.retrieval_method = {"discourse": self._discourse, "gesture_type": _not_supported("gesture_type"),
+        self.retrieval_method = {"discourse": self._discourse, "gesture_type": self._gesture_type,
                                  "llm": _not_supported("llm")}
+        self.word_model = None              # callable(w1, w2) -> similarity; None = the shipped fall-back (wordsim.py)
         self.train_indexes, self.test_indexes = {}, {}
         self.train_dbounds, self.test_dbounds = {}, {}
         self.train_qbounds, self.test_qbounds = {}, {}
@@ -409,6 +514,8 @@ class RetrievalDatabase(nn.Module):
         self.sample_names = {i: s for i, s in enumerate(self.idx_2_text.keys())}
         self._sense_index = build_sense_index(self.idx_2_sense)
         self._sense_tables = ({}, {})      # (sense -> SenseTable, connective -> id)
+        self._type_index = build_type_index(self.idx_2_gesture_labels)
+        self._word_sims = {}                # (db word, query word) -> similarity
         self._index, self._index_device = None, device
         self._corpus, self._corpus_rows = None, None
         self.corpus_budget_bytes = 64 << 30     # exemplar fields kept in HBM when the corpus fits
@@ -451,6 +558,11 @@ class RetrievalDatabase(nn.Module):
         return discourse_retrieval(index=self.text_index(dev), sense_index=self._sense_index,
                                    sense_tables=self._sense_tables, **kw)
 
+    def _gesture_type(self, **kw):
+        dev = kw["encoded_text"].device if kw["encoded_text"].is_cuda else (self._index_device or "cuda")
+        return gesture_type_retrieval(index=self.text_index(dev), type_index=self._type_index,
+                                      word_model=self.word_model, sim_cache=self._word_sims, **kw)
+
     # raggesture.py:313-477, inference branches only
     def retrieve(self, retr_method, text, text_features, audio, discourse, gesture_labels, text_times,
                  prominence, speaker_id, idx=None):
@@ -482,15 +594,24 @@ class RetrievalDatabase(nn.Module):
             raise NotImplementedError("Not released for training for retrieval")
         out = [self._cached(retr_method, c.get("idx")) for c in clips]
         miss = [i for i, o in enumerate(out) if o is None]
-        if retr_method == "discourse" and len(miss) > 1 and self.retrieval_method["discourse"] == self._discourse:
+        stock = {"discourse": self._discourse, "gesture_type": self._gesture_type}
+        if len(miss) > 1 and retr_method in stock and self.retrieval_method[retr_method] == stock[retr_method]:
             q0 = clips[miss[0]]["text_features"]
             dev = q0.device if q0.is_cuda else (self._index_device or "cuda")
-            queries = [dict(text=clips[i]["text"], discourse=clips[i]["discourse"], prominence=clips[i]["prominence"],
-                            speaker_id=clips[i]["speaker_id"], encoded_text=clips[i]["text_features"]) for i in miss]
-            res = discourse_retrieval_many(queries, self.text_index(dev), sense_index=self._sense_index,
-                                           sense_tables=self._sense_tables, db_idx_2_sense=self.idx_2_sense,
-                                           db_idx_2_discbounds=self.idx_2_discbounds,
-                                           db_idx_2_prominence=self.idx_2_prominence, text_feat_cache=self.idx_2_text)
+            if retr_method == "discourse":
+                queries = [dict(text=clips[i]["text"], discourse=clips[i]["discourse"], prominence=clips[i]["prominence"],
+                                speaker_id=clips[i]["speaker_id"], encoded_text=clips[i]["text_features"]) for i in miss]
+                res = discourse_retrieval_many(queries, self.text_index(dev), sense_index=self._sense_index,
+                                               sense_tables=self._sense_tables, db_idx_2_sense=self.idx_2_sense,
+                                               db_idx_2_discbounds=self.idx_2_discbounds,
+                                               db_idx_2_prominence=self.idx_2_prominence, text_feat_cache=self.idx_2_text)
+            else:
+                queries = [dict(text=clips[i]["text"], gesture_labels=clips[i]["gesture_labels"],
+                                speaker_id=clips[i]["speaker_id"], encoded_text=clips[i]["text_features"]) for i in miss]
+                res = gesture_type_retrieval_many(queries, self.text_index(dev), type_index=self._type_index,
+                                                  word_model=self.word_model, sim_cache=self._word_sims,
+                                                  db_idx_2_gesture_labels=self.idx_2_gesture_labels,
+                                                  text_feat_cache=self.idx_2_text)
             for i, r in zip(miss, res):
                 cached = self._cached(retr_method, clips[i].get("idx"))     # a repeated idx inside the batch
                 out[i] = cached if cached is not None else self._store(retr_method, clips[i].get("idx"), r)

@@ -242,6 +242,12 @@ CONNECTIVES = ["and", "but", "so", "because", "then", "when", "if", "also", "whi
 SENSES = ["Expansion.Conjunction", "Comparison.Contrast", "Contingency.Cause", "Temporal.Asynchronous",
           "Temporal.Synchronous", "Contingency.Condition", "Comparison.Concession", "Expansion.Alternative"]
 FILLERS = ["the", "gesture", "people", "really", "think", "time", "maybe", "little"]
+# words of the semantic gesture labels: shared stems and multi-word entries so that the word-similarity
+# fall-back of the gesture-type rules (rag/utils.py:239-272) sees exact, partial and no matches
+GESTURE_WORDS = ["this", "that", "these", "there", "here", "big", "bigger", "biggest", "small", "smaller", "round",
+                 "around", "up", "upward", "down", "downward", "open", "open hand", "both hands", "together", "apart",
+                 "you", "your", "me", "myself", "forward", "back", "backward", "one", "two", "first of all", "all"]
+GESTURE_TYPES = ["beat", "deictic", "iconic", "metaphoric"]
 
 
 class SyntheticGestureDataset:
@@ -291,8 +297,15 @@ class SyntheticGestureDataset:
                 for w in d[0].split():
                     prominence.append((w, d[6], d[7], round(r.uniform(0, 3), 4)))
         prominence.sort(key=lambda p: p[1])
-        gestures = [{"name": r.choice(["beat", "deictic", "iconic", "metaphoric"]), "start": d[6],
+        gestures = [{"name": r.choice(GESTURE_TYPES), "start": d[6],
                      "end": d[7], "word": d[0]} for d in discourse[:1]]
+        # further semantic gesture labels from their own stream (the draws above stay what the committed goldens saw)
+        r2 = random.Random(self.seed * 7_368_787 + 31 * i + 5)
+        for _ in range(r2.choice([0, 1, 1, 2, 3])):
+            gs = round(r2.uniform(0, 9.3), 3)
+            gestures.append({"name": r2.choice(GESTURE_TYPES), "start": gs,
+                             "end": round(min(10.0, gs + r2.uniform(0.2, 1.6)), 3), "word": r2.choice(GESTURE_WORDS)})
+        gestures.sort(key=lambda g_: g_["start"])
         self._ann[i] = (spk, discourse, prominence, gestures, r.randint(8, 32))
         return self._ann[i]
 

@@ -191,7 +191,8 @@ def make_ref_db_class(ns):
             self.num_retrieval, self.topk, self.latent_dim = num_retrieval, topk, latent_dim
             self.text_latent_dim, self.max_seq_len = text_latent_dim, max_seq_len
             self.motion_fps, self.motion_framechunksize = motion_fps, motion_framechunksize
-            self.retrieval_method = {"discourse": ns.discourse.discourse_retrieval}
+            self.retrieval_method = {"discourse": ns.discourse.discourse_retrieval,
+                                     "gesture_type": ns.gesture_type.gesture_type_retrieval}
             self.train_indexes, self.test_indexes = {}, {}
             self.train_dbounds, self.test_dbounds = {}, {}
             self.train_qbounds, self.test_qbounds = {}, {}
@@ -263,6 +264,45 @@ def gen_retrieval(ns):
     print("wrote retrieval.json; exemplars placed:", sum(len(x) for x in re["retr_startends"]))
 
 
+def gen_gesture_type(ns):
+    """gesture_type_retrieval of the reference (with `fuzz.partial_ratio` restated, oracle/fuzz_ratio.py: the shipped
+    word-similarity path, rag/utils.py:269-270) on the synthetic gesture labels, and RetrievalDatabase.forward with
+    retrieval_method="gesture_type" (exemplar padding -0.2/+0.1 s above 0.9 s, raggesture.py:617-627)."""
+    import json
+    from rag_gesture_b200.codec import SyntheticGestureCodec
+    ds = S.SyntheticGestureDataset(N_DB, seed=7)
+    qs = S.SyntheticGestureDataset(N_QUERY, seed=8)
+    db = make_ref_db_class(ns)(dataset=ds, **C.retrieval_cfg()).eval()
+    out = {"queries": []}
+    for i in range(N_QUERY):
+        spk, _, _, gest, _ = qs.annotations(i)
+        idx, bounds, qb = ns.gesture_type.gesture_type_retrieval(
+            text="", gesture_labels=gest, speaker_id=spk, db_idx_2_gesture_labels=db.idx_2_gesture_labels,
+            encoded_text=qs.text_feature(i), text_feat_cache=db.idx_2_text)
+        out["queries"].append(_jsonable({"idx": idx, "bounds": bounds, "qbounds": qb}))
+    codec = SyntheticGestureCodec(C.denoiser_cfg()["vae_cfg"])
+    batch = S.collate([qs[i] for i in range(N_QUERY)])
+    cond = dict(text=batch["raw_word"], audio=batch["raw_audio"], text_enc=batch["word"],
+                text_features=batch["text_features"], audio_enc=batch["audio"], discourse=batch["discourse"],
+                prominence=batch["prominence"], speaker_ids=batch["speaker_ids"],
+                gesture_labels=batch["gesture_labels"], text_times=batch["text_segments"])
+    torch.manual_seed(5)
+    with torch.no_grad():
+        re = db(cond, batch["motion_length"], "cpu", idx=batch["sample_name"], retrieval_method="gesture_type",
+                gesture_rep_encoder=codec)
+    out["retr_startends"] = _jsonable(re["retr_startends"])
+    out["query_startends"] = _jsonable(re["query_startends"])
+    out["raw_sample_names"] = _jsonable(re["raw_sample_names"])
+    out["raw_type2words"] = _jsonable(re["raw_type2words"])
+    out["re_mask_sum"] = re["re_mask"].sum(1).tolist()
+    out["latents_digest"] = digest(re["raw_motion_latents"])
+    with open(os.path.join(HERE, "gesture_type.json"), "w") as f:
+        json.dump(out, f)
+    save("gesture_type_latents", raw_motion_latents=re["raw_motion_latents"][:4])
+    print("wrote gesture_type.json; query labels:", sum(len(q["idx"]) for q in out["queries"]),
+          "exemplars placed:", sum(len(x) for x in re["retr_startends"]))
+
+
 def build_reference_architecture(ns, ds, sd):
     from rag_gesture_b200.codec import SyntheticGestureCodec
     ns.dt.GestureRepEncoder = SyntheticGestureCodec
@@ -311,6 +351,26 @@ def gen_pipeline(ns):
     save("pipeline_b3", prev_latentout=res["prev_latentout"], pred_upper=res["pred_upper"][:, ::10],
          pred_hands=res["pred_hands"][:, ::10], n_exemplars=np.array(n_ex),
          chain_w0=outs[0], chain_w1=outs[1])
+
+
+def gen_pipeline_gesture_type(ns):
+    """MotionDiffusion.forward of the reference with retrieval_method="gesture_type", B=2: exemplars chosen by the
+    semantic-gesture rules, inverted and inserted with guidance exactly as in the discourse run."""
+    ds = S.SyntheticGestureDataset(N_DB, seed=7)
+    qs = S.SyntheticGestureDataset(N_QUERY, seed=8)
+    arch = build_reference_architecture(ns, ds, S.synthetic_state_dict(0))
+    batch = S.collate([qs[i] for i in [0, 2]])
+    batch["retrieval_method"] = "gesture_type"
+    batch["inference_kwargs"] = dict(use_inversion=True, outpaint=False, inversion_start_time=-1,
+                                     insertion_guidance=True, guidance_iters=[0] * 25 + list(range(25)),
+                                     guidance_lr=0.1)
+    torch.manual_seed(515)
+    with torch.no_grad():
+        res = arch(**batch)
+    n_ex = sum(len(x) for x in res["retrieval_dict"]["retr_startends"])
+    print("gesture_type pipeline exemplars:", n_ex, res["retrieval_dict"]["raw_sample_names"])
+    save("pipeline_gesture_type_b2", prev_latentout=res["prev_latentout"], pred_upper=res["pred_upper"][:, ::10],
+         pred_hands=res["pred_hands"][:, ::10], n_exemplars=np.array(n_ex))
 
 
 def gen_outpaint(ns):
@@ -497,7 +557,8 @@ def gen_codec(ns):
 
 
 GROUPS = {"rotation": gen_rotation, "schedule": gen_schedule, "denoiser": gen_denoiser, "loops": gen_loops,
-          "retrieval": gen_retrieval, "pipeline": gen_pipeline, "outpaint": gen_outpaint, "two_branch": gen_two_branch,
+          "retrieval": gen_retrieval, "gesture_type": gen_gesture_type, "pipeline": gen_pipeline,
+          "pipeline_gesture_type": gen_pipeline_gesture_type, "outpaint": gen_outpaint, "two_branch": gen_two_branch,
           "codec": gen_codec,
           "postprocess": gen_postprocess}
 

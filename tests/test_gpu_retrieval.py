@@ -62,6 +62,42 @@ def test_discourse_retrieval_vs_reference(db, dev):
         assert json.loads(json.dumps({str(k): v for k, v in bounds.items()})) == g["bounds"], i
 
 
+def test_gesture_type_retrieval_vs_reference(db, dev):
+    """retrieval_method="gesture_type" with the CUDA tie-break ranking: per-clip triples and the batched forward
+    (retrieve_many -> gesture_type_retrieval_many, window placement) against the reference's golden vectors."""
+    from rag_gesture_b200.codec import SyntheticGestureCodec
+    with open(os.path.join(GOLDEN, "gesture_type.json")) as f:
+        gold = json.load(f)
+    norm = lambda o: json.loads(json.dumps(o))
+    qs = S.SyntheticGestureDataset(N_QUERY, seed=8)
+    for i in range(N_QUERY):
+        spk, _, _, gest, _ = qs.annotations(i)
+        idx, bounds, qb = db.retrieval_method["gesture_type"](
+            text="", gesture_labels=gest, speaker_id=spk, db_idx_2_gesture_labels=db.idx_2_gesture_labels,
+            encoded_text=qs.text_feature(i).to(dev), text_feat_cache=db.idx_2_text)
+        g = gold["queries"][i]
+        assert norm({str(k): v for k, v in idx.items()}) == g["idx"], i
+        assert norm({str(k): v for k, v in bounds.items()}) == g["bounds"], i
+    batch = S.collate([qs[i] for i in range(N_QUERY)])
+    cond = dict(text=batch["raw_word"], audio=batch["raw_audio"].to(dev), text_enc=batch["word"].to(dev),
+                text_features=[t.to(dev) for t in batch["text_features"]], audio_enc=batch["audio"].to(dev),
+                discourse=batch["discourse"], prominence=batch["prominence"], speaker_ids=batch["speaker_ids"].to(dev),
+                gesture_labels=batch["gesture_labels"], text_times=batch["text_segments"])
+    for d in (db.test_indexes, db.test_dbounds, db.test_qbounds):
+        d.clear()
+    torch.manual_seed(5)
+    re = db(cond, batch["motion_length"], dev, idx=batch["sample_name"], retrieval_method="gesture_type",
+            gesture_rep_encoder=SyntheticGestureCodec(C.denoiser_cfg()["vae_cfg"]).to(dev))
+    for d in (db.test_indexes, db.test_dbounds, db.test_qbounds):
+        d.clear()
+    assert norm([{str(k): list(v) for k, v in d.items()} for d in re["retr_startends"]]) == gold["retr_startends"]
+    assert norm([{str(k): list(v) for k, v in d.items()} for d in re["query_startends"]]) == gold["query_startends"]
+    assert norm(re["raw_sample_names"]) == gold["raw_sample_names"]
+    assert re["re_mask"].sum(1).tolist() == gold["re_mask_sum"]
+    ref = torch.from_numpy(np.load(os.path.join(GOLDEN, "gesture_type_latents.npz"))["raw_motion_latents"])
+    assert torch.allclose(re["raw_motion_latents"][:4].cpu(), ref, atol=1e-5)
+
+
 def test_sharded_retriever_vs_reference(db, dev):
     """ShardedDiscourseRetriever on the device (its own block of the text features through rg_text_similarity, the
     merge under (score, similarity, DB order)) against the reference's golden lists and bounds for all 48 queries."""
@@ -311,6 +347,34 @@ def _prev_latent_chain(arch, dev, tol, tier):
     assert max(errs) < tol
 
 
+def _gesture_type_batch(arch, dev, tol, tier):
+    g = np.load(os.path.join(GOLDEN, "pipeline_gesture_type_b2.npz"))
+    qs = S.SyntheticGestureDataset(N_QUERY, seed=8)
+    batch = S.collate([qs[i] for i in [0, 2]])
+    batch["retrieval_method"] = "gesture_type"
+    batch["inference_kwargs"] = dict(use_inversion=True, outpaint=False, inversion_start_time=-1,
+                                     insertion_guidance=True, guidance_iters=[0] * 25 + list(range(25)),
+                                     guidance_lr=0.1)
+    db = arch.model.database
+    for d in (db.test_indexes, db.test_dbounds, db.test_qbounds):
+        d.clear()
+    arch.diffusion_test.noise_fn = _cpu_noise
+    torch.manual_seed(515)
+    res = arch(**batch)
+    n_ex = sum(len(x) for x in res["retrieval_dict"]["retr_startends"])
+    assert n_ex == int(g["n_exemplars"]) == 3
+    errs = (rel_l2(res["prev_latentout"].cpu(), torch.from_numpy(g["prev_latentout"])),
+            rel_l2(res["pred_upper"][:, ::10].cpu(), torch.from_numpy(g["pred_upper"])),
+            rel_l2(res["pred_hands"][:, ::10].cpu(), torch.from_numpy(g["pred_hands"])))
+    print("gesture_type guided batch (%s tier) rel-L2 vs reference: latents %.3g, upper %.3g, hands %.3g" % ((tier,) + errs))
+    assert max(errs) < tol
+
+
+def test_gesture_type_batch_vs_reference(arch, dev):
+    """The whole guided batch with exemplars chosen by the semantic-gesture rules (retrieval_method="gesture_type")."""
+    _gesture_type_batch(arch, dev, 1e-3, "fp32")
+
+
 def test_full_guided_batch_vs_reference(arch, dev):
     """configs[1] in miniature: B=3, discourse retrieval, batched inversion, insertion guidance."""
     _full_guided_batch(arch, dev, 1e-3, "fp32")          # north_star fp32 tier
@@ -346,6 +410,11 @@ def test_tc_full_guided_batch_vs_reference(arch_tc, dev):
 def test_tc_longform_prev_latent_chain(arch_tc, dev):
     m, tol, tier = arch_tc
     _prev_latent_chain(m, dev, tol, tier)
+
+
+def test_tc_gesture_type_batch_vs_reference(arch_tc, dev):
+    a, tol, tier = arch_tc
+    _gesture_type_batch(a, dev, tol, tier)
 
 
 def _outpaint_batch(arch, dev, tol, tier):

@@ -98,6 +98,86 @@ def test_product_host_logic_vs_reference(gold, db):
     assert re2["retr_startends"] == re["retr_startends"]
 
 
+@pytest.fixture(scope="module")
+def gold_gt():
+    with open(os.path.join(GOLDEN, "gesture_type.json")) as f:
+        return json.load(f)
+
+
+def test_partial_ratio_restatements():
+    """fuzzywuzzy 0.18.0 is not in the image: the product's and the oracle's restatements of fuzz.partial_ratio
+    agree with each other and with the answers the package documents."""
+    import random
+    from oracle import fuzz_ratio
+    from rag_gesture_b200.wordsim import partial_ratio, word_similarity
+    for fn in (partial_ratio, fuzz_ratio.partial_ratio):
+        assert fn("YANKEES", "NEW YORK YANKEES") == 100
+        assert fn("NEW YORK METS", "NEW YORK YANKEES") == 69
+        assert fn("this is a test", "this is a test!") == 100
+        assert fn("", "abc") == 0 and fn(None, "abc") == 0 and fn("abc", "abc") == 100
+    r = random.Random(3)
+    words = S.GESTURE_WORDS + S.CONNECTIVES + S.FILLERS
+    for _ in range(2000):
+        a, b = r.choice(words), r.choice(words)
+        if r.random() < 0.3:
+            a = "".join(r.choice("abcdeh ") for _ in range(r.randint(1, 12)))
+        assert partial_ratio(a, b) == fuzz_ratio.partial_ratio(a, b), (a, b)
+    # the hook for a real embedding model: the reference's multi-word averaging, and its catch-all fall-back
+    const = lambda w1, w2: 0.25 if w1 != "open" else 0.75
+    assert word_similarity("open hand", "big", const) == (0.75 + 0.25) / 2
+    assert word_similarity("big", "first of all", const) == pytest.approx(0.25)
+    assert word_similarity("open hand", "both hands", const) == (0.75 + 0.75 + 0.25 + 0.25) / 4
+
+    def missing(w1, w2):
+        raise KeyError(w1)
+    assert word_similarity("around", "round", missing) == partial_ratio("around", "round") / 100 == 1.0
+
+
+def _cond(batch):
+    return dict(text=batch["raw_word"], audio=batch["raw_audio"], text_enc=batch["word"],
+                text_features=batch["text_features"], audio_enc=batch["audio"], discourse=batch["discourse"],
+                prominence=batch["prominence"], speaker_ids=batch["speaker_ids"],
+                gesture_labels=batch["gesture_labels"], text_times=batch["text_segments"])
+
+
+def test_gesture_type_host_logic_vs_reference(gold_gt, db):
+    """gesture-type rules through the type index + tiers + window placement (the -0.2/+0.1 s padding of long
+    exemplars) == the reference's gesture_type_retrieval and forward(retrieval_method="gesture_type")."""
+    import numpy as np
+    db._index = OracleIndex(db)
+    qs = S.SyntheticGestureDataset(N_QUERY, seed=8)
+    n_labels = 0
+    for i in range(N_QUERY):
+        spk, _, _, gest, _ = qs.annotations(i)
+        idx, bounds, qb = db.retrieval_method["gesture_type"](
+            text="", gesture_labels=gest, speaker_id=spk, db_idx_2_gesture_labels=db.idx_2_gesture_labels,
+            encoded_text=qs.text_feature(i), text_feat_cache=db.idx_2_text)
+        g = gold_gt["queries"][i]
+        assert _norm({str(k): v for k, v in idx.items()}) == g["idx"], i
+        assert _norm({str(k): v for k, v in bounds.items()}) == g["bounds"], i
+        assert _norm({str(k): list(v) for k, v in qb.items()}) == g["qbounds"], i
+        n_labels += len(idx)
+    assert n_labels > 60
+    batch = S.collate([qs[i] for i in range(N_QUERY)])
+    for d in (db.test_indexes, db.test_dbounds, db.test_qbounds):      # keyed by clip name, ONE method per clip (as the
+        d.clear()                                                      # reference): drop the discourse test's entries
+    torch.manual_seed(5)
+    re = db(_cond(batch), batch["motion_length"], "cpu", idx=batch["sample_name"], retrieval_method="gesture_type",
+            gesture_rep_encoder=SyntheticGestureCodec(C.denoiser_cfg()["vae_cfg"]))
+    assert _norm([{str(k): list(v) for k, v in d.items()} for d in re["retr_startends"]]) == gold_gt["retr_startends"]
+    assert _norm([{str(k): list(v) for k, v in d.items()} for d in re["query_startends"]]) == gold_gt["query_startends"]
+    assert _norm(re["raw_sample_names"]) == gold_gt["raw_sample_names"]
+    assert _norm([{str(k): list(v) for k, v in d.items()} for d in re["raw_type2words"]]) == gold_gt["raw_type2words"]
+    assert re["re_mask"].sum(1).tolist() == gold_gt["re_mask_sum"]
+    ref = torch.from_numpy(np.load(os.path.join(GOLDEN, "gesture_type_latents.npz"))["raw_motion_latents"])
+    assert torch.allclose(re["raw_motion_latents"][:4], ref, atol=1e-6)
+    # a clip without semantic labels retrieves nothing
+    assert db.retrieval_method["gesture_type"](
+        text="", gesture_labels=[{"name": "beat", "word": "and", "start": 0.0, "end": 1.0}], speaker_id=3,
+        db_idx_2_gesture_labels=db.idx_2_gesture_labels, encoded_text=qs.text_feature(0),
+        text_feat_cache=db.idx_2_text) == ({}, {}, {})
+
+
 def test_window_placement_edge_cases(db):
     # exemplar at the very end of the clip, query at the start: clamps + parity rules (App. D)
     w = db.place_window(("and", "s", 0.0, 0.2), ("and", "s", 9.8, 10.0), "discourse", -1)
