@@ -79,7 +79,7 @@ def test_gesture_type_retrieval_vs_reference(db, dev):
         assert norm({str(k): v for k, v in idx.items()}) == g["idx"], i
         assert norm({str(k): v for k, v in bounds.items()}) == g["bounds"], i
     batch = S.collate([qs[i] for i in range(N_QUERY)])
-    cond = dict(text=batch["raw_word"], audio=batch["raw_audio"].to(dev), text_enc=batch["word"].to(dev),
+    cond = dict(text=batch["raw_word"], audio=batch["raw_audio"], text_enc=batch["word"].to(dev),
                 text_features=[t.to(dev) for t in batch["text_features"]], audio_enc=batch["audio"].to(dev),
                 discourse=batch["discourse"], prominence=batch["prominence"], speaker_ids=batch["speaker_ids"].to(dev),
                 gesture_labels=batch["gesture_labels"], text_times=batch["text_segments"])
