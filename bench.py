@@ -297,7 +297,8 @@ def run_b200(args, emit):
         e2e_vae = {"value": round(clip_steps * args.steps / tv, 2), "unit": UNIT, "ms_per_step": round(1e3 * tv / args.steps, 3),
                    "codec": "vae.GestureRepEncoder: 4 TransformerVAEs (latent 512, 4 heads, ff 1024, 4 layers -- sizes guessed, the "
                             "shipped YAMLs / checkpoints are not in the reference repo), encode of B clips + E exemplars and "
-                            "decode inside the timed region, PyTorch kernels",
+                            "decode inside the timed region; projections on the tcgen05 GEMM (bf16x3), attention rg_op_mha, "
+                            "the rest PyTorch kernels",
                    "api": "GuidedPipeline(model).run(batches)"}
         del arch_v, pipe_v
         torch.cuda.empty_cache()

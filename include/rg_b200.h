@@ -180,6 +180,19 @@ int rg_op_linear(const float* x, int ldx, const float* W, const float* b, const 
  * when split) may be NULL.  Used by the unit parity tests and bench.py's roofline probe. */
 int rg_op_linear_tc(const float* x, const float* W, const float* b, const float* residual, float* out,
                     void* out_bf16, int M, int N, int K, int epilogue, int split, void* stream);
+/* The codec's projections (gesture_vae.py / detr_utils.py nn.Linear and MultiheadAttention in/out projections, the
+ * callers either side of the path: SURVEY 8f.1) keep their weights converted: rg_op_split_bf16 writes W [rows, cols]
+ * as bf16 planes ([rows, cols], or [rows, 2*cols] = hi | lo when split) into out16 once, rg_op_linear_tc_w16 is
+ * rg_op_linear_tc with that buffer in place of W. */
+int rg_op_split_bf16(const float* w, void* out16, int rows, int cols, int split, void* stream);
+int rg_op_linear_tc_w16(const float* x, const void* w16, const float* b, const float* residual, float* out,
+                        void* out_bf16, int M, int N, int K, int epilogue, int split, void* stream);
+/* Softmax multi-head attention of those VAE blocks (torch nn.MultiheadAttention core between the projections):
+ * q [N, Sq, .] with rows ldq floats apart and head h in columns [h*dh, (h+1)*dh), k and v [N, Sk, .] likewise,
+ * keep [N, Sk] bytes (non-zero = the key is attended; key_padding_mask inverted) or NULL, out [N, Sq, H*dh].
+ * softmax(q k^T / sqrt(dh)) v in fp32; dh in {16, 32, 64, 128}; pointers 16-byte aligned, strides % 4 == 0. */
+int rg_op_mha(const float* q, const float* k, const float* v, const unsigned char* keep, float* out, int N, int Sq,
+              int Sk, int H, int dh, int64_t ldq, int64_t ldk, int64_t ldv, void* stream);
 /* Measurement probe for bench.py's roofline: converts operands once, then times `reps` launches of the
  * tcgen05 GEMM alone with CUDA events on `stream` (flush_buf, if given, is overwritten before every
  * launch to evict L2); *median_ms receives the median launch time.  Synchronises. */

@@ -41,6 +41,9 @@ SIGNATURES = {
     "rg_mix_branches": (_I, [_P, _P, _I, _P, _P, _P, _P]),
     "rg_op_linear": (_I, [_P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "rg_op_linear_tc": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "rg_op_split_bf16": (_I, [_P, _P, _I, _I, _I, _P]),
+    "rg_op_linear_tc_w16": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "rg_op_mha": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _L, _L, _L, _P]),
     "rg_probe_gemm_tc": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _L, C.POINTER(C.c_float), _P]),
     "rg_probe_gemm_only": (_I, [_P, _I]),
     "rg_probe_l2_read": (_I, [_P, _L, _I, C.POINTER(C.c_float), _P]),

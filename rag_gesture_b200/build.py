@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librg_b200.so")
-SOURCES = ["capi.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm2_tc.cu", "rowops.cu", "attention.cu", "knn.cu", "knn_tc.cu"]
+SOURCES = ["capi.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm2_tc.cu", "rowops.cu", "attention.cu", "mha.cu", "knn.cu", "knn_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden", "-cudart", "static"]
 

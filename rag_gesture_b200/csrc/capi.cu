@@ -1061,38 +1061,43 @@ extern "C" int rg_op_linear(const float* x, int ldx, const float* W, const float
     LAUNCH(rg_launch_gemm_f32(g, (cudaStream_t)stream));
     return 0;
 }
-extern "C" int rg_op_linear_tc(const float* x, const float* W, const float* b, const float* residual,
-                               float* out, void* out_bf16, int M, int N, int K, int epilogue, int split,
-                               void* stream) {
-    cudaStream_t st = (cudaStream_t)stream;
+// x W^T on the tensor cores; `w16_pre`: the weight already converted by rg_op_split_bf16 (planes as `split` says),
+// or NULL to convert W here.
+static int linear_tc_impl(const float* x, const float* W, const void* w16_pre, const float* b, const float* residual,
+                          float* out, void* out_bf16, int M, int N, int K, int epilogue, int split, cudaStream_t st,
+                          const char* who) {
     int epi;
     switch (epilogue) {
         case RG_OP_NONE: epi = RG_EPI_BIAS; break;
         case RG_OP_RESIDUAL: epi = RG_EPI_BIAS_RESIDUAL; break;
         case RG_OP_GELU: epi = RG_EPI_BIAS_GELU; break;
         case RG_OP_SILU: epi = RG_EPI_BIAS_SILU; break;
-        default: return rg_fail("rg_op_linear_tc: unknown epilogue %d", epilogue);
+        default: return rg_fail("%s: unknown epilogue %d", who, epilogue);
     }
-    if (N % 128 || K % 64) return rg_fail("rg_op_linear_tc: need N %% 128 == 0 and K %% 64 == 0 (got N=%d K=%d)", N, K);
-    if (epi == RG_EPI_BIAS_RESIDUAL && !residual) return rg_fail("rg_op_linear_tc: residual epilogue without residual");
+    if (N % 128 || K % 64) return rg_fail("%s: need N %% 128 == 0 and K %% 64 == 0 (got N=%d K=%d)", who, N, K);
+    if (epi == RG_EPI_BIAS_RESIDUAL && !residual) return rg_fail("%s: residual epilogue without residual", who);
+    if (M <= 0) return 0;
     const int planes = split ? 2 : 1;
     rg_keep_mempool();
     void *a16 = nullptr, *w16 = nullptr;
     CU(cudaMallocAsync(&a16, (size_t)M * K * planes * 2, st));
-    CU(cudaMallocAsync(&w16, (size_t)N * K * planes * 2, st));
     LAUNCH(rg_launch_split_bf16(x, K, a16, K * planes, split ? K : 0, M, K, st));
-    LAUNCH(rg_launch_split_bf16(W, K, w16, K * planes, split ? K : 0, N, K, st));
+    if (!w16_pre) {
+        CU(cudaMallocAsync(&w16, (size_t)N * K * planes * 2, st));
+        LAUNCH(rg_launch_split_bf16(W, K, w16, K * planes, split ? K : 0, N, K, st));
+    }
+    void* wp = w16_pre ? const_cast<void*>(w16_pre) : w16;
     CUtensorMap tmA, tmW;
     CU(rg_make_tensor_map(&tmA, a16, M, (long long)K * planes, (long long)K * planes, 128));
-    CU(rg_make_tensor_map(&tmW, w16, N, (long long)K * planes, (long long)K * planes, 128));
+    CU(rg_make_tensor_map(&tmW, wp, N, (long long)K * planes, (long long)K * planes, 128));
     RgGemmTc p;
     memset(&p, 0, sizeof(p));
     p.M = M; p.N = N; p.K = K; p.split = split ? 1 : 0; p.a_lo_off = K; p.w_lo_off = K; p.groups = 1;
     p.bias = b; p.R = residual; p.ldr = N; p.C32 = out; p.ldc32 = N;
     p.C16_ = out_bf16; p.ldc16 = N * planes; p.c16_lo_off = split ? N : 0; p.epi = epi;
-    p.no_pdl = 1;       // W planes were written by the split kernel just above
+    p.no_pdl = 1;       // the operand planes were written by the split kernel just above
     CUtensorMap ts32, ts16, tmW64;
-    CU(rg_make_tensor_map(&tmW64, w16, N, (long long)K * planes, (long long)K * planes, 64));
+    CU(rg_make_tensor_map(&tmW64, wp, N, (long long)K * planes, (long long)K * planes, 64));
     p.tmW64 = &tmW64;
     if (out && (reinterpret_cast<uintptr_t>(out) & 15) == 0) { CU(rg_make_store_map(&ts32, out, M, N, N, 4)); p.tmC32 = &ts32; }
     if (out_bf16 && (reinterpret_cast<uintptr_t>(out_bf16) & 15) == 0) {
@@ -1101,7 +1106,34 @@ extern "C" int rg_op_linear_tc(const float* x, const float* W, const float* b, c
     }
     LAUNCH(rg_launch_gemm_tc(tmA, tmW, p, st));
     CU(cudaFreeAsync(a16, st));
-    CU(cudaFreeAsync(w16, st));
+    if (w16) CU(cudaFreeAsync(w16, st));
+    return 0;
+}
+extern "C" int rg_op_linear_tc(const float* x, const float* W, const float* b, const float* residual,
+                               float* out, void* out_bf16, int M, int N, int K, int epilogue, int split,
+                               void* stream) {
+    return linear_tc_impl(x, W, nullptr, b, residual, out, out_bf16, M, N, K, epilogue, split, (cudaStream_t)stream,
+                          "rg_op_linear_tc");
+}
+extern "C" int rg_op_split_bf16(const float* w, void* out16, int rows, int cols, int split, void* stream) {
+    if (rows <= 0 || cols <= 0) return rg_fail("rg_op_split_bf16: bad shape %d x %d", rows, cols);
+    const int planes = split ? 2 : 1;
+    LAUNCH(rg_launch_split_bf16(w, cols, out16, cols * planes, split ? cols : 0, rows, cols, (cudaStream_t)stream));
+    return 0;
+}
+extern "C" int rg_op_linear_tc_w16(const float* x, const void* w16, const float* b, const float* residual,
+                                   float* out, void* out_bf16, int M, int N, int K, int epilogue, int split,
+                                   void* stream) {
+    if (!w16) return rg_fail("rg_op_linear_tc_w16: no weight planes");
+    return linear_tc_impl(x, nullptr, w16, b, residual, out, out_bf16, M, N, K, epilogue, split, (cudaStream_t)stream,
+                          "rg_op_linear_tc_w16");
+}
+extern "C" int rg_op_mha(const float* q, const float* k, const float* v, const unsigned char* keep, float* out,
+                         int N, int Sq, int Sk, int H, int dh, int64_t ldq, int64_t ldk, int64_t ldv, void* stream) {
+    if (dh != 16 && dh != 32 && dh != 64 && dh != 128) return rg_fail("rg_op_mha: head dim %d not in {16, 32, 64, 128}", dh);
+    if ((ldq | ldk | ldv) & 3) return rg_fail("rg_op_mha: row strides must be multiples of 4 floats");
+    if (((uintptr_t)q | (uintptr_t)k | (uintptr_t)v) & 15) return rg_fail("rg_op_mha: q, k, v must be 16-byte aligned");
+    LAUNCH(rg_launch_mha(q, k, v, keep, out, N, Sq, Sk, H, dh, ldq, ldk, ldv, 1.0f / sqrtf((float)dh), (cudaStream_t)stream));
     return 0;
 }
 extern "C" int rg_probe_gemm_tc(const float* x, const float* W, const float* b, float* out, int M, int N, int K,

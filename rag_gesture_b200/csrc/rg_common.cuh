@@ -105,6 +105,11 @@ cudaError_t rg_launch_kv_state(const float* kv, int ldkv, int k_off, int v_off, 
                                float* state, long long state_clip_stride, int B, int n_sets,
                                int kv_set_stride, long long state_set_stride, cudaStream_t st);
 
+// mha.cu
+cudaError_t rg_launch_mha(const float* q, const float* k, const float* v, const unsigned char* keep, float* out,
+                          int N, int Sq, int Sk, int H, int dh, long long ldq, long long ldk, long long ldv,
+                          float scale, cudaStream_t st);
+
 // ---- programmatic dependent launch (PDL) ----------------------------------------------------
 // Every kernel of the per-step chain is launched with programmaticStreamSerialization and starts with
 // rg_pdl_launch() (lets the NEXT kernel's CTAs be scheduled early) and rg_pdl_wait() (blocks until the

@@ -49,7 +49,10 @@ def axis_angle_to_matrix(aa):
     K = torch.stack([zero, -z, y, z, zero, -x, -y, x, zero], -1).reshape(aa.shape[:-1] + (3, 3))
     s, c = torch.sin(angle)[..., None], torch.cos(angle)[..., None]
     eye = torch.eye(3, dtype=aa.dtype, device=aa.device).expand(K.shape)
-    R = eye + s * K + (1 - c) * (K @ K)
+    # K @ K = a a^T - (a . a) I for the skew matrix of a; written out: a batched 3x3 matmul over every joint of
+    # every frame is a 260 us cuBLAS call where three elementwise kernels take 15
+    KK = axis[..., :, None] * axis[..., None, :] - (axis * axis).sum(-1)[..., None, None] * eye
+    R = eye + s * K + (1 - c) * KK
     return torch.where(small[..., None], eye, R)
 
 

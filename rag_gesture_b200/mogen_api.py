@@ -276,6 +276,8 @@ class ReGestureTransformer(nn.Module):
             from .codec import build_codec
             gesture_rep_encoder = build_codec(vae_cfg, body_part_cat_axis)
         self.gesture_rep_encoder = gesture_rep_encoder
+        if precision != _lib.PREC_FP32 and hasattr(gesture_rep_encoder, "set_gemm_tier"):
+            gesture_rep_encoder.set_gemm_tier("bf16x3")        # F1: the codec's GEMMs on the tensor cores too
         n_chunks = max_seq_len if gesture_rep_encoder is None else max_seq_len // frame_chunk_size
         self.max_seq_len = n_chunks
         if gesture_rep_encoder is None:

@@ -47,6 +47,52 @@ def linear_tc(x, weight, bias=None, residual=None, epilogue=_lib.OP_NONE, split=
     return (out, o16) if want_bf16 else out
 
 
+def split_bf16(weight, split):
+    """Weight [N, K] -> its bf16 planes ([N, K], or [N, 2K] = hi | lo when split) for linear_tc(w16=...)."""
+    (weight,) = _prep(weight)
+    N, K = weight.shape
+    out = torch.empty(N, K * (2 if split else 1), device=weight.device, dtype=torch.bfloat16)
+    with torch.cuda.device(weight.device):
+        _lib.check(_lib.load().rg_op_split_bf16(_lib.ptr(weight), _lib.ptr(out), N, K, int(split), _lib.stream_ptr()))
+    return out
+
+
+def linear_tc_w16(x, w16, n_out, bias=None, epilogue=_lib.OP_NONE, split=False):
+    """linear_tc with the weight already converted by split_bf16 (the codec keeps its weights that way)."""
+    x, bias = _prep(x, bias)
+    K = x.shape[-1]
+    M = x.numel() // K
+    assert w16.dtype == torch.bfloat16 and tuple(w16.shape) == (n_out, K * (2 if split else 1)) and w16.is_contiguous()
+    out = torch.empty(*x.shape[:-1], n_out, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().rg_op_linear_tc_w16(_lib.ptr(x), _lib.ptr(w16), _lib.ptr(bias), None, _lib.ptr(out), None,
+                                                   M, n_out, K, epilogue, int(split), _lib.stream_ptr()))
+    return out
+
+
+def mha(q, k, v, heads, keep=None):
+    """softmax(q k^T / sqrt(dh)) v per head.  q [N, Sq, D], k, v [N, Sk, D] fp32 CUDA tensors whose last dim is
+    contiguous (column slices of a fused projection are taken as they are, no copy); keep [N, Sk] bool or None."""
+    _lib.require_cuda(q, k, v)
+    N, Sq, D = q.shape
+    Sk = k.shape[1]
+
+    def rows(t, S):
+        if t.dtype != torch.float32 or t.stride(2) != 1 or t.stride(0) != S * t.stride(1) or t.stride(1) % 4 \
+                or t.data_ptr() % 16:
+            t = t.float().contiguous()
+        return t, t.stride(1)
+    (q, ldq), (k, ldk), (v, ldv) = rows(q, Sq), rows(k, Sk), rows(v, Sk)
+    if keep is not None:
+        keep = keep.to(torch.bool).contiguous()
+        assert tuple(keep.shape) == (N, Sk)
+    out = torch.empty(N, Sq, D, device=q.device)
+    with torch.cuda.device(q.device):
+        _lib.check(_lib.load().rg_op_mha(q.data_ptr(), k.data_ptr(), v.data_ptr(), _lib.ptr(keep), _lib.ptr(out), N, Sq, Sk,
+                                         heads, D // heads, ldq, ldk, ldv, _lib.stream_ptr()))
+    return out
+
+
 def set_gemm_kernel(mode=0, min_rows=0, persist_tiles=0, pair128_min_rows=0):
     """rg_set_gemm_kernel: 0 automatic, 1 the 128x128 one-tile-per-CTA kernel, 2 the 2-CTA 256x256 kernel whenever
     the shape allows (N % 256 == 0; persist_tiles: pair-tile count from which its persistent variant runs), 3 the

@@ -35,6 +35,31 @@ def _activation(name):
     raise ValueError(f"transformer_activation must be relu or gelu, not {name!r}")
 
 
+def _lin(owner, x, W, b, act=None):
+    """y = act(x W^T + b).  On the device, with a GEMM tier set on `owner` (GestureRepEncoder.set_gemm_tier) and a
+    shape the tcgen05 kernel takes (N % 128 == 0, K % 64 == 0: every projection of the blocks; not the feature
+    embedding / final layer, whose nfeats side is ~100 wide), the library's tensor-core GEMM with its fused
+    bias / GELU epilogue: "bf16x3" (hi|lo operand split, three passes, fp32-class results) or "bf16".  Otherwise
+    cuBLAS fp32 through F.linear, which on this part runs on the FP32 pipes at a tenth of the rate."""
+    tier = getattr(owner, "_rg_tier", None)
+    if tier is not None and x.is_cuda and x.dtype == torch.float32 and W.shape[0] % 128 == 0 and W.shape[1] % 64 == 0:
+        from . import _lib, ops
+        split = tier == "bf16x3"
+        # the weight's bf16 planes are converted once and kept on the module that owns the projection, keyed by the
+        # row block of the parameter and checked against its storage and in-place version counter
+        cache = owner.__dict__.setdefault("_rg_w16", {})
+        key, stamp = (W.storage_offset(), W.shape[0], split), (W.data_ptr(), W._version)
+        hit = cache.get(key)
+        if hit is None or hit[0] != stamp:
+            hit = cache[key] = (stamp, ops.split_bf16(W, split))
+            torch.cuda.current_stream(x.device).synchronize()      # once per weight: other streams (the pipeline's
+                                                                   # worker / main thread) read the planes later
+        y = ops.linear_tc_w16(x, hit[1], W.shape[0], b, epilogue=_lib.OP_GELU if act is F.gelu else _lib.OP_NONE, split=split)
+        return y if act is None or act is F.gelu else act(y)
+    y = F.linear(x, W, b)
+    return y if act is None else act(y)
+
+
 class _LearnedPositions(nn.Module):
     """`pe` [max_len, 1, D] as in detr_utils.py:60-79; applied batch-first here."""
 
@@ -70,12 +95,27 @@ def _mha(container, q_in, k_in, v_in, keep):
     D, H = container.embed_dim, container.num_heads
     W, b = container.in_proj_weight, container.in_proj_bias
     N, Sq, Sk = q_in.shape[0], q_in.shape[1], k_in.shape[1]
-    q = F.linear(q_in, W[:D], b[:D]).view(N, Sq, H, D // H).transpose(1, 2)
-    k = F.linear(k_in, W[D:2 * D], b[D:2 * D]).view(N, Sk, H, D // H).transpose(1, 2)
-    v = F.linear(v_in, W[2 * D:], b[2 * D:]).view(N, Sk, H, D // H).transpose(1, 2)
-    mask = None if keep is None else keep[:, None, None, :]
-    o = F.scaled_dot_product_attention(q, k, v, attn_mask=mask)
-    return container.out_proj(o.transpose(1, 2).reshape(N, Sq, D))
+    # projections that share their input are one GEMM over the stacked weight rows
+    if q_in is k_in and k_in is v_in:
+        q, k, v = _lin(container, q_in, W, b).split(D, dim=-1)
+    elif q_in is k_in:
+        q, k = _lin(container, q_in, W[:2 * D], b[:2 * D]).split(D, dim=-1)
+        v = _lin(container, v_in, W[2 * D:], b[2 * D:])
+    elif k_in is v_in:
+        q = _lin(container, q_in, W[:D], b[:D])
+        k, v = _lin(container, k_in, W[D:], b[D:]).split(D, dim=-1)
+    else:
+        q, k, v = (_lin(container, t, W[i * D:(i + 1) * D], b[i * D:(i + 1) * D]) for i, t in enumerate((q_in, k_in, v_in)))
+    if getattr(container, "_rg_tier", None) is not None and q.is_cuda and D // H in (16, 32, 64, 128):
+        from . import ops
+        o = ops.mha(q, k, v, H, keep)                      # strided column blocks of the fused projection, no copies
+    else:
+        q = q.view(N, Sq, H, D // H).transpose(1, 2)
+        k = k.view(N, Sk, H, D // H).transpose(1, 2)
+        v = v.view(N, Sk, H, D // H).transpose(1, 2)
+        mask = None if keep is None else keep[:, None, None, :]
+        o = F.scaled_dot_product_attention(q, k, v, attn_mask=mask).transpose(1, 2).reshape(N, Sq, D)
+    return _lin(container, o, container.out_proj.weight, container.out_proj.bias)
 
 
 class _SelfBlock(nn.Module):
@@ -93,10 +133,14 @@ class _SelfBlock(nn.Module):
             y = self.norm1(x)
             qk = y if pos is None else y + pos
             x = x + _mha(self.self_attn, qk, qk, y, keep)
-            return x + self.linear2(self.act(self.linear1(self.norm2(x))))
+            return x + self._ffn(self.norm2(x))
         qk = x if pos is None else x + pos
         x = self.norm1(x + _mha(self.self_attn, qk, qk, x, keep))
-        return self.norm2(x + self.linear2(self.act(self.linear1(x))))
+        return self.norm2(x + self._ffn(x))
+
+    def _ffn(self, x):
+        return _lin(self, _lin(self, x, self.linear1.weight, self.linear1.bias, self.act), self.linear2.weight,
+                    self.linear2.bias)
 
 
 class _CrossBlock(nn.Module):
@@ -115,10 +159,12 @@ class _CrossBlock(nn.Module):
             y = self.norm1(x)
             x = x + _mha(self.self_attn, y, y, y, keep)
             x = x + _mha(self.multihead_attn, self.norm2(x), memory, memory, None)
-            return x + self.linear2(self.act(self.linear1(self.norm3(x))))
+            return x + self._ffn(self.norm3(x))
         x = self.norm1(x + _mha(self.self_attn, x, x, x, keep))
         x = self.norm2(x + _mha(self.multihead_attn, x, memory, memory, None))
-        return self.norm3(x + self.linear2(self.act(self.linear1(x))))
+        return self.norm3(x + self._ffn(x))
+
+    _ffn = _SelfBlock._ffn
 
 
 class _SkipStack(nn.Module):
@@ -144,7 +190,7 @@ class _SkipStack(nn.Module):
             kept.append(x)
         x = self.middle_block(x, **kw)
         for blk, lin in zip(self.output_blocks, self.linear_blocks):
-            x = blk(lin(torch.cat([x, kept.pop()], dim=-1)), **kw)
+            x = blk(_lin(self, torch.cat([x, kept.pop()], dim=-1), lin.weight, lin.bias), **kw)
         return self.norm(x)
 
 
@@ -261,6 +307,18 @@ class GestureRepEncoder(nn.Module):
             setattr(self, f"{part}_latproj", nn.Identity())
         self.uj = self.lj = self.hj = self.fj = None
         self.tj = 3
+
+    GEMM_TIERS = (None, "bf16x3", "bf16")
+
+    def set_gemm_tier(self, tier):
+        """None: every projection through F.linear (cuBLAS fp32).  "bf16x3" / "bf16": the 512/1024-wide projections
+        of the four VAEs through the library's tcgen05 GEMM (see _lin); ReGestureTransformer sets "bf16x3" when its
+        own precision tier is a tensor-core one, so the codec's results stay fp32-class in every tier."""
+        assert tier in self.GEMM_TIERS, tier
+        self.gemm_tier = tier
+        for m in self.modules():
+            m._rg_tier = tier
+        return self
 
     @staticmethod
     def load_vae(cfg_path):

@@ -39,6 +39,40 @@ def test_vae_device_matches_host(mg):
         assert rel_l2(zd.cpu(), z) < 1e-4 and rel_l2(recd.cpu(), rec) < 1e-4, name
 
 
+def test_vae_tensor_core_tiers_match_fp32(mg, tmp_path):
+    """F1: the four VAEs with their 512/1024-wide projections on the library's tcgen05 GEMM (set_gemm_tier) against
+    the same codec on cuBLAS fp32 -- same inputs, same Gaussian draws.  bf16x3 is held to the fp32 tier's tolerance,
+    bf16 to north_star's 2e-2; the golden-pinned CPU path is what the fp32 one is held to above."""
+    from rag_gesture_b200 import _lib
+    dev = torch.device("cuda:0")
+
+    def shapes_of(args):
+        return {k: tuple(v.shape) for k, v in TransformerVAE(args).state_dict().items()}
+    for variant in ("a", "b"):
+        cfg = mg.write_vae_files(os.path.join(str(tmp_path), variant), variant, 200, shapes_of, latent_dim=C.LATENT_DIM)
+        enc = GestureRepEncoder(cfg, "time").to(dev).eval()
+        inp = {k: v.to(dev) for k, v in mg.codec_inputs(5, 31).items()}
+        outs = {}
+        for tier in (None, "bf16x3", "bf16"):
+            enc.set_gemm_tier(tier)
+            enc.generator = torch.Generator(device=dev).manual_seed(77)
+            n0 = _lib.load().rg_launch_count()
+            motion, mask = enc.encode(**{k: v.clone() for k, v in inp.items()})
+            many, _ = enc.encode_many(**{k: v.clone() for k, v in inp.items()})
+            dec = enc.decode(motion)
+            n = C.N_CHUNKS
+            with torch.no_grad():                               # 6D rotations straight from the part decoders: the
+                raw = (enc.upper_vae.decode(motion[:, :n]),     # axis-angle outputs jump at pi (compared below only
+                       enc.hands_vae.decode(motion[:, n + 1:2 * n + 1]))     # through their linear companions)
+            outs[tier] = (motion, many, dec[4], dec[5], dec[6]) + raw
+            assert (_lib.load().rg_launch_count() > n0) == (tier is not None)       # the tcgen05 GEMM did (not) run
+        enc.generator = None
+        for tier, tol in (("bf16x3", 1e-4), ("bf16", 2e-2)):
+            errs = [rel_l2(a, b) for a, b in zip(outs[tier], outs[None])]
+            print(f"VAE variant {variant}, GEMM tier {tier}: max rel-L2 vs fp32 {max(errs):.3g}")
+            assert max(errs) < tol, (variant, tier, errs)
+
+
 def test_forward_with_transformer_vae_codec(mg, tmp_path):
     """build_architecture with the reference-style vae_cfg (four YAML + checkpoint pairs): encode -> plain DDIM
     on the CUDA path -> decode; deterministic under fixed seeds, finite, reference output shapes."""

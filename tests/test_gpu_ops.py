@@ -275,3 +275,35 @@ def test_fused_attention_stylization_tc(dev, T):
             got = ops.cross_attention_tc(q3, state, qm, gamma, beta, ss, split)
             assert rel_l2(got[keep], ref[keep]) < tol
             assert torch.isfinite(got).all()
+
+
+@pytest.mark.parametrize("N,Sq,Sk,H,dh", [(640, 17, 17, 4, 128), (64, 160, 160, 4, 128), (7, 150, 10, 4, 128),
+                                           (5, 33, 65, 8, 64), (3, 1, 200, 2, 32), (9, 40, 40, 16, 32),
+                                           (64, 160, 160, 32, 16), (3, 45, 71, 4, 16)])
+def test_mha_vs_torch_fp64(dev, N, Sq, Sk, H, dh):
+    """rg_op_mha (the codec VAEs' softmax attention) against float64 softmax(q k^T / sqrt(dh)) v, with a key-padding
+    mask, for q/k/v given as strided column blocks of one fused projection and as separate tensors."""
+    from rag_gesture_b200 import ops
+    g = torch.Generator().manual_seed(N * 1000 + Sq)
+    D = H * dh
+    keep = torch.rand(N, Sk, generator=g) > 0.3
+    keep[:, 0] = True                                    # no fully masked row (the VAE's global tokens are always kept)
+
+    def ref(q, k, v, keep):
+        qh, kh, vh = (t.double().view(N, -1, H, dh).transpose(1, 2) for t in (q, k, v))
+        s = qh @ kh.transpose(-1, -2) / dh ** 0.5
+        if keep is not None:
+            s = s.masked_fill(~keep[:, None, None, :], float("-inf"))
+        return (s.softmax(-1) @ vh).transpose(1, 2).reshape(N, -1, D)
+    if Sq == Sk:
+        qkv = torch.randn(N, Sq, 3 * D, generator=g).to(dev)
+        q, k, v = qkv.split(D, dim=-1)                   # views with row stride 3D
+    else:
+        q = torch.randn(N, Sq, D, generator=g).to(dev)
+        kv = torch.randn(N, Sk, 2 * D, generator=g).to(dev)
+        k, v = kv.split(D, dim=-1)
+    for kp in (keep.to(dev), None):
+        got = ops.mha(q, k, v, H, kp)
+        want = ref(q.cpu(), k.cpu(), v.cpu(), None if kp is None else keep)
+        assert tuple(got.shape) == (N, Sq, D)
+        assert rel_l2(got.cpu().double(), want) < 2e-6, (N, Sq, Sk, H, dh, kp is None)
