@@ -400,12 +400,15 @@ class GuidedPipeline:
         for results in GuidedPipeline(model).run(loader): ...
     """
 
-    def __init__(self, arch):
+    def __init__(self, arch, side_priority=0):
         self.arch = arch
         self.device = arch.model.out.weight.device
         if self.device.type != "cuda":
             raise RuntimeError("rg_b200: GuidedPipeline needs the model on a CUDA device (no CPU fallback)")
-        self.side = torch.cuda.Stream(self.device)
+        # Stage 1's kernels (codec, text-similarity ranks, exemplar gathers) share the GPU with the loops.  A
+        # high-priority side stream (-1) was measured and is WORSE (tools/diag_e2e.py 16 -1: 121 ms per batch against
+        # 87 at priority 0, with 150-300 ms stalls in the stage's host-to-device copies), so the default stays 0.
+        self.side = torch.cuda.Stream(self.device, priority=side_priority)
         # The main thread re-acquires the GIL after every blocking call; while the worker runs Python it may
         # wait one switch interval each time (default 5 ms).  The loops are one C call per pass
         # (rg_run_levels), so a moderate interval is enough; very short ones (50 us) make both threads thrash.

@@ -14,6 +14,7 @@ from rag_gesture_b200 import _lib, config as C, synthetic as S  # noqa: E402
 from rag_gesture_b200.architecture import GuidedPipeline  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+prio = int(sys.argv[2]) if len(sys.argv) > 2 else -1
 dev = torch.device("cuda:0")
 cfg = C.model_cfg()
 cfg["use_retrieval_for_test"] = True
@@ -23,7 +24,8 @@ arch.model.load_state_dict(S.synthetic_state_dict(0), strict=False)
 arch = arch.to(dev).eval()
 batch = bench.make_batch(0, bench.B_PER_GPU)
 db = arch.model.database
-T = {"stage1": [], "wait": [], "cond": [], "pass": [], "finish": []}
+T = {"stage1": [], "  h2d": [], "  encode": [], "  retrieve": [], "  db.forward": [], "  precond": [], "wait": [],
+     "cond": [], "pass": [], "finish": []}
 
 
 def timed(name, fn):
@@ -35,7 +37,14 @@ def timed(name, fn):
     return w
 
 
-pipe = GuidedPipeline(arch)
+pipe = GuidedPipeline(arch, side_priority=prio)
+print("side stream priority", prio)
+arch._scatter = timed("  h2d", arch._scatter)
+codec = arch.model.gesture_rep_encoder
+codec.encode = timed("  encode", codec.encode)
+db.retrieve_many = timed("  retrieve", db.retrieve_many)
+db.forward = timed("  db.forward", db.forward)
+arch.model.get_precompute_condition = timed("  precond", arch.model.get_precompute_condition)
 pipe._stage1 = timed("stage1", pipe._stage1)
 arch.encode_clip_conditions = timed("cond", arch.encode_clip_conditions)
 arch.run_pass = timed("pass", arch.run_pass)
@@ -65,5 +74,5 @@ torch.cuda.synchronize()
 tot = time.perf_counter() - t0
 print(f"{n} batches in {tot * 1e3:.1f} ms host / {a.elapsed_time(b):.1f} ms device = {tot / n * 1e3:.1f} ms per batch")
 for k, v in T.items():
-    print(f"  {k:7s} n={len(v):2d}  mean {1e3 * sum(v) / max(1, len(v)):7.2f} ms   " + " ".join(f"{1e3 * x:6.1f}" for x in v[:10]))
+    print(f"  {k:12s} n={len(v):2d}  mean {1e3 * sum(v) / max(1, len(v)):7.2f} ms   " + " ".join(f"{1e3 * x:6.1f}" for x in v[:10]))
 print("  yields at (ms): " + " ".join(f"{1e3 * m:.0f}" for m in marks))
