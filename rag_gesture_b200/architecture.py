@@ -85,18 +85,21 @@ class MotionDiffusion(nn.Module):
         if self.training:
             raise NotImplementedError("rg_b200 is inference-only; call model.eval()")
         kwargs = self._scatter(kwargs)
-        motion_mask = kwargs["motion_mask"].float()
         codec = self.model.gesture_rep_encoder
-        with torch.no_grad():
-            motion, motion_mask = codec.encode(kwargs["motion_upper"], kwargs["motion_lower"],
-                                               kwargs["motion_face"], kwargs["motion_hands"], kwargs["trans"],
-                                               kwargs["facial"], kwargs["contact"], motion_mask)
-        B, T = motion.shape[:2]
-        device = motion.device
-        # cross-attention is skipped on rows {(T-3)//4 * k}: NOT the separator rows (SURVEY 8 quirk 1)
-        qmask = torch.ones_like(motion_mask)
-        qmask[:, [(T - 3) // 4, 2 * (T - 3) // 4, 3 * (T - 3) // 4]] = 0
-        query_masks = {c: qmask for c in CFG.CONDS}
+        enc_args = (kwargs["motion_upper"], kwargs["motion_lower"], kwargs["motion_face"], kwargs["motion_hands"],
+                    kwargs["trans"], kwargs["facial"], kwargs["contact"], kwargs["motion_mask"].float())
+        device = enc_args[0].device
+        # The reference encodes the clips first and retrieves afterwards (diffusion_architecture.py:230-262).  A codec
+        # that hands out its Gaussian draws (vae.GestureRepEncoder.draw_encode_eps) gets them taken HERE, at that place
+        # in the random stream, and runs its passes AFTER the retrieval stage: the stage's host-side waits (speaker
+        # ids, text-similarity ranks) then queue behind the input copies only, not behind the clips' encode pass on a
+        # GPU that is busy with the previous batch's loops.  Same values, different order on the stream.
+        late_eps = None
+        if hasattr(codec, "draw_encode_eps") and device.type == "cuda":
+            late_eps = codec.draw_encode_eps(enc_args[0])
+        else:
+            with torch.no_grad():
+                motion, motion_mask = codec.encode(*enc_args)
 
         ik = kwargs.get("inference_kwargs", {})
         gb = GuidedBatch()
@@ -120,14 +123,22 @@ class MotionDiffusion(nn.Module):
         if self.inference_type != "ddim":
             raise NotImplementedError("rg_b200 implements inference_type='ddim' only")
 
-        kwargs.update({"motion_mask": motion_mask, "text": kwargs["word"], "raw_text": kwargs["raw_word"],
-                       "text_times": kwargs["text_segments"]})
+        kwargs.update({"text": kwargs["word"], "raw_text": kwargs["raw_word"], "text_times": kwargs["text_segments"]})
         with torch.no_grad():
             if defer_conditions:
                 model_kwargs = self.model.get_precompute_condition(device=device, xf_out={}, **kwargs)
                 gb.cond_inputs = (kwargs["text"], kwargs["audio"], kwargs["speaker_ids"])
             else:
                 model_kwargs = self.model.get_precompute_condition(device=device, **kwargs)
+            if late_eps is not None:
+                motion, motion_mask = codec.encode(*enc_args, eps=late_eps)
+        kwargs["motion_mask"] = motion_mask
+        B, T = motion.shape[:2]
+        # cross-attention is skipped on rows {(T-3)//4 * k}: NOT the separator rows (SURVEY 8 quirk 1)
+        qmask = torch.ones_like(motion_mask)
+        for col in ((T - 3) // 4, 2 * (T - 3) // 4, 3 * (T - 3) // 4):     # one column at a time: a list index would be
+            qmask[:, col] = 0                                              # uploaded with a blocking pageable copy
+        query_masks = {c: qmask for c in CFG.CONDS}
         model_kwargs["query_mask"] = query_masks
         model_kwargs["motion_mask"] = motion_mask
         model_kwargs["sample_idx"] = kwargs.get("sample_idx", None)
@@ -150,7 +161,10 @@ class MotionDiffusion(nn.Module):
                 cat = lambda key: torch.cat([lat[b][q][key] for b, q in gb.jobs], 0).to(device)
                 gb.ex = {k: cat(k) for k in ("retr_text", "retr_audio", "retr_spkid", "retr_motion_mask",
                                              "retr_motion_latent")}
-                clip_of = torch.tensor([b for b, _ in gb.jobs], device=device)
+                clip_of = torch.tensor([b for b, _ in gb.jobs])
+                if device.type == "cuda":              # pinned + asynchronous: a pageable upload would block the host
+                    clip_of = clip_of.pin_memory()     # behind the encode passes enqueued above
+                clip_of = clip_of.to(device, non_blocking=True)
                 gb.ex_query_mask = {c: m[clip_of] for c, m in query_masks.items()}
                 gb.windows = [(retrieval_dict["retr_startends"][b][q], retrieval_dict["query_startends"][b][q])
                               for b, q in gb.jobs]
@@ -400,7 +414,7 @@ class GuidedPipeline:
         for results in GuidedPipeline(model).run(loader): ...
     """
 
-    def __init__(self, arch, side_priority=0):
+    def __init__(self, arch, side_priority=0, codec_graphs=None):
         self.arch = arch
         self.device = arch.model.out.weight.device
         if self.device.type != "cuda":
@@ -409,6 +423,11 @@ class GuidedPipeline:
         # high-priority side stream (-1) was measured and is WORSE (tools/diag_e2e.py 16 -1: 121 ms per batch against
         # 87 at priority 0, with 150-300 ms stalls in the stage's host-to-device copies), so the default stays 0.
         self.side = torch.cuda.Stream(self.device, priority=side_priority)
+        # A codec that can replay its passes as CUDA graphs (vae.GestureRepEncoder.enable_graphs) does so inside run():
+        # by default whenever its GEMMs are on the tensor-core path, where the passes are bound by the host's eager
+        # launches; the fp32 tier keeps the eager passes (bit-equal to sequential forward() calls).
+        codec = arch.model.gesture_rep_encoder
+        self.codec_graphs = (getattr(codec, "gemm_tier", None) is not None) if codec_graphs is None else bool(codec_graphs)
         # The main thread re-acquires the GIL after every blocking call; while the worker runs Python it may
         # wait one switch interval each time (default 5 ms).  The loops are one C call per pass
         # (rg_run_levels), so a moderate interval is enough; very short ones (50 us) make both threads thrash.
@@ -447,12 +466,17 @@ class GuidedPipeline:
         own_gen = getattr(codec, "draws_on_device", False) and getattr(codec, "generator", None) is None
         if own_gen:
             codec.generator = self.codec_generator(self.device)
+        graphs_were = getattr(codec, "use_graphs", None)
+        if self.codec_graphs and graphs_were is False:
+            codec.use_graphs = True                 # captured passes are kept on the codec between runs
         try:
             yield from self._run(it, first, main)
         finally:
             sys.setswitchinterval(old_interval)
             if own_gen:
                 codec.generator = None
+            if graphs_were is not None:
+                codec.use_graphs = graphs_were
 
     def _run(self, it, first, main):
         from concurrent.futures import ThreadPoolExecutor

@@ -729,7 +729,7 @@ class RetrievalDatabase(nn.Module):
             keys = self.EXEMPLAR_KEYS
             corpus = self.exemplar_corpus(device) if torch.device(device).type == "cuda" else None
             if corpus is not None:
-                rows = torch.tensor([self._corpus_rows[name] for _, _, name in jobs], device=device)
+                rows = torch.tensor([self._corpus_rows[name] for _, _, name in jobs]).pin_memory().to(device, non_blocking=True)
                 ex = {k: corpus[k].index_select(0, rows) for k in keys}
             else:
                 smps = [self.dataset[name] for _, _, name in jobs]
@@ -781,9 +781,12 @@ class RetrievalDatabase(nn.Module):
         src_mask = (motions != 0).any(dim=-1).to(torch.int)
         raw_latent_mask = src_mask.clone()
         raw_latents = motions.clone()
-        dead = list(range(2 * n + 2, 3 * n + 2)) + list(range(3 * n + 3, T))     # face + lower/transl rows
-        src_mask[:, dead] = 0
-        raw_latents[:, dead, :] = 0
+        # face + lower/transl rows.  As slices: indexing with a Python list uploads an index tensor from pageable
+        # memory, a blocking copy that makes the host wait for everything this stage has enqueued (the exemplars'
+        # encode pass) on a GPU shared with the previous batch's loops -- 60 ms of the stage with the VAE codec
+        for lo, hi in ((2 * n + 2, 3 * n + 2), (3 * n + 3, T)):
+            src_mask[:, lo:hi] = 0
+            raw_latents[:, lo:hi, :] = 0
         R = self.num_retrieval
         return dict(
             re_text=None, re_motion=None, re_mask=src_mask,

@@ -46,11 +46,13 @@ def _lin(owner, x, W, b, act=None):
         from . import _lib, ops
         split = tier == "bf16x3"
         # the weight's bf16 planes are converted once and kept on the module that owns the projection, keyed by the
-        # row block of the parameter and checked against its storage and in-place version counter
+        # row block's address and checked against the parameter's in-place version counter
         cache = owner.__dict__.setdefault("_rg_w16", {})
-        key, stamp = (W.storage_offset(), W.shape[0], split), (W.data_ptr(), W._version)
+        key, stamp = (W.data_ptr(), W.shape[0], split), W._version
         hit = cache.get(key)
         if hit is None or hit[0] != stamp:
+            if len(cache) >= 16:                           # parameters moved (.to(), new storage): drop the old planes
+                cache.clear()
             hit = cache[key] = (stamp, ops.split_bf16(W, split))
             torch.cuda.current_stream(x.device).synchronize()      # once per weight: other streams (the pipeline's
                                                                    # worker / main thread) read the planes later
@@ -287,12 +289,42 @@ def _to_aa(d6, joints):
     return matrix_to_axis_angle(rotation_6d_to_matrix(d6.reshape(B, n, joints, 6))).reshape(B, n, joints * 3)
 
 
+class _CapturedPass:
+    """One codec pass (fixed shapes) as a CUDA graph: static inputs -> static outputs.  The pass is ~700 eager
+    launches (torch ops + library calls through ctypes) whose enqueue time, not their device time, bounds it once
+    the GEMMs are on the tensor cores; replayed, it is one launch."""
+
+    def __init__(self, fn, tensors):
+        import threading
+        self.lock = threading.Lock()
+        self.static_in = [t.clone() for t in tensors]
+        fn(*[t.clone() for t in self.static_in])          # eager once: weight-plane caches, cuBLAS workspaces
+        torch.cuda.current_stream().synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        # own capture stream (torch's default one is shared between threads: the pipeline's worker captures encode
+        # passes while the main thread may capture a decode pass) and thread-local error mode (the other thread keeps
+        # allocating and launching meanwhile)
+        with torch.cuda.graph(self.graph, stream=torch.cuda.Stream(tensors[0].device), capture_error_mode="thread_local"):
+            out = fn(*self.static_in)
+        self.static_out = list(out) if isinstance(out, (tuple, list)) else [out]
+
+    def __call__(self, tensors):
+        with self.lock:
+            for s_, t in zip(self.static_in, tensors):
+                s_.copy_(t)
+            self.graph.replay()
+            return [o.clone() for o in self.static_out]
+
+
 class GestureRepEncoder(nn.Module):
     """diffusion_transformer.py:130-330: SMPL-X axis-angle body parts <-> [B, 4*n_chunks+3, D] latents with zero
     separator tokens (body_part_cat_axis="time") or concatenated along features (otherwise)."""
     PARTS = ("upper", "hands", "face", "lowertrans")      # order of the sampling draws in encode
     draws_on_device = True      # rsample noise comes from a CUDA generator: `generator` (None = the default one)
     generator = None
+    gemm_tier = None            # set_gemm_tier()
+    use_graphs = False          # enable_graphs(): encode / encode_many / decode passes replayed as CUDA graphs
+    EXEMPLAR_BUCKET = 16        # encode_many pads its batch to a multiple of this under graphs (one graph per bucket)
 
     def __init__(self, vae_cfg, body_part_cat_axis="time", vaes=None):
         super().__init__()
@@ -307,6 +339,31 @@ class GestureRepEncoder(nn.Module):
             setattr(self, f"{part}_latproj", nn.Identity())
         self.uj = self.lj = self.hj = self.fj = None
         self.tj = 3
+
+    def enable_graphs(self, on=True):
+        """Replay the codec's passes as CUDA graphs (CUDA tensors, inference only).  Results are those of the eager
+        pass: the Gaussian draws are made outside the graph in the eager order, and a change of any parameter
+        (storage or in-place version) or of the GEMM tier drops the captured passes."""
+        self.use_graphs = bool(on)
+        self.__dict__["_rg_graphs"] = {}
+        return self
+
+    def _run(self, kind, fn, tensors):
+        if not (self.use_graphs and all(t.is_cuda for t in tensors)):
+            return fn(*tensors)
+        stamp = hash((getattr(self, "gemm_tier", None),) + tuple((p.data_ptr(), p._version) for p in self.parameters()))
+        graphs = self.__dict__.setdefault("_rg_graphs", {})
+        if graphs.get("stamp") != stamp:
+            graphs.clear()
+            graphs["stamp"] = stamp
+        key = (kind,) + tuple((tuple(t.shape), t.dtype) for t in tensors)
+        if key not in graphs:
+            if len(graphs) > 12:                         # a few batch sizes + exemplar buckets; not a leak
+                for k in [k for k in graphs if k != "stamp"][:4]:
+                    del graphs[k]
+            graphs[key] = _CapturedPass(fn, tensors)
+        out = graphs[key](tensors)
+        return out if len(out) > 1 else out[0]
 
     GEMM_TIERS = (None, "bf16x3", "bf16")
 
@@ -364,18 +421,38 @@ class GestureRepEncoder(nn.Module):
         sep = torch.zeros_like(z["upper"][:, :, :1])
         return torch.cat([z["upper"], sep, z["hands"], sep, z["face"], sep, z["lowertrans"]], dim=-1), m
 
-    @torch.no_grad()
-    def encode(self, motion_upper, motion_lower, motion_face, motion_hands, motion_transl, motion_facial,
-               motion_contact, motion_mask):
+    def _encode_core(self, motion_upper, motion_lower, motion_face, motion_hands, motion_transl, motion_facial,
+                     motion_contact, motion_mask, eps):
+        """eps [4, B*n_chunks, 1, D]: the rsample draw of each part (order PARTS)."""
         feats = self._features(motion_upper, motion_lower, motion_face, motion_hands, motion_transl, motion_facial,
                                motion_contact)
+        z = {p: getattr(self, f"{p}_vae").encode_to_dist(feats[p], eps=eps[i])[0] for i, p in enumerate(self.PARTS)}
+        motion, mask = self._assemble(z, motion_mask)
+        return motion, mask, motion_transl               # the translation is re-based in place, as the reference does
+
+    def _encode(self, inputs, eps):
+        motion, mask, transl = self._run("encode", self._encode_core, list(inputs) + [eps])
+        if transl.data_ptr() != inputs[4].data_ptr():    # replayed pass: hand the in-place edit back to the caller
+            inputs[4].copy_(transl)
+        return motion, mask
+
+    def draw_encode_eps(self, motion_upper):
+        """The Gaussian draws encode() makes for this batch ([4, B*n_chunks, 1, D], part order upper, hands, face,
+        lowertrans as in the reference: one Normal(...).rsample() per part).  A caller that wants the draws at
+        encode's place in the random stream but the encode itself later (MotionDiffusion.prepare) takes them here
+        and passes them back as encode(..., eps=...)."""
+        B, n = motion_upper.shape[0], motion_upper.shape[1] // self.frame_chunk_size
         gen = getattr(self, "generator", None)
-        z = {}
-        for p in self.PARTS:                     # draw order upper, hands, face, lowertrans as in the reference
-            mu_shape = (feats[p].shape[0] * (feats[p].shape[1] // self.frame_chunk_size), 1, self.vae_latent_dim)
-            eps = torch.empty(mu_shape, device=feats[p].device).normal_(generator=gen) if gen is not None else None
-            z[p] = getattr(self, f"{p}_vae").encode_to_dist(feats[p], eps=eps)[0]
-        return self._assemble(z, motion_mask)
+        return torch.stack([torch.empty(B * n, 1, self.vae_latent_dim, device=motion_upper.device).normal_(generator=gen)
+                            for _ in self.PARTS], 0)
+
+    @torch.no_grad()
+    def encode(self, motion_upper, motion_lower, motion_face, motion_hands, motion_transl, motion_facial,
+               motion_contact, motion_mask, eps=None):
+        if eps is None:
+            eps = self.draw_encode_eps(motion_upper)
+        return self._encode((motion_upper, motion_lower, motion_face, motion_hands, motion_transl, motion_facial,
+                             motion_contact, motion_mask), eps)
 
     @torch.no_grad()
     def encode_many(self, motion_upper, motion_lower, motion_face, motion_hands, motion_transl, motion_facial,
@@ -383,19 +460,33 @@ class GestureRepEncoder(nn.Module):
         """E exemplars in one pass through each VAE.  The Gaussian draws are made exemplar by exemplar, part by
         part, i.e. the sequence E separate encode() calls at B=1 consume (diffusion_architecture / raggesture.py:580
         encode one exemplar at a time)."""
-        feats = self._features(motion_upper, motion_lower, motion_face, motion_hands, motion_transl, motion_facial,
-                               motion_contact)
         E, n = motion_upper.shape[0], motion_upper.shape[1] // self.frame_chunk_size
         dev, D = motion_upper.device, self.vae_latent_dim
         gen = getattr(self, "generator", None)
         eps = torch.stack([torch.stack([torch.empty(n, 1, D, device=dev).normal_(generator=gen) for _ in self.PARTS], 0)
                            for _ in range(E)], 0)                        # [E, 4, n, 1, D]
-        z = {p: getattr(self, f"{p}_vae").encode_to_dist(feats[p], eps=eps[:, i].reshape(E * n, 1, D))[0]
-             for i, p in enumerate(self.PARTS)}
-        return self._assemble(z, motion_mask)
+        eps = eps.transpose(0, 1).reshape(len(self.PARTS), E * n, 1, D)
+        inputs = (motion_upper, motion_lower, motion_face, motion_hands, motion_transl, motion_facial, motion_contact,
+                  motion_mask)
+        pad = (-E) % self.EXEMPLAR_BUCKET if self.use_graphs and motion_upper.is_cuda else 0
+        if pad == 0:
+            return self._encode(inputs, eps)
+        # one captured pass per bucket of exemplar counts: zero rows appended, their outputs dropped
+        grow = lambda t, rows: torch.cat([t, t.new_zeros((rows,) + tuple(t.shape[1:]))], 0)
+        padded = tuple(grow(t, pad) for t in inputs)
+        eps_p = torch.cat([eps, eps.new_zeros(len(self.PARTS), pad * n, 1, D)], 1)
+        motion, mask = self._encode(padded, eps_p)
+        motion_transl.copy_(padded[4][:E])
+        return motion[:E], mask[:E]
 
     @torch.no_grad()
     def decode(self, z_output):
+        if self.uj is None:
+            raise RuntimeError("GestureRepEncoder.decode before any encode: joint counts are recorded by encode "
+                               "(diffusion_transformer.py:196-243), as in the reference")
+        return tuple(self._run("decode", self._decode_core, [z_output]))
+
+    def _decode_core(self, z_output):
         n = z_output.shape[1]
         if self.body_part_cat_axis == "time":
             n = (n - 3) // 4
@@ -407,9 +498,6 @@ class GestureRepEncoder(nn.Module):
             zu, zh = z_output[..., :d], z_output[..., d + 1:2 * d + 1]
             zf, zl = z_output[..., 2 * d + 2:3 * d + 2], z_output[..., 3 * d + 3:]
             assert zu.shape[2] == self.vae_latent_dim == zh.shape[2] == zf.shape[2] == zl.shape[2]
-        if self.uj is None:
-            raise RuntimeError("GestureRepEncoder.decode before any encode: joint counts are recorded by encode "
-                               "(diffusion_transformer.py:196-243), as in the reference")
         assert self.tj == 3
         upper = _to_aa(self.upper_vae.decode(zu), self.uj)
         hands = _to_aa(self.hands_vae.decode(zh), self.hj)

@@ -73,6 +73,53 @@ def test_vae_tensor_core_tiers_match_fp32(mg, tmp_path):
             assert max(errs) < tol, (variant, tier, errs)
 
 
+def test_codec_graph_replay_equals_eager(mg, tmp_path):
+    """enable_graphs(): encode / encode_many (padded to the exemplar bucket) / decode replayed as CUDA graphs give the
+    eager pass's results for the same generator state, across replays with different inputs, in the cuBLAS tier and
+    in the tensor-core tier (library calls with stream-ordered allocations inside the capture); a weight update drops
+    the captured passes."""
+    dev = torch.device("cuda:0")
+
+    def shapes_of(args):
+        return {k: tuple(v.shape) for k, v in TransformerVAE(args).state_dict().items()}
+    cfg = mg.write_vae_files(str(tmp_path), "a", 200, shapes_of, latent_dim=C.LATENT_DIM)
+    enc = GestureRepEncoder(cfg, "time").to(dev).eval()
+    for tier in (None, "bf16x3"):
+        enc.set_gemm_tier(tier)
+        enc.enable_graphs(True)
+        for rnd in range(3):                                # round 0 captures, 1 and 2 replay with other inputs
+            clips = {k: v.to(dev) for k, v in mg.codec_inputs(4, 50 + rnd).items()}
+            ex = {k: v.to(dev) for k, v in mg.codec_inputs(5, 60 + rnd).items()}
+            res = {}
+            for graphs in (False, True):
+                enc.use_graphs = graphs
+                enc.generator = torch.Generator(device=dev).manual_seed(5 + rnd)
+                a = {k: v.clone() for k, v in clips.items()}
+                b = {k: v.clone() for k, v in ex.items()}
+                motion, mask = enc.encode(**a)
+                many, mmask = enc.encode_many(**b)
+                dec = enc.decode(motion)
+                res[graphs] = (motion, mask, many, mmask, a["motion_transl"], b["motion_transl"], dec[4], dec[5], dec[6])
+            for i, (x, y) in enumerate(zip(res[False], res[True])):
+                assert x.shape == y.shape, (tier, rnd, i)
+                assert torch.allclose(x, y, rtol=1e-5, atol=1e-5), (tier, rnd, i, float((x - y).abs().max()))
+        n_graphs = len([k for k in enc.__dict__["_rg_graphs"] if k != "stamp"])
+        assert n_graphs == 3, n_graphs                      # encode B=4, encode 16 (5 padded), decode B=4
+        with torch.no_grad():
+            enc.face_vae.final_layer.bias.add_(1.0)        # in-place update: version bump -> passes re-captured
+        a = {k: v.clone() for k, v in clips.items()}
+        enc.generator = torch.Generator(device=dev).manual_seed(9)
+        enc.use_graphs = True
+        m_g = enc.encode(**a)[0]
+        d_g = enc.decode(m_g)
+        enc.use_graphs = False
+        d_e = enc.decode(m_g)
+        assert torch.allclose(d_g[5], d_e[5], atol=1e-5) and torch.allclose(d_g[4], d_e[4], atol=1e-5)
+        with torch.no_grad():
+            enc.face_vae.final_layer.bias.sub_(1.0)
+    enc.generator = None
+
+
 def test_forward_with_transformer_vae_codec(mg, tmp_path):
     """build_architecture with the reference-style vae_cfg (four YAML + checkpoint pairs): encode -> plain DDIM
     on the CUDA path -> decode; deterministic under fixed seeds, finite, reference output shapes."""
@@ -109,11 +156,15 @@ def test_forward_with_transformer_vae_codec(mg, tmp_path):
         assert torch.equal(a[k], b[k]), k
 
 
-def test_pipeline_with_vae_codec_is_reproducible_and_matches_sequential(mg, tmp_path):
+@pytest.mark.parametrize("tier", ["fp32", "bf16x3"])
+def test_pipeline_with_vae_codec_is_reproducible_and_matches_sequential(mg, tmp_path, tier):
     """the VAE codec draws its rsample noise on the device.  GuidedPipeline gives it its own generator, so
     (a) two pipeline runs with the same seeds agree bit for bit (no dependence on thread timing) and (b) they equal
-    sequential forward() calls made with the same codec generator installed."""
+    sequential forward() calls made with the same codec generator installed.  In the tensor-core tier the pipeline
+    replays the codec's passes as CUDA graphs (worker thread: encode, main thread: decode) while forward() runs them
+    eagerly: (b) then holds to rounding of the few cuBLAS calls left in the passes."""
     import rag_gesture_b200 as R
+    from rag_gesture_b200 import _lib
     from rag_gesture_b200.architecture import GuidedPipeline
     dev = torch.device("cuda:0")
 
@@ -121,11 +172,13 @@ def test_pipeline_with_vae_codec_is_reproducible_and_matches_sequential(mg, tmp_
         return {k: tuple(v.shape) for k, v in TransformerVAE(args).state_dict().items()}
     cfg = C.model_cfg()
     cfg["model"]["vae_cfg"] = mg.write_vae_files(str(tmp_path), "a", 300, shapes_of, latent_dim=C.LATENT_DIM)
+    cfg["model"]["precision"] = {"fp32": _lib.PREC_FP32, "bf16x3": _lib.PREC_BF16X3}[tier]
     arch = R.build_architecture(cfg, database=None)
     arch.model.load_state_dict(S.synthetic_state_dict(0), strict=False)
     arch = arch.to(dev).eval()
     codec = arch.model.gesture_rep_encoder
     assert codec.draws_on_device and codec.generator is None
+    assert codec.gemm_tier == (None if tier == "fp32" else "bf16x3") and GuidedPipeline(arch).codec_graphs == (tier != "fp32")
     qs = S.SyntheticGestureDataset(8, seed=8)
 
     def batches():
@@ -142,7 +195,7 @@ def test_pipeline_with_vae_codec_is_reproducible_and_matches_sequential(mg, tmp_
     for _ in range(2):
         seed()
         runs.append([r["prev_latentout"].cpu() for r in GuidedPipeline(arch).run(batches())])
-        assert codec.generator is None                      # restored after run()
+        assert codec.generator is None and codec.use_graphs is False      # restored after run()
     assert all(torch.equal(a, b) for a, b in zip(*runs))
     seed()
     codec.generator = GuidedPipeline.codec_generator(dev)
@@ -150,4 +203,9 @@ def test_pipeline_with_vae_codec_is_reproducible_and_matches_sequential(mg, tmp_
         seq = [arch(**b)["prev_latentout"].cpu() for b in batches()]
     finally:
         codec.generator = None
-    assert len(seq) == 3 and all(torch.equal(a, b) for a, b in zip(seq, runs[0]))
+    assert len(seq) == 3
+    if tier == "fp32":
+        assert all(torch.equal(a, b) for a, b in zip(seq, runs[0]))
+    else:
+        assert len([k for k in codec.__dict__["_rg_graphs"] if k != "stamp"]) == 6       # encode + decode at B = 2, 1, 3
+        assert max(rel_l2(a, b) for a, b in zip(seq, runs[0])) < 1e-4

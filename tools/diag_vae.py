@@ -34,8 +34,9 @@ def step():
     return enc.decode(m)
 
 
-for tier in (None, "bf16x3", "bf16"):
+for tier, graphs in ((None, False), ("bf16x3", False), ("bf16", False), ("bf16x3", True), (None, True)):
     enc.set_gemm_tier(tier)
+    enc.enable_graphs(graphs)
     for _ in range(3):
         step()
     torch.cuda.synchronize()
@@ -48,8 +49,8 @@ for tier in (None, "bf16x3", "bf16"):
     b.record()
     host = (time.perf_counter() - t0) / 5
     torch.cuda.synchronize()
-    print(f"tier {tier}: device {a.elapsed_time(b) / 5:.2f} ms per step, host enqueue {1e3 * host:.2f} ms")
-    if tier in (None, "bf16x3"):
+    print(f"tier {tier} graphs {graphs}: device {a.elapsed_time(b) / 5:.2f} ms per step, host enqueue {1e3 * host:.2f} ms")
+    if tier == "bf16x3" and not graphs:
         from torch.profiler import ProfilerActivity, profile
         with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
             step()
