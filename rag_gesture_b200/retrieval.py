@@ -75,39 +75,45 @@ class TextSimilarityIndex:
             db[i, :f.shape[0]] = f
         self.db = db.to(self.device)
         self.len = torch.tensor([f.shape[0] for f in feats], dtype=torch.int32, device=self.device)
+        self._arange = torch.arange(len(feats) + 64, dtype=torch.int64, device=self.device)
 
-    def scores(self, query, rows=None):
-        """score[j] = mean(diag(Q D_j^T)) over min(Tq, Td) aligned tokens (rag/utils.py:107-118)."""
+    def scores(self, query, rows=None, out=None):
+        """score[j] = mean(diag(Q D_j^T)) over min(Tq, Td) aligned tokens (rag/utils.py:107-118).  rows: list of DB
+        row indices or an int32 device tensor of them; out: optional fp32 device buffer to write into."""
         lib = _lib.load()
         q = query.to(device=self.device, dtype=torch.float32).contiguous()
         sub = None if rows is None else torch.as_tensor(rows, dtype=torch.int32, device=self.device)
         n_out = len(self.names) if sub is None else sub.numel()
-        out = torch.empty(n_out, device=self.device)
+        if out is None:
+            out = torch.empty(n_out, device=self.device)
+        assert out.numel() == n_out and out.dtype == torch.float32 and out.is_contiguous()
         with torch.cuda.device(self.device):
             _lib.check(lib.rg_text_similarity(_lib.ptr(self.db), _lib.ptr(self.len), len(self.names),
                                               self.max_len, self.dim, _lib.ptr(q), q.shape[0],
                                               _lib.ptr(sub), n_out, _lib.ptr(out), _lib.stream_ptr()))
         return out
 
-    def _rank_launch(self, query, rows, k):
+    def _rank_launch(self, query, rows, k, dev_rows=None):
         """Enqueue the two kernels that rank `rows` against `query` (no synchronisation): -> device int64 [32]
-        holding positions into `rows` in rank order."""
+        holding positions into `rows` in rank order.  dev_rows: the same row indices already on the device (int32)."""
         k = min(k, len(rows))
-        sc = self.scores(query, rows).view(1, 1, -1)
         lib = _lib.load()
-        # top-k of one candidate list == merge of ceil(n/32) "parts" of 32 candidates
-        n = sc.shape[-1]
+        # top-k of one candidate list == merge of ceil(n/32) "parts" of 32 candidates; the tail of the last part
+        # scores -inf (never among the first k <= n).  The scores are written straight into the padded buffer and
+        # the positions are a slice of one arange made with the index.
+        n = len(rows)
         pad = (-n) % 32
-        idx = torch.arange(n + pad, dtype=torch.int64, device=self.device)
-        if pad:
-            sc = torch.cat([sc.view(-1), torch.full((pad,), float("-inf"), device=self.device)])
-            idx[n:] = -1
+        sc = torch.full((n + pad,), float("-inf"), device=self.device) if pad else torch.empty(n, device=self.device)
+        self.scores(query, rows if dev_rows is None else dev_rows, out=sc[:n])
+        if n + pad > self._arange.numel():
+            self._arange = torch.arange(2 * (n + pad), dtype=torch.int64, device=self.device)
+        idx = self._arange[:n + pad]
         parts = (n + pad) // 32
         out_i = torch.empty(32, dtype=torch.int64, device=self.device)
         out_s = torch.empty(32, device=self.device)
         with torch.cuda.device(self.device):
-            _lib.check(lib.rg_knn_merge(_lib.ptr(idx.contiguous()), _lib.ptr(sc.contiguous().view(-1)),
-                                        parts, 1, 32, _lib.ptr(out_i), _lib.ptr(out_s), _lib.stream_ptr()))
+            _lib.check(lib.rg_knn_merge(_lib.ptr(idx), _lib.ptr(sc), parts, 1, 32, _lib.ptr(out_i), _lib.ptr(out_s),
+                                        _lib.stream_ptr()))
         return out_i, k
 
     def rank(self, query, rows, k):
@@ -119,17 +125,26 @@ class TextSimilarityIndex:
         return [rows[j] for j in out_i[:k].tolist()]
 
     def rank_many(self, requests):
-        """[(query, rows, k), ...] -> [ranked rows, ...]: every request's kernels are enqueued first, then ONE
-        device-to-host copy and synchronisation serves all of them (a batch of clips asks ~80 times; one round trip
-        each was a third of the host time of the retrieval stage)."""
-        launched = [None if not rows else self._rank_launch(q, rows, k) for q, rows, k in requests]
-        live = [x for x in launched if x is not None]
+        """[(query, rows, k), ...] -> [ranked rows, ...]: the row lists of all requests go up in ONE pinned,
+        asynchronous copy, every request's kernels are enqueued, then ONE device-to-host copy and synchronisation
+        serves all of them (a batch of clips asks ~80 times; one round trip and one blocking upload each was a
+        third of the host time of the retrieval stage)."""
+        live = [i for i, (_, rows, _) in enumerate(requests) if rows]
         if not live:
             return [[] for _ in requests]
-        host = torch.stack([o for o, _ in live], 0).cpu().tolist()
+        flat = torch.tensor([r for i in live for r in requests[i][1]], dtype=torch.int32)
+        if self.device.type == "cuda":
+            flat = flat.pin_memory()
+        flat = flat.to(self.device, non_blocking=True)
+        launched, off = {}, 0
+        for i in live:
+            q, rows, k = requests[i]
+            launched[i] = self._rank_launch(q, rows, k, flat[off:off + len(rows)])
+            off += len(rows)
+        host = torch.stack([launched[i][0] for i in live], 0).cpu().tolist()
         out, it = [], iter(host)
-        for (q, rows, _), l in zip(requests, launched):
-            out.append([] if l is None else [rows[j] for j in next(it)[:l[1]]])
+        for i, (q, rows, _) in enumerate(requests):
+            out.append([rows[j] for j in next(it)[:launched[i][1]]] if i in launched else [])
         return out
 
 
@@ -416,42 +431,52 @@ class SenseTable:
         self.e_conn = np.array(e_conn, dtype=np.int64)
         self.e_prom = np.array(e_prom, dtype=np.float64)
         self.max_len = int(self.seg_len.max()) if len(names) else 0
+        # everything that does not depend on the query, per k = "the k-th entry with this sense of every sample that
+        # has one": the rows, their connective ids and entry indices, and the subset with a prominence value
+        self.first_idx = self.e_idx[self.seg_start] if len(names) else np.zeros(0, dtype=np.int64)
+        self.cnt = np.zeros(len(names), dtype=np.int64)
+        self.steps = []
+        for k in range(self.max_len):
+            rows = np.flatnonzero(self.seg_len > k)
+            pos = self.seg_start[rows] + k
+            pr = self.e_prom[pos]
+            ok = ~np.isnan(pr)
+            self.cnt[rows[ok]] += 1
+            self.steps.append((rows, self.e_conn[pos], self.e_idx[pos], rows[ok], pr[ok], self.e_idx[pos][ok]))
+        self.withp = self.cnt > 0
 
     def score(self, conn_id, speaker_id, q_prom):
         """-> (score float64 [n], top entry index int64 [n]) for the query connective."""
         import numpy as np
         n = len(self.names)
         score = np.full(n, 2.0)
-        top = self.e_idx[self.seg_start].copy()            # first entry with the sense
+        top = self.first_idx.copy()                        # first entry with the sense
         chosen = np.zeros(n, dtype=bool)
-        acc = np.zeros(n)
-        cnt = np.zeros(n, dtype=np.int64)
-        best_d = np.full(n, np.inf)
-        best_j = np.full(n, -1, dtype=np.int64)
-        for k in range(self.max_len):                      # k-th relevant entry of every sample
-            has = self.seg_len > k
-            pos = self.seg_start[has] + k
-            hit = has.copy()
-            hit[has] = (self.e_conn[pos] == conn_id) if conn_id is not None else False
-            first = hit & ~chosen                          # list.index(): the first matching entry wins
-            top[first] = self.e_idx[self.seg_start[first] + k]
-            chosen |= hit
-            if q_prom is not None:
-                pr = self.e_prom[pos]
-                ok = ~np.isnan(pr)
-                rows = np.flatnonzero(has)[ok]
-                d = np.abs(pr[ok] - q_prom)
-                acc[rows] = acc[rows] + 4 / (1 + 2 * d)
-                cnt[rows] += 1
-                better = d < best_d[rows]                  # stable sorted(...)[0]: first minimum wins
-                best_d[rows[better]] = d[better]
-                best_j[rows[better]] = self.e_idx[pos[ok]][better]
+        if conn_id is not None:
+            for rows, conn, eidx, _, _, _ in self.steps:   # k-th relevant entry of every sample
+                m = conn == conn_id
+                if m.any():
+                    hit = rows[m]
+                    new = ~chosen[hit]                     # list.index(): the first matching entry wins
+                    top[hit[new]] = eidx[m][new]
+                    chosen[hit] = True
         score[chosen] += 4
         score[self.spk == speaker_id] += 3
-        withp = cnt > 0
-        score[withp] = score[withp] + acc[withp] / cnt[withp]
-        move = withp & ~chosen & (best_j != top)
-        top[move] = best_j[move]
+        if q_prom is not None:
+            acc = np.zeros(n)
+            best_d = np.full(n, np.inf)
+            best_j = np.full(n, -1, dtype=np.int64)
+            for _, _, _, rows, pr, eidx in self.steps:     # entry by entry, in the reference's order of additions
+                d = np.abs(pr - q_prom)
+                acc[rows] = acc[rows] + 4 / (1 + 2 * d)
+                better = d < best_d[rows]                  # stable sorted(...)[0]: first minimum wins
+                rb = rows[better]
+                best_d[rb] = d[better]
+                best_j[rb] = eidx[better]
+            withp = self.withp
+            score[withp] = score[withp] + acc[withp] / self.cnt[withp]
+            move = withp & ~chosen & (best_j != top)
+            top[move] = best_j[move]
         return score, top
 
 
