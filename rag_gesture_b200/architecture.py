@@ -409,7 +409,9 @@ class GuidedPipeline:
     gets its own device generator (`codec.generator`, seeded from torch.cuda.initial_seed() unless the caller
     installed one).  Results are then reproducible run to run, and equal to sequential forward() calls made with
     the same `codec.generator` installed -- but NOT to sequential calls that draw codec and sampler noise from
-    the one default generator, as the reference does.
+    the one default generator, as the reference does.  In the tensor-core tiers the codec's passes are replayed as
+    CUDA graphs inside run() (`codec_graphs`): still bit-reproducible run to run, and equal to the eager sequential
+    calls up to the rounding of the few cuBLAS calls left in those passes (tests/test_gpu_codec.py).
 
         for results in GuidedPipeline(model).run(loader): ...
     """
