@@ -96,3 +96,27 @@ def test_gesture_rep_encoder_vs_reference(gold, mg, tmp_path):
     torch.manual_seed(42)
     many, _ = enc.encode_many(**{k: v.clone() for k, v in inp.items()})
     assert rel_l2(many, torch.from_numpy(gold["enc_single"])) < TOL
+
+
+def test_encode_with_predrawn_noise_equals_encode(mg, tmp_path):
+    """MotionDiffusion.prepare takes the codec's Gaussian draws first (draw_encode_eps, at encode's place in the random
+    stream) and runs the encode pass after the retrieval stage: encode(eps=draw) must be encode() for the same
+    generator state, with the default generator and with an installed one, and leave the stream where encode() does."""
+    def shapes_of(args):
+        return {k: tuple(v.shape) for k, v in TransformerVAE(args).state_dict().items()}
+    enc = GestureRepEncoder(mg.write_vae_files(str(tmp_path), "b", 200, shapes_of), "time").eval()
+    inp = mg.codec_inputs(3, 77)
+    torch.manual_seed(11)
+    a, am = enc.encode(**{k: v.clone() for k, v in inp.items()})
+    after_a = torch.rand(1)
+    torch.manual_seed(11)
+    eps = enc.draw_encode_eps(inp["motion_upper"])
+    after_b = torch.rand(1)                              # something else draws between the two halves
+    b, bm = enc.encode(**{k: v.clone() for k, v in inp.items()}, eps=eps)
+    assert torch.equal(a, b) and torch.equal(am, bm) and torch.equal(after_a, after_b)
+    enc.generator = torch.Generator().manual_seed(5)
+    c, _ = enc.encode(**{k: v.clone() for k, v in inp.items()})
+    enc.generator = torch.Generator().manual_seed(5)
+    d, _ = enc.encode(**{k: v.clone() for k, v in inp.items()}, eps=enc.draw_encode_eps(inp["motion_upper"]))
+    enc.generator = None
+    assert torch.equal(c, d) and not torch.equal(a, c)
